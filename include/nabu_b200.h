@@ -1,0 +1,162 @@
+/* nabu_b200 -- C-ABI of the B200-native engine for nabu's per-utterance hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain C: device pointers + sizes, no torch / C++ types;
+ *   - every array is fp32 (lengths / labels / ids int32), row-major, batch-major, DEVICE memory
+ *     unless the parameter is documented "host";
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *     nothing synchronises, allocates or frees: the caller owns every buffer, including the
+ *     scratch sized by the matching *_workspace_bytes();
+ *   - return 0 on success, non-zero on error with a message in nabu_last_error();
+ *   - there is no CPU fallback: without a sm_100a device every call fails.
+ *
+ * "Replaces" names the reference interface (vrenkens/nabu @ 39deb62, paths under
+ * nabu/neuralnetworks/) whose arithmetic the entry point performs.
+ */
+#ifndef NABU_B200_H_
+#define NABU_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* nabu_last_error(void);
+int nabu_version(void);
+
+/* ---- dense contraction (building block; exported for tests) ------------------------------------
+ * mode 0: C[M,N] = alpha*A[M,K].B[K,N]   + beta*C + bias[N]
+ * mode 1: C[M,N] = alpha*A[M,K].B[N,K]^T + beta*C + bias[N]
+ * mode 2: C[M,N] = alpha*A[K,M]^T.B[K,N] + beta*C + bias[N]
+ * precision 0: fp32 FFMA (bit-reproducible); 1: tcgen05 3xTF32 split (fp32-grade, tensor cores).
+ * Replaces: the tf.matmul inside every TF cell / layer the hot path touches. */
+size_t nabu_gemm_workspace_bytes(void);
+int nabu_gemm(int mode, int precision, int M, int N, int K, float alpha, const float* A, int lda,
+              const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+              void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a1: BLSTM layer ----------------------------------------------------------------------------
+ * Replaces components/layer.py:8-51 `blstm` (LayerNormBasicLSTMCell(layer_norm=False) under
+ * bidirectional_dynamic_rnn, sequence_length=len).
+ *   x [B,T,D]; len [B]; kernel_{fw,bw} [(D+H),4H] (rows: input then hidden; columns i,j,f,o);
+ *   bias_{fw,bw} [4H];  y [B,yT,2H] (fw | bw), rows t>=len[b] and t in [T,yT) are zero -- yT>T
+ *   lets the caller get the zero padding ops.pyramid_stack (components/ops.py:30-38) adds.
+ *   gates [2,B,T,4H] and cells [2,B,T,H] are saved activations for nabu_blstm_bwd. */
+size_t nabu_blstm_workspace_bytes(int B, int T, int D, int H);
+int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int D, int H,
+                   const float* kernel_fw, const float* bias_fw,
+                   const float* kernel_bw, const float* bias_bw,
+                   float* y, int yT, float* gates, float* cells,
+                   void* workspace, size_t ws_bytes, void* stream);
+/* dy [B,yT,2H].  gates is overwritten (it becomes dZ).  dx may be NULL (first layer). */
+int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int D, int H,
+                   const float* kernel_fw, const float* kernel_bw,
+                   const float* y, int yT, float* gates, const float* cells, const float* dy,
+                   float* dx, float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
+                   void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a2: pyramid_stack lengths -------------------------------------------------------------------
+ * Replaces components/ops.py:55-58: out[b] = ceil(len[b] / numsteps).  (The data movement of
+ * pyramid_stack is a free reshape of the yT-padded BLSTM output.) */
+int nabu_pyramid_lengths(const int* len, int B, int numsteps, int* out, void* stream);
+
+/* ---- a5: output layer ----------------------------------------------------------------------------
+ * Replaces models/ed_decoders/dnn_decoder.py:53-57 (tf.contrib.layers.linear): y[N,V]=x[N,D].W+b. */
+int nabu_linear_fwd(const float* x, int N, int D, int V, const float* W, const float* b, float* y,
+                    void* workspace, size_t ws_bytes, void* stream);
+int nabu_linear_bwd(const float* x, int N, int D, int V, const float* W, const float* dy,
+                    float* dx, float* dW, float* db, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a9: CTC loss --------------------------------------------------------------------------------
+ * Replaces trainers/loss_functions.py:203-210 (tf.nn.ctc_loss, time_major=False, defaults): softmax
+ * over V inside, blank = V-1.  loss[b] = -log p(labels_b | logits_b); grad [B,T,V] = grad_scale *
+ * d loss[b] / d logits (zero for t >= logit_len[b]).  Infeasible utterances get loss = +inf. */
+size_t nabu_ctc_workspace_bytes(int B, int T, int V, int Lmax);
+int nabu_ctc_loss_fwd_bwd(const float* logits, const int* logit_len, const int* labels, int Lmax,
+                          const int* label_len, int B, int T, int V, float grad_scale,
+                          float* loss, float* grad, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a10: masked cross-entropy ---------------------------------------------------------------------
+ * Replaces trainers/loss_functions.py:78-109,155-165 (average_cross_entropy): per utterance
+ * sum_{u<logit_len} -log softmax(logits[b,u])[targets[b,u]] / target_len[b].  loss [B];
+ * grad [B,U,V] = grad_scale * d loss[b] / d logits. */
+int nabu_masked_ce_fwd_bwd(const float* logits, const int* targets, int ldt, const int* logit_len,
+                           const int* target_len, int B, int U, int V, float grad_scale,
+                           float* loss, float* grad, void* stream);
+
+/* ---- a11: update ---------------------------------------------------------------------------------
+ * Replaces trainers/trainer.py:556-569: g = clip_by_value(g,-clip,clip); tf.train.AdamOptimizer step
+ * `t` (>=1): m,v update; theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).  Flat buffers [n].
+ * grad_scale multiplies g before the clip (1/world for an averaged all-reduce; 1 otherwise). */
+int nabu_clip_adam_step(float* theta, const float* grad, float* m, float* v, size_t n, float lr,
+                        int t, float beta1, float beta2, float eps, float clip, float grad_scale,
+                        void* stream);
+
+/* ---- a6-a8: Speller (attention decoder), whole teacher-forced sequence ---------------------------
+ * Replaces models/ed_decoders/rnn_decoder.py:40-82 + speller.py:29-69 + components/rnn_cell.py:
+ * 145-155 + components/attention.py:142-240 with sample_prob=0 (teacher forcing).
+ * Filled in by nabu_speller_desc_t below. */
+typedef struct {
+  int B, Tm, E;            /* memory [B,Tm,E], mem_len [B] */
+  int V, H, num_layers;    /* output classes (incl. EOS/SOS = V-1), LSTM units, layers (<=4) */
+  int A;                   /* attention units (= H in the reference) */
+  int attention;           /* 0 vanilla Bahdanau, 1 location_aware */
+  int numfilt, filtersize; /* location_aware only */
+  int U;                   /* decoder steps = max target length */
+} nabu_speller_desc_t;
+
+/* Parameter pack (device pointers).  Same field order for the gradient pack. */
+typedef struct {
+  float* cell_kernel[4];   /* layer 0: [(V+E+H),4H]; layer l>0: [(H+H),4H] */
+  float* cell_bias[4];     /* [4H] */
+  float* memory_kernel;    /* [E,A]  (memory_layer, no bias) */
+  float* query_kernel;     /* [H,A]  (query_layer, no bias) */
+  float* attention_v;      /* [A] */
+  float* conv_kernel;      /* [filtersize,1,numfilt] or NULL */
+  float* conv_dense_kernel;/* [numfilt,A] or NULL (process_conv_features) */
+  float* out_kernel;       /* [(H+E),V] */
+  float* out_bias;         /* [V] */
+} nabu_speller_params_t;
+
+size_t nabu_speller_workspace_bytes(const nabu_speller_desc_t* d);
+size_t nabu_speller_saved_bytes(const nabu_speller_desc_t* d);
+/* targets [B,ldt] int32 (no SOS; the entry point prepends V-1), target_len [B].
+ * logits [B,U,V] (zero rows for u >= target_len[b]); saved = activations for the backward. */
+int nabu_speller_fwd(const nabu_speller_desc_t* d, const nabu_speller_params_t* p,
+                     const float* memory, const int* mem_len, const int* targets, int ldt,
+                     const int* target_len, float* logits, void* saved,
+                     void* workspace, size_t ws_bytes, void* stream);
+int nabu_speller_bwd(const nabu_speller_desc_t* d, const nabu_speller_params_t* p,
+                     const float* memory, const int* mem_len, const int* targets, int ldt,
+                     const int* target_len, const float* dlogits, void* saved,
+                     float* dmemory, const nabu_speller_params_t* grads,
+                     void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a13: LAS beam search -------------------------------------------------------------------------
+ * Replaces decoders/beam_search_decoder.py:30-112 + components/beam_search_decoder.py:136-485
+ * (initialize / step / finalize under dynamic_decode(maximum_iterations=max_steps)).
+ * memory [B,Tm,E] un-tiled.  Outputs: sequences [B,W,max_steps] int32 (only the first *n_steps
+ * columns are meaningful), lengths [B,W] int32, scores [B,W], alignments [B,W,max_steps,Tm].
+ * n_steps: host int, written after a stream synchronise inside the call (the loop length is
+ * data dependent: the reference stops when every beam slot has held EOS once). */
+size_t nabu_las_beam_workspace_bytes(const nabu_speller_desc_t* d, int W, int max_steps);
+int nabu_las_beam_search(const nabu_speller_desc_t* d, const nabu_speller_params_t* p,
+                         const float* memory, const int* mem_len, int W, int max_steps,
+                         float length_penalty, float temperature,
+                         int* sequences, int* lengths, float* scores, float* alignments,
+                         int* n_steps, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a12: CTC prefix beam search ------------------------------------------------------------------
+ * Replaces decoders/ctc_decoder.py:57-59 (tf.nn.ctc_beam_search_decoder: beam_width=100,
+ * top_paths=1, merge_repeated=True).  logits [B,T,V] batch-major raw scores, blank = V-1.
+ * out_ids [B,T] int32 (best path per utterance), out_len [B]. */
+size_t nabu_ctc_beam_workspace_bytes(int B, int T, int V, int beam_width);
+int nabu_ctc_beam_search(const float* logits, const int* logit_len, int B, int T, int V,
+                         int beam_width, int merge_repeated, int* out_ids, int* out_len,
+                         float* out_neg_logprob, void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NABU_B200_H_ */

@@ -1,0 +1,608 @@
+// Persistent bidirectional-LSTM recurrence for sm_100a (replaces
+// nabu/neuralnetworks/components/layer.py:8-51 = LayerNormBasicLSTMCell(layer_norm=False)
+// under bidirectional_dynamic_rnn).
+//
+// Layer forward  = input projection  Gx[d] = X.Kx[d] + b[d]   (one dense GEMM per direction,
+//                  all T at once -- the reference re-does this contraction every time step)
+//                + ONE cooperative kernel that walks the T serial steps of BOTH directions:
+//                  every CTA owns `HS` hidden units (4*HS gate columns) of one direction, keeps
+//                  that slice of the recurrent matrix Kh resident in shared memory for the whole
+//                  sequence, and per step multiplies the previous hidden state (streamed through
+//                  a 3-stage cp.async ring from a [H][B] exchange buffer in L2) against it.
+//                  CTAs of one direction hand h_t to each other through that buffer and a
+//                  monotonic release/acquire counter -- no grid-wide barrier, and the two
+//                  directions never wait for each other.
+// Layer backward = the mirrored cooperative kernel (dz_t exchanged instead of h_t, Kh^T slice
+//                  resident) followed by the three batched GEMMs dKx = X^T.dZ, dKh = Hprev^T.dZ,
+//                  dX = dZ.Kx^T.
+//
+// Semantics restated from TF-1.8: gate order i,j,f,o; forget bias +1.0 at
+// run time; zero initial state; outputs are 0 and state is frozen for t >= len[b]; the backward
+// direction visits t = len[b]-1-s at step s.
+#include "common.cuh"
+#include "gemm.h"
+#include "nabu_b200.h"
+
+namespace nabu {
+namespace {
+
+constexpr int RNN_THREADS = 256;
+constexpr int KC = 64;        // rows of the exchanged operand per pipeline stage
+constexpr int STAGES = 3;
+
+struct RecParams {
+  const float* kernel[2];   // [(D+H), 4H] per direction
+  float* gates[2];          // [B, T, 4H]  fwd: in = Gx, out = activated i,g,f,o ; bwd: in = gates, out = dZ
+  float* cells[2];          // [B, T, H]
+  float* y;                 // fwd: output [B, yT, 2H]
+  const float* dy;          // bwd: [B, yT, 2H]
+  float* dbias[2];          // bwd: [4H]
+  float* xchg;              // exchange buffer [2 dir][2 parity][R][Bp]  (R = H fwd, 4H bwd)
+  float* dcbuf;             // bwd: carried dc [2 dir][Bp][H]
+  unsigned* counters;       // [2], zeroed before launch
+  const int* len;           // [B]
+  int B, Bp, T, yT, D, H;
+  int nsl;                  // CTAs (hidden slices) per direction
+  int dir0;                 // first direction handled by this launch
+};
+
+// Shared-memory carve-up (floats): W slice | ring stages | k-split partials
+template <int TBT, int HS>
+struct RecCfg {
+  static constexpr int BT = 16 * TBT;               // batch rows per tile
+  static constexpr int CG = HS / 2;                 // column groups (2 hidden units each)
+  static constexpr int KS = 8 / CG;                 // k-split factor (warps per column group)
+  static constexpr int PAIRS = BT * HS;             // (b, j) pairs per tile
+  static constexpr int PP = (PAIRS + RNN_THREADS - 1) / RNN_THREADS;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int TBT, int HS>
+__global__ void __launch_bounds__(RNN_THREADS, 1)
+blstm_rec_fwd_kernel(const RecParams p) {
+  using C = RecCfg<TBT, HS>;
+  constexpr int BT = C::BT, CG = C::CG, KS = C::KS, PP = C::PP;
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, H4 = 4 * p.H;
+  float* Ws = smem;                                  // [H][HS][4]
+  float* ring = Ws + (size_t)H * HS * 4;             // [STAGES][KC][BT]
+  float* red = ring + (size_t)STAGES * KC * BT;      // [KS][BT][HS][4]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dir = p.dir0 + blockIdx.x / p.nsl;
+  const int slice = blockIdx.x % p.nsl;
+  const int j0 = slice * HS;
+  const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
+  float* gates = p.gates[dir];
+  float* cells = p.cells[dir];
+  unsigned* counter = p.counters + dir;
+  float* hx = p.xchg + (size_t)dir * 2 * H * p.Bp;   // [2][H][Bp]
+
+  // resident weight slice: Ws[k][jl][g] = Kh[k][g*H + j0 + jl]
+  for (int i = tid; i < H * HS * 4; i += RNN_THREADS) {
+    const int g = i & 3, jl = (i >> 2) % HS, k = i / (4 * HS);
+    Ws[i] = Kh[(size_t)k * H4 + g * H + j0 + jl];
+  }
+  __syncthreads();
+
+  const int cg = warp % CG, ks = warp / CG;
+  const int bg = lane & 15, jj = lane >> 4;
+  const int jl_mm = cg * 2 + jj;                     // hidden unit of this thread in the matmul
+  const int nchunks = H / KC;                        // host guarantees H % KC == 0
+  const int kper = KC / KS;                          // k rows per warp per chunk
+  const int ntile = (p.B + BT - 1) / BT;
+
+  for (int s = 0; s < p.T; ++s) {
+    const float* hprev = hx + (size_t)((s + 1) & 1) * H * p.Bp;   // written at step s-1
+    float* hnext = hx + (size_t)(s & 1) * H * p.Bp;
+    for (int tile = 0; tile < ntile; ++tile) {
+      const int b0 = tile * BT;
+      // ---- prefetch the pointwise operands of this thread's (b, j) pairs -----------------------
+      float gx[PP][4], cprev[PP];
+      int tb[PP];
+      bool valid[PP];
+#pragma unroll
+      for (int q = 0; q < PP; ++q) {
+        const int pr = tid + q * RNN_THREADS;
+        const int jl = pr % HS, b = b0 + pr / HS;
+        valid[q] = false; tb[q] = 0; cprev[q] = 0.f;
+        gx[q][0] = gx[q][1] = gx[q][2] = gx[q][3] = 0.f;
+        if (pr < C::PAIRS && b < p.B) {
+          const int L = p.len[b];
+          valid[q] = s < L;
+          const int t = valid[q] ? (dir ? L - 1 - s : s) : s;
+          tb[q] = t;
+          if (valid[q]) {
+            const float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gx[q][g] = __ldcg(gp + g * H);
+            if (s > 0) cprev[q] = __ldcg(cells + ((size_t)b * p.T + (dir ? t + 1 : t - 1)) * H + j0 + jl);
+          }
+        }
+      }
+
+      // ---- recurrent product  z[b, 4 gates of jl] = sum_k h_{s-1}[k][b] * Ws[k][jl][:] ---------
+      float acc[TBT][4];
+#pragma unroll
+      for (int r = 0; r < TBT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+
+      if (s > 0) {
+        if (tile == 0) {
+          if (tid == 0) {
+            const unsigned target = (unsigned)p.nsl * (unsigned)s;
+            while (ld_acquire_gpu(counter) < target) { }
+            __threadfence();
+          }
+          __syncthreads();
+        }
+        auto issue = [&](int c) {
+          if (c < nchunks) {
+            float* dst = ring + (size_t)(c % STAGES) * KC * BT;
+            const float* src = hprev + (size_t)c * KC * p.Bp + b0;
+            for (int i = tid; i < KC * BT / 4; i += RNN_THREADS) {
+              const int row = i / (BT / 4), c4 = i % (BT / 4);
+              cp_async16(dst + row * BT + c4 * 4, src + (size_t)row * p.Bp + c4 * 4);
+            }
+          }
+          cp_async_commit();
+        };
+        issue(0);
+        issue(1);
+        for (int c = 0; c < nchunks; ++c) {
+          cp_async_wait<1>();
+          __syncthreads();
+          issue(c + 2);
+          const float* hs_ = ring + (size_t)(c % STAGES) * KC * BT + (size_t)ks * kper * BT + bg * TBT;
+          const float* ws_ = Ws + ((size_t)(c * KC + ks * kper) * HS + jl_mm) * 4;
+#pragma unroll 4
+          for (int kk = 0; kk < kper; ++kk) {
+            const float4 w = *reinterpret_cast<const float4*>(ws_ + (size_t)kk * HS * 4);
+            float hv[TBT];
+            if (TBT >= 4) {
+#pragma unroll
+              for (int v = 0; v < TBT / 4; ++v) {
+                const float4 t4 = *reinterpret_cast<const float4*>(hs_ + kk * BT + v * 4);
+                hv[v * 4 + 0] = t4.x; hv[v * 4 + 1] = t4.y; hv[v * 4 + 2] = t4.z; hv[v * 4 + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < TBT; ++r) hv[r] = hs_[kk * BT + r];
+            }
+#pragma unroll
+            for (int r = 0; r < TBT; ++r) {
+              acc[r][0] = fmaf(hv[r], w.x, acc[r][0]);
+              acc[r][1] = fmaf(hv[r], w.y, acc[r][1]);
+              acc[r][2] = fmaf(hv[r], w.z, acc[r][2]);
+              acc[r][3] = fmaf(hv[r], w.w, acc[r][3]);
+            }
+          }
+        }
+        cp_async_wait<0>();
+      }
+      // ---- k-split partials -> shared ----------------------------------------------------------
+#pragma unroll
+      for (int r = 0; r < TBT; ++r) {
+        float4* dst = reinterpret_cast<float4*>(red + (((size_t)ks * BT + bg * TBT + r) * HS + jl_mm) * 4);
+        *dst = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      }
+      __syncthreads();
+
+      // ---- pointwise cell update ---------------------------------------------------------------
+#pragma unroll
+      for (int q = 0; q < PP; ++q) {
+        const int pr = tid + q * RNN_THREADS;
+        const int jl = pr % HS, bl = pr / HS, b = b0 + bl;
+        if (pr < C::PAIRS && b < p.B) {
+          float z[4] = {gx[q][0], gx[q][1], gx[q][2], gx[q][3]};
+#pragma unroll
+          for (int k2 = 0; k2 < KS; ++k2) {
+            const float4 v = *reinterpret_cast<const float4*>(red + (((size_t)k2 * BT + bl) * HS + jl) * 4);
+            z[0] += v.x; z[1] += v.y; z[2] += v.z; z[3] += v.w;
+          }
+          const float ig = sigmoid_acc(z[0]);
+          const float gg = tanhf(z[1]);
+          const float fg = sigmoid_acc(z[2] + 1.0f);
+          const float og = sigmoid_acc(z[3]);
+          const float cn = cprev[q] * fg + ig * gg;
+          const float hn = tanhf(cn) * og;
+          const int t = tb[q];
+          if (valid[q]) {
+            float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+            __stcg(gp, ig); __stcg(gp + H, gg); __stcg(gp + 2 * H, fg); __stcg(gp + 3 * H, og);
+            __stcg(cells + ((size_t)b * p.T + t) * H + j0 + jl, cn);
+          }
+          __stcg(p.y + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl, valid[q] ? hn : 0.f);
+          __stcg(hnext + (size_t)(j0 + jl) * p.Bp + b, valid[q] ? hn : 0.f);
+        }
+      }
+      __syncthreads();   // red[] and ring are reused by the next tile / step
+    }
+    // ---- publish h_s -----------------------------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) red_release_gpu_add(counter, 1u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <int TBT, int HS>
+__global__ void __launch_bounds__(RNN_THREADS, 1)
+blstm_rec_bwd_kernel(const RecParams p) {
+  using C = RecCfg<TBT, HS>;
+  constexpr int BT = C::BT, PP = C::PP;
+  constexpr int CW = HS / 2;                         // output columns per thread in the matmul
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, H4 = 4 * p.H;
+  float* Ws = smem;                                  // [4H][HS]   Ws[k][jl] = Kh[j0+jl][k]
+  float* ring = Ws + (size_t)H4 * HS;                // [STAGES][KC][BT]
+  float* red = ring + (size_t)STAGES * KC * BT;      // [8 warps][BT][HS]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dir = p.dir0 + blockIdx.x / p.nsl;
+  const int slice = blockIdx.x % p.nsl;
+  const int j0 = slice * HS;
+  const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
+  float* gates = p.gates[dir];
+  const float* cells = p.cells[dir];
+  unsigned* counter = p.counters + dir;
+  float* dzx = p.xchg + (size_t)dir * 2 * H4 * p.Bp; // [2][4H][Bp]
+  float* dcb = p.dcbuf + (size_t)dir * p.Bp * H;     // [Bp][H]
+
+  for (int i = tid; i < H4 * HS; i += RNN_THREADS) {
+    const int jl = i % HS, k = i / HS;
+    Ws[i] = Kh[(size_t)(j0 + jl) * H4 + k];
+  }
+  __syncthreads();
+
+  const int bg = lane & 15, jj = lane >> 4;
+  const int nchunks = H4 / KC;
+  const int kper = KC / 8;                           // 8 warps split every chunk
+  const int ntile = (p.B + BT - 1) / BT;
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+
+  int iter = 0;
+  for (int s = p.T - 1; s >= 0; --s, ++iter) {
+    const float* dzprev = dzx + (size_t)((iter + 1) & 1) * H4 * p.Bp;   // published at iter-1 (step s+1)
+    float* dznext = dzx + (size_t)(iter & 1) * H4 * p.Bp;
+    for (int tile = 0; tile < ntile; ++tile) {
+      const int b0 = tile * BT;
+      // ---- prefetch pointwise operands ---------------------------------------------------------
+      float gt[PP][4], ct[PP], cprev[PP], dyv[PP], dcr[PP];
+      int tb[PP];
+      bool valid[PP];
+#pragma unroll
+      for (int q = 0; q < PP; ++q) {
+        const int pr = tid + q * RNN_THREADS;
+        const int jl = pr % HS, b = b0 + pr / HS;
+        valid[q] = false; tb[q] = 0; ct[q] = cprev[q] = dyv[q] = dcr[q] = 0.f;
+        gt[q][0] = gt[q][1] = gt[q][2] = gt[q][3] = 0.f;
+        if (pr < C::PAIRS && b < p.B) {
+          const int L = p.len[b];
+          valid[q] = s < L;
+          const int t = valid[q] ? (dir ? L - 1 - s : s) : s;
+          tb[q] = t;
+          if (valid[q]) {
+            const float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gt[q][g] = __ldcg(gp + g * H);
+            ct[q] = __ldcg(cells + ((size_t)b * p.T + t) * H + j0 + jl);
+            if (s > 0) cprev[q] = __ldcg(cells + ((size_t)b * p.T + (dir ? t + 1 : t - 1)) * H + j0 + jl);
+            dyv[q] = __ldcg(p.dy + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl);
+            if (iter > 0) dcr[q] = __ldcg(dcb + (size_t)b * H + j0 + jl);
+          }
+        }
+      }
+
+      // ---- dh_rec[b, jl] = sum_k dz_{s+1}[k][b] * Kh[j0+jl][k] ---------------------------------
+      float acc[TBT][CW];
+#pragma unroll
+      for (int r = 0; r < TBT; ++r)
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[r][c] = 0.f;
+
+      if (iter > 0) {
+        if (tile == 0) {
+          if (tid == 0) {
+            const unsigned target = (unsigned)p.nsl * (unsigned)iter;
+            while (ld_acquire_gpu(counter) < target) { }
+            __threadfence();
+          }
+          __syncthreads();
+        }
+        auto issue = [&](int c) {
+          if (c < nchunks) {
+            float* dst = ring + (size_t)(c % STAGES) * KC * BT;
+            const float* src = dzprev + (size_t)c * KC * p.Bp + b0;
+            for (int i = tid; i < KC * BT / 4; i += RNN_THREADS) {
+              const int row = i / (BT / 4), c4 = i % (BT / 4);
+              cp_async16(dst + row * BT + c4 * 4, src + (size_t)row * p.Bp + c4 * 4);
+            }
+          }
+          cp_async_commit();
+        };
+        issue(0);
+        issue(1);
+        for (int c = 0; c < nchunks; ++c) {
+          cp_async_wait<1>();
+          __syncthreads();
+          issue(c + 2);
+          const float* hs_ = ring + (size_t)(c % STAGES) * KC * BT + (size_t)warp * kper * BT + bg * TBT;
+          const float* ws_ = Ws + (size_t)(c * KC + warp * kper) * HS + jj * CW;
+#pragma unroll 4
+          for (int kk = 0; kk < kper; ++kk) {
+            float w[CW];
+#pragma unroll
+            for (int c2 = 0; c2 < CW; ++c2) w[c2] = ws_[kk * HS + c2];
+            float hv[TBT];
+            if (TBT >= 4) {
+#pragma unroll
+              for (int v = 0; v < TBT / 4; ++v) {
+                const float4 t4 = *reinterpret_cast<const float4*>(hs_ + kk * BT + v * 4);
+                hv[v * 4 + 0] = t4.x; hv[v * 4 + 1] = t4.y; hv[v * 4 + 2] = t4.z; hv[v * 4 + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < TBT; ++r) hv[r] = hs_[kk * BT + r];
+            }
+#pragma unroll
+            for (int r = 0; r < TBT; ++r)
+#pragma unroll
+              for (int c2 = 0; c2 < CW; ++c2) acc[r][c2] = fmaf(hv[r], w[c2], acc[r][c2]);
+          }
+        }
+        cp_async_wait<0>();
+      }
+#pragma unroll
+      for (int r = 0; r < TBT; ++r)
+#pragma unroll
+        for (int c2 = 0; c2 < CW; ++c2)
+          red[((size_t)warp * BT + bg * TBT + r) * HS + jj * CW + c2] = acc[r][c2];
+      __syncthreads();
+
+      // ---- pointwise gate gradients ------------------------------------------------------------
+#pragma unroll
+      for (int q = 0; q < PP; ++q) {
+        const int pr = tid + q * RNN_THREADS;
+        const int jl = pr % HS, bl = pr / HS, b = b0 + bl;
+        if (pr < C::PAIRS && b < p.B) {
+          float dh = dyv[q];
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) dh += red[((size_t)w8 * BT + bl) * HS + jl];
+          float dz[4] = {0.f, 0.f, 0.f, 0.f};
+          float dcn = 0.f;
+          if (valid[q]) {
+            const float ig = gt[q][0], gg = gt[q][1], fg = gt[q][2], og = gt[q][3];
+            const float tc = tanhf(ct[q]);
+            const float d_o = dh * tc;
+            const float dc = dcr[q] + dh * og * (1.f - tc * tc);
+            dz[0] = dc * gg * ig * (1.f - ig);
+            dz[1] = dc * ig * (1.f - gg * gg);
+            dz[2] = dc * cprev[q] * fg * (1.f - fg);
+            dz[3] = d_o * og * (1.f - og);
+            dcn = dc * fg;
+          }
+          const int t = tb[q];
+          float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            __stcg(gp + g * H, dz[g]);
+            __stcg(dznext + (size_t)(g * H + j0 + jl) * p.Bp + b, dz[g]);
+            dbacc[g] += dz[g];
+          }
+          __stcg(dcb + (size_t)b * H + j0 + jl, dcn);
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) red_release_gpu_add(counter, 1u);
+  }
+
+  // bias gradient: every thread's pairs share jl = tid % HS (256 % HS == 0); fixed-order sum
+  {
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ring[tid * 4 + g] = dbacc[g];
+    __syncthreads();
+    if (tid < 4 * HS) {
+      const int g = tid / HS, j = tid % HS;
+      float sum = 0.f;
+      for (int i = j; i < RNN_THREADS; i += HS) sum += ring[i * 4 + g];
+      p.dbias[dir][g * H + j0 + j] = sum;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  int tbt, hs, nsl, ndir_concurrent;
+  size_t smem_fwd, smem_bwd;
+  int Bp;
+};
+
+int make_plan(int B, int H, Plan* pl) {
+  NABU_REQUIRE(H % KC == 0, "blstm: num_units=%d must be a multiple of %d", H, KC);
+  pl->tbt = B <= 16 ? 1 : B <= 32 ? 2 : B <= 64 ? 4 : 8;
+  const int BT = 16 * pl->tbt;
+  pl->Bp = ceil_div(B, BT) * BT;
+  const int sms = num_sms();
+  const size_t cap = (size_t)max_smem_optin();
+  const int cand[4] = {2, 4, 8, 16};
+  for (int pass = 0; pass < 2; ++pass) {          // pass 0: both directions concurrently
+    const int ndir = pass == 0 ? 2 : 1;
+    for (int ci = 0; ci < 4; ++ci) {
+      const int hs = cand[ci];
+      if (H % hs) continue;
+      const int nsl = H / hs;
+      if (ndir * nsl > sms) continue;
+      const int ks = 8 / (hs / 2);
+      const size_t ringf = (size_t)STAGES * KC * BT;
+      const size_t fwd = ((size_t)H * hs * 4 + ringf + (size_t)ks * BT * hs * 4) * sizeof(float);
+      const size_t bwd = ((size_t)4 * H * hs + ringf + (size_t)8 * BT * hs) * sizeof(float) + 1024;
+      if (fwd > cap || bwd > cap) continue;
+      pl->hs = hs; pl->nsl = nsl; pl->ndir_concurrent = ndir; pl->smem_fwd = fwd; pl->smem_bwd = bwd;
+      return 0;
+    }
+  }
+  set_error("blstm: num_units=%d does not fit the persistent kernel (needs H/hs <= %d CTAs and the Kh slice in %zu B shared memory)",
+            H, sms, cap);
+  return 2;
+}
+
+template <int TBT, int HS>
+int launch_rec(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t stream) {
+  const void* fn = backward ? (const void*)blstm_rec_bwd_kernel<TBT, HS> : (const void*)blstm_rec_fwd_kernel<TBT, HS>;
+  const size_t smem = backward ? pl.smem_bwd : pl.smem_fwd;
+  NABU_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int d0 = 0; d0 < 2; d0 += pl.ndir_concurrent) {
+    RecParams q = rp;
+    q.dir0 = d0;
+    void* args[] = {(void*)&q};
+    NABU_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pl.nsl * pl.ndir_concurrent), dim3(RNN_THREADS), args,
+                                                smem, stream));
+  }
+  return 0;
+}
+
+template <int TBT>
+int dispatch_hs(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t stream) {
+  switch (pl.hs) {
+    case 2: return launch_rec<TBT, 2>(backward, rp, pl, stream);
+    case 4: return launch_rec<TBT, 4>(backward, rp, pl, stream);
+    case 8: return launch_rec<TBT, 8>(backward, rp, pl, stream);
+    case 16: return launch_rec<TBT, 16>(backward, rp, pl, stream);
+  }
+  set_error("blstm: bad hs");
+  return 2;
+}
+
+int dispatch(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t stream) {
+  switch (pl.tbt) {
+    case 1: return dispatch_hs<1>(backward, rp, pl, stream);
+    case 2: return dispatch_hs<2>(backward, rp, pl, stream);
+    case 4: return dispatch_hs<4>(backward, rp, pl, stream);
+    case 8: return dispatch_hs<8>(backward, rp, pl, stream);
+  }
+  set_error("blstm: bad tbt");
+  return 2;
+}
+
+// workspace layout: [counters 256 B][exchange 2*2*4H*Bp floats][dcbuf 2*Bp*H floats][gemm scratch]
+struct Ws {
+  unsigned* counters; float* xchg; float* dcbuf; float* gemm; size_t gemm_bytes; size_t total;
+};
+Ws carve(void* base, int H, int Bp) {
+  Ws w;
+  size_t off = 0;
+  char* b = (char*)base;
+  w.counters = (unsigned*)(b + off); off += 256;
+  w.xchg = (float*)(b + off); off += align_up((size_t)2 * 2 * 4 * H * Bp * sizeof(float), 256);
+  w.dcbuf = (float*)(b + off); off += align_up((size_t)2 * Bp * H * sizeof(float), 256);
+  w.gemm = (float*)(b + off); w.gemm_bytes = sgemm_workspace_bytes(); off += w.gemm_bytes;
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+}  // namespace nabu
+
+using namespace nabu;
+
+extern "C" size_t nabu_blstm_workspace_bytes(int B, int T, int D, int H) {
+  (void)T; (void)D;
+  Plan pl;
+  if (make_plan(B, H, &pl)) return 0;
+  return carve(nullptr, H, pl.Bp).total;
+}
+
+extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int D, int H,
+                              const float* kernel_fw, const float* bias_fw, const float* kernel_bw,
+                              const float* bias_bw, float* y, int yT, float* gates, float* cells,
+                              void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_fwd: bad shape B=%d T=%d D=%d H=%d yT=%d", B, T, D, H, yT);
+  Plan pl;
+  if (int e = make_plan(B, H, &pl)) return e;
+  Ws w = carve(workspace, H, pl.Bp);
+  NABU_REQUIRE(ws_bytes >= w.total, "blstm_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  const int H4 = 4 * H;
+  const float* kern[2] = {kernel_fw, kernel_bw};
+  const float* bias[2] = {bias_fw, bias_bw};
+  float* g[2] = {gates, gates + (size_t)B * T * H4};
+  float* c[2] = {cells, cells + (size_t)B * T * H};
+  // input projection for all T at once: Gx = X . Kx + b
+  for (int d = 0; d < 2; ++d)
+    if (int e = sgemm(GEMM_NN, B * T, H4, D, 1.f, x, D, kern[d], H4, 0.f, g[d], H4, bias[d], nullptr, nullptr, 0, stream))
+      return e;
+  NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
+  NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * pl.Bp * sizeof(float), stream));
+  if (yT > T)
+    NABU_CHECK_CUDA(cudaMemset2DAsync(y + (size_t)T * 2 * H, (size_t)yT * 2 * H * sizeof(float), 0,
+                                      (size_t)(yT - T) * 2 * H * sizeof(float), B, stream));
+  RecParams rp = {};
+  rp.kernel[0] = kern[0]; rp.kernel[1] = kern[1];
+  rp.gates[0] = g[0]; rp.gates[1] = g[1];
+  rp.cells[0] = c[0]; rp.cells[1] = c[1];
+  rp.y = y; rp.xchg = w.xchg; rp.counters = w.counters; rp.len = len;
+  rp.B = B; rp.Bp = pl.Bp; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H; rp.nsl = pl.nsl;
+  return dispatch(false, rp, pl, stream);
+}
+
+extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int D, int H,
+                              const float* kernel_fw, const float* kernel_bw, const float* y, int yT,
+                              float* gates, const float* cells, const float* dy, float* dx,
+                              float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
+                              void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_bwd: bad shape");
+  Plan pl;
+  if (int e = make_plan(B, H, &pl)) return e;
+  Ws w = carve(workspace, H, pl.Bp);
+  NABU_REQUIRE(ws_bytes >= w.total, "blstm_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  const int H4 = 4 * H;
+  const float* kern[2] = {kernel_fw, kernel_bw};
+  float* dkern[2] = {dkernel_fw, dkernel_bw};
+  float* g[2] = {gates, gates + (size_t)B * T * H4};
+  const float* c[2] = {cells, cells + (size_t)B * T * H};
+  NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
+  RecParams rp = {};
+  rp.kernel[0] = kern[0]; rp.kernel[1] = kern[1];
+  rp.gates[0] = g[0]; rp.gates[1] = g[1];
+  rp.cells[0] = (float*)c[0]; rp.cells[1] = (float*)c[1];
+  rp.dy = dy; rp.dbias[0] = dbias_fw; rp.dbias[1] = dbias_bw;
+  rp.xchg = w.xchg; rp.dcbuf = w.dcbuf; rp.counters = w.counters; rp.len = len;
+  rp.B = B; rp.Bp = pl.Bp; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H; rp.nsl = pl.nsl;
+  if (int e = dispatch(true, rp, pl, stream)) return e;
+  // gates[] now hold dZ (zero for t >= len)
+  for (int d = 0; d < 2; ++d) {
+    // dKx = X^T . dZ
+    if (int e = sgemm(GEMM_TN, D, H4, B * T, 1.f, x, D, g[d], H4, 0.f, dkern[d], H4, nullptr, nullptr, w.gemm,
+                      w.gemm_bytes, stream))
+      return e;
+    // dKh = Hprev^T . dZ ; fw: Hprev[b,t] = y[b,t-1,:H] ; bw: Hprev[b,t] = y[b,t+1,H:]
+    float* dKh = dkern[d] + (size_t)D * H4;
+    if (T > 1) {
+      GemmSeg seg;
+      seg.seg = T - 1; seg.segA = yT; seg.segB = T;
+      seg.offA = d == 0 ? 0 : 1; seg.offB = d == 0 ? 1 : 0;
+      if (int e = sgemm(GEMM_TN, H, H4, B * (T - 1), 1.f, y + d * H, 2 * H, g[d], H4, 0.f, dKh, H4, nullptr, &seg,
+                        w.gemm, w.gemm_bytes, stream))
+        return e;
+    } else {
+      NABU_CHECK_CUDA(cudaMemsetAsync(dKh, 0, (size_t)H * H4 * sizeof(float), stream));
+    }
+    // dX (+)= dZ . Kx^T
+    if (dx)
+      if (int e = sgemm(GEMM_NT, B * T, D, H4, 1.f, g[d], H4, kern[d], H4, d == 0 ? 0.f : 1.f, dx, D, nullptr, nullptr,
+                        nullptr, 0, stream))
+        return e;
+  }
+  return 0;
+}

@@ -1,0 +1,318 @@
+"""Device-side plumbing between the Python mirror of nabu's plugin API and the C-ABI kernels.
+
+* `ParamStore`: every trainable variable of a model lives in ONE flat fp32 buffer (theta) with
+  matching flat grad / Adam m / Adam v buffers, so the data-parallel step is a single NCCL
+  all-reduce over `grad` followed by a single fused clip+Adam launch (trainer.py:556-569).
+  Variables are named like the reference's TF variable scopes.
+* autograd Functions: one per C-ABI forward/backward pair.  Weight gradients are written by the
+  kernels straight into the flat grad buffer (each variable is used once per step), so autograd
+  only carries activations.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+
+# ---------------------------------------------------------------------------------------------
+# parameters
+# ---------------------------------------------------------------------------------------------
+
+def glorot_uniform_(gen, shape):
+    """tf.glorot_uniform_initializer (get_variable default in TF-1.8)."""
+    if len(shape) == 1:
+        fan_in = fan_out = shape[0]
+    elif len(shape) == 2:
+        fan_in, fan_out = shape
+    else:
+        rf = int(np.prod(shape[:-2]))
+        fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * limit
+
+
+class Variable(object):
+    __slots__ = ('name', 'shape', 'offset', 'numel', 'data', 'grad', 'init')
+
+    def __init__(self, name, shape, init):
+        self.name, self.shape, self.init = name, tuple(shape), init
+        self.numel = int(np.prod(shape))
+        self.offset = None
+        self.data = None
+        self.grad = None
+
+
+class ParamStore(object):
+    """Flat fp32 parameter / gradient / Adam-moment buffers."""
+
+    ALIGN = 64   # floats; keeps every variable 256-byte aligned for 128-bit accesses
+
+    def __init__(self, seed=0):
+        self.vars = {}
+        self.order = []
+        self.theta = self.grad = self.m = self.v = None
+        self.seed = seed
+        self.device = None
+
+    def get(self, name, shape, init='glorot'):
+        """tf.get_variable with AUTO_REUSE semantics."""
+        if name in self.vars:
+            v = self.vars[name]
+            if v.shape != tuple(shape):
+                raise ValueError('variable %s: shape %s != %s' % (name, v.shape, tuple(shape)))
+            return v
+        if self.theta is not None:
+            raise RuntimeError('ParamStore already materialised; cannot add %s' % name)
+        v = Variable(name, shape, init)
+        self.vars[name] = v
+        self.order.append(v)
+        return v
+
+    @property
+    def materialised(self):
+        return self.theta is not None
+
+    def materialise(self, device):
+        off = 0
+        for v in self.order:
+            v.offset = off
+            off += (v.numel + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.size = off
+        gen = torch.Generator().manual_seed(self.seed)
+        host = torch.zeros(off, dtype=torch.float32)
+        for v in self.order:
+            if v.init == 'glorot':
+                host[v.offset:v.offset + v.numel] = glorot_uniform_(gen, v.shape).reshape(-1)
+            elif v.init == 'zeros':
+                pass
+            else:
+                raise ValueError(v.init)
+        self.device = torch.device(device)
+        self.theta = host.to(self.device)
+        self.grad = torch.zeros_like(self.theta)
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        for v in self.order:
+            d = self.theta[v.offset:v.offset + v.numel].view(v.shape)
+            d.requires_grad_(True)
+            v.data = d
+            v.grad = self.grad[v.offset:v.offset + v.numel].view(v.shape)
+        return self
+
+    def load_numpy(self, arrays):
+        """Overwrite variables from {name: ndarray} (shared weights for parity runs)."""
+        with torch.no_grad():
+            for name, arr in arrays.items():
+                v = self.vars[name]
+                v.data.copy_(torch.as_tensor(np.asarray(arr, np.float32)).reshape(v.shape))
+
+    def to_numpy(self):
+        return {v.name: v.data.detach().cpu().numpy().copy() for v in self.order}
+
+    def grads_numpy(self):
+        return {v.name: v.grad.detach().cpu().numpy().copy() for v in self.order}
+
+    def num_params(self):
+        return sum(v.numel for v in self.order)
+
+    def state_dict(self):
+        return {'theta': self.theta.cpu(), 'm': self.m.cpu(), 'v': self.v.cpu(),
+                'names': [(v.name, v.shape, v.offset) for v in self.order]}
+
+    def load_state_dict(self, sd):
+        self.theta.copy_(sd['theta'])
+        self.m.copy_(sd['m'])
+        self.v.copy_(sd['v'])
+
+
+def clip_adam_step(store, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, clip=1.0, grad_scale=1.0):
+    lib = L.load()
+    L.check(lib.nabu_clip_adam_step(L.ptr(store.theta), L.ptr(store.grad), L.ptr(store.m), L.ptr(store.v),
+                                    store.size, lr, t, beta1, beta2, eps, clip, grad_scale, L.stream()),
+            'nabu_clip_adam_step')
+
+
+# ---------------------------------------------------------------------------------------------
+# ops
+# ---------------------------------------------------------------------------------------------
+
+def _i32(t, device):
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+class _BLSTM(torch.autograd.Function):
+    """components/layer.py:8-51 via nabu_blstm_fwd / nabu_blstm_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, lens, kf, bf, kb, bb, H, yT, gvars):
+        lib = L.load()
+        x = x.contiguous()
+        B, T, D = x.shape
+        y = torch.empty((B, yT, 2 * H), device=x.device, dtype=torch.float32)
+        gates = torch.empty((2, B, T, 4 * H), device=x.device, dtype=torch.float32)
+        cells = torch.empty((2, B, T, H), device=x.device, dtype=torch.float32)
+        nws = lib.nabu_blstm_workspace_bytes(B, T, D, H)
+        if nws == 0:
+            L.check(2, 'nabu_blstm_workspace_bytes')
+        ws = L.WORKSPACE.get(nws, x.device)
+        L.check(lib.nabu_blstm_fwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(bf), L.ptr(kb), L.ptr(bb),
+                                   L.ptr(y), yT, L.ptr(gates), L.ptr(cells), L.ptr(ws), ws.numel(), L.stream()),
+                'nabu_blstm_fwd')
+        ctx.save_for_backward(x, lens, kf, kb, y, gates, cells)
+        ctx.H, ctx.yT, ctx.gvars = H, yT, gvars
+        ctx.need_dx = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, lens, kf, kb, y, gates, cells = ctx.saved_tensors
+        B, T, D = x.shape
+        H, yT = ctx.H, ctx.yT
+        dkf, dbf, dkb, dbb = ctx.gvars
+        dy = dy.contiguous()
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        ws = L.WORKSPACE.get(lib.nabu_blstm_workspace_bytes(B, T, D, H), x.device)
+        L.check(lib.nabu_blstm_bwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(kb), L.ptr(y), yT,
+                                   L.ptr(gates), L.ptr(cells), L.ptr(dy), L.ptr(dx), L.ptr(dkf), L.ptr(dbf),
+                                   L.ptr(dkb), L.ptr(dbb), L.ptr(ws), ws.numel(), L.stream()),
+                'nabu_blstm_bwd')
+        return dx, None, None, None, None, None, None, None, None
+
+
+def blstm(x, lens, vf_k, vf_b, vb_k, vb_b, H, yT=None):
+    """x [B,T,D] -> y [B,yT,2H]; v*_ are engine.Variable."""
+    yT = x.shape[1] if yT is None else yT
+    return _BLSTM.apply(x, lens, vf_k.data, vf_b.data, vb_k.data, vb_b.data, H, yT,
+                        (vf_k.grad, vf_b.grad, vb_k.grad, vb_b.grad))
+
+
+def pyramid_lengths(lens, numsteps):
+    lib = L.load()
+    out = torch.empty_like(lens)
+    L.check(lib.nabu_pyramid_lengths(L.ptr(lens), lens.numel(), numsteps, L.ptr(out), L.stream()),
+            'nabu_pyramid_lengths')
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """models/ed_decoders/dnn_decoder.py:53-57 via nabu_linear_fwd / nabu_linear_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, gvars):
+        lib = L.load()
+        x = x.contiguous()
+        D, V = W.shape
+        N = x.numel() // D
+        y = torch.empty(x.shape[:-1] + (V,), device=x.device, dtype=torch.float32)
+        L.check(lib.nabu_linear_fwd(L.ptr(x), N, D, V, L.ptr(W), L.ptr(b), L.ptr(y), None, 0, L.stream()),
+                'nabu_linear_fwd')
+        ctx.save_for_backward(x, W)
+        ctx.gvars = gvars
+        ctx.need_dx = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, W = ctx.saved_tensors
+        D, V = W.shape
+        N = x.numel() // D
+        dW, db = ctx.gvars
+        dy = dy.contiguous()
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        ws = L.WORKSPACE.get(lib.nabu_gemm_workspace_bytes(), x.device)
+        L.check(lib.nabu_linear_bwd(L.ptr(x), N, D, V, L.ptr(W), L.ptr(dy), L.ptr(dx), L.ptr(dW), L.ptr(db),
+                                    L.ptr(ws), ws.numel(), L.stream()), 'nabu_linear_bwd')
+        return dx, None, None, None
+
+
+def linear(x, vW, vb):
+    return _Linear.apply(x, vW.data, vb.data, (vW.grad, vb.grad))
+
+
+class _CTC(torch.autograd.Function):
+    """trainers/loss_functions.py:203-212: mean over the batch of tf.nn.ctc_loss."""
+
+    @staticmethod
+    def forward(ctx, logits, logit_len, labels, label_len):
+        lib = L.load()
+        logits = logits.contiguous()
+        B, T, V = logits.shape
+        labels = labels.contiguous()
+        Lmax = labels.shape[1]
+        loss = torch.empty(B, device=logits.device, dtype=torch.float32)
+        grad = torch.empty_like(logits)
+        ws = L.WORKSPACE.get(lib.nabu_ctc_workspace_bytes(B, T, V, Lmax), logits.device)
+        L.check(lib.nabu_ctc_loss_fwd_bwd(L.ptr(logits), L.ptr(logit_len), L.ptr(labels), Lmax, L.ptr(label_len),
+                                          B, T, V, 1.0 / B, L.ptr(loss), L.ptr(grad), L.ptr(ws), ws.numel(),
+                                          L.stream()), 'nabu_ctc_loss_fwd_bwd')
+        ctx.save_for_backward(grad)
+        ctx.per_utt = loss
+        return loss.mean()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None
+
+
+def ctc_loss_per_utt(logits, logit_len, labels, label_len, want_grad=False, grad_scale=1.0):
+    """Raw per-utterance NLL (and optionally grad_scale * dNLL/dlogits)."""
+    lib = L.load()
+    logits = logits.contiguous()
+    B, T, V = logits.shape
+    labels = labels.contiguous()
+    Lmax = labels.shape[1]
+    loss = torch.empty(B, device=logits.device, dtype=torch.float32)
+    grad = torch.empty_like(logits) if want_grad else None
+    ws = L.WORKSPACE.get(lib.nabu_ctc_workspace_bytes(B, T, V, Lmax), logits.device)
+    L.check(lib.nabu_ctc_loss_fwd_bwd(L.ptr(logits), L.ptr(logit_len), L.ptr(labels), Lmax, L.ptr(label_len), B, T,
+                                      V, grad_scale, L.ptr(loss), L.ptr(grad), L.ptr(ws), ws.numel(), L.stream()),
+            'nabu_ctc_loss_fwd_bwd')
+    return loss, grad
+
+
+class _MaskedCE(torch.autograd.Function):
+    """trainers/loss_functions.py:155-165 average_cross_entropy (single output)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, logit_len, target_len):
+        lib = L.load()
+        logits = logits.contiguous()
+        B, U, V = logits.shape
+        targets = targets.contiguous()
+        loss = torch.empty(B, device=logits.device, dtype=torch.float32)
+        grad = torch.empty_like(logits)
+        L.check(lib.nabu_masked_ce_fwd_bwd(L.ptr(logits), L.ptr(targets), targets.shape[1], L.ptr(logit_len),
+                                           L.ptr(target_len), B, U, V, 1.0 / B, L.ptr(loss), L.ptr(grad),
+                                           L.stream()), 'nabu_masked_ce_fwd_bwd')
+        ctx.save_for_backward(grad)
+        return loss.mean()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None
+
+
+def ctc_mean(logits, logit_len, labels, label_len):
+    return _CTC.apply(logits, logit_len, labels, label_len)
+
+
+def masked_ce_mean(logits, targets, logit_len, target_len):
+    return _MaskedCE.apply(logits, targets, logit_len, target_len)
+
+
+def gemm(mode, A, B, M, N, K, lda, ldb, ldc, C=None, alpha=1.0, beta=0.0, bias=None, precision=0):
+    """Raw nabu_gemm call (tests)."""
+    lib = L.load()
+    if C is None:
+        C = torch.zeros((M, ldc), device=A.device, dtype=torch.float32)
+    ws = L.WORKSPACE.get(lib.nabu_gemm_workspace_bytes(), A.device)
+    L.check(lib.nabu_gemm(mode, precision, M, N, K, alpha, L.ptr(A), lda, L.ptr(B), ldb, beta, L.ptr(C), ldc,
+                          L.ptr(bias), L.ptr(ws), ws.numel(), L.stream()), 'nabu_gemm')
+    return C

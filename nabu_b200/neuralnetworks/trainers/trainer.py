@@ -1,0 +1,109 @@
+"""Trainer (reference: nabu/neuralnetworks/trainers/trainer.py).
+
+Only the update step is the hot path: model forward, loss, backward,
+one gradient all-reduce when world_size > 1, elementwise clip(-1,1) + TF-Adam on the flat buffers,
+`exponential_decay` learning rate.  The TF session / parameter-server / queue machinery of the
+reference (trainer.py:73-510) is replaced by a plain loop over a batch source: one process per
+GPU, synchronous data parallelism -- numerically the reference's `non_distributed` run at the
+global batch size.  Validation control flow is a "next" row (f2) and is not built here.
+"""
+import os
+import time
+from abc import ABCMeta, abstractmethod
+
+import torch
+import torch.distributed as dist
+
+from ... import engine
+from ...tools.default_conf import apply_defaults, defaults_path
+from ..models.model import Model
+from . import loss_functions
+
+
+class Trainer(object, metaclass=ABCMeta):
+    """Trainer(conf, dataconf, modelconf, evaluatorconf, expdir, server, task_index)."""
+
+    def __init__(self, conf, dataconf, modelconf, evaluatorconf, expdir, server=None, task_index=0,
+                 batch_source=None, device=None, seed=0):
+        self.conf = dict(conf.items('trainer'))
+        apply_defaults(self.conf, os.path.join(os.path.dirname(os.path.realpath(__file__)), 'defaults',
+                                               type(self).__name__.lower() + '.cfg'))
+        self.dataconf, self.evaluatorconf = dataconf, evaluatorconf
+        self.expdir, self.server, self.task_index = expdir, server, task_index
+        if self.conf.get('norm_constraint', 'None') != 'None':
+            raise Exception('norm_constraint (MaxNorm) is outside the B200 hot path (SURVEY.md section 8 f4)')
+        if int(self.conf['cut_sequence_length']) > 0:
+            raise Exception('cut_sequence_length (TBPTT) is outside the B200 hot path (SURVEY.md section 8 f4)')
+        self.model = Model(conf=modelconf, trainlabels=int(self.conf['trainlabels']), constraint=None, seed=seed)
+        self.loss_fn = loss_functions.factory(self.conf['loss'])
+        self.batch_source = batch_source
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.global_step = 0
+        self.learning_rate_fact = 1.0
+        self.num_steps = None      # steps per epoch * num_epochs, set by train()
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    # ---- learning rate: trainer.py:161-166 ------------------------------------------------------
+    def learning_rate(self):
+        lr0 = float(self.conf['initial_learning_rate'])
+        decay = float(self.conf['learning_rate_decay'])
+        total = self.num_steps if self.num_steps else 1
+        return lr0 * decay ** (float(self.global_step) / float(total)) * self.learning_rate_fact
+
+    # ---- the hot path: one minibatch update (trainer.py:169-174, 512-580, 757-767, 787) ---------
+    def update(self, inputs, input_seq_length, targets, target_seq_length):
+        """Returns (loss tensor on device, learning rate used).  No host synchronisation."""
+        model = self.model
+        logits, logit_seq_length = model(inputs, input_seq_length, targets, target_seq_length, True)
+        loss = self.loss_fn(targets, logits, logit_seq_length, target_seq_length)
+        extra = self.aditional_loss()
+        if extra is not None:
+            loss = loss + extra
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(model.store.grad, op=dist.ReduceOp.SUM)
+        lr = self.learning_rate()
+        # clip AFTER the reduction so the update equals the reference's at the global batch size
+        engine.clip_adam_step(model.store, lr, self.global_step + 1, clip=1.0, grad_scale=1.0 / self.world)
+        self.global_step += 1
+        return loss.detach(), lr
+
+    def train(self, testing=False):
+        """Loop over the batch source (trainer.py:582-792).  `testing` builds the model and returns."""
+        src = self.batch_source
+        if src is None:
+            raise Exception('Trainer.train needs a batch_source (the TFRecord input pipeline is row f1, not built)')
+        steps_per_epoch = len(src)
+        self.num_steps = steps_per_epoch * int(self.conf['num_epochs'])
+        self.model.build(src.input_dims, self.device)
+        if testing:
+            return
+        while self.global_step < self.num_steps:
+            for batch in src:
+                if self.global_step >= self.num_steps:
+                    break
+                start = time.time()
+                loss, lr = self.update(*batch)
+                loss_v = float(loss)          # the reference fetches the loss every step as well
+                frames = int(sum(int(v.sum()) for v in batch[1].values()))
+                elapsed = time.time() - start
+                print('WORKER %d: step %d/%d loss: %f, learning rate: %f \n\t time elapsed: %f sec'
+                      '\n\t %.0f frames/sec, peak memory usage: %d/%d MB'
+                      % (self.task_index, self.global_step - 1, self.num_steps, loss_v, lr, elapsed,
+                         frames / max(elapsed, 1e-9), torch.cuda.max_memory_allocated() / 1e6,
+                         torch.cuda.get_device_properties(self.device).total_memory / 1e6))
+        if self.expdir and self.task_index == 0:
+            os.makedirs(os.path.join(self.expdir, 'model'), exist_ok=True)
+            torch.save(self.model.store.state_dict(), os.path.join(self.expdir, 'model', 'network.pt'))
+
+    @abstractmethod
+    def aditional_loss(self):
+        """an extra loss term or None"""
+
+    @abstractmethod
+    def chief_only_hooks(self, outputs):
+        """kept for API compatibility (session hooks have no equivalent here)"""
+
+    @abstractmethod
+    def hooks(self, outputs):
+        """kept for API compatibility"""

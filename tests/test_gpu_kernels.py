@@ -1,0 +1,188 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the NumPy oracle on the same
+seeded inputs.  Tolerance: 1e-4 relative (BASELINE.json north_star) for fp32 values, written next
+to each assert; integer outputs are compared exactly."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('shape', [(128, 128, 64), (200, 72, 40), (37, 29, 515), (1000, 256, 129), (5, 3, 7)])
+def test_gemm(mode, shape):
+    from nabu_b200 import engine
+    M, N, K = shape
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((K, N))
+    bias = rng.standard_normal(N); C0 = rng.standard_normal((M, N))
+    ref = 0.5 * A @ B + 2.0 * C0 + bias
+    a = dev(A if mode != 2 else A.T, torch.float32)
+    b = dev(B if mode != 1 else B.T, torch.float32)
+    c = dev(C0, torch.float32)
+    engine.gemm(mode, a, b, M, N, K, a.shape[1], b.shape[1], N, C=c, alpha=0.5, beta=2.0,
+                bias=dev(bias, torch.float32))
+    assert rel_err(c.cpu().numpy(), ref) < 2e-5
+
+
+def test_gemm_large_splitk():
+    from nabu_b200 import engine
+    rng = np.random.default_rng(1)
+    R, M, N = 20000, 40, 256
+    A = rng.standard_normal((R, M)).astype(np.float32); B = rng.standard_normal((R, N)).astype(np.float32)
+    c = engine.gemm(2, dev(A), dev(B), M, N, R, M, N, N)
+    assert rel_err(c.cpu().numpy(), A.astype(np.float64).T @ B.astype(np.float64)) < 2e-5
+
+
+def _blstm_case(B, T, D, H, ragged, seed, yT=None, need_dx=True):
+    from nabu_b200 import lib as L
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, T, D)).astype(np.float32)
+    lens = rng.integers(max(1, T // 2), T + 1, size=B).astype(np.int32) if ragged else np.full(B, T, np.int32)
+    if ragged:
+        lens[0] = T
+    p = O.init_blstm_params(rng, D, H)
+    yT = T if yT is None else yT
+    dy = rng.standard_normal((B, yT, 2 * H)).astype(np.float32)
+    y_ref, cache = O.blstm_fwd(x, lens, p, np.float64)
+    dx_ref, g_ref = O.blstm_bwd(cache, dy[:, :T].astype(np.float64))
+
+    lib = L.load()
+    xd, ld = dev(x), dev(lens)
+    pd = {k: dev(v) for k, v in p.items()}
+    y = torch.full((B, yT, 2 * H), 7.0, device='cuda')
+    gates = torch.empty((2, B, T, 4 * H), device='cuda'); cells = torch.empty((2, B, T, H), device='cuda')
+    nws = lib.nabu_blstm_workspace_bytes(B, T, D, H)
+    assert nws > 0
+    ws = torch.empty(nws, dtype=torch.uint8, device='cuda')
+    L.check(lib.nabu_blstm_fwd(L.ptr(xd), L.ptr(ld), B, T, D, H, L.ptr(pd['fw_kernel']), L.ptr(pd['fw_bias']),
+                               L.ptr(pd['bw_kernel']), L.ptr(pd['bw_bias']), L.ptr(y), yT, L.ptr(gates),
+                               L.ptr(cells), L.ptr(ws), nws, L.stream()), 'fwd')
+    torch.cuda.synchronize()
+    yh = y.cpu().numpy()
+    assert rel_err(yh[:, :T], y_ref) < TOL                       # 1e-4 relative fp32
+    assert np.all(yh[:, T:] == 0)
+    for b in range(B):
+        assert np.all(yh[b, lens[b]:] == 0)
+    dyd = dev(dy)
+    dx = torch.empty_like(xd) if need_dx else None
+    gk = {k: torch.full_like(v, 3.0) for k, v in pd.items()}
+    L.check(lib.nabu_blstm_bwd(L.ptr(xd), L.ptr(ld), B, T, D, H, L.ptr(pd['fw_kernel']), L.ptr(pd['bw_kernel']),
+                               L.ptr(y), yT, L.ptr(gates), L.ptr(cells), L.ptr(dyd), L.ptr(dx),
+                               L.ptr(gk['fw_kernel']), L.ptr(gk['fw_bias']), L.ptr(gk['bw_kernel']),
+                               L.ptr(gk['bw_bias']), L.ptr(ws), nws, L.stream()), 'bwd')
+    torch.cuda.synchronize()
+    if need_dx:
+        assert rel_err(dx.cpu().numpy(), dx_ref) < TOL
+    for k in g_ref:
+        assert rel_err(gk[k].cpu().numpy(), g_ref[k]) < TOL, k
+
+
+@pytest.mark.parametrize('B,T,D,H,ragged', [
+    (3, 7, 5, 64, True),         # tiny batch, TBT=1, hs=2
+    (20, 12, 40, 64, True),      # TBT=2
+    (40, 9, 24, 128, True),      # TBT=4, hs=2
+    (100, 6, 40, 256, True),     # TBT=8, hs=4, padded batch tile
+    (130, 5, 16, 64, False),     # two batch tiles
+    (16, 10, 40, 512, True),     # hs=8 (cfg-3 width)
+    (4, 1, 8, 64, False),        # T=1
+])
+def test_blstm_fwd_bwd(B, T, D, H, ragged):
+    _blstm_case(B, T, D, H, ragged, seed=B * 1000 + T)
+
+
+def test_blstm_padded_output_and_no_dx():
+    _blstm_case(6, 7, 12, 64, True, seed=5, yT=8, need_dx=False)
+
+
+def test_blstm_h1024_sequential_directions():
+    _blstm_case(8, 4, 32, 1024, True, seed=11)
+
+
+@pytest.mark.parametrize('B,T,V,L,ragged', [(4, 30, 6, 7, True), (32, 200, 29, 20, True), (2, 5, 3, 2, False),
+                                            (3, 40, 29, 0, False)])
+def test_ctc(B, T, V, L, ragged):
+    from nabu_b200 import engine
+    rng = np.random.default_rng(B + T)
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    lens = rng.integers(max(2 * L + 1, T // 2), T + 1, size=B).astype(np.int32) if ragged else np.full(B, T, np.int32)
+    Lp = max(L, 1)
+    labels = rng.integers(0, V - 1, size=(B, Lp)).astype(np.int32)
+    if L > 1:
+        labels[0, 1] = labels[0, 0]          # a repeat: needs the blank-between-repeats rule
+    ll = rng.integers(max(L // 2, 0), L + 1, size=B).astype(np.int32) if (ragged and L > 0) else np.full(B, L, np.int32)
+    loss_ref, grad_ref = O.ctc_loss_and_grad(logits, lens, labels, ll, dtype=np.float64)
+    loss, grad = engine.ctc_loss_per_utt(dev(logits), dev(lens), dev(labels), dev(ll), want_grad=True)
+    assert rel_err(loss.cpu().numpy(), loss_ref) < TOL           # 1e-4 relative fp32
+    assert np.abs(grad.cpu().numpy() - grad_ref).max() < 1e-4    # probabilities: absolute 1e-4
+
+
+def test_ctc_infeasible_is_inf():
+    from nabu_b200 import engine
+    logits = np.zeros((1, 3, 4), np.float32)
+    labels = np.array([[0, 0, 1, 2]], np.int32)
+    loss, grad = engine.ctc_loss_per_utt(dev(logits), dev(np.array([3], np.int32)), dev(labels),
+                                         dev(np.array([4], np.int32)), want_grad=True)
+    assert np.isinf(loss.cpu().numpy()[0]) and np.all(grad.cpu().numpy() == 0)
+
+
+def test_linear_and_ce():
+    from nabu_b200 import lib as L
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    N, D, V = 333, 96, 29
+    x = rng.standard_normal((N, D)).astype(np.float32)
+    p = O.init_linear_params(rng, D, V)
+    p['biases'] = rng.standard_normal(V).astype(np.float32)
+    dy = rng.standard_normal((N, V)).astype(np.float32)
+    y_ref = O.linear_fwd(x, p)
+    dx_ref, g_ref = O.linear_bwd(x, p, dy.astype(np.float64))
+    xd, Wd, bd, dyd = dev(x), dev(p['weights']), dev(p['biases']), dev(dy)
+    y = torch.empty((N, V), device='cuda'); dx = torch.empty_like(xd); dW = torch.empty_like(Wd); db = torch.empty_like(bd)
+    ws = torch.empty(lib.nabu_gemm_workspace_bytes(), dtype=torch.uint8, device='cuda')
+    L.check(lib.nabu_linear_fwd(L.ptr(xd), N, D, V, L.ptr(Wd), L.ptr(bd), L.ptr(y), None, 0, L.stream()), 'lf')
+    L.check(lib.nabu_linear_bwd(L.ptr(xd), N, D, V, L.ptr(Wd), L.ptr(dyd), L.ptr(dx), L.ptr(dW), L.ptr(db),
+                                L.ptr(ws), ws.numel(), L.stream()), 'lb')
+    assert rel_err(y.cpu().numpy(), y_ref) < TOL
+    assert rel_err(dx.cpu().numpy(), dx_ref) < TOL
+    assert rel_err(dW.cpu().numpy(), g_ref['weights']) < TOL
+    assert rel_err(db.cpu().numpy(), g_ref['biases']) < TOL
+    # masked cross-entropy
+    B, U = 7, 11
+    logits = rng.standard_normal((B, U, V)).astype(np.float32) * 3
+    tl = rng.integers(1, U + 1, size=B).astype(np.int32); tl[0] = U
+    tg = rng.integers(0, V, size=(B, U)).astype(np.int32)
+    loss_ref, d_ref = O.average_cross_entropy(logits, tg, tl, tl)
+    loss = torch.empty(B, device='cuda'); grad = torch.empty((B, U, V), device='cuda')
+    L.check(lib.nabu_masked_ce_fwd_bwd(L.ptr(dev(logits)), L.ptr(dev(tg)), U, L.ptr(dev(tl)), L.ptr(dev(tl)), B, U, V,
+                                       1.0 / B, L.ptr(loss), L.ptr(grad), L.stream()), 'ce')
+    assert abs(loss.mean().item() - loss_ref) / abs(loss_ref) < TOL
+    assert rel_err(grad.cpu().numpy(), d_ref) < TOL
+
+
+def test_clip_adam_matches_tf_formula():
+    from nabu_b200 import lib as L
+    lib = L.load()
+    rng = np.random.default_rng(4)
+    n = 10007
+    th = rng.standard_normal(n).astype(np.float32); g = (rng.standard_normal(n) * 2).astype(np.float32)
+    m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    thd, md, vd = dev(th), dev(m), dev(v)
+    for t in range(1, 4):
+        gd = dev(g * t)
+        L.check(lib.nabu_clip_adam_step(L.ptr(thd), L.ptr(gd), L.ptr(md), L.ptr(vd), n, 1e-3, t, 0.9, 0.999, 1e-8,
+                                        1.0, 1.0, L.stream()), 'adam')
+        th, m, v = O.tf_adam_clip(th, g * t, m, v, 1e-3, t, dtype=np.float64)
+    assert rel_err(thd.cpu().numpy(), th) < 1e-6
+    assert rel_err(md.cpu().numpy(), m) < 1e-6 and rel_err(vd.cpu().numpy(), v) < 1e-6
