@@ -25,6 +25,13 @@ extern "C" {
 const char* nabu_last_error(void);
 int nabu_version(void);
 
+/* Instrumentation used by bench.py: kernels launched by this library since it was loaded, and
+ * optional CUDA-event bracketing of every launch (on the launch stream).  nabu_profile_collect
+ * synchronises the device and writes {"kernel": [launches, total_ms], ...} as JSON. */
+unsigned long long nabu_kernel_launches(void);
+int nabu_profile_enable(int on);
+int nabu_profile_collect(char* json_out, size_t cap);
+
 /* ---- dense contraction (building block; exported for tests) ------------------------------------
  * mode 0: C[M,N] = alpha*A[M,K].B[K,N]   + beta*C + bias[N]
  * mode 1: C[M,N] = alpha*A[M,K].B[N,K]^T + beta*C + bias[N]

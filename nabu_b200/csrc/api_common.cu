@@ -40,4 +40,65 @@ int max_smem_optin() {
   return cached[dev];
 }
 
+
+// ---- launch counter + optional per-kernel event timing ----------------------------------------
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+constexpr int kMaxRec = 1 << 16;
+ProfRec g_rec[kMaxRec];
+int g_nrec = 0;
+bool g_prof = false;
+unsigned long long g_launches = 0;
+}  // namespace
+
+KernelScope::KernelScope(const char* name, cudaStream_t stream) : stream_(stream), slot_(-1) {
+  ++g_launches;
+  if (g_prof && g_nrec < kMaxRec) {
+    slot_ = g_nrec++;
+    ProfRec& r = g_rec[slot_];
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, stream);
+  }
+}
+KernelScope::~KernelScope() {
+  if (slot_ >= 0) cudaEventRecord(g_rec[slot_].b, stream_);
+}
+
+unsigned long long kernel_launches() { return g_launches; }
+void profile_enable(bool on) { g_prof = on; }
+
+// Synchronises, then writes {"name": [count, total_ms], ...} and frees the events.
+int profile_collect(char* out, size_t cap) {
+  cudaDeviceSynchronize();
+  struct Agg { const char* name; int n; double ms; };
+  Agg agg[256];
+  int na = 0;
+  for (int i = 0; i < g_nrec; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_rec[i].a, g_rec[i].b);
+    cudaEventDestroy(g_rec[i].a);
+    cudaEventDestroy(g_rec[i].b);
+    int j = 0;
+    for (; j < na; ++j)
+      if (strcmp(agg[j].name, g_rec[i].name) == 0) break;
+    if (j == na) {
+      if (na == 256) continue;
+      agg[na].name = g_rec[i].name; agg[na].n = 0; agg[na].ms = 0.0; ++na;
+    }
+    agg[j].n += 1;
+    agg[j].ms += ms;
+  }
+  g_nrec = 0;
+  size_t off = 0;
+  auto put = [&](const char* fmt, auto... a) {
+    if (off < cap) off += snprintf(out + off, cap - off, fmt, a...);
+  };
+  put("{");
+  for (int j = 0; j < na; ++j) put("%s\"%s\": [%d, %.6f]", j ? ", " : "", agg[j].name, agg[j].n, agg[j].ms);
+  put("}");
+  return off < cap ? 0 : 1;
+}
+
 }  // namespace nabu

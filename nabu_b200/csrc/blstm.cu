@@ -465,6 +465,7 @@ int launch_rec(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t 
     RecParams q = rp;
     q.dir0 = d0;
     void* args[] = {(void*)&q};
+    KernelScope ks(backward ? "blstm_rec_bwd" : "blstm_rec_fwd", stream);
     NABU_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pl.nsl * pl.ndir_concurrent), dim3(RNN_THREADS), args,
                                                 smem, stream));
   }

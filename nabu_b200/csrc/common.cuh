@@ -30,6 +30,15 @@ void set_error(const char* fmt, ...);
 
 #define NABU_CHECK_LAUNCH() NABU_CHECK_CUDA(cudaGetLastError())
 
+// Counts one kernel launch and, when profiling is on, brackets it with CUDA events on `stream`
+// (bench.py's live per-kernel timing).  Use as:  { KernelScope ks("name", stream); kernel<<<...>>>(); }
+struct KernelScope {
+  KernelScope(const char* name, cudaStream_t stream);
+  ~KernelScope();
+  cudaStream_t stream_;
+  int slot_;
+};
+
 int num_sms();                 // SM count of the current device (cached)
 int max_smem_optin();          // max dynamic shared memory per block (opt-in)
 

@@ -28,8 +28,8 @@ __global__ void clip_adam_kernel(float* __restrict__ theta, const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float gc = fminf(fmaxf(g[j] * gscale, -clip), clip);
-      mm[j] = beta1 * mm[j] + (1.f - beta1) * gc;
-      vv[j] = beta2 * vv[j] + (1.f - beta2) * gc * gc;
+      mm[j] += (gc - mm[j]) * (1.f - beta1);        // ApplyAdam functor form (training_ops.cc)
+      vv[j] += (gc * gc - vv[j]) * (1.f - beta2);
       t[j] -= lr_t * mm[j] / (sqrtf(vv[j]) + eps);
     }
     reinterpret_cast<float4*>(theta)[i] = make_float4(t[0], t[1], t[2], t[3]);
@@ -40,8 +40,8 @@ __global__ void clip_adam_kernel(float* __restrict__ theta, const float* __restr
   const size_t tail0 = n4 * 4;
   for (size_t i = tail0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gc = fminf(fmaxf(grad[i] * gscale, -clip), clip);
-    const float mn = beta1 * m[i] + (1.f - beta1) * gc;
-    const float vn = beta2 * v[i] + (1.f - beta2) * gc * gc;
+    const float mn = m[i] + (gc - m[i]) * (1.f - beta1);
+    const float vn = v[i] + (gc * gc - v[i]) * (1.f - beta2);
     m[i] = mn; v[i] = vn;
     theta[i] -= lr_t * mn / (sqrtf(vn) + eps);
   }
@@ -101,6 +101,11 @@ using namespace nabu;
 extern "C" const char* nabu_last_error(void) { return nabu::last_error(); }
 extern "C" int nabu_version(void) { return 100; }
 
+namespace nabu { unsigned long long kernel_launches(); void profile_enable(bool); int profile_collect(char*, size_t); }
+extern "C" unsigned long long nabu_kernel_launches(void) { return nabu::kernel_launches(); }
+extern "C" int nabu_profile_enable(int on) { nabu::profile_enable(on != 0); return 0; }
+extern "C" int nabu_profile_collect(char* json_out, size_t cap) { return nabu::profile_collect(json_out, cap); }
+
 extern "C" size_t nabu_gemm_workspace_bytes(void) { return sgemm_workspace_bytes(); }
 
 extern "C" int nabu_gemm(int mode, int precision, int M, int N, int K, float alpha, const float* A, int lda,
@@ -120,8 +125,9 @@ extern "C" int nabu_clip_adam_step(float* theta, const float* grad, float* m, fl
   // lr_t in double like the host-side scalar math of tf.train.AdamOptimizer._prepare
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t));
   const int blocks = 2 * num_sms() * 4;
-  clip_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, (float)lr_t, beta1, beta2, eps,
-                                                            clip, grad_scale);
+  { KernelScope ks("clip_adam", (cudaStream_t)stream);
+    clip_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, (float)lr_t, beta1, beta2, eps,
+                                                              clip, grad_scale); }
   NABU_CHECK_LAUNCH();
   return 0;
 }
@@ -131,14 +137,16 @@ extern "C" int nabu_masked_ce_fwd_bwd(const float* logits, const int* targets, i
                                       float* grad, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NABU_REQUIRE(B > 0 && U > 0 && V > 0 && ldt >= U, "masked_ce: bad shape");
-  masked_ce_kernel<<<B, 256, 0, stream>>>(logits, targets, ldt, logit_len, target_len, U, V, grad_scale, loss, grad);
+  { KernelScope ks("masked_ce", stream);
+    masked_ce_kernel<<<B, 256, 0, stream>>>(logits, targets, ldt, logit_len, target_len, U, V, grad_scale, loss, grad); }
   NABU_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int nabu_pyramid_lengths(const int* len, int B, int numsteps, int* out, void* stream) {
   NABU_REQUIRE(B > 0 && numsteps > 0, "pyramid_lengths: bad args");
-  pyramid_lengths_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(len, B, numsteps, out);
+  { KernelScope ks("pyramid_lengths", (cudaStream_t)stream);
+    pyramid_lengths_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(len, B, numsteps, out); }
   NABU_CHECK_LAUNCH();
   return 0;
 }

@@ -254,17 +254,21 @@ int sgemm(GemmMode mode, int M, int N, int K, float alpha, const float* A, int l
   g.part = (splits > 1) ? workspace : nullptr;
 
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits), block(NT);
-  switch (mode) {
-    case GEMM_NN: sgemm_kernel<true, false, false><<<grid, block, 0, stream>>>(g); break;
-    case GEMM_NT: sgemm_kernel<true, true, false><<<grid, block, 0, stream>>>(g); break;
-    case GEMM_TN:
-      if (segp) sgemm_kernel<false, false, true><<<grid, block, 0, stream>>>(g);
-      else sgemm_kernel<false, false, false><<<grid, block, 0, stream>>>(g);
-      break;
+  {
+    KernelScope ks(mode == GEMM_NN ? "sgemm_nn" : mode == GEMM_NT ? "sgemm_nt" : "sgemm_tn", stream);
+    switch (mode) {
+      case GEMM_NN: sgemm_kernel<true, false, false><<<grid, block, 0, stream>>>(g); break;
+      case GEMM_NT: sgemm_kernel<true, true, false><<<grid, block, 0, stream>>>(g); break;
+      case GEMM_TN:
+        if (segp) sgemm_kernel<false, false, true><<<grid, block, 0, stream>>>(g);
+        else sgemm_kernel<false, false, false><<<grid, block, 0, stream>>>(g);
+        break;
+    }
   }
   NABU_CHECK_LAUNCH();
   if (splits > 1) {
     const long tot = (long)M * N;
+    KernelScope ks("splitk_reduce", stream);
     splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(workspace, splits, C, M, N, ldc,
                                                                           alpha, beta, bias);
     NABU_CHECK_LAUNCH();
@@ -274,6 +278,7 @@ int sgemm(GemmMode mode, int M, int N, int K, float alpha, const float* A, int l
 
 int colsum(const float* X, int M, int N, int ldx, float* out, cudaStream_t stream) {
   if (N <= 0) return 0;
+  KernelScope ks("colsum", stream);
   colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, stream>>>(X, M, N, ldx, out);
   NABU_CHECK_LAUNCH();
   return 0;

@@ -34,6 +34,9 @@ class SpellerParams(ctypes.Structure):
 SIGNATURES = {
     'nabu_last_error': (ctypes.c_char_p, []),
     'nabu_version': (c_int, []),
+    'nabu_kernel_launches': (ctypes.c_ulonglong, []),
+    'nabu_profile_enable': (c_int, [c_int]),
+    'nabu_profile_collect': (c_int, [ctypes.c_char_p, c_size_t]),
     'nabu_gemm_workspace_bytes': (c_size_t, []),
     'nabu_gemm': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P, P,
                           c_size_t, P]),

@@ -303,11 +303,11 @@ def _ctc_one(logp, labels, blank):
     alpha[0, 0] = logp[0, blank]
     if S > 1:
         alpha[0, 1] = logp[0, lp[1]]
-    with np.errstate(invalid='ignore'):
+    with np.errstate(invalid='ignore', divide='ignore'):
         for t in range(1, T):
             a = alpha[t - 1]
-            a1 = np.concatenate([[ninf], a[:-1]])
-            a2 = np.where(can_skip, np.concatenate([[ninf, ninf], a[:-2]]),
+            a1 = np.concatenate([[ninf], a])[:S]
+            a2 = np.where(can_skip, np.concatenate([[ninf, ninf], a])[:S],
                           ninf)
             alpha[t] = np.logaddexp(np.logaddexp(a, a1), a2) + logp[t, lp]
         beta = np.full((T, S), ninf, dtype)
@@ -318,8 +318,8 @@ def _ctc_one(logp, labels, blank):
         skip_from[:-2] = can_skip[2:]
         for t in range(T - 2, -1, -1):
             b = beta[t + 1] + logp[t + 1, lp]
-            b1 = np.concatenate([b[1:], [ninf]])
-            b2 = np.where(skip_from, np.concatenate([b[2:], [ninf, ninf]]),
+            b1 = np.concatenate([b, [ninf]])[1:S + 1]
+            b2 = np.where(skip_from, np.concatenate([b, [ninf, ninf]])[2:S + 2],
                           ninf)
             beta[t] = np.logaddexp(np.logaddexp(b, b1), b2)
         log_p = np.logaddexp(alpha[T - 1, S - 1],
@@ -667,8 +667,11 @@ def tf_adam_clip(theta, grad, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8,
     lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps)."""
     theta = np.asarray(theta, dtype)
     g = np.clip(np.asarray(grad, dtype), -clip, clip)
-    m = dtype(beta1) * np.asarray(m, dtype) + dtype(1 - beta1) * g
-    v = dtype(beta2) * np.asarray(v, dtype) + dtype(1 - beta2) * g * g
+    m = np.asarray(m, dtype)
+    v = np.asarray(v, dtype)
+    # tensorflow/core/kernels/training_ops.cc ApplyAdam: m += (g-m)*(1-b1); v += (g*g-v)*(1-b2)
+    m = m + (g - m) * (dtype(1) - dtype(beta1))
+    v = v + (g * g - v) * (dtype(1) - dtype(beta2))
     lr_t = dtype(lr * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t))
     theta = theta - lr_t * m / (np.sqrt(v) + dtype(eps))
     return theta, m, v

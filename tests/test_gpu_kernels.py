@@ -111,7 +111,7 @@ def test_blstm_h1024_sequential_directions():
 
 
 @pytest.mark.parametrize('B,T,V,L,ragged', [(4, 30, 6, 7, True), (32, 200, 29, 20, True), (2, 5, 3, 2, False),
-                                            (3, 40, 29, 0, False)])
+                                            (3, 40, 29, 0, False), (8, 1500, 29, 150, True)])
 def test_ctc(B, T, V, L, ragged):
     from nabu_b200 import engine
     rng = np.random.default_rng(B + T)
@@ -123,17 +123,18 @@ def test_ctc(B, T, V, L, ragged):
         labels[0, 1] = labels[0, 0]          # a repeat: needs the blank-between-repeats rule
     ll = rng.integers(max(L // 2, 0), L + 1, size=B).astype(np.int32) if (ragged and L > 0) else np.full(B, L, np.int32)
     loss_ref, grad_ref = O.ctc_loss_and_grad(logits, lens, labels, ll, dtype=np.float64)
-    loss, grad = engine.ctc_loss_per_utt(dev(logits), dev(lens), dev(labels), dev(ll), want_grad=True)
-    assert rel_err(loss.cpu().numpy(), loss_ref) < TOL           # 1e-4 relative fp32
-    assert np.abs(grad.cpu().numpy() - grad_ref).max() < 1e-4    # probabilities: absolute 1e-4
+    args = (dev(logits), dev(lens), dev(labels), dev(ll))
+    loss, grad = engine.ctc_loss_per_utt(*args, want_grad=True)
+    assert rel_err(loss.cpu().numpy(), loss_ref) < 1e-5          # far inside the 1e-4 relative bar
+    assert np.abs(grad.cpu().numpy() - grad_ref).max() < 1e-5    # posteriors: absolute 1e-5
 
 
 def test_ctc_infeasible_is_inf():
     from nabu_b200 import engine
     logits = np.zeros((1, 3, 4), np.float32)
     labels = np.array([[0, 0, 1, 2]], np.int32)
-    loss, grad = engine.ctc_loss_per_utt(dev(logits), dev(np.array([3], np.int32)), dev(labels),
-                                         dev(np.array([4], np.int32)), want_grad=True)
+    args = (dev(logits), dev(np.array([3], np.int32)), dev(labels), dev(np.array([4], np.int32)))
+    loss, grad = engine.ctc_loss_per_utt(*args, want_grad=True)
     assert np.isinf(loss.cpu().numpy()[0]) and np.all(grad.cpu().numpy() == 0)
 
 
@@ -165,7 +166,8 @@ def test_linear_and_ce():
     tg = rng.integers(0, V, size=(B, U)).astype(np.int32)
     loss_ref, d_ref = O.average_cross_entropy(logits, tg, tl, tl)
     loss = torch.empty(B, device='cuda'); grad = torch.empty((B, U, V), device='cuda')
-    L.check(lib.nabu_masked_ce_fwd_bwd(L.ptr(dev(logits)), L.ptr(dev(tg)), U, L.ptr(dev(tl)), L.ptr(dev(tl)), B, U, V,
+    lgd, tgd, tld = dev(logits), dev(tg), dev(tl)        # keep the device buffers alive across the call
+    L.check(lib.nabu_masked_ce_fwd_bwd(L.ptr(lgd), L.ptr(tgd), U, L.ptr(tld), L.ptr(tld), B, U, V,
                                        1.0 / B, L.ptr(loss), L.ptr(grad), L.stream()), 'ce')
     assert abs(loss.mean().item() - loss_ref) / abs(loss_ref) < TOL
     assert rel_err(grad.cpu().numpy(), d_ref) < TOL
@@ -184,5 +186,6 @@ def test_clip_adam_matches_tf_formula():
         L.check(lib.nabu_clip_adam_step(L.ptr(thd), L.ptr(gd), L.ptr(md), L.ptr(vd), n, 1e-3, t, 0.9, 0.999, 1e-8,
                                         1.0, 1.0, L.stream()), 'adam')
         th, m, v = O.tf_adam_clip(th, g * t, m, v, 1e-3, t, dtype=np.float64)
-    assert rel_err(thd.cpu().numpy(), th) < 1e-6
-    assert rel_err(md.cpu().numpy(), m) < 1e-6 and rel_err(vd.cpu().numpy(), v) < 1e-6
+    # fp32 (1 - beta2) carries a 1.3e-5 relative rounding, in TF's kernel exactly as here
+    assert rel_err(thd.cpu().numpy(), th) < 1e-5
+    assert rel_err(md.cpu().numpy(), m) < 1e-5 and rel_err(vd.cpu().numpy(), v) < 5e-5

@@ -1,0 +1,104 @@
+"""GPU parity tests, model level: the Python mirror of nabu's plugin API (Model / Trainer / losses)
+driving the CUDA kernels, against the NumPy oracle on shared weights and seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from tests.util import make_conf, rel_err, synthetic_ctc_batch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4      # BASELINE.json north_star: 1e-4 relative fp32
+
+
+def _dblstm_layers(params, NL, inp='features'):
+    layers = []
+    for l in range(NL):
+        base = 'DBLSTM/%s/layer%d/bidirectional_rnn/%%s/layer_norm_basic_lstm_cell/%%s' % (inp, l)
+        layers.append({'fw_kernel': params[base % ('fw', 'kernel')], 'fw_bias': params[base % ('fw', 'bias')],
+                       'bw_kernel': params[base % ('bw', 'kernel')], 'bw_bias': params[base % ('bw', 'bias')]})
+    return layers
+
+
+def _ctc_trainer(H, NL, V, dev, seed=3):
+    from nabu_b200.neuralnetworks.trainers import trainer_factory
+    mconf = make_conf('[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = dblstm\n'
+                      'num_units = %d\nnum_layers = %d\ninput_noise = 0\ndropout = 1\n[decoder]\n'
+                      'decoder = dnn_decoder\nnum_layers = 0\n' % (V - 1, H, NL))
+    tconf = make_conf('[trainer]\ntrainer = standard\nloss = CTC\ntrainlabels = 1\ntargets = text\n'
+                      'initial_learning_rate = 1e-3\nlearning_rate_decay = 0.1\n')
+    tr = trainer_factory.factory('standard')(tconf, None, mconf, None, None, None, 0, device=dev, seed=seed)
+    tr.num_steps = 100
+    return tr
+
+
+@pytest.mark.parametrize('B,T,H,NL,ragged', [(6, 40, 64, 2, True), (32, 200, 256, 2, True)])
+def test_dblstm_ctc_train_step_matches_oracle(B, T, H, NL, ragged):
+    """cfg-1 (DBLSTM 2x256 + CTC, 29 labels, 32x200x40): loss, every gradient and the Adam update."""
+    dev = torch.device('cuda', 0)
+    D, V = 40, 29
+    tr = _ctc_trainer(H, NL, V, dev)
+    tr.model.build({'features': D}, dev)
+    store = tr.model.store
+    x, lens, labels, ll = synthetic_ctc_batch(B, T, D, V, ragged)
+    params = store.to_numpy()
+    batch = ({'features': torch.from_numpy(x).to(dev)}, {'features': torch.from_numpy(lens).to(dev)},
+             {'text': torch.from_numpy(labels).to(dev)}, {'text': torch.from_numpy(ll).to(dev)})
+    loss, lr = tr.update(*batch)
+    # oracle (float64) on the same weights
+    layers = _dblstm_layers(params, NL)
+    lin = {'weights': params['DNNDecoder/text/outlayer/weights'], 'biases': params['DNNDecoder/text/outlayer/biases']}
+    enc, _, caches = O.dblstm_fwd(x, lens, layers)
+    logits = O.linear_fwd(enc, lin)
+    ref_loss, dlogits = O.ctc_loss_mean(logits, lens, labels, ll)
+    denc, glin = O.linear_bwd(enc, lin, dlogits)
+    _, glayers = O.dblstm_bwd(caches, denc)
+    assert abs(float(loss) - ref_loss) / abs(ref_loss) < TOL
+    grads = store.grads_numpy()
+    assert rel_err(grads['DNNDecoder/text/outlayer/weights'], glin['weights']) < TOL
+    assert rel_err(grads['DNNDecoder/text/outlayer/biases'], glin['biases']) < TOL
+    for l in range(NL):
+        base = 'DBLSTM/features/layer%d/bidirectional_rnn/%%s/layer_norm_basic_lstm_cell/%%s' % l
+        for d in ('fw', 'bw'):
+            for k in ('kernel', 'bias'):
+                assert rel_err(grads[base % (d, k)], glayers[l]['%s_%s' % (d, k)]) < 5 * TOL, (l, d, k)
+    # update: clip(-1,1) + TF-Adam step 1 at lr0 (global_step 0)
+    assert abs(lr - 1e-3) < 1e-12
+    new = store.to_numpy()
+    name = 'DBLSTM/features/layer0/bidirectional_rnn/fw/layer_norm_basic_lstm_cell/kernel'
+    th, _, _ = O.tf_adam_clip(params[name], glayers[0]['fw_kernel'], 0 * params[name], 0 * params[name], 1e-3, 1,
+                              dtype=np.float64)
+    # Adam's first step is lr*sign(g) wherever |g| >> eps; compare where the oracle gradient is not ~0
+    big = np.abs(glayers[0]['fw_kernel']) > 1e-6
+    assert np.abs(new[name] - th)[big].max() < 2e-6
+    assert tr.global_step == 1
+
+
+def test_logits_match_oracle_full_length():
+    dev = torch.device('cuda', 0)
+    B, T, D, H, NL, V = 16, 120, 40, 128, 3, 29
+    tr = _ctc_trainer(H, NL, V, dev, seed=11)
+    tr.model.build({'features': D}, dev)
+    x, lens, labels, ll = synthetic_ctc_batch(B, T, D, V, ragged=False)
+    params = tr.model.store.to_numpy()
+    with torch.no_grad():
+        logits, out_lens = tr.model({'features': torch.from_numpy(x).to(dev)},
+                                    {'features': torch.from_numpy(lens).to(dev)}, None, None, False)
+    layers = _dblstm_layers(params, NL)
+    lin = {'weights': params['DNNDecoder/text/outlayer/weights'], 'biases': params['DNNDecoder/text/outlayer/biases']}
+    enc, _, _ = O.dblstm_fwd(x, lens, layers)
+    ref = O.linear_fwd(enc, lin)
+    assert rel_err(logits['text'].cpu().numpy(), ref) < TOL
+    assert np.array_equal(out_lens['text'].cpu().numpy(), lens)
+
+
+def test_training_reduces_loss():
+    dev = torch.device('cuda', 0)
+    B, T, D, H, NL, V = 8, 60, 40, 64, 2, 29
+    tr = _ctc_trainer(H, NL, V, dev, seed=5)
+    tr.model.build({'features': D}, dev)
+    x, lens, labels, ll = synthetic_ctc_batch(B, T, D, V, ragged=True)
+    batch = ({'features': torch.from_numpy(x).to(dev)}, {'features': torch.from_numpy(lens).to(dev)},
+             {'text': torch.from_numpy(labels).to(dev)}, {'text': torch.from_numpy(ll).to(dev)})
+    losses = [float(tr.update(*batch)[0]) for _ in range(30)]
+    assert losses[-1] < 0.8 * losses[0], losses
