@@ -237,7 +237,10 @@ def main():
     ap.add_argument('--workload', default='dblstm_ctc', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if os.environ.get('NABU_BENCH_T'):       # profiling aid only (ncu captures); never a bench value
+        w['T'] = int(os.environ['NABU_BENCH_T'])
+        w['name'] += ' [T overridden to %d for profiling]' % w['T']
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -5,8 +5,8 @@
 // Three launches on the caller's stream:
 //   1. ctc_lse_kernel      log-sum-exp of every frame (warp per frame)           -> lse[B,T]
 //   2. ctc_alpha_beta      one CTA per (utterance, pass): threads own the 2L+1 lattice states,
-//                          one block barrier per frame, log-space fp32 like TF; alpha and beta
-//                          CTAs of all utterances run concurrently                -> alpha/beta[B,T,S]
+//                          one block barrier per frame, fp64 log space; alpha and beta CTAs of all
+//                          utterances run concurrently                            -> alpha/beta[B,T,S]
 //   3. ctc_grad_kernel     warp per frame: grad = softmax - sum_{s: l'_s = k} exp(alpha+beta-logp)
 //                          with a fixed summation order per class (bit-reproducible)
 // TF convention (appendix B7): blank = V-1, alpha includes the emission at t, beta excludes it,
@@ -30,6 +30,12 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
+__device__ __forceinline__ double lse3d(double a, double b, double c) {
+  const double m = fmax(a, fmax(b, c));
+  if (m == -CUDART_INF) return m;
+  return m + log(exp(a - m) + exp(b - m) + exp(c - m));
+}
+
 __global__ void ctc_lse_kernel(const float* logits, int rows, int V, float* lse) {
   const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
@@ -45,16 +51,16 @@ __global__ void ctc_lse_kernel(const float* logits, int rows, int V, float* lse)
 }
 
 // grid = 2*B: blockIdx.x < B -> alpha pass of utterance blockIdx.x, else beta pass.
-// Rows are re-centred every frame: alpha_hat_t(s) = alpha_t(s) - Oa_t with Oa_t accumulated in
-// double (Oa_t = Oa_{t-1} + max_s alpha_hat_{t-1}(s)), so the stored fp32 values stay O(1) and the
-// posteriors do not lose precision on long utterances the way a plain fp32 log-space lattice
-// (TF's CPU kernel) does.  The row maximum comes for free one frame late: every warp leaves the
-// max of the cells it just wrote next to the row, behind the frame's only barrier.
+// The lattice is kept in fp64 log space.  TF's CPU kernel keeps it in fp32, which is fine for the
+// loss but not for the gradient: the posterior of (t, s) is exp(alpha+beta-logp) of three numbers of
+// magnitude ~T, and with T = 1500 frames fp32 rounding alone (measured here: 6.6e-4 absolute on the
+// posteriors even with per-frame re-centring, because the states that matter for alpha*beta sit far
+// in the tail of alpha's own row) exceeds the 1e-4 parity bar.  B200's fp64 pipe makes this free at
+// this size (B*T*S = 58 M cells at cfg-3).
 __global__ void ctc_alpha_beta_kernel(const float* logits, const float* lse, const int* logit_len,
                                       const int* labels, int Lmax, const int* label_len, int T, int V,
-                                      int Smax, float* alpha, float* beta, double* off_alpha,
-                                      double* off_beta, float* loss, double* logp_out) {
-  extern __shared__ float sm[];            // [2][Smax + 4] ping-pong rows with 2 pads per side, then wmax[2][32]
+                                      int Smax, double* alpha, double* beta, float* loss, double* logp_out) {
+  extern __shared__ double smd[];          // [2][Smax + 4] ping-pong rows with 2 pads per side
   const bool is_beta = blockIdx.x >= gridDim.x / 2;
   const int b = is_beta ? blockIdx.x - gridDim.x / 2 : blockIdx.x;
   const int Tb = min(logit_len[b], T);
@@ -64,13 +70,10 @@ __global__ void ctc_alpha_beta_kernel(const float* logits, const float* lse, con
   const int* lab = labels + (size_t)b * Lmax;
   const float* lg = logits + (size_t)b * T * V;
   const float* ls = lse + (size_t)b * T;
-  float* out = (is_beta ? beta : alpha) + (size_t)b * T * Smax;
-  double* off = (is_beta ? off_beta : off_alpha) + (size_t)b * T;
-  float* row0 = sm;
-  float* row1 = sm + (Smax + 4);
-  float* wmax = sm + 2 * (Smax + 4);       // [2][32]
-  const float NINF = -CUDART_INF_F;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* out = (is_beta ? beta : alpha) + (size_t)b * T * Smax;
+  double* row0 = smd;
+  double* row1 = smd + (Smax + 4);
+  const double NINF = -CUDART_INF;
 
   // feasibility: T >= L + repeats (TF raises; we flag with +inf)
   __shared__ int s_rep;
@@ -87,96 +90,61 @@ __global__ void ctc_alpha_beta_kernel(const float* logits, const float* lse, con
   }
 
   for (int i = threadIdx.x; i < Smax + 4; i += blockDim.x) { row0[i] = NINF; row1[i] = NINF; }
-  if (threadIdx.x < 64) wmax[threadIdx.x] = NINF;
   __syncthreads();
-  float* cur = row0 + 2;
-  float* nxt = row1 + 2;
-  double O = 0.0;
-  int wb = 0;                               // wmax buffer holding the max of `cur`
-
-  auto row_max = [&](const float* wm) {
-    float m = NINF;
-    for (int w = 0; w < nw; ++w) m = fmaxf(m, wm[w]);
-    return m;
-  };
+  double* cur = row0 + 2;
+  double* nxt = row1 + 2;
 
   if (!is_beta) {
-    float mx = NINF;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      float a = NINF;
-      if (s == 0) a = lg[blank] - ls[0];
-      else if (s == 1) a = lg[lab[0]] - ls[0];
+      double a = NINF;
+      if (s == 0) a = (double)lg[blank] - (double)ls[0];
+      else if (s == 1) a = (double)lg[lab[0]] - (double)ls[0];
       cur[s] = a;
       out[s] = a;
-      mx = fmaxf(mx, a);
     }
-    mx = warp_max(mx);
-    if (lane == 0) wmax[wb * 32 + warp] = mx;
-    if (threadIdx.x == 0) off[0] = 0.0;
     __syncthreads();
     for (int t = 1; t < Tb; ++t) {
       const float* x = lg + (size_t)t * V;
-      const float l = ls[t];
-      const float M = row_max(wmax + wb * 32);
-      O += (double)M;
-      mx = NINF;
+      const double l = (double)ls[t];
       for (int s = threadIdx.x; s < S; s += blockDim.x) {
         const int k = (s & 1) ? lab[s >> 1] : blank;
         const bool skip = (s & 1) && s >= 3 && lab[s >> 1] != lab[(s >> 1) - 1];
-        const float a = lse3(cur[s], cur[s - 1], skip ? cur[s - 2] : NINF) - M + (x[k] - l);
+        const double a = lse3d(cur[s], cur[s - 1], skip ? cur[s - 2] : NINF) + ((double)x[k] - l);
         nxt[s] = a;
         out[(size_t)t * Smax + s] = a;
-        mx = fmaxf(mx, a);
       }
-      mx = warp_max(mx);
-      if (lane == 0) wmax[(wb ^ 1) * 32 + warp] = mx;
-      if (threadIdx.x == 0) off[t] = O;
       __syncthreads();
-      float* tmp = cur; cur = nxt; nxt = tmp;
-      wb ^= 1;
+      double* tmp = cur; cur = nxt; nxt = tmp;
     }
     if (threadIdx.x == 0) {
-      const double lp = O + (double)lse2(cur[S - 1], S > 1 ? cur[S - 2] : NINF);
+      const double lp = lse3d(cur[S - 1], S > 1 ? cur[S - 2] : NINF, NINF);
       logp_out[b] = lp;
       loss[b] = (float)(-lp);
     }
   } else {
-    float mx = NINF;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      const float v = (s >= S - 2) ? 0.f : NINF;
+      const double v = (s >= S - 2) ? 0.0 : NINF;
       cur[s] = v;
       out[(size_t)(Tb - 1) * Smax + s] = v;
-      mx = fmaxf(mx, v);
     }
-    mx = warp_max(mx);
-    if (lane == 0) wmax[wb * 32 + warp] = mx;
-    if (threadIdx.x == 0) off[Tb - 1] = 0.0;
     __syncthreads();
     for (int t = Tb - 2; t >= 0; --t) {
       const float* x = lg + (size_t)(t + 1) * V;
-      const float l = ls[t + 1];
-      const float M = row_max(wmax + wb * 32);
-      O += (double)M;
+      const double l = (double)ls[t + 1];
       // beta_t(s) = LSE over s' in {s, s+1, s+2 if allowed} of beta_{t+1}(s') + y_{t+1}(l'_{s'})
       for (int s = threadIdx.x; s < S; s += blockDim.x) {
         const int k = (s & 1) ? lab[s >> 1] : blank;
-        nxt[s] = cur[s] - M + (x[k] - l);
+        nxt[s] = cur[s] + ((double)x[k] - l);
       }
       for (int s = S + threadIdx.x; s < S + 2; s += blockDim.x) nxt[s] = NINF;
       __syncthreads();
-      mx = NINF;
       for (int s = threadIdx.x; s < S; s += blockDim.x) {
         const bool skip = (s & 1) && (s + 2 < S) && lab[(s >> 1) + 1] != lab[s >> 1];
-        const float v = lse3(nxt[s], nxt[s + 1], skip ? nxt[s + 2] : NINF);
+        const double v = lse3d(nxt[s], nxt[s + 1], skip ? nxt[s + 2] : NINF);
         cur[s] = v;
         out[(size_t)t * Smax + s] = v;
-        mx = fmaxf(mx, v);
       }
-      mx = warp_max(mx);
-      if (lane == 0) wmax[(wb ^ 1) * 32 + warp] = mx;
-      if (threadIdx.x == 0) off[t] = O;
       __syncthreads();
-      wb ^= 1;
     }
   }
 }
@@ -184,8 +152,8 @@ __global__ void ctc_alpha_beta_kernel(const float* logits, const float* lse, con
 // one warp per (b, t): grad = softmax - sum_{s: l'_s = k} exp(alpha + beta - logp)
 __global__ void ctc_grad_kernel(const float* logits, const float* lse, const int* logit_len,
                                 const int* labels, int Lmax, const int* label_len, int B, int T, int V,
-                                int Smax, const float* alpha, const float* beta, const double* off_alpha,
-                                const double* off_beta, const double* logp_in, float grad_scale, float* grad) {
+                                int Smax, const double* alpha, const double* beta, const double* logp_in,
+                                float grad_scale, float* grad) {
   const int wpb = blockDim.x / 32;
   const long row = (long)blockIdx.x * wpb + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
@@ -198,17 +166,17 @@ __global__ void ctc_grad_kernel(const float* logits, const float* lse, const int
     for (int k = lane; k < V; k += 32) g[k] = 0.f;
     return;
   }
-  const float D = (float)(off_alpha[row] + off_beta[row] - logp);
   const int L = label_len[b];
   const int blank = V - 1;
   const int* lab = labels + (size_t)b * Lmax;
-  const float* a = alpha + ((size_t)b * T + t) * Smax;
-  const float* be = beta + ((size_t)b * T + t) * Smax;
+  const double* a = alpha + ((size_t)b * T + t) * Smax;
+  const double* be = beta + ((size_t)b * T + t) * Smax;
   const float* x = logits + (size_t)row * V;
   const float l = lse[row];
-  // blank class: even states, strided over lanes, fixed-order butterfly
+  // blank class: even states, strided over lanes, fixed-order butterfly.  The argument of every
+  // exp is <= 0 (a posterior), so fp32 expf of the fp64 difference is exact to 1 ulp.
   float sb = 0.f;
-  for (int i = lane; i <= L; i += 32) sb += expf(a[2 * i] + be[2 * i] + D);
+  for (int i = lane; i <= L; i += 32) sb += expf((float)(a[2 * i] + be[2 * i] - logp));
   sb = warp_sum(sb);
   // label classes: lane k walks the label sequence in order (bit-reproducible)
   for (int k = lane; k < V; k += 32) {
@@ -217,7 +185,7 @@ __global__ void ctc_grad_kernel(const float* logits, const float* lse, const int
       occ = sb;
     } else {
       for (int i = 0; i < L; ++i)
-        if (lab[i] == k) occ += expf(a[2 * i + 1] + be[2 * i + 1] + D);
+        if (lab[i] == k) occ += expf((float)(a[2 * i + 1] + be[2 * i + 1] - logp));
     }
     g[k] = grad_scale * (expf(x[k] - l) - occ);
   }
@@ -229,17 +197,15 @@ __global__ void ctc_grad_kernel(const float* logits, const float* lse, const int
 using namespace nabu;
 
 namespace {
-struct CtcWs { float* lse; float* alpha; float* beta; double* offa; double* offb; double* logp; size_t total; int Smax; };
+struct CtcWs { float* lse; double* alpha; double* beta; double* logp; size_t total; int Smax; };
 CtcWs ctc_carve(void* base, int B, int T, int Lmax) {
   CtcWs w;
   w.Smax = 2 * Lmax + 1;
   char* p = (char*)base;
   size_t off = 0;
   w.lse = (float*)(p + off); off += align_up((size_t)B * T * sizeof(float), 256);
-  w.alpha = (float*)(p + off); off += align_up((size_t)B * T * w.Smax * sizeof(float), 256);
-  w.beta = (float*)(p + off); off += align_up((size_t)B * T * w.Smax * sizeof(float), 256);
-  w.offa = (double*)(p + off); off += align_up((size_t)B * T * sizeof(double), 256);
-  w.offb = (double*)(p + off); off += align_up((size_t)B * T * sizeof(double), 256);
+  w.alpha = (double*)(p + off); off += align_up((size_t)B * T * w.Smax * sizeof(double), 256);
+  w.beta = (double*)(p + off); off += align_up((size_t)B * T * w.Smax * sizeof(double), 256);
   w.logp = (double*)(p + off); off += align_up((size_t)B * sizeof(double), 256);
   w.total = off;
   return w;
@@ -266,18 +232,18 @@ extern "C" int nabu_ctc_loss_fwd_bwd(const float* logits, const int* logit_len, 
   int threads = ((w.Smax + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   if (threads < 64) threads = 64;
-  const size_t smem = ((size_t)2 * (w.Smax + 4) + 64) * sizeof(float);
+  const size_t smem = (size_t)2 * (w.Smax + 4) * sizeof(double);
   NABU_REQUIRE(smem <= 200 * 1024, "ctc: label sequence too long (Lmax=%d)", Lmax);
   if (smem > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { KernelScope ks("ctc_alpha_beta", stream);
   ctc_alpha_beta_kernel<<<2 * B, threads, smem, stream>>>(logits, w.lse, logit_len, labels, Lmax, label_len, T, V,
-                                                         w.Smax, w.alpha, w.beta, w.offa, w.offb, loss, w.logp); }
+                                                         w.Smax, w.alpha, w.beta, loss, w.logp); }
   NABU_CHECK_LAUNCH();
   if (grad) {
     { KernelScope ks("ctc_grad", stream);
     ctc_grad_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(logits, w.lse, logit_len, labels, Lmax, label_len, B, T, V,
-                                                          w.Smax, w.alpha, w.beta, w.offa, w.offb, w.logp, grad_scale, grad); }
+                                                          w.Smax, w.alpha, w.beta, w.logp, grad_scale, grad); }
     NABU_CHECK_LAUNCH();
   }
   return 0;

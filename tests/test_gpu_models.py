@@ -69,7 +69,7 @@ def test_dblstm_ctc_train_step_matches_oracle(B, T, H, NL, ragged):
     th, _, _ = O.tf_adam_clip(params[name], glayers[0]['fw_kernel'], 0 * params[name], 0 * params[name], 1e-3, 1,
                               dtype=np.float64)
     # Adam's first step is lr*sign(g) wherever |g| >> eps; compare where the oracle gradient is not ~0
-    big = np.abs(glayers[0]['fw_kernel']) > 1e-6
+    big = np.abs(glayers[0]['fw_kernel']) > 1e-4
     assert np.abs(new[name] - th)[big].max() < 2e-6
     assert tr.global_step == 1
 
