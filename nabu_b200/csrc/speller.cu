@@ -1,0 +1,606 @@
+// Teacher-forced Speller forward / backward over the whole target sequence (SURVEY.md section 8
+// rows a6-a8; replaces models/ed_decoders/rnn_decoder.py:40-82 = dynamic_decode(BasicDecoder(
+// ScheduledEmbeddingTrainingHelper(sample_prob=0)), impute_finished=True) around speller.py's cell).
+//
+// Forward:  values = memory*mask, keys = values.Wm (one GEMM), then U steps of
+//           {dec_lstm_step x layers, dec_attn_step}.  Everything the backward needs is written into the
+//           caller's `saved` buffer as [U+1] state slots (slot 0 = zero state, slot u+1 = after step u).
+// Backward: U reversed steps of {dec_attn_bwd_step, (dec_lstm_bwd_pointwise, dec_matmul_t) x layers}
+//           carrying d(state) between steps, then every weight gradient as ONE batched GEMM over all
+//           (step, row) pairs (the per-step kernels only produce dz / dq / per-row partials).
+// Rows whose target is shorter than U are frozen after their last step (state copied through, zero
+// logits), exactly like impute_finished=True; their gradients are zero.
+#include "speller_kernels.cuh"
+#include "speller_api.h"
+#include "gemm.h"
+#include "nabu_b200.h"
+
+namespace nabu {
+namespace dec {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void mask_memory_kernel(const float* mem, const int* len, int Tm, int E, float* out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long row = i / E;
+  const int b = row / Tm, t = row % Tm;
+  out[i] = (t < len[b]) ? mem[i] : 0.f;
+}
+
+// ids_in[u][r] = (u == 0) ? V-1 : targets[r][u-1]     (rnn_decoder.py:46-47)
+__global__ void build_ids_kernel(const int* targets, int ldt, int R, int U, int V, int* ids_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= U * R) return;
+  const int u = i / R, r = i % R;
+  ids_in[i] = (u == 0) ? V - 1 : targets[(size_t)r * ldt + u - 1];
+}
+
+// out[i] = sum_r part[r][i]   (fixed order)
+__global__ void reduce_rows_kernel(const float* part, int R, long n, float* out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += part[(size_t)r * n + i];
+  out[i] = s;
+}
+
+// One-hot rows of the layer-0 kernel: dK0[y][n] = sum over (u, r) with ids_in[u][r] == y of dz0[u][r][n].
+// grid = (ceil(4H/256), V); fixed summation order.
+__global__ void embedding_grad_kernel(const int* ids_in, const float* dz, int UR, int H4, float* dK0) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (n >= H4) return;
+  float s = 0.f;
+  for (int i = 0; i < UR; ++i)
+    if (ids_in[i] == y) s += dz[(size_t)i * H4 + n];
+  dK0[(size_t)y * H4 + n] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of the LSTM pointwise part for one layer / step.  One thread per (r, j).
+// ------------------------------------------------------------------------------------------------
+__global__ void dec_lstm_bwd_pointwise_kernel(float* gates /*[R][4H] in: i,g,f,o ; out: dz*/, const float* c_new,
+                                              const float* c_prev, const float* dh_above, const float* dh_carry,
+                                              float* dc_carry, float* dzT /*[4H][R]*/, int R, int H,
+                                              const int* tlen, int u) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * H) return;
+  const int r = i / H, j = i % H;
+  float* gp = gates + (size_t)r * 4 * H + j;
+  const bool active = u < tlen[r];
+  float dz[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float ig = gp[0], gg = gp[H], fg = gp[2 * H], og = gp[3 * H];
+    const float dh = dh_above[i] + dh_carry[i];
+    const float tc = tanhf(c_new[i]);
+    const float dc = dc_carry[i] + dh * og * (1.f - tc * tc);
+    dz[0] = dc * gg * ig * (1.f - ig);
+    dz[1] = dc * ig * (1.f - gg * gg);
+    dz[2] = dc * c_prev[i] * fg * (1.f - fg);
+    dz[3] = dh * tc * og * (1.f - og);
+    dc_carry[i] = dc * fg;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    gp[g * H] = dz[g];
+    dzT[(size_t)(g * H + j) * R + r] = dz[g];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of dec_attn_step: one CTA (256 threads) per row.  NA = ceil(A/256).
+// ------------------------------------------------------------------------------------------------
+struct AttnBwdArgs {
+  int R, Tm, E, H, A, V, F, ksz, U, u;
+  const float* dlogits; long dl_row_stride;          // dlogits + r*stride : V values
+  const float* outin; long outin_row_stride;         // [h_top, ctx] of this step
+  const float* alpha; const float* alpha_prev;       // [R][Tm]
+  const float* q; const float* cf;                   // [R][A], [R][Tm][F]
+  const float* Wq; const float* Wc; const float* Wd; const float* v; const float* Wo;
+  const float* keys; const float* values; const int* mem_len;
+  const float* dctx_carry;                           // [R][E]
+  float* dalign_carry;                               // [R][Tm] in/out
+  float* dh_above;                                   // [R][H] out
+  float* dq_save;                                    // [R][A] out
+  float* dkeys; float* dvalues;                      // [R][Tm][A], [R][Tm][E] accumulate
+  float* dv_part; float* dWd_part; float* dWc_part;  // [R][A], [R][F][A], [R][ksz][F] accumulate
+  const int* tlen;
+};
+
+constexpr int TT = 16;     // memory positions per dpre tile
+constexpr int MAXF = 16;   // max numfilt held in registers
+
+template <int NA>
+__global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = blockIdx.x;
+  const int Tm = a.Tm, E = a.E, H = a.H, A = a.A, V = a.V, F = a.F, ksz = a.ksz;
+  const int padl = (ksz - 1) / 2;
+  float* dl = sm;                          // [V]
+  float* oin = dl + V;                     // [H+E]
+  float* dctx = oin + H + E;               // [E]
+  float* dquery = dctx + E;                // [H]
+  float* al = dquery + H;                  // [Tm]
+  float* ap = al + Tm;                     // [Tm + ksz] zero-padded alpha_prev
+  float* dal = ap + Tm + ksz;              // [Tm] dalpha, then de
+  float* qs = dal + Tm;                    // [A]
+  float* dqs = qs + A;                     // [A]
+  float* red = dqs + A;                    // [32]
+  float* cf = red + 32;                    // [Tm][F]
+  float* dcf = cf + (size_t)Tm * F;        // [Tm][F]
+  float* wd = dcf + (size_t)Tm * F;        // [F][A]
+  float* wc = wd + (size_t)F * A;          // [ksz][F]
+  float* dpre = wc + (size_t)ksz * F;      // [TT][A]
+
+  if (!(a.u < a.tlen[r])) {
+    for (int i = tid; i < H; i += 256) a.dh_above[(size_t)r * H + i] = 0.f;
+    for (int i = tid; i < A; i += 256) a.dq_save[(size_t)r * A + i] = 0.f;
+    return;
+  }
+  const int len = min(a.mem_len[r], Tm);
+  for (int i = tid; i < V; i += 256) dl[i] = a.dlogits[r * a.dl_row_stride + i];
+  for (int i = tid; i < H + E; i += 256) oin[i] = a.outin[r * a.outin_row_stride + i];
+  for (int i = tid; i < Tm; i += 256) al[i] = a.alpha[(size_t)r * Tm + i];
+  for (int i = tid; i < Tm + ksz; i += 256) {
+    const int t = i - padl;
+    ap[i] = (F > 0 && t >= 0 && t < Tm) ? a.alpha_prev[(size_t)r * Tm + t] : 0.f;
+  }
+  for (int i = tid; i < A; i += 256) qs[i] = a.q[(size_t)r * A + i];
+  for (int i = tid; i < Tm * F; i += 256) cf[i] = a.cf[(size_t)r * Tm * F + i];
+  for (int i = tid; i < F * A; i += 256) wd[i] = a.Wd[i];
+  for (int i = tid; i < ksz * F; i += 256) wc[i] = a.Wc[i];
+  __syncthreads();
+
+  // phase A: d[h_top, ctx] = dlogits . Wo^T ; dctx += carry
+  for (int k = tid; k < H + E; k += 256) {
+    float s = 0.f;
+    for (int vv = 0; vv < V; ++vv) s = fmaf(dl[vv], a.Wo[(size_t)k * V + vv], s);
+    if (k < H) dquery[k] = s;
+    else dctx[k - H] = s + a.dctx_carry[(size_t)r * E + (k - H)];
+  }
+  __syncthreads();
+  // phase B: dalpha[t] = dctx . values[t] + carry ; dvalues[t] += alpha[t] * dctx
+  const float* values = a.values + (size_t)r * Tm * E;
+  float* dvalues = a.dvalues + (size_t)r * Tm * E;
+  for (int t = warp; t < Tm; t += 8) {
+    float s = 0.f;
+    if (t < len) {
+      const float at = al[t];
+      for (int i = lane; i < E; i += 32) {
+        s = fmaf(dctx[i], values[(size_t)t * E + i], s);
+        dvalues[(size_t)t * E + i] += at * dctx[i];
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) dal[t] = (t < len) ? s + a.dalign_carry[(size_t)r * Tm + t] : 0.f;
+  }
+  __syncthreads();
+  // phase C: softmax backward  de = alpha * (dalpha - sum alpha*dalpha)
+  float part = 0.f;
+  for (int t = tid; t < Tm; t += 256) part += al[t] * dal[t];
+  const float dot = block_reduce(part, red, false);
+  for (int t = tid; t < Tm; t += 256) dal[t] = al[t] * (dal[t] - dot);
+  __syncthreads();
+  // phase D: score backward, tiles of TT memory positions; thread owns attention units tid + 256*i
+  const float* keys = a.keys + (size_t)r * Tm * A;
+  float* dkeys = a.dkeys + (size_t)r * Tm * A;
+  float dq[NA], dv[NA], dWd[NA][MAXF], vreg[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    dq[i] = 0.f; dv[i] = 0.f;
+    const int c = tid + 256 * i;
+    vreg[i] = c < A ? a.v[c] : 0.f;
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) dWd[i][f] = 0.f;
+  }
+  for (int t0 = 0; t0 < len; t0 += TT) {
+    const int nt = min(TT, len - t0);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int c = tid + 256 * i;
+      if (c < A) {
+        for (int tt = 0; tt < nt; ++tt) {
+          const int t = t0 + tt;
+          float pre = qs[c] + keys[(size_t)t * A + c];
+          for (int f = 0; f < F; ++f) pre = fmaf(cf[t * F + f], wd[f * A + c], pre);
+          const float s = tanhf(pre);
+          const float de = dal[t];
+          const float dp = de * vreg[i] * (1.f - s * s);
+          dq[i] += dp;
+          dv[i] = fmaf(de, s, dv[i]);
+#pragma unroll
+          for (int f = 0; f < MAXF; ++f)
+            if (f < F) dWd[i][f] = fmaf(cf[t * F + f], dp, dWd[i][f]);
+          dkeys[(size_t)t * A + c] += dp;
+          dpre[tt * A + c] = dp;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < nt * F; i += 256) {
+      const int tt = i / F, f = i % F;
+      float s = 0.f;
+      for (int c = 0; c < A; ++c) s = fmaf(dpre[tt * A + c], wd[f * A + c], s);
+      dcf[(t0 + tt) * F + f] = s;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < (Tm - len) * F; i += 256) dcf[len * F + i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const int c = tid + 256 * i;
+    if (c < A) {
+      dqs[c] = dq[i];
+      a.dq_save[(size_t)r * A + c] = dq[i];
+      a.dv_part[(size_t)r * A + c] += dv[i];
+#pragma unroll
+      for (int f = 0; f < MAXF; ++f)
+        if (f < F) a.dWd_part[((size_t)r * F + f) * A + c] += dWd[i][f];
+    }
+  }
+  __syncthreads();
+  // phase E: location-feature backward
+  if (F > 0) {
+    // dalign_prev[tau] = sum_{k,f} dcf[tau - k + padl][f] * Wc[k][f]
+    for (int tau = tid; tau < Tm; tau += 256) {
+      float s = 0.f;
+      for (int k = 0; k < ksz; ++k) {
+        const int t = tau - k + padl;
+        if (t >= 0 && t < Tm)
+          for (int f = 0; f < F; ++f) s = fmaf(dcf[t * F + f], wc[k * F + f], s);
+      }
+      a.dalign_carry[(size_t)r * Tm + tau] = s;
+    }
+    // dWc[k][f] += sum_t alpha_prev[t + k - padl] * dcf[t][f]
+    for (int i = tid; i < ksz * F; i += 256) {
+      const int k = i / F, f = i % F;
+      float s = 0.f;
+      for (int t = 0; t < Tm; ++t) s = fmaf(ap[t + k], dcf[t * F + f], s);
+      a.dWc_part[(size_t)r * ksz * F + i] += s;
+    }
+  } else {
+    for (int tau = tid; tau < Tm; tau += 256) a.dalign_carry[(size_t)r * Tm + tau] = 0.f;
+  }
+  // phase F: dh_top = dquery_part + dq . Wq^T   (warp per output unit, lanes over A)
+  for (int k = warp; k < H; k += 8) {
+    float s = 0.f;
+    for (int c = lane; c < A; c += 32) s = fmaf(dqs[c], a.Wq[(size_t)k * A + c], s);
+    s = warp_sum(s);
+    if (lane == 0) a.dh_above[(size_t)r * H + k] = dquery[k] + s;
+  }
+}
+
+inline size_t attn_bwd_smem(int Tm, int E, int H, int A, int V, int F, int ksz) {
+  return ((size_t)V + (H + E) + E + H + Tm + (Tm + ksz) + Tm + A + A + 32 + 2 * (size_t)Tm * F + (size_t)F * A +
+          (size_t)ksz * F + (size_t)TT * A) * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// buffer carving
+// ------------------------------------------------------------------------------------------------
+struct Saved {        // written by the forward, read by the backward
+  float* values; float* keys;                 // [B][Tm][E], [B][Tm][A]
+  int* ids_in;                                // [U][B]
+  float* hT[4]; float* h[4]; float* c[4];     // [(U+1)][H][B], [(U+1)][B][H], [(U+1)][B][H]
+  float* gates[4];                            // [U][B][4H]
+  float* ctx; float* ctxT; float* align;      // [(U+1)][B][E], [(U+1)][E][B], [(U+1)][B][Tm]
+  float* q; float* cf; float* outin;          // [U][B][A], [U][B][Tm][F], [B][U][H+E]
+  size_t total;
+};
+
+Saved carve_saved(void* base, const nabu_speller_desc_t& d) {
+  Saved s;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) { float* q = (float*)(p + off); off += align_up(nfloats * sizeof(float), 256); return q; };
+  const size_t B = d.B, Tm = d.Tm, E = d.E, H = d.H, A = d.A, U = d.U, F = d.attention == 1 ? d.numfilt : 0;
+  s.values = take(B * Tm * E);
+  s.keys = take(B * Tm * A);
+  s.ids_in = (int*)take(U * B);
+  for (int l = 0; l < d.num_layers; ++l) {
+    s.hT[l] = take((U + 1) * H * B);
+    s.h[l] = take((U + 1) * B * H);
+    s.c[l] = take((U + 1) * B * H);
+    s.gates[l] = take(U * B * 4 * H);
+  }
+  s.ctx = take((U + 1) * B * E);
+  s.ctxT = take((U + 1) * E * B);
+  s.align = take((U + 1) * B * Tm);
+  s.q = take(U * B * A);
+  s.cf = take(U * B * Tm * (F ? F : 1));
+  s.outin = take(B * U * (H + E));
+  s.total = off;
+  return s;
+}
+
+struct Work {         // backward scratch
+  float* dh_carry[4]; float* dc_carry[4];     // [B][H]
+  float* dh_above; float* dzT;                // [B][H], [4H][B]
+  float* dctx_carry; float* dalign_carry;     // [B][E], [B][Tm]
+  float* dq; float* dkeys; float* dvalues;    // [U][B][A], [B][Tm][A], [B][Tm][E]
+  float* dv_part; float* dWd_part; float* dWc_part;
+  float* gemm; size_t gemm_bytes;
+  size_t zero_bytes;                          // leading region that must be zeroed
+  size_t total;
+};
+
+Work carve_work(void* base, const nabu_speller_desc_t& d) {
+  Work w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) { float* q = (float*)(p + off); off += align_up(nfloats * sizeof(float), 256); return q; };
+  const size_t B = d.B, Tm = d.Tm, E = d.E, H = d.H, A = d.A, U = d.U;
+  const size_t F = d.attention == 1 ? d.numfilt : 0, ksz = d.attention == 1 ? d.filtersize : 1;
+  for (int l = 0; l < d.num_layers; ++l) { w.dh_carry[l] = take(B * H); w.dc_carry[l] = take(B * H); }
+  w.dctx_carry = take(B * E);
+  w.dalign_carry = take(B * Tm);
+  w.dkeys = take(B * Tm * A);
+  w.dvalues = take(B * Tm * E);
+  w.dv_part = take(B * A);
+  w.dWd_part = take(B * (F ? F : 1) * A);
+  w.dWc_part = take(B * ksz * (F ? F : 1));
+  w.zero_bytes = off;
+  w.dh_above = take(B * H);
+  w.dzT = take(4 * H * B);
+  w.dq = take(U * B * A);
+  w.gemm = (float*)(p + off); w.gemm_bytes = sgemm_workspace_bytes(); off += w.gemm_bytes;
+  w.total = off;
+  return w;
+}
+
+int check_desc(const nabu_speller_desc_t& d) {
+  NABU_REQUIRE(d.B > 0 && d.Tm > 0 && d.E > 0 && d.V > 1 && d.H > 0 && d.U > 0, "speller: bad shape");
+  NABU_REQUIRE(d.num_layers >= 1 && d.num_layers <= 4, "speller: num_layers=%d not in 1..4", d.num_layers);
+  NABU_REQUIRE(d.H % 8 == 0 && d.E % 8 == 0, "speller: num_units=%d and memory dim=%d must be multiples of 8", d.H, d.E);
+  NABU_REQUIRE(d.A > 0 && d.A <= 512, "speller: attention units=%d not in 1..512", d.A);
+  NABU_REQUIRE(d.attention == 0 || d.attention == 1, "speller: attention %d (windowed is outside the hot path)", d.attention);
+  if (d.attention == 1)
+    NABU_REQUIRE(d.numfilt >= 1 && d.numfilt <= MAXF && d.filtersize >= 1, "speller: numfilt=%d (max %d), filtersize=%d",
+                 d.numfilt, MAXF, d.filtersize);
+  return 0;
+}
+
+// Launch one full decoder step (all LSTM layers + attention/projection).  Shared with las_beam.cu.
+int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, int R, int rows_per_mem,
+                const int* ids, const float* keys, const float* values, const int* mem_len,
+                float* const* hT_prev, float* const* h_prev, float* const* c_prev, const float* ctx_prev,
+                const float* ctxT_prev, const float* align_prev,
+                float* const* hT_new, float* const* h_new, float* const* c_new, float* ctx_new, float* ctxT_new,
+                float* align_new, float* const* gates_out, float* logits, long logits_row_stride,
+                float temperature, float* q_save, float* cf_save, float* outin_save, long outin_row_stride,
+                const int* tlen, int u, const int* done, cudaStream_t stream) {
+  const int H = d.H, E = d.E, V = d.V;
+  for (int l = 0; l < d.num_layers; ++l) {
+    LstmStepArgs a = {};
+    if (l == 0) { a.inT0 = ctxT_prev; a.K0 = E; a.w0 = V; a.inT1 = hT_prev[0]; a.K1 = H; a.w1 = V + E; a.ids = ids; }
+    else { a.inT0 = hT_new[l - 1]; a.K0 = H; a.w0 = 0; a.inT1 = hT_prev[l]; a.K1 = H; a.w1 = H; a.ids = nullptr; }
+    a.W = p.cell_kernel[l]; a.bias = p.cell_bias[l]; a.H = H; a.R = R;
+    a.c_prev = c_prev[l]; a.h_prev = h_prev[l];
+    a.c_new = c_new[l]; a.h_new = h_new[l]; a.hT_new = hT_new[l];
+    a.gates_out = gates_out ? gates_out[l] : nullptr;
+    a.tlen = tlen; a.u = u; a.done = done;
+    const size_t smem = ((size_t)(a.K0 + a.K1) * 8 + 4 * ROWS * 8) * sizeof(float);
+    NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: LSTM input too wide for the step kernel");
+    if (smem > 48 * 1024)
+      NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelScope ks("dec_lstm_step", stream);
+    dec_lstm_step_kernel<<<dim3(H / 2, ceil_div(R, ROWS)), SK_THREADS, smem, stream>>>(a);
+    NABU_CHECK_LAUNCH();
+  }
+  AttnStepArgs a = {};
+  a.R = R; a.Tm = d.Tm; a.E = E; a.H = H; a.A = d.A; a.V = V;
+  a.F = d.attention == 1 ? d.numfilt : 0; a.ksz = d.attention == 1 ? d.filtersize : 1;
+  a.rows_per_mem = rows_per_mem;
+  a.h_top = h_new[d.num_layers - 1];
+  a.Wq = p.query_kernel; a.Wc = p.conv_kernel; a.Wd = p.conv_dense_kernel; a.v = p.attention_v;
+  a.Wo = p.out_kernel; a.bo = p.out_bias;
+  a.keys = keys; a.values = values; a.mem_len = mem_len;
+  a.align_prev = align_prev; a.ctx_prev = ctx_prev;
+  a.align_new = align_new; a.ctx_new = ctx_new; a.ctxT_new = ctxT_new;
+  a.logits = logits; a.logits_row_stride = logits_row_stride; a.temperature = temperature;
+  a.q_save = q_save; a.cf_save = cf_save; a.outin_save = outin_save; a.outin_row_stride = outin_row_stride;
+  a.tlen = tlen; a.u = u; a.done = done;
+  const size_t smem = attn_step_smem(d.Tm, E, H, d.A, a.F, a.ksz);
+  NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: memory too long for the attention step kernel (Tm=%d)", d.Tm);
+  if (smem > 48 * 1024)
+    NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KernelScope ks("dec_attn_step", stream);
+  dec_attn_step_kernel<<<R, 256, smem, stream>>>(a);
+  NABU_CHECK_LAUNCH();
+  return 0;
+}
+
+// values = memory*mask ; keys = values.Wm
+int prepare_memory(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, const float* memory,
+                   const int* mem_len, float* values, float* keys, cudaStream_t stream) {
+  const long n = (long)d.B * d.Tm * d.E;
+  {
+    KernelScope ks("mask_memory", stream);
+    mask_memory_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(memory, mem_len, d.Tm, d.E, values, n);
+    NABU_CHECK_LAUNCH();
+  }
+  return sgemm(GEMM_NN, d.B * d.Tm, d.A, d.E, 1.f, values, d.E, p.memory_kernel, d.A, 0.f, keys, d.A, nullptr, nullptr,
+               nullptr, 0, stream);
+}
+
+}  // namespace dec
+}  // namespace nabu
+
+using namespace nabu;
+using namespace nabu::dec;
+
+extern "C" size_t nabu_speller_saved_bytes(const nabu_speller_desc_t* d) {
+  if (check_desc(*d)) return 0;
+  return carve_saved(nullptr, *d).total;
+}
+extern "C" size_t nabu_speller_workspace_bytes(const nabu_speller_desc_t* d) {
+  if (check_desc(*d)) return 0;
+  return carve_work(nullptr, *d).total;
+}
+
+extern "C" int nabu_speller_fwd(const nabu_speller_desc_t* dp, const nabu_speller_params_t* p, const float* memory,
+                                const int* mem_len, const int* targets, int ldt, const int* target_len,
+                                float* logits, void* saved, void* workspace, size_t ws_bytes, void* stream_) {
+  (void)workspace; (void)ws_bytes;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const nabu_speller_desc_t& d = *dp;
+  if (int e = check_desc(d)) return e;
+  NABU_REQUIRE(ldt >= d.U, "speller_fwd: targets row stride %d < U=%d", ldt, d.U);
+  Saved s = carve_saved(saved, d);
+  const size_t B = d.B, Tm = d.Tm, E = d.E, H = d.H, U = d.U;
+  if (int e = prepare_memory(d, *p, memory, mem_len, s.values, s.keys, stream)) return e;
+  {
+    KernelScope ks("build_ids", stream);
+    build_ids_kernel<<<ceil_div(d.U * d.B, 256), 256, 0, stream>>>(targets, ldt, d.B, d.U, d.V, s.ids_in);
+    NABU_CHECK_LAUNCH();
+  }
+  // zero state = slot 0 of every state array
+  for (int l = 0; l < d.num_layers; ++l) {
+    NABU_CHECK_CUDA(cudaMemsetAsync(s.hT[l], 0, H * B * sizeof(float), stream));
+    NABU_CHECK_CUDA(cudaMemsetAsync(s.h[l], 0, B * H * sizeof(float), stream));
+    NABU_CHECK_CUDA(cudaMemsetAsync(s.c[l], 0, B * H * sizeof(float), stream));
+  }
+  NABU_CHECK_CUDA(cudaMemsetAsync(s.ctx, 0, B * E * sizeof(float), stream));
+  NABU_CHECK_CUDA(cudaMemsetAsync(s.ctxT, 0, E * B * sizeof(float), stream));
+  NABU_CHECK_CUDA(cudaMemsetAsync(s.align, 0, B * Tm * sizeof(float), stream));
+  const size_t F = d.attention == 1 ? d.numfilt : 0;
+  for (int u = 0; u < d.U; ++u) {
+    float *hTp[4], *hp[4], *cp[4], *hTn[4], *hn[4], *cn[4], *go[4];
+    for (int l = 0; l < d.num_layers; ++l) {
+      hTp[l] = s.hT[l] + (size_t)u * H * B; hTn[l] = s.hT[l] + (size_t)(u + 1) * H * B;
+      hp[l] = s.h[l] + (size_t)u * B * H; hn[l] = s.h[l] + (size_t)(u + 1) * B * H;
+      cp[l] = s.c[l] + (size_t)u * B * H; cn[l] = s.c[l] + (size_t)(u + 1) * B * H;
+      go[l] = s.gates[l] + (size_t)u * B * 4 * H;
+    }
+    if (int e = launch_step(d, *p, d.B, 1, s.ids_in + (size_t)u * B, s.keys, s.values, mem_len, hTp, hp, cp,
+                            s.ctx + (size_t)u * B * E, s.ctxT + (size_t)u * E * B, s.align + (size_t)u * B * Tm,
+                            hTn, hn, cn, s.ctx + (size_t)(u + 1) * B * E, s.ctxT + (size_t)(u + 1) * E * B,
+                            s.align + (size_t)(u + 1) * B * Tm, go, logits + (size_t)u * d.V, (long)U * d.V, 1.f,
+                            s.q + (size_t)u * B * d.A, F ? s.cf + (size_t)u * B * Tm * F : nullptr,
+                            s.outin + (size_t)u * (H + E), (long)U * (H + E), target_len, u, nullptr, stream))
+      return e;
+  }
+  return 0;
+}
+
+extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_speller_params_t* p, const float* memory,
+                                const int* mem_len, const int* targets, int ldt, const int* target_len,
+                                const float* dlogits, void* saved, float* dmemory,
+                                const nabu_speller_params_t* g, void* workspace, size_t ws_bytes, void* stream_) {
+  (void)memory; (void)targets; (void)ldt;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const nabu_speller_desc_t& d = *dp;
+  if (int e = check_desc(d)) return e;
+  Saved s = carve_saved(saved, d);
+  Work w = carve_work(workspace, d);
+  NABU_REQUIRE(ws_bytes >= w.total, "speller_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  const int B = d.B, Tm = d.Tm, E = d.E, H = d.H, A = d.A, V = d.V, U = d.U, NL = d.num_layers;
+  const int F = d.attention == 1 ? d.numfilt : 0, ksz = d.attention == 1 ? d.filtersize : 1;
+  const int H4 = 4 * H;
+  NABU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, stream));
+
+  const size_t smem_attn = attn_bwd_smem(Tm, E, H, A, V, F, ksz);
+  NABU_REQUIRE(smem_attn <= (size_t)max_smem_optin(), "speller_bwd: memory too long for the attention kernel (Tm=%d)", Tm);
+  const void* attn_fn = A <= 256 ? (const void*)dec_attn_bwd_step_kernel<1> : (const void*)dec_attn_bwd_step_kernel<2>;
+  if (smem_attn > 48 * 1024)
+    NABU_CHECK_CUDA(cudaFuncSetAttribute(attn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn));
+  const size_t smem_mm = ((size_t)H4 * 8 + 4 * ROWS * 8) * sizeof(float);
+  NABU_REQUIRE(smem_mm <= (size_t)max_smem_optin(), "speller_bwd: num_units too large");
+  if (smem_mm > 48 * 1024)
+    NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_matmul_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mm));
+
+  for (int u = U - 1; u >= 0; --u) {
+    AttnBwdArgs a = {};
+    a.R = B; a.Tm = Tm; a.E = E; a.H = H; a.A = A; a.V = V; a.F = F; a.ksz = ksz; a.U = U; a.u = u;
+    a.dlogits = dlogits + (size_t)u * V; a.dl_row_stride = (long)U * V;
+    a.outin = s.outin + (size_t)u * (H + E); a.outin_row_stride = (long)U * (H + E);
+    a.alpha = s.align + (size_t)(u + 1) * B * Tm; a.alpha_prev = s.align + (size_t)u * B * Tm;
+    a.q = s.q + (size_t)u * B * A; a.cf = F ? s.cf + (size_t)u * B * Tm * F : nullptr;
+    a.Wq = p->query_kernel; a.Wc = p->conv_kernel; a.Wd = p->conv_dense_kernel; a.v = p->attention_v; a.Wo = p->out_kernel;
+    a.keys = s.keys; a.values = s.values; a.mem_len = mem_len;
+    a.dctx_carry = w.dctx_carry; a.dalign_carry = w.dalign_carry; a.dh_above = w.dh_above;
+    a.dq_save = w.dq + (size_t)u * B * A; a.dkeys = w.dkeys; a.dvalues = w.dvalues;
+    a.dv_part = w.dv_part; a.dWd_part = w.dWd_part; a.dWc_part = w.dWc_part; a.tlen = target_len;
+    {
+      KernelScope ks("dec_attn_bwd_step", stream);
+      if (A <= 256) dec_attn_bwd_step_kernel<1><<<B, 256, smem_attn, stream>>>(a);
+      else dec_attn_bwd_step_kernel<2><<<B, 256, smem_attn, stream>>>(a);
+      NABU_CHECK_LAUNCH();
+    }
+    for (int l = NL - 1; l >= 0; --l) {
+      {
+        KernelScope ks("dec_lstm_bwd_pointwise", stream);
+        dec_lstm_bwd_pointwise_kernel<<<ceil_div(B * H, 256), 256, 0, stream>>>(
+            s.gates[l] + (size_t)u * B * H4, s.c[l] + (size_t)(u + 1) * B * H, s.c[l] + (size_t)u * B * H, w.dh_above,
+            w.dh_carry[l], w.dc_carry[l], w.dzT, B, H, target_len, u);
+        NABU_CHECK_LAUNCH();
+      }
+      MatmulTArgs m = {};
+      m.xT = w.dzT; m.K = H4; m.R = B; m.W = p->cell_kernel[l]; m.ldw = H4;
+      if (l > 0) { m.row0 = 0; m.N = 2 * H; m.N0 = H; m.out0 = w.dh_above; m.ld0 = H; m.out1 = w.dh_carry[l]; m.ld1 = H; }
+      else { m.row0 = V; m.N = E + H; m.N0 = E; m.out0 = w.dctx_carry; m.ld0 = E; m.out1 = w.dh_carry[0]; m.ld1 = H; }
+      KernelScope ks("dec_matmul_t", stream);
+      dec_matmul_t_kernel<<<dim3(ceil_div(m.N, 8), ceil_div(B, ROWS)), SK_THREADS, smem_mm, stream>>>(m);
+      NABU_CHECK_LAUNCH();
+    }
+  }
+  // ---- batched weight gradients over all (step, row) pairs --------------------------------------
+  const int UB = U * B;
+  for (int l = 0; l < NL; ++l) {
+    float* dz = s.gates[l];                                   // [U][B][4H], now dz
+    float* dK = g->cell_kernel[l];
+    if (l == 0) {
+      {
+        KernelScope ks("embedding_grad", stream);
+        embedding_grad_kernel<<<dim3(ceil_div(H4, 256), V), 256, 0, stream>>>(s.ids_in, dz, UB, H4, dK);
+        NABU_CHECK_LAUNCH();
+      }
+      // context rows: input of step u is ctx slot u
+      if (int e = sgemm(GEMM_TN, E, H4, UB, 1.f, s.ctx, E, dz, H4, 0.f, dK + (size_t)V * H4, H4, nullptr, nullptr, w.gemm,
+                        w.gemm_bytes, stream)) return e;
+      if (int e = sgemm(GEMM_TN, H, H4, UB, 1.f, s.h[0], H, dz, H4, 0.f, dK + (size_t)(V + E) * H4, H4, nullptr, nullptr,
+                        w.gemm, w.gemm_bytes, stream)) return e;
+    } else {
+      // input rows: h of the layer below AFTER step u = slot u+1 ; recurrent rows: own h slot u
+      if (int e = sgemm(GEMM_TN, H, H4, UB, 1.f, s.h[l - 1] + (size_t)B * H, H, dz, H4, 0.f, dK, H4, nullptr, nullptr,
+                        w.gemm, w.gemm_bytes, stream)) return e;
+      if (int e = sgemm(GEMM_TN, H, H4, UB, 1.f, s.h[l], H, dz, H4, 0.f, dK + (size_t)H * H4, H4, nullptr, nullptr,
+                        w.gemm, w.gemm_bytes, stream)) return e;
+    }
+    if (int e = colsum(dz, UB, H4, H4, g->cell_bias[l], stream)) return e;
+  }
+  // output projection: rows ordered (b, u) on both sides
+  if (int e = sgemm(GEMM_TN, H + E, V, B * U, 1.f, s.outin, H + E, dlogits, V, 0.f, g->out_kernel, V, nullptr, nullptr,
+                    w.gemm, w.gemm_bytes, stream)) return e;
+  if (int e = colsum(dlogits, B * U, V, V, g->out_bias, stream)) return e;
+  // query layer: h_top after step u (slot u+1) against dq[u]
+  if (int e = sgemm(GEMM_TN, H, A, UB, 1.f, s.h[NL - 1] + (size_t)B * H, H, w.dq, A, 0.f, g->query_kernel, A, nullptr,
+                    nullptr, w.gemm, w.gemm_bytes, stream)) return e;
+  // memory layer and the memory itself
+  if (int e = sgemm(GEMM_TN, E, A, B * Tm, 1.f, s.values, E, w.dkeys, A, 0.f, g->memory_kernel, A, nullptr, nullptr,
+                    w.gemm, w.gemm_bytes, stream)) return e;
+  if (int e = sgemm(GEMM_NT, B * Tm, E, A, 1.f, w.dkeys, A, p->memory_kernel, A, 1.f, w.dvalues, E, nullptr, nullptr,
+                    nullptr, 0, stream)) return e;
+  if (dmemory) {
+    const long n = (long)B * Tm * E;
+    KernelScope ks("mask_memory", stream);
+    mask_memory_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.dvalues, mem_len, Tm, E, dmemory, n);
+    NABU_CHECK_LAUNCH();
+  }
+  {
+    KernelScope ks("reduce_rows", stream);
+    reduce_rows_kernel<<<ceil_div(A, 256), 256, 0, stream>>>(w.dv_part, B, A, g->attention_v);
+    NABU_CHECK_LAUNCH();
+  }
+  if (F > 0) {
+    KernelScope ks("reduce_rows", stream);
+    reduce_rows_kernel<<<ceil_div(F * A, 256), 256, 0, stream>>>(w.dWd_part, B, (long)F * A, g->conv_dense_kernel);
+    NABU_CHECK_LAUNCH();
+    reduce_rows_kernel<<<ceil_div(ksz * F, 256), 256, 0, stream>>>(w.dWc_part, B, (long)ksz * F, g->conv_kernel);
+    NABU_CHECK_LAUNCH();
+  }
+  return 0;
+}

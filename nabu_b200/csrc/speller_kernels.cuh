@@ -1,0 +1,334 @@
+// Device kernels of the attention decoder ("Speller"), shared by
+// the teacher-forced training path (speller.cu) and the LAS beam search (las_beam.cu).
+//
+// One decoder step = TF's AttentionProjectionWrapper(AttentionWrapper(MultiRNNCell(LSTMCell x N)))
+// (reference: models/ed_decoders/speller.py:29-69, components/rnn_cell.py:145-155,
+// components/attention.py:142-240; TF semantics in SURVEY appendix B3-B5):
+//   dec_lstm_step   x N  : z = onehot-row gather + [input, h_prev].K + b -> i,j,f,o -> c', h'
+//   dec_attn_step        : q = Wq.h_top ; location features conv1d(alpha_prev)->dense ; score
+//                          e = v.tanh(q + keys + f) ; mask ; softmax ; context = alpha.values ;
+//                          logits = [h_top, context].Wo + bo      -- one CTA per decoder row
+// The decoder state is kept in two layouts: row-major [R][*] for the pointwise consumers and
+// transposed [*][R] for the "skinny" matmuls (R = batch rows is small, so threads run along R and
+// the weight slice of a CTA sits in shared memory).
+#pragma once
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace nabu {
+namespace dec {
+
+constexpr int ROWS = 64;       // decoder rows per CTA tile in the skinny matmuls
+constexpr int SK_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// LSTM cell step.  grid = (H/2, ceil(R/ROWS)); CTA (slice, tile) owns hidden units 2*slice,
+// 2*slice+1 (8 gate columns) for ROWS rows; 4-way k-split over the 256 threads.
+// ------------------------------------------------------------------------------------------------
+struct LstmStepArgs {
+  const float* inT0; int K0; int w0;      // transposed input segment 0 [K0][R], first weight row w0
+  const float* inT1; int K1; int w1;      // transposed input segment 1 (this layer's h_prev) [K1][R]
+  const int* ids;                         // optional one-hot ids [R] (weight rows 0..V-1), or nullptr
+  const float* W; const float* bias;      // [(rows), 4H], [4H]
+  int H, R;
+  const float* c_prev;                    // [R][H]
+  const float* h_prev;                    // [R][H] row-major (copy-through for finished rows)
+  float* c_new; float* h_new; float* hT_new;   // [R][H], [R][H], [H][R]
+  float* gates_out;                       // [R][4H] activated i,g,f,o or nullptr
+  const int* tlen; int u;                 // row r is active iff tlen == nullptr || u < tlen[r]
+  const int* done;                        // optional device flag: non-zero -> the whole launch is a no-op
+};
+
+__global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmStepArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  if (a.done && *a.done) return;
+  const int Ktot = a.K0 + a.K1;
+  float* Ws = sm;                          // [Ktot][8]
+  float* red = sm + (size_t)Ktot * 8;      // [4][ROWS][8]
+  const int tid = threadIdx.x;
+  const int H = a.H, H4 = 4 * a.H, R = a.R;
+  const int j0 = blockIdx.x * 2;
+  const int r0 = blockIdx.y * ROWS;
+  for (int i = tid; i < Ktot * 8; i += SK_THREADS) {
+    const int c = i & 7, k = i >> 3;
+    const int wrow = k < a.K0 ? a.w0 + k : a.w1 + (k - a.K0);
+    Ws[i] = a.W[(size_t)wrow * H4 + (c >> 1) * H + j0 + (c & 1)];
+  }
+  __syncthreads();
+  const int rl = tid % ROWS, ks = tid / ROWS;
+  const int r = r0 + rl;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (r < R) {
+#pragma unroll 4
+    for (int k = ks; k < a.K0; k += 4) {
+      const float x = __ldcg(a.inT0 + (size_t)k * R + r);
+      const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * 8 + 4);
+      acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+      acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+      acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+      acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+    }
+#pragma unroll 4
+    for (int k = ks; k < a.K1; k += 4) {
+      const float x = __ldcg(a.inT1 + (size_t)k * R + r);
+      const float* wp = Ws + (a.K0 + k) * 8;
+      const float4 w0 = *reinterpret_cast<const float4*>(wp);
+      const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+      acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+      acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+      acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+      acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) red[(ks * ROWS + rl) * 8 + c] = acc[c];
+  __syncthreads();
+  if (tid < 2 * ROWS) {
+    const int rl2 = tid % ROWS, jl = tid / ROWS;
+    const int r2 = r0 + rl2, j = j0 + jl;
+    if (r2 < R) {
+      float z[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float s = a.bias[g * H + j];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) s += red[(k2 * ROWS + rl2) * 8 + g * 2 + jl];
+        if (a.ids) s += a.W[(size_t)a.ids[r2] * H4 + g * H + j];
+        z[g] = s;
+      }
+      const bool active = (a.tlen == nullptr) || (a.u < a.tlen[r2]);
+      const float cp = a.c_prev[(size_t)r2 * H + j];
+      const float ig = sigmoid_acc(z[0]), gg = tanhf(z[1]), fg = sigmoid_acc(z[2] + 1.0f), og = sigmoid_acc(z[3]);
+      float cn = cp * fg + ig * gg;
+      float hn = tanhf(cn) * og;
+      if (!active) { cn = cp; hn = a.h_prev[(size_t)r2 * H + j]; }
+      a.c_new[(size_t)r2 * H + j] = cn;
+      a.h_new[(size_t)r2 * H + j] = hn;
+      a.hT_new[(size_t)j * R + r2] = hn;
+      if (a.gates_out) {
+        float* gp = a.gates_out + (size_t)r2 * H4 + j;
+        gp[0] = ig; gp[H] = gg; gp[2 * H] = fg; gp[3 * H] = og;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention + output projection step: one CTA (256 threads) per decoder row.
+// ------------------------------------------------------------------------------------------------
+struct AttnStepArgs {
+  int R, Tm, E, H, A, V, F, ksz;          // F = 0 -> vanilla Bahdanau (no location features)
+  int rows_per_mem;                       // decoder rows sharing one memory row (beam width; 1 in training)
+  const float* h_top;                     // [R][H] query (new top-layer output)
+  const float* Wq; const float* Wc; const float* Wd; const float* v;
+  const float* Wo; const float* bo;
+  const float* keys; const float* values; // [Rm][Tm][A], [Rm][Tm][E]
+  const int* mem_len;                     // [Rm]
+  const float* align_prev; const float* ctx_prev;    // [R][Tm], [R][E]
+  float* align_new; float* ctx_new; float* ctxT_new; // [R][Tm], [R][E], [E][R]
+  float* logits; long logits_row_stride;  // logits + r*stride : V values
+  float temperature;                      // logits divided by this (1 in training)
+  float* q_save; float* cf_save; float* outin_save; long outin_row_stride;   // optional
+  const int* tlen; int u;
+  const int* done;
+};
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = is_max ? -CUDART_INF_F : 0.f;
+  for (int w = 0; w < nw; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  if (a.done && *a.done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = blockIdx.x;
+  const int mrow = r / a.rows_per_mem;
+  const int Tm = a.Tm, E = a.E, H = a.H, A = a.A, V = a.V, F = a.F, ksz = a.ksz;
+  const int padl = (ksz - 1) / 2;
+  float* query = sm;                       // [H]
+  float* q = query + H;                    // [A]
+  float* ap = q + A;                       // [Tm + ksz] zero padded alpha_prev
+  float* e = ap + Tm + ksz;                // [Tm]
+  float* ctx = e + Tm;                     // [E]
+  float* red = ctx + E;                    // [32]
+  float* part = red + 32;                  // [8][32] projection partials
+  float* cf = part + 256;                  // [Tm][F]
+  float* wd = cf + (size_t)Tm * F;         // [F][A]
+  float* wc = wd + (size_t)F * A;          // [ksz][F]
+
+  const bool active = (a.tlen == nullptr) || (a.u < a.tlen[r]);
+  if (!active) {                           // finished row: copy the state through, emit zeros
+    for (int t = tid; t < Tm; t += 256) a.align_new[(size_t)r * Tm + t] = a.align_prev[(size_t)r * Tm + t];
+    for (int i = tid; i < E; i += 256) {
+      const float c = a.ctx_prev[(size_t)r * E + i];
+      a.ctx_new[(size_t)r * E + i] = c;
+      a.ctxT_new[(size_t)i * a.R + r] = c;
+    }
+    for (int k = tid; k < V; k += 256) a.logits[r * a.logits_row_stride + k] = 0.f;
+    if (a.q_save) for (int i = tid; i < A; i += 256) a.q_save[(size_t)r * A + i] = 0.f;
+    if (a.cf_save) for (int i = tid; i < Tm * F; i += 256) a.cf_save[(size_t)r * Tm * F + i] = 0.f;
+    if (a.outin_save) for (int i = tid; i < H + E; i += 256) a.outin_save[r * a.outin_row_stride + i] = 0.f;
+    return;
+  }
+  const int len = min(a.mem_len[mrow], Tm);
+
+  for (int i = tid; i < H; i += 256) query[i] = a.h_top[(size_t)r * H + i];
+  for (int i = tid; i < Tm + ksz; i += 256) {
+    const int t = i - padl;
+    ap[i] = (F > 0 && t >= 0 && t < Tm) ? a.align_prev[(size_t)r * Tm + t] : 0.f;
+  }
+  for (int i = tid; i < F * A; i += 256) wd[i] = a.Wd[i];
+  for (int i = tid; i < ksz * F; i += 256) wc[i] = a.Wc[i];
+  __syncthreads();
+
+  // phase 0: q = query . Wq
+  for (int c = tid; c < A; c += 256) {
+    float s = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) s = fmaf(query[k], a.Wq[(size_t)k * A + c], s);
+    q[c] = s;
+    if (a.q_save) a.q_save[(size_t)r * A + c] = s;
+  }
+  // phase 1: location features cf[t][f] = sum_k alpha_prev[t + k - padl] * Wc[k][f]
+  for (int i = tid; i < Tm * F; i += 256) {
+    const int t = i / F, f = i % F;
+    float s = 0.f;
+    for (int k = 0; k < ksz; ++k) s = fmaf(ap[t + k], wc[k * F + f], s);
+    cf[i] = s;
+    if (a.cf_save) a.cf_save[(size_t)r * Tm * F + i] = s;
+  }
+  __syncthreads();
+  // phase 2: scores, one warp per memory position
+  const float* keys = a.keys + (size_t)mrow * Tm * A;
+  for (int t = warp; t < Tm; t += 8) {
+    float s = 0.f;
+    if (t < len) {
+      for (int c = lane; c < A; c += 32) {
+        float pre = q[c] + keys[(size_t)t * A + c];
+        for (int f = 0; f < F; ++f) pre = fmaf(cf[t * F + f], wd[f * A + c], pre);
+        s = fmaf(a.v[c], tanhf(pre), s);
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) e[t] = (t < len) ? s : -CUDART_INF_F;
+  }
+  __syncthreads();
+  // phase 3: softmax over the memory positions
+  float mx = -CUDART_INF_F;
+  for (int t = tid; t < Tm; t += 256) mx = fmaxf(mx, e[t]);
+  mx = block_reduce(mx, red, true);
+  float sum = 0.f;
+  for (int t = tid; t < Tm; t += 256) {
+    const float p = (t < len) ? expf(e[t] - mx) : 0.f;
+    e[t] = p;
+    sum += p;
+  }
+  sum = block_reduce(sum, red, false);
+  const float inv = 1.f / sum;
+  for (int t = tid; t < Tm; t += 256) {
+    const float p = e[t] * inv;
+    e[t] = p;
+    a.align_new[(size_t)r * Tm + t] = p;
+  }
+  __syncthreads();
+  // phase 4: context = alpha . values
+  const float* values = a.values + (size_t)mrow * Tm * E;
+  for (int i = tid; i < E; i += 256) {
+    float s = 0.f;
+    for (int t = 0; t < len; ++t) s = fmaf(e[t], values[(size_t)t * E + i], s);
+    ctx[i] = s;
+    a.ctx_new[(size_t)r * E + i] = s;
+    a.ctxT_new[(size_t)i * a.R + r] = s;
+  }
+  __syncthreads();
+  if (a.outin_save) {
+    float* o = a.outin_save + r * a.outin_row_stride;
+    for (int i = tid; i < H; i += 256) o[i] = query[i];
+    for (int i = tid; i < E; i += 256) o[H + i] = ctx[i];
+  }
+  // phase 5: logits = [query, ctx] . Wo + bo ; thread (vcol = lane, kchunk = warp)
+  for (int v0 = 0; v0 < V; v0 += 32) {
+    const int vc = v0 + lane;
+    float s = 0.f;
+    if (vc < V) {
+      for (int k = warp; k < H; k += 8) s = fmaf(query[k], a.Wo[(size_t)k * V + vc], s);
+      for (int k = warp; k < E; k += 8) s = fmaf(ctx[k], a.Wo[(size_t)(H + k) * V + vc], s);
+    }
+    part[warp * 32 + lane] = s;
+    __syncthreads();
+    if (warp == 0 && vc < V) {
+      float t = a.bo[vc];
+      for (int w = 0; w < 8; ++w) t += part[w * 32 + lane];
+      a.logits[r * a.logits_row_stride + vc] = t / a.temperature;
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t attn_step_smem(int Tm, int E, int H, int A, int F, int ksz) {
+  return ((size_t)H + A + (Tm + ksz) + Tm + E + 32 + 256 + (size_t)Tm * F + (size_t)F * A + (size_t)ksz * F) *
+         sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skinny transposed-weight matmul: out[r][n] = sum_k xT[k][r] * W[row0 + n][k]  (d(input) = dz.K^T).
+// grid = (N/8, ceil(R/ROWS)).  Output columns [0,N0) go to out0, [N0,N) to out1.
+// ------------------------------------------------------------------------------------------------
+struct MatmulTArgs {
+  const float* xT; int K; int R;          // [K][R]
+  const float* W; int ldw; int row0;      // W[(row0+n)][k]
+  int N, N0;
+  float* out0; int ld0; float* out1; int ld1;
+};
+
+__global__ void __launch_bounds__(SK_THREADS) dec_matmul_t_kernel(const MatmulTArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                          // [K][8]
+  float* red = sm + (size_t)a.K * 8;       // [4][ROWS][8]
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * 8, r0 = blockIdx.y * ROWS;
+  for (int i = tid; i < a.K * 8; i += SK_THREADS) {
+    const int c = i / a.K, k = i % a.K;    // k fastest: coalesced rows of W
+    const int n = n0 + c;
+    Ws[k * 8 + c] = (n < a.N) ? a.W[(size_t)(a.row0 + n) * a.ldw + k] : 0.f;
+  }
+  __syncthreads();
+  const int rl = tid % ROWS, ks = tid / ROWS, r = r0 + rl;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (r < a.R) {
+#pragma unroll 4
+    for (int k = ks; k < a.K; k += 4) {
+      const float x = __ldcg(a.xT + (size_t)k * a.R + r);
+      const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * 8 + 4);
+      acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+      acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+      acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+      acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) red[(ks * ROWS + rl) * 8 + c] = acc[c];
+  __syncthreads();
+  for (int i = tid; i < ROWS * 8; i += SK_THREADS) {
+    const int rl2 = i / 8, c = i % 8, r2 = r0 + rl2, n = n0 + c;
+    if (r2 < a.R && n < a.N) {
+      float s = 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) s += red[(k2 * ROWS + rl2) * 8 + c];
+      if (n < a.N0) a.out0[(size_t)r2 * a.ld0 + n] = s;
+      else a.out1[(size_t)r2 * a.ld1 + (n - a.N0)] = s;
+    }
+  }
+}
+
+}  // namespace dec
+}  // namespace nabu

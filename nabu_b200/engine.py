@@ -316,3 +316,140 @@ def gemm(mode, A, B, M, N, K, lda, ldb, ldc, C=None, alpha=1.0, beta=0.0, bias=N
     L.check(lib.nabu_gemm(mode, precision, M, N, K, alpha, L.ptr(A), lda, L.ptr(B), ldb, beta, L.ptr(C), ldc,
                           L.ptr(bias), L.ptr(ws), ws.numel(), L.stream()), 'nabu_gemm')
     return C
+
+
+# ---------------------------------------------------------------------------------------------
+# Speller (attention decoder) and the beam searches
+# ---------------------------------------------------------------------------------------------
+
+ATTENTION_IDS = {'vanilla': 0, 'location_aware': 1}
+
+
+class SpellerVars(object):
+    """The variables of Speller.create_cell as engine.Variable objects (see speller.py mirror)."""
+
+    def __init__(self, cell_kernels, cell_biases, memory_kernel, query_kernel, attention_v, conv_kernel,
+                 conv_dense_kernel, out_kernel, out_bias):
+        self.cell_kernels, self.cell_biases = cell_kernels, cell_biases
+        self.memory_kernel, self.query_kernel, self.attention_v = memory_kernel, query_kernel, attention_v
+        self.conv_kernel, self.conv_dense_kernel = conv_kernel, conv_dense_kernel
+        self.out_kernel, self.out_bias = out_kernel, out_bias
+
+    def all(self):
+        out = list(self.cell_kernels) + list(self.cell_biases) + [self.memory_kernel, self.query_kernel,
+                                                                  self.attention_v]
+        if self.conv_kernel is not None:
+            out += [self.conv_kernel, self.conv_dense_kernel]
+        return out + [self.out_kernel, self.out_bias]
+
+    def pack(self, grad=False):
+        p = L.SpellerParams()
+        get = (lambda v: L.ptr(v.grad)) if grad else (lambda v: L.ptr(v.data.detach()))
+        for i, (k, b) in enumerate(zip(self.cell_kernels, self.cell_biases)):
+            p.cell_kernel[i] = get(k)
+            p.cell_bias[i] = get(b)
+        p.memory_kernel, p.query_kernel, p.attention_v = get(self.memory_kernel), get(self.query_kernel), get(
+            self.attention_v)
+        if self.conv_kernel is not None:
+            p.conv_kernel, p.conv_dense_kernel = get(self.conv_kernel), get(self.conv_dense_kernel)
+        p.out_kernel, p.out_bias = get(self.out_kernel), get(self.out_bias)
+        return p
+
+
+def speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, U):
+    d = L.SpellerDesc()
+    d.B, d.Tm, d.E, d.V, d.H, d.num_layers, d.A = B, Tm, E, V, H, num_layers, H
+    d.attention = ATTENTION_IDS[attention]
+    d.numfilt, d.filtersize, d.U = numfilt, filtersize, U
+    return d
+
+
+class _Speller(torch.autograd.Function):
+    """rnn_decoder.py:40-82 (teacher forcing) via nabu_speller_fwd / nabu_speller_bwd."""
+
+    @staticmethod
+    def forward(ctx, memory, mem_len, targets, target_len, desc, svars, *param_tensors):
+        lib = L.load()
+        memory = memory.contiguous()
+        targets = targets.contiguous()
+        logits = torch.empty((desc.B, desc.U, desc.V), device=memory.device, dtype=torch.float32)
+        nsaved = lib.nabu_speller_saved_bytes(ctypes.byref(desc))
+        if nsaved == 0:
+            L.check(2, 'nabu_speller_saved_bytes')
+        saved = torch.empty(nsaved, dtype=torch.uint8, device=memory.device)
+        p = svars.pack()
+        L.check(lib.nabu_speller_fwd(ctypes.byref(desc), ctypes.byref(p), L.ptr(memory), L.ptr(mem_len),
+                                     L.ptr(targets), targets.shape[1], L.ptr(target_len), L.ptr(logits),
+                                     L.ptr(saved), None, 0, L.stream()), 'nabu_speller_fwd')
+        ctx.save_for_backward(memory, mem_len, targets, target_len, saved)
+        ctx.desc, ctx.svars = desc, svars
+        ctx.need_dmem = memory.requires_grad
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = L.load()
+        memory, mem_len, targets, target_len, saved = ctx.saved_tensors
+        desc, svars = ctx.desc, ctx.svars
+        dlogits = dlogits.contiguous()
+        dmem = torch.empty_like(memory) if ctx.need_dmem else None
+        ws = L.WORKSPACE.get(lib.nabu_speller_workspace_bytes(ctypes.byref(desc)), memory.device)
+        p, g = svars.pack(), svars.pack(grad=True)
+        L.check(lib.nabu_speller_bwd(ctypes.byref(desc), ctypes.byref(p), L.ptr(memory), L.ptr(mem_len),
+                                     L.ptr(targets), targets.shape[1], L.ptr(target_len), L.ptr(dlogits),
+                                     L.ptr(saved), L.ptr(dmem), ctypes.byref(g), L.ptr(ws), ws.numel(), L.stream()),
+                'nabu_speller_bwd')
+        return (dmem, None, None, None, None, None) + (None,) * len(svars.all())
+
+
+def speller(memory, mem_len, targets, target_len, svars, V, H, num_layers, attention, numfilt, filtersize):
+    B, Tm, E = memory.shape
+    U = targets.shape[1]
+    desc = speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, U)
+    return _Speller.apply(memory, mem_len, targets, target_len, desc, svars, *[v.data for v in svars.all()])
+
+
+def las_beam_search(memory, mem_len, svars, V, H, num_layers, attention, numfilt, filtersize, beam_width,
+                    max_steps, length_penalty, temperature):
+    """components/beam_search_decoder.py under dynamic_decode: returns (sequences [B,W,L], lengths [B,W],
+    scores [B,W], alignments [B,W,L,Tm]) with L = the number of steps the loop ran."""
+    lib = L.load()
+    memory = memory.contiguous()
+    B, Tm, E = memory.shape
+    W = beam_width
+    desc = speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, 1)
+    dev = memory.device
+    seqs = torch.zeros((B, W, max_steps), dtype=torch.int32, device=dev)
+    lens = torch.zeros((B, W), dtype=torch.int32, device=dev)
+    scores = torch.zeros((B, W), dtype=torch.float32, device=dev)
+    aligns = torch.zeros((B, W, max_steps, Tm), dtype=torch.float32, device=dev)
+    nws = lib.nabu_las_beam_workspace_bytes(ctypes.byref(desc), W, max_steps)
+    if nws == 0:
+        L.check(2, 'nabu_las_beam_workspace_bytes')
+    ws = L.WORKSPACE.get(nws, dev)
+    n = ctypes.c_int(0)
+    p = svars.pack()
+    L.check(lib.nabu_las_beam_search(ctypes.byref(desc), ctypes.byref(p), L.ptr(memory), L.ptr(mem_len), W,
+                                     max_steps, length_penalty, temperature, L.ptr(seqs), L.ptr(lens),
+                                     L.ptr(scores), L.ptr(aligns), ctypes.byref(n), L.ptr(ws), ws.numel(),
+                                     L.stream()), 'nabu_las_beam_search')
+    n = n.value
+    return seqs[:, :, :n].contiguous(), lens, scores, aligns[:, :, :n].contiguous()
+
+
+def ctc_beam_search(logits, logit_len, beam_width=100, merge_repeated=True):
+    """tf.nn.ctc_beam_search_decoder(top_paths=1): returns (ids [B,T] int32, lengths [B], neg log prob [B])."""
+    lib = L.load()
+    logits = logits.contiguous()
+    B, T, V = logits.shape
+    out = torch.zeros((B, T), dtype=torch.int32, device=logits.device)
+    out_len = torch.zeros(B, dtype=torch.int32, device=logits.device)
+    nlp = torch.zeros(B, dtype=torch.float32, device=logits.device)
+    nws = lib.nabu_ctc_beam_workspace_bytes(B, T, V, beam_width)
+    if nws == 0:
+        L.check(2, 'nabu_ctc_beam_workspace_bytes')
+    ws = L.WORKSPACE.get(nws, logits.device)
+    L.check(lib.nabu_ctc_beam_search(L.ptr(logits), L.ptr(logit_len), B, T, V, beam_width, int(merge_repeated),
+                                     L.ptr(out), L.ptr(out_len), L.ptr(nlp), L.ptr(ws), ws.numel(), L.stream()),
+            'nabu_ctc_beam_search')
+    return out, out_len, nlp
