@@ -14,7 +14,7 @@ from abc import ABCMeta, abstractmethod
 import torch
 import torch.distributed as dist
 
-from ... import engine
+from ... import engine, parallel
 from ...tools.default_conf import apply_defaults, defaults_path
 from ..models.model import Model
 from . import loss_functions
@@ -60,8 +60,7 @@ class Trainer(object, metaclass=ABCMeta):
         if extra is not None:
             loss = loss + extra
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(model.store.grad, op=dist.ReduceOp.SUM)
+        parallel.allreduce_sum_(model.store.grad)        # the step's only collective
         lr = self.learning_rate()
         # clip AFTER the reduction so the update equals the reference's at the global batch size
         engine.clip_adam_step(model.store, lr, self.global_step + 1, clip=1.0, grad_scale=1.0 / self.world)
