@@ -2,12 +2,14 @@
 // -> tf.nn.ctc_beam_search_decoder(beam_width=100, top_paths=1, merge_repeated=True), which TF-1.8 only
 // runs on the CPU: tensorflow/core/util/ctc/ctc_beam_search.h, restated in SURVEY appendix B8).
 //
-// One CTA per utterance walks its frames.  TF's Step() inserts candidates one by one into a bounded
-// top-N heap; because a child's score never exceeds its parent's, and the heap's bottom only rises,
-// the leaf set after a frame is exactly the `beam_width` best of
-//     { updated existing leaves }  U  { (leaf b, label c) children that are not currently leaves },
-// so the frame is evaluated in parallel: every thread scores candidates, a bitonic sort on
-// (score desc, index asc) picks the survivors.  The prefix tree lives in global memory as
+// One CTA per utterance walks its frames.  Per frame the existing leaves are updated in parallel, but
+// the "grow new leaves" phase is replayed in TF's exact order (branches by descending oldp, labels
+// ascending) by one warp: TF's Step() has an order-dependent side effect -- a rejected child gets
+// oldp.Reset(), and when that child is itself a leaf that was evicted earlier in the same frame and has
+// not had its turn as a branch yet, it silently loses its chance to grow -- so "the beam_width best of
+// all candidates" is NOT what the reference computes (measured: 1 in 4 random utterances differs).
+// The warp keeps the bounded top-N as a flat array + its current bottom (warp arg-min), scores the
+// labels of one branch across lanes and settles them with ballots.  The prefix tree lives in global memory as
 // (parent, label) arrays plus an open-addressing hash (parent, label) -> node, so a prefix that drops
 // out and later re-enters is the SAME node, as in TF (its children keep their parent link).
 #include "common.cuh"
@@ -17,7 +19,7 @@
 namespace nabu {
 namespace {
 
-constexpr int CB_THREADS = 256;
+constexpr int CB_THREADS = 128;
 constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 
 __device__ __forceinline__ float lse_tf(float a, float b) {     // ctc_loss_util.h LogSumExp
@@ -61,27 +63,33 @@ __device__ int hash_find_or_insert(const UttBuf& u, int parent, int label, int V
   }
 }
 
-// dynamic smem layout (W = beam width, NS = sort size, V classes)
-//   float old_t/old_b/old_l/new_t/new_b/new_l [W]; int slot_node[W]; int sel_node[W]; float sel_val[3][W]
-//   unsigned long long sortbuf[NS]; float x[V]; unsigned char active_child[W*V]
+// dynamic smem layout (W = beam width, V classes):
+//   float old_t/old_b/old_l/new_t/new_b/new_l/tmp_t/tmp_b/tmp_l [W]; float ent_val[W];
+//   int slot_node[W], tmp_node[W], ent_ref[W]; int alive[W], dead_old[W]; float x[V];
+//   unsigned short child_slot[W*V]
+constexpr unsigned short NO_CHILD = 0xFFFFu;
+
 __global__ void __launch_bounds__(CB_THREADS) ctc_beam_kernel(
-    const float* logits, const int* logit_len, int T, int V, int W, int NS, int merge_repeated,
+    const float* logits, const int* logit_len, int T, int V, int W, int merge_repeated,
     int* g_node_parent, int* g_node_label, int* g_node_slot, unsigned long long* g_hkeys, int* g_hvals,
     int* g_node_count, int nmax, int hcap, int* out_ids, int* out_len, float* out_neg_logprob) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int blank = V - 1;
   const float NINF = -CUDART_INF_F;
-  unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(smraw);
-  float* old_t = reinterpret_cast<float*>(sortbuf + NS);
+  float* old_t = reinterpret_cast<float*>(smraw);
   float* old_b = old_t + W; float* old_l = old_b + W;
   float* new_t = old_l + W; float* new_b = new_t + W; float* new_l = new_b + W;
-  float* sv_t = new_l + W; float* sv_b = sv_t + W; float* sv_l = sv_b + W;
-  int* slot_node = reinterpret_cast<int*>(sv_l + W);
-  int* sel_node = slot_node + W;
-  float* x = reinterpret_cast<float*>(sel_node + W);
-  unsigned char* active_child = reinterpret_cast<unsigned char*>(x + V);
-  __shared__ int s_nleaf;
+  float* tmp_t = new_l + W; float* tmp_b = tmp_t + W; float* tmp_l = tmp_b + W;
+  float* ent_val = tmp_l + W;
+  int* slot_node = reinterpret_cast<int*>(ent_val + W);
+  int* tmp_node = slot_node + W;
+  int* ent_ref = tmp_node + W;
+  int* alive = ent_ref + W;
+  int* dead_old = alive + W;
+  float* x = reinterpret_cast<float*>(dead_old + W);
+  unsigned short* child_slot = reinterpret_cast<unsigned short*>(x + V);
+  __shared__ int s_nleaf, s_n;
   __shared__ float s_max;
 
   UttBuf u;
@@ -106,22 +114,21 @@ __global__ void __launch_bounds__(CB_THREADS) ctc_beam_kernel(
   const float* lg = logits + (size_t)b * T * V;
 
   for (int t = 0; t < Tb; ++t) {
-    const int nleaf = s_nleaf;
-    // x = logits[t] - max   (Step(): "remove the max for stability")
-    if (tid < 32) {
+    const int nleaf = s_nleaf;          // leaves are stored sorted by newp.total, descending (Extract())
+    // ---- A: x = logits[t] - max   (Step(): "remove the max for stability") ------------------------
+    if (warp == 0) {
       float m = NINF;
-      for (int k = tid; k < V; k += 32) m = fmaxf(m, lg[(size_t)t * V + k]);
+      for (int k = lane; k < V; k += 32) m = fmaxf(m, lg[(size_t)t * V + k]);
       m = warp_max(m);
-      if (tid == 0) s_max = m;
+      if (lane == 0) s_max = m;
     }
-    for (int i = tid; i < W * V; i += CB_THREADS) active_child[i] = 0;
+    for (int i = tid; i < W * V; i += CB_THREADS) child_slot[i] = NO_CHILD;
     __syncthreads();
     for (int k = tid; k < V; k += CB_THREADS) x[k] = lg[(size_t)t * V + k] - s_max;
-    // oldp = newp
+    // ---- B: oldp = newp -------------------------------------------------------------------------------
     for (int i = tid; i < nleaf; i += CB_THREADS) { old_t[i] = new_t[i]; old_b[i] = new_b[i]; old_l[i] = new_l[i]; }
     __syncthreads();
-    // existing leaves: extend by blank / repeat of their own label; mark the (parent slot, label) pairs that
-    // are leaves already so they are not spawned again
+    // ---- C: existing leaves extend by blank / by a repeat of their own label --------------------------
     for (int i = tid; i < nleaf; i += CB_THREADS) {
       const int node = slot_node[i];
       float nl = old_l[i];
@@ -129,95 +136,119 @@ __global__ void __launch_bounds__(CB_THREADS) ctc_beam_kernel(
         const int label = u.node_label[node];
         const int par = u.node_parent[node];
         const int ps = u.node_slot[par];
-        if (ps >= 0) {
+        if (ps >= 0) {                                      // parent->Active()
           const int plabel = u.node_label[par];
           const float prev = (label == plabel) ? old_b[ps] : old_t[ps];
           nl = lse_tf(nl, prev);
-          active_child[ps * V + label] = 1;
+          child_slot[ps * V + label] = (unsigned short)i;   // this (branch, label) child is a leaf already
         }
         nl = nl + x[label];
       }
       const float nb = old_t[i] + x[blank];
-      new_l[i] = nl; new_b[i] = nb; new_t[i] = lse_tf(nb, nl);
+      const float nt = lse_tf(nb, nl);
+      new_l[i] = nl; new_b[i] = nb; new_t[i] = nt;
+      ent_val[i] = nt; ent_ref[i] = i; alive[i] = 1; dead_old[i] = 0;
     }
     __syncthreads();
-    // candidates -> sort keys.  index space: [0, W) existing leaves, W + i*V + c child c of leaf i.
-    for (int i = tid; i < NS; i += CB_THREADS) {
-      float val = NINF;
-      if (i < W) {
-        if (i < nleaf) val = new_t[i];
-      } else {
-        const int j = i - W, li = j / V, c = j % V;
-        if (li < nleaf && c != blank && !active_child[li * V + c]) {
-          const int node = slot_node[li];
-          const int label = (node == 0) ? -1 : u.node_label[node];
-          const float prev = (c == label) ? old_b[li] : old_t[li];
-          val = x[c] + prev;
+    // ---- D: "grow new leaves", in TF's order: branches by descending oldp, labels ascending.  One warp
+    //      replays the bounded top-N insertions; lanes hold the labels of the current branch. ----------
+    if (warp == 0) {
+      int n = nleaf;
+      float bot_val = NINF; int bot_idx = -1;
+      auto find_bottom = [&]() {
+        float bv = CUDART_INF_F; int bi = 0x7fffffff;
+        for (int k = lane; k < n; k += 32) {
+          const float v = ent_val[k];
+          if (v < bv || (v == bv && k < bi)) { bv = v; bi = k; }
         }
-      }
-      sortbuf[i] = ((unsigned long long)f2ord(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-    }
-    __syncthreads();
-    // bitonic sort, descending
-    for (int k = 2; k <= NS; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < NS; i += CB_THREADS) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const unsigned long long a = sortbuf[i], c2 = sortbuf[ixj];
-            const bool desc = ((i & k) == 0);
-            if (desc ? (a < c2) : (a > c2)) { sortbuf[i] = c2; sortbuf[ixj] = a; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        bot_val = bv; bot_idx = bi;
+      };
+      if (n == W) find_bottom();
+      for (int i = 0; i < nleaf; ++i) {
+        const float ot = old_t[i], ob = old_b[i];
+        // is_candidate(b->oldp); a branch whose oldp was Reset() by the quirk below has total = log 0
+        if (dead_old[i] || !(ot > NINF)) continue;
+        if (n == W && !(ot > bot_val)) continue;
+        const int bnode = slot_node[i];
+        const int blabel = (bnode == 0) ? -1 : u.node_label[bnode];
+        for (int c0 = 0; c0 < blank; c0 += 32) {
+          const int c = c0 + lane;
+          const bool has = c < blank;
+          const int cs = has ? (int)child_slot[i * V + c] : (int)NO_CHILD;
+          const float val = has ? x[c] + ((c == blabel) ? ob : ot) : NINF;
+          unsigned remaining = __ballot_sync(0xffffffffu, has);
+          while (remaining) {
+            const bool mine = (remaining >> lane) & 1u;
+            const bool active_now = mine && cs != (int)NO_CHILD && alive[cs];
+            const bool pass = mine && !active_now && val > NINF && (n < W || val > bot_val);
+            const unsigned pmask = __ballot_sync(0xffffffffu, pass);
+            const int L = pmask ? (__ffs(pmask) - 1) : 32;
+            // labels before L are settled now: an inactive child that is not a candidate gets
+            // oldp.Reset()/newp.Reset() -- if that child is itself a pending branch it will not grow
+            if (mine && lane < L && !active_now && cs != (int)NO_CHILD) dead_old[cs] = 1;
+            if (L == 32) break;
+            if (lane == L) {
+              int pos;
+              if (n < W) {
+                pos = n;
+              } else {
+                pos = bot_idx;
+                const int ref = ent_ref[pos];
+                if (ref < W) alive[ref] = 0;              // bottom->newp.Reset()
+              }
+              ent_val[pos] = val;
+              ent_ref[pos] = W + i * V + c;
+            }
+            __syncwarp();
+            if (n < W) ++n;
+            if (n == W) find_bottom();
+            remaining &= ~((2u << L) - 1u);               // lanes <= L are done
           }
+          __syncwarp();
         }
-        __syncthreads();
       }
+      if (lane == 0) s_n = n;
     }
-    // survivors: the first W entries with a finite score
+    __syncthreads();
+    // ---- E: materialise the survivors -------------------------------------------------------------------
+    const int n = s_n;
     for (int i = tid; i < nleaf; i += CB_THREADS) u.node_slot[slot_node[i]] = -1;
     __syncthreads();
-    const unsigned ninf_ord = f2ord(NINF);
-    for (int k = tid; k < W; k += CB_THREADS) {
-      const unsigned long long key = sortbuf[k];
-      const unsigned ord = (unsigned)(key >> 32);
-      int node = -1;
-      float vt = NINF, vb = NINF, vl = NINF;
-      if (ord != ninf_ord) {
-        const int idx = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-        if (idx < W) {
-          node = slot_node[idx]; vt = new_t[idx]; vb = new_b[idx]; vl = new_l[idx];
-        } else {
-          const int j = idx - W, li = j / V, c = j % V;
-          const int pnode = slot_node[li];
-          const int plabel = (pnode == 0) ? -1 : u.node_label[pnode];
-          const float prev = (c == plabel) ? old_b[li] : old_t[li];
-          vl = x[c] + prev; vt = vl; vb = NINF;
-          node = hash_find_or_insert(u, pnode, c, V, node_count);
-        }
+    for (int k = tid; k < n; k += CB_THREADS) {
+      const int ref = ent_ref[k];
+      if (ref < W) {
+        tmp_node[k] = slot_node[ref]; tmp_t[k] = new_t[ref]; tmp_b[k] = new_b[ref]; tmp_l[k] = new_l[ref];
+      } else {
+        const int j = ref - W, li = j / V, c = j % V;
+        tmp_node[k] = hash_find_or_insert(u, slot_node[li], c, V, node_count);
+        tmp_t[k] = ent_val[k]; tmp_b[k] = NINF; tmp_l[k] = ent_val[k];
       }
-      sel_node[k] = node; sv_t[k] = vt; sv_b[k] = vb; sv_l[k] = vl;
     }
     __syncthreads();
-    if (tid == 0) {
-      int n = 0;
-      while (n < W && sel_node[n] >= 0) ++n;
-      s_nleaf = n;
-    }
-    for (int k = tid; k < W; k += CB_THREADS) {
-      const int node = sel_node[k];
-      if (node >= 0) {
-        slot_node[k] = node; new_t[k] = sv_t[k]; new_b[k] = sv_b[k]; new_l[k] = sv_l[k];
-        u.node_slot[node] = k;
+    // ---- F: next frame's branch order = descending newp.total (rank sort, stable) ---------------------
+    for (int k = tid; k < n; k += CB_THREADS) {
+      const float v = tmp_t[k];
+      int r = 0;
+      for (int j = 0; j < n; ++j) {
+        const float o = tmp_t[j];
+        r += (o > v || (o == v && j < k)) ? 1 : 0;
       }
+      slot_node[r] = tmp_node[k]; new_t[r] = v; new_b[r] = tmp_b[k]; new_l[r] = tmp_l[k];
+      u.node_slot[tmp_node[k]] = r;
     }
-    __threadfence_block();
+    if (tid == 0) s_nleaf = n;
     __syncthreads();
   }
 
   if (tid == 0) {
-    const int nleaf = s_nleaf;
-    int best = 0;
-    for (int i = 1; i < nleaf; ++i)
-      if (new_t[i] > new_t[best]) best = i;
+    // TopPaths(1): the best leaf is slot 0 (leaves are kept sorted)
+    const int best = 0;
     // LabelSeq(merge_repeated): walk to the root, dropping a label equal to the one emitted after it
     int* out = out_ids + (size_t)b * T;
     int n = 0, prev_label = -1;
@@ -277,16 +308,15 @@ extern "C" int nabu_ctc_beam_search(const float* logits, const int* logit_len, i
   const int W = beam_width;
   CbWs w = cb_carve(workspace, B, T, W);
   NABU_REQUIRE(ws_bytes >= w.total, "ctc_beam_search: workspace %zu < %zu bytes", ws_bytes, w.total);
-  int NS = 1;
-  while (NS < W + W * V) NS <<= 1;
-  const size_t smem = (size_t)NS * 8 + (size_t)9 * W * 4 + (size_t)2 * W * 4 + (size_t)V * 4 + (size_t)W * V + 16;
+  NABU_REQUIRE(W < 65535, "ctc_beam_search: beam_width=%d too large", W);
+  const size_t smem = (size_t)15 * W * 4 + (size_t)V * 4 + (size_t)W * V * 2 + 16;
   NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "ctc_beam_search: beam_width*classes too large (%d x %d)", W, V);
   NABU_CHECK_CUDA(cudaMemsetAsync(w.hkeys, 0xFF, w.hkeys_bytes, stream));
   NABU_CHECK_CUDA(cudaMemsetAsync(w.hvals, 0xFF, w.hvals_bytes, stream));
   if (smem > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelScope ks("ctc_beam", stream);
-  ctc_beam_kernel<<<B, CB_THREADS, smem, stream>>>(logits, logit_len, T, V, W, NS, merge_repeated, w.node_parent,
+  ctc_beam_kernel<<<B, CB_THREADS, smem, stream>>>(logits, logit_len, T, V, W, merge_repeated, w.node_parent,
                                                    w.node_label, w.node_slot, w.hkeys, w.hvals, w.node_count, w.nmax,
                                                    w.hcap, out_ids, out_len, out_neg_logprob);
   NABU_CHECK_LAUNCH();
