@@ -112,7 +112,13 @@ extern "C" int nabu_gemm(int mode, int precision, int M, int N, int K, float alp
                          const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
                          void* workspace, size_t ws_bytes, void* stream) {
   NABU_REQUIRE(mode >= 0 && mode <= 2, "gemm: bad mode %d", mode);
-  NABU_REQUIRE(precision == 0, "gemm: precision %d not available in this build", precision);
+  NABU_REQUIRE(precision == 0 || precision == 1, "gemm: precision %d unknown", precision);
+  if (precision == 1) {
+    NABU_REQUIRE(gemm_tc_eligible((GemmMode)mode, M, N, K, A, lda, B, ldb),
+                 "gemm: operands not eligible for the tensor-core path (16-byte aligned pointers, ld %% 4 == 0, M*N >= 128*128)");
+    return gemm_tc((GemmMode)mode, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, nullptr, (float*)workspace,
+                   ws_bytes, (cudaStream_t)stream);
+  }
   return sgemm((GemmMode)mode, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, nullptr, (float*)workspace,
                ws_bytes, (cudaStream_t)stream);
 }

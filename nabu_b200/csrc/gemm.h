@@ -17,6 +17,22 @@ int sgemm(GemmMode mode, int M, int N, int K, float alpha, const float* A, int l
           int ldb, float beta, float* C, int ldc, const float* bias, const GemmSeg* seg,
           float* workspace, size_t ws_bytes, cudaStream_t stream);
 
+// Deterministic second pass of split-K: C = alpha * sum_z part[z] + beta*C + bias.
+int splitk_reduce(const float* part, int splits, float* C, int M, int N, int ldc, float alpha, float beta,
+                  const float* bias, cudaStream_t stream);
+
+// tcgen05 / TMEM / TMA path with 3xTF32 split precision (gemm_tc.cu).  Same contract as sgemm().
+bool gemm_tc_eligible(GemmMode mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb);
+int gemm_tc(GemmMode mode, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+            float beta, float* C, int ldc, const float* bias, const GemmSeg* seg, float* workspace,
+            size_t ws_bytes, cudaStream_t stream);
+
+// Dispatcher used by the layer code: tensor-core path when eligible (and not disabled with
+// NABU_GEMM=simt), FFMA path otherwise.
+int gemm(GemmMode mode, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+         float beta, float* C, int ldc, const float* bias, const GemmSeg* seg, float* workspace,
+         size_t ws_bytes, cudaStream_t stream);
+
 // out[n] = sum_m X[m,n]
 int colsum(const float* X, int M, int N, int ldx, float* out, cudaStream_t stream);
 

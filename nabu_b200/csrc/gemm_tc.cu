@@ -1,0 +1,387 @@
+// tcgen05 / TMEM / TMA dense contraction for sm_100a with fp32-grade accuracy ("3xTF32").
+//
+// Every big GEMM of the hot path (input projection X.Kx, dKx = X^T.dZ, dKh = Hprev^T.dZ,
+// dX = dZ.Kx^T) must hold the 1e-4 fp32 parity bar, which a single TF32 or BF16 tensor-core pass
+// does not.  So each fp32 operand is split on the fly into hi = rn_tf32(a) and
+// lo = a - hi (exact in fp32) and the tensor core accumulates  hi.hi + hi.lo + lo.hi  in fp32 TMEM:
+// the dropped lo.lo term is ~2^-22 relative.  Cost: 3 TF32 MMAs per k-step, still ~6x the fp32 FFMA
+// roofline of the SIMT kernel in sgemm.cu.
+//
+// Kernel anatomy (one CTA = one 128 x 256 output tile, 192 threads, 2-stage ring, BK = 32):
+//   warp 0     TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes, OOB rows/cols zero-filled, so
+//              M/N/K tails and the per-utterance row segmentation of dKh need no special cases)
+//   warps 2-5  converters: rewrite the landed fp32 tile in place as `hi` and write `lo` next to it
+//              (generic proxy -> fence.proxy.async -> mbarrier), later the epilogue warps
+//   warp 1     MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8) x 4 k-steps x 3
+//              products per stage, tcgen05.commit frees the stage / signals the epilogue
+//   epilogue   tcgen05.ld 32x32b -> alpha, beta, bias -> 128-bit global stores
+// Operands may be K-major (row = M/N index, K contiguous) or MN-major (row = K index): both are legal
+// UMMA layouts for TF32, selected in the instruction descriptor, so NN / NT / TN need no transposes.
+#include "common.cuh"
+#include "gemm.h"
+#include <cuda.h>
+
+namespace nabu {
+namespace {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB
+constexpr int B_TILE_BYTES = TC_BN * TC_BK * 4;          // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // hi+lo of both = 96 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcArgs {
+  int M, N;
+  int kblocks;            // total k-blocks of 32
+  int kps;                // k-blocks per row segment (MN-major operands); == kblocks when unsegmented
+  int kb_per_split;       // k-blocks per blockIdx.z
+  int a_mn_major, b_mn_major;
+  float alpha, beta;
+  const float* bias;
+  float* C; int ldc;
+  float* part;            // split-K partials [splits][M][N] or nullptr
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tile(uint8_t* tile, int tile_bytes, int ct) {
+#pragma unroll 4
+  for (int c = ct; c < tile_bytes / 16; c += 128) {
+    const float4 v = *reinterpret_cast<float4*>(tile + c * 16);
+    float4 hi, lo;
+    hi.x = rn_tf32(v.x); hi.y = rn_tf32(v.y); hi.z = rn_tf32(v.z); hi.w = rn_tf32(v.w);
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+    *reinterpret_cast<float4*>(tile + c * 16) = hi;
+    *reinterpret_cast<float4*>(tile + tile_bytes + c * 16) = lo;
+  }
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;        // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-B alignment
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + TC_STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[s], conv[s], empty[s], tmem_full ; then the TMEM base address
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_conv = [&](int s) { return bars + 8u * (TC_STAGES + s); };
+  auto bar_empty = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
+  const uint32_t bar_tmem = bars + 8u * (3 * TC_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + TC_STAGES * STAGE_BYTES + 8 * (3 * TC_STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int kb_begin = blockIdx.z * g.kb_per_split;
+  const int kb_end = min(g.kblocks, kb_begin + g.kb_per_split);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_conv(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb_begin + i;
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(bar_empty(s), ph ^ 1);
+        mbar_expect_tx(bar_full(s), A_TILE_BYTES + B_TILE_BYTES);
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint32_t sb = sa + 2 * A_TILE_BYTES;
+        const int seg = kb / g.kps, kk = (kb % g.kps) * TC_BK;
+        if (g.a_mn_major) {
+          for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(sa + j * 4096, &mapA, bar_full(s), m0 + 32 * j, kk, seg);
+        } else {
+          tma_load_3d(sa, &mapA, bar_full(s), kb * TC_BK, m0, 0);
+        }
+        if (g.b_mn_major) {
+          for (int j = 0; j < TC_BN / 32; ++j) tma_load_3d(sb + j * 4096, &mapB, bar_full(s), n0 + 32 * j, kk, seg);
+        } else {
+          tma_load_3d(sb, &mapB, bar_full(s), kb * TC_BK, n0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn_major << 15) |
+                             ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      // K-major: 8-row groups 1024 B apart (SBO), k-step = +32 B inside the swizzled 128-B row.
+      // MN-major: 32-element column blocks 4096 B apart (LBO), 8-row k-groups 1024 B apart (SBO, the k-step).
+      const uint32_t a_lbo = g.a_mn_major ? 4096u : 16u, b_lbo = g.b_mn_major ? 4096u : 16u;
+      const uint32_t a_kstep = g.a_mn_major ? 1024u : 32u, b_kstep = g.b_mn_major ? 1024u : 32u;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (i / TC_STAGES) & 1;
+        mbar_wait(bar_conv(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint32_t sb = sa + 2 * A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t a_hi = make_desc(sa + k * a_kstep, a_lbo, 1024u);
+          const uint64_t a_lo = make_desc(sa + A_TILE_BYTES + k * a_kstep, a_lbo, 1024u);
+          const uint64_t b_hi = make_desc(sb + k * b_kstep, b_lbo, 1024u);
+          const uint64_t b_lo = make_desc(sb + B_TILE_BYTES + k * b_kstep, b_lbo, 1024u);
+          umma_tf32(tmem_d, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);   // small terms first
+          umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+          umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+        }
+        umma_commit(bar_empty(s));                 // frees the stage once these MMAs have read it
+      }
+      umma_commit(bar_tmem);                       // accumulator complete
+    }
+  } else {
+    // ===== converters (then epilogue) =====
+    const int ct = threadIdx.x - 64;               // 0..127
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % TC_STAGES;
+      const uint32_t ph = (i / TC_STAGES) & 1;
+      mbar_wait(bar_full(s), ph);
+      uint8_t* sa = base_ptr + s * STAGE_BYTES;
+      uint8_t* sb = sa + 2 * A_TILE_BYTES;
+split_tile(sa, A_TILE_BYTES, ct);
+      split_tile(sb, B_TILE_BYTES, ct);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+      mbar_arrive(bar_conv(s));
+    }
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int m = m0 + 32 * q + lane;
+    const bool split = g.part != nullptr;
+    float* Cout = split ? g.part + (size_t)blockIdx.z * g.M * g.N : g.C;
+    const int ldc = split ? g.N : g.ldc;
+    const bool vec = ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (ldc % 4 == 0);
+    if (nkb > 0) {
+      mbar_wait(bar_tmem, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (m < g.M) {
+        float* crow = Cout + (size_t)m * ldc;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const int n = n0 + c0 + j4;
+          if (n >= g.N) break;
+          float v[4] = {__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]),
+                        __uint_as_float(r[j4 + 3])};
+          const int nv = min(4, g.N - n);
+          if (!split) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < nv) {
+                float o = g.alpha * v[j];
+                if (g.bias) o += g.bias[n + j];
+                if (g.beta != 0.f) o += g.beta * crow[n + j];
+                v[j] = o;
+              }
+            }
+          }
+          if (nv == 4 && vec) *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+          else for (int j = 0; j < nv; ++j) crow[n + j] = v[j];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256u) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D fp32 tensor map: dims (inner, mid, outer), row strides in elements
+int make_map(CUtensorMap* map, const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+             uint64_t stride2, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  NABU_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1 * 4, stride2 * 4};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NABU_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+bool gemm_tc_eligible(GemmMode mode, int M, int N, int K, const float* A, int lda, const float* B, int ldb) {
+  (void)mode;
+  if (M < 1 || N < 1 || K < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if (lda % 4 || ldb % 4) return false;
+  // tiny problems are not worth a 128x256 tile
+  if ((long)M * N < 128L * 128L) return false;
+  return true;
+}
+
+int gemm_tc(GemmMode mode, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+            float beta, float* C, int ldc, const float* bias, const GemmSeg* segp, float* workspace,
+            size_t ws_bytes, cudaStream_t stream) {
+  NABU_REQUIRE(!(segp && mode != GEMM_TN), "gemm_tc: row segmentation only in TN mode");
+  CUtensorMap mapA, mapB;
+  TcArgs g = {};
+  g.M = M; g.N = N; g.alpha = alpha; g.beta = beta; g.bias = bias; g.C = C; g.ldc = ldc;
+  if (mode == GEMM_TN) {
+    const int seg = segp ? segp->seg : K;
+    const int nseg = segp ? K / segp->seg : 1;
+    NABU_REQUIRE(!segp || K % segp->seg == 0, "gemm_tc: K must be a multiple of the segment length");
+    const uint64_t sA = segp ? (uint64_t)segp->segA : (uint64_t)K, sB = segp ? (uint64_t)segp->segB : (uint64_t)K;
+    const float* Ap = A + (segp ? (size_t)segp->offA * lda : 0);
+    const float* Bp = B + (segp ? (size_t)segp->offB * ldb : 0);
+    if (int e = make_map(&mapA, Ap, M, seg, nseg, lda, sA * lda, 32, 32)) return e;
+    if (int e = make_map(&mapB, Bp, N, seg, nseg, ldb, sB * ldb, 32, 32)) return e;
+    g.a_mn_major = 1; g.b_mn_major = 1;
+    g.kps = ceil_div(seg, TC_BK);
+    g.kblocks = g.kps * nseg;
+  } else {
+    if (int e = make_map(&mapA, A, K, M, 1, lda, (uint64_t)M * lda, 32, TC_BM)) return e;
+    g.a_mn_major = 0;
+    if (mode == GEMM_NN) {
+      if (int e = make_map(&mapB, B, N, K, 1, ldb, (uint64_t)K * ldb, 32, 32)) return e;
+      g.b_mn_major = 1;
+    } else {
+      if (int e = make_map(&mapB, B, K, N, 1, ldb, (uint64_t)N * ldb, 32, TC_BN)) return e;
+      g.b_mn_major = 0;
+    }
+    g.kblocks = ceil_div(K, TC_BK);
+    g.kps = g.kblocks;
+  }
+  const int tiles = ceil_div(M, TC_BM) * ceil_div(N, TC_BN);
+  int splits = 1;
+  if (workspace != nullptr && tiles < num_sms() && g.kblocks >= 64) {
+    splits = min(num_sms() / tiles, g.kblocks / 16);
+    const size_t per = (size_t)M * N * sizeof(float);
+    if ((size_t)splits * per > ws_bytes) splits = (int)(ws_bytes / per);
+    if (splits < 1) splits = 1;
+  }
+  g.kb_per_split = ceil_div(g.kblocks, splits);
+  splits = ceil_div(g.kblocks, g.kb_per_split);
+  g.part = splits > 1 ? workspace : nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NABU_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  {
+    KernelScope ks(mode == GEMM_NN ? "gemm_tc_nn" : mode == GEMM_NT ? "gemm_tc_nt" : "gemm_tc_tn", stream);
+    gemm_tc_kernel<<<dim3(ceil_div(N, TC_BN), ceil_div(M, TC_BM), splits), TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, g);
+    NABU_CHECK_LAUNCH();
+  }
+  if (splits > 1) return splitk_reduce(workspace, splits, C, M, N, ldc, alpha, beta, bias, stream);
+  return 0;
+}
+
+}  // namespace nabu

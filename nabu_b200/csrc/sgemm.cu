@@ -11,6 +11,8 @@
 // too small to fill 148 SMs.
 #include "common.cuh"
 #include "gemm.h"
+#include <stdlib.h>
+#include <string.h>
 
 namespace nabu {
 
@@ -274,6 +276,28 @@ int sgemm(GemmMode mode, int M, int N, int K, float alpha, const float* A, int l
     NABU_CHECK_LAUNCH();
   }
   return 0;
+}
+
+int splitk_reduce(const float* part, int splits, float* C, int M, int N, int ldc, float alpha, float beta,
+                  const float* bias, cudaStream_t stream) {
+  const long tot = (long)M * N;
+  KernelScope ks("splitk_reduce", stream);
+  splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(part, splits, C, M, N, ldc, alpha, beta, bias);
+  NABU_CHECK_LAUNCH();
+  return 0;
+}
+
+int gemm(GemmMode mode, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+         float beta, float* C, int ldc, const float* bias, const GemmSeg* seg, float* workspace,
+         size_t ws_bytes, cudaStream_t stream) {
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("NABU_GEMM");
+    use_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  if (use_tc && gemm_tc_eligible(mode, M, N, K, A, lda, B, ldb))
+    return gemm_tc(mode, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, seg, workspace, ws_bytes, stream);
+  return sgemm(mode, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, seg, workspace, ws_bytes, stream);
 }
 
 int colsum(const float* X, int M, int N, int ldx, float* out, cudaStream_t stream) {
