@@ -540,7 +540,7 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   float* c[2] = {cells, cells + (size_t)B * T * H};
   // input projection for all T at once: Gx = X . Kx + b
   for (int d = 0; d < 2; ++d)
-    if (int e = sgemm(GEMM_NN, B * T, H4, D, 1.f, x, D, kern[d], H4, 0.f, g[d], H4, bias[d], nullptr, nullptr, 0, stream))
+    if (int e = gemm(GEMM_NN, B * T, H4, D, 1.f, x, D, kern[d], H4, 0.f, g[d], H4, bias[d], nullptr, nullptr, 0, stream))
       return e;
   NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
   NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * pl.Bp * sizeof(float), stream));
@@ -584,7 +584,7 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   // gates[] now hold dZ (zero for t >= len)
   for (int d = 0; d < 2; ++d) {
     // dKx = X^T . dZ
-    if (int e = sgemm(GEMM_TN, D, H4, B * T, 1.f, x, D, g[d], H4, 0.f, dkern[d], H4, nullptr, nullptr, w.gemm,
+    if (int e = gemm(GEMM_TN, D, H4, B * T, 1.f, x, D, g[d], H4, 0.f, dkern[d], H4, nullptr, nullptr, w.gemm,
                       w.gemm_bytes, stream))
       return e;
     // dKh = Hprev^T . dZ ; fw: Hprev[b,t] = y[b,t-1,:H] ; bw: Hprev[b,t] = y[b,t+1,H:]
@@ -593,7 +593,7 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
       GemmSeg seg;
       seg.seg = T - 1; seg.segA = yT; seg.segB = T;
       seg.offA = d == 0 ? 0 : 1; seg.offB = d == 0 ? 1 : 0;
-      if (int e = sgemm(GEMM_TN, H, H4, B * (T - 1), 1.f, y + d * H, 2 * H, g[d], H4, 0.f, dKh, H4, nullptr, &seg,
+      if (int e = gemm(GEMM_TN, H, H4, B * (T - 1), 1.f, y + d * H, 2 * H, g[d], H4, 0.f, dKh, H4, nullptr, &seg,
                         w.gemm, w.gemm_bytes, stream))
         return e;
     } else {
@@ -601,7 +601,7 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
     }
     // dX (+)= dZ . Kx^T
     if (dx)
-      if (int e = sgemm(GEMM_NT, B * T, D, H4, 1.f, g[d], H4, kern[d], H4, d == 0 ? 0.f : 1.f, dx, D, nullptr, nullptr,
+      if (int e = gemm(GEMM_NT, B * T, D, H4, 1.f, g[d], H4, kern[d], H4, d == 0 ? 0.f : 1.f, dx, D, nullptr, nullptr,
                         nullptr, 0, stream))
         return e;
   }

@@ -160,16 +160,16 @@ extern "C" int nabu_pyramid_lengths(const int* len, int B, int numsteps, int* ou
 extern "C" int nabu_linear_fwd(const float* x, int N, int D, int V, const float* W, const float* b, float* y,
                                void* workspace, size_t ws_bytes, void* stream) {
   (void)workspace; (void)ws_bytes;
-  return sgemm(GEMM_NN, N, V, D, 1.f, x, D, W, V, 0.f, y, V, b, nullptr, nullptr, 0, (cudaStream_t)stream);
+  return gemm(GEMM_NN, N, V, D, 1.f, x, D, W, V, 0.f, y, V, b, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int nabu_linear_bwd(const float* x, int N, int D, int V, const float* W, const float* dy, float* dx,
                                float* dW, float* db, void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (dx)
-    if (int e = sgemm(GEMM_NT, N, D, V, 1.f, dy, V, W, V, 0.f, dx, D, nullptr, nullptr, nullptr, 0, stream)) return e;
+    if (int e = gemm(GEMM_NT, N, D, V, 1.f, dy, V, W, V, 0.f, dx, D, nullptr, nullptr, nullptr, 0, stream)) return e;
   if (dW)
-    if (int e = sgemm(GEMM_TN, D, V, N, 1.f, x, D, dy, V, 0.f, dW, V, nullptr, nullptr, (float*)workspace, ws_bytes,
+    if (int e = gemm(GEMM_TN, D, V, N, 1.f, x, D, dy, V, 0.f, dW, V, nullptr, nullptr, (float*)workspace, ws_bytes,
                       stream))
       return e;
   if (db)

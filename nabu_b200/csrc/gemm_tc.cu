@@ -112,13 +112,13 @@ __device__ __forceinline__ void split_tile(uint8_t* tile, int tile_bytes, int ct
 }
 
 // 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;        // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B (K-major), 1 = SWIZZLE_128B_BASE32B (MN-major TF32)
   return d;
 }
 
@@ -190,9 +190,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn_major << 15) |
                              ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
-      // K-major: 8-row groups 1024 B apart (SBO), k-step = +32 B inside the swizzled 128-B row.
-      // MN-major: 32-element column blocks 4096 B apart (LBO), 8-row k-groups 1024 B apart (SBO, the k-step).
+      // K-major (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), k-step = +32 B inside the swizzled row.
+      // MN-major: TF32 only supports SWIZZLE_128B_BASE32B there (Swizzle<2,5,2>: 32-B chunks XOR row%4):
+      // 32-element column blocks 4096 B apart (LBO), 4-row k-groups 512 B apart (SBO), k-step (8 rows) = 1024 B.
       const uint32_t a_lbo = g.a_mn_major ? 4096u : 16u, b_lbo = g.b_mn_major ? 4096u : 16u;
+      const uint32_t a_sbo = g.a_mn_major ? 512u : 1024u, b_sbo = g.b_mn_major ? 512u : 1024u;
+      const uint32_t a_lt = g.a_mn_major ? 1u : 2u, b_lt = g.b_mn_major ? 1u : 2u;
       const uint32_t a_kstep = g.a_mn_major ? 1024u : 32u, b_kstep = g.b_mn_major ? 1024u : 32u;
       for (int i = 0; i < nkb; ++i) {
         const int s = i % TC_STAGES;
@@ -203,10 +206,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t sb = sa + 2 * A_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint64_t a_hi = make_desc(sa + k * a_kstep, a_lbo, 1024u);
-          const uint64_t a_lo = make_desc(sa + A_TILE_BYTES + k * a_kstep, a_lbo, 1024u);
-          const uint64_t b_hi = make_desc(sb + k * b_kstep, b_lbo, 1024u);
-          const uint64_t b_lo = make_desc(sb + B_TILE_BYTES + k * b_kstep, b_lbo, 1024u);
+          const uint64_t a_hi = make_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t a_lo = make_desc(sa + A_TILE_BYTES + k * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t b_hi = make_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
+          const uint64_t b_lo = make_desc(sb + B_TILE_BYTES + k * b_kstep, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_d, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);   // small terms first
           umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
           umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
@@ -301,7 +304,7 @@ EncodeTiledFn get_encode() {
 
 // 3-D fp32 tensor map: dims (inner, mid, outer), row strides in elements
 int make_map(CUtensorMap* map, const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
-             uint64_t stride2, uint32_t box0, uint32_t box1) {
+             uint64_t stride2, uint32_t box0, uint32_t box1, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   NABU_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -309,7 +312,8 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t d0, uint64_t d1, uint6
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NABU_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
@@ -341,19 +345,19 @@ int gemm_tc(GemmMode mode, int M, int N, int K, float alpha, const float* A, int
     const uint64_t sA = segp ? (uint64_t)segp->segA : (uint64_t)K, sB = segp ? (uint64_t)segp->segB : (uint64_t)K;
     const float* Ap = A + (segp ? (size_t)segp->offA * lda : 0);
     const float* Bp = B + (segp ? (size_t)segp->offB * ldb : 0);
-    if (int e = make_map(&mapA, Ap, M, seg, nseg, lda, sA * lda, 32, 32)) return e;
-    if (int e = make_map(&mapB, Bp, N, seg, nseg, ldb, sB * ldb, 32, 32)) return e;
+    if (int e = make_map(&mapA, Ap, M, seg, nseg, lda, sA * lda, 32, 32, true)) return e;
+    if (int e = make_map(&mapB, Bp, N, seg, nseg, ldb, sB * ldb, 32, 32, true)) return e;
     g.a_mn_major = 1; g.b_mn_major = 1;
     g.kps = ceil_div(seg, TC_BK);
     g.kblocks = g.kps * nseg;
   } else {
-    if (int e = make_map(&mapA, A, K, M, 1, lda, (uint64_t)M * lda, 32, TC_BM)) return e;
+    if (int e = make_map(&mapA, A, K, M, 1, lda, (uint64_t)M * lda, 32, TC_BM, false)) return e;
     g.a_mn_major = 0;
     if (mode == GEMM_NN) {
-      if (int e = make_map(&mapB, B, N, K, 1, ldb, (uint64_t)K * ldb, 32, 32)) return e;
+      if (int e = make_map(&mapB, B, N, K, 1, ldb, (uint64_t)K * ldb, 32, 32, true)) return e;
       g.b_mn_major = 1;
     } else {
-      if (int e = make_map(&mapB, B, K, N, 1, ldb, (uint64_t)N * ldb, 32, TC_BN)) return e;
+      if (int e = make_map(&mapB, B, K, N, 1, ldb, (uint64_t)N * ldb, 32, TC_BN, false)) return e;
       g.b_mn_major = 0;
     }
     g.kblocks = ceil_div(K, TC_BK);

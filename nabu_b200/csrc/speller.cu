@@ -422,7 +422,7 @@ int prepare_memory(const nabu_speller_desc_t& d, const nabu_speller_params_t& p,
     mask_memory_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(memory, mem_len, d.Tm, d.E, values, n);
     NABU_CHECK_LAUNCH();
   }
-  return sgemm(GEMM_NN, d.B * d.Tm, d.A, d.E, 1.f, values, d.E, p.memory_kernel, d.A, 0.f, keys, d.A, nullptr, nullptr,
+  return gemm(GEMM_NN, d.B * d.Tm, d.A, d.E, 1.f, values, d.E, p.memory_kernel, d.A, 0.f, keys, d.A, nullptr, nullptr,
                nullptr, 0, stream);
 }
 
@@ -559,30 +559,30 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
         NABU_CHECK_LAUNCH();
       }
       // context rows: input of step u is ctx slot u
-      if (int e = sgemm(GEMM_TN, E, H4, UB, 1.f, s.ctx, E, dz, H4, 0.f, dK + (size_t)V * H4, H4, nullptr, nullptr, w.gemm,
+      if (int e = gemm(GEMM_TN, E, H4, UB, 1.f, s.ctx, E, dz, H4, 0.f, dK + (size_t)V * H4, H4, nullptr, nullptr, w.gemm,
                         w.gemm_bytes, stream)) return e;
-      if (int e = sgemm(GEMM_TN, H, H4, UB, 1.f, s.h[0], H, dz, H4, 0.f, dK + (size_t)(V + E) * H4, H4, nullptr, nullptr,
+      if (int e = gemm(GEMM_TN, H, H4, UB, 1.f, s.h[0], H, dz, H4, 0.f, dK + (size_t)(V + E) * H4, H4, nullptr, nullptr,
                         w.gemm, w.gemm_bytes, stream)) return e;
     } else {
       // input rows: h of the layer below AFTER step u = slot u+1 ; recurrent rows: own h slot u
-      if (int e = sgemm(GEMM_TN, H, H4, UB, 1.f, s.h[l - 1] + (size_t)B * H, H, dz, H4, 0.f, dK, H4, nullptr, nullptr,
+      if (int e = gemm(GEMM_TN, H, H4, UB, 1.f, s.h[l - 1] + (size_t)B * H, H, dz, H4, 0.f, dK, H4, nullptr, nullptr,
                         w.gemm, w.gemm_bytes, stream)) return e;
-      if (int e = sgemm(GEMM_TN, H, H4, UB, 1.f, s.h[l], H, dz, H4, 0.f, dK + (size_t)H * H4, H4, nullptr, nullptr,
+      if (int e = gemm(GEMM_TN, H, H4, UB, 1.f, s.h[l], H, dz, H4, 0.f, dK + (size_t)H * H4, H4, nullptr, nullptr,
                         w.gemm, w.gemm_bytes, stream)) return e;
     }
     if (int e = colsum(dz, UB, H4, H4, g->cell_bias[l], stream)) return e;
   }
   // output projection: rows ordered (b, u) on both sides
-  if (int e = sgemm(GEMM_TN, H + E, V, B * U, 1.f, s.outin, H + E, dlogits, V, 0.f, g->out_kernel, V, nullptr, nullptr,
+  if (int e = gemm(GEMM_TN, H + E, V, B * U, 1.f, s.outin, H + E, dlogits, V, 0.f, g->out_kernel, V, nullptr, nullptr,
                     w.gemm, w.gemm_bytes, stream)) return e;
   if (int e = colsum(dlogits, B * U, V, V, g->out_bias, stream)) return e;
   // query layer: h_top after step u (slot u+1) against dq[u]
-  if (int e = sgemm(GEMM_TN, H, A, UB, 1.f, s.h[NL - 1] + (size_t)B * H, H, w.dq, A, 0.f, g->query_kernel, A, nullptr,
+  if (int e = gemm(GEMM_TN, H, A, UB, 1.f, s.h[NL - 1] + (size_t)B * H, H, w.dq, A, 0.f, g->query_kernel, A, nullptr,
                     nullptr, w.gemm, w.gemm_bytes, stream)) return e;
   // memory layer and the memory itself
-  if (int e = sgemm(GEMM_TN, E, A, B * Tm, 1.f, s.values, E, w.dkeys, A, 0.f, g->memory_kernel, A, nullptr, nullptr,
+  if (int e = gemm(GEMM_TN, E, A, B * Tm, 1.f, s.values, E, w.dkeys, A, 0.f, g->memory_kernel, A, nullptr, nullptr,
                     w.gemm, w.gemm_bytes, stream)) return e;
-  if (int e = sgemm(GEMM_NT, B * Tm, E, A, 1.f, w.dkeys, A, p->memory_kernel, A, 1.f, w.dvalues, E, nullptr, nullptr,
+  if (int e = gemm(GEMM_NT, B * Tm, E, A, 1.f, w.dkeys, A, p->memory_kernel, A, 1.f, w.dvalues, E, nullptr, nullptr,
                     nullptr, 0, stream)) return e;
   if (dmemory) {
     const long n = (long)B * Tm * E;
