@@ -21,7 +21,10 @@
 // direction visits t = len[b]-1-s at step s.
 #include "common.cuh"
 #include "gemm.h"
+#include "blstm_tc.h"
 #include "nabu_b200.h"
+#include <stdlib.h>
+#include <string.h>
 
 namespace nabu {
 namespace {
@@ -504,7 +507,11 @@ Ws carve(void* base, int H, int Bp) {
   size_t off = 0;
   char* b = (char*)base;
   w.counters = (unsigned*)(b + off); off += 256;
-  w.xchg = (float*)(b + off); off += align_up((size_t)2 * 2 * 4 * H * Bp * sizeof(float), 256);
+  {
+    size_t xf = (size_t)2 * 2 * 4 * H * Bp;
+    if (xf < (size_t)4 * 128 * H) xf = (size_t)4 * 128 * H;      // the tcgen05 path exchanges [2][2][128][H]
+    w.xchg = (float*)(b + off); off += align_up(xf * sizeof(float), 256);
+  }
   w.dcbuf = (float*)(b + off); off += align_up((size_t)2 * Bp * H * sizeof(float), 256);
   w.gemm = (float*)(b + off); w.gemm_bytes = sgemm_workspace_bytes(); off += w.gemm_bytes;
   w.total = off;
@@ -543,10 +550,20 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
     if (int e = gemm(GEMM_NN, B * T, H4, D, 1.f, x, D, kern[d], H4, 0.f, g[d], H4, bias[d], nullptr, nullptr, 0, stream))
       return e;
   NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
-  NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * pl.Bp * sizeof(float), stream));
   if (yT > T)
     NABU_CHECK_CUDA(cudaMemset2DAsync(y + (size_t)T * 2 * H, (size_t)yT * 2 * H * sizeof(float), 0,
                                       (size_t)(yT - T) * 2 * H * sizeof(float), B, stream));
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("NABU_REC");
+    use_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  BlstmTcPlan tpl;
+  if (use_tc && blstm_tc_plan(B, H, &tpl)) {
+    NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)4 * 128 * H * sizeof(float), stream));
+    return blstm_rec_fwd_tc(tpl, kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream);
+  }
+  NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * pl.Bp * sizeof(float), stream));
   RecParams rp = {};
   rp.kernel[0] = kern[0]; rp.kernel[1] = kern[1];
   rp.gates[0] = g[0]; rp.gates[1] = g[1];
