@@ -29,7 +29,8 @@
 namespace nabu {
 namespace {
 
-constexpr int RNN_THREADS = 256;
+constexpr int RNN_THREADS = 512;
+constexpr int RNN_WARPS = RNN_THREADS / 32;
 constexpr int KC = 64;        // rows of the exchanged operand per pipeline stage
 constexpr int STAGES = 3;
 
@@ -54,7 +55,7 @@ template <int TBT, int HS>
 struct RecCfg {
   static constexpr int BT = 16 * TBT;               // batch rows per tile
   static constexpr int CG = HS / 2;                 // column groups (2 hidden units each)
-  static constexpr int KS = 8 / CG;                 // k-split factor (warps per column group)
+  static constexpr int KS = RNN_WARPS / CG;         // k-split factor (warps per column group)
   static constexpr int PAIRS = BT * HS;             // (b, j) pairs per tile
   static constexpr int PP = (PAIRS + RNN_THREADS - 1) / RNN_THREADS;
 };
@@ -242,7 +243,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
   const int H = p.H, H4 = 4 * p.H;
   float* Ws = smem;                                  // [4H][HS]   Ws[k][jl] = Kh[j0+jl][k]
   float* ring = Ws + (size_t)H4 * HS;                // [STAGES][KC][BT]
-  float* red = ring + (size_t)STAGES * KC * BT;      // [8 warps][BT][HS]
+  float* red = ring + (size_t)STAGES * KC * BT;      // [RNN_WARPS][BT][HS]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int dir = p.dir0 + blockIdx.x / p.nsl;
@@ -263,7 +264,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
 
   const int bg = lane & 15, jj = lane >> 4;
   const int nchunks = H4 / KC;
-  const int kper = KC / 8;                           // 8 warps split every chunk
+  const int kper = KC / RNN_WARPS;                   // all warps split every chunk
   const int ntile = (p.B + BT - 1) / BT;
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -338,8 +339,18 @@ blstm_rec_bwd_kernel(const RecParams p) {
 #pragma unroll 4
           for (int kk = 0; kk < kper; ++kk) {
             float w[CW];
+            if (CW == 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ws_ + kk * HS);
+              w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[CW - 1] = w4.w;
+            } else if (CW == 8) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ws_ + kk * HS);
+              const float4 w5 = *reinterpret_cast<const float4*>(ws_ + kk * HS + 4);
+              w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+              w[CW - 4] = w5.x; w[CW - 3] = w5.y; w[CW - 2] = w5.z; w[CW - 1] = w5.w;
+            } else {
 #pragma unroll
-            for (int c2 = 0; c2 < CW; ++c2) w[c2] = ws_[kk * HS + c2];
+              for (int c2 = 0; c2 < CW; ++c2) w[c2] = ws_[kk * HS + c2];
+            }
             float hv[TBT];
             if (TBT >= 4) {
 #pragma unroll
@@ -374,7 +385,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
         if (pr < C::PAIRS && b < p.B) {
           float dh = dyv[q];
 #pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) dh += red[((size_t)w8 * BT + bl) * HS + jl];
+          for (int w8 = 0; w8 < RNN_WARPS; ++w8) dh += red[((size_t)w8 * BT + bl) * HS + jl];
           float dz[4] = {0.f, 0.f, 0.f, 0.f};
           float dcn = 0.f;
           if (valid[q]) {
@@ -445,10 +456,10 @@ int make_plan(int B, int H, Plan* pl) {
       if (H % hs) continue;
       const int nsl = H / hs;
       if (ndir * nsl > sms) continue;
-      const int ks = 8 / (hs / 2);
+      const int ks = RNN_WARPS / (hs / 2);
       const size_t ringf = (size_t)STAGES * KC * BT;
       const size_t fwd = ((size_t)H * hs * 4 + ringf + (size_t)ks * BT * hs * 4) * sizeof(float);
-      const size_t bwd = ((size_t)4 * H * hs + ringf + (size_t)8 * BT * hs) * sizeof(float) + 1024;
+      const size_t bwd = ((size_t)4 * H * hs + ringf + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 256;
       if (fwd > cap || bwd > cap) continue;
       pl->hs = hs; pl->nsl = nsl; pl->ndir_concurrent = ndir; pl->smem_fwd = fwd; pl->smem_bwd = bwd;
       return 0;
