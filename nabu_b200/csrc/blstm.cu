@@ -29,7 +29,7 @@
 namespace nabu {
 namespace {
 
-constexpr int RNN_THREADS = 512;
+constexpr int RNN_THREADS = 256;
 constexpr int RNN_WARPS = RNN_THREADS / 32;
 constexpr int KC = 64;        // rows of the exchanged operand per pipeline stage
 constexpr int STAGES = 3;
@@ -48,7 +48,17 @@ struct RecParams {
   int B, Bp, T, yT, D, H;
   int nsl;                  // CTAs (hidden slices) per direction
   int dir0;                 // first direction handled by this launch
+  int kc, stages;           // bwd ring: rows per stage, number of stages
+  int dbg;                  // profiling aid (NABU_REC_DBG): bit0 = skip the ring loads, bit1 = skip the FMAs
 };
+
+// Batch rows of a thread inside a tile.  For TBT == 8 the rows are two groups of 4 (bg*4.. and 64+bg*4..)
+// so that the 16 lanes of a half-warp read 256 contiguous bytes per LDS.128 (conflict-free); 8 contiguous
+// rows per lane would put lanes 0 and 4 on the same banks (2-way conflict on every operand load).
+template <int TBT>
+__device__ __forceinline__ int tile_row(int bg, int r) {
+  return TBT == 8 ? ((r >> 2) * 64 + bg * 4 + (r & 3)) : bg * TBT + r;
+}
 
 // Shared-memory carve-up (floats): W slice | ring stages | k-split partials
 template <int TBT, int HS>
@@ -158,7 +168,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
           cp_async_wait<1>();
           __syncthreads();
           issue(c + 2);
-          const float* hs_ = ring + (size_t)(c % STAGES) * KC * BT + (size_t)ks * kper * BT + bg * TBT;
+          const float* hs_ = ring + (size_t)(c % STAGES) * KC * BT + (size_t)ks * kper * BT;
           const float* ws_ = Ws + ((size_t)(c * KC + ks * kper) * HS + jl_mm) * 4;
 #pragma unroll 4
           for (int kk = 0; kk < kper; ++kk) {
@@ -167,12 +177,12 @@ blstm_rec_fwd_kernel(const RecParams p) {
             if (TBT >= 4) {
 #pragma unroll
               for (int v = 0; v < TBT / 4; ++v) {
-                const float4 t4 = *reinterpret_cast<const float4*>(hs_ + kk * BT + v * 4);
+                const float4 t4 = *reinterpret_cast<const float4*>(hs_ + kk * BT + tile_row<TBT>(bg, v * 4));
                 hv[v * 4 + 0] = t4.x; hv[v * 4 + 1] = t4.y; hv[v * 4 + 2] = t4.z; hv[v * 4 + 3] = t4.w;
               }
             } else {
 #pragma unroll
-              for (int r = 0; r < TBT; ++r) hv[r] = hs_[kk * BT + r];
+              for (int r = 0; r < TBT; ++r) hv[r] = hs_[kk * BT + bg * TBT + r];
             }
 #pragma unroll
             for (int r = 0; r < TBT; ++r) {
@@ -188,7 +198,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
       // ---- k-split partials -> shared ----------------------------------------------------------
 #pragma unroll
       for (int r = 0; r < TBT; ++r) {
-        float4* dst = reinterpret_cast<float4*>(red + (((size_t)ks * BT + bg * TBT + r) * HS + jl_mm) * 4);
+        float4* dst = reinterpret_cast<float4*>(red + (((size_t)ks * BT + tile_row<TBT>(bg, r)) * HS + jl_mm) * 4);
         *dst = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
       }
       __syncthreads();
@@ -243,7 +253,8 @@ blstm_rec_bwd_kernel(const RecParams p) {
   const int H = p.H, H4 = 4 * p.H;
   float* Ws = smem;                                  // [4H][HS]   Ws[k][jl] = Kh[j0+jl][k]
   float* ring = Ws + (size_t)H4 * HS;                // [STAGES][KC][BT]
-  float* red = ring + (size_t)STAGES * KC * BT;      // [RNN_WARPS][BT][HS]
+  const int kc = p.kc;
+  float* red = ring + (size_t)p.stages * kc * BT;    // [RNN_WARPS][BT][HS]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int dir = p.dir0 + blockIdx.x / p.nsl;
@@ -263,8 +274,8 @@ blstm_rec_bwd_kernel(const RecParams p) {
   __syncthreads();
 
   const int bg = lane & 15, jj = lane >> 4;
-  const int nchunks = H4 / KC;
-  const int kper = KC / RNN_WARPS;                   // all warps split every chunk
+  const int nchunks = H4 / kc;
+  const int kper = kc / RNN_WARPS;                   // all warps split every chunk
   const int ntile = (p.B + BT - 1) / BT;
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -318,24 +329,26 @@ blstm_rec_bwd_kernel(const RecParams p) {
           __syncthreads();
         }
         auto issue = [&](int c) {
-          if (c < nchunks) {
-            float* dst = ring + (size_t)(c % STAGES) * KC * BT;
-            const float* src = dzprev + (size_t)c * KC * p.Bp + b0;
-            for (int i = tid; i < KC * BT / 4; i += RNN_THREADS) {
+          if (c < nchunks && !(p.dbg & 1)) {
+            float* dst = ring + (size_t)(c % p.stages) * kc * BT;
+            const float* src = dzprev + (size_t)c * kc * p.Bp + b0;
+            for (int i = tid; i < kc * BT / 4; i += RNN_THREADS) {
               const int row = i / (BT / 4), c4 = i % (BT / 4);
               cp_async16(dst + row * BT + c4 * 4, src + (size_t)row * p.Bp + c4 * 4);
             }
           }
           cp_async_commit();
         };
+        // ring of p.stages buffers with p.stages-1 chunks in flight
         issue(0);
-        issue(1);
+        if (p.stages == 3) issue(1);
         for (int c = 0; c < nchunks; ++c) {
-          cp_async_wait<1>();
+          if (p.stages == 3) cp_async_wait<1>(); else cp_async_wait<0>();
           __syncthreads();
-          issue(c + 2);
-          const float* hs_ = ring + (size_t)(c % STAGES) * KC * BT + (size_t)warp * kper * BT + bg * TBT;
-          const float* ws_ = Ws + (size_t)(c * KC + warp * kper) * HS + jj * CW;
+          issue(c + p.stages - 1);
+          const float* hs_ = ring + (size_t)(c % p.stages) * kc * BT + (size_t)warp * kper * BT;
+          const float* ws_ = Ws + (size_t)(c * kc + warp * kper) * HS + jj * CW;
+          if (p.dbg & 2) continue;
 #pragma unroll 4
           for (int kk = 0; kk < kper; ++kk) {
             float w[CW];
@@ -355,12 +368,12 @@ blstm_rec_bwd_kernel(const RecParams p) {
             if (TBT >= 4) {
 #pragma unroll
               for (int v = 0; v < TBT / 4; ++v) {
-                const float4 t4 = *reinterpret_cast<const float4*>(hs_ + kk * BT + v * 4);
+                const float4 t4 = *reinterpret_cast<const float4*>(hs_ + kk * BT + tile_row<TBT>(bg, v * 4));
                 hv[v * 4 + 0] = t4.x; hv[v * 4 + 1] = t4.y; hv[v * 4 + 2] = t4.z; hv[v * 4 + 3] = t4.w;
               }
             } else {
 #pragma unroll
-              for (int r = 0; r < TBT; ++r) hv[r] = hs_[kk * BT + r];
+              for (int r = 0; r < TBT; ++r) hv[r] = hs_[kk * BT + bg * TBT + r];
             }
 #pragma unroll
             for (int r = 0; r < TBT; ++r)
@@ -374,7 +387,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
       for (int r = 0; r < TBT; ++r)
 #pragma unroll
         for (int c2 = 0; c2 < CW; ++c2)
-          red[((size_t)warp * BT + bg * TBT + r) * HS + jj * CW + c2] = acc[r][c2];
+          red[((size_t)warp * BT + tile_row<TBT>(bg, r)) * HS + jj * CW + c2] = acc[r][c2];
       __syncthreads();
 
       // ---- pointwise gate gradients ------------------------------------------------------------
@@ -436,7 +449,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Plan {
-  int tbt, hs, nsl, ndir_concurrent;
+  int tbt, hs, nsl, ndir_concurrent, bwd_kc, bwd_stages;
   size_t smem_fwd, smem_bwd;
   int Bp;
 };
@@ -459,8 +472,15 @@ int make_plan(int B, int H, Plan* pl) {
       const int ks = RNN_WARPS / (hs / 2);
       const size_t ringf = (size_t)STAGES * KC * BT;
       const size_t fwd = ((size_t)H * hs * 4 + ringf + (size_t)ks * BT * hs * 4) * sizeof(float);
-      const size_t bwd = ((size_t)4 * H * hs + ringf + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 256;
+      // backward ring: prefer 2 stages of 128 rows (half as many barriers per step), else 3 stages of 64
+      int bkc = 128, bst = 2;
+      size_t bwd = ((size_t)4 * H * hs + (size_t)bst * bkc * BT + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 256;
+      if (bwd > cap || (4 * H) % bkc) {
+        bkc = KC; bst = STAGES;
+        bwd = ((size_t)4 * H * hs + ringf + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 256;
+      }
       if (fwd > cap || bwd > cap) continue;
+      pl->bwd_kc = bkc; pl->bwd_stages = bst;
       pl->hs = hs; pl->nsl = nsl; pl->ndir_concurrent = ndir; pl->smem_fwd = fwd; pl->smem_bwd = bwd;
       return 0;
     }
@@ -475,9 +495,13 @@ int launch_rec(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t 
   const void* fn = backward ? (const void*)blstm_rec_bwd_kernel<TBT, HS> : (const void*)blstm_rec_fwd_kernel<TBT, HS>;
   const size_t smem = backward ? pl.smem_bwd : pl.smem_fwd;
   NABU_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("NABU_REC_DBG"); dbg = e ? atoi(e) : 0; }
   for (int d0 = 0; d0 < 2; d0 += pl.ndir_concurrent) {
     RecParams q = rp;
     q.dir0 = d0;
+    q.dbg = dbg;
+    q.kc = pl.bwd_kc; q.stages = pl.bwd_stages;
     void* args[] = {(void*)&q};
     KernelScope ks(backward ? "blstm_rec_bwd" : "blstm_rec_fwd", stream);
     NABU_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pl.nsl * pl.ndir_concurrent), dim3(RNN_THREADS), args,
