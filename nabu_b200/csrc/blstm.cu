@@ -34,6 +34,43 @@ constexpr int RNN_WARPS = RNN_THREADS / 32;
 constexpr int KC = 64;        // rows of the exchanged operand per pipeline stage
 constexpr int STAGES = 3;
 
+// ---- mbarrier + 1-D bulk async copy (TMA without a tensor map): the ring stages are contiguous slabs of the
+// exchange buffer, so ONE thread issues ONE instruction per stage instead of 256 threads x 16 cp.async.
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rb_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rb_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rb_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(sm_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
+}
+// Stage `c` of the current product: rows [c*kc, (c+1)*kc) of the [R][Bp] exchange slab, batch columns b0..b0+BT.
+__device__ __forceinline__ void ring_issue(float* dst, const float* src, int kc, int BT, int Bp, uint64_t* bar, int tid) {
+  if (Bp == BT) {                        // one batch tile: the stage is one contiguous slab
+    if (tid == 0) {
+      rb_expect_tx(bar, (unsigned)(kc * BT * 4));
+      bulk_g2s(dst, src, (unsigned)(kc * BT * 4), bar);
+    }
+  } else {                               // several batch tiles: one row copy per thread
+    if (tid == 0) rb_expect_tx(bar, (unsigned)(kc * BT * 4));
+    if (tid < kc) bulk_g2s(dst + (size_t)tid * BT, src + (size_t)tid * Bp, (unsigned)(BT * 4), bar);
+  }
+}
+
 struct RecParams {
   const float* kernel[2];   // [(D+H), 4H] per direction
   float* gates[2];          // [B, T, 4H]  fwd: in = Gx, out = activated i,g,f,o ; bwd: in = gates, out = dZ
@@ -101,6 +138,13 @@ blstm_rec_fwd_kernel(const RecParams p) {
   }
   __syncthreads();
 
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) rb_init(&full_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned gq = 0;                                   // ring stages consumed so far (same in every thread)
   const int cg = warp % CG, ks = warp / CG;
   const int bg = lane & 15, jj = lane >> 4;
   const int jl_mm = cg * 2 + jj;                     // hidden unit of this thread in the matmul
@@ -148,27 +192,23 @@ blstm_rec_fwd_kernel(const RecParams p) {
             const unsigned target = (unsigned)p.nsl * (unsigned)s;
             while (ld_acquire_gpu(counter) < target) { }
             __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");   // peers' generic stores -> our bulk (async proxy) loads
           }
           __syncthreads();
         }
+        const unsigned g0 = gq;
         auto issue = [&](int c) {
-          if (c < nchunks) {
-            float* dst = ring + (size_t)(c % STAGES) * KC * BT;
-            const float* src = hprev + (size_t)c * KC * p.Bp + b0;
-            for (int i = tid; i < KC * BT / 4; i += RNN_THREADS) {
-              const int row = i / (BT / 4), c4 = i % (BT / 4);
-              cp_async16(dst + row * BT + c4 * 4, src + (size_t)row * p.Bp + c4 * 4);
-            }
-          }
-          cp_async_commit();
+          if (c < nchunks)
+            ring_issue(ring + (size_t)((g0 + c) % STAGES) * KC * BT, hprev + (size_t)c * KC * p.Bp + b0, KC, BT, p.Bp,
+                       &full_bar[(g0 + c) % STAGES], tid);
         };
         issue(0);
         issue(1);
         for (int c = 0; c < nchunks; ++c) {
-          cp_async_wait<1>();
-          __syncthreads();
+          rb_wait(&full_bar[(g0 + c) % STAGES], ((g0 + c) / STAGES) & 1);
+          __syncthreads();                           // everyone is done with stage c-1 -> its buffer may be refilled
           issue(c + 2);
-          const float* hs_ = ring + (size_t)(c % STAGES) * KC * BT + (size_t)ks * kper * BT;
+          const float* hs_ = ring + (size_t)((g0 + c) % STAGES) * KC * BT + (size_t)ks * kper * BT;
           const float* ws_ = Ws + ((size_t)(c * KC + ks * kper) * HS + jl_mm) * 4;
 #pragma unroll 4
           for (int kk = 0; kk < kper; ++kk) {
@@ -193,7 +233,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
             }
           }
         }
-        cp_async_wait<0>();
+        gq = g0 + nchunks;
       }
       // ---- k-split partials -> shared ----------------------------------------------------------
 #pragma unroll
@@ -234,6 +274,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
       __syncthreads();   // red[] and ring are reused by the next tile / step
     }
     // ---- publish h_s -----------------------------------------------------------------------------
+    asm volatile("fence.proxy.async;" ::: "memory");   // our generic stores -> the peers' bulk (async proxy) loads
     __threadfence();
     __syncthreads();
     if (tid == 0) red_release_gpu_add(counter, 1u);
@@ -273,6 +314,13 @@ blstm_rec_bwd_kernel(const RecParams p) {
   }
   __syncthreads();
 
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) rb_init(&full_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned gq = 0;
   const int bg = lane & 15, jj = lane >> 4;
   const int nchunks = H4 / kc;
   const int kper = kc / RNN_WARPS;                   // all warps split every chunk
@@ -325,28 +373,24 @@ blstm_rec_bwd_kernel(const RecParams p) {
             const unsigned target = (unsigned)p.nsl * (unsigned)iter;
             while (ld_acquire_gpu(counter) < target) { }
             __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");   // peers' generic stores -> our bulk (async proxy) loads
           }
           __syncthreads();
         }
+        const unsigned g0 = gq;
+        const int S = p.stages;
         auto issue = [&](int c) {
-          if (c < nchunks && !(p.dbg & 1)) {
-            float* dst = ring + (size_t)(c % p.stages) * kc * BT;
-            const float* src = dzprev + (size_t)c * kc * p.Bp + b0;
-            for (int i = tid; i < kc * BT / 4; i += RNN_THREADS) {
-              const int row = i / (BT / 4), c4 = i % (BT / 4);
-              cp_async16(dst + row * BT + c4 * 4, src + (size_t)row * p.Bp + c4 * 4);
-            }
-          }
-          cp_async_commit();
+          if (c < nchunks && !(p.dbg & 1))
+            ring_issue(ring + (size_t)((g0 + c) % S) * kc * BT, dzprev + (size_t)c * kc * p.Bp + b0, kc, BT, p.Bp,
+                       &full_bar[(g0 + c) % S], tid);
         };
-        // ring of p.stages buffers with p.stages-1 chunks in flight
-        issue(0);
-        if (p.stages == 3) issue(1);
+        // ring of S buffers with S-1 stages in flight
+        for (int c = 0; c < S - 1; ++c) issue(c);
         for (int c = 0; c < nchunks; ++c) {
-          if (p.stages == 3) cp_async_wait<1>(); else cp_async_wait<0>();
-          __syncthreads();
-          issue(c + p.stages - 1);
-          const float* hs_ = ring + (size_t)(c % p.stages) * kc * BT + (size_t)warp * kper * BT;
+          if (!(p.dbg & 1)) rb_wait(&full_bar[(g0 + c) % S], ((g0 + c) / S) & 1);
+          __syncthreads();                           // everyone is done with stage c-1 -> its buffer may be refilled
+          issue(c + S - 1);
+          const float* hs_ = ring + (size_t)((g0 + c) % S) * kc * BT + (size_t)warp * kper * BT;
           const float* ws_ = Ws + (size_t)(c * kc + warp * kper) * HS + jj * CW;
           if (p.dbg & 2) continue;
 #pragma unroll 4
@@ -381,7 +425,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
               for (int c2 = 0; c2 < CW; ++c2) acc[r][c2] = fmaf(hv[r], w[c2], acc[r][c2]);
           }
         }
-        cp_async_wait<0>();
+        if (!(p.dbg & 1)) gq = g0 + nchunks;
       }
 #pragma unroll
       for (int r = 0; r < TBT; ++r)
@@ -425,6 +469,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
       }
       __syncthreads();
     }
+    asm volatile("fence.proxy.async;" ::: "memory");   // our generic stores -> the peers' bulk (async proxy) loads
     __threadfence();
     __syncthreads();
     if (tid == 0) red_release_gpu_add(counter, 1u);
@@ -473,7 +518,7 @@ int make_plan(int B, int H, Plan* pl) {
       const size_t ringf = (size_t)STAGES * KC * BT;
       const size_t fwd = ((size_t)H * hs * 4 + ringf + (size_t)ks * BT * hs * 4) * sizeof(float);
       // backward ring: prefer 2 stages of 128 rows (half as many barriers per step), else 3 stages of 64
-      int bkc = 128, bst = 2;
+      int bkc = 64, bst = 3;
       size_t bwd = ((size_t)4 * H * hs + (size_t)bst * bkc * BT + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 256;
       if (bwd > cap || (4 * H) % bkc) {
         bkc = KC; bst = STAGES;
