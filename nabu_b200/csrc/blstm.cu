@@ -58,16 +58,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
 }
-// Stage `c` of the current product: rows [c*kc, (c+1)*kc) of the [R][Bp] exchange slab, batch columns b0..b0+BT.
-__device__ __forceinline__ void ring_issue(float* dst, const float* src, int kc, int BT, int Bp, uint64_t* bar, int tid) {
-  if (Bp == BT) {                        // one batch tile: the stage is one contiguous slab
-    if (tid == 0) {
-      rb_expect_tx(bar, (unsigned)(kc * BT * 4));
-      bulk_g2s(dst, src, (unsigned)(kc * BT * 4), bar);
-    }
-  } else {                               // several batch tiles: one row copy per thread
-    if (tid == 0) rb_expect_tx(bar, (unsigned)(kc * BT * 4));
-    if (tid < kc) bulk_g2s(dst + (size_t)tid * BT, src + (size_t)tid * Bp, (unsigned)(BT * 4), bar);
+// Stage of the current product: `kc` rows of one batch tile's [R][BT] exchange slab (tile-major layout, so a
+// stage is one contiguous slab and ONE thread issues ONE bulk copy for it).
+__device__ __forceinline__ void ring_issue(float* dst, const float* src, int kc, int BT, uint64_t* bar, int tid) {
+  if (tid == 0) {
+    rb_expect_tx(bar, (unsigned)(kc * BT * 4));
+    bulk_g2s(dst, src, (unsigned)(kc * BT * 4), bar);
   }
 }
 
@@ -78,14 +74,16 @@ struct RecParams {
   float* y;                 // fwd: output [B, yT, 2H]
   const float* dy;          // bwd: [B, yT, 2H]
   float* dbias[2];          // bwd: [4H]
-  float* xchg;              // exchange buffer [2 dir][2 parity][R][Bp]  (R = H fwd, 4H bwd)
+  float* xchg;              // exchange buffer [2 dir][2 parity][tile][R][BT]  (R = H fwd, 4H bwd)
   float* dcbuf;             // bwd: carried dc [2 dir][Bp][H]
-  unsigned* counters;       // [2], zeroed before launch
+  unsigned* counters;       // [2 dir][8 groups], zeroed before launch
   const int* len;           // [B]
   int B, Bp, T, yT, D, H;
-  int nsl;                  // CTAs (hidden slices) per direction
+  int nsl;                  // CTAs (hidden slices) per direction and batch group
+  int ngrp;                 // batch groups: CTA (dir, grp, slice) owns batch tiles grp, grp+ngrp, ...
   int dir0;                 // first direction handled by this launch
   int kc, stages;           // bwd ring: rows per stage, number of stages
+  int fstages;              // fwd ring stages (KC rows each)
   int dbg;                  // profiling aid (NABU_REC_DBG): bit0 = skip the ring loads, bit1 = skip the FMAs
 };
 
@@ -111,7 +109,7 @@ struct RecCfg {
 // forward
 // ---------------------------------------------------------------------------------------------
 template <int TBT, int HS>
-__global__ void __launch_bounds__(RNN_THREADS, 1)
+__global__ void __launch_bounds__(RNN_THREADS, (TBT <= 4) ? 2 : 1)
 blstm_rec_fwd_kernel(const RecParams p) {
   using C = RecCfg<TBT, HS>;
   constexpr int BT = C::BT, CG = C::CG, KS = C::KS, PP = C::PP;
@@ -119,16 +117,18 @@ blstm_rec_fwd_kernel(const RecParams p) {
   const int H = p.H, H4 = 4 * p.H;
   float* Ws = smem;                                  // [H][HS][4]
   float* ring = Ws + (size_t)H * HS * 4;             // [STAGES][KC][BT]
-  float* red = ring + (size_t)STAGES * KC * BT;      // [KS][BT][HS][4]
+  const int S = p.fstages;
+  float* red = ring + (size_t)S * KC * BT;           // [KS][BT][HS][4]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int dir = p.dir0 + blockIdx.x / p.nsl;
+  const int dir = p.dir0 + blockIdx.x / (p.nsl * p.ngrp);
+  const int grp = (blockIdx.x / p.nsl) % p.ngrp;
   const int slice = blockIdx.x % p.nsl;
   const int j0 = slice * HS;
   const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
   float* gates = p.gates[dir];
   float* cells = p.cells[dir];
-  unsigned* counter = p.counters + dir;
+  unsigned* counter = p.counters + dir * 8 + grp;
   float* hx = p.xchg + (size_t)dir * 2 * H * p.Bp;   // [2][H][Bp]
 
   // resident weight slice: Ws[k][jl][g] = Kh[k][g*H + j0 + jl]
@@ -155,7 +155,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
   for (int s = 0; s < p.T; ++s) {
     const float* hprev = hx + (size_t)((s + 1) & 1) * H * p.Bp;   // written at step s-1
     float* hnext = hx + (size_t)(s & 1) * H * p.Bp;
-    for (int tile = 0; tile < ntile; ++tile) {
+    for (int tile = grp; tile < ntile; tile += p.ngrp) {
       const int b0 = tile * BT;
       // ---- prefetch the pointwise operands of this thread's (b, j) pairs -----------------------
       float gx[PP][4], cprev[PP];
@@ -187,7 +187,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
       for (int r = 0; r < TBT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
 
       if (s > 0) {
-        if (tile == 0) {
+        if (tile == grp) {
           if (tid == 0) {
             const unsigned target = (unsigned)p.nsl * (unsigned)s;
             while (ld_acquire_gpu(counter) < target) { }
@@ -199,16 +199,15 @@ blstm_rec_fwd_kernel(const RecParams p) {
         const unsigned g0 = gq;
         auto issue = [&](int c) {
           if (c < nchunks)
-            ring_issue(ring + (size_t)((g0 + c) % STAGES) * KC * BT, hprev + (size_t)c * KC * p.Bp + b0, KC, BT, p.Bp,
-                       &full_bar[(g0 + c) % STAGES], tid);
+            ring_issue(ring + (size_t)((g0 + c) % S) * KC * BT, hprev + ((size_t)tile * H + (size_t)c * KC) * BT, KC, BT,
+                       &full_bar[(g0 + c) % S], tid);
         };
-        issue(0);
-        issue(1);
+        for (int c = 0; c < S - 1; ++c) issue(c);
         for (int c = 0; c < nchunks; ++c) {
-          rb_wait(&full_bar[(g0 + c) % STAGES], ((g0 + c) / STAGES) & 1);
+          rb_wait(&full_bar[(g0 + c) % S], ((g0 + c) / S) & 1);
           __syncthreads();                           // everyone is done with stage c-1 -> its buffer may be refilled
-          issue(c + 2);
-          const float* hs_ = ring + (size_t)((g0 + c) % STAGES) * KC * BT + (size_t)ks * kper * BT;
+          issue(c + S - 1);
+          const float* hs_ = ring + (size_t)((g0 + c) % S) * KC * BT + (size_t)ks * kper * BT;
           const float* ws_ = Ws + ((size_t)(c * KC + ks * kper) * HS + jl_mm) * 4;
 #pragma unroll 4
           for (int kk = 0; kk < kper; ++kk) {
@@ -268,7 +267,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
             __stcg(cells + ((size_t)b * p.T + t) * H + j0 + jl, cn);
           }
           __stcg(p.y + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl, valid[q] ? hn : 0.f);
-          __stcg(hnext + (size_t)(j0 + jl) * p.Bp + b, valid[q] ? hn : 0.f);
+          __stcg(hnext + ((size_t)tile * H + j0 + jl) * BT + bl, valid[q] ? hn : 0.f);
         }
       }
       __syncthreads();   // red[] and ring are reused by the next tile / step
@@ -285,7 +284,7 @@ blstm_rec_fwd_kernel(const RecParams p) {
 // backward
 // ---------------------------------------------------------------------------------------------
 template <int TBT, int HS>
-__global__ void __launch_bounds__(RNN_THREADS, 1)
+__global__ void __launch_bounds__(RNN_THREADS, (TBT <= 4) ? 2 : 1)
 blstm_rec_bwd_kernel(const RecParams p) {
   using C = RecCfg<TBT, HS>;
   constexpr int BT = C::BT, PP = C::PP;
@@ -298,13 +297,14 @@ blstm_rec_bwd_kernel(const RecParams p) {
   float* red = ring + (size_t)p.stages * kc * BT;    // [RNN_WARPS][BT][HS]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int dir = p.dir0 + blockIdx.x / p.nsl;
+  const int dir = p.dir0 + blockIdx.x / (p.nsl * p.ngrp);
+  const int grp = (blockIdx.x / p.nsl) % p.ngrp;
   const int slice = blockIdx.x % p.nsl;
   const int j0 = slice * HS;
   const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
   float* gates = p.gates[dir];
   const float* cells = p.cells[dir];
-  unsigned* counter = p.counters + dir;
+  unsigned* counter = p.counters + dir * 8 + grp;
   float* dzx = p.xchg + (size_t)dir * 2 * H4 * p.Bp; // [2][4H][Bp]
   float* dcb = p.dcbuf + (size_t)dir * p.Bp * H;     // [Bp][H]
 
@@ -331,7 +331,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
   for (int s = p.T - 1; s >= 0; --s, ++iter) {
     const float* dzprev = dzx + (size_t)((iter + 1) & 1) * H4 * p.Bp;   // published at iter-1 (step s+1)
     float* dznext = dzx + (size_t)(iter & 1) * H4 * p.Bp;
-    for (int tile = 0; tile < ntile; ++tile) {
+    for (int tile = grp; tile < ntile; tile += p.ngrp) {
       const int b0 = tile * BT;
       // ---- prefetch pointwise operands ---------------------------------------------------------
       float gt[PP][4], ct[PP], cprev[PP], dyv[PP], dcr[PP];
@@ -368,7 +368,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
         for (int c = 0; c < CW; ++c) acc[r][c] = 0.f;
 
       if (iter > 0) {
-        if (tile == 0) {
+        if (tile == grp) {
           if (tid == 0) {
             const unsigned target = (unsigned)p.nsl * (unsigned)iter;
             while (ld_acquire_gpu(counter) < target) { }
@@ -381,7 +381,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
         const int S = p.stages;
         auto issue = [&](int c) {
           if (c < nchunks && !(p.dbg & 1))
-            ring_issue(ring + (size_t)((g0 + c) % S) * kc * BT, dzprev + (size_t)c * kc * p.Bp + b0, kc, BT, p.Bp,
+            ring_issue(ring + (size_t)((g0 + c) % S) * kc * BT, dzprev + ((size_t)tile * H4 + (size_t)c * kc) * BT, kc, BT,
                        &full_bar[(g0 + c) % S], tid);
         };
         // ring of S buffers with S-1 stages in flight
@@ -461,7 +461,7 @@ blstm_rec_bwd_kernel(const RecParams p) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             __stcg(gp + g * H, dz[g]);
-            __stcg(dznext + (size_t)(g * H + j0 + jl) * p.Bp + b, dz[g]);
+            __stcg(dznext + ((size_t)tile * H4 + g * H + j0 + jl) * BT + bl, dz[g]);
             dbacc[g] += dz[g];
           }
           __stcg(dcb + (size_t)b * H + j0 + jl, dcn);
@@ -494,18 +494,21 @@ blstm_rec_bwd_kernel(const RecParams p) {
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Plan {
-  int tbt, hs, nsl, ndir_concurrent, bwd_kc, bwd_stages;
+  int tbt, hs, nsl, ngrp, ndir_concurrent, bwd_kc, bwd_stages, fwd_stages, ctas_per_sm;
   size_t smem_fwd, smem_bwd;
-  int Bp;
 };
 
-int make_plan(int B, int H, Plan* pl) {
+// split = true: batch tiles of 64 rows, each owned by its own set of CTAs, two CTAs per SM -- while one batch
+// group waits on its per-step handshake (about 10 us of fences, polling and barriers) the other one computes.
+int make_plan(int B, int H, bool split, Plan* pl) {
   NABU_REQUIRE(H % KC == 0, "blstm: num_units=%d must be a multiple of %d", H, KC);
-  pl->tbt = B <= 16 ? 1 : B <= 32 ? 2 : B <= 64 ? 4 : 8;
+  pl->tbt = split ? 4 : (B <= 16 ? 1 : B <= 32 ? 2 : B <= 64 ? 4 : 8);
   const int BT = 16 * pl->tbt;
-  pl->Bp = ceil_div(B, BT) * BT;
+  pl->ngrp = split ? ceil_div(B, BT) : 1;
+  pl->ctas_per_sm = split ? 2 : 1;
+  if (split && (pl->ngrp < 2 || pl->ngrp > 8)) return 3;
   const int sms = num_sms();
-  const size_t cap = (size_t)max_smem_optin();
+  const size_t cap = split ? (size_t)(233472 - 2048) / 2 : (size_t)max_smem_optin();
   const int cand[4] = {2, 4, 8, 16};
   for (int pass = 0; pass < 2; ++pass) {          // pass 0: both directions concurrently
     const int ndir = pass == 0 ? 2 : 1;
@@ -513,23 +516,20 @@ int make_plan(int B, int H, Plan* pl) {
       const int hs = cand[ci];
       if (H % hs) continue;
       const int nsl = H / hs;
-      if (ndir * nsl > sms) continue;
+      if (ndir * nsl * pl->ngrp > sms * pl->ctas_per_sm) continue;
+      if (ndir * nsl > sms) continue;               // keep at most one CTA of a batch group per SM
       const int ks = RNN_WARPS / (hs / 2);
-      const size_t ringf = (size_t)STAGES * KC * BT;
-      const size_t fwd = ((size_t)H * hs * 4 + ringf + (size_t)ks * BT * hs * 4) * sizeof(float);
-      // backward ring: prefer 2 stages of 128 rows (half as many barriers per step), else 3 stages of 64
-      int bkc = 64, bst = 3;
-      size_t bwd = ((size_t)4 * H * hs + (size_t)bst * bkc * BT + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 256;
-      if (bwd > cap || (4 * H) % bkc) {
-        bkc = KC; bst = STAGES;
-        bwd = ((size_t)4 * H * hs + ringf + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 256;
+      for (int st = STAGES; st >= 2; --st) {
+        const size_t fwd = ((size_t)H * hs * 4 + (size_t)st * KC * BT + (size_t)ks * BT * hs * 4) * sizeof(float) + 64;
+        const size_t bwd = ((size_t)4 * H * hs + (size_t)st * KC * BT + (size_t)RNN_WARPS * BT * hs) * sizeof(float) + 64;
+        if (fwd > cap || bwd > cap) continue;
+        pl->bwd_kc = KC; pl->bwd_stages = st; pl->fwd_stages = st;
+        pl->hs = hs; pl->nsl = nsl; pl->ndir_concurrent = ndir; pl->smem_fwd = fwd; pl->smem_bwd = bwd;
+        return 0;
       }
-      if (fwd > cap || bwd > cap) continue;
-      pl->bwd_kc = bkc; pl->bwd_stages = bst;
-      pl->hs = hs; pl->nsl = nsl; pl->ndir_concurrent = ndir; pl->smem_fwd = fwd; pl->smem_bwd = bwd;
-      return 0;
     }
   }
+  if (split) return 3;
   set_error("blstm: num_units=%d does not fit the persistent kernel (needs H/hs <= %d CTAs and the Kh slice in %zu B shared memory)",
             H, sms, cap);
   return 2;
@@ -540,17 +540,21 @@ int launch_rec(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t 
   const void* fn = backward ? (const void*)blstm_rec_bwd_kernel<TBT, HS> : (const void*)blstm_rec_fwd_kernel<TBT, HS>;
   const size_t smem = backward ? pl.smem_bwd : pl.smem_fwd;
   NABU_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = pl.nsl * pl.ngrp * pl.ndir_concurrent;
+  int per_sm = 0;
+  NABU_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RNN_THREADS, smem));
+  if (per_sm * num_sms() < grid) return 3;          // not co-resident: the caller falls back to the unsplit plan
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("NABU_REC_DBG"); dbg = e ? atoi(e) : 0; }
   for (int d0 = 0; d0 < 2; d0 += pl.ndir_concurrent) {
     RecParams q = rp;
     q.dir0 = d0;
     q.dbg = dbg;
-    q.kc = pl.bwd_kc; q.stages = pl.bwd_stages;
+    q.kc = pl.bwd_kc; q.stages = pl.bwd_stages; q.fstages = pl.fwd_stages;
+    q.nsl = pl.nsl; q.ngrp = pl.ngrp;
     void* args[] = {(void*)&q};
     KernelScope ks(backward ? "blstm_rec_bwd" : "blstm_rec_fwd", stream);
-    NABU_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pl.nsl * pl.ndir_concurrent), dim3(RNN_THREADS), args,
-                                                smem, stream));
+    NABU_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RNN_THREADS), args, smem, stream));
   }
   return 0;
 }
@@ -578,11 +582,33 @@ int dispatch(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t st
   return 2;
 }
 
+// Launch the recurrence: batch-group split (two CTAs per SM) when the batch is large enough and it is co-resident,
+// else one CTA per (direction, slice).  NABU_REC_SPLIT=0 disables the split.
+int run_recurrence(bool backward, RecParams rp, int B, int H, cudaStream_t stream) {
+  static int use_split = -1;
+  if (use_split < 0) {
+    const char* e = getenv("NABU_REC_SPLIT");
+    use_split = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  Plan pl;
+  if (use_split && B > 64 && make_plan(B, H, true, &pl) == 0) {
+    rp.Bp = pl.ngrp * 16 * pl.tbt;
+    const int e = dispatch(backward, rp, pl, stream);
+    if (e != 3) return e;
+  }
+  if (int e = make_plan(B, H, false, &pl)) return e;
+  rp.Bp = ceil_div(B, 16 * pl.tbt) * 16 * pl.tbt;
+  const int e = dispatch(backward, rp, pl, stream);
+  NABU_REQUIRE(e != 3, "blstm: the persistent kernel is not co-resident on this device");
+  return e;
+}
+
 // workspace layout: [counters 256 B][exchange 2*2*4H*Bp floats][dcbuf 2*Bp*H floats][gemm scratch]
 struct Ws {
   unsigned* counters; float* xchg; float* dcbuf; float* gemm; size_t gemm_bytes; size_t total;
 };
-Ws carve(void* base, int H, int Bp) {
+Ws carve(void* base, int H, int B) {
+  const int Bp = ceil_div(B, 128) * 128;
   Ws w;
   size_t off = 0;
   char* b = (char*)base;
@@ -606,8 +632,8 @@ using namespace nabu;
 extern "C" size_t nabu_blstm_workspace_bytes(int B, int T, int D, int H) {
   (void)T; (void)D;
   Plan pl;
-  if (make_plan(B, H, &pl)) return 0;
-  return carve(nullptr, H, pl.Bp).total;
+  if (make_plan(B, H, false, &pl)) return 0;
+  return carve(nullptr, H, B).total;
 }
 
 extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int D, int H,
@@ -616,9 +642,7 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
                               void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_fwd: bad shape B=%d T=%d D=%d H=%d yT=%d", B, T, D, H, yT);
-  Plan pl;
-  if (int e = make_plan(B, H, &pl)) return e;
-  Ws w = carve(workspace, H, pl.Bp);
+  Ws w = carve(workspace, H, B);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
   const int H4 = 4 * H;
   const float* kern[2] = {kernel_fw, kernel_bw};
@@ -633,24 +657,26 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   if (yT > T)
     NABU_CHECK_CUDA(cudaMemset2DAsync(y + (size_t)T * 2 * H, (size_t)yT * 2 * H * sizeof(float), 0,
                                       (size_t)(yT - T) * 2 * H * sizeof(float), B, stream));
+  // The tcgen05 recurrence (blstm_tc.cu) is opt-in (NABU_REC=tc): measured 20.8 us/step at cfg-3, the FFMA kernel
+  // with the batch-group split is faster; see DESIGN.md section 6.
   static int use_tc = -1;
   if (use_tc < 0) {
     const char* e = getenv("NABU_REC");
-    use_tc = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    use_tc = (e && strcmp(e, "tc") == 0) ? 1 : 0;
   }
   BlstmTcPlan tpl;
   if (use_tc && blstm_tc_plan(B, H, &tpl)) {
     NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)4 * 128 * H * sizeof(float), stream));
     return blstm_rec_fwd_tc(tpl, kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream);
   }
-  NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * pl.Bp * sizeof(float), stream));
+  NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * (ceil_div(B, 128) * 128) * sizeof(float), stream));
   RecParams rp = {};
   rp.kernel[0] = kern[0]; rp.kernel[1] = kern[1];
   rp.gates[0] = g[0]; rp.gates[1] = g[1];
   rp.cells[0] = c[0]; rp.cells[1] = c[1];
   rp.y = y; rp.xchg = w.xchg; rp.counters = w.counters; rp.len = len;
-  rp.B = B; rp.Bp = pl.Bp; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H; rp.nsl = pl.nsl;
-  return dispatch(false, rp, pl, stream);
+  rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
+  return run_recurrence(false, rp, B, H, stream);
 }
 
 extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int D, int H,
@@ -660,9 +686,7 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
                               void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_bwd: bad shape");
-  Plan pl;
-  if (int e = make_plan(B, H, &pl)) return e;
-  Ws w = carve(workspace, H, pl.Bp);
+  Ws w = carve(workspace, H, B);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
   const int H4 = 4 * H;
   const float* kern[2] = {kernel_fw, kernel_bw};
@@ -676,8 +700,8 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   rp.cells[0] = (float*)c[0]; rp.cells[1] = (float*)c[1];
   rp.dy = dy; rp.dbias[0] = dbias_fw; rp.dbias[1] = dbias_bw;
   rp.xchg = w.xchg; rp.dcbuf = w.dcbuf; rp.counters = w.counters; rp.len = len;
-  rp.B = B; rp.Bp = pl.Bp; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H; rp.nsl = pl.nsl;
-  if (int e = dispatch(true, rp, pl, stream)) return e;
+  rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
+  if (int e = run_recurrence(true, rp, B, H, stream)) return e;
   // gates[] now hold dZ (zero for t >= len)
   for (int d = 0; d < 2; ++d) {
     // dKx = X^T . dZ
