@@ -74,6 +74,7 @@ struct RecParams {
   float* y;                 // fwd: output [B, yT, 2H]
   const float* dy;          // bwd: [B, yT, 2H]
   float* dbias[2];          // bwd: [4H]
+  float* dbpart;            // bwd: per batch-group partials [2 dir][8 grp][4H]
   float* xchg;              // exchange buffer [2 dir][2 parity][tile][R][BT]  (R = H fwd, 4H bwd)
   float* dcbuf;             // bwd: carried dc [2 dir][Bp][H]
   unsigned* counters;       // [2 dir][8 groups], zeroed before launch
@@ -485,9 +486,18 @@ blstm_rec_bwd_kernel(const RecParams p) {
       const int g = tid / HS, j = tid % HS;
       float sum = 0.f;
       for (int i = j; i < RNN_THREADS; i += HS) sum += ring[i * 4 + g];
-      p.dbias[dir][g * H + j0 + j] = sum;
+      p.dbpart[((size_t)dir * 8 + grp) * H4 + g * H + j0 + j] = sum;
     }
   }
+}
+
+__global__ void sum_groups_kernel(const float* part, int ngrp, int n, float* out0, float* out1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n) return;
+  const int dir = i / n, k = i % n;
+  float s = 0.f;
+  for (int g = 0; g < ngrp; ++g) s += part[((size_t)dir * 8 + g) * n + k];
+  (dir ? out1 : out0)[k] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -583,21 +593,23 @@ int dispatch(bool backward, const RecParams& rp, const Plan& pl, cudaStream_t st
 }
 
 // Launch the recurrence: batch-group split (two CTAs per SM) when the batch is large enough and it is co-resident,
-// else one CTA per (direction, slice).  NABU_REC_SPLIT=0 disables the split.
-int run_recurrence(bool backward, RecParams rp, int B, int H, cudaStream_t stream) {
+// else one CTA per (direction, slice).  NABU_REC_SPLIT=1 enables the split.
+int run_recurrence(bool backward, RecParams rp, int B, int H, cudaStream_t stream, int* ngrp_used = nullptr) {
   static int use_split = -1;
   if (use_split < 0) {
     const char* e = getenv("NABU_REC_SPLIT");
-    use_split = (e && strcmp(e, "0") == 0) ? 0 : 1;
+    use_split = (e && strcmp(e, "1") == 0) ? 1 : 0;     // opt-in: measured no gain at cfg-3 (547 vs 550 ms/step)
   }
   Plan pl;
   if (use_split && B > 64 && make_plan(B, H, true, &pl) == 0) {
     rp.Bp = pl.ngrp * 16 * pl.tbt;
     const int e = dispatch(backward, rp, pl, stream);
+    if (ngrp_used) *ngrp_used = pl.ngrp;
     if (e != 3) return e;
   }
   if (int e = make_plan(B, H, false, &pl)) return e;
   rp.Bp = ceil_div(B, 16 * pl.tbt) * 16 * pl.tbt;
+  if (ngrp_used) *ngrp_used = 1;
   const int e = dispatch(backward, rp, pl, stream);
   NABU_REQUIRE(e != 3, "blstm: the persistent kernel is not co-resident on this device");
   return e;
@@ -605,7 +617,7 @@ int run_recurrence(bool backward, RecParams rp, int B, int H, cudaStream_t strea
 
 // workspace layout: [counters 256 B][exchange 2*2*4H*Bp floats][dcbuf 2*Bp*H floats][gemm scratch]
 struct Ws {
-  unsigned* counters; float* xchg; float* dcbuf; float* gemm; size_t gemm_bytes; size_t total;
+  unsigned* counters; float* xchg; float* dcbuf; float* dbpart; float* gemm; size_t gemm_bytes; size_t total;
 };
 Ws carve(void* base, int H, int B) {
   const int Bp = ceil_div(B, 128) * 128;
@@ -619,6 +631,7 @@ Ws carve(void* base, int H, int B) {
     w.xchg = (float*)(b + off); off += align_up(xf * sizeof(float), 256);
   }
   w.dcbuf = (float*)(b + off); off += align_up((size_t)2 * Bp * H * sizeof(float), 256);
+  w.dbpart = (float*)(b + off); off += align_up((size_t)2 * 8 * 4 * H * sizeof(float), 256);
   w.gemm = (float*)(b + off); w.gemm_bytes = sgemm_workspace_bytes(); off += w.gemm_bytes;
   w.total = off;
   return w;
@@ -699,9 +712,15 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   rp.gates[0] = g[0]; rp.gates[1] = g[1];
   rp.cells[0] = (float*)c[0]; rp.cells[1] = (float*)c[1];
   rp.dy = dy; rp.dbias[0] = dbias_fw; rp.dbias[1] = dbias_bw;
-  rp.xchg = w.xchg; rp.dcbuf = w.dcbuf; rp.counters = w.counters; rp.len = len;
+  rp.xchg = w.xchg; rp.dcbuf = w.dcbuf; rp.dbpart = w.dbpart; rp.counters = w.counters; rp.len = len;
   rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
-  if (int e = run_recurrence(true, rp, B, H, stream)) return e;
+  int ngrp = 1;
+  if (int e = run_recurrence(true, rp, B, H, stream, &ngrp)) return e;
+  {
+    KernelScope ks("sum_groups", stream);
+    sum_groups_kernel<<<ceil_div(2 * H4, 256), 256, 0, stream>>>(w.dbpart, ngrp, H4, dbias_fw, dbias_bw);
+    NABU_CHECK_LAUNCH();
+  }
   // gates[] now hold dZ (zero for t >= len)
   for (int d = 0; d < 2; ++d) {
     // dKx = X^T . dZ
