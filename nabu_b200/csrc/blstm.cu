@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "blstm_tc.h"
+#include "blstm_cl.h"
 #include "nabu_b200.h"
 #include <stdlib.h>
 #include <string.h>
@@ -715,7 +716,15 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   rp.xchg = w.xchg; rp.dcbuf = w.dcbuf; rp.dbpart = w.dbpart; rp.counters = w.counters; rp.len = len;
   rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
   int ngrp = 1;
-  if (int e = run_recurrence(true, rp, B, H, stream, &ngrp)) return e;
+  bool launched = false;
+  if (blstm_bwd_cluster_eligible(B, H)) {
+    const float* cc[2] = {c[0], c[1]};
+    if (int e = blstm_rec_bwd_cluster(kern, g, cc, dy, w.dbpart, w.xchg, w.dcbuf, w.counters, len, B, T, yT, D, H, stream,
+                                      &launched))
+      return e;
+  }
+  if (!launched)
+    if (int e = run_recurrence(true, rp, B, H, stream, &ngrp)) return e;
   {
     KernelScope ks("sum_groups", stream);
     sum_groups_kernel<<<ceil_div(2 * H4, 256), 256, 0, stream>>>(w.dbpart, ngrp, H4, dbias_fw, dbias_bw);

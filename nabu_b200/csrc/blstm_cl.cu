@@ -1,0 +1,350 @@
+// Cluster K-split version of the BLSTM backward recurrence (row a1; semantics in blstm.cu).
+//
+// dh_{t-1}[B,H] = dz_t[B,4H] . Kh^T: with the flat partition of blstm.cu every CTA owns 8 outputs and must
+// stream the whole dz_t (1 MB at cfg-3) every step, in 64-row chunks with a barrier and an 8-way smem
+// reduction per chunk -- measured 32 us per step, loads and FFMA not overlapping.  Here
+//   * a thread-block CLUSTER of 8 CTAs owns 8*HS hidden units (64 at H=512); CTA r of every cluster multiplies
+//     only the K-slice of dz that cluster r of the same direction produces (4 gates x 64 units = 256 columns,
+//     128 KB per step instead of 1 MB, fetched as four 32 KB bulk copies through a 2-stage ring) against a
+//     resident [256 x 64] slice of Kh^T -- a straight, barrier-free 256-deep FFMA loop with no k-split;
+//   * the 8 partial [B x 64] products of a cluster are reduce-scattered through distributed shared memory:
+//     warp w of every CTA holds exactly the columns CTA w owns and stores them into CTA w's receive buffer
+//     (st.shared::cluster, 32 KB in per CTA), one cluster barrier, then each CTA sums its 8 partials in a fixed
+//     order (bit-reproducible) and does the pointwise gate gradients for its own HS units as before;
+//   * dz_t is handed between clusters through L2 with one release/acquire counter PER CLUSTER, so a CTA only
+//     waits for the 8 producers of its own K-slice, not for the whole direction.
+#include "common.cuh"
+#include "blstm_cl.h"
+#include <stdlib.h>
+#include <string.h>
+
+namespace nabu {
+namespace {
+
+constexpr int CL = 8;                 // CTAs per cluster = K-slices = warps per CTA
+constexpr int CL_THREADS = 256;
+
+struct ClParams {
+  const float* kernel[2];
+  float* gates[2];          // in: activated i,g,f,o ; out: dZ
+  const float* cells[2];
+  const float* dy;
+  float* dbpart;            // [2 dir][8][4H] (slot 0 used)
+  float* xchg;              // [2 dir][2 parity][8 cluster][4 gate][8*HS unit][BT]
+  float* dcbuf;             // [2 dir][BT][H]
+  unsigned* counters;       // [2 dir][8 cluster]
+  const int* len;
+  int B, T, yT, D, H;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cb_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cb_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cb_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(s_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cb_bulk(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int TBT>
+__device__ __forceinline__ int cl_row(int bg, int r) {     // see tile_row in blstm.cu
+  return TBT == 8 ? ((r >> 2) * 64 + bg * 4 + (r & 3)) : bg * TBT + r;
+}
+
+template <int TBT, int HS>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+blstm_rec_bwd_cluster_kernel(const ClParams p) {
+  constexpr int BT = 16 * TBT;             // batch rows (one tile)
+  constexpr int NC = CL * HS;              // hidden units (= output columns) per cluster
+  constexpr int CW = HS >= 2 ? HS / 2 : 1; // output columns per lane
+  constexpr int PAIRS = BT * HS;
+  constexpr int PP = (PAIRS + CL_THREADS - 1) / CL_THREADS;
+  extern __shared__ __align__(16) float smem[];
+  float* Wl = smem;                                   // [4*NC][NC]   Wl[g*NC+u][n] = Kh[NC*q+n][g*H + NC*r + u]
+  float* ring = Wl + 4 * NC * NC;                     // [2][NC][BT]
+  float* rbuf = ring + 2 * NC * BT;                   // [2 parity][CL src][BT][HS]
+  __shared__ __align__(8) uint64_t full_bar[2];
+
+  const int H = p.H, H4 = 4 * p.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per_dir = H / HS;                         // CTAs per direction (= 8 clusters of 8)
+  const int dir = blockIdx.x / per_dir;
+  const int q = (blockIdx.x % per_dir) / CL;          // cluster within the direction
+  const int r = blockIdx.x % CL;                      // rank in the cluster == K-slice
+  const int j0 = (q * CL + r) * HS;                   // own hidden units
+  const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
+  float* gates = p.gates[dir];
+  const float* cells = p.cells[dir];
+  unsigned* cnt = p.counters + dir * 8;
+  float* dzx = p.xchg + (size_t)dir * 2 * H4 * BT;    // [2 parity][8 cluster][4][NC][BT]
+  float* dcb = p.dcbuf + (size_t)dir * BT * H;
+
+  for (int i = tid; i < 4 * NC * NC; i += CL_THREADS) {
+    const int n = i % NC, kl = i / NC, g = kl / NC, u = kl % NC;
+    Wl[i] = Kh[(size_t)(NC * q + n) * H4 + g * H + NC * r + u];
+  }
+  if (tid == 0) {
+    cb_init(&full_bar[0], 1);
+    cb_init(&full_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // peers' smem exists before anyone stores into it
+
+  const int bg = lane & 15, jj = lane >> 4;
+  const int ncol0 = HS * warp + jj * CW;               // first of this lane's output columns (owned by CTA `warp`)
+  const uint32_t rbuf_remote = map_to_rank(s_u32(rbuf), (uint32_t)warp);
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned useq = 0;                                   // gate blocks consumed so far
+
+  int iter = 0;
+  for (int s = p.T - 1; s >= 0; --s, ++iter) {
+    const float* dzprev = dzx + (size_t)((iter + 1) & 1) * H4 * BT;
+    float* dznext = dzx + (size_t)(iter & 1) * H4 * BT;
+    float* rb = rbuf + (size_t)(iter & 1) * CL * BT * HS;
+    // ---- prefetch pointwise operands -----------------------------------------------------------
+    float gt[PP][4], ct[PP], cprev[PP], dyv[PP], dcr[PP];
+    int tb[PP];
+    bool valid[PP];
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      const int pr = tid + k * CL_THREADS;
+      const int jl = pr % HS, b = pr / HS;
+      valid[k] = false; tb[k] = 0; ct[k] = cprev[k] = dyv[k] = dcr[k] = 0.f;
+      gt[k][0] = gt[k][1] = gt[k][2] = gt[k][3] = 0.f;
+      if (pr < PAIRS && b < p.B) {
+        const int L = p.len[b];
+        valid[k] = s < L;
+        const int t = valid[k] ? (dir ? L - 1 - s : s) : s;
+        tb[k] = t;
+        if (valid[k]) {
+          const float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) gt[k][g] = __ldcg(gp + g * H);
+          ct[k] = __ldcg(cells + ((size_t)b * p.T + t) * H + j0 + jl);
+          if (s > 0) cprev[k] = __ldcg(cells + ((size_t)b * p.T + (dir ? t + 1 : t - 1)) * H + j0 + jl);
+          dyv[k] = __ldcg(p.dy + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl);
+          if (iter > 0) dcr[k] = __ldcg(dcb + (size_t)b * H + j0 + jl);
+        }
+      }
+    }
+
+    if (iter > 0) {
+      // ---- partial[b, n] = sum over my K-slice of dz_{s+1}[k][b] * Wl[k][n] ------------------------
+      float acc[TBT][CW];
+#pragma unroll
+      for (int i = 0; i < TBT; ++i)
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[i][c] = 0.f;
+      const float* slab = dzprev + (size_t)r * 4 * NC * BT;          // produced by cluster r
+      if (tid == 0) {
+        const unsigned target = (unsigned)CL * (unsigned)iter;
+        while (ld_acquire_gpu(cnt + r) < target) { }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int g = 0; g < 2; ++g) {
+          uint64_t* bar = &full_bar[(useq + g) & 1];
+          cb_expect_tx(bar, NC * BT * 4);
+          cb_bulk(ring + (size_t)((useq + g) & 1) * NC * BT, slab + (size_t)g * NC * BT, NC * BT * 4, bar);
+        }
+      }
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g, ++useq) {
+        cb_wait(&full_bar[useq & 1], (useq >> 1) & 1);
+        const float* hs_ = ring + (size_t)(useq & 1) * NC * BT;
+        const float* ws_ = Wl + (size_t)g * NC * NC + ncol0;
+#pragma unroll 4
+        for (int kk = 0; kk < NC; ++kk) {
+          float w[CW];
+          if (CW == 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(ws_ + kk * NC);
+            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[CW - 1] = w4.w;
+          } else if (CW == 2) {
+            const float2 w2 = *reinterpret_cast<const float2*>(ws_ + kk * NC);
+            w[0] = w2.x; w[CW - 1] = w2.y;
+          } else {
+            w[0] = ws_[kk * NC];
+          }
+          float hv[TBT];
+#pragma unroll
+          for (int v = 0; v < TBT / 4; ++v) {
+            const float4 t4 = *reinterpret_cast<const float4*>(hs_ + kk * BT + cl_row<TBT>(bg, v * 4));
+            hv[v * 4 + 0] = t4.x; hv[v * 4 + 1] = t4.y; hv[v * 4 + 2] = t4.z; hv[v * 4 + 3] = t4.w;
+          }
+#pragma unroll
+          for (int i = 0; i < TBT; ++i)
+#pragma unroll
+            for (int c = 0; c < CW; ++c) acc[i][c] = fmaf(hv[i], w[c], acc[i][c]);
+        }
+        if (g + 2 < 4) {
+          __syncthreads();                              // every warp is done with this ring buffer
+          if (tid == 0) {
+            uint64_t* bar = &full_bar[useq & 1];
+            cb_expect_tx(bar, NC * BT * 4);
+            cb_bulk(ring + (size_t)(useq & 1) * NC * BT, slab + (size_t)(g + 2) * NC * BT, NC * BT * 4, bar);
+          }
+        }
+      }
+      // ---- reduce-scatter: my columns HS*warp .. belong to CTA `warp` -----------------------------------
+      const uint32_t dst = rbuf_remote + (uint32_t)(((size_t)(iter & 1) * CL + r) * BT * HS) * 4u;
+#pragma unroll
+      for (int i = 0; i < TBT; ++i) {
+        const uint32_t a = dst + (uint32_t)(cl_row<TBT>(bg, i) * HS + jj * CW) * 4u;
+        if (CW == 4) st_cluster_v4(a, acc[i][0], acc[i][1], acc[i][2], acc[i][CW - 1]);
+        else if (CW == 2) st_cluster_v2(a, acc[i][0], acc[i][CW - 1]);
+        else st_cluster_f32(a, acc[i][0]);
+      }
+      cluster_sync_all();
+    }
+
+    // ---- pointwise gate gradients for my HS units -------------------------------------------------------
+    float* dzmine = dznext + ((size_t)q * 4 * NC) * BT;                // my cluster's slab
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      const int pr = tid + k * CL_THREADS;
+      const int jl = pr % HS, b = pr / HS;
+      if (pr < PAIRS && b < p.B) {
+        float dh = dyv[k];
+        if (iter > 0) {
+#pragma unroll
+          for (int src = 0; src < CL; ++src) dh += rb[((size_t)src * BT + b) * HS + jl];
+        }
+        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+        float dcn = 0.f;
+        if (valid[k]) {
+          const float ig = gt[k][0], gg = gt[k][1], fg = gt[k][2], og = gt[k][3];
+          const float tc = tanhf(ct[k]);
+          const float d_o = dh * tc;
+          const float dc = dcr[k] + dh * og * (1.f - tc * tc);
+          dz[0] = dc * gg * ig * (1.f - ig);
+          dz[1] = dc * ig * (1.f - gg * gg);
+          dz[2] = dc * cprev[k] * fg * (1.f - fg);
+          dz[3] = d_o * og * (1.f - og);
+          dcn = dc * fg;
+        }
+        const int t = tb[k];
+        float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __stcg(gp + g * H, dz[g]);
+          __stcg(dzmine + ((size_t)g * NC + r * HS + jl) * BT + b, dz[g]);
+          dbacc[g] += dz[g];
+        }
+        __stcg(dcb + (size_t)b * H + j0 + jl, dcn);
+      }
+    }
+    // ---- publish dz_s of this CTA (per-cluster counter) ---------------------------------------------------
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) red_release_gpu_add(cnt + q, 1u);
+  }
+
+  // bias gradient: every thread's pairs share jl = tid % HS; fixed-order sum over threads
+  {
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ring[tid * 4 + g] = dbacc[g];
+    __syncthreads();
+    if (tid < 4 * HS) {
+      const int g = tid / HS, j = tid % HS;
+      float sum = 0.f;
+      for (int i = j; i < CL_THREADS; i += HS) sum += ring[i * 4 + g];
+      p.dbpart[((size_t)dir * 8) * H4 + g * H + j0 + j] = sum;
+    }
+  }
+  cluster_sync_all();                                    // nobody exits while a peer may still store into it
+}
+
+template <int TBT, int HS>
+int launch_cl(const ClParams& p, cudaStream_t stream, bool* launched) {
+  constexpr int BT = 16 * TBT, NC = CL * HS;
+  const size_t smem = ((size_t)4 * NC * NC + 2 * NC * BT + 2 * CL * BT * HS) * sizeof(float);
+  auto* fn = blstm_rec_bwd_cluster_kernel<TBT, HS>;
+  *launched = false;
+  if (smem > (size_t)max_smem_optin()) return 0;
+  NABU_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (p.H / HS));
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters * CL < (int)cfg.gridDim.x) {
+    cudaGetLastError();
+    return 0;                                            // not co-resident on this device: caller uses the flat kernel
+  }
+  KernelScope ks("blstm_rec_bwd_cluster", stream);
+  NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
+  *launched = true;
+  return 0;
+}
+
+}  // namespace
+
+bool blstm_bwd_cluster_eligible(int B, int H) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("NABU_REC_BWD");
+    enabled = (e && strcmp(e, "flat") == 0) ? 0 : 1;
+  }
+  if (!enabled) return false;
+  return B <= 128 && B > 0 && (H == 128 || H == 256 || H == 512);
+}
+
+int blstm_rec_bwd_cluster(const float* const kernel[2], float* const gates[2], const float* const cells[2],
+                          const float* dy, float* dbpart, float* xchg, float* dcbuf, unsigned* counters,
+                          const int* len, int B, int T, int yT, int D, int H, cudaStream_t stream, bool* launched) {
+  ClParams p = {};
+  p.kernel[0] = kernel[0]; p.kernel[1] = kernel[1];
+  p.gates[0] = gates[0]; p.gates[1] = gates[1];
+  p.cells[0] = cells[0]; p.cells[1] = cells[1];
+  p.dy = dy; p.dbpart = dbpart; p.xchg = xchg; p.dcbuf = dcbuf; p.counters = counters; p.len = len;
+  p.B = B; p.T = T; p.yT = yT; p.D = D; p.H = H;
+  const int hs = H / 64;
+  const bool small = B <= 64;
+  if (hs == 8) return small ? launch_cl<4, 8>(p, stream, launched) : launch_cl<8, 8>(p, stream, launched);
+  if (hs == 4) return small ? launch_cl<4, 4>(p, stream, launched) : launch_cl<8, 4>(p, stream, launched);
+  return small ? launch_cl<4, 2>(p, stream, launched) : launch_cl<8, 2>(p, stream, launched);
+}
+
+}  // namespace nabu

@@ -1,0 +1,15 @@
+// Cluster K-split backward recurrence (blstm_cl.cu), used by nabu_blstm_bwd when eligible.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace nabu {
+
+// B <= 128 and num_units in {128, 256, 512} (64 CTAs per direction = 8 clusters of 8); NABU_REC_BWD=flat disables.
+bool blstm_bwd_cluster_eligible(int B, int H);
+
+// *launched = false (and status 0) when the clusters are not co-resident on this device: use the flat kernel.
+int blstm_rec_bwd_cluster(const float* const kernel[2], float* const gates[2], const float* const cells[2],
+                          const float* dy, float* dbpart, float* xchg, float* dcbuf, unsigned* counters,
+                          const int* len, int B, int T, int yT, int D, int H, cudaStream_t stream, bool* launched);
+
+}  // namespace nabu
