@@ -12,7 +12,9 @@
 //     (st.shared::cluster, 32 KB in per CTA), one cluster barrier, then each CTA sums its 8 partials in a fixed
 //     order (bit-reproducible) and does the pointwise gate gradients for its own HS units as before;
 //   * dz_t is handed between clusters through L2 with one release/acquire counter PER CLUSTER, so a CTA only
-//     waits for the 8 producers of its own K-slice, not for the whole direction.
+//     waits for the producers of its own K-slice, not for the whole direction.
+// Only 15 clusters of 8 are co-resident on a B200 (16 needed), so the kernel is also built for clusters of 4
+// (K-slice of 512 columns = 256 KB per step, two k-split warp groups per CTA); the host picks the largest that fits.
 #include "common.cuh"
 #include "blstm_cl.h"
 #include <stdlib.h>
@@ -21,8 +23,8 @@
 namespace nabu {
 namespace {
 
-constexpr int CL = 8;                 // CTAs per cluster = K-slices = warps per CTA
 constexpr int CL_THREADS = 256;
+constexpr int CL_WARPS = 8;
 
 struct ClParams {
   const float* kernel[2];
@@ -30,9 +32,9 @@ struct ClParams {
   const float* cells[2];
   const float* dy;
   float* dbpart;            // [2 dir][8][4H] (slot 0 used)
-  float* xchg;              // [2 dir][2 parity][8 cluster][4 gate][8*HS unit][BT]
+  float* xchg;              // [2 dir][2 parity][cluster][4 gate][CLS*HS unit][BT]
   float* dcbuf;             // [2 dir][BT][H]
-  unsigned* counters;       // [2 dir][8 cluster]
+  unsigned* counters;       // [2 dir][<=16 clusters]
   const int* len;
   int B, T, yT, D, H;
 };
@@ -83,37 +85,49 @@ __device__ __forceinline__ int cl_row(int bg, int r) {     // see tile_row in bl
   return TBT == 8 ? ((r >> 2) * 64 + bg * 4 + (r & 3)) : bg * TBT + r;
 }
 
-template <int TBT, int HS>
+// CLS = cluster size (8 or 4).  Per direction there are H/HS = 64 CTAs = 64/CLS clusters.  CTA r of a cluster
+// multiplies K-slice r = the dz columns produced by clusters [r*CPS, (r+1)*CPS) of its direction (CPS = 64/CLS/CLS).
+// The 8 warps are KH = 8/CLS k-split groups x CLS destination ranks: warp w owns the HS output columns of rank
+// w % CLS and the k-range w / CLS of the slice, so its partial goes to receive slot r*KH + w/CLS of that rank.
+template <int TBT, int HS, int CLS>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 blstm_rec_bwd_cluster_kernel(const ClParams p) {
   constexpr int BT = 16 * TBT;             // batch rows (one tile)
-  constexpr int NC = CL * HS;              // hidden units (= output columns) per cluster
+  constexpr int NC = CLS * HS;             // hidden units (= output columns) per cluster
+  constexpr int KH = CL_WARPS / CLS;       // k-split groups per CTA
+  constexpr int CPS = 64 / CLS / CLS;      // producer clusters per K-slice
+  constexpr int KW = 32 * HS;              // k rows per warp group per step (= 4H / 8)
+  constexpr int RB = 64 / KH;              // rows per ring sub-block; a stage = KH sub-blocks = 64 rows = 32 KB at BT=128
+  constexpr int NBLK = KW / RB;            // stages per step
   constexpr int CW = HS >= 2 ? HS / 2 : 1; // output columns per lane
   constexpr int PAIRS = BT * HS;
   constexpr int PP = (PAIRS + CL_THREADS - 1) / CL_THREADS;
+  constexpr int SLAB = 4 * NC;             // exchange rows per producer cluster
   extern __shared__ __align__(16) float smem[];
-  float* Wl = smem;                                   // [4*NC][NC]   Wl[g*NC+u][n] = Kh[NC*q+n][g*H + NC*r + u]
-  float* ring = Wl + 4 * NC * NC;                     // [2][NC][BT]
-  float* rbuf = ring + 2 * NC * BT;                   // [2 parity][CL src][BT][HS]
+  float* Wl = smem;                                   // [CPS*SLAB][NC]
+  float* ring = Wl + CPS * SLAB * NC;                 // [2 stages][KH][RB][BT]
+  float* rbuf = ring + 2 * KH * RB * BT;              // [2 parity][8 slots][BT][HS]
   __shared__ __align__(8) uint64_t full_bar[2];
 
   const int H = p.H, H4 = 4 * p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per_dir = H / HS;                         // CTAs per direction (= 8 clusters of 8)
+  const int per_dir = H / HS;                         // 64 CTAs per direction
   const int dir = blockIdx.x / per_dir;
-  const int q = (blockIdx.x % per_dir) / CL;          // cluster within the direction
-  const int r = blockIdx.x % CL;                      // rank in the cluster == K-slice
-  const int j0 = (q * CL + r) * HS;                   // own hidden units
+  const int q = (blockIdx.x % per_dir) / CLS;         // cluster within the direction
+  const int r = blockIdx.x % CLS;                     // rank in the cluster == K-slice
+  const int j0 = (q * CLS + r) * HS;                  // own hidden units
   const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
   float* gates = p.gates[dir];
   const float* cells = p.cells[dir];
-  unsigned* cnt = p.counters + dir * 8;
-  float* dzx = p.xchg + (size_t)dir * 2 * H4 * BT;    // [2 parity][8 cluster][4][NC][BT]
+  unsigned* cnt = p.counters + dir * 16;
+  float* dzx = p.xchg + (size_t)dir * 2 * H4 * BT;    // [2 parity][cluster][4][NC][BT]
   float* dcb = p.dcbuf + (size_t)dir * BT * H;
 
-  for (int i = tid; i < 4 * NC * NC; i += CL_THREADS) {
-    const int n = i % NC, kl = i / NC, g = kl / NC, u = kl % NC;
-    Wl[i] = Kh[(size_t)(NC * q + n) * H4 + g * H + NC * r + u];
+  // Wl[kl][n] = Kh[NC*q + n][g*H + NC*(r*CPS + cl) + u]   with kl = (cl*4 + g)*NC + u
+  for (int i = tid; i < CPS * SLAB * NC; i += CL_THREADS) {
+    const int n = i % NC, kl = i / NC;
+    const int cl = kl / SLAB, g = (kl % SLAB) / NC, u = kl % NC;
+    Wl[i] = Kh[(size_t)(NC * q + n) * H4 + g * H + NC * (r * CPS + cl) + u];
   }
   if (tid == 0) {
     cb_init(&full_bar[0], 1);
@@ -124,16 +138,17 @@ blstm_rec_bwd_cluster_kernel(const ClParams p) {
   cluster_sync_all();                                  // peers' smem exists before anyone stores into it
 
   const int bg = lane & 15, jj = lane >> 4;
-  const int ncol0 = HS * warp + jj * CW;               // first of this lane's output columns (owned by CTA `warp`)
-  const uint32_t rbuf_remote = map_to_rank(s_u32(rbuf), (uint32_t)warp);
+  const int dst_rank = warp % CLS, kh = warp / CLS;
+  const int ncol0 = HS * dst_rank + jj * CW;           // first of this lane's output columns
+  const uint32_t rbuf_remote = map_to_rank(s_u32(rbuf), (uint32_t)dst_rank);
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  unsigned useq = 0;                                   // gate blocks consumed so far
+  unsigned useq = 0;                                   // ring stages consumed so far
 
   int iter = 0;
   for (int s = p.T - 1; s >= 0; --s, ++iter) {
     const float* dzprev = dzx + (size_t)((iter + 1) & 1) * H4 * BT;
     float* dznext = dzx + (size_t)(iter & 1) * H4 * BT;
-    float* rb = rbuf + (size_t)(iter & 1) * CL * BT * HS;
+    float* rb = rbuf + (size_t)(iter & 1) * 8 * BT * HS;
     // ---- prefetch pointwise operands -----------------------------------------------------------
     float gt[PP][4], ct[PP], cprev[PP], dyv[PP], dcr[PP];
     int tb[PP];
@@ -168,25 +183,32 @@ blstm_rec_bwd_cluster_kernel(const ClParams p) {
       for (int i = 0; i < TBT; ++i)
 #pragma unroll
         for (int c = 0; c < CW; ++c) acc[i][c] = 0.f;
-      const float* slab = dzprev + (size_t)r * 4 * NC * BT;          // produced by cluster r
+      const float* slab = dzprev + (size_t)r * CPS * SLAB * BT;       // rows of my K-slice, contiguous
+      // stage `blk`: for every k-split group kh2 the RB rows [kh2*KW + blk*RB, +RB) of the slice
+      auto issue = [&](int blk, unsigned seq) {
+        uint64_t* bar = &full_bar[seq & 1];
+        cb_expect_tx(bar, KH * RB * BT * 4);
+#pragma unroll
+        for (int kh2 = 0; kh2 < KH; ++kh2)
+          cb_bulk(ring + ((size_t)(seq & 1) * KH + kh2) * RB * BT, slab + ((size_t)kh2 * KW + (size_t)blk * RB) * BT,
+                  RB * BT * 4, bar);
+      };
       if (tid == 0) {
-        const unsigned target = (unsigned)CL * (unsigned)iter;
-        while (ld_acquire_gpu(cnt + r) < target) { }
+        const unsigned target = (unsigned)CLS * (unsigned)iter;
+        for (int c = 0; c < CPS; ++c)
+          while (ld_acquire_gpu(cnt + r * CPS + c) < target) { }
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
-        for (int g = 0; g < 2; ++g) {
-          uint64_t* bar = &full_bar[(useq + g) & 1];
-          cb_expect_tx(bar, NC * BT * 4);
-          cb_bulk(ring + (size_t)((useq + g) & 1) * NC * BT, slab + (size_t)g * NC * BT, NC * BT * 4, bar);
-        }
+        issue(0, useq);
+        if (NBLK > 1) issue(1, useq + 1);
       }
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g, ++useq) {
+      for (int blk = 0; blk < NBLK; ++blk, ++useq) {
         cb_wait(&full_bar[useq & 1], (useq >> 1) & 1);
-        const float* hs_ = ring + (size_t)(useq & 1) * NC * BT;
-        const float* ws_ = Wl + (size_t)g * NC * NC + ncol0;
+        const float* hs_ = ring + ((size_t)(useq & 1) * KH + kh) * RB * BT;
+        const float* ws_ = Wl + ((size_t)kh * KW + (size_t)blk * RB) * NC + ncol0;
 #pragma unroll 4
-        for (int kk = 0; kk < NC; ++kk) {
+        for (int kk = 0; kk < RB; ++kk) {
           float w[CW];
           if (CW == 4) {
             const float4 w4 = *reinterpret_cast<const float4*>(ws_ + kk * NC);
@@ -208,17 +230,13 @@ blstm_rec_bwd_cluster_kernel(const ClParams p) {
 #pragma unroll
             for (int c = 0; c < CW; ++c) acc[i][c] = fmaf(hv[i], w[c], acc[i][c]);
         }
-        if (g + 2 < 4) {
-          __syncthreads();                              // every warp is done with this ring buffer
-          if (tid == 0) {
-            uint64_t* bar = &full_bar[useq & 1];
-            cb_expect_tx(bar, NC * BT * 4);
-            cb_bulk(ring + (size_t)(useq & 1) * NC * BT, slab + (size_t)(g + 2) * NC * BT, NC * BT * 4, bar);
-          }
+        if (blk + 2 < NBLK) {
+          __syncthreads();                              // every warp is done with this ring stage
+          if (tid == 0) issue(blk + 2, useq);           // (useq + 2) & 1 == useq & 1
         }
       }
-      // ---- reduce-scatter: my columns HS*warp .. belong to CTA `warp` -----------------------------------
-      const uint32_t dst = rbuf_remote + (uint32_t)(((size_t)(iter & 1) * CL + r) * BT * HS) * 4u;
+      // ---- reduce-scatter: my columns belong to CTA dst_rank, receive slot r*KH + kh -------------------------
+      const uint32_t dst = rbuf_remote + (uint32_t)(((size_t)(iter & 1) * 8 + r * KH + kh) * BT * HS) * 4u;
 #pragma unroll
       for (int i = 0; i < TBT; ++i) {
         const uint32_t a = dst + (uint32_t)(cl_row<TBT>(bg, i) * HS + jj * CW) * 4u;
@@ -230,7 +248,7 @@ blstm_rec_bwd_cluster_kernel(const ClParams p) {
     }
 
     // ---- pointwise gate gradients for my HS units -------------------------------------------------------
-    float* dzmine = dznext + ((size_t)q * 4 * NC) * BT;                // my cluster's slab
+    float* dzmine = dznext + ((size_t)q * SLAB) * BT;                  // my cluster's slab
 #pragma unroll
     for (int k = 0; k < PP; ++k) {
       const int pr = tid + k * CL_THREADS;
@@ -239,7 +257,7 @@ blstm_rec_bwd_cluster_kernel(const ClParams p) {
         float dh = dyv[k];
         if (iter > 0) {
 #pragma unroll
-          for (int src = 0; src < CL; ++src) dh += rb[((size_t)src * BT + b) * HS + jl];
+          for (int src = 0; src < 8; ++src) dh += rb[((size_t)src * BT + b) * HS + jl];
         }
         float dz[4] = {0.f, 0.f, 0.f, 0.f};
         float dcn = 0.f;
@@ -288,11 +306,11 @@ blstm_rec_bwd_cluster_kernel(const ClParams p) {
   cluster_sync_all();                                    // nobody exits while a peer may still store into it
 }
 
-template <int TBT, int HS>
+template <int TBT, int HS, int CLS>
 int launch_cl(const ClParams& p, cudaStream_t stream, bool* launched) {
-  constexpr int BT = 16 * TBT, NC = CL * HS;
-  const size_t smem = ((size_t)4 * NC * NC + 2 * NC * BT + 2 * CL * BT * HS) * sizeof(float);
-  auto* fn = blstm_rec_bwd_cluster_kernel<TBT, HS>;
+  constexpr int BT = 16 * TBT, NC = CLS * HS, KH = CL_WARPS / CLS, CPS = 64 / CLS / CLS, RB = 64 / KH;
+  const size_t smem = ((size_t)CPS * 4 * NC * NC + 2 * KH * RB * BT + 2 * 8 * BT * HS) * sizeof(float);
+  auto* fn = blstm_rec_bwd_cluster_kernel<TBT, HS, CLS>;
   *launched = false;
   if (smem > (size_t)max_smem_optin()) return 0;
   NABU_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -303,20 +321,32 @@ int launch_cl(const ClParams& p, cudaStream_t stream, bool* launched) {
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = CLS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 2;
   int nclusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters * CL < (int)cfg.gridDim.x) {
+  const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg);
+  if (getenv("NABU_DEBUG"))
+    fprintf(stderr, "[nabu] bwd cluster kernel TBT=%d HS=%d CLS=%d: smem %zu B, max active clusters %d (%s), need %d\n", TBT,
+            HS, CLS, smem, nclusters, cudaGetErrorString(oe), (int)cfg.gridDim.x / CLS);
+  if (oe != cudaSuccess || nclusters * CLS < (int)cfg.gridDim.x) {
     cudaGetLastError();
-    return 0;                                            // not co-resident on this device: caller uses the flat kernel
+    return 0;                                            // not co-resident on this device
   }
-  KernelScope ks("blstm_rec_bwd_cluster", stream);
+  KernelScope ks(CLS == 8 ? "blstm_rec_bwd_cluster8" : "blstm_rec_bwd_cluster4", stream);
   NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
   *launched = true;
   return 0;
+}
+
+// largest co-resident cluster size first (8 clusters of 8 per direction need 16 free 8-SM groups; B200 offers 15)
+template <int TBT, int HS>
+int launch_any(const ClParams& p, cudaStream_t stream, bool* launched) {
+  if (int e = launch_cl<TBT, HS, 8>(p, stream, launched)) return e;
+  if (*launched) return 0;
+  return launch_cl<TBT, HS, 4>(p, stream, launched);
 }
 
 }  // namespace
@@ -342,9 +372,9 @@ int blstm_rec_bwd_cluster(const float* const kernel[2], float* const gates[2], c
   p.B = B; p.T = T; p.yT = yT; p.D = D; p.H = H;
   const int hs = H / 64;
   const bool small = B <= 64;
-  if (hs == 8) return small ? launch_cl<4, 8>(p, stream, launched) : launch_cl<8, 8>(p, stream, launched);
-  if (hs == 4) return small ? launch_cl<4, 4>(p, stream, launched) : launch_cl<8, 4>(p, stream, launched);
-  return small ? launch_cl<4, 2>(p, stream, launched) : launch_cl<8, 2>(p, stream, launched);
+  if (hs == 8) return small ? launch_any<4, 8>(p, stream, launched) : launch_any<8, 8>(p, stream, launched);
+  if (hs == 4) return small ? launch_any<4, 4>(p, stream, launched) : launch_any<8, 4>(p, stream, launched);
+  return small ? launch_any<4, 2>(p, stream, launched) : launch_any<8, 2>(p, stream, launched);
 }
 
 }  // namespace nabu
