@@ -684,6 +684,17 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
     return blstm_rec_fwd_tc(tpl, kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream);
   }
   NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * (ceil_div(B, 128) * 128) * sizeof(float), stream));
+  if (blstm_fwd_cluster_tc_eligible(B, H)) {
+    bool launched = false;
+    if (int e = blstm_rec_fwd_cluster_tc(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched))
+      return e;
+    if (launched) return 0;
+  }
+  if (blstm_fwd_cluster_eligible(B, H)) {
+    bool launched = false;
+    if (int e = blstm_rec_fwd_cluster(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched)) return e;
+    if (launched) return 0;
+  }
   RecParams rp = {};
   rp.kernel[0] = kern[0]; rp.kernel[1] = kern[1];
   rp.gates[0] = g[0]; rp.gates[1] = g[1];

@@ -1,4 +1,4 @@
-// Cluster K-split backward recurrence (blstm_cl.cu), used by nabu_blstm_bwd when eligible.
+// Cluster K-split recurrences (blstm_cl.cu), used by nabu_blstm_fwd / nabu_blstm_bwd when eligible.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -11,5 +11,17 @@ bool blstm_bwd_cluster_eligible(int B, int H);
 int blstm_rec_bwd_cluster(const float* const kernel[2], float* const gates[2], const float* const cells[2],
                           const float* dy, float* dbpart, float* xchg, float* dcbuf, unsigned* counters,
                           const int* len, int B, int T, int yT, int D, int H, cudaStream_t stream, bool* launched);
+
+// forward twin (clusters of 4): same eligibility; NABU_REC_FWD=flat disables.
+bool blstm_fwd_cluster_eligible(int B, int H);
+int blstm_rec_fwd_cluster(const float* const kernel[2], float* const gates[2], float* const cells[2], float* y,
+                          float* xchg, unsigned* counters, const int* len, int B, int T, int yT, int D, int H,
+                          cudaStream_t stream, bool* launched);
+
+// tcgen05 forward (blstm_cl_tc.cu): B <= 128, num_units in {256, 512}; NABU_REC_FWD=ffma|flat disables.
+bool blstm_fwd_cluster_tc_eligible(int B, int H);
+int blstm_rec_fwd_cluster_tc(const float* const kernel[2], float* const gates[2], float* const cells[2], float* y,
+                             float* xchg, unsigned* counters, const int* len, int B, int T, int yT, int D, int H,
+                             cudaStream_t stream, bool* launched);
 
 }  // namespace nabu

@@ -1,0 +1,107 @@
+// Shared by the cluster recurrences (blstm_cl.cu: FFMA, blstm_cl_tc.cu: tcgen05): parameters, DSMEM / bulk-copy /
+// cluster-barrier PTX wrappers and the NABU_REC_TRACE phase stamps.
+#pragma once
+#include "common.cuh"
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace nabu {
+namespace {
+
+constexpr int CL_THREADS = 256;
+constexpr int CL_WARPS = 8;
+
+struct ClParams {
+  const float* kernel[2];
+  float* gates[2];          // in: activated i,g,f,o ; out: dZ
+  const float* cells[2];
+  const float* dy;
+  float* y;                 // fwd: output [B, yT, 2H]
+  float* dbpart;            // [2 dir][8][4H] (slot 0 used)
+  float* xchg;              // [2 dir][2 parity][cluster][4 gate][CLS*HS unit][BT]
+  float* dcbuf;             // [2 dir][BT][H]
+  unsigned* counters;       // [2 dir][<=16 clusters]
+  const int* len;
+  long long* trace;         // NABU_REC_TRACE: per-phase clock64 stamps of CTA 0 for steps [TRACE_S0, TRACE_S0 + TRACE_N)
+  int B, T, yT, D, H;
+};
+
+constexpr int TRACE_S0 = 200, TRACE_N = 8, TRACE_PH = 10;
+#define CL_STAMP(step, i)                                                                                   \
+  do {                                                                                                      \
+    if (p.trace && blockIdx.x == 0 && tid == 0 && (step) >= TRACE_S0 && (step) < TRACE_S0 + TRACE_N)        \
+      p.trace[((step) - TRACE_S0) * TRACE_PH + (i)] = clock64();                                            \
+  } while (0)
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cb_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cb_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cb_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(s_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cb_bulk(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int TBT>
+__device__ __forceinline__ int cl_row(int bg, int r) {     // see tile_row in blstm.cu
+  return TBT == 8 ? ((r >> 2) * 64 + bg * 4 + (r & 3)) : bg * TBT + r;
+}
+
+// NABU_REC_TRACE=1 (debugging only): synchronise after the launch and print the phase stamps of CTA 0.
+long long* trace_buffer() {
+  static long long* buf = nullptr;
+  static int on = -1;
+  if (on < 0) on = getenv("NABU_REC_TRACE") ? 1 : 0;
+  if (on && !buf) {
+    if (cudaMalloc(&buf, TRACE_N * TRACE_PH * sizeof(long long)) != cudaSuccess) buf = nullptr;
+  }
+  return on ? buf : nullptr;
+}
+void trace_dump(const char* name, long long* dev, cudaStream_t stream) {
+  if (!dev) return;
+  long long h[TRACE_N * TRACE_PH];
+  cudaStreamSynchronize(stream);
+  cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < TRACE_N; ++i) {
+    fprintf(stderr, "[trace] %s step %d:", name, TRACE_S0 + i);
+    for (int j = 1; j < TRACE_PH; ++j) fprintf(stderr, " %lld", h[i * TRACE_PH + j] - h[i * TRACE_PH]);
+    if (i + 1 < TRACE_N) fprintf(stderr, " | next %lld", h[(i + 1) * TRACE_PH] - h[i * TRACE_PH]);
+    fprintf(stderr, "\n");
+  }
+}
+
+}  // namespace
+}  // namespace nabu
