@@ -616,16 +616,16 @@ int run_recurrence(bool backward, RecParams rp, int B, int H, cudaStream_t strea
   return e;
 }
 
-// workspace layout: [counters 256 B][exchange 2*2*4H*Bp floats][dcbuf 2*Bp*H floats][gemm scratch]
+// workspace layout: [counters 256 B | per-row max |dy| 512 B | pad][exchange 2*2*4H*Bp floats][dcbuf 2*Bp*H floats][gemm scratch]
 struct Ws {
-  unsigned* counters; float* xchg; float* dcbuf; float* dbpart; float* gemm; size_t gemm_bytes; size_t total;
+  unsigned* counters; unsigned* rowmax; float* xchg; float* dcbuf; float* dbpart; float* gemm; size_t gemm_bytes; size_t total;
 };
 Ws carve(void* base, int H, int B) {
   const int Bp = ceil_div(B, 128) * 128;
   Ws w;
   size_t off = 0;
   char* b = (char*)base;
-  w.counters = (unsigned*)(b + off); off += 256;
+  w.counters = (unsigned*)(b + off); w.rowmax = (unsigned*)(b + off + 256); off += 1024;
   {
     size_t xf = (size_t)2 * 2 * 4 * H * Bp;
     if (xf < (size_t)4 * 128 * H) xf = (size_t)4 * 128 * H;      // the tcgen05 path exchanges [2][2][128][H]
@@ -728,7 +728,15 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
   int ngrp = 1;
   bool launched = false;
-  if (blstm_bwd_cluster_eligible(B, H)) {
+  if (blstm_bwd_cluster_tc_eligible(B, H)) {
+    const float* cc[2] = {c[0], c[1]};
+    NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, stream));
+    NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H4 * 128 * sizeof(float), stream));
+    if (int e = blstm_rec_bwd_cluster_tc(kern, g, cc, dy, w.dbpart, w.xchg, w.dcbuf, w.counters, w.rowmax, len, B, T, yT, D,
+                                         H, stream, &launched))
+      return e;
+  }
+  if (!launched && blstm_bwd_cluster_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};
     if (int e = blstm_rec_bwd_cluster(kern, g, cc, dy, w.dbpart, w.xchg, w.dcbuf, w.counters, len, B, T, yT, D, H, stream,
                                       &launched))

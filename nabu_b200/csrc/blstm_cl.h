@@ -24,4 +24,12 @@ int blstm_rec_fwd_cluster_tc(const float* const kernel[2], float* const gates[2]
                              float* xchg, unsigned* counters, const int* len, int B, int T, int yT, int D, int H,
                              cudaStream_t stream, bool* launched);
 
+// tcgen05 backward: same eligibility; rowmax = 128 zeroed words of scratch (per-row max |dy|, filled by a pre-pass);
+// the exchange buffer must be zeroed by the caller (rows b >= B are read); NABU_REC_BWD=ffma|flat disables.
+bool blstm_bwd_cluster_tc_eligible(int B, int H);
+int blstm_rec_bwd_cluster_tc(const float* const kernel[2], float* const gates[2], const float* const cells[2],
+                             const float* dy, float* dbpart, float* xchg, float* dcbuf, unsigned* counters,
+                             unsigned* rowmax, const int* len, int B, int T, int yT, int D, int H, cudaStream_t stream,
+                             bool* launched);
+
 }  // namespace nabu

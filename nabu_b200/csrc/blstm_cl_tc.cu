@@ -324,6 +324,365 @@ int launch_fwd_tc(const ClParams& p, cudaStream_t stream, bool* launched) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// backward: dh_{t-1}[B, H] = dz_t[B, 4H] . Kh^T with the partition of blstm_rec_bwd_cluster_kernel<CLS = 4>: CTA r of
+// a cluster multiplies the 1024*HS/8... K-slice r (4H/4 dz columns, produced by 4 clusters) against its resident
+// [4H/4 x 4*HS] block of Kh^T: M = 128 batch rows, N = 4*HS, K = 64*HS, as HS K-blocks of 64 streamed through a
+// 3-stage bulk-copy ring (32 KB per stage, hi|lo), stages recycled by tcgen05.commit.
+//
+// dz is a gradient: its magnitude is arbitrary, fp16's range is not.  Every batch row b is therefore exchanged
+// multiplied by a power of two S_b chosen so that max_t,j |dy[b,t,j]| lands in [32, 64) (row_absmax_kernel runs
+// before the recurrence).  Gate derivatives are <= 1, so dz starts below that bound and would have to grow 1000x
+// through the recurrence to reach fp16's maximum (conversions saturate instead of producing inf); 20 binades below
+// the row maximum keep the full 22 bits, smaller values keep an absolute error of 2^-36 of the row maximum.  The
+// scale is exact (power of two) and is divided out in the epilogue, per row.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ __half sat_half(float x) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return __ushort_as_half(h);
+}
+__device__ __forceinline__ void split_h_sat(float x, __half* hi, __half* lo) {
+  const __half h = sat_half(x);
+  *hi = h;
+  *lo = sat_half((x - __half2float(h)) * 2048.f);
+}
+
+__global__ void row_absmax_kernel(const float* __restrict__ dy, const int* __restrict__ len, int yT, int W, unsigned* rowmax) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)len[b] * W;                 // valid frames are the first len[b] rows of [yT, W]
+  const float* src = dy + (size_t)b * yT * W;
+  float m = 0.f;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i + 3 < n; i += (size_t)gridDim.x * blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(rowmax + b, __float_as_uint(m));
+}
+
+template <int HS>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ rowmax) {
+  constexpr int CLS = TC_CLS;
+  constexpr int BT = 128;
+  constexpr int NC = CLS * HS;             // hidden units (= output columns) per cluster = MMA N
+  constexpr int CPS = 64 / CLS / CLS;      // producer clusters per K-slice
+  constexpr int SLAB = 4 * NC;             // dz columns per producer cluster
+  constexpr int KBN = CPS * SLAB / 64;     // K blocks per slice (= HS)
+  constexpr int KBC = KBN / CPS;           // K blocks per producer cluster
+  constexpr int NST = 3;                   // ring stages
+  constexpr int B_TILE = NC * 128;         // bytes of one [NC rows x 64 fp16] tile
+  constexpr int TCOLS = 2 * NC < 32 ? 32 : 2 * NC;
+  constexpr int PAIRS = BT * HS;
+  constexpr int PP = PAIRS / CL_THREADS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Bs = sm;                                    // [KBN][hi|lo][B_TILE]
+  uint8_t* ring = Bs + KBN * 2 * B_TILE;               // [NST][hi|lo][A_TILE]
+  float* rbuf = reinterpret_cast<float*>(ring + NST * 2 * A_TILE);   // [2 parity][CLS src][BT][HS]
+  float* red = rbuf + 2 * CLS * BT * HS;               // [CL_THREADS][4] bias-gradient scratch
+  __shared__ __align__(8) uint64_t full_bar[NST];
+  __shared__ __align__(8) uint64_t empty_bar[NST];
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float scale[BT], inv_scale[BT];
+
+  const int H = p.H, H4 = 4 * p.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per_dir = H / HS;
+  const int dir = blockIdx.x / per_dir;
+  const int q = (blockIdx.x % per_dir) / CLS;
+  const int r = blockIdx.x % CLS;
+  const int j0 = (q * CLS + r) * HS;
+  const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
+  float* gates = p.gates[dir];
+  const float* cells = p.cells[dir];
+  unsigned* cnt = p.counters + dir * 16;
+  uint8_t* dzx = reinterpret_cast<uint8_t*>(p.xchg) + (size_t)dir * 2 * H4 * BT * 4;   // [2 parity][slice][KBN][hi|lo][A_TILE]
+  float* dcb = p.dcbuf + (size_t)dir * BT * H;
+
+  // resident weights, split: B[n][kl] = Kh[NC*q + n][g*H + NC*(r*CPS + cl) + u],  kl = (cl*4 + g)*NC + u
+  for (int i = tid; i < CPS * SLAB * NC; i += CL_THREADS) {
+    const int kl = i % (CPS * SLAB), n = i / (CPS * SLAB);
+    const int cl = kl / SLAB, g = (kl % SLAB) / NC, u = kl % NC;
+    const float w = Kh[(size_t)(NC * q + n) * H4 + g * H + NC * (r * CPS + cl) + u];
+    __half hi, lo;
+    split_h(w, &hi, &lo);
+    uint8_t* t = Bs + (size_t)(kl / 64) * 2 * B_TILE + sw128_h(n, kl % 64);
+    *reinterpret_cast<__half*>(t) = hi;
+    *reinterpret_cast<__half*>(t + B_TILE) = lo;
+  }
+  if (tid < BT) {
+    const float G = tid < p.B ? __uint_as_float(rowmax[tid]) : 0.f;
+    float S = 1.f;
+    if (G > 0.f && G < 3.0e38f) {
+      int e;
+      frexpf(G, &e);                                   // G in [2^(e-1), 2^e)
+      e = e < -100 ? -100 : (e > 100 ? 100 : e);
+      S = ldexpf(1.f, 6 - e);                          // G * S in [32, 64)
+    }
+    scale[tid] = S;
+    inv_scale[tid] = 1.f / S;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(&mma_bar), 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_slot;
+  cluster_arrive();
+  cluster_wait();
+
+  const uint32_t idesc = make_idesc_f16(128, NC);
+  const uint32_t ring_u = smem_u32(ring), Bs_u = smem_u32(Bs);
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned gq = 0;                                     // K blocks consumed so far (ring position), used by tid 0
+
+  int iter = 0;
+  for (int s = p.T - 1; s >= 0; --s, ++iter) {
+    const uint8_t* dzprev = dzx + (size_t)((iter + 1) & 1) * H4 * BT * 4;
+    uint8_t* dznext = dzx + (size_t)(iter & 1) * H4 * BT * 4;
+    float* rb = rbuf + (size_t)(iter & 1) * CLS * BT * HS;
+    CL_STAMP(iter, 0);
+    // ---- prefetch pointwise operands -----------------------------------------------------------
+    float gt[PP][4], ct[PP], cprev[PP], dyv[PP], dcr[PP];
+    int tb[PP];
+    bool valid[PP];
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      const int pr = tid + k * CL_THREADS;
+      const int jl = pr % HS, b = pr / HS;
+      valid[k] = false; tb[k] = 0; ct[k] = cprev[k] = dyv[k] = dcr[k] = 0.f;
+      gt[k][0] = gt[k][1] = gt[k][2] = gt[k][3] = 0.f;
+      if (b < p.B) {
+        const int L = p.len[b];
+        valid[k] = s < L;
+        const int t = valid[k] ? (dir ? L - 1 - s : s) : s;
+        tb[k] = t;
+        if (valid[k]) {
+          const float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) gt[k][g] = __ldcg(gp + g * H);
+          ct[k] = __ldcg(cells + ((size_t)b * p.T + t) * H + j0 + jl);
+          if (s > 0) cprev[k] = __ldcg(cells + ((size_t)b * p.T + (dir ? t + 1 : t - 1)) * H + j0 + jl);
+          dyv[k] = __ldcg(p.dy + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl);
+          if (iter > 0) dcr[k] = __ldcg(dcb + (size_t)b * H + j0 + jl);
+        }
+      }
+    }
+
+    if (iter > 0) {
+      if (tid == 0) {
+        const unsigned target = (unsigned)CLS * (unsigned)iter;
+        const uint8_t* slab = dzprev + (size_t)r * KBN * 2 * A_TILE;
+        const unsigned g0 = gq;
+        auto issue = [&](int kb) {                     // K block kb of this step -> ring position g0 + kb
+          if (kb % KBC == 0) {                         // first block of a producer cluster: wait for its dz
+            while (ld_acquire_gpu(cnt + r * CPS + kb / KBC) < target) { }
+            __threadfence();
+            fence_proxy_async_all();
+          }
+          const unsigned pos = g0 + kb, st = pos % NST;
+          if (pos >= NST) mbar_wait(smem_u32(&empty_bar[st]), (pos / NST - 1) & 1);   // MMAs of the previous tenant done
+          mbar_expect_tx(smem_u32(&full_bar[st]), 2 * A_TILE);
+          cb_bulk(ring + (size_t)st * 2 * A_TILE, slab + (size_t)kb * 2 * A_TILE, 2 * A_TILE, &full_bar[st]);
+        };
+        for (int kb = 0; kb < NST && kb < KBN; ++kb) issue(kb);
+        CL_STAMP(iter, 1);
+#pragma unroll 1
+        for (int kb = 0; kb < KBN; ++kb) {
+          const unsigned pos = g0 + kb, st = pos % NST;
+          mbar_wait(smem_u32(&full_bar[st]), (pos / NST) & 1);
+          if (kb == 0) CL_STAMP(iter, 2);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ah = make_desc(ring_u + (st * 2 + 0) * A_TILE + ks * 32, 16, 1024, 2);
+            const uint64_t al = make_desc(ring_u + (st * 2 + 1) * A_TILE + ks * 32, 16, 1024, 2);
+            const uint64_t bh = make_desc(Bs_u + (kb * 2 + 0) * B_TILE + ks * 32, 16, 1024, 2);
+            const uint64_t bl = make_desc(Bs_u + (kb * 2 + 1) * B_TILE + ks * 32, 16, 1024, 2);
+            const uint32_t acc = (kb | ks) != 0;
+            umma_f16(tm, ah, bh, idesc, acc);
+            umma_f16(tm + NC, ah, bl, idesc, acc);
+            umma_f16(tm + NC, al, bh, idesc, 1u);
+          }
+          umma_commit(smem_u32(&empty_bar[st]));
+          if (kb >= 1 && kb - 1 + NST < KBN) issue(kb - 1 + NST);
+        }
+        umma_commit(smem_u32(&mma_bar));
+        gq = g0 + KBN;
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&mma_bar), (unsigned)(iter - 1) & 1u);
+      tc_fence_after();
+      CL_STAMP(iter, 3);
+      // ---- TMEM -> receive buffers: thread = one batch row, columns [d*HS, (d+1)*HS) go to CTA d, slot r --------
+      if (warp < 4) {
+        const int row = warp * 32 + lane;
+        const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
+        uint32_t v1[NC], v2[NC];
+        if constexpr (NC == 32) {
+          tmem_ld32(taddr, reinterpret_cast<uint32_t(&)[32]>(v1));
+          tmem_ld32(taddr + NC, reinterpret_cast<uint32_t(&)[32]>(v2));
+        } else {
+          tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(v1));
+          tmem_ld16(taddr + NC, reinterpret_cast<uint32_t(&)[16]>(v2));
+        }
+        tmem_ld_wait();
+        const float is = inv_scale[row];
+#pragma unroll
+        for (int d = 0; d < CLS; ++d) {
+          const uint32_t dst = map_to_rank(smem_u32(rbuf), (uint32_t)d) +
+                               (uint32_t)((((iter & 1) * CLS + r) * BT + row) * HS) * 4u;
+#pragma unroll
+          for (int c4 = 0; c4 < HS / 4; ++c4) {
+            float z[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = d * HS + c4 * 4 + e;
+              z[e] = fmaf(__uint_as_float(v2[c]), 1.f / 2048.f, __uint_as_float(v1[c])) * is;
+            }
+            const int pos = HS == 8 ? (c4 ^ ((row >> 2) & 1)) : c4;
+            st_cluster_v4(dst + (uint32_t)pos * 16u, z[0], z[1], z[2], z[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      CL_STAMP(iter, 4);
+      cluster_arrive();
+      cluster_wait();
+      CL_STAMP(iter, 5);
+    }
+
+    // ---- pointwise gate gradients for my HS units -------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      const int pr = tid + k * CL_THREADS;
+      const int jl = pr % HS, b = pr / HS;
+      if (b < p.B) {
+        float dh = dyv[k];
+        if (iter > 0) {
+          const int pos = HS == 8 ? ((jl >> 2) ^ ((b >> 2) & 1)) : 0;
+#pragma unroll
+          for (int src = 0; src < CLS; ++src) dh += rb[((size_t)src * BT + b) * HS + pos * 4 + (jl & 3)];
+        }
+        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+        float dcn = 0.f;
+        if (valid[k]) {
+          const float ig = gt[k][0], gg = gt[k][1], fg = gt[k][2], og = gt[k][3];
+          const float tc_ = tanhf(ct[k]);
+          const float d_o = dh * tc_;
+          const float dc = dcr[k] + dh * og * (1.f - tc_ * tc_);
+          dz[0] = dc * gg * ig * (1.f - ig);
+          dz[1] = dc * ig * (1.f - gg * gg);
+          dz[2] = dc * cprev[k] * fg * (1.f - fg);
+          dz[3] = d_o * og * (1.f - og);
+          dcn = dc * fg;
+        }
+        const int t = tb[k];
+        float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+        const float S = scale[b];
+        // my cluster is producer (q % CPS) of K-slice q / CPS; column kl = ((q % CPS)*4 + g)*NC + r*HS + jl
+        uint8_t* xs = dznext + (size_t)(q / CPS) * KBN * 2 * A_TILE;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __stcg(gp + g * H, dz[g]);
+          const int kl = ((q % CPS) * 4 + g) * NC + r * HS + jl;
+          __half hi, lo;
+          split_h_sat(dz[g] * S, &hi, &lo);
+          uint8_t* tptr = xs + (size_t)(kl / 64) * 2 * A_TILE + sw128_h(b, kl % 64);
+          __stcg(reinterpret_cast<unsigned short*>(tptr), __half_as_ushort(hi));
+          __stcg(reinterpret_cast<unsigned short*>(tptr + A_TILE), __half_as_ushort(lo));
+          dbacc[g] += dz[g];
+        }
+        __stcg(dcb + (size_t)b * H + j0 + jl, dcn);
+      }
+    }
+    CL_STAMP(iter, 6);
+    fence_proxy_async_all();
+    __threadfence();
+    CL_STAMP(iter, 7);
+    __syncthreads();
+    CL_STAMP(iter, 8);
+    if (tid == 0) red_release_gpu_add(cnt + q, 1u);
+    CL_STAMP(iter, 9);
+  }
+
+  // bias gradient: every thread's pairs share jl = tid % HS; fixed-order sum over threads
+  {
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) red[tid * 4 + g] = dbacc[g];
+    __syncthreads();
+    if (tid < 4 * HS) {
+      const int g = tid / HS, j = tid % HS;
+      float sum = 0.f;
+      for (int i = j; i < CL_THREADS; i += HS) sum += red[i * 4 + g];
+      p.dbpart[((size_t)dir * 8) * H4 + g * H + j0 + j] = sum;
+    }
+  }
+  tc_fence_before();
+  cluster_arrive();
+  cluster_wait();
+  if (warp == 0) tmem_dealloc(tm, TCOLS);
+}
+
+template <int HS>
+int launch_bwd_tc(const ClParams& p, unsigned* rowmax, cudaStream_t stream, bool* launched) {
+  constexpr int CLS = TC_CLS, NC = CLS * HS, KBN = HS, NST = 3;
+  const size_t smem = 1024 + (size_t)KBN * 2 * NC * 128 + (size_t)NST * 2 * A_TILE +
+                      (size_t)2 * CLS * 128 * HS * sizeof(float) + (size_t)CL_THREADS * 4 * sizeof(float);
+  auto* fn = blstm_rec_bwd_cluster_tc_kernel<HS>;
+  *launched = false;
+  if (smem > (size_t)max_smem_optin()) return 0;
+  NABU_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (p.H / HS));
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CLS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  int nclusters = 0;
+  const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg);
+  if (getenv("NABU_DEBUG"))
+    fprintf(stderr, "[nabu] bwd tcgen05 cluster kernel HS=%d: smem %zu B, max active clusters %d (%s), need %d\n", HS, smem,
+            nclusters, cudaGetErrorString(oe), (int)cfg.gridDim.x / CLS);
+  if (oe != cudaSuccess || nclusters * CLS < (int)cfg.gridDim.x) {
+    cudaGetLastError();
+    return 0;
+  }
+  {
+    KernelScope ks("row_absmax", stream);
+    row_absmax_kernel<<<dim3(32, p.B), 256, 0, stream>>>(p.dy, p.len, p.yT, 2 * p.H, rowmax);
+    NABU_CHECK_LAUNCH();
+  }
+  KernelScope ks("blstm_rec_bwd_cluster_tc", stream);
+  ClParams pt = p;
+  pt.trace = trace_buffer();
+  const unsigned* rm = rowmax;
+  NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, pt, rm));
+  trace_dump("bwd_tc", pt.trace, stream);
+  *launched = true;
+  return 0;
+}
+
 }  // namespace
 
 bool blstm_fwd_cluster_tc_eligible(int B, int H) {
@@ -346,6 +705,29 @@ int blstm_rec_fwd_cluster_tc(const float* const kernel[2], float* const gates[2]
   p.y = y; p.xchg = xchg; p.counters = counters; p.len = len;
   p.B = B; p.T = T; p.yT = yT; p.D = D; p.H = H;
   return H == 512 ? launch_fwd_tc<8>(p, stream, launched) : launch_fwd_tc<4>(p, stream, launched);
+}
+
+bool blstm_bwd_cluster_tc_eligible(int B, int H) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("NABU_REC_BWD");
+    enabled = (e && (strcmp(e, "flat") == 0 || strcmp(e, "ffma") == 0)) ? 0 : 1;
+  }
+  if (!enabled) return false;
+  return B <= 128 && B > 0 && (H == 256 || H == 512);
+}
+
+int blstm_rec_bwd_cluster_tc(const float* const kernel[2], float* const gates[2], const float* const cells[2],
+                             const float* dy, float* dbpart, float* xchg, float* dcbuf, unsigned* counters,
+                             unsigned* rowmax, const int* len, int B, int T, int yT, int D, int H, cudaStream_t stream,
+                             bool* launched) {
+  ClParams p = {};
+  p.kernel[0] = kernel[0]; p.kernel[1] = kernel[1];
+  p.gates[0] = gates[0]; p.gates[1] = gates[1];
+  p.cells[0] = cells[0]; p.cells[1] = cells[1];
+  p.dy = dy; p.dbpart = dbpart; p.xchg = xchg; p.dcbuf = dcbuf; p.counters = counters; p.len = len;
+  p.B = B; p.T = T; p.yT = yT; p.D = D; p.H = H;
+  return H == 512 ? launch_bwd_tc<8>(p, rowmax, stream, launched) : launch_bwd_tc<4>(p, rowmax, stream, launched);
 }
 
 }  // namespace nabu
