@@ -23,15 +23,22 @@ struct ClParams {
   float* dcbuf;             // [2 dir][BT][H]
   unsigned* counters;       // [2 dir][<=16 clusters]
   const int* len;
-  long long* trace;         // NABU_REC_TRACE: per-phase clock64 stamps of CTA 0 for steps [TRACE_S0, TRACE_S0 + TRACE_N)
+  long long* trace;         // NABU_REC_TRACE: per-phase globaltimer stamps of every CTA for steps [TRACE_S0, TRACE_S0 + TRACE_N)
   int B, T, yT, D, H;
+  int fences;               // NABU_REC_FENCES: per-thread __threadfence + proxy fence before publishing (debug)
 };
 
-constexpr int TRACE_S0 = 200, TRACE_N = 8, TRACE_PH = 10;
+constexpr int TRACE_S0 = 200, TRACE_N = 8, TRACE_PH = 10, TRACE_CTAS = 256;
+__device__ __forceinline__ long long trace_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// thread 0 of every CTA stamps the GPU-wide nanosecond timer: [cta][step][phase]
 #define CL_STAMP(step, i)                                                                                   \
   do {                                                                                                      \
-    if (p.trace && blockIdx.x == 0 && tid == 0 && (step) >= TRACE_S0 && (step) < TRACE_S0 + TRACE_N)        \
-      p.trace[((step) - TRACE_S0) * TRACE_PH + (i)] = clock64();                                            \
+    if (p.trace && tid == 0 && (step) >= TRACE_S0 && (step) < TRACE_S0 + TRACE_N)                           \
+      p.trace[((size_t)blockIdx.x * TRACE_N + ((step) - TRACE_S0)) * TRACE_PH + (i)] = trace_now();         \
   } while (0)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,28 +87,31 @@ __device__ __forceinline__ int cl_row(int bg, int r) {     // see tile_row in bl
   return TBT == 8 ? ((r >> 2) * 64 + bg * 4 + (r & 3)) : bg * TBT + r;
 }
 
-// NABU_REC_TRACE=1 (debugging only): synchronise after the launch and print the phase stamps of CTA 0.
+// NABU_REC_TRACE=<prefix> (debugging only): synchronise after the launch and write the stamps of every CTA to
+// <prefix>.<kernel>.bin (int64 [TRACE_CTAS][TRACE_N][TRACE_PH], nanoseconds; the last call wins).
 long long* trace_buffer() {
   static long long* buf = nullptr;
   static int on = -1;
   if (on < 0) on = getenv("NABU_REC_TRACE") ? 1 : 0;
   if (on && !buf) {
-    if (cudaMalloc(&buf, TRACE_N * TRACE_PH * sizeof(long long)) != cudaSuccess) buf = nullptr;
+    if (cudaMalloc(&buf, (size_t)TRACE_CTAS * TRACE_N * TRACE_PH * sizeof(long long)) != cudaSuccess) buf = nullptr;
   }
+  if (buf) cudaMemset(buf, 0, (size_t)TRACE_CTAS * TRACE_N * TRACE_PH * sizeof(long long));
   return on ? buf : nullptr;
 }
 void trace_dump(const char* name, long long* dev, cudaStream_t stream) {
   if (!dev) return;
-  long long h[TRACE_N * TRACE_PH];
+  const size_t n = (size_t)TRACE_CTAS * TRACE_N * TRACE_PH;
+  long long* h = (long long*)malloc(n * sizeof(long long));
   cudaStreamSynchronize(stream);
-  cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
-  for (int i = 0; i < TRACE_N; ++i) {
-    fprintf(stderr, "[trace] %s step %d:", name, TRACE_S0 + i);
-    for (int j = 1; j < TRACE_PH; ++j) fprintf(stderr, " %lld", h[i * TRACE_PH + j] - h[i * TRACE_PH]);
-    if (i + 1 < TRACE_N) fprintf(stderr, " | next %lld", h[(i + 1) * TRACE_PH] - h[i * TRACE_PH]);
-    fprintf(stderr, "\n");
+  cudaMemcpy(h, dev, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  char path[512];
+  snprintf(path, sizeof(path), "%s.%s.bin", getenv("NABU_REC_TRACE"), name);
+  if (FILE* f = fopen(path, "wb")) {
+    fwrite(h, sizeof(long long), n, f);
+    fclose(f);
   }
+  free(h);
 }
-
 }  // namespace
 }  // namespace nabu
