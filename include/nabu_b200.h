@@ -36,9 +36,12 @@ int nabu_profile_collect(char* json_out, size_t cap);
  * mode 0: C[M,N] = alpha*A[M,K].B[K,N]   + beta*C + bias[N]
  * mode 1: C[M,N] = alpha*A[M,K].B[N,K]^T + beta*C + bias[N]
  * mode 2: C[M,N] = alpha*A[K,M]^T.B[K,N] + beta*C + bias[N]
- * precision 0: fp32 FFMA (bit-reproducible); 1: tcgen05 3xTF32 split (fp32-grade, tensor cores).
+ * precision 0: fp32 FFMA (bit-reproducible); 1: tcgen05 3xTF32 split (fp32-grade, tensor cores);
+ * 2: tcgen05 on operands pre-split into two scaled fp16 terms (fp32-grade, twice the TF32 rate; workspace from
+ * nabu_gemm_h2_workspace_bytes).
  * Replaces: the tf.matmul inside every TF cell / layer the hot path touches. */
 size_t nabu_gemm_workspace_bytes(void);
+size_t nabu_gemm_h2_workspace_bytes(int mode, int M, int N, int K);
 int nabu_gemm(int mode, int precision, int M, int N, int K, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
               void* workspace, size_t ws_bytes, void* stream);

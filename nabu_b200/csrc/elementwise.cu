@@ -108,11 +108,21 @@ extern "C" int nabu_profile_collect(char* json_out, size_t cap) { return nabu::p
 
 extern "C" size_t nabu_gemm_workspace_bytes(void) { return sgemm_workspace_bytes(); }
 
+extern "C" size_t nabu_gemm_h2_workspace_bytes(int mode, int M, int N, int K) {
+  if (mode < 0 || mode > 2 || M < 1 || N < 1 || K < 1) return 0;
+  return gemm_h2_auto_workspace_bytes((GemmMode)mode, M, N, K);
+}
+
 extern "C" int nabu_gemm(int mode, int precision, int M, int N, int K, float alpha, const float* A, int lda,
                          const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
                          void* workspace, size_t ws_bytes, void* stream) {
   NABU_REQUIRE(mode >= 0 && mode <= 2, "gemm: bad mode %d", mode);
-  NABU_REQUIRE(precision == 0 || precision == 1, "gemm: precision %d unknown", precision);
+  NABU_REQUIRE(precision >= 0 && precision <= 2, "gemm: precision %d unknown", precision);
+  if (precision == 2) {
+    NABU_REQUIRE(gemm_h2_eligible((GemmMode)mode, M, N, K), "gemm: problem too small for the tensor-core path (M*N >= 128*128)");
+    return gemm_h2_auto((GemmMode)mode, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, workspace, ws_bytes,
+                        (cudaStream_t)stream);
+  }
   if (precision == 1) {
     NABU_REQUIRE(gemm_tc_eligible((GemmMode)mode, M, N, K, A, lda, B, ldb),
                  "gemm: operands not eligible for the tensor-core path (16-byte aligned pointers, ld %% 4 == 0, M*N >= 128*128)");

@@ -33,6 +33,27 @@ int gemm(GemmMode mode, int M, int N, int K, float alpha, const float* A, int ld
          float beta, float* C, int ldc, const float* bias, const GemmSeg* seg, float* workspace,
          size_t ws_bytes, cudaStream_t stream);
 
+// Pre-split fp16 path (gemm_h2.cu): x * S stored as hi = fp16(x S), lo = fp16((x S - hi) * 2^11), S a power of two
+// per row (split_rows: operands whose rows run along K) or per matrix (split_global: operands whose rows run along
+// M/N, i.e. both TN operands and the NN weight).  hi/lo are [R][ldo] fp16 planes, ldo % 8 == 0, columns >= C zero.
+struct H2Operand {
+  const void* hi; const void* lo; int ld;
+  const float* row_inv;    // 1/S per row (device) or nullptr
+  const float* glob_inv;   // 1/S of the matrix (device scalar) or nullptr
+};
+int split_rows(const float* src, int ld, int R, int C, void* hi, void* lo, int ldo, float* row_inv, cudaStream_t stream);
+int split_global(const float* src, int ld, int R, int C, void* hi, void* lo, int ldo, unsigned* maxbits /*device scratch*/,
+                 float* glob_inv, cudaStream_t stream);
+// Same contract as gemm_tc() on pre-split operands.  NN: A rows / B global; NT: A rows, B rows or global; TN: global.
+int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A, const H2Operand& B, float beta, float* C,
+            int ldc, const float* bias, const GemmSeg* seg, float* workspace, size_t ws_bytes, cudaStream_t stream);
+
+// fp32 operands: split both into `workspace` (gemm_h2_auto_workspace_bytes), then gemm_h2.
+size_t gemm_h2_auto_workspace_bytes(GemmMode mode, int M, int N, int K);
+bool gemm_h2_eligible(GemmMode mode, int M, int N, int K);
+int gemm_h2_auto(GemmMode mode, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+                 float beta, float* C, int ldc, const float* bias, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 // out[n] = sum_m X[m,n]
 int colsum(const float* X, int M, int N, int ldx, float* out, cudaStream_t stream);
 

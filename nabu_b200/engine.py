@@ -312,7 +312,8 @@ def gemm(mode, A, B, M, N, K, lda, ldb, ldc, C=None, alpha=1.0, beta=0.0, bias=N
     lib = L.load()
     if C is None:
         C = torch.zeros((M, ldc), device=A.device, dtype=torch.float32)
-    ws = L.WORKSPACE.get(lib.nabu_gemm_workspace_bytes(), A.device)
+    nbytes = lib.nabu_gemm_h2_workspace_bytes(mode, M, N, K) if precision == 2 else lib.nabu_gemm_workspace_bytes()
+    ws = L.WORKSPACE.get(nbytes, A.device)
     L.check(lib.nabu_gemm(mode, precision, M, N, K, alpha, L.ptr(A), lda, L.ptr(B), ldb, beta, L.ptr(C), ldc,
                           L.ptr(bias), L.ptr(ws), ws.numel(), L.stream()), 'nabu_gemm')
     return C

@@ -38,6 +38,7 @@ SIGNATURES = {
     'nabu_profile_enable': (c_int, [c_int]),
     'nabu_profile_collect': (c_int, [ctypes.c_char_p, c_size_t]),
     'nabu_gemm_workspace_bytes': (c_size_t, []),
+    'nabu_gemm_h2_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'nabu_gemm': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P, P,
                           c_size_t, P]),
     'nabu_blstm_workspace_bytes': (c_size_t, [c_int] * 4),

@@ -221,3 +221,52 @@ def test_gemm_tensor_core_splitk_tn():
     A = rng.standard_normal((R, M)).astype(np.float32); B = rng.standard_normal((R, N)).astype(np.float32)
     c = engine.gemm(2, dev(A), dev(B), M, N, R, M, N, N, precision=1)
     assert rel_err(c.cpu().numpy(), A.astype(np.float64).T @ B.astype(np.float64)) < 2e-5
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('shape', [(128, 256, 64), (256, 512, 128), (1000, 260, 132), (300, 520, 40), (132, 257 * 4, 1028),
+                                   (4096, 2048, 1024)])
+def test_gemm_tensor_core_split_fp16(mode, shape):
+    """tcgen05 kind::f16 on pre-split, power-of-two scaled operands: fp32-grade accuracy, every layout, ragged tiles."""
+    from nabu_b200 import engine
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32); B = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32); C0 = rng.standard_normal((M, N)).astype(np.float32)
+    ref = 0.5 * A.astype(np.float64) @ B.astype(np.float64) + 2.0 * C0 + bias
+    a = dev(A if mode != 2 else np.ascontiguousarray(A.T))
+    b = dev(B if mode != 1 else np.ascontiguousarray(B.T))
+    c = dev(C0)
+    engine.gemm(mode, a, b, M, N, K, a.shape[1], b.shape[1], N, C=c, alpha=0.5, beta=2.0, bias=dev(bias), precision=2)
+    err = rel_err(c.cpu().numpy(), ref)
+    print('gemm_h2 mode %d %s rel err %.3g' % (mode, shape, err))
+    assert err < 2e-5
+
+
+def test_gemm_split_fp16_dynamic_range():
+    """Rows 1e-30 .. 1e+30 apart (gradients next to activations): the per-row power-of-two scales keep every output
+    row at fp32-grade RELATIVE accuracy, which a plain fp16 cast or a global scale cannot."""
+    from nabu_b200 import engine
+    rng = np.random.default_rng(77)
+    M, N, K = 512, 256, 320
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    A *= (10.0 ** rng.uniform(-30, 30, size=(M, 1))).astype(np.float32)
+    Bt = rng.standard_normal((N, K)).astype(np.float32)
+    Bt *= (10.0 ** rng.uniform(-6, 6, size=(N, 1))).astype(np.float32)
+    ref = A.astype(np.float64) @ Bt.astype(np.float64).T
+    c = engine.gemm(1, dev(A), dev(Bt), M, N, K, K, K, N, precision=2).cpu().numpy().astype(np.float64)
+    row_scale = np.abs(ref).max(axis=1, keepdims=True)
+    col_scale = np.abs(ref / row_scale).max(axis=0, keepdims=True)
+    err = np.abs((c - ref) / row_scale / col_scale).max()
+    print('gemm_h2 dynamic range err', err)
+    assert np.isfinite(c).all() and err < 2e-5
+
+
+def test_gemm_split_fp16_splitk_tn():
+    from nabu_b200 import engine
+    rng = np.random.default_rng(12)
+    R, M, N = 40000, 256, 512
+    A = rng.standard_normal((R, M)).astype(np.float32) * 1e-4
+    B = rng.standard_normal((R, N)).astype(np.float32) * 1e3
+    c = engine.gemm(2, dev(A), dev(B), M, N, R, M, N, N, precision=2)
+    assert rel_err(c.cpu().numpy(), A.astype(np.float64).T @ B.astype(np.float64)) < 2e-5
