@@ -23,6 +23,8 @@
 #include "gemm.h"
 #include "blstm_tc.h"
 #include "blstm_cl.h"
+#include <cuda_fp16.h>
+#include <algorithm>
 #include "nabu_b200.h"
 #include <stdlib.h>
 #include <string.h>
@@ -616,26 +618,53 @@ int run_recurrence(bool backward, RecParams rp, int B, int H, cudaStream_t strea
   return e;
 }
 
-// workspace layout: [counters 256 B | per-row max |dy| 512 B | pad][exchange 2*2*4H*Bp floats][dcbuf 2*Bp*H floats][gemm scratch]
+// workspace layout: [counters 256 B | per-row max |dy| 512 B | pad][exchange 2*2*4H*Bp floats][dcbuf 2*Bp*H floats]
+// [gemm scratch][fp16 split planes P1 (layer input / output side), P2, P3 (gate side), weights, scales]
+constexpr int YT_SLACK = 16;    // yT - T the split planes are sized for (pyramid padding)
 struct Ws {
-  unsigned* counters; unsigned* rowmax; float* xchg; float* dcbuf; float* dbpart; float* gemm; size_t gemm_bytes; size_t total;
+  unsigned* counters; unsigned* rowmax; float* xchg; float* dcbuf; float* dbpart; float* gemm; size_t gemm_bytes;
+  void *p1h, *p1l, *p2h, *p2l, *p3h, *p3l, *wh[2], *wl[2];
+  float *row1, *row2, *glob;      // row scales of P1 / P2|P3 rows; 16 global scalars (inverse scales + max bits)
+  size_t total;
 };
-Ws carve(void* base, int H, int B) {
+Ws carve(void* base, int H, int B, int T, int D) {
   const int Bp = ceil_div(B, 128) * 128;
   Ws w;
   size_t off = 0;
   char* b = (char*)base;
-  w.counters = (unsigned*)(b + off); w.rowmax = (unsigned*)(b + off + 256); off += 1024;
+  auto take = [&](size_t bytes) { void* p = b + off; off += align_up(bytes, 256); return p; };
+  w.counters = (unsigned*)take(1024); w.rowmax = w.counters + 64;
   {
     size_t xf = (size_t)2 * 2 * 4 * H * Bp;
     if (xf < (size_t)4 * 128 * H) xf = (size_t)4 * 128 * H;      // the tcgen05 path exchanges [2][2][128][H]
-    w.xchg = (float*)(b + off); off += align_up(xf * sizeof(float), 256);
+    w.xchg = (float*)take(xf * sizeof(float));
   }
-  w.dcbuf = (float*)(b + off); off += align_up((size_t)2 * Bp * H * sizeof(float), 256);
-  w.dbpart = (float*)(b + off); off += align_up((size_t)2 * 8 * 4 * H * sizeof(float), 256);
-  w.gemm = (float*)(b + off); w.gemm_bytes = sgemm_workspace_bytes(); off += w.gemm_bytes;
+  w.dcbuf = (float*)take((size_t)2 * Bp * H * sizeof(float));
+  w.dbpart = (float*)take((size_t)2 * 8 * 4 * H * sizeof(float));
+  w.gemm_bytes = sgemm_workspace_bytes();
+  w.gemm = (float*)take(w.gemm_bytes);
+  const size_t D8 = align_up(D, 8), H4 = (size_t)4 * H;
+  const size_t e1 = std::max((size_t)B * T * D8, (size_t)B * (T + YT_SLACK) * 2 * H);
+  const size_t e2 = (size_t)B * T * H4;
+  w.p1h = take(e1 * 2); w.p1l = take(e1 * 2);
+  w.p2h = take(e2 * 2); w.p2l = take(e2 * 2);
+  w.p3h = take(e2 * 2); w.p3l = take(e2 * 2);
+  for (int d = 0; d < 2; ++d) { w.wh[d] = take((size_t)(D + H) * H4 * 2); w.wl[d] = take((size_t)(D + H) * H4 * 2); }
+  w.row1 = (float*)take((size_t)B * T * 4); w.row2 = (float*)take((size_t)B * T * 4);
+  w.glob = (float*)take(256);
   w.total = off;
   return w;
+}
+
+// fp16-split tensor-core GEMMs (gemm_h2.cu) for the layer-sized contractions; NABU_GEMM=tf32|simt keeps gemm().
+bool use_h2(int B, int T, int D, int H, int yT) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("NABU_GEMM");
+    enabled = (e && (strcmp(e, "tf32") == 0 || strcmp(e, "simt") == 0)) ? 0 : 1;
+  }
+  return enabled && yT - T <= YT_SLACK && D % 4 == 0 && H % 8 == 0 && gemm_h2_eligible(GEMM_NN, B * T, 4 * H, D) &&
+         gemm_h2_eligible(GEMM_TN, D, 4 * H, B * T);
 }
 
 }  // namespace
@@ -644,10 +673,9 @@ Ws carve(void* base, int H, int B) {
 using namespace nabu;
 
 extern "C" size_t nabu_blstm_workspace_bytes(int B, int T, int D, int H) {
-  (void)T; (void)D;
   Plan pl;
   if (make_plan(B, H, false, &pl)) return 0;
-  return carve(nullptr, H, B).total;
+  return carve(nullptr, H, B, T, D).total;
 }
 
 extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int D, int H,
@@ -656,7 +684,7 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
                               void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_fwd: bad shape B=%d T=%d D=%d H=%d yT=%d", B, T, D, H, yT);
-  Ws w = carve(workspace, H, B);
+  Ws w = carve(workspace, H, B, T, D);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
   const int H4 = 4 * H;
   const float* kern[2] = {kernel_fw, kernel_bw};
@@ -664,9 +692,21 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   float* g[2] = {gates, gates + (size_t)B * T * H4};
   float* c[2] = {cells, cells + (size_t)B * T * H};
   // input projection for all T at once: Gx = X . Kx + b
-  for (int d = 0; d < 2; ++d)
-    if (int e = gemm(GEMM_NN, B * T, H4, D, 1.f, x, D, kern[d], H4, 0.f, g[d], H4, bias[d], nullptr, nullptr, 0, stream))
-      return e;
+  if (use_h2(B, T, D, H, yT)) {
+    const int D8 = (int)align_up(D, 8);
+    if (int e = split_rows(x, D, B * T, D, w.p1h, w.p1l, D8, w.row1, stream)) return e;
+    H2Operand xa = {w.p1h, w.p1l, D8, w.row1, nullptr};
+    for (int d = 0; d < 2; ++d) {
+      if (int e = split_global(kern[d], H4, D, H4, w.wh[d], w.wl[d], H4, (unsigned*)(w.glob + 8 + d), w.glob + d, stream))
+        return e;
+      H2Operand kb = {w.wh[d], w.wl[d], H4, nullptr, w.glob + d};
+      if (int e = gemm_h2(GEMM_NN, B * T, H4, D, 1.f, xa, kb, 0.f, g[d], H4, bias[d], nullptr, nullptr, 0, stream)) return e;
+    }
+  } else {
+    for (int d = 0; d < 2; ++d)
+      if (int e = gemm(GEMM_NN, B * T, H4, D, 1.f, x, D, kern[d], H4, 0.f, g[d], H4, bias[d], nullptr, nullptr, 0, stream))
+        return e;
+  }
   NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
   if (yT > T)
     NABU_CHECK_CUDA(cudaMemset2DAsync(y + (size_t)T * 2 * H, (size_t)yT * 2 * H * sizeof(float), 0,
@@ -711,7 +751,7 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
                               void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_bwd: bad shape");
-  Ws w = carve(workspace, H, B);
+  Ws w = carve(workspace, H, B, T, D);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
   const int H4 = 4 * H;
   const float* kern[2] = {kernel_fw, kernel_bw};
@@ -750,6 +790,50 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
     NABU_CHECK_LAUNCH();
   }
   // gates[] now hold dZ (zero for t >= len)
+  if (use_h2(B, T, D, H, yT)) {
+    // One split per operand and use: x, y and dZ with a global scale for the contractions over the B*T rows (dKx, dKh),
+    // dZ again with per-row scales and the weights with a global scale for dX.
+    const int D8 = (int)align_up(D, 8);
+    unsigned* mx = (unsigned*)(w.glob + 8);
+    void* zh[2] = {w.p2h, w.p3h};
+    void* zl[2] = {w.p2l, w.p3l};
+    if (int e = split_global(x, D, B * T, D, w.p1h, w.p1l, D8, mx + 0, w.glob + 0, stream)) return e;
+    H2Operand xa = {w.p1h, w.p1l, D8, nullptr, w.glob + 0};
+    for (int d = 0; d < 2; ++d) {
+      if (int e = split_global(g[d], H4, B * T, H4, zh[d], zl[d], H4, mx + 1 + d, w.glob + 1 + d, stream)) return e;
+      H2Operand zb = {zh[d], zl[d], H4, nullptr, w.glob + 1 + d};
+      if (int e = gemm_h2(GEMM_TN, D, H4, B * T, 1.f, xa, zb, 0.f, dkern[d], H4, nullptr, nullptr, w.gemm, w.gemm_bytes, stream))
+        return e;
+    }
+    if (T > 1) {
+      if (int e = split_global(y, 2 * H, B * yT, 2 * H, w.p1h, w.p1l, 2 * H, mx + 3, w.glob + 3, stream)) return e;
+    }
+    for (int d = 0; d < 2; ++d) {
+      float* dKh = dkern[d] + (size_t)D * H4;
+      if (T > 1) {
+        GemmSeg seg;
+        seg.seg = T - 1; seg.segA = yT; seg.segB = T;
+        seg.offA = d == 0 ? 0 : 1; seg.offB = d == 0 ? 1 : 0;
+        H2Operand ya = {(const __half*)w.p1h + d * H, (const __half*)w.p1l + d * H, 2 * H, nullptr, w.glob + 3};
+        H2Operand zb = {zh[d], zl[d], H4, nullptr, w.glob + 1 + d};
+        if (int e = gemm_h2(GEMM_TN, H, H4, B * (T - 1), 1.f, ya, zb, 0.f, dKh, H4, nullptr, &seg, w.gemm, w.gemm_bytes, stream))
+          return e;
+      } else {
+        NABU_CHECK_CUDA(cudaMemsetAsync(dKh, 0, (size_t)H * H4 * sizeof(float), stream));
+      }
+    }
+    if (dx) {
+      for (int d = 0; d < 2; ++d) {
+        if (int e = split_rows(g[d], H4, B * T, H4, zh[d], zl[d], H4, w.row2, stream)) return e;
+        if (int e = split_global(kern[d], H4, D, H4, w.wh[d], w.wl[d], H4, mx + 4 + d, w.glob + 4 + d, stream)) return e;
+        H2Operand za = {zh[d], zl[d], H4, w.row2, nullptr};
+        H2Operand kb = {w.wh[d], w.wl[d], H4, nullptr, w.glob + 4 + d};
+        if (int e = gemm_h2(GEMM_NT, B * T, D, H4, 1.f, za, kb, d == 0 ? 0.f : 1.f, dx, D, nullptr, nullptr, nullptr, 0, stream))
+          return e;
+      }
+    }
+    return 0;
+  }
   for (int d = 0; d < 2; ++d) {
     // dKx = X^T . dZ
     if (int e = gemm(GEMM_TN, D, H4, B * T, 1.f, x, D, g[d], H4, 0.f, dkern[d], H4, nullptr, nullptr, w.gemm,
