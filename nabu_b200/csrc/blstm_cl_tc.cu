@@ -131,23 +131,32 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
   const uint32_t As_u = smem_u32(As), Bs_u = smem_u32(Bs);
   const int lg = warp & 3, ch = warp >> 2;             // TMEM lane group, column half
   const int row = lg * 32 + lane;
+  // a thread owns the same (batch row, unit) pairs at every step: cell state and length stay in registers
+  float ccarry[PP];
+  int lenr[PP];
+#pragma unroll
+  for (int k = 0; k < PP; ++k) {
+    const int b = (tid + k * CL_THREADS) / HS;
+    ccarry[k] = 0.f;
+    lenr[k] = b < p.B ? p.len[b] : 0;
+  }
 
   for (int s = 0; s < p.T; ++s) {
     const uint8_t* hprev = hx + (size_t)((s + 1) & 1) * H * BT * 4;
     uint8_t* hnext = hx + (size_t)(s & 1) * H * BT * 4;
     CL_STAMP(s, 0);
     // ---- prefetch pointwise operands -------------------------------------------------------------
-    float gx[PP][4], cprev[PP];
+    float gx[PP][4];
     int tb[PP];
     bool valid[PP];
 #pragma unroll
     for (int k = 0; k < PP; ++k) {
       const int pr = tid + k * CL_THREADS;
       const int jl = pr % HS, b = pr / HS;
-      valid[k] = false; tb[k] = 0; cprev[k] = 0.f;
+      valid[k] = false; tb[k] = 0;
       gx[k][0] = gx[k][1] = gx[k][2] = gx[k][3] = 0.f;
       if (b < p.B) {
-        const int L = p.len[b];
+        const int L = lenr[k];
         valid[k] = s < L;
         const int t = valid[k] ? (dir ? L - 1 - s : s) : s;
         tb[k] = t;
@@ -155,7 +164,6 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
           const float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
 #pragma unroll
           for (int g = 0; g < 4; ++g) gx[k][g] = __ldcg(gp + g * H);
-          if (s > 0) cprev[k] = __ldcg(cells + ((size_t)b * p.T + (dir ? t + 1 : t - 1)) * H + j0 + jl);
         }
       }
     }
@@ -229,12 +237,14 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
       CL_STAMP(s, 5);
     }
 
-    // ---- pointwise cell update for my HS units ----------------------------------------------------------
+    // ---- pointwise cell update for my HS units.  Only h_t (the exchange) is on the critical path of the next
+    // time step: it is stored first and published; gates, cell and output go to memory after the release. -------------
+    float av[PP][5], hn[PP];
 #pragma unroll
     for (int k = 0; k < PP; ++k) {
       const int pr = tid + k * CL_THREADS;
       const int jl = pr % HS, b = pr / HS;
-      float hn = 0.f;
+      hn[k] = 0.f;
       if (b < p.B) {
         float z[4] = {gx[k][0], gx[k][1], gx[k][2], gx[k][3]};
         if (s > 0) {
@@ -250,21 +260,16 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
         const float gg = tanhf(z[1]);
         const float fg = sigmoid_tc(z[2] + 1.0f);
         const float og = sigmoid_tc(z[3]);
-        const float cn = cprev[k] * fg + ig * gg;
-        hn = valid[k] ? tanhf(cn) * og : 0.f;
-        const int t = tb[k];
+        const float cn = ccarry[k] * fg + ig * gg;
+        av[k][0] = ig; av[k][1] = gg; av[k][2] = fg; av[k][3] = og; av[k][4] = cn;
         if (valid[k]) {
-          float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
-          __stcg(gp, ig); __stcg(gp + H, gg); __stcg(gp + 2 * H, fg); __stcg(gp + 3 * H, og);
-          __stcg(cells + ((size_t)b * p.T + t) * H + j0 + jl, cn);
+          hn[k] = tanhf(cn) * og;
+          ccarry[k] = cn;                              // valid steps are s = 0 .. len-1, so the carry is c_{s-1}
         }
-        __stcg(p.y + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl, hn);
-      }
-      // h_t, split, in the consumer's UMMA layout (rows b >= B stay zero from the host memset)
-      if (b < p.B) {
+        // h_t, split, in the consumer's UMMA layout (rows b >= B stay zero from the host memset)
         const int j = j0 + jl;
         __half hi, lo;
-        split_h(hn, &hi, &lo);
+        split_h(hn[k], &hi, &lo);
         uint8_t* t = hnext + (size_t)((j / KS) * KB + (j % KS) / 64) * 2 * A_TILE + sw128_h(b, j % 64);
         __stcg(reinterpret_cast<unsigned short*>(t), __half_as_ushort(hi));
         __stcg(reinterpret_cast<unsigned short*>(t + A_TILE), __half_as_ushort(lo));
@@ -284,6 +289,21 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
     CL_STAMP(s, 8);
     if (tid == 0) red_release_gpu_add(cnt + q, 1u);
     CL_STAMP(s, 9);
+    // ---- off the critical path: what the backward pass and the next layer need --------------------------
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      const int pr = tid + k * CL_THREADS;
+      const int jl = pr % HS, b = pr / HS;
+      if (b < p.B) {
+        const int t = tb[k];
+        if (valid[k]) {
+          float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+          __stcg(gp, av[k][0]); __stcg(gp + H, av[k][1]); __stcg(gp + 2 * H, av[k][2]); __stcg(gp + 3 * H, av[k][3]);
+          __stcg(cells + ((size_t)b * p.T + t) * H + j0 + jl, av[k][4]);
+        }
+        __stcg(p.y + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl, hn[k]);
+      }
+    }
   }
   tc_fence_before();
   cluster_arrive();
@@ -378,7 +398,7 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
   constexpr int SLAB = 4 * NC;             // dz columns per producer cluster
   constexpr int KBN = CPS * SLAB / 64;     // K blocks per slice (= HS)
   constexpr int KBC = KBN / CPS;           // K blocks per producer cluster
-  constexpr int NST = 3;                   // ring stages
+  constexpr int NST = HS == 8 ? 4 : 3;     // ring stages (all the shared memory that is left)
   constexpr int B_TILE = NC * 128;         // bytes of one [NC rows x 64 fp16] tile
   constexpr int TCOLS = 2 * NC < 32 ? 32 : 2 * NC;
   constexpr int PAIRS = BT * HS;
@@ -388,12 +408,12 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
   uint8_t* Bs = sm;                                    // [KBN][hi|lo][B_TILE]
   uint8_t* ring = Bs + KBN * 2 * B_TILE;               // [NST][hi|lo][A_TILE]
   float* rbuf = reinterpret_cast<float*>(ring + NST * 2 * A_TILE);   // [2 parity][CLS src][BT][HS]
-  float* red = rbuf + 2 * CLS * BT * HS;               // [CL_THREADS][4] bias-gradient scratch
+  float* red = reinterpret_cast<float*>(ring);          // [CL_THREADS][4] bias-gradient scratch (after the loop)
   __shared__ __align__(8) uint64_t full_bar[NST];
   __shared__ __align__(8) uint64_t empty_bar[NST];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float scale[BT], inv_scale[BT];
+  __shared__ float scale[BT];
 
   const int H = p.H, H4 = 4 * p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -407,7 +427,6 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
   const float* cells = p.cells[dir];
   unsigned* cnt = p.counters + dir * 16;
   uint8_t* dzx = reinterpret_cast<uint8_t*>(p.xchg) + (size_t)dir * 2 * H4 * BT * 4;   // [2 parity][slice][KBN][hi|lo][A_TILE]
-  float* dcb = p.dcbuf + (size_t)dir * BT * H;
 
   // resident weights, split: B[n][kl] = Kh[NC*q + n][g*H + NC*(r*CPS + cl) + u],  kl = (cl*4 + g)*NC + u
   for (int i = tid; i < CPS * SLAB * NC; i += CL_THREADS) {
@@ -430,7 +449,6 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
       S = ldexpf(1.f, 6 - e);                          // G * S in [32, 64)
     }
     scale[tid] = S;
-    inv_scale[tid] = 1.f / S;
   }
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -453,7 +471,16 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
   const uint32_t idesc = make_idesc_f16(128, NC);
   const uint32_t ring_u = smem_u32(ring), Bs_u = smem_u32(Bs);
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  unsigned gq = 0;                                     // K blocks consumed so far (ring position), used by tid 0
+  unsigned gq = 0;                                     // K blocks consumed so far (ring position)
+  // a thread owns the same (batch row, unit) pairs at every step: the carried dc and the length stay in registers
+  float dcc[PP];
+  int lenr[PP];
+#pragma unroll
+  for (int k = 0; k < PP; ++k) {
+    const int b = (tid + k * CL_THREADS) / HS;
+    dcc[k] = 0.f;
+    lenr[k] = b < p.B ? p.len[b] : 0;
+  }
 
   int iter = 0;
   for (int s = p.T - 1; s >= 0; --s, ++iter) {
@@ -462,17 +489,17 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
     float* rb = rbuf + (size_t)(iter & 1) * CLS * BT * HS;
     CL_STAMP(iter, 0);
     // ---- prefetch pointwise operands -----------------------------------------------------------
-    float gt[PP][4], ct[PP], cprev[PP], dyv[PP], dcr[PP];
+    float gt[PP][4], ct[PP], cprev[PP], dyv[PP];
     int tb[PP];
     bool valid[PP];
 #pragma unroll
     for (int k = 0; k < PP; ++k) {
       const int pr = tid + k * CL_THREADS;
       const int jl = pr % HS, b = pr / HS;
-      valid[k] = false; tb[k] = 0; ct[k] = cprev[k] = dyv[k] = dcr[k] = 0.f;
+      valid[k] = false; tb[k] = 0; ct[k] = cprev[k] = dyv[k] = 0.f;
       gt[k][0] = gt[k][1] = gt[k][2] = gt[k][3] = 0.f;
       if (b < p.B) {
-        const int L = p.len[b];
+        const int L = lenr[k];
         valid[k] = s < L;
         const int t = valid[k] ? (dir ? L - 1 - s : s) : s;
         tb[k] = t;
@@ -483,34 +510,36 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
           ct[k] = __ldcg(cells + ((size_t)b * p.T + t) * H + j0 + jl);
           if (s > 0) cprev[k] = __ldcg(cells + ((size_t)b * p.T + (dir ? t + 1 : t - 1)) * H + j0 + jl);
           dyv[k] = __ldcg(p.dy + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl);
-          if (iter > 0) dcr[k] = __ldcg(dcb + (size_t)b * H + j0 + jl);
         }
       }
     }
 
     if (iter > 0) {
-      if (tid == 0) {
+      const unsigned g0 = gq;
+      if (tid == 32) {
+        // ---- loader (warp 1): K block kb of this step -> ring position g0 + kb, as soon as its producer cluster has
+        // published and the previous tenant of the stage has been consumed by the tensor core ----------------------
         const unsigned target = (unsigned)CLS * (unsigned)iter;
         const uint8_t* slab = dzprev + (size_t)r * KBN * 2 * A_TILE;
-        const unsigned g0 = gq;
-        auto issue = [&](int kb) {                     // K block kb of this step -> ring position g0 + kb
-          if (kb % KBC == 0) {                         // first block of a producer cluster: wait for its dz
+#pragma unroll 1
+        for (int kb = 0; kb < KBN; ++kb) {
+          if (kb % KBC == 0) {
             while (ld_acquire_gpu(cnt + r * CPS + kb / KBC) < target) { }
             __threadfence();
             fence_proxy_async_all();
           }
           const unsigned pos = g0 + kb, st = pos % NST;
-          if (pos >= NST) mbar_wait(smem_u32(&empty_bar[st]), (pos / NST - 1) & 1);   // MMAs of the previous tenant done
+          if (pos >= NST) mbar_wait(smem_u32(&empty_bar[st]), (pos / NST - 1) & 1);
           mbar_expect_tx(smem_u32(&full_bar[st]), 2 * A_TILE);
           cb_bulk(ring + (size_t)st * 2 * A_TILE, slab + (size_t)kb * 2 * A_TILE, 2 * A_TILE, &full_bar[st]);
-        };
-        for (int kb = 0; kb < NST && kb < KBN; ++kb) issue(kb);
-        CL_STAMP(iter, 1);
+        }
+      } else if (tid == 0) {
+        // ---- MMA issuer (warp 0) ----------------------------------------------------------------------------
 #pragma unroll 1
         for (int kb = 0; kb < KBN; ++kb) {
           const unsigned pos = g0 + kb, st = pos % NST;
           mbar_wait(smem_u32(&full_bar[st]), (pos / NST) & 1);
-          if (kb == 0) CL_STAMP(iter, 2);
+          if (kb == 0) { CL_STAMP(iter, 1); CL_STAMP(iter, 2); }
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -524,11 +553,10 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
             umma_f16(tm + NC, al, bh, idesc, 1u);
           }
           umma_commit(smem_u32(&empty_bar[st]));
-          if (kb >= 1 && kb - 1 + NST < KBN) issue(kb - 1 + NST);
         }
         umma_commit(smem_u32(&mma_bar));
-        gq = g0 + KBN;
       }
+      gq = g0 + KBN;
       __syncwarp();
       mbar_wait(smem_u32(&mma_bar), (unsigned)(iter - 1) & 1u);
       tc_fence_after();
@@ -546,7 +574,7 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
           tmem_ld16(taddr + NC, reinterpret_cast<uint32_t(&)[16]>(v2));
         }
         tmem_ld_wait();
-        const float is = inv_scale[row];
+        const float is = 1.f / scale[row];                // exact: S is a power of two
 #pragma unroll
         for (int d = 0; d < CLS; ++d) {
           const uint32_t dst = map_to_rank(smem_u32(rbuf), (uint32_t)d) +
@@ -571,11 +599,14 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
       CL_STAMP(iter, 5);
     }
 
-    // ---- pointwise gate gradients for my HS units -------------------------------------------------------
+    // ---- pointwise gate gradients for my HS units.  Only the exchanged dz is on the critical path of the next
+    // time step; the fp32 dz the GEMMs read (gates[]) goes to memory after the release. -------------------------------
+    float dzv[PP][4];
 #pragma unroll
     for (int k = 0; k < PP; ++k) {
       const int pr = tid + k * CL_THREADS;
       const int jl = pr % HS, b = pr / HS;
+      dzv[k][0] = dzv[k][1] = dzv[k][2] = dzv[k][3] = 0.f;
       if (b < p.B) {
         float dh = dyv[k];
         if (iter > 0) {
@@ -583,36 +614,32 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
 #pragma unroll
           for (int src = 0; src < CLS; ++src) dh += rb[((size_t)src * BT + b) * HS + pos * 4 + (jl & 3)];
         }
-        float dz[4] = {0.f, 0.f, 0.f, 0.f};
         float dcn = 0.f;
         if (valid[k]) {
           const float ig = gt[k][0], gg = gt[k][1], fg = gt[k][2], og = gt[k][3];
           const float tc_ = tanhf(ct[k]);
           const float d_o = dh * tc_;
-          const float dc = dcr[k] + dh * og * (1.f - tc_ * tc_);
-          dz[0] = dc * gg * ig * (1.f - ig);
-          dz[1] = dc * ig * (1.f - gg * gg);
-          dz[2] = dc * cprev[k] * fg * (1.f - fg);
-          dz[3] = d_o * og * (1.f - og);
+          const float dc = dcc[k] + dh * og * (1.f - tc_ * tc_);
+          dzv[k][0] = dc * gg * ig * (1.f - ig);
+          dzv[k][1] = dc * ig * (1.f - gg * gg);
+          dzv[k][2] = dc * cprev[k] * fg * (1.f - fg);
+          dzv[k][3] = d_o * og * (1.f - og);
           dcn = dc * fg;
         }
-        const int t = tb[k];
-        float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+        dcc[k] = dcn;
         const float S = scale[b];
         // my cluster is producer (q % CPS) of K-slice q / CPS; column kl = ((q % CPS)*4 + g)*NC + r*HS + jl
         uint8_t* xs = dznext + (size_t)(q / CPS) * KBN * 2 * A_TILE;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          __stcg(gp + g * H, dz[g]);
           const int kl = ((q % CPS) * 4 + g) * NC + r * HS + jl;
           __half hi, lo;
-          split_h_sat(dz[g] * S, &hi, &lo);
+          split_h_sat(dzv[k][g] * S, &hi, &lo);
           uint8_t* tptr = xs + (size_t)(kl / 64) * 2 * A_TILE + sw128_h(b, kl % 64);
           __stcg(reinterpret_cast<unsigned short*>(tptr), __half_as_ushort(hi));
           __stcg(reinterpret_cast<unsigned short*>(tptr + A_TILE), __half_as_ushort(lo));
-          dbacc[g] += dz[g];
+          dbacc[g] += dzv[k][g];
         }
-        __stcg(dcb + (size_t)b * H + j0 + jl, dcn);
       }
     }
     CL_STAMP(iter, 6);
@@ -625,6 +652,16 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
     CL_STAMP(iter, 8);
     if (tid == 0) red_release_gpu_add(cnt + q, 1u);
     CL_STAMP(iter, 9);
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      const int pr = tid + k * CL_THREADS;
+      const int jl = pr % HS, b = pr / HS;
+      if (b < p.B) {
+        float* gp = gates + ((size_t)b * p.T + tb[k]) * H4 + j0 + jl;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) __stcg(gp + g * H, dzv[k][g]);
+      }
+    }
   }
 
   // bias gradient: every thread's pairs share jl = tid % HS; fixed-order sum over threads
@@ -648,9 +685,8 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
 
 template <int HS>
 int launch_bwd_tc(const ClParams& p, unsigned* rowmax, cudaStream_t stream, bool* launched) {
-  constexpr int CLS = TC_CLS, NC = CLS * HS, KBN = HS, NST = 3;
-  const size_t smem = 1024 + (size_t)KBN * 2 * NC * 128 + (size_t)NST * 2 * A_TILE +
-                      (size_t)2 * CLS * 128 * HS * sizeof(float) + (size_t)CL_THREADS * 4 * sizeof(float);
+  constexpr int CLS = TC_CLS, NC = CLS * HS, KBN = HS, NST = HS == 8 ? 4 : 3;
+  const size_t smem = 1024 + (size_t)KBN * 2 * NC * 128 + (size_t)NST * 2 * A_TILE + (size_t)2 * CLS * 128 * HS * sizeof(float);
   auto* fn = blstm_rec_bwd_cluster_tc_kernel<HS>;
   *launched = false;
   if (smem > (size_t)max_smem_optin()) return 0;
