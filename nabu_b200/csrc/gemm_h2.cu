@@ -31,7 +31,8 @@ constexpr int H2_THREADS = 192;
 constexpr int H2_A_TILE = H2_BM * H2_BK * 2;             // 16 KB
 constexpr int H2_B_TILE = H2_BN * H2_BK * 2;             // 32 KB
 constexpr int H2_STAGE = 2 * H2_A_TILE + 2 * H2_B_TILE;  // 96 KB
-constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256;
+constexpr int H2_TPAD = 36;                              // padded row of the epilogue transpose buffer (floats)
+constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256 + 4 * 32 * H2_TPAD * 4;
 
 struct H2Args {
   int M, N;
@@ -153,7 +154,10 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       umma_commit(bar_tmem);
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> (warp-private smem transpose) -> coalesced global stores =====
+    // tcgen05.ld hands every thread one ROW of the tile; storing that directly makes each warp instruction touch 32
+    // rows (measured: 29 us per tile, 0.7 TB/s).  Each warp therefore transposes its 32 x 32 chunk through a padded
+    // shared buffer and writes full 128-byte row segments (8 lanes x float4 per row, 4 rows per instruction).
     const int q = warp & 3;
     const int m = m0 + 32 * q + lane;
     const bool split = g.part != nullptr;
@@ -162,12 +166,15 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     const bool vec = ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (ldc % 4 == 0);
     float sa_inv = g.a_glob_inv ? __ldg(g.a_glob_inv) : 1.f;
     if (g.a_row_inv && m < g.M) sa_inv *= __ldg(g.a_row_inv + m);
-    const float sb_glob = g.b_glob_inv ? __ldg(g.b_glob_inv) : 1.f;
+    sa_inv *= g.b_glob_inv ? __ldg(g.b_glob_inv) : 1.f;
+    float* tbuf = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256) + (warp - 2) * (32 * H2_TPAD);
+    const int rl = lane >> 3, c4 = (lane & 7) * 4;       // read phase: row within a group of 4, first of 4 columns
     if (nkb > 0) {
       mbar_wait(bar_tmem, 0);
       tc_fence_after();
     }
     for (int c0 = 0; c0 < H2_BN; c0 += 32) {
+      if (n0 + c0 >= g.N) break;
       uint32_t r1[32], r2[32];
       if (nkb > 0) {
         tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r1);
@@ -177,31 +184,48 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) r1[j] = r2[j] = 0u;
       }
-      if (m < g.M) {
-        float* crow = Cout + (size_t)m * ldc;
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const int n = n0 + c0 + j4;
-          if (n >= g.N) break;
-          const int nv = min(4, g.N - n);
-          float v[4];
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        float4 v;
+        v.x = fmaf(__uint_as_float(r2[j4 + 0]), 1.f / 2048.f, __uint_as_float(r1[j4 + 0])) * sa_inv;
+        v.y = fmaf(__uint_as_float(r2[j4 + 1]), 1.f / 2048.f, __uint_as_float(r1[j4 + 1])) * sa_inv;
+        v.z = fmaf(__uint_as_float(r2[j4 + 2]), 1.f / 2048.f, __uint_as_float(r1[j4 + 2])) * sa_inv;
+        v.w = fmaf(__uint_as_float(r2[j4 + 3]), 1.f / 2048.f, __uint_as_float(r1[j4 + 3])) * sa_inv;
+        *reinterpret_cast<float4*>(tbuf + lane * H2_TPAD + j4) = v;
+      }
+      __syncwarp();
+      const int n = n0 + c0 + c4;
+      float cs[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[j] = fmaf(__uint_as_float(r2[j4 + j]), 1.f / 2048.f, __uint_as_float(r1[j4 + j])) * sa_inv * sb_glob;
-            if (j < nv) {
-              if (g.b_row_inv) v[j] *= __ldg(g.b_row_inv + n + j);
-              if (!split) {
-                float o = g.alpha * v[j];
-                if (g.bias) o += g.bias[n + j];
-                if (g.beta != 0.f) o += g.beta * crow[n + j];
-                v[j] = o;
-              }
-            }
+      for (int j = 0; j < 4; ++j)
+        if (n + j < g.N) {
+          if (g.b_row_inv) cs[j] = __ldg(g.b_row_inv + n + j);
+          if (!split) {
+            cs[j] *= g.alpha;
+            if (g.bias) bs[j] = __ldg(g.bias + n + j);
           }
-          if (nv == 4 && vec) *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-          else for (int j = 0; j < nv; ++j) crow[n + j] = v[j];
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rl;
+        const int mm = m0 + 32 * q + rr;
+        const float4 t4 = *reinterpret_cast<const float4*>(tbuf + rr * H2_TPAD + c4);
+        float v[4] = {fmaf(t4.x, cs[0], bs[0]), fmaf(t4.y, cs[1], bs[1]), fmaf(t4.z, cs[2], bs[2]), fmaf(t4.w, cs[3], bs[3])};
+        if (mm < g.M && n < g.N) {
+          float* cp = Cout + (size_t)mm * ldc + n;
+          const int nv = min(4, g.N - n);
+          if (nv == 4 && vec) {
+            if (!split && g.beta != 0.f) {
+              const float4 o = *reinterpret_cast<const float4*>(cp);
+              v[0] += g.beta * o.x; v[1] += g.beta * o.y; v[2] += g.beta * o.z; v[3] += g.beta * o.w;
+            }
+            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            for (int j = 0; j < nv; ++j) cp[j] = (!split && g.beta != 0.f) ? v[j] + g.beta * cp[j] : v[j];
+          }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

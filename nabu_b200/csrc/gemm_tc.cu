@@ -14,7 +14,7 @@
 //              (generic proxy -> fence.proxy.async -> mbarrier), later the epilogue warps
 //   warp 1     MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8) x 4 k-steps x 3
 //              products per stage, tcgen05.commit frees the stage / signals the epilogue
-//   epilogue   tcgen05.ld 32x32b -> alpha, beta, bias -> 128-bit global stores
+//   epilogue   tcgen05.ld 32x32b -> warp-private smem transpose -> alpha, beta, bias -> coalesced 128-bit stores
 // Operands may be K-major (row = M/N index, K contiguous) or MN-major (row = K index): both are legal
 // UMMA layouts for TF32, selected in the instruction descriptor, so NN / NT / TN need no transposes.
 #include "common.cuh"
@@ -29,7 +29,8 @@ constexpr int TC_THREADS = 192;
 constexpr int A_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB
 constexpr int B_TILE_BYTES = TC_BN * TC_BK * 4;          // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // hi+lo of both = 96 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_TPAD = 36;                              // padded row of the epilogue transpose buffer (floats)
+constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * TC_TPAD * 4;
 
 struct TcArgs {
   int M, N;
@@ -151,18 +152,21 @@ split_tile(sa, A_TILE_BYTES, ct, 128);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
       mbar_arrive(bar_conv(s));
     }
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> (warp-private smem transpose) -> coalesced global stores =====
+    // (see gemm_h2.cu: storing the row each thread gets from tcgen05.ld directly touches 32 rows per instruction)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int m = m0 + 32 * q + lane;
     const bool split = g.part != nullptr;
     float* Cout = split ? g.part + (size_t)blockIdx.z * g.M * g.N : g.C;
     const int ldc = split ? g.N : g.ldc;
     const bool vec = ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (ldc % 4 == 0);
+    float* tbuf = reinterpret_cast<float*>(base_ptr + TC_STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * TC_TPAD);
+    const int rl = lane >> 3, c4 = (lane & 7) * 4;
     if (nkb > 0) {
       mbar_wait(bar_tmem, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      if (n0 + c0 >= g.N) break;
       uint32_t r[32];
       if (nkb > 0) {
         tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
@@ -171,30 +175,39 @@ split_tile(sa, A_TILE_BYTES, ct, 128);
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (m < g.M) {
-        float* crow = Cout + (size_t)m * ldc;
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const int n = n0 + c0 + j4;
-          if (n >= g.N) break;
-          float v[4] = {__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]),
-                        __uint_as_float(r[j4 + 3])};
+      for (int j4 = 0; j4 < 32; j4 += 4)
+        *reinterpret_cast<float4*>(tbuf + lane * TC_TPAD + j4) =
+            make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]), __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
+      __syncwarp();
+      const int n = n0 + c0 + c4;
+      float cs = split ? 1.f : g.alpha, bs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!split && g.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < g.N) bs[j] = __ldg(g.bias + n + j);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rl;
+        const int mm = m0 + 32 * q + rr;
+        const float4 t4 = *reinterpret_cast<const float4*>(tbuf + rr * TC_TPAD + c4);
+        float v[4] = {fmaf(t4.x, cs, bs[0]), fmaf(t4.y, cs, bs[1]), fmaf(t4.z, cs, bs[2]), fmaf(t4.w, cs, bs[3])};
+        if (mm < g.M && n < g.N) {
+          float* cp = Cout + (size_t)mm * ldc + n;
           const int nv = min(4, g.N - n);
-          if (!split) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < nv) {
-                float o = g.alpha * v[j];
-                if (g.bias) o += g.bias[n + j];
-                if (g.beta != 0.f) o += g.beta * crow[n + j];
-                v[j] = o;
-              }
+          if (nv == 4 && vec) {
+            if (!split && g.beta != 0.f) {
+              const float4 o = *reinterpret_cast<const float4*>(cp);
+              v[0] += g.beta * o.x; v[1] += g.beta * o.y; v[2] += g.beta * o.z; v[3] += g.beta * o.w;
             }
+            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            for (int j = 0; j < nv; ++j) cp[j] = (!split && g.beta != 0.f) ? v[j] + g.beta * cp[j] : v[j];
           }
-          if (nv == 4 && vec) *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-          else for (int j = 0; j < nv; ++j) crow[n + j] = v[j];
         }
       }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
