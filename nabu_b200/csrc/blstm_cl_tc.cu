@@ -55,7 +55,36 @@ __device__ __forceinline__ void split_h(float x, __half* hi, __half* lo) {
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+// Gate non-linearities from MUFU.EX2 / MUFU.RCP (4-5 instructions instead of ~40 for expf and ~60 for tanhf; the
+// pointwise stage of a time step is issue-bound on them).  Absolute error <= 2e-7 on values in (-1, 1): the same order
+// as the fp32 rounding of the cell state they feed, three orders below the 1e-4 parity bar (tests/test_gpu_kernels.py).
+__device__ __forceinline__ float sigmoid_tc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_tc(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+// ---- flag-in-data exchange ("LL"): the value written at step s carries ll_flag(s) in the lowest bit of BOTH of its
+// fp16 halves; a buffer is rewritten every second step, so consecutive tenants of a location differ in that bit and the
+// memset-zero initial state differs from the first one.  The residual is computed against the flagged hi half, so
+// hi' + lo' * 2^-11 still carries x to 2^-20 relative (the flag costs at most one ulp of lo).
+__device__ __forceinline__ uint32_t ll_flag(int step) { return (((uint32_t)step >> 1) & 1u) ^ 1u; }
+__device__ __forceinline__ void split_h_flag(float x, unsigned short fb, unsigned short* hi, unsigned short* lo) {
+  const unsigned short h = (unsigned short)((__half_as_ushort(__float2half_rn(x)) & 0xFFFEu) | fb);
+  *hi = h;
+  const float res = (x - __half2float(__ushort_as_half(h))) * 2048.f;
+  *lo = (unsigned short)((__half_as_ushort(__float2half_rn(res)) & 0xFFFEu) | fb);
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool ll_ok(const uint4& v, uint32_t fl) {
+  return (((v.x ^ fl) | (v.y ^ fl) | (v.z ^ fl) | (v.w ^ fl)) & 0x00010001u) == 0u;
+}
 
 // receive buffer: [4 src][128 rows][4*HS floats], 16-byte chunks XOR-swizzled per row
 template <int HS>
@@ -72,18 +101,15 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
   constexpr int GC = 4 * NC;               // gate columns per cluster = MMA N
   constexpr int KS = 64 * HS / CLS;        // h rows per K-slice
   constexpr int KB = KS / 64;              // 64-wide K blocks per slice
-  constexpr int CPS = 64 / CLS / CLS;      // producer clusters per K-slice
   constexpr int B_TILE = GC * 128;         // bytes of one [GC rows x 64 fp16] tile
   constexpr int RW = 4 * HS;               // floats per receive row
   constexpr int TCOLS = 2 * GC;            // TMEM columns: D1 | D2
-  constexpr int PAIRS = BT * HS;
-  constexpr int PP = PAIRS / CL_THREADS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Bs = sm;                                    // [KB][hi|lo][B_TILE]
   uint8_t* As = Bs + KB * 2 * B_TILE;                  // [KB][hi|lo][A_TILE]
   float* rbuf = reinterpret_cast<float*>(As + KB * 2 * A_TILE);   // [CLS][BT][RW]
-  __shared__ __align__(8) uint64_t a_bar[2];
+  __shared__ __align__(8) uint64_t rx_bar;
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
 
@@ -97,7 +123,6 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
   const float* Kh = p.kernel[dir] + (size_t)p.D * H4;
   float* gates = p.gates[dir];
   float* cells = const_cast<float*>(p.cells[dir]);
-  unsigned* cnt = p.counters + dir * 16;
   uint8_t* hx = reinterpret_cast<uint8_t*>(p.xchg) + (size_t)dir * 2 * H * BT * 4;   // [2 parity][slice][KB][hi|lo][A_TILE]
 
   // resident weights, split: B[n][k] = Kh[r*KS + k][g*H + NC*q + d*HS + u],  n = d*4*HS + g*HS + u
@@ -112,8 +137,7 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
     *reinterpret_cast<__half*>(t + B_TILE) = lo;
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&a_bar[0]), 1);
-    mbar_init(smem_u32(&a_bar[1]), 1);
+    mbar_init(smem_u32(&rx_bar), 1);
     mbar_init(smem_u32(&mma_bar), 1);
     fence_barrier_init();
   }
@@ -131,62 +155,75 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
   const uint32_t As_u = smem_u32(As), Bs_u = smem_u32(Bs);
   const int lg = warp & 3, ch = warp >> 2;             // TMEM lane group, column half
   const int row = lg * 32 + lane;
-  // a thread owns the same (batch row, unit) pairs at every step: cell state and length stay in registers
-  float ccarry[PP];
-  int lenr[PP];
+  // A thread owns batch row pb and UPT consecutive units at every step (one 16- or 8-byte access per array): cell
+  // state and length stay in registers.
+  constexpr int UPT = HS / 2;
+  constexpr int NCH = KB * 2 * A_TILE / 16 / CL_THREADS;   // 16-byte chunks of my K-slice per thread
+  const int pb = tid >> 1, pu = (tid & 1) * UPT;
+  const bool prow = pb < p.B;
+  const int plen = prow ? p.len[pb] : 0;
+  float ccarry[UPT];
 #pragma unroll
-  for (int k = 0; k < PP; ++k) {
-    const int b = (tid + k * CL_THREADS) / HS;
-    ccarry[k] = 0.f;
-    lenr[k] = b < p.B ? p.len[b] : 0;
-  }
+  for (int u = 0; u < UPT; ++u) ccarry[u] = 0.f;
+  const uint32_t rbuf_u = smem_u32(rbuf);
 
   for (int s = 0; s < p.T; ++s) {
     const uint8_t* hprev = hx + (size_t)((s + 1) & 1) * H * BT * 4;
     uint8_t* hnext = hx + (size_t)(s & 1) * H * BT * 4;
     CL_STAMP(s, 0);
     // ---- prefetch pointwise operands -------------------------------------------------------------
-    float gx[PP][4];
-    int tb[PP];
-    bool valid[PP];
+    float gx[4][UPT];
+    const bool valid = s < plen;
+    const int tt = valid ? (dir ? plen - 1 - s : s) : s;
 #pragma unroll
-    for (int k = 0; k < PP; ++k) {
-      const int pr = tid + k * CL_THREADS;
-      const int jl = pr % HS, b = pr / HS;
-      valid[k] = false; tb[k] = 0;
-      gx[k][0] = gx[k][1] = gx[k][2] = gx[k][3] = 0.f;
-      if (b < p.B) {
-        const int L = lenr[k];
-        valid[k] = s < L;
-        const int t = valid[k] ? (dir ? L - 1 - s : s) : s;
-        tb[k] = t;
-        if (valid[k]) {
-          const float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+    for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int g = 0; g < 4; ++g) gx[k][g] = __ldcg(gp + g * H);
+      for (int u = 0; u < UPT; ++u) gx[g][u] = 0.f;
+    if (valid) {
+      const float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if constexpr (UPT == 4) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + g * H));
+          gx[g][0] = v.x; gx[g][1] = v.y; gx[g][2] = v.z; gx[g][3] = v.w;
+        } else {
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(gp + g * H));
+          gx[g][0] = v.x; gx[g][1] = v.y;
         }
       }
     }
 
     if (s > 0) {
       const unsigned par = (unsigned)(s - 1) & 1u;
-      if (tid == 0) {
-        const unsigned target = (unsigned)CLS * (unsigned)s;
-        for (int c = 0; c < CPS; ++c)
-          while (ld_acquire_gpu(cnt + r * CPS + c) < target) { }
+      if (tid == 0) mbar_expect_tx(smem_u32(&rx_bar), (CLS - 1) * BT * RW * 4);
+      // ---- fetch my K-slice of h_{s-1}.  No counters and no release/acquire round trips: every 16-bit half carries
+      // the flag of the step that wrote it in its lowest bit (see the producer below), so the data validate themselves.
+      // A thread spins on its first 16-byte chunk only (4 KB of polling traffic per CTA and round trip), then
+      // fetches the rest and re-reads whatever is still stale; the slice is already the UMMA image of the A operand.
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(hprev + (size_t)r * KB * 2 * A_TILE) + tid;
+        const uint32_t fl = ll_flag(s - 1) ? 0x00010001u : 0u;
+        uint4 v[NCH];
+        do { v[0] = ld_relaxed_v4(src); } while (!ll_ok(v[0], fl));
         CL_STAMP(s, 1);
-        __threadfence();
-        fence_proxy_async_all();
+#pragma unroll
+        for (int i = 1; i < NCH; ++i) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
+#pragma unroll
+        for (int i = 1; i < NCH; ++i)
+          while (!ll_ok(v[i], fl)) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
+        // peers have read their receive buffers of step s-1, hence received my quarters: As and their buffers are free
+        cluster_wait();
+        uint4* dstA = reinterpret_cast<uint4*>(As) + tid;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) dstA[i * CL_THREADS] = v[i];
+        fence_proxy_async_smem();
+        __syncthreads();
+      }
+      if (tid == 0) {
+        CL_STAMP(s, 2);
+        tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_expect_tx(smem_u32(&a_bar[kb]), 2 * A_TILE);
-          cb_bulk(As + (size_t)kb * 2 * A_TILE, hprev + (size_t)(r * KB + kb) * 2 * A_TILE, 2 * A_TILE, &a_bar[kb]);
-        }
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(smem_u32(&a_bar[kb]), par);
-          if (kb == 0) CL_STAMP(s, 2);
-          tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ah = make_desc(As_u + (kb * 2 + 0) * A_TILE + ks * 32, 16, 1024, 2);
@@ -205,8 +242,11 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
       mbar_wait(smem_u32(&mma_bar), par);
       tc_fence_after();
       CL_STAMP(s, 3);
-      cluster_wait();                                  // every peer has finished reading its receive buffer (step s-1)
-      // ---- TMEM -> peers' receive buffers (slot r) ----------------------------------------------------------
+      // ---- TMEM -> receive buffers (slot r).  My own quarter goes straight into my buffer; the three remote quarters
+      // are staged in As (free: the MMAs have consumed it) and pushed by ONE bulk DSMEM copy each, which completes on
+      // the destination's mbarrier: no remote store instructions and no closing cluster barrier (those two cost
+      // 4.5 us of an 10.5 us time step; st.shared::cluster moved ~15 bytes/ns).  As is free again for the next step
+      // because the cluster_wait before the next step's As stores implies the peers' rx_bar phases completed. ----------
 #pragma unroll
       for (int dd = 0; dd < 2; ++dd) {
         const int d = 2 * ch + dd;
@@ -220,89 +260,105 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
           tmem_ld16(taddr + GC, reinterpret_cast<uint32_t(&)[16]>(v2));
         }
         tmem_ld_wait();
-        const uint32_t dst = map_to_rank(smem_u32(rbuf), (uint32_t)d) + (uint32_t)((r * BT + row) * RW) * 4u;
+        float* dstl = (d == r) ? rbuf + (size_t)(r * BT + row) * RW
+                               : reinterpret_cast<float*>(As) + (size_t)(d * BT + row) * RW;
 #pragma unroll
         for (int c4 = 0; c4 < RW / 4; ++c4) {
-          float z[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            z[e] = fmaf(__uint_as_float(v2[c4 * 4 + e]), 1.f / 2048.f, __uint_as_float(v1[c4 * 4 + e]));
-          st_cluster_v4(dst + (uint32_t)rb_chunk<HS>(row, c4) * 16u, z[0], z[1], z[2], z[3]);
+          float4 z;
+          z.x = fmaf(__uint_as_float(v2[c4 * 4 + 0]), 1.f / 2048.f, __uint_as_float(v1[c4 * 4 + 0]));
+          z.y = fmaf(__uint_as_float(v2[c4 * 4 + 1]), 1.f / 2048.f, __uint_as_float(v1[c4 * 4 + 1]));
+          z.z = fmaf(__uint_as_float(v2[c4 * 4 + 2]), 1.f / 2048.f, __uint_as_float(v1[c4 * 4 + 2]));
+          z.w = fmaf(__uint_as_float(v2[c4 * 4 + 3]), 1.f / 2048.f, __uint_as_float(v1[c4 * 4 + 3]));
+          *reinterpret_cast<float4*>(dstl + rb_chunk<HS>(row, c4) * 4) = z;
         }
       }
       tc_fence_before();
+      fence_proxy_async_smem();
+      __syncthreads();
       CL_STAMP(s, 4);
-      cluster_arrive();
-      cluster_wait();
+      if (tid < CLS && tid != r) {
+        constexpr uint32_t QB = BT * RW * 4;           // bytes of one quarter
+        bulk_s2s(map_to_rank(rbuf_u + (uint32_t)r * QB, (uint32_t)tid), As_u + (uint32_t)tid * QB, QB,
+                 map_to_rank(smem_u32(&rx_bar), (uint32_t)tid));
+      }
+      mbar_wait(smem_u32(&rx_bar), par);               // the three remote quarters have landed in my buffer
       CL_STAMP(s, 5);
     }
 
-    // ---- pointwise cell update for my HS units.  Only h_t (the exchange) is on the critical path of the next
-    // time step: it is stored first and published; gates, cell and output go to memory after the release. -------------
-    float av[PP][5], hn[PP];
+    // ---- pointwise cell update for my units.  Only h_t (the exchange) is on the critical path of the next time
+    // step: it is stored first and published; gates, cell and output go to memory after the release. ---------------
+    float av[5][UPT], hn[UPT];
 #pragma unroll
-    for (int k = 0; k < PP; ++k) {
-      const int pr = tid + k * CL_THREADS;
-      const int jl = pr % HS, b = pr / HS;
-      hn[k] = 0.f;
-      if (b < p.B) {
-        float z[4] = {gx[k][0], gx[k][1], gx[k][2], gx[k][3]};
-        if (s > 0) {
+    for (int u = 0; u < UPT; ++u) hn[u] = 0.f;
+    if (s > 0) {
 #pragma unroll
-          for (int src = 0; src < CLS; ++src)
+      for (int src = 0; src < CLS; ++src)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int c = g * HS + jl;
-              z[g] += rbuf[((size_t)src * BT + b) * RW + rb_chunk<HS>(b, c >> 2) * 4 + (c & 3)];
-            }
+        for (int g = 0; g < 4; ++g) {
+          const float* rp = rbuf + ((size_t)src * BT + pb) * RW;
+          if constexpr (UPT == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(rp + rb_chunk<HS>(pb, g * 2 + (tid & 1)) * 4);
+            gx[g][0] += v.x; gx[g][1] += v.y; gx[g][2] += v.z; gx[g][3] += v.w;
+          } else {
+            const float2 v = *reinterpret_cast<const float2*>(rp + rb_chunk<HS>(pb, g) * 4 + (tid & 1) * 2);
+            gx[g][0] += v.x; gx[g][1] += v.y;
+          }
         }
-        const float ig = sigmoid_tc(z[0]);
-        const float gg = tanhf(z[1]);
-        const float fg = sigmoid_tc(z[2] + 1.0f);
-        const float og = sigmoid_tc(z[3]);
-        const float cn = ccarry[k] * fg + ig * gg;
-        av[k][0] = ig; av[k][1] = gg; av[k][2] = fg; av[k][3] = og; av[k][4] = cn;
-        if (valid[k]) {
-          hn[k] = tanhf(cn) * og;
-          ccarry[k] = cn;                              // valid steps are s = 0 .. len-1, so the carry is c_{s-1}
+    }
+    // My receive buffer is free for step s+1 as soon as these loads have returned: a relaxed arrive (nothing to
+    // publish; the release form would wait for the h stores below and sat on the critical path for 0.6 us).
+    if (s + 1 < p.T) cluster_arrive_relaxed();
+    if (prow) {
+#pragma unroll
+      for (int u = 0; u < UPT; ++u) {
+        const float ig = sigmoid_tc(gx[0][u]);
+        const float gg = tanh_tc(gx[1][u]);
+        const float fg = sigmoid_tc(gx[2][u] + 1.0f);
+        const float og = sigmoid_tc(gx[3][u]);
+        const float cn = ccarry[u] * fg + ig * gg;
+        av[0][u] = ig; av[1][u] = gg; av[2][u] = fg; av[3][u] = og; av[4][u] = cn;
+        if (valid) {
+          hn[u] = tanh_tc(cn) * og;
+          ccarry[u] = cn;                              // valid steps are s = 0 .. len-1, so the carry is c_{s-1}
         }
-        // h_t, split, in the consumer's UMMA layout (rows b >= B stay zero from the host memset)
-        const int j = j0 + jl;
-        __half hi, lo;
-        split_h(hn[k], &hi, &lo);
-        uint8_t* t = hnext + (size_t)((j / KS) * KB + (j % KS) / 64) * 2 * A_TILE + sw128_h(b, j % 64);
-        __stcg(reinterpret_cast<unsigned short*>(t), __half_as_ushort(hi));
-        __stcg(reinterpret_cast<unsigned short*>(t + A_TILE), __half_as_ushort(lo));
       }
     }
-    CL_STAMP(s, 6);
-    // Publish: the CTA barrier orders every thread's stores before thread 0's red.release.gpu, which is cumulative,
-    // and the consumer fences the async proxy after its acquire -- per-thread fences here are redundant (measured
-    // 0.9 us per step).  NABU_REC_FENCES=1 brings them back for debugging.
-    if (p.fences) {
-      fence_proxy_async_all();
-      __threadfence();
+    {
+      // h_t, split, flagged, in the consumer's UMMA layout.  All 128 rows are written (rows b >= B as zeros): the
+      // consumers wait for every half of their slice to carry this step's flag.
+      const unsigned short fb = (unsigned short)ll_flag(s);
+      unsigned short hh[UPT], hl[UPT];
+#pragma unroll
+      for (int u = 0; u < UPT; ++u) split_h_flag(hn[u], fb, &hh[u], &hl[u]);
+      const int j = j0 + pu;
+      uint8_t* t = hnext + (size_t)((j / KS) * KB + (j % KS) / 64) * 2 * A_TILE + sw128_h(pb, j % 64);
+      if constexpr (UPT == 4) {
+        __stcg(reinterpret_cast<uint2*>(t), make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16)));
+        __stcg(reinterpret_cast<uint2*>(t + A_TILE), make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16)));
+      } else {
+        __stcg(reinterpret_cast<unsigned*>(t), (uint32_t)hh[0] | ((uint32_t)hh[1] << 16));
+        __stcg(reinterpret_cast<unsigned*>(t + A_TILE), (uint32_t)hl[0] | ((uint32_t)hl[1] << 16));
+      }
     }
-    CL_STAMP(s, 7);
-    if (s + 1 < p.T) cluster_arrive();                 // my receive buffer is free for step s+1
-    __syncthreads();
-    CL_STAMP(s, 8);
-    if (tid == 0) red_release_gpu_add(cnt + q, 1u);
-    CL_STAMP(s, 9);
+    CL_STAMP(s, 6); CL_STAMP(s, 7); CL_STAMP(s, 8); CL_STAMP(s, 9);
     // ---- off the critical path: what the backward pass and the next layer need --------------------------
+    if (prow) {
+      if (valid) {
+        float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
+        float* cp = cells + ((size_t)pb * p.T + tt) * H + j0 + pu;
+        if constexpr (UPT == 4) {
 #pragma unroll
-    for (int k = 0; k < PP; ++k) {
-      const int pr = tid + k * CL_THREADS;
-      const int jl = pr % HS, b = pr / HS;
-      if (b < p.B) {
-        const int t = tb[k];
-        if (valid[k]) {
-          float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
-          __stcg(gp, av[k][0]); __stcg(gp + H, av[k][1]); __stcg(gp + 2 * H, av[k][2]); __stcg(gp + 3 * H, av[k][3]);
-          __stcg(cells + ((size_t)b * p.T + t) * H + j0 + jl, av[k][4]);
+          for (int g = 0; g < 4; ++g) __stcg(reinterpret_cast<float4*>(gp + g * H), make_float4(av[g][0], av[g][1], av[g][2], av[g][3]));
+          __stcg(reinterpret_cast<float4*>(cp), make_float4(av[4][0], av[4][1], av[4][2], av[4][3]));
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) __stcg(reinterpret_cast<float2*>(gp + g * H), make_float2(av[g][0], av[g][1]));
+          __stcg(reinterpret_cast<float2*>(cp), make_float2(av[4][0], av[4][1]));
         }
-        __stcg(p.y + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl, hn[k]);
       }
+      float* yp = p.y + ((size_t)pb * p.yT + tt) * 2 * H + dir * H + j0 + pu;
+      if constexpr (UPT == 4) __stcg(reinterpret_cast<float4*>(yp), make_float4(hn[0], hn[1], hn[2], hn[3]));
+      else __stcg(reinterpret_cast<float2*>(yp), make_float2(hn[0], hn[1]));
     }
   }
   tc_fence_before();
@@ -401,8 +457,6 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
   constexpr int NST = HS == 8 ? 4 : 3;     // ring stages (all the shared memory that is left)
   constexpr int B_TILE = NC * 128;         // bytes of one [NC rows x 64 fp16] tile
   constexpr int TCOLS = 2 * NC < 32 ? 32 : 2 * NC;
-  constexpr int PAIRS = BT * HS;
-  constexpr int PP = PAIRS / CL_THREADS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Bs = sm;                                    // [KBN][hi|lo][B_TILE]
@@ -470,17 +524,19 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
 
   const uint32_t idesc = make_idesc_f16(128, NC);
   const uint32_t ring_u = smem_u32(ring), Bs_u = smem_u32(Bs);
-  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  unsigned gq = 0;                                     // K blocks consumed so far (ring position)
-  // a thread owns the same (batch row, unit) pairs at every step: the carried dc and the length stay in registers
-  float dcc[PP];
-  int lenr[PP];
+  constexpr int UPT = HS / 2;                          // a thread owns batch row pb and UPT consecutive units
+  const int pb = tid >> 1, pu = (tid & 1) * UPT;
+  const bool prow = pb < p.B;
+  const int plen = prow ? p.len[pb] : 0;
+  float dbacc[4][UPT], dcc[UPT];
 #pragma unroll
-  for (int k = 0; k < PP; ++k) {
-    const int b = (tid + k * CL_THREADS) / HS;
-    dcc[k] = 0.f;
-    lenr[k] = b < p.B ? p.len[b] : 0;
+  for (int u = 0; u < UPT; ++u) {
+    dcc[u] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) dbacc[g][u] = 0.f;
   }
+  unsigned gq = 0;                                     // K blocks consumed so far (ring position)
+  const float pS = scale[pb];
 
   int iter = 0;
   for (int s = p.T - 1; s >= 0; --s, ++iter) {
@@ -489,28 +545,48 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
     float* rb = rbuf + (size_t)(iter & 1) * CLS * BT * HS;
     CL_STAMP(iter, 0);
     // ---- prefetch pointwise operands -----------------------------------------------------------
-    float gt[PP][4], ct[PP], cprev[PP], dyv[PP];
-    int tb[PP];
-    bool valid[PP];
+    float gt[4][UPT], ct[UPT], cprev[UPT], dyv[UPT];
+    const bool valid = s < plen;
+    const int tt = valid ? (dir ? plen - 1 - s : s) : s;
 #pragma unroll
-    for (int k = 0; k < PP; ++k) {
-      const int pr = tid + k * CL_THREADS;
-      const int jl = pr % HS, b = pr / HS;
-      valid[k] = false; tb[k] = 0; ct[k] = cprev[k] = dyv[k] = 0.f;
-      gt[k][0] = gt[k][1] = gt[k][2] = gt[k][3] = 0.f;
-      if (b < p.B) {
-        const int L = lenr[k];
-        valid[k] = s < L;
-        const int t = valid[k] ? (dir ? L - 1 - s : s) : s;
-        tb[k] = t;
-        if (valid[k]) {
-          const float* gp = gates + ((size_t)b * p.T + t) * H4 + j0 + jl;
+    for (int u = 0; u < UPT; ++u) {
+      ct[u] = cprev[u] = dyv[u] = 0.f;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) gt[k][g] = __ldcg(gp + g * H);
-          ct[k] = __ldcg(cells + ((size_t)b * p.T + t) * H + j0 + jl);
-          if (s > 0) cprev[k] = __ldcg(cells + ((size_t)b * p.T + (dir ? t + 1 : t - 1)) * H + j0 + jl);
-          dyv[k] = __ldcg(p.dy + ((size_t)b * p.yT + t) * 2 * H + dir * H + j0 + jl);
+      for (int g = 0; g < 4; ++g) gt[g][u] = 0.f;
+    }
+    if (valid) {
+      const float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
+      const float* cp = cells + ((size_t)pb * p.T + tt) * H + j0 + pu;
+      const float* cq = cells + ((size_t)pb * p.T + (dir ? tt + 1 : tt - 1)) * H + j0 + pu;
+      const float* yp = p.dy + ((size_t)pb * p.yT + tt) * 2 * H + dir * H + j0 + pu;
+      if constexpr (UPT == 4) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + g * H));
+          gt[g][0] = v.x; gt[g][1] = v.y; gt[g][2] = v.z; gt[g][3] = v.w;
         }
+        float4 v = __ldcg(reinterpret_cast<const float4*>(cp));
+        ct[0] = v.x; ct[1] = v.y; ct[2] = v.z; ct[3] = v.w;
+        if (s > 0) {
+          v = __ldcg(reinterpret_cast<const float4*>(cq));
+          cprev[0] = v.x; cprev[1] = v.y; cprev[2] = v.z; cprev[3] = v.w;
+        }
+        v = __ldcg(reinterpret_cast<const float4*>(yp));
+        dyv[0] = v.x; dyv[1] = v.y; dyv[2] = v.z; dyv[3] = v.w;
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(gp + g * H));
+          gt[g][0] = v.x; gt[g][1] = v.y;
+        }
+        float2 v = __ldcg(reinterpret_cast<const float2*>(cp));
+        ct[0] = v.x; ct[1] = v.y;
+        if (s > 0) {
+          v = __ldcg(reinterpret_cast<const float2*>(cq));
+          cprev[0] = v.x; cprev[1] = v.y;
+        }
+        v = __ldcg(reinterpret_cast<const float2*>(yp));
+        dyv[0] = v.x; dyv[1] = v.y;
       }
     }
 
@@ -525,7 +601,6 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
         for (int kb = 0; kb < KBN; ++kb) {
           if (kb % KBC == 0) {
             while (ld_acquire_gpu(cnt + r * CPS + kb / KBC) < target) { }
-            __threadfence();
             fence_proxy_async_all();
           }
           const unsigned pos = g0 + kb, st = pos % NST;
@@ -599,46 +674,64 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
       CL_STAMP(iter, 5);
     }
 
-    // ---- pointwise gate gradients for my HS units.  Only the exchanged dz is on the critical path of the next
-    // time step; the fp32 dz the GEMMs read (gates[]) goes to memory after the release. -------------------------------
-    float dzv[PP][4];
+    // ---- pointwise gate gradients for my units.  Only the exchanged dz is on the critical path of the next time
+    // step; the fp32 dz the GEMMs read (gates[]) goes to memory after the release. ---------------------------------
+    float dzv[4][UPT];
 #pragma unroll
-    for (int k = 0; k < PP; ++k) {
-      const int pr = tid + k * CL_THREADS;
-      const int jl = pr % HS, b = pr / HS;
-      dzv[k][0] = dzv[k][1] = dzv[k][2] = dzv[k][3] = 0.f;
-      if (b < p.B) {
-        float dh = dyv[k];
-        if (iter > 0) {
-          const int pos = HS == 8 ? ((jl >> 2) ^ ((b >> 2) & 1)) : 0;
+    for (int u = 0; u < UPT; ++u) dzv[0][u] = dzv[1][u] = dzv[2][u] = dzv[3][u] = 0.f;
+    if (prow) {
+      float dh[UPT];
 #pragma unroll
-          for (int src = 0; src < CLS; ++src) dh += rb[((size_t)src * BT + b) * HS + pos * 4 + (jl & 3)];
+      for (int u = 0; u < UPT; ++u) dh[u] = dyv[u];
+      if (iter > 0) {
+#pragma unroll
+        for (int src = 0; src < CLS; ++src) {
+          const float* rp = rb + ((size_t)src * BT + pb) * HS;
+          if constexpr (UPT == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(rp + ((tid & 1) ^ ((pb >> 2) & 1)) * 4);
+            dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
+          } else {
+            const float2 v = *reinterpret_cast<const float2*>(rp + (tid & 1) * 2);
+            dh[0] += v.x; dh[1] += v.y;
+          }
         }
+      }
+#pragma unroll
+      for (int u = 0; u < UPT; ++u) {
         float dcn = 0.f;
-        if (valid[k]) {
-          const float ig = gt[k][0], gg = gt[k][1], fg = gt[k][2], og = gt[k][3];
-          const float tc_ = tanhf(ct[k]);
-          const float d_o = dh * tc_;
-          const float dc = dcc[k] + dh * og * (1.f - tc_ * tc_);
-          dzv[k][0] = dc * gg * ig * (1.f - ig);
-          dzv[k][1] = dc * ig * (1.f - gg * gg);
-          dzv[k][2] = dc * cprev[k] * fg * (1.f - fg);
-          dzv[k][3] = d_o * og * (1.f - og);
+        if (valid) {
+          const float ig = gt[0][u], gg = gt[1][u], fg = gt[2][u], og = gt[3][u];
+          const float tc_ = tanh_tc(ct[u]);
+          const float d_o = dh[u] * tc_;
+          const float dc = dcc[u] + dh[u] * og * (1.f - tc_ * tc_);
+          dzv[0][u] = dc * gg * ig * (1.f - ig);
+          dzv[1][u] = dc * ig * (1.f - gg * gg);
+          dzv[2][u] = dc * cprev[u] * fg * (1.f - fg);
+          dzv[3][u] = d_o * og * (1.f - og);
           dcn = dc * fg;
         }
-        dcc[k] = dcn;
-        const float S = scale[b];
-        // my cluster is producer (q % CPS) of K-slice q / CPS; column kl = ((q % CPS)*4 + g)*NC + r*HS + jl
-        uint8_t* xs = dznext + (size_t)(q / CPS) * KBN * 2 * A_TILE;
+        dcc[u] = dcn;
+      }
+      // my cluster is producer (q % CPS) of K-slice q / CPS; column kl = ((q % CPS)*4 + g)*NC + r*HS + pu + u
+      uint8_t* xs = dznext + (size_t)(q / CPS) * KBN * 2 * A_TILE;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int kl = ((q % CPS) * 4 + g) * NC + r * HS + jl;
+      for (int g = 0; g < 4; ++g) {
+        const int kl = ((q % CPS) * 4 + g) * NC + r * HS + pu;
+        unsigned short hh[UPT], hl[UPT];
+#pragma unroll
+        for (int u = 0; u < UPT; ++u) {
           __half hi, lo;
-          split_h_sat(dzv[k][g] * S, &hi, &lo);
-          uint8_t* tptr = xs + (size_t)(kl / 64) * 2 * A_TILE + sw128_h(b, kl % 64);
-          __stcg(reinterpret_cast<unsigned short*>(tptr), __half_as_ushort(hi));
-          __stcg(reinterpret_cast<unsigned short*>(tptr + A_TILE), __half_as_ushort(lo));
-          dbacc[g] += dzv[k][g];
+          split_h_sat(dzv[g][u] * pS, &hi, &lo);
+          hh[u] = __half_as_ushort(hi); hl[u] = __half_as_ushort(lo);
+          dbacc[g][u] += dzv[g][u];
+        }
+        uint8_t* tptr = xs + (size_t)(kl / 64) * 2 * A_TILE + sw128_h(pb, kl % 64);
+        if constexpr (UPT == 4) {
+          __stcg(reinterpret_cast<uint2*>(tptr), make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16)));
+          __stcg(reinterpret_cast<uint2*>(tptr + A_TILE), make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16)));
+        } else {
+          __stcg(reinterpret_cast<unsigned*>(tptr), (uint32_t)hh[0] | ((uint32_t)hh[1] << 16));
+          __stcg(reinterpret_cast<unsigned*>(tptr + A_TILE), (uint32_t)hl[0] | ((uint32_t)hl[1] << 16));
         }
       }
     }
@@ -652,28 +745,28 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
     CL_STAMP(iter, 8);
     if (tid == 0) red_release_gpu_add(cnt + q, 1u);
     CL_STAMP(iter, 9);
+    if (prow) {
+      float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
 #pragma unroll
-    for (int k = 0; k < PP; ++k) {
-      const int pr = tid + k * CL_THREADS;
-      const int jl = pr % HS, b = pr / HS;
-      if (b < p.B) {
-        float* gp = gates + ((size_t)b * p.T + tb[k]) * H4 + j0 + jl;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) __stcg(gp + g * H, dzv[k][g]);
+      for (int g = 0; g < 4; ++g) {
+        if constexpr (UPT == 4) __stcg(reinterpret_cast<float4*>(gp + g * H), make_float4(dzv[g][0], dzv[g][1], dzv[g][2], dzv[g][3]));
+        else __stcg(reinterpret_cast<float2*>(gp + g * H), make_float2(dzv[g][0], dzv[g][1]));
       }
     }
   }
 
-  // bias gradient: every thread's pairs share jl = tid % HS; fixed-order sum over threads
+  // bias gradient: thread (row, half) holds the sums of its row for units half*UPT + u; fixed-order sum over rows
   {
     __syncthreads();
 #pragma unroll
-    for (int g = 0; g < 4; ++g) red[tid * 4 + g] = dbacc[g];
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int u = 0; u < UPT; ++u) red[(tid * 4 + g) * UPT + u] = dbacc[g][u];
     __syncthreads();
     if (tid < 4 * HS) {
       const int g = tid / HS, j = tid % HS;
       float sum = 0.f;
-      for (int i = j; i < CL_THREADS; i += HS) sum += red[i * 4 + g];
+      for (int i = j / UPT; i < CL_THREADS; i += 2) sum += red[(i * 4 + g) * UPT + (j % UPT)];
       p.dbpart[((size_t)dir * 8) * H4 + g * H + j0 + j] = sum;
     }
   }
