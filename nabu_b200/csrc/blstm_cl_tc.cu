@@ -53,6 +53,13 @@ __device__ __forceinline__ void split_h(float x, __half* hi, __half* lo) {
   *hi = h;
   *lo = __float2half_rn((x - __half2float(h)) * 2048.f);
 }
+// One lane of a converged warp (cute::elect_one_sync): the MMA-issuing warp stays converged so that descriptors live in
+// uniform registers and each tcgen05.mma is a predicated instruction, not a per-thread loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
@@ -115,6 +122,7 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
 
   const int H = p.H, H4 = 4 * p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform
   const int per_dir = H / HS;
   const int dir = blockIdx.x / per_dir;
   const int q = (blockIdx.x % per_dir) / CLS;
@@ -219,7 +227,7 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
         fence_proxy_async_smem();
         __syncthreads();
       }
-      if (tid == 0) {
+      if (warp_u == 0) {                               // converged warp; one elected lane issues
         CL_STAMP(s, 2);
         tc_fence_after();
 #pragma unroll
@@ -231,14 +239,15 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
             const uint64_t bh = make_desc(Bs_u + (kb * 2 + 0) * B_TILE + ks * 32, 16, 1024, 2);
             const uint64_t bl = make_desc(Bs_u + (kb * 2 + 1) * B_TILE + ks * 32, 16, 1024, 2);
             const uint32_t acc = (kb | ks) != 0;
-            umma_f16(tm, ah, bh, idesc, acc);
-            umma_f16(tm + GC, ah, bl, idesc, acc);
-            umma_f16(tm + GC, al, bh, idesc, 1u);
+            if (elect_one()) {
+              umma_f16(tm, ah, bh, idesc, acc);
+              umma_f16(tm + GC, ah, bl, idesc, acc);
+              umma_f16(tm + GC, al, bh, idesc, 1u);
+            }
           }
         }
-        umma_commit(smem_u32(&mma_bar));
+        if (elect_one()) umma_commit(smem_u32(&mma_bar));
       }
-      __syncwarp();
       mbar_wait(smem_u32(&mma_bar), par);
       tc_fence_after();
       CL_STAMP(s, 3);
@@ -456,7 +465,7 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
   constexpr int KBC = KBN / CPS;           // K blocks per producer cluster
   constexpr int NST = HS == 8 ? 4 : 3;     // ring stages (all the shared memory that is left)
   constexpr int B_TILE = NC * 128;         // bytes of one [NC rows x 64 fp16] tile
-  constexpr int TCOLS = 2 * NC < 32 ? 32 : 2 * NC;
+  constexpr int TCOLS = 4 * NC < 32 ? 32 : 4 * NC;   // D1 | D2a | D2b | (unused): independent accumulate chains
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Bs = sm;                                    // [KBN][hi|lo][B_TILE]
@@ -471,6 +480,7 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
 
   const int H = p.H, H4 = 4 * p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform
   const int per_dir = H / HS;
   const int dir = blockIdx.x / per_dir;
   const int q = (blockIdx.x % per_dir) / CLS;
@@ -608,8 +618,8 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
           mbar_expect_tx(smem_u32(&full_bar[st]), 2 * A_TILE);
           cb_bulk(ring + (size_t)st * 2 * A_TILE, slab + (size_t)kb * 2 * A_TILE, 2 * A_TILE, &full_bar[st]);
         }
-      } else if (tid == 0) {
-        // ---- MMA issuer (warp 0) ----------------------------------------------------------------------------
+      } else if (warp_u == 0) {
+        // ---- MMA issuer (warp 0, converged; one elected lane issues) --------------------------------------------
 #pragma unroll 1
         for (int kb = 0; kb < KBN; ++kb) {
           const unsigned pos = g0 + kb, st = pos % NST;
@@ -623,13 +633,15 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
             const uint64_t bh = make_desc(Bs_u + (kb * 2 + 0) * B_TILE + ks * 32, 16, 1024, 2);
             const uint64_t bl = make_desc(Bs_u + (kb * 2 + 1) * B_TILE + ks * 32, 16, 1024, 2);
             const uint32_t acc = (kb | ks) != 0;
-            umma_f16(tm, ah, bh, idesc, acc);
-            umma_f16(tm + NC, ah, bl, idesc, acc);
-            umma_f16(tm + NC, al, bh, idesc, 1u);
+            if (elect_one()) {
+              umma_f16(tm, ah, bh, idesc, acc);
+              umma_f16(tm + NC, ah, bl, idesc, acc);
+              umma_f16(tm + 2 * NC, al, bh, idesc, acc);
+            }
           }
-          umma_commit(smem_u32(&empty_bar[st]));
+          if (elect_one()) umma_commit(smem_u32(&empty_bar[st]));
         }
-        umma_commit(smem_u32(&mma_bar));
+        if (elect_one()) umma_commit(smem_u32(&mma_bar));
       }
       gq = g0 + KBN;
       __syncwarp();
@@ -640,13 +652,15 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
       if (warp < 4) {
         const int row = warp * 32 + lane;
         const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
-        uint32_t v1[NC], v2[NC];
+        uint32_t v1[NC], v2[NC], v3[NC];
         if constexpr (NC == 32) {
           tmem_ld32(taddr, reinterpret_cast<uint32_t(&)[32]>(v1));
           tmem_ld32(taddr + NC, reinterpret_cast<uint32_t(&)[32]>(v2));
+          tmem_ld32(taddr + 2 * NC, reinterpret_cast<uint32_t(&)[32]>(v3));
         } else {
           tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(v1));
           tmem_ld16(taddr + NC, reinterpret_cast<uint32_t(&)[16]>(v2));
+          tmem_ld16(taddr + 2 * NC, reinterpret_cast<uint32_t(&)[16]>(v3));
         }
         tmem_ld_wait();
         const float is = 1.f / scale[row];                // exact: S is a power of two
@@ -660,7 +674,7 @@ blstm_rec_bwd_cluster_tc_kernel(const ClParams p, const unsigned* __restrict__ r
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = d * HS + c4 * 4 + e;
-              z[e] = fmaf(__uint_as_float(v2[c]), 1.f / 2048.f, __uint_as_float(v1[c])) * is;
+              z[e] = fmaf(__uint_as_float(v2[c]) + __uint_as_float(v3[c]), 1.f / 2048.f, __uint_as_float(v1[c])) * is;
             }
             const int pos = HS == 8 ? (c4 ^ ((row >> 2) & 1)) : c4;
             st_cluster_v4(dst + (uint32_t)pos * 16u, z[0], z[1], z[2], z[3]);
