@@ -376,6 +376,14 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
   if (warp == 0) tmem_dealloc(tm, TCOLS);
 }
 
+// NABU_REC_NOCOOP=1 launches without the cooperative attribute (profilers that cannot replay cooperative cluster
+// launches; co-residency then rests on the occupancy check alone, which holds when the GPU is otherwise idle).
+bool coop_attr() {
+  static int on = -1;
+  if (on < 0) on = getenv("NABU_REC_NOCOOP") ? 0 : 1;
+  return on != 0;
+}
+
 template <int HS>
 int launch_fwd_tc(const ClParams& p, cudaStream_t stream, bool* launched) {
   constexpr int CLS = TC_CLS, GC = 16 * HS, KB = (64 * HS / CLS) / 64;
@@ -395,7 +403,7 @@ int launch_fwd_tc(const ClParams& p, cudaStream_t stream, bool* launched) {
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = coop_attr() ? 2 : 1;
   int nclusters = 0;
   const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg);
   if (getenv("NABU_DEBUG"))
@@ -809,7 +817,7 @@ int launch_bwd_tc(const ClParams& p, unsigned* rowmax, cudaStream_t stream, bool
   at[1].id = cudaLaunchAttributeCooperative;
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = coop_attr() ? 2 : 1;
   int nclusters = 0;
   const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg);
   if (getenv("NABU_DEBUG"))
