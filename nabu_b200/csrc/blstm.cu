@@ -768,7 +768,14 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
   int ngrp = 1;
   bool launched = false;
-  if (blstm_bwd_cluster_tc_eligible(B, H)) {
+  if (blstm_bwd_cluster8_eligible(B, H)) {
+    const float* cc[2] = {c[0], c[1]};
+    NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, stream));
+    NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H4 * 128 * sizeof(float), stream));
+    if (int e = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, stream, &launched))
+      return e;
+  }
+  if (!launched && blstm_bwd_cluster_tc_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};
     NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, stream));
     NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H4 * 128 * sizeof(float), stream));

@@ -32,4 +32,12 @@ int blstm_rec_bwd_cluster_tc(const float* const kernel[2], float* const gates[2]
                              unsigned* rowmax, const int* len, int B, int T, int yT, int D, int H, cudaStream_t stream,
                              bool* launched);
 
+// tcgen05 backward on clusters of 8 with the recurrent weights resident in TMEM (blstm_cl_bwd8.cu): B <= 128,
+// num_units in {256, 512}; preferred over the cluster-of-4 kernel; NABU_REC_BWD=cl4|ffma|flat disables.  rowmax and the
+// (zeroed) exchange buffer as for blstm_rec_bwd_cluster_tc.
+bool blstm_bwd_cluster8_eligible(int B, int H);
+int blstm_rec_bwd_cluster8(const float* const kernel[2], float* const gates[2], const float* const cells[2],
+                           const float* dy, float* dbpart, float* xchg, unsigned* rowmax, const int* len, int B, int T, int yT,
+                           int D, int H, cudaStream_t stream, bool* launched);
+
 }  // namespace nabu
