@@ -58,7 +58,6 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
   constexpr int SLICE = KBN * 2 * A_TILE;             // bytes of the UMMA image of a dz slice (hi | lo per K block)
   constexpr int ACOLS = KBN * 32;                     // TMEM columns of one half of the weights
   constexpr uint32_t TM_D1 = 0, TM_D2 = 128, TM_AH = 256, TM_AL = 256 + ACOLS;
-  constexpr int NBATCH = KBN / 2;                     // fetches of 2 K blocks = 16 chunks of 16 bytes per thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Bs = sm;                                   // dz slice [KBN][hi|lo][A_TILE]; after the MMAs: staging of 7 blocks
@@ -67,7 +66,6 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float scale[BT];
-  __shared__ __align__(16) float invscale[BT];
 
   const int H = p.H, H4 = 4 * p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,7 +90,6 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
       S = ldexpf(1.f, 6 - e);                          // G * S in [32, 64)
     }
     scale[tid] = S;
-    invscale[tid] = 1.f / S;                           // exact: S is a power of two
   }
   if (tid == 0) {
     mbar_init(smem_u32(&rx_bar), 1);
@@ -142,12 +139,13 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
   // transaction count, not bytes, bounded the first version of this kernel: one 16-byte access per lane and line).
   const int ug = (tid & 3) * 4, rw = tid >> 2;
   int plen[2];
-  float pS[2];
+  float pS[2], pSi[2];
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int b = rw + 64 * rr;
     plen[rr] = b < p.B ? p.len[b] : 0;
     pS[rr] = scale[b];
+    pSi[rr] = 1.f / pS[rr];
   }
   float dbacc[4][4], dcc[2][4];
 #pragma unroll
@@ -192,49 +190,48 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
       if (tid == 0) mbar_expect_tx(smem_u32(&rx_bar), (CLS - 1) * B8_BLK);
       // ---- fetch my dz slice (self-validating data, see "LL" in cl_tc_common.cuh) and multiply as it arrives ---------
       const uint32_t fl = ll_flag(iter - 1) ? 0x00010001u : 0u;
-#pragma unroll 1
-      for (int bt = 0; bt < NBATCH; ++bt) {
-        const uint4* src = reinterpret_cast<const uint4*>(dzprev + (size_t)r * SLICE + (size_t)bt * 4 * A_TILE) + tid;
-        uint4 v[16];
-        if (bt == 0) {
-          do { v[0] = ld_relaxed_v4(src); } while (!ll_ok(v[0], fl));
-          CL_STAMP(iter, 1);
-        } else {
-          v[0] = ld_relaxed_v4(src);
+      // One K block (hi and lo tile, 8 chunks of 16 bytes per thread) at a time, the next block's loads in flight while
+      // this one is validated, stored and multiplied.
+      uint4 v[2][8];
+      const uint4* src = reinterpret_cast<const uint4*>(dzprev + (size_t)r * SLICE) + tid;
+      do { v[0][0] = ld_relaxed_v4(src); } while (!ll_ok(v[0][0], fl));
+      CL_STAMP(iter, 1);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) v[0][i] = ld_relaxed_v4(src + i * CL_THREADS);
+#pragma unroll
+      for (int kb = 0; kb < KBN; ++kb) {
+        const uint4* cur = src + (size_t)kb * (2 * A_TILE / 16);
+        if (kb + 1 < KBN) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[(kb + 1) & 1][i] = ld_relaxed_v4(cur + (2 * A_TILE / 16) + i * CL_THREADS);
         }
 #pragma unroll
-        for (int i = 1; i < 16; ++i) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          while (!ll_ok(v[i], fl)) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
+        for (int i = 0; i < 8; ++i)
+          while (!ll_ok(v[kb & 1][i], fl)) v[kb & 1][i] = ld_relaxed_v4(cur + i * CL_THREADS);
         // peers have read their receive buffers of the previous step, hence received my blocks: Bs and theirs are free
-        if (bt == 0) cluster_wait();
-        uint4* dst = reinterpret_cast<uint4*>(Bs + (size_t)bt * 4 * A_TILE) + tid;
+        if (kb == 0) cluster_wait();
+        uint4* dst = reinterpret_cast<uint4*>(Bs + (size_t)kb * 2 * A_TILE) + tid;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dst[i * CL_THREADS] = v[i];
+        for (int i = 0; i < 8; ++i) dst[i * CL_THREADS] = v[kb & 1][i];
         fence_proxy_async_smem();
         __syncthreads();
         if (warp_u == 0) {                             // converged warp; one elected lane issues
-          if (bt == 0) CL_STAMP(iter, 2);
+          if (kb == 0) CL_STAMP(iter, 2);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int kb = 2 * bt + kk;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t bh = make_desc(Bs_u + (kb * 2 + 0) * A_TILE + ks * 32, 16, 1024, 2);
-              const uint64_t bl = make_desc(Bs_u + (kb * 2 + 1) * A_TILE + ks * 32, 16, 1024, 2);
-              const uint32_t ah = tm + TM_AH + (uint32_t)(kb * 4 + ks) * 8;
-              const uint32_t al = tm + TM_AL + (uint32_t)(kb * 4 + ks) * 8;
-              const uint32_t acc = (kb | ks) != 0;
-              if (elect_one()) {
-                umma_f16_ts(tm + TM_D1, ah, bh, idesc, acc);
-                umma_f16_ts(tm + TM_D2, ah, bl, idesc, acc);
-                umma_f16_ts(tm + TM_D2, al, bh, idesc, 1u);
-              }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bh = make_desc(Bs_u + (kb * 2 + 0) * A_TILE + ks * 32, 16, 1024, 2);
+            const uint64_t bl = make_desc(Bs_u + (kb * 2 + 1) * A_TILE + ks * 32, 16, 1024, 2);
+            const uint32_t ah = tm + TM_AH + (uint32_t)(kb * 4 + ks) * 8;
+            const uint32_t al = tm + TM_AL + (uint32_t)(kb * 4 + ks) * 8;
+            const uint32_t acc = (kb | ks) != 0;
+            if (elect_one()) {
+              umma_f16_ts(tm + TM_D1, ah, bh, idesc, acc);
+              umma_f16_ts(tm + TM_D2, ah, bl, idesc, acc);
+              umma_f16_ts(tm + TM_D2, al, bh, idesc, 1u);
             }
           }
-          if (bt == NBATCH - 1 && elect_one()) umma_commit(smem_u32(&mma_bar));
+          if (kb == KBN - 1 && elect_one()) umma_commit(smem_u32(&mma_bar));
         }
         __syncwarp();
       }
@@ -259,7 +256,7 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            dstcol[(c0 + i) * 16] = fmaf(__uint_as_float(v2[i]), 1.f / 2048.f, __uint_as_float(v1[i])) * invscale[c0 + i];
+            dstcol[(c0 + i) * 16] = fmaf(__uint_as_float(v2[i]), 1.f / 2048.f, __uint_as_float(v1[i]));
         }
       }
       tc_fence_before();
@@ -278,7 +275,7 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) dh[rr][u] = dyv[rr][u];
+      for (int u = 0; u < 4; ++u) dh[rr][u] = 0.f;
     if (iter > 0) {
 #pragma unroll
       for (int src = 0; src < CLS; ++src)
@@ -288,6 +285,11 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
           dh[rr][0] += v.x; dh[rr][1] += v.y; dh[rr][2] += v.z; dh[rr][3] += v.w;
         }
     }
+    // the exchanged gradients carry the row's power-of-two scale: divide it out (exact) and add this layer's dy
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dh[rr][u] = fmaf(dh[rr][u], pSi[rr], dyv[rr][u]);
     // my receive buffer is free for the next step once these loads have returned (nothing to publish: relaxed)
     if (s > 0) cluster_arrive_relaxed();
     float dzv[2][4][4];
