@@ -32,6 +32,16 @@ unsigned long long nabu_kernel_launches(void);
 int nabu_profile_enable(int on);
 int nabu_profile_collect(char* json_out, size_t cap);
 
+/* Deferred weight gradients (off by default).  With nabu_set_overlap(1), nabu_blstm_bwd returns once the recurrence
+ * and dx are enqueued on `stream`; the weight gradients (dkernel_*) of that call are computed on a library-owned side
+ * stream, in library-owned scratch, concurrently with whatever the caller enqueues next (the next layer's backward
+ * recurrence leaves more than half of the SMs idle).  The caller must then (1) keep x, y and gates of that call alive
+ * and unmodified and (2) not read dkernel_* until nabu_side_join(stream) has made `stream` wait for the deferred work.
+ * nabu_blstm_fwd and nabu_clip_adam_step join implicitly.  (The reference has no counterpart: TF's executor schedules
+ * independent gradient ops of `tf.gradients` concurrently on its own, trainers/trainer.py:556-558.) */
+int nabu_set_overlap(int on);
+int nabu_side_join(void* stream);
+
 /* ---- dense contraction (building block; exported for tests) ------------------------------------
  * mode 0: C[M,N] = alpha*A[M,K].B[K,N]   + beta*C + bias[N]
  * mode 1: C[M,N] = alpha*A[M,K].B[N,K]^T + beta*C + bias[N]

@@ -41,6 +41,43 @@ int max_smem_optin() {
 }
 
 
+// ---- deferred weight gradients ---------------------------------------------------------------------
+Overlap& overlap() {
+  static Overlap o = {};
+  return o;
+}
+int overlap_init() {
+  Overlap& o = overlap();
+  if (o.hp) return 0;
+  int lo = 0, hi = 0;
+  NABU_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  NABU_CHECK_CUDA(cudaStreamCreateWithPriority(&o.hp, cudaStreamNonBlocking, hi));
+  NABU_CHECK_CUDA(cudaStreamCreateWithPriority(&o.side, cudaStreamNonBlocking, lo));
+  NABU_CHECK_CUDA(cudaEventCreateWithFlags(&o.ev_pre, cudaEventDisableTiming));
+  NABU_CHECK_CUDA(cudaEventCreateWithFlags(&o.ev_rec, cudaEventDisableTiming));
+  NABU_CHECK_CUDA(cudaEventCreateWithFlags(&o.ev_done, cudaEventDisableTiming));
+  return 0;
+}
+int overlap_workspace(size_t bytes) {
+  Overlap& o = overlap();
+  if (bytes <= o.ws_bytes) return 0;
+  if (o.ws) {
+    NABU_CHECK_CUDA(cudaStreamSynchronize(o.side));
+    NABU_CHECK_CUDA(cudaFree(o.ws));
+    o.ws = nullptr; o.ws_bytes = 0;
+  }
+  NABU_CHECK_CUDA(cudaMalloc(&o.ws, bytes));
+  o.ws_bytes = bytes;
+  return 0;
+}
+int overlap_join(cudaStream_t stream) {
+  Overlap& o = overlap();
+  if (!o.pending) return 0;
+  NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, o.ev_done, 0));
+  o.pending = false;
+  return 0;
+}
+
 // ---- launch counter + optional per-kernel event timing ----------------------------------------
 namespace {
 struct ProfRec { const char* name; cudaEvent_t a, b; };

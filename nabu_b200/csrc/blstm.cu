@@ -656,6 +656,25 @@ Ws carve(void* base, int H, int B, int T, int D) {
   return w;
 }
 
+// scratch of the deferred weight gradients (library-owned, see Overlap): gemm scratch, scales, planes P1..P3
+Ws carve_side(void* base, int H, int B, int T, int D) {
+  Ws w = {};
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) { void* p = b + off; off += align_up(bytes, 256); return p; };
+  w.gemm_bytes = sgemm_workspace_bytes();
+  w.gemm = (float*)take(w.gemm_bytes);
+  w.glob = (float*)take(256);
+  const size_t D8 = align_up(D, 8), H4 = (size_t)4 * H;
+  const size_t e1 = std::max((size_t)B * T * D8, (size_t)B * (T + YT_SLACK) * 2 * H);
+  const size_t e2 = (size_t)B * T * H4;
+  w.p1h = take(e1 * 2); w.p1l = take(e1 * 2);
+  w.p2h = take(e2 * 2); w.p2l = take(e2 * 2);
+  w.p3h = take(e2 * 2); w.p3l = take(e2 * 2);
+  w.total = off;
+  return w;
+}
+
 // fp16-split tensor-core GEMMs (gemm_h2.cu) for the layer-sized contractions; NABU_GEMM=tf32|simt keeps gemm().
 bool use_h2(int B, int T, int D, int H, int yT) {
   static int enabled = -1;
@@ -686,6 +705,7 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_fwd: bad shape B=%d T=%d D=%d H=%d yT=%d", B, T, D, H, yT);
   Ws w = carve(workspace, H, B, T, D);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  if (int e = overlap_join(stream)) return e;          // deferred weight gradients of the previous step read the parameters' neighbours
   const int H4 = 4 * H;
   const float* kern[2] = {kernel_fw, kernel_bw};
   const float* bias[2] = {bias_fw, bias_bw};
@@ -768,12 +788,27 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
   int ngrp = 1;
   bool launched = false;
+  // Deferred weight gradients (nabu_set_overlap): the cluster-of-8 recurrence leaves 84 of the 148 SMs idle, so the
+  // weight-gradient GEMMs of THIS layer run on a side stream while the caller goes on to the next layer's recurrence,
+  // which is issued on a high-priority stream so that its clusters take SMs as the GEMM's CTAs retire.
+  Overlap& ov = overlap();
+  const bool defer = ov.on && blstm_bwd_cluster8_eligible(B, H) && use_h2(B, T, D, H, yT);
   if (blstm_bwd_cluster8_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};
     NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, stream));
     NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H4 * 128 * sizeof(float), stream));
-    if (int e = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, stream, &launched))
+    cudaStream_t rs = stream;
+    if (defer) {
+      NABU_CHECK_CUDA(cudaEventRecord(ov.ev_pre, stream));
+      NABU_CHECK_CUDA(cudaStreamWaitEvent(ov.hp, ov.ev_pre, 0));
+      rs = ov.hp;
+    }
+    if (int e = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched))
       return e;
+    if (defer) {
+      NABU_CHECK_CUDA(cudaEventRecord(ov.ev_rec, ov.hp));
+      NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, ov.ev_rec, 0));
+    }
   }
   if (!launched && blstm_bwd_cluster_tc_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};
@@ -801,34 +836,52 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
     // One split per operand and use: x, y and dZ with a global scale for the contractions over the B*T rows (dKx, dKh),
     // dZ again with per-row scales and the weights with a global scale for dX.
     const int D8 = (int)align_up(D, 8);
-    unsigned* mx = (unsigned*)(w.glob + 8);
     void* zh[2] = {w.p2h, w.p3h};
     void* zl[2] = {w.p2l, w.p3l};
-    if (int e = split_global(x, D, B * T, D, w.p1h, w.p1l, D8, mx + 0, w.glob + 0, stream)) return e;
-    H2Operand xa = {w.p1h, w.p1l, D8, nullptr, w.glob + 0};
-    for (int d = 0; d < 2; ++d) {
-      if (int e = split_global(g[d], H4, B * T, H4, zh[d], zl[d], H4, mx + 1 + d, w.glob + 1 + d, stream)) return e;
-      H2Operand zb = {zh[d], zl[d], H4, nullptr, w.glob + 1 + d};
-      if (int e = gemm_h2(GEMM_TN, D, H4, B * T, 1.f, xa, zb, 0.f, dkern[d], H4, nullptr, nullptr, w.gemm, w.gemm_bytes, stream))
-        return e;
-    }
-    if (T > 1) {
-      if (int e = split_global(y, 2 * H, B * yT, 2 * H, w.p1h, w.p1l, 2 * H, mx + 3, w.glob + 3, stream)) return e;
-    }
-    for (int d = 0; d < 2; ++d) {
-      float* dKh = dkern[d] + (size_t)D * H4;
-      if (T > 1) {
-        GemmSeg seg;
-        seg.seg = T - 1; seg.segA = yT; seg.segB = T;
-        seg.offA = d == 0 ? 0 : 1; seg.offB = d == 0 ? 1 : 0;
-        H2Operand ya = {(const __half*)w.p1h + d * H, (const __half*)w.p1l + d * H, 2 * H, nullptr, w.glob + 3};
-        H2Operand zb = {zh[d], zl[d], H4, nullptr, w.glob + 1 + d};
-        if (int e = gemm_h2(GEMM_TN, H, H4, B * (T - 1), 1.f, ya, zb, 0.f, dKh, H4, nullptr, &seg, w.gemm, w.gemm_bytes, stream))
+    // weight gradients: on `ws` with the planes of `pw` (the caller's workspace, or the library's side scratch)
+    auto weight_grads = [&](cudaStream_t ws, const Ws& pw) -> int {
+      unsigned* mx = (unsigned*)(pw.glob + 8);
+      void* qh[2] = {pw.p2h, pw.p3h};
+      void* ql[2] = {pw.p2l, pw.p3l};
+      if (int e = split_global(x, D, B * T, D, pw.p1h, pw.p1l, D8, mx + 0, pw.glob + 0, ws)) return e;
+      H2Operand xa = {pw.p1h, pw.p1l, D8, nullptr, pw.glob + 0};
+      for (int d = 0; d < 2; ++d) {
+        if (int e = split_global(g[d], H4, B * T, H4, qh[d], ql[d], H4, mx + 1 + d, pw.glob + 1 + d, ws)) return e;
+        H2Operand zb = {qh[d], ql[d], H4, nullptr, pw.glob + 1 + d};
+        if (int e = gemm_h2(GEMM_TN, D, H4, B * T, 1.f, xa, zb, 0.f, dkern[d], H4, nullptr, nullptr, pw.gemm, pw.gemm_bytes, ws))
           return e;
-      } else {
-        NABU_CHECK_CUDA(cudaMemsetAsync(dKh, 0, (size_t)H * H4 * sizeof(float), stream));
       }
+      if (T > 1) {
+        if (int e = split_global(y, 2 * H, B * yT, 2 * H, pw.p1h, pw.p1l, 2 * H, mx + 3, pw.glob + 3, ws)) return e;
+      }
+      for (int d = 0; d < 2; ++d) {
+        float* dKh = dkern[d] + (size_t)D * H4;
+        if (T > 1) {
+          GemmSeg seg;
+          seg.seg = T - 1; seg.segA = yT; seg.segB = T;
+          seg.offA = d == 0 ? 0 : 1; seg.offB = d == 0 ? 1 : 0;
+          H2Operand ya = {(const __half*)pw.p1h + d * H, (const __half*)pw.p1l + d * H, 2 * H, nullptr, pw.glob + 3};
+          H2Operand zb = {qh[d], ql[d], H4, nullptr, pw.glob + 1 + d};
+          if (int e = gemm_h2(GEMM_TN, H, H4, B * (T - 1), 1.f, ya, zb, 0.f, dKh, H4, nullptr, &seg, pw.gemm, pw.gemm_bytes, ws))
+            return e;
+        } else {
+          NABU_CHECK_CUDA(cudaMemsetAsync(dKh, 0, (size_t)H * H4 * sizeof(float), ws));
+        }
+      }
+      return 0;
+    };
+    if (defer && launched) {
+      const Ws side_probe = carve_side(nullptr, H, B, T, D);
+      if (int e = overlap_workspace(side_probe.total)) return e;
+      const Ws sw = carve_side(ov.ws, H, B, T, D);
+      NABU_CHECK_CUDA(cudaStreamWaitEvent(ov.side, ov.ev_rec, 0));
+      if (int e = weight_grads(ov.side, sw)) return e;
+      NABU_CHECK_CUDA(cudaEventRecord(ov.ev_done, ov.side));
+      ov.pending = true;
+    } else {
+      if (int e = weight_grads(stream, w)) return e;
     }
+    unsigned* mx = (unsigned*)(w.glob + 8);
     if (dx) {
       for (int d = 0; d < 2; ++d) {
         if (int e = split_rows(g[d], H4, B * T, H4, zh[d], zl[d], H4, w.row2, stream)) return e;

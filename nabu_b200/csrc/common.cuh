@@ -39,6 +39,21 @@ struct KernelScope {
   int slot_;
 };
 
+// Deferred weight gradients (nabu_set_overlap, blstm.cu): the backward recurrence runs on a high-priority stream, the
+// weight-gradient GEMMs of a layer on a side stream concurrently with the next layer's recurrence.
+struct Overlap {
+  int on;
+  cudaStream_t hp, side;
+  cudaEvent_t ev_pre, ev_rec, ev_done;
+  bool pending;
+  void* ws;
+  size_t ws_bytes;
+};
+Overlap& overlap();
+int overlap_init();                       // creates streams / events on first use
+int overlap_workspace(size_t bytes);      // grow-only device scratch owned by the library (side stream only)
+int overlap_join(cudaStream_t stream);    // stream waits for the deferred work, if any
+
 int num_sms();                 // SM count of the current device (cached)
 int max_smem_optin();          // max dynamic shared memory per block (opt-in)
 

@@ -105,6 +105,12 @@ namespace nabu { unsigned long long kernel_launches(); void profile_enable(bool)
 extern "C" unsigned long long nabu_kernel_launches(void) { return nabu::kernel_launches(); }
 extern "C" int nabu_profile_enable(int on) { nabu::profile_enable(on != 0); return 0; }
 extern "C" int nabu_profile_collect(char* json_out, size_t cap) { return nabu::profile_collect(json_out, cap); }
+extern "C" int nabu_set_overlap(int on) {
+  if (on) if (int e = nabu::overlap_init()) return e;
+  nabu::overlap().on = on ? 1 : 0;
+  return 0;
+}
+extern "C" int nabu_side_join(void* stream) { return nabu::overlap_join((cudaStream_t)stream); }
 
 extern "C" size_t nabu_gemm_workspace_bytes(void) { return sgemm_workspace_bytes(); }
 
@@ -138,6 +144,7 @@ extern "C" int nabu_clip_adam_step(float* theta, const float* grad, float* m, fl
                                    void* stream) {
   NABU_REQUIRE(t >= 1, "clip_adam: step t=%d must be >= 1", t);
   if (n == 0) return 0;
+  if (int e = nabu::overlap_join((cudaStream_t)stream)) return e;   // deferred weight gradients must have landed
   // lr_t in double like the host-side scalar math of tf.train.AdamOptimizer._prepare
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t));
   const int blocks = 2 * num_sms() * 4;

@@ -180,7 +180,26 @@ class _BLSTM(torch.autograd.Function):
                                    L.ptr(gates), L.ptr(cells), L.ptr(dy), L.ptr(dx), L.ptr(dkf), L.ptr(dbf),
                                    L.ptr(dkb), L.ptr(dbb), L.ptr(ws), ws.numel(), L.stream()),
                 'nabu_blstm_bwd')
+        if _OVERLAP['on']:
+            # deferred weight gradients read these on the library's side stream until side_join()
+            _OVERLAP['keep'].append((x, y, gates))
         return dx, None, None, None, None, None, None, None, None
+
+
+_OVERLAP = {'on': False, 'keep': []}
+
+
+def set_overlap(on):
+    """Deferred weight gradients (include/nabu_b200.h: nabu_set_overlap).  The trainer turns this on; side_join() must
+    run between the backward pass and the first reader of the gradients."""
+    L.check(L.load().nabu_set_overlap(1 if on else 0), 'nabu_set_overlap')
+    _OVERLAP['on'] = bool(on)
+
+
+def side_join():
+    if _OVERLAP['on']:
+        L.check(L.load().nabu_side_join(L.stream()), 'nabu_side_join')
+        _OVERLAP['keep'].clear()
 
 
 def blstm(x, lens, vf_k, vf_b, vb_k, vb_b, H, yT=None):

@@ -37,6 +37,8 @@ SIGNATURES = {
     'nabu_kernel_launches': (ctypes.c_ulonglong, []),
     'nabu_profile_enable': (c_int, [c_int]),
     'nabu_profile_collect': (c_int, [ctypes.c_char_p, c_size_t]),
+    'nabu_set_overlap': (c_int, [c_int]),
+    'nabu_side_join': (c_int, [P]),
     'nabu_gemm_workspace_bytes': (c_size_t, []),
     'nabu_gemm_h2_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'nabu_gemm': (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P, c_int, c_float, P, c_int, P, P,

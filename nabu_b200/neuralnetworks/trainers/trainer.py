@@ -42,6 +42,9 @@ class Trainer(object, metaclass=ABCMeta):
         self.learning_rate_fact = 1.0
         self.num_steps = None      # steps per epoch * num_epochs, set by train()
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        # weight-gradient GEMMs of a BLSTM layer overlap the next layer's backward recurrence (NABU_OVERLAP=0 disables)
+        if self.device.type == 'cuda' and os.environ.get('NABU_OVERLAP', '1') != '0':
+            engine.set_overlap(True)
 
     # ---- learning rate: trainer.py:161-166 ------------------------------------------------------
     def learning_rate(self):
@@ -60,6 +63,7 @@ class Trainer(object, metaclass=ABCMeta):
         if extra is not None:
             loss = loss + extra
         loss.backward()
+        engine.side_join()                               # deferred weight gradients land before the reduction
         parallel.allreduce_sum_(model.store.grad)        # the step's only collective
         lr = self.learning_rate()
         # clip AFTER the reduction so the update equals the reference's at the global batch size
