@@ -375,8 +375,15 @@ def main():
             key = 'rec_fwd_bytes' if 'fwd' in name else 'rec_bwd_bytes'
             per_launch = work[key] / work['rec_launches']
             ach = per_launch / (tot / cnt * 1e-3) / 1e9
+            # DRAM bytes per frame of one launch from the ncu --set full capture (profiles/r1d_ncu_full.md, T=96 launch:
+            # dram__bytes_read.sum + dram__bytes_write.sum over 12 288 frames), scaled to this launch's frames
+            ncu_bytes_per_frame = 37.4e3 if 'fwd' in name else 38.0e3
             roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                        'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src}
+                        'frac': ach / hbm_peak, 'traffic': ncu_bytes_per_frame * w['B'] * w['T'],
+                        'traffic_unit': 'bytes per launch (ncu capture at T=96, scaled by frames)',
+                        'algorithmic_bytes_per_launch': per_launch, 'peak_source': peak_src,
+                        'serial_steps_per_launch': w['T'], 'us_per_serial_step': tot / cnt * 1e3 / w['T'],
+                        'note': 'latency-bound serial scan: T dependent time steps per launch; see DESIGN.md section 6'}
     elif top[0] is not None:
         name, (cnt, tot) = top
         roofline = {'kernel': name, 'bound': 'hbm', 'achieved': None, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': None,
@@ -384,6 +391,8 @@ def main():
     if roofline is not None:
         roofline['avg_launch_ms'] = top[1][1] / max(top[1][0], 1)
         roofline['kernel_time_shares'] = shares
+        roofline['shares_note'] = ('per-kernel CUDA-event time / step time; the weight-gradient GEMMs run on a side '
+                                   'stream under the backward recurrences, so shares can sum to more than 1')
 
     out = dict(base)
     out.update({'value': value, 'ms_per_step': step_ms, 'loss': last, 'clocks': clk, 'gpu_launches': int(launches),
