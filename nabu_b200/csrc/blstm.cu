@@ -803,8 +803,10 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
       NABU_CHECK_CUDA(cudaStreamWaitEvent(ov.hp, ov.ev_pre, 0));
       rs = ov.hp;
     }
-    if (int e = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched))
-      return e;
+    ov.in_defer = defer;
+    const int re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched);
+    ov.in_defer = false;
+    if (re) return re;
     if (defer) {
       NABU_CHECK_CUDA(cudaEventRecord(ov.ev_rec, ov.hp));
       NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, ov.ev_rec, 0));

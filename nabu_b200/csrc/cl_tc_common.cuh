@@ -106,7 +106,7 @@ __global__ void row_absmax_kernel(const float* __restrict__ dy, const int* __res
 bool coop_attr() {
   static int on = -1;
   if (on < 0) on = getenv("NABU_REC_NOCOOP") ? 0 : 1;
-  return on != 0 && !overlap().on;        // deferred weight gradients share the GPU with this launch
+  return on != 0 && !overlap().in_defer;  // deferred weight gradients share the GPU with this launch
 }
 
 }  // namespace

@@ -46,6 +46,7 @@ struct Overlap {
   cudaStream_t hp, side;
   cudaEvent_t ev_pre, ev_rec, ev_done;
   bool pending;
+  bool in_defer;             // set around a launch that shares the GPU with deferred work (no cooperative attribute)
   void* ws;
   size_t ws_bytes;
 };

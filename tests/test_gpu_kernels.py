@@ -97,6 +97,8 @@ def _blstm_case(B, T, D, H, ragged, seed, yT=None, need_dx=True):
     (130, 5, 16, 64, False),     # two batch tiles
     (16, 10, 40, 512, True),     # hs=8 (cfg-3 width)
     (4, 1, 8, 64, False),        # T=1
+    (128, 48, 40, 512, True),    # cfg-3 width and batch: every row of the tcgen05 cluster kernels, flag parity wraps 12 times
+    (77, 33, 24, 256, True),     # H=256 variants (clusters of 4 forward, 2 clusters of 8 per direction backward), odd batch
 ])
 def test_blstm_fwd_bwd(B, T, D, H, ragged):
     _blstm_case(B, T, D, H, ragged, seed=B * 1000 + T)
