@@ -44,6 +44,11 @@ struct H2Operand {
 int split_rows(const float* src, int ld, int R, int C, void* hi, void* lo, int ldo, float* row_inv, cudaStream_t stream);
 int split_global(const float* src, int ld, int R, int C, void* hi, void* lo, int ldo, unsigned* maxbits /*device scratch*/,
                  float* glob_inv, cudaStream_t stream);
+// [s0 | s1] side by side (both [R, C], row pitch ld) as one [R, 2C] operand: one scale per row / one global scale.
+int split_rows_pair(const float* s0, const float* s1, int ld, int R, int C, void* hi, void* lo, float* row_inv,
+                    cudaStream_t stream);
+int split_global_pair(const float* s0, const float* s1, int ld, int R, int C, void* hi, void* lo, unsigned* maxbits,
+                      float* glob_inv, cudaStream_t stream);
 // Same contract as gemm_tc() on pre-split operands.  NN: A rows / B global; NT: A rows, B rows or global; TN: global.
 int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A, const H2Operand& B, float beta, float* C,
             int ldc, const float* bias, const GemmSeg* seg, float* workspace, size_t ws_bytes, cudaStream_t stream);

@@ -358,6 +358,54 @@ split_global_kernel(const float* __restrict__ src, int ld, size_t R, size_t C, c
   }
 }
 
+// Two [R, C] matrices side by side -> one [R, 2C] operand with ONE power-of-two scale per row (the two directions' dZ
+// for the single dX GEMM over K = 8H).  One block per row, C % 8 == 0, 16-byte aligned sources.
+__global__ void __launch_bounds__(256)
+split_rows_pair_kernel(const float* __restrict__ s0, const float* __restrict__ s1, int ld, int C, __half* __restrict__ hi,
+                       __half* __restrict__ lo, float* __restrict__ row_inv) {
+  const size_t row = blockIdx.x;
+  const float* x0 = s0 + row * ld;
+  const float* x1 = s1 + row * ld;
+  __shared__ float wmax[8];
+  float m = 0.f;
+  for (int c = threadIdx.x * 8; c < 2 * C; c += 256 * 8) {
+    float v[8];
+    load8(c < C ? x0 : x1, true, c < C ? c : c - C, C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(v[j]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = wmax[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, wmax[i]);
+  const float S = pow2_scale(m);
+  if (threadIdx.x == 0) row_inv[row] = 1.f / S;
+  for (int c = threadIdx.x * 8; c < 2 * C; c += 256 * 8) {
+    float v[8];
+    load8(c < C ? x0 : x1, true, c < C ? c : c - C, C, v);
+    split8(v, S, hi + row * 2 * C + c, lo + row * 2 * C + c);
+  }
+}
+
+// C columns (C % 8 == 0) of an [R, C] matrix into columns [col0, col0 + C) of planes with row pitch ldo; the scale is
+// read from maxbits (accumulated by absmax_kernel over every matrix that shares it).
+__global__ void __launch_bounds__(256)
+split_global_sub_kernel(const float* __restrict__ src, int ld, int R, int C, const unsigned* __restrict__ maxbits,
+                        __half* __restrict__ hi, __half* __restrict__ lo, size_t ldo, int col0, float* __restrict__ glob_inv) {
+  const float S = pow2_scale(__uint_as_float(*maxbits));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *glob_inv = 1.f / S;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const float* x = src + (size_t)r * ld;
+    for (int c = threadIdx.x * 8; c < C; c += 256 * 8) {
+      float v[8];
+      load8(x, true, c, C, v);
+      split8(v, S, hi + (size_t)r * ldo + col0 + c, lo + (size_t)r * ldo + col0 + c);
+    }
+  }
+}
+
 int make_map_h(CUtensorMap* map, const __half* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                uint64_t stride2, uint32_t box0, uint32_t box1) {
   EncodeTiledFn enc = get_encode();
@@ -381,6 +429,37 @@ int split_rows(const float* src, int ld, int R, int C, void* hi, void* lo, int l
   if (C <= 256) split_rows_kernel<32><<<ceil_div(R, 8), 256, 0, stream>>>(src, ld, R, C, (__half*)hi, (__half*)lo, ldo, row_inv);
   else split_rows_kernel<256><<<R, 256, 0, stream>>>(src, ld, R, C, (__half*)hi, (__half*)lo, ldo, row_inv);
   NABU_CHECK_LAUNCH();
+  return 0;
+}
+
+int split_rows_pair(const float* s0, const float* s1, int ld, int R, int C, void* hi, void* lo, float* row_inv,
+                    cudaStream_t stream) {
+  NABU_REQUIRE(C % 8 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1)) & 15) == 0,
+               "split_rows_pair: C %% 8, ld %% 4 and 16-byte alignment required");
+  KernelScope ks("split_rows", stream);
+  split_rows_pair_kernel<<<R, 256, 0, stream>>>(s0, s1, ld, C, (__half*)hi, (__half*)lo, row_inv);
+  NABU_CHECK_LAUNCH();
+  return 0;
+}
+
+int split_global_pair(const float* s0, const float* s1, int ld, int R, int C, void* hi, void* lo, unsigned* maxbits,
+                      float* glob_inv, cudaStream_t stream) {
+  NABU_REQUIRE(C % 8 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1)) & 15) == 0,
+               "split_global_pair: C %% 8, ld %% 4 and 16-byte alignment required");
+  NABU_CHECK_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned), stream));
+  const int blocks = (int)min((size_t)num_sms() * 4, (size_t)R);
+  const float* src[2] = {s0, s1};
+  for (int d = 0; d < 2; ++d) {
+    KernelScope ks("absmax", stream);
+    absmax_kernel<<<blocks, 256, 0, stream>>>(src[d], ld, (size_t)R, (size_t)C, maxbits);
+    NABU_CHECK_LAUNCH();
+  }
+  for (int d = 0; d < 2; ++d) {
+    KernelScope ks("split_global", stream);
+    split_global_sub_kernel<<<blocks, 256, 0, stream>>>(src[d], ld, R, C, maxbits, (__half*)hi, (__half*)lo, (size_t)2 * C, d * C,
+                                                        glob_inv);
+    NABU_CHECK_LAUNCH();
+  }
   return 0;
 }
 
