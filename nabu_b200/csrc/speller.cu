@@ -119,21 +119,22 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
   const int r = blockIdx.x;
   const int Tm = a.Tm, E = a.E, H = a.H, A = a.A, V = a.V, F = a.F, ksz = a.ksz;
   const int padl = (ksz - 1) / 2;
+  auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };   // every piece starts on a 16-byte boundary (attn_bwd_smem)
   float* dl = sm;                          // [V]
-  float* oin = dl + V;                     // [H+E]
-  float* dctx = oin + H + E;               // [E]
-  float* dquery = dctx + E;                // [H]
-  float* al = dquery + H;                  // [Tm]
-  float* ap = al + Tm;                     // [Tm + ksz] zero-padded alpha_prev
-  float* dal = ap + Tm + ksz;              // [Tm] dalpha, then de
-  float* qs = dal + Tm;                    // [A]
-  float* dqs = qs + A;                     // [A]
-  float* red = dqs + A;                    // [32]
+  float* oin = dl + r4(V);                 // [H+E]
+  float* dctx = oin + r4(H + E);           // [E]
+  float* dquery = dctx + r4(E);            // [H]
+  float* al = dquery + r4(H);              // [Tm]
+  float* ap = al + r4(Tm);                 // [Tm + ksz] zero-padded alpha_prev
+  float* dal = ap + r4(Tm + ksz);          // [Tm] dalpha, then de
+  float* qs = dal + r4(Tm);                // [A]
+  float* dqs = qs + r4(A);                 // [A]
+  float* red = dqs + r4(A);                // [32]
   float* cf = red + 32;                    // [Tm][F]
-  float* dcf = cf + (size_t)Tm * F;        // [Tm][F]
-  float* wd = dcf + (size_t)Tm * F;        // [F][A]
-  float* wc = wd + (size_t)F * A;          // [ksz][F]
-  float* dpre = wc + (size_t)ksz * F;      // [TT][A]
+  float* dcf = cf + r4((size_t)Tm * F);    // [Tm][F]
+  float* wd = dcf + r4((size_t)Tm * F);    // [F][A]
+  float* wc = wd + r4((size_t)F * A);      // [ksz][F]
+  float* dpre = wc + r4((size_t)ksz * F);  // [TT][A]
 
   if (!(a.u < a.tlen[r])) {
     for (int i = tid; i < H; i += 256) a.dh_above[(size_t)r * H + i] = 0.f;
@@ -165,13 +166,38 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
   // phase B: dalpha[t] = dctx . values[t] + carry ; dvalues[t] += alpha[t] * dctx
   const float* values = a.values + (size_t)r * Tm * E;
   float* dvalues = a.dvalues + (size_t)r * Tm * E;
+  const bool vecE = (E & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.values) | reinterpret_cast<uintptr_t>(a.dvalues)) & 15) == 0;
   for (int t = warp; t < Tm; t += 8) {
     float s = 0.f;
     if (t < len) {
       const float at = al[t];
-      for (int i = lane; i < E; i += 32) {
-        s = fmaf(dctx[i], values[(size_t)t * E + i], s);
-        dvalues[(size_t)t * E + i] += at * dctx[i];
+      if (vecE && E <= 512) {
+        // all of this position's loads (values and the dvalues accumulator) are issued before the first use: the old
+        // scalar read-modify-write loop was a chain of E/32 dependent L2 round trips per position
+        const float4* vp = reinterpret_cast<const float4*>(values + (size_t)t * E);
+        float4* dp = reinterpret_cast<float4*>(dvalues + (size_t)t * E);
+        float4 xv[4], xd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i4 = lane + 32 * j;
+          if (i4 * 4 < E) { xv[j] = __ldg(vp + i4); xd[j] = dp[i4]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i4 = lane + 32 * j;
+          if (i4 * 4 < E) {
+            const float4 dc = *reinterpret_cast<const float4*>(dctx + i4 * 4);
+            s += (dc.x * xv[j].x + dc.y * xv[j].y) + (dc.z * xv[j].z + dc.w * xv[j].w);
+            xd[j].x = fmaf(at, dc.x, xd[j].x); xd[j].y = fmaf(at, dc.y, xd[j].y);
+            xd[j].z = fmaf(at, dc.z, xd[j].z); xd[j].w = fmaf(at, dc.w, xd[j].w);
+            dp[i4] = xd[j];
+          }
+        }
+      } else {
+        for (int i = lane; i < E; i += 32) {
+          s = fmaf(dctx[i], values[(size_t)t * E + i], s);
+          dvalues[(size_t)t * E + i] += at * dctx[i];
+        }
       }
       s = warp_sum(s);
     }
@@ -202,29 +228,52 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
     for (int i = 0; i < NA; ++i) {
       const int c = tid + 256 * i;
       if (c < A) {
-        for (int tt = 0; tt < nt; ++tt) {
-          const int t = t0 + tt;
-          float pre = qs[c] + keys[(size_t)t * A + c];
-          for (int f = 0; f < F; ++f) pre = fmaf(cf[t * F + f], wd[f * A + c], pre);
-          const float s = tanhf(pre);
-          const float de = dal[t];
-          const float dp = de * vreg[i] * (1.f - s * s);
-          dq[i] += dp;
-          dv[i] = fmaf(de, s, dv[i]);
+        // the tile's keys and dkeys accumulators are fetched up front (2*TT independent loads in flight per thread)
+        float kv[TT], dk[TT];
 #pragma unroll
-          for (int f = 0; f < MAXF; ++f)
-            if (f < F) dWd[i][f] = fmaf(cf[t * F + f], dp, dWd[i][f]);
-          dkeys[(size_t)t * A + c] += dp;
-          dpre[tt * A + c] = dp;
+        for (int tt = 0; tt < TT; ++tt) {
+          kv[tt] = tt < nt ? __ldg(keys + (size_t)(t0 + tt) * A + c) : 0.f;
+          dk[tt] = tt < nt ? dkeys[(size_t)(t0 + tt) * A + c] : 0.f;
+        }
+#pragma unroll
+        for (int tt = 0; tt < TT; ++tt) {
+          if (tt < nt) {
+            const int t = t0 + tt;
+            float pre = qs[c] + kv[tt];
+            for (int f = 0; f < F; ++f) pre = fmaf(cf[t * F + f], wd[f * A + c], pre);
+            const float s = tanh_fast(pre);
+            const float de = dal[t];
+            const float dp = de * vreg[i] * (1.f - s * s);
+            dq[i] += dp;
+            dv[i] = fmaf(de, s, dv[i]);
+#pragma unroll
+            for (int f = 0; f < MAXF; ++f)
+              if (f < F) dWd[i][f] = fmaf(cf[t * F + f], dp, dWd[i][f]);
+            dkeys[(size_t)t * A + c] = dk[tt] + dp;
+            dpre[tt * A + c] = dp;
+          }
         }
       }
     }
     __syncthreads();
-    for (int i = tid; i < nt * F; i += 256) {
-      const int tt = i / F, f = i % F;
-      float s = 0.f;
-      for (int c = 0; c < A; ++c) s = fmaf(dpre[tt * A + c], wd[f * A + c], s);
-      dcf[(t0 + tt) * F + f] = s;
+    // dcf[t][f] = sum_c dpre[t][c] * Wd[f][c]: one warp per memory position, lanes stride the attention units (both
+    // operands are then read at consecutive addresses; the (t, f)-per-thread mapping hit one bank with 10 lanes)
+    for (int tt = warp; tt < nt; tt += 8) {
+      float acc[MAXF];
+#pragma unroll
+      for (int f = 0; f < MAXF; ++f) acc[f] = 0.f;
+      for (int c = lane; c < A; c += 32) {
+        const float dp = dpre[tt * A + c];
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f)
+          if (f < F) acc[f] = fmaf(dp, wd[f * A + c], acc[f]);
+      }
+#pragma unroll
+      for (int f = 0; f < MAXF; ++f)
+        if (f < F) {
+          const float t = warp_sum(acc[f]);
+          if (lane == 0) dcf[(t0 + tt) * F + f] = t;
+        }
     }
     __syncthreads();
   }
@@ -265,17 +314,26 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
     for (int tau = tid; tau < Tm; tau += 256) a.dalign_carry[(size_t)r * Tm + tau] = 0.f;
   }
   // phase F: dh_top = dquery_part + dq . Wq^T   (warp per output unit, lanes over A)
-  for (int k = warp; k < H; k += 8) {
-    float s = 0.f;
-    for (int c = lane; c < A; c += 32) s = fmaf(dqs[c], a.Wq[(size_t)k * A + c], s);
-    s = warp_sum(s);
-    if (lane == 0) a.dh_above[(size_t)r * H + k] = dquery[k] + s;
+  for (int k = warp; k < H; k += 32) {                   // 4 output units per warp iteration: independent load chains
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < A; c += 32) {
+      const float dqc = dqs[c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k + 8 * j < H) s[j] = fmaf(dqc, __ldg(a.Wq + (size_t)(k + 8 * j) * A + c), s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = warp_sum(s[j]);
+      if (lane == 0 && k + 8 * j < H) a.dh_above[(size_t)r * H + k + 8 * j] = dquery[k + 8 * j] + t;
+    }
   }
 }
 
 inline size_t attn_bwd_smem(int Tm, int E, int H, int A, int V, int F, int ksz) {
-  return ((size_t)V + (H + E) + E + H + Tm + (Tm + ksz) + Tm + A + A + 32 + 2 * (size_t)Tm * F + (size_t)F * A +
-          (size_t)ksz * F + (size_t)TT * A) * sizeof(float);
+  auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
+  return (r4(V) + r4(H + E) + r4(E) + r4(H) + r4(Tm) + r4(Tm + ksz) + r4(Tm) + r4(A) + r4(A) + 32 + 2 * r4((size_t)Tm * F) +
+          r4((size_t)F * A) + r4((size_t)ksz * F) + (size_t)TT * A) * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------------------------

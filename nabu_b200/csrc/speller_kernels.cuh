@@ -153,16 +153,19 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
   const int mrow = r / a.rows_per_mem;
   const int Tm = a.Tm, E = a.E, H = a.H, A = a.A, V = a.V, F = a.F, ksz = a.ksz;
   const int padl = (ksz - 1) / 2;
+  auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };   // every piece starts on a 16-byte boundary (attn_step_smem)
   float* query = sm;                       // [H]
-  float* q = query + H;                    // [A]
-  float* ap = q + A;                       // [Tm + ksz] zero padded alpha_prev
-  float* e = ap + Tm + ksz;                // [Tm]
-  float* ctx = e + Tm;                     // [E]
-  float* red = ctx + E;                    // [32]
+  float* q = query + r4(H);                // [A]
+  float* ap = q + r4(A);                   // [Tm + ksz] zero padded alpha_prev
+  float* e = ap + r4(Tm + ksz);            // [Tm]
+  float* ctx = e + r4(Tm);                 // [E]
+  float* red = ctx + r4(E);                // [32]
   float* part = red + 32;                  // [8][32] projection partials
   float* cf = part + 256;                  // [Tm][F]
-  float* wd = cf + (size_t)Tm * F;         // [F][A]
-  float* wc = wd + (size_t)F * A;          // [ksz][F]
+  float* wd = cf + r4((size_t)Tm * F);     // [F][A]
+  float* wc = wd + r4((size_t)F * A);      // [ksz][F]
+  float* vs = wc + r4((size_t)ksz * F);    // [A] attention vector
+  float* cpart = vs + r4(A);               // [1024] context partials of the t-splits
 
   const bool active = (a.tlen == nullptr) || (a.u < a.tlen[r]);
   if (!active) {                           // finished row: copy the state through, emit zeros
@@ -187,13 +190,23 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
   }
   for (int i = tid; i < F * A; i += 256) wd[i] = a.Wd[i];
   for (int i = tid; i < ksz * F; i += 256) wc[i] = a.Wc[i];
+  for (int i = tid; i < A; i += 256) vs[i] = a.v[i];
   __syncthreads();
 
   // phase 0: q = query . Wq
   for (int c = tid; c < A; c += 256) {
-    float s = 0.f;
+    // four independent chains, 16 weight loads in flight per thread (the loop is bound by L2 latency, not by FMAs)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
 #pragma unroll 4
-    for (int k = 0; k < H; ++k) s = fmaf(query[k], a.Wq[(size_t)k * A + c], s);
+    for (; k + 3 < H; k += 4) {
+      s0 = fmaf(query[k + 0], __ldg(a.Wq + (size_t)(k + 0) * A + c), s0);
+      s1 = fmaf(query[k + 1], __ldg(a.Wq + (size_t)(k + 1) * A + c), s1);
+      s2 = fmaf(query[k + 2], __ldg(a.Wq + (size_t)(k + 2) * A + c), s2);
+      s3 = fmaf(query[k + 3], __ldg(a.Wq + (size_t)(k + 3) * A + c), s3);
+    }
+    for (; k < H; ++k) s0 = fmaf(query[k], __ldg(a.Wq + (size_t)k * A + c), s0);
+    const float s = (s0 + s1) + (s2 + s3);
     q[c] = s;
     if (a.q_save) a.q_save[(size_t)r * A + c] = s;
   }
@@ -206,19 +219,51 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
     if (a.cf_save) a.cf_save[(size_t)r * Tm * F + i] = s;
   }
   __syncthreads();
-  // phase 2: scores, one warp per memory position
+  // phase 2: scores e[t] = v . tanh(q + keys[t] + cf[t] . Wd), one warp per memory position, 128-bit loads of the keys
+  // (two positions in flight per warp), tanh from MUFU
   const float* keys = a.keys + (size_t)mrow * Tm * A;
-  for (int t = warp; t < Tm; t += 8) {
-    float s = 0.f;
-    if (t < len) {
-      for (int c = lane; c < A; c += 32) {
-        float pre = q[c] + keys[(size_t)t * A + c];
-        for (int f = 0; f < F; ++f) pre = fmaf(cf[t * F + f], wd[f * A + c], pre);
-        s = fmaf(a.v[c], tanhf(pre), s);
+  const bool vec4 = ((A | E) & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.keys) | reinterpret_cast<uintptr_t>(a.values)) & 15) == 0;
+  if (vec4) {
+    for (int t = warp; t < Tm; t += 16) {
+      const int t1 = t + 8;
+      float sa = 0.f, sb = 0.f;
+      for (int c = lane * 4; c < A; c += 128) {
+        float4 ka = make_float4(0.f, 0.f, 0.f, 0.f), kb = ka;
+        if (t < len) ka = __ldg(reinterpret_cast<const float4*>(keys + (size_t)t * A + c));
+        if (t1 < len) kb = __ldg(reinterpret_cast<const float4*>(keys + (size_t)t1 * A + c));
+        const float4 qq = *reinterpret_cast<const float4*>(q + c);
+        const float4 vv = *reinterpret_cast<const float4*>(vs + c);
+        float pa[4] = {qq.x + ka.x, qq.y + ka.y, qq.z + ka.z, qq.w + ka.w};
+        float pb[4] = {qq.x + kb.x, qq.y + kb.y, qq.z + kb.z, qq.w + kb.w};
+        for (int f = 0; f < F; ++f) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wd + f * A + c);
+          const float ca = cf[t * F + f], cb = t1 < Tm ? cf[t1 * F + f] : 0.f;
+          pa[0] = fmaf(ca, w4.x, pa[0]); pa[1] = fmaf(ca, w4.y, pa[1]); pa[2] = fmaf(ca, w4.z, pa[2]); pa[3] = fmaf(ca, w4.w, pa[3]);
+          pb[0] = fmaf(cb, w4.x, pb[0]); pb[1] = fmaf(cb, w4.y, pb[1]); pb[2] = fmaf(cb, w4.z, pb[2]); pb[3] = fmaf(cb, w4.w, pb[3]);
+        }
+        sa += vv.x * tanh_fast(pa[0]) + vv.y * tanh_fast(pa[1]) + vv.z * tanh_fast(pa[2]) + vv.w * tanh_fast(pa[3]);
+        sb += vv.x * tanh_fast(pb[0]) + vv.y * tanh_fast(pb[1]) + vv.z * tanh_fast(pb[2]) + vv.w * tanh_fast(pb[3]);
       }
-      s = warp_sum(s);
+      sa = warp_sum(sa);
+      sb = warp_sum(sb);
+      if (lane == 0) {
+        e[t] = (t < len) ? sa : -CUDART_INF_F;
+        if (t1 < Tm) e[t1] = (t1 < len) ? sb : -CUDART_INF_F;
+      }
     }
-    if (lane == 0) e[t] = (t < len) ? s : -CUDART_INF_F;
+  } else {
+    for (int t = warp; t < Tm; t += 8) {
+      float s = 0.f;
+      if (t < len) {
+        for (int c = lane; c < A; c += 32) {
+          float pre = q[c] + keys[(size_t)t * A + c];
+          for (int f = 0; f < F; ++f) pre = fmaf(cf[t * F + f], wd[f * A + c], pre);
+          s = fmaf(vs[c], tanh_fast(pre), s);
+        }
+        s = warp_sum(s);
+      }
+      if (lane == 0) e[t] = (t < len) ? s : -CUDART_INF_F;
+    }
   }
   __syncthreads();
   // phase 3: softmax over the memory positions
@@ -239,14 +284,51 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
     a.align_new[(size_t)r * Tm + t] = p;
   }
   __syncthreads();
-  // phase 4: context = alpha . values
+  // phase 4: context = alpha . values.  128-bit loads; the memory positions are split over 256 / (E/4) thread groups and
+  // every thread keeps 4 loads in flight (the old one-column-per-thread loop was a chain of Tm dependent loads).
   const float* values = a.values + (size_t)mrow * Tm * E;
-  for (int i = tid; i < E; i += 256) {
-    float s = 0.f;
-    for (int t = 0; t < len; ++t) s = fmaf(e[t], values[(size_t)t * E + i], s);
-    ctx[i] = s;
-    a.ctx_new[(size_t)r * E + i] = s;
-    a.ctxT_new[(size_t)i * a.R + r] = s;
+  if (vec4 && E <= 1024) {
+    const int NC4 = E >> 2;
+    const int TS = 256 / NC4 > 0 ? 256 / NC4 : 1;          // E <= 1024 -> NC4 <= 256
+    const int cg = tid % NC4, ts = tid / NC4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ts < TS) {
+      int t = ts;
+#pragma unroll 1
+      for (; t + 3 * TS < len; t += 4 * TS) {
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(values + (size_t)(t) * E) + cg);
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(values + (size_t)(t + TS) * E) + cg);
+        const float4 x2 = __ldg(reinterpret_cast<const float4*>(values + (size_t)(t + 2 * TS) * E) + cg);
+        const float4 x3 = __ldg(reinterpret_cast<const float4*>(values + (size_t)(t + 3 * TS) * E) + cg);
+        const float e0 = e[t], e1 = e[t + TS], e2 = e[t + 2 * TS], e3 = e[t + 3 * TS];
+        acc.x += (e0 * x0.x + e1 * x1.x) + (e2 * x2.x + e3 * x3.x);
+        acc.y += (e0 * x0.y + e1 * x1.y) + (e2 * x2.y + e3 * x3.y);
+        acc.z += (e0 * x0.z + e1 * x1.z) + (e2 * x2.z + e3 * x3.z);
+        acc.w += (e0 * x0.w + e1 * x1.w) + (e2 * x2.w + e3 * x3.w);
+      }
+      for (; t < len; t += TS) {
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(values + (size_t)t * E) + cg);
+        const float e0 = e[t];
+        acc.x = fmaf(e0, x0.x, acc.x); acc.y = fmaf(e0, x0.y, acc.y); acc.z = fmaf(e0, x0.z, acc.z); acc.w = fmaf(e0, x0.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(cpart + (size_t)tid * 4) = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < E; i += 256) {
+      float s = 0.f;
+      for (int k = 0; k < TS; ++k) s += cpart[(size_t)(k * NC4 + (i >> 2)) * 4 + (i & 3)];
+      ctx[i] = s;
+      a.ctx_new[(size_t)r * E + i] = s;
+      a.ctxT_new[(size_t)i * a.R + r] = s;
+    }
+  } else {
+    for (int i = tid; i < E; i += 256) {
+      float s = 0.f;
+      for (int t = 0; t < len; ++t) s = fmaf(e[t], values[(size_t)t * E + i], s);
+      ctx[i] = s;
+      a.ctx_new[(size_t)r * E + i] = s;
+      a.ctxT_new[(size_t)i * a.R + r] = s;
+    }
   }
   __syncthreads();
   if (a.outin_save) {
@@ -259,8 +341,22 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
     const int vc = v0 + lane;
     float s = 0.f;
     if (vc < V) {
-      for (int k = warp; k < H; k += 8) s = fmaf(query[k], a.Wo[(size_t)k * V + vc], s);
-      for (int k = warp; k < E; k += 8) s = fmaf(ctx[k], a.Wo[(size_t)(H + k) * V + vc], s);
+      float s1 = 0.f;
+      int k = warp;
+#pragma unroll 4
+      for (; k + 8 < H; k += 16) {
+        s = fmaf(query[k], __ldg(a.Wo + (size_t)k * V + vc), s);
+        s1 = fmaf(query[k + 8], __ldg(a.Wo + (size_t)(k + 8) * V + vc), s1);
+      }
+      for (; k < H; k += 8) s = fmaf(query[k], __ldg(a.Wo + (size_t)k * V + vc), s);
+      k = warp;
+#pragma unroll 4
+      for (; k + 8 < E; k += 16) {
+        s = fmaf(ctx[k], __ldg(a.Wo + (size_t)(H + k) * V + vc), s);
+        s1 = fmaf(ctx[k + 8], __ldg(a.Wo + (size_t)(H + k + 8) * V + vc), s1);
+      }
+      for (; k < E; k += 8) s = fmaf(ctx[k], __ldg(a.Wo + (size_t)(H + k) * V + vc), s);
+      s += s1;
     }
     part[warp * 32 + lane] = s;
     __syncthreads();
@@ -274,8 +370,10 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
 }
 
 inline size_t attn_step_smem(int Tm, int E, int H, int A, int F, int ksz) {
-  return ((size_t)H + A + (Tm + ksz) + Tm + E + 32 + 256 + (size_t)Tm * F + (size_t)F * A + (size_t)ksz * F) *
-         sizeof(float);
+  // the arrays read with 128-bit accesses (q, wd, vs, cpart) must start on 16-byte boundaries: round every piece up to 4
+  auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
+  return (r4(H) + r4(A) + r4(Tm + ksz) + r4(Tm) + r4(E) + 32 + 256 + r4((size_t)Tm * F) + r4((size_t)F * A) +
+          r4((size_t)ksz * F) + r4(A) + 1024) * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------------------------
