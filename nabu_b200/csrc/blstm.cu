@@ -802,6 +802,25 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
       NABU_CHECK_CUDA(cudaEventRecord(ov.ev_pre, stream));
       NABU_CHECK_CUDA(cudaStreamWaitEvent(ov.hp, ov.ev_pre, 0));
       rs = ov.hp;
+      // The concurrent GEMMs stream gigabytes through L2; keep the 4 MB exchange buffer of the recurrence resident
+      // (persisting access-policy window on the recurrence's stream) so that its polls do not go to DRAM.
+      static int l2_pinned = -1;
+      if (l2_pinned < 0) {
+        l2_pinned = (getenv("NABU_L2_PIN") && atoi(getenv("NABU_L2_PIN")) == 0) ? 0 : 1;
+        if (l2_pinned && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)16 << 20) != cudaSuccess) {
+          cudaGetLastError();
+          l2_pinned = 0;
+        }
+      }
+      if (l2_pinned) {
+        cudaStreamAttrValue av = {};
+        av.accessPolicyWindow.base_ptr = w.xchg;
+        av.accessPolicyWindow.num_bytes = (size_t)2 * 2 * H4 * 128 * sizeof(float);
+        av.accessPolicyWindow.hitRatio = 1.f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(ov.hp, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+      }
     }
     ov.in_defer = defer;
     const int re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched);
