@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
   const int r = r0 + rl;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (r < R) {
-#pragma unroll 4
+#pragma unroll 16
     for (int k = ks; k < a.K0; k += 4) {
       const float x = __ldcg(a.inT0 + (size_t)k * R + r);
       const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * 8);
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
       acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
       acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
     }
-#pragma unroll 4
+#pragma unroll 16
     for (int k = ks; k < a.K1; k += 4) {
       const float x = __ldcg(a.inT1 + (size_t)k * R + r);
       const float* wp = Ws + (a.K0 + k) * 8;
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_matmul_t_kernel(const MatmulTA
   const int rl = tid % ROWS, ks = tid / ROWS, r = r0 + rl;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (r < a.R) {
-#pragma unroll 4
+#pragma unroll 16
     for (int k = ks; k < a.K; k += 4) {
       const float x = __ldcg(a.xT + (size_t)k * a.R + r);
       const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * 8);
