@@ -107,6 +107,7 @@ struct AttnBwdArgs {
   float* dkeys; float* dvalues;                      // [R][Tm][A], [R][Tm][E] accumulate
   float* dv_part; float* dWd_part; float* dWc_part;  // [R][A], [R][F][A], [R][ksz][F] accumulate
   const int* tlen;
+  int ablate;                                        // NABU_ATTN_ABLATE (profiling only, results are then wrong): 1 skip dcf, 2 skip the conv backward, 4 skip the score backward
 };
 
 constexpr int TT = 16;     // memory positions per dpre tile
@@ -213,21 +214,24 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
   // phase D: score backward, tiles of TT memory positions; thread owns attention units tid + 256*i
   const float* keys = a.keys + (size_t)r * Tm * A;
   float* dkeys = a.dkeys + (size_t)r * Tm * A;
-  float dq[NA], dv[NA], dWd[NA][MAXF], vreg[NA];
+  float dq[NA], dv[NA], dWd[NA][MAXF], vreg[NA], wdreg[NA][MAXF];
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
     dq[i] = 0.f; dv[i] = 0.f;
     const int c = tid + 256 * i;
     vreg[i] = c < A ? a.v[c] : 0.f;
 #pragma unroll
-    for (int f = 0; f < MAXF; ++f) dWd[i][f] = 0.f;
+    for (int f = 0; f < MAXF; ++f) {
+      dWd[i][f] = 0.f;
+      wdreg[i][f] = (f < F && c < A) ? wd[f * A + c] : 0.f;   // this thread's column of Wd: constant over the positions
+    }
   }
   for (int t0 = 0; t0 < len; t0 += TT) {
     const int nt = min(TT, len - t0);
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int c = tid + 256 * i;
-      if (c < A) {
+      if (c < A && !(a.ablate & 4)) {
         // the tile's keys and dkeys accumulators are fetched up front (2*TT independent loads in flight per thread)
         float kv[TT], dk[TT];
 #pragma unroll
@@ -239,16 +243,19 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
         for (int tt = 0; tt < TT; ++tt) {
           if (tt < nt) {
             const int t = t0 + tt;
+            float cfr[MAXF];                         // location features of this position: one broadcast read each
+#pragma unroll
+            for (int f = 0; f < MAXF; ++f) cfr[f] = f < F ? cf[t * F + f] : 0.f;
             float pre = qs[c] + kv[tt];
-            for (int f = 0; f < F; ++f) pre = fmaf(cf[t * F + f], wd[f * A + c], pre);
+#pragma unroll
+            for (int f = 0; f < MAXF; ++f) pre = fmaf(cfr[f], wdreg[i][f], pre);
             const float s = tanh_fast(pre);
             const float de = dal[t];
             const float dp = de * vreg[i] * (1.f - s * s);
             dq[i] += dp;
             dv[i] = fmaf(de, s, dv[i]);
 #pragma unroll
-            for (int f = 0; f < MAXF; ++f)
-              if (f < F) dWd[i][f] = fmaf(cf[t * F + f], dp, dWd[i][f]);
+            for (int f = 0; f < MAXF; ++f) dWd[i][f] = fmaf(cfr[f], dp, dWd[i][f]);
             dkeys[(size_t)t * A + c] = dk[tt] + dp;
             dpre[tt * A + c] = dp;
           }
@@ -258,21 +265,32 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
     __syncthreads();
     // dcf[t][f] = sum_c dpre[t][c] * Wd[f][c]: one warp per memory position, lanes stride the attention units (both
     // operands are then read at consecutive addresses; the (t, f)-per-thread mapping hit one bank with 10 lanes)
-    for (int tt = warp; tt < nt; tt += 8) {
-      float acc[MAXF];
+    if (!(a.ablate & 1))
+    for (int tt = warp; tt < nt; tt += 16) {           // positions tt and tt + 8 share every Wd read
+      const int t1 = tt + 8;
+      const bool two = t1 < nt;
+      float acc0[MAXF], acc1[MAXF];
 #pragma unroll
-      for (int f = 0; f < MAXF; ++f) acc[f] = 0.f;
+      for (int f = 0; f < MAXF; ++f) acc0[f] = acc1[f] = 0.f;
       for (int c = lane; c < A; c += 32) {
-        const float dp = dpre[tt * A + c];
+        const float d0 = dpre[tt * A + c];
+        const float d1 = two ? dpre[t1 * A + c] : 0.f;
 #pragma unroll
         for (int f = 0; f < MAXF; ++f)
-          if (f < F) acc[f] = fmaf(dp, wd[f * A + c], acc[f]);
+          if (f < F) {
+            const float wv = wd[f * A + c];
+            acc0[f] = fmaf(d0, wv, acc0[f]);
+            acc1[f] = fmaf(d1, wv, acc1[f]);
+          }
       }
 #pragma unroll
       for (int f = 0; f < MAXF; ++f)
         if (f < F) {
-          const float t = warp_sum(acc[f]);
-          if (lane == 0) dcf[(t0 + tt) * F + f] = t;
+          const float s0 = warp_sum(acc0[f]), s1 = warp_sum(acc1[f]);
+          if (lane == 0) {
+            dcf[(t0 + tt) * F + f] = s0;
+            if (two) dcf[(t0 + t1) * F + f] = s1;
+          }
         }
     }
     __syncthreads();
@@ -292,16 +310,37 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
   }
   __syncthreads();
   // phase E: location-feature backward
-  if (F > 0) {
+  if (F > 0 && !(a.ablate & 2)) {
     // dalign_prev[tau] = sum_{k,f} dcf[tau - k + padl][f] * Wc[k][f]
-    for (int tau = tid; tau < Tm; tau += 256) {
-      float s = 0.f;
-      for (int k = 0; k < ksz; ++k) {
-        const int t = tau - k + padl;
-        if (t >= 0 && t < Tm)
-          for (int f = 0; f < F; ++f) s = fmaf(dcf[t * F + f], wc[k * F + f], s);
+    // (the taps are split over the two halves of the block; partial sums meet in the dpre scratch)
+    {
+      const bool split2 = 2 * Tm <= TT * A;             // room for both halves' partial sums in the scratch
+      const int half = split2 ? tid >> 7 : 0, kh = split2 ? (ksz + 1) / 2 : ksz;
+      const int k0 = half * kh, k1 = min(ksz, k0 + kh);
+      for (int tau = split2 ? (tid & 127) : tid; tau < Tm; tau += split2 ? 128 : 256) {
+        float s = 0.f;
+        for (int k = k0; k < k1; ++k) {
+          const int t = tau - k + padl;
+          if (t >= 0 && t < Tm) {
+            if ((F & 1) == 0) {
+              const float2* dr = reinterpret_cast<const float2*>(dcf + t * F);
+              const float2* wr = reinterpret_cast<const float2*>(wc + k * F);
+              for (int f2 = 0; f2 < F / 2; ++f2) {
+                const float2 x = dr[f2], y = wr[f2];
+                s = fmaf(x.x, y.x, s);
+                s = fmaf(x.y, y.y, s);
+              }
+            } else {
+              for (int f = 0; f < F; ++f) s = fmaf(dcf[t * F + f], wc[k * F + f], s);
+            }
+          }
+        }
+        if (split2) dpre[half * Tm + tau] = s;
+        else a.dalign_carry[(size_t)r * Tm + tau] = s;
       }
-      a.dalign_carry[(size_t)r * Tm + tau] = s;
+      __syncthreads();
+      if (split2)
+        for (int tau = tid; tau < Tm; tau += 256) a.dalign_carry[(size_t)r * Tm + tau] = dpre[tau] + dpre[Tm + tau];
     }
     // dWc[k][f] += sum_t alpha_prev[t + k - padl] * dcf[t][f]
     for (int i = tid; i < ksz * F; i += 256) {
@@ -583,6 +622,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
     a.dq_save = w.dq + (size_t)u * B * A; a.dkeys = w.dkeys; a.dvalues = w.dvalues;
     a.dv_part = w.dv_part; a.dWd_part = w.dWd_part; a.dWc_part = w.dWc_part; a.tlen = target_len;
     {
+      a.ablate = getenv("NABU_ATTN_ABLATE") ? atoi(getenv("NABU_ATTN_ABLATE")) : 0;
       KernelScope ks("dec_attn_bwd_step", stream);
       if (A <= 256) dec_attn_bwd_step_kernel<1><<<B, 256, smem_attn, stream>>>(a);
       else dec_attn_bwd_step_kernel<2><<<B, 256, smem_attn, stream>>>(a);
