@@ -102,3 +102,28 @@ def test_training_reduces_loss():
              {'text': torch.from_numpy(labels).to(dev)}, {'text': torch.from_numpy(ll).to(dev)})
     losses = [float(tr.update(*batch)[0]) for _ in range(30)]
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+def test_deferred_weight_gradients_change_nothing():
+    """nabu_set_overlap (weight-gradient GEMMs on a side stream under the next layer's backward recurrence) is a pure
+    scheduling change: two updates from the same initial state give bit-identical parameters with it on and off."""
+    from nabu_b200 import engine
+    dev = torch.device('cuda', 0)
+    B, T, D, H, NL, V = 24, 36, 40, 512, 3, 29
+    x, lens, labels, ll = synthetic_ctc_batch(B, T, D, V, ragged=True)
+    batch = ({'features': torch.from_numpy(x).to(dev)}, {'features': torch.from_numpy(lens).to(dev)},
+             {'text': torch.from_numpy(labels).to(dev)}, {'text': torch.from_numpy(ll).to(dev)})
+    results = []
+    try:
+        for on in (True, False):
+            tr = _ctc_trainer(H, NL, V, dev, seed=3)
+            tr.model.build({'features': D}, dev)
+            engine.set_overlap(on)
+            losses = [float(tr.update(*batch)[0]) for _ in range(2)]
+            torch.cuda.synchronize()
+            results.append((losses, tr.model.store.to_numpy()))
+    finally:
+        engine.set_overlap(True)
+    assert results[0][0] == results[1][0]
+    for k in results[0][1]:
+        assert np.array_equal(results[0][1][k], results[1][1][k]), k
