@@ -147,37 +147,40 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
         CL_STAMP(s, 1);
 #pragma unroll
         for (int i = 1; i < NCH; ++i) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
-#pragma unroll
-        for (int i = 1; i < NCH; ++i)
-          while (!ll_ok(v[i], fl)) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
-        // peers have read their receive buffers of step s-1, hence received my quarters: As and their buffers are free
-        cluster_wait();
+        // K block by K block: the MMAs of block kb run while block kb+1 is validated and stored (its loads are in flight)
+        constexpr int CPB = NCH / KB;                  // chunks per thread and K block (hi tile then lo tile)
         uint4* dstA = reinterpret_cast<uint4*>(As) + tid;
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) dstA[i * CL_THREADS] = v[i];
-        fence_proxy_async_smem();
-        __syncthreads();
-      }
-      if (warp_u == 0) {                               // converged warp; one elected lane issues
-        CL_STAMP(s, 2);
-        tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ah = make_desc(As_u + (kb * 2 + 0) * A_TILE + ks * 32, 16, 1024, 2);
-            const uint64_t al = make_desc(As_u + (kb * 2 + 1) * A_TILE + ks * 32, 16, 1024, 2);
-            const uint64_t bh = make_desc(Bs_u + (kb * 2 + 0) * B_TILE + ks * 32, 16, 1024, 2);
-            const uint64_t bl = make_desc(Bs_u + (kb * 2 + 1) * B_TILE + ks * 32, 16, 1024, 2);
-            const uint32_t acc = (kb | ks) != 0;
-            if (elect_one()) {
-              umma_f16(tm, ah, bh, idesc, acc);
-              umma_f16(tm + GC, ah, bl, idesc, acc);
-              umma_f16(tm + GC, al, bh, idesc, 1u);
+          for (int i = kb * CPB; i < (kb + 1) * CPB; ++i)
+            while (!ll_ok(v[i], fl)) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
+          // peers have read their receive buffers of step s-1, hence received my quarters: As and their buffers are free
+          if (kb == 0) cluster_wait();
+#pragma unroll
+          for (int i = kb * CPB; i < (kb + 1) * CPB; ++i) dstA[i * CL_THREADS] = v[i];
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (warp_u == 0) {                           // converged warp; one elected lane issues
+            if (kb == 0) CL_STAMP(s, 2);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ah = make_desc(As_u + (kb * 2 + 0) * A_TILE + ks * 32, 16, 1024, 2);
+              const uint64_t al = make_desc(As_u + (kb * 2 + 1) * A_TILE + ks * 32, 16, 1024, 2);
+              const uint64_t bh = make_desc(Bs_u + (kb * 2 + 0) * B_TILE + ks * 32, 16, 1024, 2);
+              const uint64_t bl = make_desc(Bs_u + (kb * 2 + 1) * B_TILE + ks * 32, 16, 1024, 2);
+              const uint32_t acc = (kb | ks) != 0;
+              if (elect_one()) {
+                umma_f16(tm, ah, bh, idesc, acc);
+                umma_f16(tm + GC, ah, bl, idesc, acc);
+                umma_f16(tm + GC, al, bh, idesc, 1u);
+              }
             }
+            if (kb == KB - 1 && elect_one()) umma_commit(smem_u32(&mma_bar));
           }
+          __syncwarp();
         }
-        if (elect_one()) umma_commit(smem_u32(&mma_bar));
       }
       mbar_wait(smem_u32(&mma_bar), par);
       tc_fence_after();
