@@ -160,6 +160,20 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
     const uint8_t* dzprev = dzx + (size_t)((iter + 1) & 1) * H4 * BT * 4;
     uint8_t* dznext = dzx + (size_t)(iter & 1) * H4 * BT * 4;
     CL_STAMP(iter, 0);
+    // ---- first the critical load: my dz slice (self-validating data, see "LL" in cl_tc_common.cuh).  The poll and the
+    // first K block's loads are issued BEFORE the pointwise operands' 14 loads per thread, which would otherwise sit in
+    // front of them in the LSU queue (~0.9 us on the slowest CTA's path). -------------------------------------------------
+    const unsigned par = (unsigned)(iter - 1) & 1u;
+    const uint32_t fl = ll_flag(iter - 1) ? 0x00010001u : 0u;
+    uint4 v[2][8];
+    const uint4* src = reinterpret_cast<const uint4*>(dzprev + (size_t)r * SLICE) + tid;
+    if (iter > 0) {
+      if (tid == 0) mbar_expect_tx(smem_u32(&rx_bar), (CLS - 1) * B8_BLK);
+      do { v[0][0] = ld_relaxed_v4(src); } while (!ll_ok(v[0][0], fl));
+      CL_STAMP(iter, 1);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) v[0][i] = ld_relaxed_v4(src + i * CL_THREADS);
+    }
     // ---- prefetch pointwise operands -------------------------------------------------------------------------
     float gt[2][4][4], ct[2][4], cprev[2][4], dyv[2][4];
     bool valid[2];
@@ -186,18 +200,8 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
     }
 
     if (iter > 0) {
-      const unsigned par = (unsigned)(iter - 1) & 1u;
-      if (tid == 0) mbar_expect_tx(smem_u32(&rx_bar), (CLS - 1) * B8_BLK);
-      // ---- fetch my dz slice (self-validating data, see "LL" in cl_tc_common.cuh) and multiply as it arrives ---------
-      const uint32_t fl = ll_flag(iter - 1) ? 0x00010001u : 0u;
       // One K block (hi and lo tile, 8 chunks of 16 bytes per thread) at a time, the next block's loads in flight while
       // this one is validated, stored and multiplied.
-      uint4 v[2][8];
-      const uint4* src = reinterpret_cast<const uint4*>(dzprev + (size_t)r * SLICE) + tid;
-      do { v[0][0] = ld_relaxed_v4(src); } while (!ll_ok(v[0][0], fl));
-      CL_STAMP(iter, 1);
-#pragma unroll
-      for (int i = 1; i < 8; ++i) v[0][i] = ld_relaxed_v4(src + i * CL_THREADS);
 #pragma unroll
       for (int kb = 0; kb < KBN; ++kb) {
         const uint4* cur = src + (size_t)kb * (2 * A_TILE / 16);

@@ -118,19 +118,23 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
     for (int g = 0; g < 4; ++g)
 #pragma unroll
       for (int u = 0; u < UPT; ++u) gx[g][u] = 0.f;
-    if (valid) {
-      const float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
+    // issued AFTER the critical loads of the h slice below (it would sit in front of them in the LSU queue)
+    auto prefetch_gx = [&]() {
+      if (valid) {
+        const float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if constexpr (UPT == 4) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + g * H));
-          gx[g][0] = v.x; gx[g][1] = v.y; gx[g][2] = v.z; gx[g][3] = v.w;
-        } else {
-          const float2 v = __ldcg(reinterpret_cast<const float2*>(gp + g * H));
-          gx[g][0] = v.x; gx[g][1] = v.y;
+        for (int g = 0; g < 4; ++g) {
+          if constexpr (UPT == 4) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + g * H));
+            gx[g][0] = v.x; gx[g][1] = v.y; gx[g][2] = v.z; gx[g][3] = v.w;
+          } else {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(gp + g * H));
+            gx[g][0] = v.x; gx[g][1] = v.y;
+          }
         }
       }
-    }
+    };
+    if (s == 0) prefetch_gx();
 
     if (s > 0) {
       const unsigned par = (unsigned)(s - 1) & 1u;
@@ -147,6 +151,7 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
         CL_STAMP(s, 1);
 #pragma unroll
         for (int i = 1; i < NCH; ++i) v[i] = ld_relaxed_v4(src + i * CL_THREADS);
+        prefetch_gx();
         // K block by K block: the MMAs of block kb run while block kb+1 is validated and stored (its loads are in flight)
         constexpr int CPB = NCH / KB;                  // chunks per thread and K block (hi tile then lo tile)
         uint4* dstA = reinterpret_cast<uint4*>(As) + tid;
