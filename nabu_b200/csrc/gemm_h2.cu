@@ -32,7 +32,7 @@ constexpr int H2_A_TILE = H2_BM * H2_BK * 2;             // 16 KB
 constexpr int H2_B_TILE = H2_BN * H2_BK * 2;             // 32 KB
 constexpr int H2_STAGE = 2 * H2_A_TILE + 2 * H2_B_TILE;  // 96 KB
 constexpr int H2_TPAD = 36;                              // padded row of the epilogue transpose buffer (floats)
-constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256 + 4 * 32 * H2_TPAD * 4;
+constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256 + 4 * 32 * H2_TPAD * 4 + 2 * H2_BN * 4;   // + column scale / bias of the tile
 
 struct H2Args {
   int M, N;
@@ -168,49 +168,66 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     if (g.a_row_inv && m < g.M) sa_inv *= __ldg(g.a_row_inv + m);
     sa_inv *= g.b_glob_inv ? __ldg(g.b_glob_inv) : 1.f;
     float* tbuf = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256) + (warp - 2) * (32 * H2_TPAD);
+    // Column scale and bias of this tile are staged in shared memory while the main loop runs (the epilogue warps are
+    // idle then); per-chunk global loads of them used to stall every chunk of the epilogue.
+    float* cs_s = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256) + 4 * 32 * H2_TPAD;
+    float* bs_s = cs_s + H2_BN;
+    for (int c = threadIdx.x - 64; c < H2_BN; c += 128) {
+      const int n = n0 + c;
+      float cs = 1.f, bs = 0.f;
+      if (n < g.N) {
+        if (g.b_row_inv) cs = __ldg(g.b_row_inv + n);
+        if (!split) {
+          cs *= g.alpha;
+          if (g.bias) bs = __ldg(g.bias + n);
+        }
+      }
+      cs_s[c] = cs;
+      bs_s[c] = bs;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int rl = lane >> 3, c4 = (lane & 7) * 4;       // read phase: row within a group of 4, first of 4 columns
     if (nkb > 0) {
       mbar_wait(bar_tmem, 0);
       tc_fence_after();
     }
-    for (int c0 = 0; c0 < H2_BN; c0 += 32) {
-      if (n0 + c0 >= g.N) break;
-      uint32_t r1[32], r2[32];
+    const int nchunks = max(0, min(H2_BN / 32, (g.N - n0 + 31) / 32));
+    uint32_t ra[2][32], rb[2][32];                     // double-buffered TMEM reads: chunk c+1 is in flight during chunk c
+    auto issue = [&](int ch, int buf) {
       if (nkb > 0) {
-        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r1);
-        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(H2_BN + c0), r2);
-        tmem_ld_wait();
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(ch * 32), ra[buf]);
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(H2_BN + ch * 32), rb[buf]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r1[j] = r2[j] = 0u;
+        for (int j = 0; j < 32; ++j) ra[buf][j] = rb[buf][j] = 0u;
       }
+    };
+    if (nchunks > 0) issue(0, 0);
+#pragma unroll
+    for (int ch = 0; ch < H2_BN / 32; ++ch) {
+      if (ch >= nchunks) break;
+      const int c0 = ch * 32, buf = ch & 1;
+      if (nkb > 0) tmem_ld_wait();
+      if (ch + 1 < nchunks) issue(ch + 1, buf ^ 1);
 #pragma unroll
       for (int j4 = 0; j4 < 32; j4 += 4) {
         float4 v;
-        v.x = fmaf(__uint_as_float(r2[j4 + 0]), 1.f / 2048.f, __uint_as_float(r1[j4 + 0])) * sa_inv;
-        v.y = fmaf(__uint_as_float(r2[j4 + 1]), 1.f / 2048.f, __uint_as_float(r1[j4 + 1])) * sa_inv;
-        v.z = fmaf(__uint_as_float(r2[j4 + 2]), 1.f / 2048.f, __uint_as_float(r1[j4 + 2])) * sa_inv;
-        v.w = fmaf(__uint_as_float(r2[j4 + 3]), 1.f / 2048.f, __uint_as_float(r1[j4 + 3])) * sa_inv;
+        v.x = fmaf(__uint_as_float(rb[buf][j4 + 0]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 0])) * sa_inv;
+        v.y = fmaf(__uint_as_float(rb[buf][j4 + 1]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 1])) * sa_inv;
+        v.z = fmaf(__uint_as_float(rb[buf][j4 + 2]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 2])) * sa_inv;
+        v.w = fmaf(__uint_as_float(rb[buf][j4 + 3]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 3])) * sa_inv;
         *reinterpret_cast<float4*>(tbuf + lane * H2_TPAD + j4) = v;
       }
       __syncwarp();
       const int n = n0 + c0 + c4;
-      float cs[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (n + j < g.N) {
-          if (g.b_row_inv) cs[j] = __ldg(g.b_row_inv + n + j);
-          if (!split) {
-            cs[j] *= g.alpha;
-            if (g.bias) bs[j] = __ldg(g.bias + n + j);
-          }
-        }
+      const float4 cs4 = *reinterpret_cast<const float4*>(cs_s + c0 + c4);
+      const float4 bs4 = *reinterpret_cast<const float4*>(bs_s + c0 + c4);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rl;
         const int mm = m0 + 32 * q + rr;
         const float4 t4 = *reinterpret_cast<const float4*>(tbuf + rr * H2_TPAD + c4);
-        float v[4] = {fmaf(t4.x, cs[0], bs[0]), fmaf(t4.y, cs[1], bs[1]), fmaf(t4.z, cs[2], bs[2]), fmaf(t4.w, cs[3], bs[3])};
+        float v[4] = {fmaf(t4.x, cs4.x, bs4.x), fmaf(t4.y, cs4.y, bs4.y), fmaf(t4.z, cs4.z, bs4.z), fmaf(t4.w, cs4.w, bs4.w)};
         if (mm < g.M && n < g.N) {
           float* cp = Cout + (size_t)mm * ldc + n;
           const int nv = min(4, g.N - n);
