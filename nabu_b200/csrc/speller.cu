@@ -113,8 +113,11 @@ struct AttnBwdArgs {
 constexpr int TT = 16;     // memory positions per dpre tile
 constexpr int MAXF = 16;   // max numfilt held in registers
 
-template <int NA>
-__global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArgs a) {
+// 512 threads per row.  TSPLIT = 2 (A <= 256): thread (unit c = tid % 256, half th = tid / 256) takes the tile's positions
+// of parity th in the score backward; TSPLIT = 1 (A <= 512): one unit per thread.
+template <int TSPLIT>
+__global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArgs a) {
+  constexpr int NT = 512, NW = NT / 32, NA = 1;
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.x;
@@ -138,26 +141,26 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
   float* dpre = wc + r4((size_t)ksz * F);  // [TT][A]
 
   if (!(a.u < a.tlen[r])) {
-    for (int i = tid; i < H; i += 256) a.dh_above[(size_t)r * H + i] = 0.f;
-    for (int i = tid; i < A; i += 256) a.dq_save[(size_t)r * A + i] = 0.f;
+    for (int i = tid; i < H; i += NT) a.dh_above[(size_t)r * H + i] = 0.f;
+    for (int i = tid; i < A; i += NT) a.dq_save[(size_t)r * A + i] = 0.f;
     return;
   }
   const int len = min(a.mem_len[r], Tm);
-  for (int i = tid; i < V; i += 256) dl[i] = a.dlogits[r * a.dl_row_stride + i];
-  for (int i = tid; i < H + E; i += 256) oin[i] = a.outin[r * a.outin_row_stride + i];
-  for (int i = tid; i < Tm; i += 256) al[i] = a.alpha[(size_t)r * Tm + i];
-  for (int i = tid; i < Tm + ksz; i += 256) {
+  for (int i = tid; i < V; i += NT) dl[i] = a.dlogits[r * a.dl_row_stride + i];
+  for (int i = tid; i < H + E; i += NT) oin[i] = a.outin[r * a.outin_row_stride + i];
+  for (int i = tid; i < Tm; i += NT) al[i] = a.alpha[(size_t)r * Tm + i];
+  for (int i = tid; i < Tm + ksz; i += NT) {
     const int t = i - padl;
     ap[i] = (F > 0 && t >= 0 && t < Tm) ? a.alpha_prev[(size_t)r * Tm + t] : 0.f;
   }
-  for (int i = tid; i < A; i += 256) qs[i] = a.q[(size_t)r * A + i];
-  for (int i = tid; i < Tm * F; i += 256) cf[i] = a.cf[(size_t)r * Tm * F + i];
-  for (int i = tid; i < F * A; i += 256) wd[i] = a.Wd[i];
-  for (int i = tid; i < ksz * F; i += 256) wc[i] = a.Wc[i];
+  for (int i = tid; i < A; i += NT) qs[i] = a.q[(size_t)r * A + i];
+  for (int i = tid; i < Tm * F; i += NT) cf[i] = a.cf[(size_t)r * Tm * F + i];
+  for (int i = tid; i < F * A; i += NT) wd[i] = a.Wd[i];
+  for (int i = tid; i < ksz * F; i += NT) wc[i] = a.Wc[i];
   __syncthreads();
 
   // phase A: d[h_top, ctx] = dlogits . Wo^T ; dctx += carry
-  for (int k = tid; k < H + E; k += 256) {
+  for (int k = tid; k < H + E; k += NT) {
     float s = 0.f;
     for (int vv = 0; vv < V; ++vv) s = fmaf(dl[vv], a.Wo[(size_t)k * V + vv], s);
     if (k < H) dquery[k] = s;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
   const float* values = a.values + (size_t)r * Tm * E;
   float* dvalues = a.dvalues + (size_t)r * Tm * E;
   const bool vecE = (E & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.values) | reinterpret_cast<uintptr_t>(a.dvalues)) & 15) == 0;
-  for (int t = warp; t < Tm; t += 8) {
+  for (int t = warp; t < Tm; t += NW) {
     float s = 0.f;
     if (t < len) {
       const float at = al[t];
@@ -207,9 +210,9 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
   __syncthreads();
   // phase C: softmax backward  de = alpha * (dalpha - sum alpha*dalpha)
   float part = 0.f;
-  for (int t = tid; t < Tm; t += 256) part += al[t] * dal[t];
+  for (int t = tid; t < Tm; t += NT) part += al[t] * dal[t];
   const float dot = block_reduce(part, red, false);
-  for (int t = tid; t < Tm; t += 256) dal[t] = al[t] * (dal[t] - dot);
+  for (int t = tid; t < Tm; t += NT) dal[t] = al[t] * (dal[t] - dot);
   __syncthreads();
   // phase D: score backward, tiles of TT memory positions; thread owns attention units tid + 256*i
   const float* keys = a.keys + (size_t)r * Tm * A;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
 #pragma unroll
   for (int i = 0; i < NA; ++i) {
     dq[i] = 0.f; dv[i] = 0.f;
-    const int c = tid + 256 * i;
+    const int c = TSPLIT == 2 ? (tid & 255) : tid;
     vreg[i] = c < A ? a.v[c] : 0.f;
 #pragma unroll
     for (int f = 0; f < MAXF; ++f) {
@@ -230,23 +233,26 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
     const int nt = min(TT, len - t0);
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
-      const int c = tid + 256 * i;
+      const int c = TSPLIT == 2 ? (tid & 255) : tid;
+      const int th = TSPLIT == 2 ? (tid >> 8) : 0;
       if (c < A && !(a.ablate & 4)) {
         // the tile's keys and dkeys accumulators are fetched up front (2*TT independent loads in flight per thread)
-        float kv[TT], dk[TT];
+        float kv[TT / TSPLIT], dk[TT / TSPLIT];
 #pragma unroll
-        for (int tt = 0; tt < TT; ++tt) {
-          kv[tt] = tt < nt ? __ldg(keys + (size_t)(t0 + tt) * A + c) : 0.f;
-          dk[tt] = tt < nt ? dkeys[(size_t)(t0 + tt) * A + c] : 0.f;
+        for (int j = 0; j < TT / TSPLIT; ++j) {
+          const int tt = j * TSPLIT + th;
+          kv[j] = tt < nt ? __ldg(keys + (size_t)(t0 + tt) * A + c) : 0.f;
+          dk[j] = tt < nt ? dkeys[(size_t)(t0 + tt) * A + c] : 0.f;
         }
 #pragma unroll
-        for (int tt = 0; tt < TT; ++tt) {
+        for (int j = 0; j < TT / TSPLIT; ++j) {
+          const int tt = j * TSPLIT + th;
           if (tt < nt) {
             const int t = t0 + tt;
             float cfr[MAXF];                         // location features of this position: one broadcast read each
 #pragma unroll
             for (int f = 0; f < MAXF; ++f) cfr[f] = f < F ? cf[t * F + f] : 0.f;
-            float pre = qs[c] + kv[tt];
+            float pre = qs[c] + kv[j];
 #pragma unroll
             for (int f = 0; f < MAXF; ++f) pre = fmaf(cfr[f], wdreg[i][f], pre);
             const float s = tanh_fast(pre);
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
             dv[i] = fmaf(de, s, dv[i]);
 #pragma unroll
             for (int f = 0; f < MAXF; ++f) dWd[i][f] = fmaf(cfr[f], dp, dWd[i][f]);
-            dkeys[(size_t)t * A + c] = dk[tt] + dp;
+            dkeys[(size_t)t * A + c] = dk[j] + dp;
             dpre[tt * A + c] = dp;
           }
         }
@@ -266,46 +272,47 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
     // dcf[t][f] = sum_c dpre[t][c] * Wd[f][c]: one warp per memory position, lanes stride the attention units (both
     // operands are then read at consecutive addresses; the (t, f)-per-thread mapping hit one bank with 10 lanes)
     if (!(a.ablate & 1))
-    for (int tt = warp; tt < nt; tt += 16) {           // positions tt and tt + 8 share every Wd read
-      const int t1 = tt + 8;
-      const bool two = t1 < nt;
-      float acc0[MAXF], acc1[MAXF];
+    for (int tt = warp; tt < nt; tt += NW) {
+      float acc0[MAXF];
 #pragma unroll
-      for (int f = 0; f < MAXF; ++f) acc0[f] = acc1[f] = 0.f;
+      for (int f = 0; f < MAXF; ++f) acc0[f] = 0.f;
       for (int c = lane; c < A; c += 32) {
         const float d0 = dpre[tt * A + c];
-        const float d1 = two ? dpre[t1 * A + c] : 0.f;
 #pragma unroll
         for (int f = 0; f < MAXF; ++f)
-          if (f < F) {
-            const float wv = wd[f * A + c];
-            acc0[f] = fmaf(d0, wv, acc0[f]);
-            acc1[f] = fmaf(d1, wv, acc1[f]);
-          }
+          if (f < F) acc0[f] = fmaf(d0, wd[f * A + c], acc0[f]);
       }
 #pragma unroll
       for (int f = 0; f < MAXF; ++f)
         if (f < F) {
-          const float s0 = warp_sum(acc0[f]), s1 = warp_sum(acc1[f]);
-          if (lane == 0) {
-            dcf[(t0 + tt) * F + f] = s0;
-            if (two) dcf[(t0 + t1) * F + f] = s1;
-          }
+          const float s0 = warp_sum(acc0[f]);
+          if (lane == 0) dcf[(t0 + tt) * F + f] = s0;
         }
     }
     __syncthreads();
   }
-  for (int i = tid; i < (Tm - len) * F; i += 256) dcf[len * F + i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    const int c = tid + 256 * i;
-    if (c < A) {
-      dqs[c] = dq[i];
-      a.dq_save[(size_t)r * A + c] = dq[i];
-      a.dv_part[(size_t)r * A + c] += dv[i];
+  for (int i = tid; i < (Tm - len) * F; i += NT) dcf[len * F + i] = 0.f;
+  {
+    const int c = TSPLIT == 2 ? (tid & 255) : tid;
+    const int th = TSPLIT == 2 ? (tid >> 8) : 0;
+    // the upper half hands its partial sums to the lower half through the dpre scratch ([2 + F][A] <= [TT][A] floats)
+    if (TSPLIT == 2 && th == 1 && c < A) {
+      dpre[c] = dq[0];
+      dpre[A + c] = dv[0];
 #pragma unroll
       for (int f = 0; f < MAXF; ++f)
-        if (f < F) a.dWd_part[((size_t)r * F + f) * A + c] += dWd[i][f];
+        if (f < F) dpre[(2 + f) * A + c] = dWd[0][f];
+    }
+    __syncthreads();
+    if (th == 0 && c < A) {
+      float q0 = dq[0], v0 = dv[0];
+      if (TSPLIT == 2) { q0 += dpre[c]; v0 += dpre[A + c]; }
+      dqs[c] = q0;
+      a.dq_save[(size_t)r * A + c] = q0;
+      a.dv_part[(size_t)r * A + c] += v0;
+#pragma unroll
+      for (int f = 0; f < MAXF; ++f)
+        if (f < F) a.dWd_part[((size_t)r * F + f) * A + c] += dWd[0][f] + (TSPLIT == 2 ? dpre[(2 + f) * A + c] : 0.f);
     }
   }
   __syncthreads();
@@ -314,10 +321,11 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
     // dalign_prev[tau] = sum_{k,f} dcf[tau - k + padl][f] * Wc[k][f]
     // (the taps are split over the two halves of the block; partial sums meet in the dpre scratch)
     {
-      const bool split2 = 2 * Tm <= TT * A;             // room for both halves' partial sums in the scratch
-      const int half = split2 ? tid >> 7 : 0, kh = split2 ? (ksz + 1) / 2 : ksz;
+      constexpr int NG = NT / 128;                      // tap groups
+      const bool split2 = NG * Tm <= TT * A;            // room for every group's partial sums in the scratch
+      const int half = split2 ? tid >> 7 : 0, kh = split2 ? (ksz + NG - 1) / NG : ksz;
       const int k0 = half * kh, k1 = min(ksz, k0 + kh);
-      for (int tau = split2 ? (tid & 127) : tid; tau < Tm; tau += split2 ? 128 : 256) {
+      for (int tau = split2 ? (tid & 127) : tid; tau < Tm; tau += split2 ? 128 : NT) {
         float s = 0.f;
         for (int k = k0; k < k1; ++k) {
           const int t = tau - k + padl;
@@ -340,31 +348,36 @@ __global__ void __launch_bounds__(256) dec_attn_bwd_step_kernel(const AttnBwdArg
       }
       __syncthreads();
       if (split2)
-        for (int tau = tid; tau < Tm; tau += 256) a.dalign_carry[(size_t)r * Tm + tau] = dpre[tau] + dpre[Tm + tau];
+        for (int tau = tid; tau < Tm; tau += NT) {
+          float s = 0.f;
+#pragma unroll
+          for (int gq = 0; gq < NG; ++gq) s += dpre[gq * Tm + tau];
+          a.dalign_carry[(size_t)r * Tm + tau] = s;
+        }
     }
     // dWc[k][f] += sum_t alpha_prev[t + k - padl] * dcf[t][f]
-    for (int i = tid; i < ksz * F; i += 256) {
+    for (int i = tid; i < ksz * F; i += NT) {
       const int k = i / F, f = i % F;
       float s = 0.f;
       for (int t = 0; t < Tm; ++t) s = fmaf(ap[t + k], dcf[t * F + f], s);
       a.dWc_part[(size_t)r * ksz * F + i] += s;
     }
   } else {
-    for (int tau = tid; tau < Tm; tau += 256) a.dalign_carry[(size_t)r * Tm + tau] = 0.f;
+    for (int tau = tid; tau < Tm; tau += NT) a.dalign_carry[(size_t)r * Tm + tau] = 0.f;
   }
   // phase F: dh_top = dquery_part + dq . Wq^T   (warp per output unit, lanes over A)
-  for (int k = warp; k < H; k += 32) {                   // 4 output units per warp iteration: independent load chains
+  for (int k = warp; k < H; k += 4 * NW) {               // 4 output units per warp iteration: independent load chains
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = lane; c < A; c += 32) {
       const float dqc = dqs[c];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k + 8 * j < H) s[j] = fmaf(dqc, __ldg(a.Wq + (size_t)(k + 8 * j) * A + c), s[j]);
+        if (k + NW * j < H) s[j] = fmaf(dqc, __ldg(a.Wq + (size_t)(k + NW * j) * A + c), s[j]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float t = warp_sum(s[j]);
-      if (lane == 0 && k + 8 * j < H) a.dh_above[(size_t)r * H + k + 8 * j] = dquery[k + 8 * j] + t;
+      if (lane == 0 && k + NW * j < H) a.dh_above[(size_t)r * H + k + NW * j] = dquery[k + NW * j] + t;
     }
   }
 }
@@ -601,7 +614,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
 
   const size_t smem_attn = attn_bwd_smem(Tm, E, H, A, V, F, ksz);
   NABU_REQUIRE(smem_attn <= (size_t)max_smem_optin(), "speller_bwd: memory too long for the attention kernel (Tm=%d)", Tm);
-  const void* attn_fn = A <= 256 ? (const void*)dec_attn_bwd_step_kernel<1> : (const void*)dec_attn_bwd_step_kernel<2>;
+  const void* attn_fn = A <= 256 ? (const void*)dec_attn_bwd_step_kernel<2> : (const void*)dec_attn_bwd_step_kernel<1>;
   if (smem_attn > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(attn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn));
   const size_t smem_mm = ((size_t)H4 * 8 + 4 * ROWS * 8) * sizeof(float);
@@ -624,8 +637,8 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
     {
       a.ablate = getenv("NABU_ATTN_ABLATE") ? atoi(getenv("NABU_ATTN_ABLATE")) : 0;
       KernelScope ks("dec_attn_bwd_step", stream);
-      if (A <= 256) dec_attn_bwd_step_kernel<1><<<B, 256, smem_attn, stream>>>(a);
-      else dec_attn_bwd_step_kernel<2><<<B, 256, smem_attn, stream>>>(a);
+      if (A <= 256) dec_attn_bwd_step_kernel<2><<<B, 512, smem_attn, stream>>>(a);
+      else dec_attn_bwd_step_kernel<1><<<B, 512, smem_attn, stream>>>(a);
       NABU_CHECK_LAUNCH();
     }
     for (int l = NL - 1; l >= 0; --l) {
