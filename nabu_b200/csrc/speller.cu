@@ -518,7 +518,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
   if (smem > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelScope ks("dec_attn_step", stream);
-  dec_attn_step_kernel<<<R, 256, smem, stream>>>(a);
+  dec_attn_step_kernel<<<R, 512, smem, stream>>>(a);
   NABU_CHECK_LAUNCH();
   return 0;
 }

@@ -145,7 +145,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
-__global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a) {
+__global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a) {
+  constexpr int NT = 512, NW = NT / 32;                // 512 threads per decoder row
   extern __shared__ __align__(16) float sm[];
   if (a.done && *a.done) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,41 +161,41 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
   float* e = ap + r4(Tm + ksz);            // [Tm]
   float* ctx = e + r4(Tm);                 // [E]
   float* red = ctx + r4(E);                // [32]
-  float* part = red + 32;                  // [8][32] projection partials
-  float* cf = part + 256;                  // [Tm][F]
+  float* part = red + 32;                  // [NW][32] projection partials
+  float* cf = part + NW * 32;              // [Tm][F]
   float* wd = cf + r4((size_t)Tm * F);     // [F][A]
   float* wc = wd + r4((size_t)F * A);      // [ksz][F]
   float* vs = wc + r4((size_t)ksz * F);    // [A] attention vector
-  float* cpart = vs + r4(A);               // [1024] context partials of the t-splits
+  float* cpart = vs + r4(A);               // [NT * 4] context partials of the t-splits
 
   const bool active = (a.tlen == nullptr) || (a.u < a.tlen[r]);
   if (!active) {                           // finished row: copy the state through, emit zeros
-    for (int t = tid; t < Tm; t += 256) a.align_new[(size_t)r * Tm + t] = a.align_prev[(size_t)r * Tm + t];
-    for (int i = tid; i < E; i += 256) {
+    for (int t = tid; t < Tm; t += NT) a.align_new[(size_t)r * Tm + t] = a.align_prev[(size_t)r * Tm + t];
+    for (int i = tid; i < E; i += NT) {
       const float c = a.ctx_prev[(size_t)r * E + i];
       a.ctx_new[(size_t)r * E + i] = c;
       a.ctxT_new[(size_t)i * a.R + r] = c;
     }
-    for (int k = tid; k < V; k += 256) a.logits[r * a.logits_row_stride + k] = 0.f;
-    if (a.q_save) for (int i = tid; i < A; i += 256) a.q_save[(size_t)r * A + i] = 0.f;
-    if (a.cf_save) for (int i = tid; i < Tm * F; i += 256) a.cf_save[(size_t)r * Tm * F + i] = 0.f;
-    if (a.outin_save) for (int i = tid; i < H + E; i += 256) a.outin_save[r * a.outin_row_stride + i] = 0.f;
+    for (int k = tid; k < V; k += NT) a.logits[r * a.logits_row_stride + k] = 0.f;
+    if (a.q_save) for (int i = tid; i < A; i += NT) a.q_save[(size_t)r * A + i] = 0.f;
+    if (a.cf_save) for (int i = tid; i < Tm * F; i += NT) a.cf_save[(size_t)r * Tm * F + i] = 0.f;
+    if (a.outin_save) for (int i = tid; i < H + E; i += NT) a.outin_save[r * a.outin_row_stride + i] = 0.f;
     return;
   }
   const int len = min(a.mem_len[mrow], Tm);
 
-  for (int i = tid; i < H; i += 256) query[i] = a.h_top[(size_t)r * H + i];
-  for (int i = tid; i < Tm + ksz; i += 256) {
+  for (int i = tid; i < H; i += NT) query[i] = a.h_top[(size_t)r * H + i];
+  for (int i = tid; i < Tm + ksz; i += NT) {
     const int t = i - padl;
     ap[i] = (F > 0 && t >= 0 && t < Tm) ? a.align_prev[(size_t)r * Tm + t] : 0.f;
   }
-  for (int i = tid; i < F * A; i += 256) wd[i] = a.Wd[i];
-  for (int i = tid; i < ksz * F; i += 256) wc[i] = a.Wc[i];
-  for (int i = tid; i < A; i += 256) vs[i] = a.v[i];
+  for (int i = tid; i < F * A; i += NT) wd[i] = a.Wd[i];
+  for (int i = tid; i < ksz * F; i += NT) wc[i] = a.Wc[i];
+  for (int i = tid; i < A; i += NT) vs[i] = a.v[i];
   __syncthreads();
 
   // phase 0: q = query . Wq
-  for (int c = tid; c < A; c += 256) {
+  for (int c = tid; c < A; c += NT) {
     // four independent chains, 16 weight loads in flight per thread (the loop is bound by L2 latency, not by FMAs)
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int k = 0;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
     if (a.q_save) a.q_save[(size_t)r * A + c] = s;
   }
   // phase 1: location features cf[t][f] = sum_k alpha_prev[t + k - padl] * Wc[k][f]
-  for (int i = tid; i < Tm * F; i += 256) {
+  for (int i = tid; i < Tm * F; i += NT) {
     const int t = i / F, f = i % F;
     float s = 0.f;
     for (int k = 0; k < ksz; ++k) s = fmaf(ap[t + k], wc[k * F + f], s);
@@ -224,8 +225,8 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
   const float* keys = a.keys + (size_t)mrow * Tm * A;
   const bool vec4 = ((A | E) & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.keys) | reinterpret_cast<uintptr_t>(a.values)) & 15) == 0;
   if (vec4) {
-    for (int t = warp; t < Tm; t += 16) {
-      const int t1 = t + 8;
+    for (int t = warp; t < Tm; t += 2 * NW) {
+      const int t1 = t + NW;
       float sa = 0.f, sb = 0.f;
       for (int c = lane * 4; c < A; c += 128) {
         float4 ka = make_float4(0.f, 0.f, 0.f, 0.f), kb = ka;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
       }
     }
   } else {
-    for (int t = warp; t < Tm; t += 8) {
+    for (int t = warp; t < Tm; t += NW) {
       float s = 0.f;
       if (t < len) {
         for (int c = lane; c < A; c += 32) {
@@ -268,17 +269,17 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
   __syncthreads();
   // phase 3: softmax over the memory positions
   float mx = -CUDART_INF_F;
-  for (int t = tid; t < Tm; t += 256) mx = fmaxf(mx, e[t]);
+  for (int t = tid; t < Tm; t += NT) mx = fmaxf(mx, e[t]);
   mx = block_reduce(mx, red, true);
   float sum = 0.f;
-  for (int t = tid; t < Tm; t += 256) {
+  for (int t = tid; t < Tm; t += NT) {
     const float p = (t < len) ? expf(e[t] - mx) : 0.f;
     e[t] = p;
     sum += p;
   }
   sum = block_reduce(sum, red, false);
   const float inv = 1.f / sum;
-  for (int t = tid; t < Tm; t += 256) {
+  for (int t = tid; t < Tm; t += NT) {
     const float p = e[t] * inv;
     e[t] = p;
     a.align_new[(size_t)r * Tm + t] = p;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
   const float* values = a.values + (size_t)mrow * Tm * E;
   if (vec4 && E <= 1024) {
     const int NC4 = E >> 2;
-    const int TS = 256 / NC4 > 0 ? 256 / NC4 : 1;          // E <= 1024 -> NC4 <= 256
+    const int TS = NT / NC4 > 0 ? NT / NC4 : 1;            // E <= 1024 -> NC4 <= 256
     const int cg = tid % NC4, ts = tid / NC4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ts < TS) {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
       *reinterpret_cast<float4*>(cpart + (size_t)tid * 4) = acc;
     }
     __syncthreads();
-    for (int i = tid; i < E; i += 256) {
+    for (int i = tid; i < E; i += NT) {
       float s = 0.f;
       for (int k = 0; k < TS; ++k) s += cpart[(size_t)(k * NC4 + (i >> 2)) * 4 + (i & 3)];
       ctx[i] = s;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
       a.ctxT_new[(size_t)i * a.R + r] = s;
     }
   } else {
-    for (int i = tid; i < E; i += 256) {
+    for (int i = tid; i < E; i += NT) {
       float s = 0.f;
       for (int t = 0; t < len; ++t) s = fmaf(e[t], values[(size_t)t * E + i], s);
       ctx[i] = s;
@@ -333,8 +334,8 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
   __syncthreads();
   if (a.outin_save) {
     float* o = a.outin_save + r * a.outin_row_stride;
-    for (int i = tid; i < H; i += 256) o[i] = query[i];
-    for (int i = tid; i < E; i += 256) o[H + i] = ctx[i];
+    for (int i = tid; i < H; i += NT) o[i] = query[i];
+    for (int i = tid; i < E; i += NT) o[H + i] = ctx[i];
   }
   // phase 5: logits = [query, ctx] . Wo + bo ; thread (vcol = lane, kchunk = warp)
   for (int v0 = 0; v0 < V; v0 += 32) {
@@ -344,25 +345,25 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
       float s1 = 0.f;
       int k = warp;
 #pragma unroll 4
-      for (; k + 8 < H; k += 16) {
+      for (; k + NW < H; k += 2 * NW) {
         s = fmaf(query[k], __ldg(a.Wo + (size_t)k * V + vc), s);
-        s1 = fmaf(query[k + 8], __ldg(a.Wo + (size_t)(k + 8) * V + vc), s1);
+        s1 = fmaf(query[k + NW], __ldg(a.Wo + (size_t)(k + NW) * V + vc), s1);
       }
-      for (; k < H; k += 8) s = fmaf(query[k], __ldg(a.Wo + (size_t)k * V + vc), s);
+      for (; k < H; k += NW) s = fmaf(query[k], __ldg(a.Wo + (size_t)k * V + vc), s);
       k = warp;
 #pragma unroll 4
-      for (; k + 8 < E; k += 16) {
+      for (; k + NW < E; k += 2 * NW) {
         s = fmaf(ctx[k], __ldg(a.Wo + (size_t)(H + k) * V + vc), s);
-        s1 = fmaf(ctx[k + 8], __ldg(a.Wo + (size_t)(H + k + 8) * V + vc), s1);
+        s1 = fmaf(ctx[k + NW], __ldg(a.Wo + (size_t)(H + k + NW) * V + vc), s1);
       }
-      for (; k < E; k += 8) s = fmaf(ctx[k], __ldg(a.Wo + (size_t)(H + k) * V + vc), s);
+      for (; k < E; k += NW) s = fmaf(ctx[k], __ldg(a.Wo + (size_t)(H + k) * V + vc), s);
       s += s1;
     }
     part[warp * 32 + lane] = s;
     __syncthreads();
     if (warp == 0 && vc < V) {
       float t = a.bo[vc];
-      for (int w = 0; w < 8; ++w) t += part[w * 32 + lane];
+      for (int w = 0; w < NW; ++w) t += part[w * 32 + lane];
       a.logits[r * a.logits_row_stride + vc] = t / a.temperature;
     }
     __syncthreads();
@@ -372,8 +373,8 @@ __global__ void __launch_bounds__(256) dec_attn_step_kernel(const AttnStepArgs a
 inline size_t attn_step_smem(int Tm, int E, int H, int A, int F, int ksz) {
   // the arrays read with 128-bit accesses (q, wd, vs, cpart) must start on 16-byte boundaries: round every piece up to 4
   auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
-  return (r4(H) + r4(A) + r4(Tm + ksz) + r4(Tm) + r4(E) + 32 + 256 + r4((size_t)Tm * F) + r4((size_t)F * A) +
-          r4((size_t)ksz * F) + r4(A) + 1024) * sizeof(float);
+  return (r4(H) + r4(A) + r4(Tm + ksz) + r4(Tm) + r4(E) + 32 + 512 + r4((size_t)Tm * F) + r4((size_t)F * A) +
+          r4((size_t)ksz * F) + r4(A) + 2048) * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------------------------
