@@ -492,7 +492,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
     a.c_new = c_new[l]; a.h_new = h_new[l]; a.hT_new = hT_new[l];
     a.gates_out = gates_out ? gates_out[l] : nullptr;
     a.tlen = tlen; a.u = u; a.done = done;
-    const size_t smem = ((size_t)(a.K0 + a.K1) * 8 + 4 * ROWS * 8) * sizeof(float);
+    const size_t smem = ((size_t)(a.K0 + a.K1) * 8 + SK_KSPLIT * ROWS * 8) * sizeof(float);
     NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: LSTM input too wide for the step kernel");
     if (smem > 48 * 1024)
       NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -617,7 +617,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
   const void* attn_fn = A <= 256 ? (const void*)dec_attn_bwd_step_kernel<2> : (const void*)dec_attn_bwd_step_kernel<1>;
   if (smem_attn > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(attn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn));
-  const size_t smem_mm = ((size_t)H4 * 8 + 4 * ROWS * 8) * sizeof(float);
+  const size_t smem_mm = ((size_t)H4 * 8 + MT_KSPLIT * ROWS * 8) * sizeof(float);
   NABU_REQUIRE(smem_mm <= (size_t)max_smem_optin(), "speller_bwd: num_units too large");
   if (smem_mm > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_matmul_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mm));
@@ -654,7 +654,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
       if (l > 0) { m.row0 = 0; m.N = 2 * H; m.N0 = H; m.out0 = w.dh_above; m.ld0 = H; m.out1 = w.dh_carry[l]; m.ld1 = H; }
       else { m.row0 = V; m.N = E + H; m.N0 = E; m.out0 = w.dctx_carry; m.ld0 = E; m.out1 = w.dh_carry[0]; m.ld1 = H; }
       KernelScope ks("dec_matmul_t", stream);
-      dec_matmul_t_kernel<<<dim3(ceil_div(m.N, 8), ceil_div(B, ROWS)), SK_THREADS, smem_mm, stream>>>(m);
+      dec_matmul_t_kernel<<<dim3(ceil_div(m.N, 8), ceil_div(B, ROWS)), MT_THREADS, smem_mm, stream>>>(m);
       NABU_CHECK_LAUNCH();
     }
   }

@@ -19,11 +19,14 @@ namespace nabu {
 namespace dec {
 
 constexpr int ROWS = 64;       // decoder rows per CTA tile in the skinny matmuls
-constexpr int SK_THREADS = 256;
+constexpr int SK_THREADS = 512;
+constexpr int SK_KSPLIT = SK_THREADS / ROWS;   // k-split of the LSTM step (8 partial sums per output)
+constexpr int MT_THREADS = 256;                // dec_matmul_t: measured slower with 512 threads (8.0 vs 5.6 ms per LAS step)
+constexpr int MT_KSPLIT = MT_THREADS / ROWS;
 
 // ------------------------------------------------------------------------------------------------
 // LSTM cell step.  grid = (H/2, ceil(R/ROWS)); CTA (slice, tile) owns hidden units 2*slice,
-// 2*slice+1 (8 gate columns) for ROWS rows; 4-way k-split over the 256 threads.
+// 2*slice+1 (8 gate columns) for ROWS rows; SK_KSPLIT-way k-split over the SK_THREADS threads.
 // ------------------------------------------------------------------------------------------------
 struct LstmStepArgs {
   const float* inT0; int K0; int w0;      // transposed input segment 0 [K0][R], first weight row w0
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
   if (a.done && *a.done) return;
   const int Ktot = a.K0 + a.K1;
   float* Ws = sm;                          // [Ktot][8]
-  float* red = sm + (size_t)Ktot * 8;      // [4][ROWS][8]
+  float* red = sm + (size_t)Ktot * 8;      // [SK_KSPLIT][ROWS][8]
   const int tid = threadIdx.x;
   const int H = a.H, H4 = 4 * a.H, R = a.R;
   const int j0 = blockIdx.x * 2;
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (r < R) {
 #pragma unroll 16
-    for (int k = ks; k < a.K0; k += 4) {
+    for (int k = ks; k < a.K0; k += SK_KSPLIT) {
       const float x = __ldcg(a.inT0 + (size_t)k * R + r);
       const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * 8 + 4);
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
       acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
     }
 #pragma unroll 16
-    for (int k = ks; k < a.K1; k += 4) {
+    for (int k = ks; k < a.K1; k += SK_KSPLIT) {
       const float x = __ldcg(a.inT1 + (size_t)k * R + r);
       const float* wp = Ws + (a.K0 + k) * 8;
       const float4 w0 = *reinterpret_cast<const float4*>(wp);
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
       for (int g = 0; g < 4; ++g) {
         float s = a.bias[g * H + j];
 #pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2) s += red[(k2 * ROWS + rl2) * 8 + g * 2 + jl];
+        for (int k2 = 0; k2 < SK_KSPLIT; ++k2) s += red[(k2 * ROWS + rl2) * 8 + g * 2 + jl];
         if (a.ids) s += a.W[(size_t)a.ids[r2] * H4 + g * H + j];
         z[g] = s;
       }
@@ -388,13 +391,13 @@ struct MatmulTArgs {
   float* out0; int ld0; float* out1; int ld1;
 };
 
-__global__ void __launch_bounds__(SK_THREADS) dec_matmul_t_kernel(const MatmulTArgs a) {
+__global__ void __launch_bounds__(MT_THREADS) dec_matmul_t_kernel(const MatmulTArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                          // [K][8]
-  float* red = sm + (size_t)a.K * 8;       // [4][ROWS][8]
+  float* red = sm + (size_t)a.K * 8;       // [MT_KSPLIT][ROWS][8]
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * 8, r0 = blockIdx.y * ROWS;
-  for (int i = tid; i < a.K * 8; i += SK_THREADS) {
+  for (int i = tid; i < a.K * 8; i += MT_THREADS) {
     const int c = i / a.K, k = i % a.K;    // k fastest: coalesced rows of W
     const int n = n0 + c;
     Ws[k * 8 + c] = (n < a.N) ? a.W[(size_t)(a.row0 + n) * a.ldw + k] : 0.f;
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(SK_THREADS) dec_matmul_t_kernel(const MatmulTA
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (r < a.R) {
 #pragma unroll 16
-    for (int k = ks; k < a.K; k += 4) {
+    for (int k = ks; k < a.K; k += MT_KSPLIT) {
       const float x = __ldcg(a.xT + (size_t)k * a.R + r);
       const float4 w0 = *reinterpret_cast<const float4*>(Ws + k * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(Ws + k * 8 + 4);
@@ -417,12 +420,12 @@ __global__ void __launch_bounds__(SK_THREADS) dec_matmul_t_kernel(const MatmulTA
 #pragma unroll
   for (int c = 0; c < 8; ++c) red[(ks * ROWS + rl) * 8 + c] = acc[c];
   __syncthreads();
-  for (int i = tid; i < ROWS * 8; i += SK_THREADS) {
+  for (int i = tid; i < ROWS * 8; i += MT_THREADS) {
     const int rl2 = i / 8, c = i % 8, r2 = r0 + rl2, n = n0 + c;
     if (r2 < a.R && n < a.N) {
       float s = 0.f;
 #pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) s += red[(k2 * ROWS + rl2) * 8 + c];
+      for (int k2 = 0; k2 < MT_KSPLIT; ++k2) s += red[(k2 * ROWS + rl2) * 8 + c];
       if (n < a.N0) a.out0[(size_t)r2 * a.ld0 + n] = s;
       else a.out1[(size_t)r2 * a.ld1 + (n - a.N0)] = s;
     }
