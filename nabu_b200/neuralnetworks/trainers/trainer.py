@@ -20,11 +20,64 @@ from ..models.model import Model
 from . import loss_functions
 
 
+class ValidationController(object):
+    """The chief's validation / early-stopping branch of Trainer.train (reference: trainers/trainer.py:189-265 for the
+    state, 646-733 for the control flow) -- SURVEY.md section 8 row f2.
+
+    State = the reference's graph variables: `validated_step` (initialised to -valid_frequency), `best_validation`
+    (1.79e308) and the Python-side `num_tries`.  `save` / `restore` are the ValidationSaveHook's (hooks.py:54-86): the
+    reference checkpoints ALL global variables, so a restore also winds back global_step, learning_rate_fact,
+    validated_step and best_validation -- the callbacks given here must do the same.
+    """
+
+    def __init__(self, conf, save, restore, half_lr):
+        self.valid_frequency = int(conf['valid_frequency'])
+        self.valid_adapt = conf['valid_adapt'] == 'True'
+        self.go_back = conf['go_back'] == 'True'
+        self.max_tries = None if conf['num_tries'] == 'None' else int(conf['num_tries'])
+        self.reset_tries = conf['reset_tries'] == 'True'
+        self.validated_step = -self.valid_frequency
+        self.best_validation = 1.79e+308
+        self.num_tries = 0
+        self._save, self._restore, self._half_lr = save, restore, half_lr
+
+    def should_validate(self, global_step):
+        return global_step - self.validated_step >= self.valid_frequency          # trainer.py:204-206
+
+    def state(self):
+        return {'validated_step': self.validated_step, 'best_validation': self.best_validation}
+
+    def load_state(self, st):
+        self.validated_step, self.best_validation = st['validated_step'], st['best_validation']
+
+    def update(self, validation_loss, global_step):
+        """Fold one validation result in.  Returns 'terminate' or 'continue' (trainer.py:680-733)."""
+        if validation_loss >= self.best_validation:                               # worse (or equal)
+            if self.max_tries is not None and self.num_tries == self.max_tries:
+                self._restore()
+                return 'terminate'
+            self.num_tries += 1
+            if self.go_back:
+                self._restore()
+            else:
+                self.validated_step = global_step
+            if self.valid_adapt:
+                self._half_lr()
+                self._save()
+        else:
+            if self.reset_tries:
+                self.num_tries = 0
+            self.validated_step = global_step
+            self.best_validation = validation_loss
+            self._save()
+        return 'continue'
+
+
 class Trainer(object, metaclass=ABCMeta):
     """Trainer(conf, dataconf, modelconf, evaluatorconf, expdir, server, task_index)."""
 
     def __init__(self, conf, dataconf, modelconf, evaluatorconf, expdir, server=None, task_index=0,
-                 batch_source=None, device=None, seed=0):
+                 batch_source=None, device=None, seed=0, val_source=None):
         self.conf = dict(conf.items('trainer'))
         apply_defaults(self.conf, os.path.join(os.path.dirname(os.path.realpath(__file__)), 'defaults',
                                                type(self).__name__.lower() + '.cfg'))
@@ -37,6 +90,7 @@ class Trainer(object, metaclass=ABCMeta):
         self.model = Model(conf=modelconf, trainlabels=int(self.conf['trainlabels']), constraint=None, seed=seed)
         self.loss_fn = loss_functions.factory(self.conf['loss'])
         self.batch_source = batch_source
+        self.val_source = val_source
         self.device = torch.device(device if device is not None else 'cuda')
         self.global_step = 0
         self.learning_rate_fact = 1.0
@@ -81,10 +135,31 @@ class Trainer(object, metaclass=ABCMeta):
         self.model.build(src.input_dims, self.device)
         if testing:
             return
-        while self.global_step < self.num_steps:
+        # validation (trainer.py:189-265, 646-733): evaluator named in the evaluator cfg, run by the chief every
+        # valid_frequency steps on `val_source`
+        evaluator, controller = None, None
+        if (self.evaluatorconf is not None and self.val_source is not None
+                and self.evaluatorconf.get('evaluator', 'evaluator') != 'None'):
+            from ..evaluators import evaluator_factory
+            evaluator = evaluator_factory.factory(self.evaluatorconf.get('evaluator', 'evaluator'))(
+                self.evaluatorconf, self.dataconf, self.model, batch_source=self.val_source)
+            controller = ValidationController(self.conf, self._save_validated, self._restore_validated, self._half_lr)
+            self._controller = controller
+        terminated = False
+        while self.global_step < self.num_steps and not terminated:
             for batch in src:
                 if self.global_step >= self.num_steps:
                     break
+                if controller is not None and controller.should_validate(self.global_step):
+                    print('WORKER %d: validating model' % self.task_index)
+                    validation_loss, _ = evaluator.evaluate()
+                    print('WORKER %d: validation loss: %f' % (self.task_index, validation_loss))
+                    if validation_loss >= controller.best_validation:
+                        print('WORKER %d: validation loss is worse' % self.task_index)
+                    if controller.update(validation_loss, self.global_step) == 'terminate':
+                        print('WORKER %d: terminating training' % self.task_index)
+                        terminated = True
+                        break
                 start = time.time()
                 loss, lr = self.update(*batch)
                 loss_v = float(loss)          # the reference fetches the loss every step as well
@@ -98,6 +173,26 @@ class Trainer(object, metaclass=ABCMeta):
         if self.expdir and self.task_index == 0:
             os.makedirs(os.path.join(self.expdir, 'model'), exist_ok=True)
             torch.save(self.model.store.state_dict(), os.path.join(self.expdir, 'model', 'network.pt'))
+
+    # ---- ValidationSaveHook (hooks.py:54-86): every global variable, in memory -----------------------
+    def _save_validated(self):
+        st = self.model.store
+        self._validated = {'theta': st.theta.clone(), 'm': st.m.clone(), 'v': st.v.clone(),
+                           'global_step': self.global_step, 'learning_rate_fact': self.learning_rate_fact,
+                           'controller': self._controller.state()}
+
+    def _restore_validated(self):
+        snap = getattr(self, '_validated', None)
+        if snap is None:          # the reference would fail to find validated.ckpt; nothing was ever better
+            return
+        st = self.model.store
+        st.theta.copy_(snap['theta']); st.m.copy_(snap['m']); st.v.copy_(snap['v'])
+        self.global_step = snap['global_step']
+        self.learning_rate_fact = snap['learning_rate_fact']
+        self._controller.load_state(snap['controller'])
+
+    def _half_lr(self):
+        self.learning_rate_fact = self.learning_rate_fact / 2.0
 
     @abstractmethod
     def aditional_loss(self):

@@ -127,3 +127,51 @@ def test_deferred_weight_gradients_change_nothing():
     assert results[0][0] == results[1][0]
     for k in results[0][1]:
         assert np.array_equal(results[0][1][k], results[1][1][k]), k
+
+
+def test_loss_evaluator_and_validation_in_train_loop(capsys):
+    """Row f2: LossEvaluator's utterance-weighted validation loss against the oracle, and Trainer.train running the
+    validation controller (valid_frequency, early stop after num_tries worse results)."""
+    from nabu_b200.neuralnetworks.evaluators import evaluator_factory
+    dev = torch.device('cuda', 0)
+    D, H, NL, V = 40, 64, 2, 29
+    tr = _ctc_trainer(H, NL, V, dev, seed=2)
+    tr.model.build({'features': D}, dev)
+
+    def batch(B, T, seed):
+        x, lens, labels, ll = synthetic_ctc_batch(B, T, D, V, ragged=True, seed=seed)
+        return (({'features': torch.from_numpy(x).to(dev)}, {'features': torch.from_numpy(lens).to(dev)},
+                 {'text': torch.from_numpy(labels).to(dev)}, {'text': torch.from_numpy(ll).to(dev)}), (x, lens, labels, ll))
+
+    val = [batch(4, 30, 1), batch(7, 24, 2), batch(3, 36, 3)]
+    econf = make_conf('[evaluator]\nevaluator = loss_evaluator\nloss = CTC\ntargets = text\nbatch_size = 4\nfeatures = devfbank\n'
+                      'text = devtext\n')
+    ev = evaluator_factory.factory('loss_evaluator')(econf, None, tr.model, batch_source=[b[0] for b in val])
+    got, n = ev.evaluate()
+    params = tr.model.store.to_numpy()
+    layers = _dblstm_layers(params, NL)
+    lin = {'weights': params['DNNDecoder/text/outlayer/weights'], 'biases': params['DNNDecoder/text/outlayer/biases']}
+    tot, cnt = 0.0, 0
+    for _, (x, lens, labels, ll) in val:
+        enc, _, _ = O.dblstm_fwd(x, lens, layers)
+        l, _ = O.ctc_loss_mean(O.linear_fwd(enc, lin), lens, labels, ll)
+        tot += l * x.shape[0]
+        cnt += x.shape[0]
+    assert n == 3 and abs(got - tot / cnt) / (tot / cnt) < TOL
+
+    # the train loop: validate every 2 steps; a validation set that never improves stops training after num_tries
+    class Src(list):
+        input_dims = {'features': D}
+    tconf = make_conf('[trainer]\ntrainer = standard\nloss = CTC\ntrainlabels = 1\ntargets = text\nnum_epochs = 50\n'
+                      'valid_frequency = 2\nnum_tries = 1\ninitial_learning_rate = 0\n')
+    from nabu_b200.neuralnetworks.trainers import trainer_factory
+    mconf = make_conf('[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = dblstm\nnum_units = %d\n'
+                      'num_layers = %d\ninput_noise = 0\ndropout = 1\n[decoder]\ndecoder = dnn_decoder\nnum_layers = 0\n'
+                      % (V - 1, H, NL))
+    tr2 = trainer_factory.factory('standard')(tconf, None, mconf, econf, None, None, 0, device=dev, seed=2,
+                                              batch_source=Src([val[0][0], val[1][0]]), val_source=[b[0] for b in val])
+    tr2.train()
+    out = capsys.readouterr().out
+    # lr = 0: the validation loss repeats -> step 0 better (saved), step 2 worse (try 1), step 4 worse -> terminate
+    assert out.count('validating model') == 3 and 'terminating training' in out
+    assert tr2.global_step == 0                        # the terminate path restores the validated model (saved at step 0)

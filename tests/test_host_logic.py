@@ -100,3 +100,73 @@ def test_data_parallel_gradients_world_size_2_gloo():
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert 'DP_OK' in r.stdout
+
+
+# ---- row f2: the validation / early-stopping controller (reference trainers/trainer.py:189-265, 646-733) ----------
+def _controller(**kw):
+    from nabu_b200.neuralnetworks.trainers.trainer import ValidationController
+    conf = {'valid_frequency': '10', 'valid_adapt': 'False', 'go_back': 'False', 'num_tries': '2', 'reset_tries': 'True'}
+    conf.update({k: str(v) for k, v in kw.items()})
+    log = []
+    state = {'lr_fact': 1.0, 'saved': None}
+    ctl = ValidationController(conf, save=lambda: log.append('save'), restore=lambda: log.append('restore'),
+                               half_lr=lambda: (log.append('half'), state.__setitem__('lr_fact', state['lr_fact'] / 2)))
+    return ctl, log, state
+
+
+def test_validation_controller_early_stopping_follows_the_reference():
+    ctl, log, _ = _controller()
+    assert ctl.should_validate(0)                      # validated_step starts at -valid_frequency
+    assert ctl.update(1.0, 0) == 'continue' and log == ['save'] and ctl.best_validation == 1.0
+    assert not ctl.should_validate(9) and ctl.should_validate(10)
+    assert ctl.update(0.9, 10) == 'continue' and ctl.best_validation == 0.9 and ctl.num_tries == 0
+    assert ctl.update(0.95, 20) == 'continue' and ctl.num_tries == 1 and ctl.validated_step == 20
+    assert ctl.update(0.9, 30) == 'continue' and ctl.num_tries == 2        # equal counts as worse (>=)
+    assert log == ['save', 'save']                     # nothing saved for the two worse results
+    assert ctl.update(0.99, 40) == 'terminate' and log[-1] == 'restore'   # num_tries == conf -> restore and stop
+    # a better result resets the tries (reset_tries = True)
+    ctl, log, _ = _controller()
+    ctl.update(1.0, 0); ctl.update(1.1, 10)
+    assert ctl.num_tries == 1
+    ctl.update(0.5, 20)
+    assert ctl.num_tries == 0 and ctl.best_validation == 0.5
+    # num_tries = None disables early stopping
+    ctl, log, _ = _controller(num_tries='None')
+    ctl.update(1.0, 0)
+    for i in range(1, 6):
+        assert ctl.update(2.0, 10 * i) == 'continue'
+    assert ctl.num_tries == 5
+
+
+def test_validation_controller_go_back_and_lr_halving():
+    ctl, log, state = _controller(go_back=True, valid_adapt=True)
+    ctl.update(1.0, 0)
+    assert log == ['save']
+    # worse: restore the validated model, halve the learning rate, save the halved state (trainer.py:700-725)
+    assert ctl.update(1.2, 10) == 'continue'
+    assert log == ['save', 'restore', 'half', 'save'] and state['lr_fact'] == 0.5
+    assert ctl.validated_step == 0                     # go_back does not advance validated_step (the restore winds it back)
+    # without go_back the step advances and the learning rate still halves
+    ctl, log, state = _controller(valid_adapt=True)
+    ctl.update(1.0, 0); ctl.update(1.2, 10)
+    assert log == ['save', 'half', 'save'] and ctl.validated_step == 10 and state['lr_fact'] == 0.5
+
+
+def test_evaluator_factory_and_running_mean():
+    from nabu_b200.neuralnetworks.evaluators import evaluator_factory, evaluator
+    assert evaluator_factory.factory('loss_evaluator').__name__ == 'LossEvaluator'
+    assert evaluator_factory.factory('decoder_evaluator').__name__ == 'DecoderEvaluator'
+    with pytest.raises(Exception):
+        evaluator_factory.factory('nope')
+
+    class Fixed(evaluator.Evaluator):                  # utterance-weighted running mean of loss_evaluator.py:54-57
+        def __init__(self, batches):
+            self.batch_source = batches
+
+        def update_loss(self, loss, batch_loss, batch_utt, *_):
+            new = loss['count'] + batch_utt
+            loss['loss'] = (loss['loss'] * loss['count'] + batch_loss * batch_utt) / new
+            loss['count'] = new
+
+    val, n = Fixed([(2.0, 4.0, None, None), (1.0, 12.0, None, None)]).evaluate()
+    assert n == 2 and abs(val - (2.0 * 4 + 1.0 * 12) / 16) < 1e-12
