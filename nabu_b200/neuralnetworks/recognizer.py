@@ -1,0 +1,57 @@
+"""Recognizer (reference: nabu/neuralnetworks/recognizer.py:18-143) -- SURVEY.md section 8 row f2.
+
+Decodes a data set batch by batch with the decoder named in the recognizer cfg and writes the results
+through `decoder.write` into `<expdir>/decoded`.  The reference builds a TF input pipeline over the
+database sections named in the cfg and restores `model/network.ckpt`; here the batches come from a batch
+source (an iterable of `(inputs, input_seq_length)` dict pairs plus the utterance names -- the TFRecord
+pipeline is row f1) and the parameters from `<expdir>/model/network.pt` when it exists (what
+`Trainer.train` saves).  The reference's default file `defaults/recognizer.cfg` does not exist and
+`apply_defaults` tolerates that (tools/default_conf.py:19); `batch_size` must therefore be in the cfg.
+"""
+import os
+import shutil
+
+import torch
+
+from ..tools.default_conf import apply_defaults
+from .decoders import decoder_factory
+
+
+class Recognizer(object):
+    """Recognizer(model, conf, dataconf, expdir).recognize()"""
+
+    def __init__(self, model, conf, dataconf, expdir, batch_source=None, names=None):
+        self.conf = dict(conf.items('recognizer'))
+        apply_defaults(self.conf, os.path.join(os.path.dirname(os.path.realpath(__file__)), 'defaults',
+                                               type(self).__name__.lower() + '.cfg'))
+        self.expdir = expdir
+        self.model = model
+        self.dataconf = dataconf
+        self.decoder = decoder_factory.factory(conf.get('decoder', 'decoder'))(conf, self.model)
+        self.batch_size = int(self.conf['batch_size'])
+        self.batch_source = batch_source
+        # the reference's names carry the index the pipeline appended ("<utt>-<i>"); it is cut off before writing
+        self.names = list(names) if names is not None else None
+
+    def recognize(self):
+        if self.batch_source is None:
+            raise Exception('Recognizer.recognize needs a batch_source (the TFRecord input pipeline is row f1)')
+        ckpt = os.path.join(self.expdir, 'model', 'network.pt') if self.expdir else None
+        if ckpt and os.path.isfile(ckpt) and self.model.store.materialised():
+            self.model.store.load_state_dict(torch.load(ckpt))
+        directory = os.path.join(self.expdir, 'decoded')
+        if os.path.isdir(directory):
+            shutil.rmtree(directory)
+        os.makedirs(directory)
+        nameid = 0
+        for inputs, input_seq_length in self.batch_source:
+            outputs = self.decoder(inputs, input_seq_length)
+            n = int(list(input_seq_length.values())[0].shape[0])
+            if self.names is not None:
+                names = self.names[nameid:nameid + n]
+                names = ['-'.join(name.split('-')[:-1]) if '-' in name else name for name in names]
+            else:
+                names = ['utt%d' % (nameid + i) for i in range(n)]
+            self.decoder.write(outputs, directory, names)
+            nameid += n
+        return directory

@@ -106,3 +106,40 @@ def test_beam_search_decoder_plugin(tmp_path):
     v = dec.update_evaluation_loss(loss, out, {'text': torch.from_numpy(targets)}, {'text': torch.from_numpy(tl)})
     err = sum(O.edit_distance(ref[0][i, 0, :ref[1][i, 0]], targets[i, :tl[i] - 1]) for i in range(B))
     assert abs(v - err / float(tl.sum())) < 1e-9
+
+
+def test_recognizer_and_decoder_evaluator(tmp_path):
+    """Row f2: Recognizer.recognize writes one line per utterance through the decoder (names with the pipeline's index
+    suffix cut off); DecoderEvaluator's running label error rate equals the decoder's own evaluation loss."""
+    from nabu_b200.neuralnetworks.evaluators import evaluator_factory
+    from nabu_b200.neuralnetworks.models.model import Model
+    from nabu_b200.neuralnetworks.recognizer import Recognizer
+    dev = torch.device('cuda', 0)
+    D, H, NL, V = 40, 64, 2, 9
+    mconf = make_conf('[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = dblstm\n'
+                      'num_units = %d\nnum_layers = %d\n[decoder]\ndecoder = dnn_decoder\nnum_layers = 0\n'
+                      % (V - 1, H, NL))
+    model = Model(mconf, 1, None, seed=4).build({'features': D}, dev)
+    alphabet = ' '.join('s%d' % i for i in range(V - 1))
+    batches, names = [], []
+    for i, B in enumerate((4, 3)):
+        x, lens, labels, ll = synthetic_ctc_batch(B, 40, D, V, ragged=True, seed=10 + i)
+        batches.append(({'features': torch.from_numpy(x).to(dev)}, {'features': torch.from_numpy(lens).to(dev)},
+                        {'text': torch.from_numpy(labels)}, {'text': torch.from_numpy(ll)}))
+        names += ['spk%d-utt%d-%d' % (i, j, len(names) + j) for j in range(B)]
+    rconf = make_conf('[recognizer]\nbatch_size = 4\nfeatures = testfbank\n[decoder]\ndecoder = ctc_decoder\n'
+                      'text_alphabet = %s\n' % alphabet)
+    rec = Recognizer(model, rconf, None, str(tmp_path), batch_source=[b[:2] for b in batches], names=names)
+    directory = rec.recognize()
+    lines = open(os.path.join(directory, 'text')).read().strip().split('\n')
+    assert len(lines) == 7 and lines[0].split(' ')[0] == 'spk0-utt0' and lines[4].split(' ')[0] == 'spk1-utt0'
+    # decoder evaluator == the decoder's own update_evaluation_loss over the same batches
+    econf = make_conf('[evaluator]\nevaluator = decoder_evaluator\ntargets = text\nbatch_size = 4\n[decoder]\n'
+                      'decoder = ctc_decoder\ntext_alphabet = %s\n' % alphabet)
+    ev = evaluator_factory.factory('decoder_evaluator')(econf, None, model, batch_source=batches)
+    val, n = ev.evaluate()
+    from nabu_b200.neuralnetworks.decoders.decoder import RunningLoss
+    loss = RunningLoss()
+    for b in batches:
+        ref = rec.decoder.update_evaluation_loss(loss, rec.decoder(b[0], b[1]), b[2], b[3])
+    assert n == 2 and abs(val - ref) < 1e-12 and 0.0 < val
