@@ -1,0 +1,148 @@
+"""Input pipeline of nabu on in-process iterators.
+
+reference: processing/input_pipeline.py -- `get_filenames` (:10-55), `input_pipeline` (:57-174: one reader per data
+stream, `bucket_by_sequence_length` on the FIRST stream's length with `dynamic_pad`, optional variable batch size),
+`bucket_boundaries` (:176-202).  TF's queue runners are replaced by a deterministic generator: examples are read in
+the order of the (optionally shuffled) filename list, appended to their bucket, and a bucket is emitted when it holds
+its batch size; leftovers are emitted at the end when `allow_smaller_final_batch` (the reference's queues emit in a
+thread-dependent order, so only the batch CONTENTS per bucket are comparable, not the order of batches).
+"""
+import os
+
+import numpy as np
+
+from . import tfreaders
+
+
+def get_filenames(dataconfs):
+    """dataconfs: list (one per data stream) of lists of database sections (dicts with 'dir').  Returns
+    (tab-joined filenames per example, names).  An example is kept only if every stream has it; names carry the
+    index of the section within the stream (`<name>-<i>`), as in the reference."""
+    files = []
+    for dataconfset in dataconfs:
+        setfiles = dict()
+        for i, dataconf in enumerate(dataconfset):
+            with open(os.path.join(dataconf['dir'], 'pointers.scp')) as fid:
+                for line in fid:
+                    (n, f) = line.strip().split('\t')
+                    setfiles['%s-%d' % (n, i)] = f
+        files.append(setfiles)
+    data_queue_elements, names = [], []
+    for name in files[0]:
+        if all(name in setfile for setfile in files):
+            data_queue_elements.append('\t'.join(setfile[name] for setfile in files))
+            names.append(name)
+        else:
+            print('%s was not found in all sets of data, ignoring this example' % name)
+    return data_queue_elements, names
+
+
+def bucket_boundaries(histogram, numbuckets):
+    """greedy boundaries that spread the elements of `histogram` evenly over the buckets (input_pipeline.py:176-202)"""
+    histogram = np.asarray(histogram)
+    boundaries = [0] * numbuckets
+    for i in range(numbuckets - 1):
+        numelements = int(histogram[boundaries[i]:].sum() / (numbuckets - i))
+        if numelements == 0:
+            print('%d buckets could not be reached, using %d buckets' % (numbuckets, i))
+        j = boundaries[i] + 1
+        while (j + 1 < len(histogram) and
+               abs(histogram[boundaries[i]:j].sum() - numelements) >=
+               abs(histogram[boundaries[i]:j + 1].sum() - numelements)):
+            j += 1
+        boundaries[i + 1] = j
+    return boundaries[1:]
+
+
+def batch_plan(histogram, batch_size, numbuckets, variable_batch_size=False):
+    """(boundaries, batch size per bucket, num_steps) exactly as input_pipeline.py:131-160 computes them"""
+    histogram = np.asarray(histogram)
+    if numbuckets > 1:
+        boundaries = bucket_boundaries(histogram, numbuckets)
+        if variable_batch_size:
+            batch_sizes = [max(int(batch_size * boundaries[0] / b), 1) for b in boundaries + [histogram.size]]
+            numutt = [histogram[boundaries[i]:b].sum() for i, b in enumerate(boundaries[1:])]
+            numutt = [histogram[:boundaries[0]].sum()] + numutt + [histogram[boundaries[-1]:].sum()]
+            num_steps = int((np.array(numutt) / np.array(batch_sizes)).sum())
+        else:
+            batch_sizes = [int(batch_size)] * (len(boundaries) + 1)
+            num_steps = int(histogram.sum() / int(batch_size))
+        return boundaries, batch_sizes, num_steps
+    return [], [int(batch_size)], int(histogram.sum() / int(batch_size))
+
+
+def _pad(arrays):
+    """tf's dynamic_pad: zero-pad every example to the longest of the batch along axis 0"""
+    T = max(a.shape[0] for a in arrays)
+    out = np.zeros((len(arrays), T) + arrays[0].shape[1:], arrays[0].dtype)
+    for i, a in enumerate(arrays):
+        out[i, :a.shape[0]] = a
+    return out
+
+
+class BatchSource(object):
+    """Iterable of `(inputs, input_seq_length, targets, target_seq_length)` dict tuples of torch tensors -- what
+    Trainer.train / Evaluator.evaluate consume.  `input_names` / `target_names` name the streams in the order of
+    `dataconfs` (inputs first), as trainers/trainer.py:404-415 does."""
+
+    def __init__(self, dataconfs, input_names, target_names, batch_size, numbuckets=1, variable_batch_size=False,
+                 allow_smaller_final_batch=False, shuffle_seed=None, device='cpu'):
+        import torch
+        self._torch = torch
+        self.device = device
+        self.input_names, self.target_names = list(input_names), list(target_names)
+        self.elements, self.names = get_filenames(dataconfs)
+        self.readers = []
+        for dataconfset in dataconfs:
+            types = [d['type'] for d in dataconfset]
+            if len(set(types)) > 1:
+                raise Exception('all data types in a set must be the same')
+            self.readers.append(tfreaders.factory(types[0])([d['dir'] for d in dataconfset]))
+        hist = self.readers[0].metadata['sequence_length_histogram']
+        self.max_length = hist.size
+        self.boundaries, self.batch_sizes, self.num_steps = batch_plan(hist, batch_size, numbuckets, variable_batch_size)
+        self.allow_smaller_final_batch = allow_smaller_final_batch
+        self.shuffle_seed = shuffle_seed
+        self.input_dims = {n: self.readers[i].metadata['dim'] for i, n in enumerate(self.input_names)
+                           if 'dim' in self.readers[i].metadata}
+        self._epoch = 0
+
+    def __len__(self):
+        return self.num_steps
+
+    def _bucket(self, length):
+        # bucket_by_sequence_length: bucket i holds lengths in [boundaries[i-1], boundaries[i])
+        return int(np.searchsorted(np.asarray(self.boundaries), length, side='right')) if self.boundaries else 0
+
+    def _emit(self, items):
+        torch = self._torch
+        streams = list(zip(*items))                     # per stream: list of (array, length)
+        tensors, lengths = [], []
+        for st in streams:
+            tensors.append(torch.from_numpy(_pad([a for a, _ in st])).to(self.device))
+            lengths.append(torch.tensor([l for _, l in st], dtype=torch.int32).to(self.device))
+        ni = len(self.input_names)
+        inputs = {n: tensors[i] for i, n in enumerate(self.input_names)}
+        ilen = {n: lengths[i] for i, n in enumerate(self.input_names)}
+        targets = {n: tensors[ni + i] for i, n in enumerate(self.target_names)}
+        tlen = {n: lengths[ni + i] for i, n in enumerate(self.target_names)}
+        return inputs, ilen, targets, tlen
+
+    def __iter__(self):
+        order = list(range(len(self.elements)))
+        if self.shuffle_seed is not None:
+            np.random.default_rng(self.shuffle_seed + self._epoch).shuffle(order)
+        self._epoch += 1
+        buckets = [[] for _ in self.batch_sizes]
+        for idx in order:
+            files = self.elements[idx].split('\t')
+            item = [reader(f) for reader, f in zip(self.readers, files)]
+            b = self._bucket(item[0][1])
+            buckets[b].append(item)
+            if len(buckets[b]) == self.batch_sizes[b]:
+                yield self._emit(buckets[b])
+                buckets[b] = []
+        if self.allow_smaller_final_batch:
+            for items in buckets:
+                if items:
+                    yield self._emit(items)

@@ -1,0 +1,124 @@
+"""Row f1: nabu's on-disk data format and bucketed input pipeline, without TensorFlow.
+
+Pins: CRC-32C check value and TFRecord framing; tf.train.Example parsing on hand-assembled protobuf bytes (packed
+and unpacked repeated scalars); `bucket_boundaries` against vectors produced by the reference's own function
+(tests/golden/make_bucket_golden.py); reader semantics (float32 [T, dim], EOS = alphabet size appended, length + 1)
+and the batch plan of input_pipeline.py:131-160 restated independently in the test.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from nabu_b200.processing import input_pipeline as ip
+from nabu_b200.processing import tfreaders, tfrecord
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_crc32c_and_framing(tmp_path):
+    assert tfrecord.crc32c(b'123456789') == 0xE3069283            # the CRC-32C check value
+    assert tfrecord.crc32c(b'') == 0
+    path = str(tmp_path / 'a.rec')
+    tfrecord.write_records(path, [b'hello', b'', b'x' * 1000])
+    assert list(tfrecord.read_records(path)) == [b'hello', b'', b'x' * 1000]
+    raw = bytearray(open(path, 'rb').read())
+    assert raw[:8] == (5).to_bytes(8, 'little')                   # uint64 length first
+    raw[13] ^= 1                                                  # flip a payload bit
+    open(path, 'wb').write(raw)
+    with pytest.raises(IOError):
+        list(tfrecord.read_records(path))
+
+
+def test_example_parser_on_hand_assembled_protobuf():
+    # Example{features{feature{"length": Int64List[3]}}}, packed (what protobuf emits) and unpacked
+    packed = bytes.fromhex('0a110a0f0a066c656e67746812051a030a0103')
+    unpacked = bytes.fromhex('0a100a0e0a066c656e67746812041a020803')
+    for blob in (packed, unpacked):
+        p = tfrecord.parse_example(blob)
+        assert list(p) == ['length'] and p['length'].tolist() == [3]
+    # bytes + float features, negative int64 (10-byte varint)
+    ex = tfrecord.make_example({'data': b'a b', 'w': np.array([1.5, -2.0], np.float32), 'n': [-1]})
+    p = tfrecord.parse_example(ex)
+    assert p['data'] == [b'a b'] and p['w'].tolist() == [1.5, -2.0] and p['n'].tolist() == [-1]
+    assert tfrecord.make_example({'length': [3]}) == packed
+
+
+def test_bucket_boundaries_match_the_reference_function():
+    cases = json.load(open(os.path.join(GOLD, 'bucket_boundaries.json')))
+    assert len(cases) >= 8
+    for c in cases:
+        assert ip.bucket_boundaries(c['histogram'], c['numbuckets']) == c['boundaries']
+
+
+def _write_stream(root, kind, items, dim=None, alphabet=None):
+    """a nabu data directory: pointers.scp, data/file<i>, max_length, sequence_length_histogram.npy, dim | alphabet"""
+    os.makedirs(os.path.join(root, 'data'))
+    lengths = []
+    with open(os.path.join(root, 'pointers.scp'), 'w') as scp:
+        for i, (name, value) in enumerate(items):
+            f = os.path.join(root, 'data', 'file%d' % i)
+            if kind == 'audio':
+                ex = tfrecord.make_example({'shape': np.array(value.shape, np.int32).tobytes(),
+                                            'data': value.reshape(-1).astype(np.float32).tobytes()})
+                lengths.append(value.shape[0])
+            else:
+                ex = tfrecord.make_example({'length': [len(value.split(' '))], 'data': value.encode()})
+                lengths.append(len(value.split(' ')))
+            tfrecord.write_records(f, [ex])
+            scp.write('%s\t%s\n' % (name, f))
+    open(os.path.join(root, 'max_length'), 'w').write(str(max(lengths)))
+    np.save(os.path.join(root, 'sequence_length_histogram.npy'), np.bincount(lengths, minlength=max(lengths) + 1))
+    if kind == 'audio':
+        open(os.path.join(root, 'dim'), 'w').write(str(dim))
+    else:
+        open(os.path.join(root, 'alphabet'), 'w').write(' '.join(alphabet))
+        open(os.path.join(root, 'nonesymbol'), 'w').write('<none>')
+
+
+def test_readers_and_bucketed_batches(tmp_path):
+    rng = np.random.default_rng(0)
+    alphabet = ['a', 'b', 'c', 'd']
+    lens = [12, 30, 7, 25, 18, 9, 28, 14, 22, 11]
+    feats = [('utt%d' % i, rng.standard_normal((L, 5)).astype(np.float32)) for i, L in enumerate(lens)]
+    texts = [('utt%d' % i, ' '.join(rng.choice(alphabet, size=1 + L // 6))) for i, L in enumerate(lens)]
+    fdir, tdir = str(tmp_path / 'fbank'), str(tmp_path / 'text')
+    _write_stream(fdir, 'audio', feats, dim=5)
+    _write_stream(tdir, 'text', texts[:-1], alphabet=alphabet)            # the last utterance has no transcription
+    fconf, tconf = {'dir': fdir, 'type': 'audio_feature'}, {'dir': tdir, 'type': 'string_eos'}
+
+    elements, names = ip.get_filenames([[fconf], [tconf]])
+    assert names == ['utt%d-0' % i for i in range(9)] and all(len(e.split('\t')) == 2 for e in elements)
+
+    ar = tfreaders.factory('audio_feature')([fdir])
+    x, n = ar(elements[1].split('\t')[0])
+    assert n == 30 and x.dtype == np.float32 and np.array_equal(x, feats[1][1])
+    sr = tfreaders.factory('string_eos')([tdir])
+    ids, n = sr(elements[1].split('\t')[1])
+    want = [alphabet.index(s) for s in texts[1][1].split(' ')] + [len(alphabet)]       # EOS = alphabet size
+    assert ids.dtype == np.int32 and ids.tolist() == want and n == len(want)
+    assert sr.metadata['eos_label'] == 4 and sr.metadata['max_length'] == max(1 + L // 6 for L in lens[:-1]) + 1
+
+    # batch plan restated: boundaries from the histogram of the FIRST stream, variable batch sizes, num_steps
+    hist = ar.metadata['sequence_length_histogram']
+    bounds = ip.bucket_boundaries(hist, 3)
+    sizes = [max(int(4 * bounds[0] / b), 1) for b in bounds + [hist.size]]
+    src = ip.BatchSource([[fconf], [tconf]], ['features'], ['text'], batch_size=4, numbuckets=3,
+                         variable_batch_size=True, allow_smaller_final_batch=True)
+    assert src.boundaries == bounds and src.batch_sizes == sizes and src.input_dims == {'features': 5}
+    seen = 0
+    for inputs, ilen, targets, tlen in src:
+        B = inputs['features'].shape[0]
+        L = ilen['features'].numpy()
+        b = np.searchsorted(bounds, L, side='right')
+        assert len(set(b.tolist())) == 1 and B <= sizes[int(b[0])]                 # one bucket per batch
+        assert inputs['features'].shape == (B, int(L.max()), 5)                    # dynamic_pad to the longest
+        for i in range(B):
+            assert np.all(inputs['features'][i, L[i]:].numpy() == 0)
+            assert int(targets['text'][i, tlen['text'][i] - 1]) == 4               # ends with EOS
+        seen += B
+    assert seen == 9
+    # fixed batch size, no buckets: num_steps = floor(#utterances / batch_size), the tail is dropped
+    src = ip.BatchSource([[fconf], [tconf]], ['features'], ['text'], batch_size=4)
+    assert len(src) == int(hist.sum() / 4) and sum(b[0]['features'].shape[0] for b in src) == 8
