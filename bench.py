@@ -388,6 +388,19 @@ def main():
         name, (cnt, tot) = top
         roofline = {'kernel': name, 'bound': 'hbm', 'achieved': None, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': None,
                     'traffic': None, 'peak_source': peak_src}
+    roofline_gemm = None
+    if w['kind'] == 'ctc' and prof:
+        # second view: the dense contractions (tensor-bound).  fp32-equivalent FLOPs / summed GEMM kernel time; each
+        # product costs 3 fp16 MMAs, so the tensor pipe does 3x this rate.  Under the deferred-weight-gradient overlap the
+        # TN GEMMs share the GPU with the backward recurrence, which lengthens their event-timed duration.
+        work = ctc_step_work(w)
+        gemm_ms = sum(v[1] for k, v in prof.items() if k.startswith('gemm_h2') or k.startswith('gemm_tc'))
+        if gemm_ms > 0:
+            ach = work['gemm_flops'] * args.steps / (gemm_ms * 1e-3) / 1e12
+            roofline_gemm = {'kernel': 'gemm_h2 (fp16 hi/lo split, 3 MMAs per product)', 'bound': 'tensor',
+                             'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
+                             'mma_rate_tflops': 3 * ach, 'mma_frac': 3 * ach / tf_peak, 'traffic': None,
+                             'peak_source': peak_src + ' bf16 sustained (fp16 MMA runs at the same rate)'}
     if roofline is not None:
         roofline['avg_launch_ms'] = top[1][1] / max(top[1][0], 1)
         roofline['kernel_time_shares'] = shares
@@ -397,7 +410,7 @@ def main():
     out = dict(base)
     out.update({'value': value, 'ms_per_step': step_ms, 'loss': last, 'clocks': clk, 'gpu_launches': int(launches),
                 'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
-                'roofline': roofline})
+                'roofline': roofline, 'roofline_gemm': roofline_gemm})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(cores)
         fps, sec, desc, n = run_cpu(w, 3, 1, budget_s=30)
