@@ -124,6 +124,8 @@ typedef struct {
   int attention;           /* 0 vanilla Bahdanau, 1 location_aware */
   int numfilt, filtersize; /* location_aware only */
   int U;                   /* decoder steps = max target length */
+  int probability_fn;      /* alignments from the masked scores (components/attention.py:9-13, 41-55):
+                            * 0 softmax, 1 normalized_sigmoid (sigmoid / its sum over the memory), 2 sigmoid */
 } nabu_speller_desc_t;
 
 /* Parameter pack (device pointers).  Same field order for the gradient pack. */

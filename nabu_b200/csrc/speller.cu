@@ -107,6 +107,8 @@ struct AttnBwdArgs {
   float* dkeys; float* dvalues;                      // [R][Tm][A], [R][Tm][E] accumulate
   float* dv_part; float* dWd_part; float* dWc_part;  // [R][A], [R][F][A], [R][ksz][F] accumulate
   const int* tlen;
+  int prob;                                          // probability_fn: 0 softmax, 1 normalized_sigmoid, 2 sigmoid
+  const float* asum;                                 // [R] sum of sigmoids of this step (prob == 1)
   int ablate;                                        // NABU_ATTN_ABLATE (profiling only, results are then wrong): 1 skip dcf, 2 skip the conv backward, 4 skip the score backward
 };
 
@@ -208,11 +210,26 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
     if (lane == 0) dal[t] = (t < len) ? s + a.dalign_carry[(size_t)r * Tm + t] : 0.f;
   }
   __syncthreads();
-  // phase C: softmax backward  de = alpha * (dalpha - sum alpha*dalpha)
-  float part = 0.f;
-  for (int t = tid; t < Tm; t += NT) part += al[t] * dal[t];
-  const float dot = block_reduce(part, red, false);
-  for (int t = tid; t < Tm; t += NT) dal[t] = al[t] * (dal[t] - dot);
+  // phase C: probability function backward (components/attention.py:9-13, 41-55)
+  //   softmax:             de = alpha * (dalpha - sum alpha*dalpha)
+  //   normalized_sigmoid:  alpha = s / S  ->  de = (dalpha - sum alpha*dalpha) / S * s * (1 - s),  s = alpha * S
+  //   sigmoid:             de = dalpha * alpha * (1 - alpha)
+  if (a.prob == 2) {
+    for (int t = tid; t < Tm; t += NT) dal[t] = dal[t] * al[t] * (1.f - al[t]);
+  } else {
+    float part = 0.f;
+    for (int t = tid; t < Tm; t += NT) part += al[t] * dal[t];
+    const float dot = block_reduce(part, red, false);
+    if (a.prob == 0) {
+      for (int t = tid; t < Tm; t += NT) dal[t] = al[t] * (dal[t] - dot);
+    } else {
+      const float S = a.asum[r], iS = 1.f / S;
+      for (int t = tid; t < Tm; t += NT) {
+        const float sg = al[t] * S;
+        dal[t] = (dal[t] - dot) * iS * sg * (1.f - sg);
+      }
+    }
+  }
   __syncthreads();
   // phase D: score backward, tiles of TT memory positions; thread owns attention units tid + 256*i
   const float* keys = a.keys + (size_t)r * Tm * A;
@@ -398,6 +415,7 @@ struct Saved {        // written by the forward, read by the backward
   float* gates[4];                            // [U][B][4H]
   float* ctx; float* ctxT; float* align;      // [(U+1)][B][E], [(U+1)][E][B], [(U+1)][B][Tm]
   float* q; float* cf; float* outin;          // [U][B][A], [U][B][Tm][F], [B][U][H+E]
+  float* asum;                                // [U][B] sum of sigmoids (probability_fn = normalized_sigmoid)
   size_t total;
 };
 
@@ -422,6 +440,7 @@ Saved carve_saved(void* base, const nabu_speller_desc_t& d) {
   s.q = take(U * B * A);
   s.cf = take(U * B * Tm * (F ? F : 1));
   s.outin = take(B * U * (H + E));
+  s.asum = take(U * B);
   s.total = off;
   return s;
 }
@@ -467,6 +486,7 @@ int check_desc(const nabu_speller_desc_t& d) {
   NABU_REQUIRE(d.H % 8 == 0 && d.E % 8 == 0, "speller: num_units=%d and memory dim=%d must be multiples of 8", d.H, d.E);
   NABU_REQUIRE(d.A > 0 && d.A <= 512, "speller: attention units=%d not in 1..512", d.A);
   NABU_REQUIRE(d.attention == 0 || d.attention == 1, "speller: attention %d (windowed is outside the hot path)", d.attention);
+  NABU_REQUIRE(d.probability_fn >= 0 && d.probability_fn <= 2, "speller: probability_fn=%d not in 0..2", d.probability_fn);
   if (d.attention == 1)
     NABU_REQUIRE(d.numfilt >= 1 && d.numfilt <= MAXF && d.filtersize >= 1, "speller: numfilt=%d (max %d), filtersize=%d",
                  d.numfilt, MAXF, d.filtersize);
@@ -481,7 +501,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
                 float* const* hT_new, float* const* h_new, float* const* c_new, float* ctx_new, float* ctxT_new,
                 float* align_new, float* const* gates_out, float* logits, long logits_row_stride,
                 float temperature, float* q_save, float* cf_save, float* outin_save, long outin_row_stride,
-                const int* tlen, int u, const int* done, cudaStream_t stream) {
+                const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save) {
   const int H = d.H, E = d.E, V = d.V;
   for (int l = 0; l < d.num_layers; ++l) {
     LstmStepArgs a = {};
@@ -513,6 +533,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
   a.logits = logits; a.logits_row_stride = logits_row_stride; a.temperature = temperature;
   a.q_save = q_save; a.cf_save = cf_save; a.outin_save = outin_save; a.outin_row_stride = outin_row_stride;
   a.tlen = tlen; a.u = u; a.done = done;
+  a.prob = d.probability_fn; a.asum_save = asum_save;
   const size_t smem = attn_step_smem(d.Tm, E, H, d.A, a.F, a.ksz);
   NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: memory too long for the attention step kernel (Tm=%d)", d.Tm);
   if (smem > 48 * 1024)
@@ -590,7 +611,8 @@ extern "C" int nabu_speller_fwd(const nabu_speller_desc_t* dp, const nabu_spelle
                             hTn, hn, cn, s.ctx + (size_t)(u + 1) * B * E, s.ctxT + (size_t)(u + 1) * E * B,
                             s.align + (size_t)(u + 1) * B * Tm, go, logits + (size_t)u * d.V, (long)U * d.V, 1.f,
                             s.q + (size_t)u * B * d.A, F ? s.cf + (size_t)u * B * Tm * F : nullptr,
-                            s.outin + (size_t)u * (H + E), (long)U * (H + E), target_len, u, nullptr, stream))
+                            s.outin + (size_t)u * (H + E), (long)U * (H + E), target_len, u, nullptr, stream,
+                            s.asum + (size_t)u * B))
       return e;
   }
   return 0;
@@ -636,6 +658,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
     a.dv_part = w.dv_part; a.dWd_part = w.dWd_part; a.dWc_part = w.dWc_part; a.tlen = target_len;
     {
       a.ablate = getenv("NABU_ATTN_ABLATE") ? atoi(getenv("NABU_ATTN_ABLATE")) : 0;
+      a.prob = d.probability_fn; a.asum = s.asum + (size_t)u * B;
       KernelScope ks("dec_attn_bwd_step", stream);
       if (A <= 256) dec_attn_bwd_step_kernel<2><<<B, 512, smem_attn, stream>>>(a);
       else dec_attn_bwd_step_kernel<1><<<B, 512, smem_attn, stream>>>(a);

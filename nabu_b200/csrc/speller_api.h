@@ -15,7 +15,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
                 float* const* hT_new, float* const* h_new, float* const* c_new, float* ctx_new, float* ctxT_new,
                 float* align_new, float* const* gates_out, float* logits, long logits_row_stride,
                 float temperature, float* q_save, float* cf_save, float* outin_save, long outin_row_stride,
-                const int* tlen, int u, const int* done, cudaStream_t stream);
+                const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save = nullptr);
 
 int prepare_memory(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, const float* memory,
                    const int* mem_len, float* values, float* keys, cudaStream_t stream);

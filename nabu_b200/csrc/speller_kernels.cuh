@@ -135,6 +135,8 @@ struct AttnStepArgs {
   float* q_save; float* cf_save; float* outin_save; long outin_row_stride;   // optional
   const int* tlen; int u;
   const int* done;
+  int prob;                               // probability_fn: 0 softmax, 1 normalized_sigmoid, 2 sigmoid (attention.py:9-13)
+  float* asum_save;                       // optional [R]: sum of sigmoids (prob == 1), for the backward
 };
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
@@ -270,22 +272,45 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     }
   }
   __syncthreads();
-  // phase 3: softmax over the memory positions
-  float mx = -CUDART_INF_F;
-  for (int t = tid; t < Tm; t += NT) mx = fmaxf(mx, e[t]);
-  mx = block_reduce(mx, red, true);
-  float sum = 0.f;
-  for (int t = tid; t < Tm; t += NT) {
-    const float p = (t < len) ? expf(e[t] - mx) : 0.f;
-    e[t] = p;
-    sum += p;
-  }
-  sum = block_reduce(sum, red, false);
-  const float inv = 1.f / sum;
-  for (int t = tid; t < Tm; t += NT) {
-    const float p = e[t] * inv;
-    e[t] = p;
-    a.align_new[(size_t)r * Tm + t] = p;
+  // phase 3: alignments from the masked scores: softmax, or sigmoid / normalised sigmoid (components/attention.py:41-55;
+  // tf.sigmoid(-inf) = 0 on the masked positions)
+  if (a.prob == 0) {
+    float mx = -CUDART_INF_F;
+    for (int t = tid; t < Tm; t += NT) mx = fmaxf(mx, e[t]);
+    mx = block_reduce(mx, red, true);
+    float sum = 0.f;
+    for (int t = tid; t < Tm; t += NT) {
+      const float p = (t < len) ? expf(e[t] - mx) : 0.f;
+      e[t] = p;
+      sum += p;
+    }
+    sum = block_reduce(sum, red, false);
+    const float inv = 1.f / sum;
+    for (int t = tid; t < Tm; t += NT) {
+      const float p = e[t] * inv;
+      e[t] = p;
+      a.align_new[(size_t)r * Tm + t] = p;
+    }
+  } else {
+    float sum = 0.f;
+    for (int t = tid; t < Tm; t += NT) {
+      const float p = (t < len) ? 1.f / (1.f + expf(-e[t])) : 0.f;
+      e[t] = p;
+      sum += p;
+    }
+    float inv = 1.f;
+    if (a.prob == 1) {
+      sum = block_reduce(sum, red, false);
+      inv = 1.f / sum;
+      if (a.asum_save && tid == 0) a.asum_save[r] = sum;
+    } else {
+      __syncthreads();
+    }
+    for (int t = tid; t < Tm; t += NT) {
+      const float p = e[t] * inv;
+      e[t] = p;
+      a.align_new[(size_t)r * Tm + t] = p;
+    }
   }
   __syncthreads();
   // phase 4: context = alpha . values.  128-bit loads; the memory positions are split over 256 / (E/4) thread groups and

@@ -343,6 +343,7 @@ def gemm(mode, A, B, M, N, K, lda, ldb, ldc, C=None, alpha=1.0, beta=0.0, bias=N
 # ---------------------------------------------------------------------------------------------
 
 ATTENTION_IDS = {'vanilla': 0, 'location_aware': 1}
+PROBABILITY_FN_IDS = {'softmax': 0, 'normalized_sigmoid': 1, 'sigmoid': 2}      # components/attention.py:9-13
 
 
 class SpellerVars(object):
@@ -379,7 +380,9 @@ class SpellerVars(object):
 def speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, U):
     d = L.SpellerDesc()
     d.B, d.Tm, d.E, d.V, d.H, d.num_layers, d.A = B, Tm, E, V, H, num_layers, H
-    d.attention = ATTENTION_IDS[attention]
+    base, _, pf = attention.partition('+')
+    d.attention = ATTENTION_IDS[base]
+    d.probability_fn = PROBABILITY_FN_IDS[pf or 'softmax']
     d.numfilt, d.filtersize, d.U = numfilt, filtersize, U
     return d
 

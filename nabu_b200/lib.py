@@ -21,7 +21,7 @@ class NabuError(RuntimeError):
 
 class SpellerDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ('B', 'Tm', 'E', 'V', 'H', 'num_layers', 'A', 'attention', 'numfilt',
-                                    'filtersize', 'U')]
+                                    'filtersize', 'U', 'probability_fn')]
 
 
 class SpellerParams(ctypes.Structure):

@@ -5,14 +5,16 @@ dec_attn_step (csrc/speller_kernels.cuh)."""
 
 
 def factory(conf):
-    """Returns (attention name, numfilt, filtersize) for the kernels."""
-    if conf['probability_fn'] != 'softmax':
-        raise Exception('probability_fn %s is outside the B200 hot path (SURVEY.md section 8 f4)'
-                        % conf['probability_fn'])
+    """Returns (attention name, numfilt, filtersize) for the kernels.  A probability function other than softmax
+    (attention.py:9-13: `normalized_sigmoid`, `sigmoid`) travels as a suffix of the name: 'location_aware+sigmoid'."""
+    pf = conf['probability_fn']
+    if pf not in ('softmax', 'normalized_sigmoid', 'sigmoid'):
+        raise Exception('unknown probability_fn %s' % pf)
+    suffix = '' if pf == 'softmax' else '+' + pf
     if conf['attention'] == 'location_aware':
-        return 'location_aware', int(conf['numfilt']), int(conf['filtersize'])
+        return 'location_aware' + suffix, int(conf['numfilt']), int(conf['filtersize'])
     if conf['attention'] == 'vanilla':
-        return 'vanilla', 0, 1
+        return 'vanilla' + suffix, 0, 1
     if conf['attention'] == 'windowed':
         raise Exception('windowed attention is outside the B200 hot path (SURVEY.md section 8 f4)')
     raise Exception('unknown attention %s' % conf['attention'])

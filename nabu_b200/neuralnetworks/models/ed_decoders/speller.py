@@ -18,12 +18,12 @@ class Speller(rnn_decoder.RNNDecoder):
         kernels = [g(cell % (l, 'kernel'), ((V + E if l == 0 else H) + H, 4 * H), 'glorot') for l in range(NL)]
         biases = [g(cell % (l, 'bias'), (4 * H,), 'zeros') for l in range(NL)]
         mem = g(s + '/memory_layer/kernel', (E, A), 'glorot')
-        att_scope = s + '/decoder/attention_wrapper/' + ('location_aware_attention' if att == 'location_aware'
+        att_scope = s + '/decoder/attention_wrapper/' + ('location_aware_attention' if att.startswith('location_aware')
                                                          else 'bahdanau_attention')
         qk = g(att_scope + '/query_layer/kernel', (H, A), 'glorot')
         v = g(att_scope + '/attention_v', (A,), 'glorot')
         ck = dk = None
-        if att == 'location_aware':
+        if att.startswith('location_aware'):
             ck = g(att_scope + '/conv1d/kernel', (filtersize, 1, numfilt), 'glorot')
             dk = g(att_scope + '/process_conv_features/kernel', (numfilt, A), 'glorot')
         ok = g(s + '/decoder/dense/kernel', (H + E, V), 'glorot')

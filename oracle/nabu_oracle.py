@@ -484,7 +484,7 @@ def speller_zero_state(B, Tm, E, H, num_layers, dtype=np.float64):
 
 
 def speller_step(ids, state, values, keys, mask, p, attention, dtype,
-                 want_cache=False):
+                 want_cache=False, probability_fn='softmax'):
     """One AttentionProjectionWrapper(AttentionWrapper(MultiRNNCell)) step
     (rnn_cell.py:145-155 + appendix B5) on one-hot inputs `ids` [B]."""
     num_layers = len(state['h'])
@@ -516,9 +516,22 @@ def speller_step(ids, state, values, keys, mask, p, attention, dtype,
     sact = np.tanh(pre)
     e = sact @ np.asarray(p['attention_v'], dtype)
     e = np.where(mask, e, -np.inf)
-    m = e.max(1, keepdims=True)
-    ex = np.exp(e - m)
-    alpha = ex / ex.sum(1, keepdims=True)
+    ssum = None
+    if probability_fn == 'softmax':
+        m = e.max(1, keepdims=True)
+        ex = np.exp(e - m)
+        alpha = ex / ex.sum(1, keepdims=True)
+    else:
+        # components/attention.py:6-55: tf.sigmoid or normalized_sigmoid on the -inf masked scores
+        with np.errstate(over='ignore'):
+            sig = np.where(mask, 1.0 / (1.0 + np.exp(-np.where(mask, e, 0))), 0).astype(dtype)
+        if probability_fn == 'sigmoid':
+            alpha = sig
+        elif probability_fn == 'normalized_sigmoid':
+            ssum = sig.sum(1, keepdims=True)
+            alpha = sig / ssum
+        else:
+            raise ValueError('unknown probability_fn %r' % probability_fn)
     ctx = np.einsum('bt,bte->be', alpha, values)
     out_in = np.concatenate([query, ctx], 1)
     logits = out_in @ np.asarray(p['out_kernel'], dtype) \
@@ -529,12 +542,12 @@ def speller_step(ids, state, values, keys, mask, p, attention, dtype,
         cache = dict(ids=ids, xins=xins, gates=gs, cs=cs, c_prev=state['c'],
                      h_prev=state['h'], query=query, sact=sact, cf=cf,
                      win=win, alpha=alpha, ctx=ctx, out_in=out_in,
-                     prev_align=state['alignments'])
+                     prev_align=state['alignments'], ssum=ssum)
     return logits, new_state, cache
 
 
 def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
-                num_layers=2, dtype=np.float64):
+                num_layers=2, dtype=np.float64, probability_fn='softmax'):
     """RNNDecoder._decode with sample_prob=0, dropout=1 (rnn_decoder.py:40-82):
     prepend SOS=V-1, teacher-forced dynamic_decode(impute_finished=True).
     Returns logits [B, max(target_lens), V] (zeros past each target length)."""
@@ -553,7 +566,8 @@ def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
     for u in range(U):
         active = (u < target_lens)
         lg, ns, cache = speller_step(ids_in[:, u], state, values, keys, mask,
-                                     p, attention, dtype, want_cache=True)
+                                     p, attention, dtype, want_cache=True,
+                                     probability_fn=probability_fn)
         am = active[:, None]
         logits[:, u] = np.where(am, lg, 0)
         state = {
@@ -566,7 +580,7 @@ def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
         caches.append(cache)
     ctx = dict(caches=caches, values=values, keys=keys, mask=mask,
                memory=memory, p=p, attention=attention, num_layers=num_layers,
-               dtype=dtype)
+               dtype=dtype, probability_fn=probability_fn)
     return logits, ctx
 
 
@@ -599,7 +613,14 @@ def speller_bwd(ctx, dlogits):
         dctx = dout_in[:, H:] + np.where(am, dattn, 0)
         dalpha = np.einsum('be,bte->bt', dctx, values) + np.where(am, dalign, 0)
         dvalues += c['alpha'][:, :, None] * dctx[:, None, :]
-        de = c['alpha'] * (dalpha - (c['alpha'] * dalpha).sum(1, keepdims=True))
+        pf = ctx.get('probability_fn', 'softmax')
+        if pf == 'softmax':
+            de = c['alpha'] * (dalpha - (c['alpha'] * dalpha).sum(1, keepdims=True))
+        elif pf == 'sigmoid':
+            de = dalpha * c['alpha'] * (1 - c['alpha'])
+        else:                                   # alpha = s / S,  s = sigmoid(e)
+            sg = c['alpha'] * c['ssum']
+            de = (dalpha - (c['alpha'] * dalpha).sum(1, keepdims=True)) / c['ssum'] * sg * (1 - sg)
         dpre = de[:, :, None] * P['attention_v'][None, None, :] \
             * (1 - c['sact'] ** 2)
         g['attention_v'] += np.einsum('bt,bta->a', de, c['sact'])
@@ -791,7 +812,7 @@ def ctc_beam_search(logits, seq_len, beam_width=100, merge_repeated=True,
 
 def las_beam_search(memory, mem_lens, p, beam_width, max_steps,
                     attention='vanilla', num_layers=2, length_penalty=1.0,
-                    temperature=1.0, dtype=np.float32):
+                    temperature=1.0, dtype=np.float32, probability_fn='softmax'):
     """Returns sequences[B,W,L] int32, lengths[B,W] int32, scores[B,W] f32,
     alignments[B,W,L,Tm] f32 exactly as BeamSearchDecoder.__call__ does."""
     memory = np.asarray(memory, dtype)
@@ -834,7 +855,7 @@ def las_beam_search(memory, mem_lens, p, beam_width, max_steps,
         while not loop_finished.all():
             logits, new_state, _ = speller_step(ids.reshape(-1), state, values,
                                                 keys, mask, p, attention,
-                                                dtype)
+                                                dtype, probability_fn=probability_fn)
             out = (logits.astype(f32) / f32(temperature)).reshape(B, W, V)
             new_lp = log_softmax(out).astype(f32)
             new_lp = np.where(finished[:, :, None], -fmax, new_lp)

@@ -44,11 +44,18 @@ def _grads(sv, NL, attention):
     ('vanilla', 4, 9, 24, 9, 16, 2, 5, 0, 1),
     ('location_aware', 3, 20, 32, 30, 32, 1, 7, 10, 21),
     ('location_aware', 70, 11, 16, 12, 24, 3, 4, 4, 4),     # > 64 rows (two row tiles), even filter
+    ('location_aware+normalized_sigmoid', 6, 15, 16, 8, 16, 2, 6, 3, 5),   # row f4: attention.py:41-55
+    ('location_aware+sigmoid', 6, 15, 16, 8, 16, 2, 6, 3, 5),
+    ('vanilla+normalized_sigmoid', 4, 9, 24, 9, 16, 2, 5, 0, 1),
+    ('vanilla+sigmoid', 4, 9, 24, 9, 16, 1, 5, 0, 1),
 ])
 def test_speller_fwd_bwd(attention, B, Tm, E, V, H, NL, U, numfilt, fs):
     from nabu_b200 import engine
     dev = torch.device('cuda', 0)
     rng = np.random.default_rng(B * 100 + U)
+    full_attention = attention
+    attention, _, prob_fn = attention.partition('+')
+    prob_fn = prob_fn or 'softmax'
     p = O.init_speller_params(rng, V, E, H, NL, attention, max(numfilt, 1), fs)
     for k in p:
         if k.endswith('bias'):
@@ -62,13 +69,13 @@ def test_speller_fwd_bwd(attention, B, Tm, E, V, H, NL, U, numfilt, fs):
     dlog = rng.standard_normal((B, U, V)).astype(np.float32)
     for b in range(B):
         dlog[b, tl[b]:] = 0
-    ref_logits, ctx = O.speller_fwd(memory, mem_len, targets, tl, p, attention, NL, np.float64)
+    ref_logits, ctx = O.speller_fwd(memory, mem_len, targets, tl, p, attention, NL, np.float64, probability_fn=prob_fn)
     ref_dmem, ref_g = O.speller_bwd(ctx, dlog.astype(np.float64))
 
     sv = _svars(p, attention, NL, dev)
     mem_d = torch.tensor(memory, device=dev, requires_grad=True)
     logits = engine.speller(mem_d, torch.tensor(mem_len, device=dev), torch.tensor(targets, device=dev),
-                            torch.tensor(tl, device=dev), sv, V, H, NL, attention, numfilt, fs)
+                            torch.tensor(tl, device=dev), sv, V, H, NL, full_attention, numfilt, fs)
     assert rel_err(logits.detach().cpu().numpy(), ref_logits) < TOL
     logits.backward(torch.tensor(dlog, device=dev))
     assert rel_err(mem_d.grad.cpu().numpy(), ref_dmem) < TOL
@@ -81,11 +88,15 @@ def test_speller_fwd_bwd(attention, B, Tm, E, V, H, NL, U, numfilt, fs):
     ('location_aware', 3, 4, 12, 16, 7, 8, 2, 9, 1.0),
     ('vanilla', 2, 3, 8, 8, 5, 8, 1, 6, 0.0),
     ('location_aware', 4, 16, 25, 32, 30, 32, 2, 20, 1.0),   # beam 16 like the LAS recipe
+    ('location_aware+normalized_sigmoid', 3, 4, 12, 16, 7, 8, 2, 9, 1.0),
+    ('vanilla+sigmoid', 2, 3, 8, 8, 5, 8, 1, 6, 0.0),
 ])
 def test_las_beam_search_ids_bit_exact(attention, B, W, Tm, E, V, H, NL, max_steps, lp):
     from nabu_b200 import engine
     dev = torch.device('cuda', 0)
     rng = np.random.default_rng(B * 10 + W)
+    full_attention = attention
+    attention, _, prob_fn = attention.partition('+')
     numfilt, fs = (3, 5) if attention == 'location_aware' else (0, 1)
     p = O.init_speller_params(rng, V, E, H, NL, attention, max(numfilt, 1), fs)
     p['out_bias'] = rng.standard_normal(V).astype(np.float32)
@@ -93,10 +104,11 @@ def test_las_beam_search_ids_bit_exact(attention, B, W, Tm, E, V, H, NL, max_ste
     memory = rng.standard_normal((B, Tm, E)).astype(np.float32)
     mem_len = rng.integers(max(1, Tm // 2), Tm + 1, size=B).astype(np.int32)
     mem_len[0] = Tm
-    ref = O.las_beam_search(memory, mem_len, p, W, max_steps, attention, NL, lp, 1.0, np.float32)
+    ref = O.las_beam_search(memory, mem_len, p, W, max_steps, attention, NL, lp, 1.0, np.float32,
+                            probability_fn=prob_fn or 'softmax')
     sv = _svars(p, attention, NL, dev)
     got = engine.las_beam_search(torch.tensor(memory, device=dev), torch.tensor(mem_len, device=dev), sv, V, H, NL,
-                                 attention, numfilt, fs, W, max_steps, lp, 1.0)
+                                 full_attention, numfilt, fs, W, max_steps, lp, 1.0)
     seqs, lens, scores, aligns = [g.cpu().numpy() for g in got]
     assert seqs.shape == ref[0].shape, (seqs.shape, ref[0].shape)      # same number of loop iterations
     assert np.array_equal(seqs, ref[0])                                 # token ids: bit-exact

@@ -83,7 +83,7 @@ def test_pyramid_stack():
     assert np.array_equal(O.pyramid_stack_bwd(y, 5, 2), x)
 
 
-def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL):
+def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_fn='softmax'):
     """Independent torch-autograd twin of the Speller forward (used only to check the oracle)."""
     B, Tm, E = memory.shape
     V = p['out_bias'].shape[0]
@@ -119,7 +119,12 @@ def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL):
             pre = pre + cf.transpose(1, 2) @ p['conv_dense_kernel']
         e = torch.tanh(pre) @ p['attention_v']
         e = e.masked_fill(~mask, float('-inf'))
-        a = torch.softmax(e, 1)
+        if probability_fn == 'softmax':
+            a = torch.softmax(e, 1)
+        else:
+            a = torch.sigmoid(e)                     # sigmoid(-inf) = 0 on the masked positions
+            if probability_fn == 'normalized_sigmoid':
+                a = a / a.sum(1, keepdim=True)
         ctx = torch.einsum('bt,bte->be', a, values)
         lg = torch.cat([inp, ctx], 1) @ p['out_kernel'] + p['out_bias']
         outs.append(torch.where(act, lg, torch.zeros_like(lg)))
@@ -130,8 +135,9 @@ def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL):
     return torch.stack(outs, 1)
 
 
+@pytest.mark.parametrize('probability_fn', ['softmax', 'sigmoid', 'normalized_sigmoid'])
 @pytest.mark.parametrize('attention', ['vanilla', 'location_aware'])
-def test_speller_oracle_matches_torch_autograd(attention):
+def test_speller_oracle_matches_torch_autograd(attention, probability_fn):
     rng = np.random.default_rng(2)
     B, Tm, E, V, H, NL, U = 4, 9, 6, 5, 4, 2, 5
     p = O.init_speller_params(rng, V, E, H, NL, attention, 3, 4, np.float64)
@@ -145,11 +151,11 @@ def test_speller_oracle_matches_torch_autograd(attention):
     dlog = rng.normal(size=(B, U, V))
     for b in range(B):
         dlog[b, tl[b]:] = 0
-    logits, ctx = O.speller_fwd(memory, mem_lens, targets, tl, p, attention, NL)
+    logits, ctx = O.speller_fwd(memory, mem_lens, targets, tl, p, attention, NL, probability_fn=probability_fn)
     dmem, g = O.speller_bwd(ctx, dlog)
     tp = {k: torch.tensor(v, requires_grad=True) for k, v in p.items()}
     tm = torch.tensor(memory, requires_grad=True)
-    tlog = _torch_speller(tm, mem_lens, targets, tl, tp, attention, NL)
+    tlog = _torch_speller(tm, mem_lens, targets, tl, tp, attention, NL, probability_fn)
     assert np.abs(tlog.detach().numpy() - logits).max() < 1e-12
     (tlog * torch.tensor(dlog)).sum().backward()
     assert np.abs(tm.grad.numpy() - dmem).max() < 1e-10
