@@ -121,8 +121,8 @@ typedef struct {
   int B, Tm, E;            /* memory [B,Tm,E], mem_len [B] */
   int V, H, num_layers;    /* output classes (incl. EOS/SOS = V-1), LSTM units, layers (<=4) */
   int A;                   /* attention units (= H in the reference) */
-  int attention;           /* 0 vanilla Bahdanau, 1 location_aware */
-  int numfilt, filtersize; /* location_aware only */
+  int attention;           /* 0 vanilla Bahdanau, 1 location_aware, 2 windowed (attention.py:294-396) */
+  int numfilt, filtersize; /* location_aware: conv filters / taps; windowed: left_window_width / right_window_width */
   int U;                   /* decoder steps = max target length */
   int probability_fn;      /* alignments from the masked scores (components/attention.py:9-13, 41-55):
                             * 0 softmax, 1 normalized_sigmoid (sigmoid / its sum over the memory), 2 sigmoid */

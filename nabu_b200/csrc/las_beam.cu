@@ -288,6 +288,8 @@ extern "C" int nabu_las_beam_search(const nabu_speller_desc_t* dp, const nabu_sp
   NABU_CHECK_CUDA(cudaMemsetAsync(bb.ctx[0], 0, (size_t)R * E * 4, stream));
   NABU_CHECK_CUDA(cudaMemsetAsync(bb.ctxT[0], 0, (size_t)E * R * 4, stream));
   NABU_CHECK_CUDA(cudaMemsetAsync(bb.align[0], 0, (size_t)R * Tm * 4, stream));
+  if (d.attention == 2)
+    if (int e = dec::init_window_alignments(bb.align[0], R, Tm, stream)) return e;
   {
     KernelScope ks("las_init", stream);
     las_init_kernel<<<ceil_div(R, 256), 256, 0, stream>>>(bb.ids, bb.logprobs, bb.lengths, bb.finished, bb.loop_finished,

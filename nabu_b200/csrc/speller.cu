@@ -30,6 +30,12 @@ __global__ void mask_memory_kernel(const float* mem, const int* len, int Tm, int
 }
 
 // ids_in[u][r] = (u == 0) ? V-1 : targets[r][u-1]     (rnn_decoder.py:46-47)
+// WindowedAttention.initial_alignments (attention.py:344-351): all mass on frame 0
+__global__ void onehot0_kernel(float* align, int R, int Tm) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) align[(size_t)r * Tm] = 1.f;
+}
+
 __global__ void build_ids_kernel(const int* targets, int ldt, int R, int U, int V, int* ids_in) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= U * R) return;
@@ -480,12 +486,23 @@ Work carve_work(void* base, const nabu_speller_desc_t& d) {
   return w;
 }
 
+int init_window_alignments(float* align, int R, int Tm, cudaStream_t stream) {
+  KernelScope ks("onehot0", stream);
+  onehot0_kernel<<<ceil_div(R, 256), 256, 0, stream>>>(align, R, Tm);
+  NABU_CHECK_LAUNCH();
+  return 0;
+}
+
 int check_desc(const nabu_speller_desc_t& d) {
   NABU_REQUIRE(d.B > 0 && d.Tm > 0 && d.E > 0 && d.V > 1 && d.H > 0 && d.U > 0, "speller: bad shape");
   NABU_REQUIRE(d.num_layers >= 1 && d.num_layers <= 4, "speller: num_layers=%d not in 1..4", d.num_layers);
   NABU_REQUIRE(d.H % 8 == 0 && d.E % 8 == 0, "speller: num_units=%d and memory dim=%d must be multiples of 8", d.H, d.E);
   NABU_REQUIRE(d.A > 0 && d.A <= 512, "speller: attention units=%d not in 1..512", d.A);
-  NABU_REQUIRE(d.attention == 0 || d.attention == 1, "speller: attention %d (windowed is outside the hot path)", d.attention);
+  NABU_REQUIRE(d.attention >= 0 && d.attention <= 2, "speller: attention %d not in 0..2", d.attention);
+  if (d.attention == 2)
+    NABU_REQUIRE(d.numfilt >= 0 && d.filtersize >= 1 && d.Tm <= 2048,
+                 "speller: windowed attention needs left_window_width >= 0, right_window_width >= 1 (the reference slices "
+                 "[:, :-right]) and Tm <= 2048 (left=%d right=%d Tm=%d)", d.numfilt, d.filtersize, d.Tm);
   NABU_REQUIRE(d.probability_fn >= 0 && d.probability_fn <= 2, "speller: probability_fn=%d not in 0..2", d.probability_fn);
   if (d.attention == 1)
     NABU_REQUIRE(d.numfilt >= 1 && d.numfilt <= MAXF && d.filtersize >= 1, "speller: numfilt=%d (max %d), filtersize=%d",
@@ -534,6 +551,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
   a.q_save = q_save; a.cf_save = cf_save; a.outin_save = outin_save; a.outin_row_stride = outin_row_stride;
   a.tlen = tlen; a.u = u; a.done = done;
   a.prob = d.probability_fn; a.asum_save = asum_save;
+  a.win_left = d.attention == 2 ? d.numfilt : -1; a.win_right = d.filtersize;
   const size_t smem = attn_step_smem(d.Tm, E, H, d.A, a.F, a.ksz);
   NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: memory too long for the attention step kernel (Tm=%d)", d.Tm);
   if (smem > 48 * 1024)
@@ -597,6 +615,8 @@ extern "C" int nabu_speller_fwd(const nabu_speller_desc_t* dp, const nabu_spelle
   NABU_CHECK_CUDA(cudaMemsetAsync(s.ctx, 0, B * E * sizeof(float), stream));
   NABU_CHECK_CUDA(cudaMemsetAsync(s.ctxT, 0, E * B * sizeof(float), stream));
   NABU_CHECK_CUDA(cudaMemsetAsync(s.align, 0, B * Tm * sizeof(float), stream));
+  if (d.attention == 2)
+    if (int e = init_window_alignments(s.align, (int)B, (int)Tm, stream)) return e;
   const size_t F = d.attention == 1 ? d.numfilt : 0;
   for (int u = 0; u < d.U; ++u) {
     float *hTp[4], *hp[4], *cp[4], *hTn[4], *hn[4], *cn[4], *go[4];

@@ -17,6 +17,9 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
                 float temperature, float* q_save, float* cf_save, float* outin_save, long outin_row_stride,
                 const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save = nullptr);
 
+// WindowedAttention's initial alignments: align [R][Tm] (already zeroed) gets 1 at frame 0 of every row
+int init_window_alignments(float* align, int R, int Tm, cudaStream_t stream);
+
 int prepare_memory(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, const float* memory,
                    const int* mem_len, float* values, float* keys, cudaStream_t stream);
 

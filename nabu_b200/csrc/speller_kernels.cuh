@@ -137,6 +137,7 @@ struct AttnStepArgs {
   const int* done;
   int prob;                               // probability_fn: 0 softmax, 1 normalized_sigmoid, 2 sigmoid (attention.py:9-13)
   float* asum_save;                       // optional [R]: sum of sigmoids (prob == 1), for the backward
+  int win_left, win_right;                // WindowedAttention (attention.py:294-396): window widths, win_left < 0 = off
 };
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   for (int i = tid; i < H; i += NT) query[i] = a.h_top[(size_t)r * H + i];
   for (int i = tid; i < Tm + ksz; i += NT) {
     const int t = i - padl;
-    ap[i] = (F > 0 && t >= 0 && t < Tm) ? a.align_prev[(size_t)r * Tm + t] : 0.f;
+    ap[i] = ((F > 0 || a.win_left >= 0) && t >= 0 && t < Tm) ? a.align_prev[(size_t)r * Tm + t] : 0.f;
   }
   for (int i = tid; i < F * A; i += NT) wd[i] = a.Wd[i];
   for (int i = tid; i < ksz * F; i += NT) wc[i] = a.Wc[i];
@@ -272,6 +273,23 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     }
   }
   __syncthreads();
+  // WindowedAttention: keep the scores inside the window around the previous alignment's median frame only
+  // (attention.py:372-386): half_step = cumsum(alpha_prev) > 0.5 (sequential fp32 sum, as a CPU tf.cumsum), window =
+  // half_step shifted left by win_left + 1 (true shifted in) XOR shifted right by win_right (false shifted in).
+  if (a.win_left >= 0) {
+    for (int t = tid; t < Tm; t += NT) {
+      float c = 0.f;
+      for (int j = 0; j <= t; ++j) c += ap[j];         // padl = 0 here: ap[j] = alpha_prev[j]
+      cpart[t] = c > 0.5f ? 1.f : 0.f;
+    }
+    __syncthreads();
+    for (int t = tid; t < Tm; t += NT) {
+      const bool sl = t + a.win_left + 1 < Tm ? cpart[t + a.win_left + 1] != 0.f : true;
+      const bool sr = t - a.win_right >= 0 ? cpart[t - a.win_right] != 0.f : false;
+      if (!(sl != sr)) e[t] = -CUDART_INF_F;
+    }
+    __syncthreads();
+  }
   // phase 3: alignments from the masked scores: softmax, or sigmoid / normalised sigmoid (components/attention.py:41-55;
   // tf.sigmoid(-inf) = 0 on the masked positions)
   if (a.prob == 0) {

@@ -342,7 +342,7 @@ def gemm(mode, A, B, M, N, K, lda, ldb, ldc, C=None, alpha=1.0, beta=0.0, bias=N
 # Speller (attention decoder) and the beam searches
 # ---------------------------------------------------------------------------------------------
 
-ATTENTION_IDS = {'vanilla': 0, 'location_aware': 1}
+ATTENTION_IDS = {'vanilla': 0, 'location_aware': 1, 'windowed': 2}
 PROBABILITY_FN_IDS = {'softmax': 0, 'normalized_sigmoid': 1, 'sigmoid': 2}      # components/attention.py:9-13
 
 

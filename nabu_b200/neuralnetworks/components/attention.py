@@ -15,6 +15,6 @@ def factory(conf):
         return 'location_aware' + suffix, int(conf['numfilt']), int(conf['filtersize'])
     if conf['attention'] == 'vanilla':
         return 'vanilla' + suffix, 0, 1
-    if conf['attention'] == 'windowed':
-        raise Exception('windowed attention is outside the B200 hot path (SURVEY.md section 8 f4)')
+    if conf['attention'] == 'windowed':          # the two widths travel in the numfilt / filtersize slots
+        return 'windowed' + suffix, int(conf['left_window_width']), int(conf['right_window_width'])
     raise Exception('unknown attention %s' % conf['attention'])

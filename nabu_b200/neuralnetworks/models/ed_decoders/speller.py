@@ -19,6 +19,7 @@ class Speller(rnn_decoder.RNNDecoder):
         biases = [g(cell % (l, 'bias'), (4 * H,), 'zeros') for l in range(NL)]
         mem = g(s + '/memory_layer/kernel', (E, A), 'glorot')
         att_scope = s + '/decoder/attention_wrapper/' + ('location_aware_attention' if att.startswith('location_aware')
+                                                         else 'windowed_attention' if att.startswith('windowed')
                                                          else 'bahdanau_attention')
         qk = g(att_scope + '/query_layer/kernel', (H, A), 'glorot')
         v = g(att_scope + '/attention_v', (A,), 'glorot')

@@ -20,7 +20,7 @@ __all__ = [
     'dblstm_bwd', 'listener_fwd', 'listener_bwd', 'linear_fwd', 'linear_bwd',
     'log_softmax', 'ctc_loss_and_grad', 'ctc_brute_force', 'ctc_loss_mean',
     'average_cross_entropy', 'speller_fwd', 'speller_bwd', 'speller_step',
-    'speller_zero_state', 'attention_keys', 'tf_adam_clip',
+    'speller_zero_state', 'attention_keys', 'attention_window', 'tf_adam_clip',
     'exponential_decay', 'ctc_beam_search', 'las_beam_search',
     'edit_distance', 'init_blstm_params', 'init_speller_params',
     'init_linear_params',
@@ -476,15 +476,36 @@ def _lstm_cell(xin, h, c, K, b):
     return h_new, c_new, (i, g, f, o)
 
 
-def speller_zero_state(B, Tm, E, H, num_layers, dtype=np.float64):
+def speller_zero_state(B, Tm, E, H, num_layers, dtype=np.float64,
+                       attention='vanilla'):
+    al = np.zeros((B, Tm), dtype)
+    if attention == 'windowed':           # WindowedAttention.initial_alignments
+        al[:, 0] = 1                      # (attention.py:344-351): all mass on frame 0
     return {'h': [np.zeros((B, H), dtype) for _ in range(num_layers)],
             'c': [np.zeros((B, H), dtype) for _ in range(num_layers)],
             'attention': np.zeros((B, E), dtype),
-            'alignments': np.zeros((B, Tm), dtype)}
+            'alignments': al}
+
+
+def attention_window(prev_align, left, right):
+    """WindowedAttention's score window (attention.py:372-383): True where the
+    score is kept.  half_step = cumsum(prev) > 0.5; the window is the xor of
+    half_step shifted left by left+1 (True shifted in) and shifted right by
+    `right` (False shifted in).  right must be >= 1 (the reference slices
+    half_step[:, :-right])."""
+    half = np.cumsum(prev_align, 1) > 0.5
+    B, Tm = half.shape
+    sl = np.ones((B, Tm), bool)
+    if left + 1 < Tm:
+        sl[:, :Tm - left - 1] = half[:, left + 1:]
+    sr = np.zeros((B, Tm), bool)
+    if right < Tm:
+        sr[:, right:] = half[:, :Tm - right]
+    return np.logical_xor(sl, sr)
 
 
 def speller_step(ids, state, values, keys, mask, p, attention, dtype,
-                 want_cache=False, probability_fn='softmax'):
+                 want_cache=False, probability_fn='softmax', window=None):
     """One AttentionProjectionWrapper(AttentionWrapper(MultiRNNCell)) step
     (rnn_cell.py:145-155 + appendix B5) on one-hot inputs `ids` [B]."""
     num_layers = len(state['h'])
@@ -515,6 +536,8 @@ def speller_step(ids, state, values, keys, mask, p, attention, dtype,
         pre = pre + cf @ Wd
     sact = np.tanh(pre)
     e = sact @ np.asarray(p['attention_v'], dtype)
+    if attention == 'windowed':
+        e = np.where(attention_window(state['alignments'], *window), e, -np.inf)
     e = np.where(mask, e, -np.inf)
     ssum = None
     if probability_fn == 'softmax':
@@ -547,7 +570,8 @@ def speller_step(ids, state, values, keys, mask, p, attention, dtype,
 
 
 def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
-                num_layers=2, dtype=np.float64, probability_fn='softmax'):
+                num_layers=2, dtype=np.float64, probability_fn='softmax',
+                window=None):
     """RNNDecoder._decode with sample_prob=0, dropout=1 (rnn_decoder.py:40-82):
     prepend SOS=V-1, teacher-forced dynamic_decode(impute_finished=True).
     Returns logits [B, max(target_lens), V] (zeros past each target length)."""
@@ -560,14 +584,15 @@ def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
     values, keys, mask = attention_keys(memory, mem_lens, p, dtype)
     ids_in = np.concatenate([np.full((B, 1), V - 1, np.int64),
                              np.asarray(targets, np.int64)[:, :U]], 1)
-    state = speller_zero_state(B, Tm, E, H, num_layers, dtype)
+    state = speller_zero_state(B, Tm, E, H, num_layers, dtype, attention)
     logits = np.zeros((B, U, V), dtype)
     caches = []
     for u in range(U):
         active = (u < target_lens)
         lg, ns, cache = speller_step(ids_in[:, u], state, values, keys, mask,
                                      p, attention, dtype, want_cache=True,
-                                     probability_fn=probability_fn)
+                                     probability_fn=probability_fn,
+                                     window=window)
         am = active[:, None]
         logits[:, u] = np.where(am, lg, 0)
         state = {
@@ -812,7 +837,8 @@ def ctc_beam_search(logits, seq_len, beam_width=100, merge_repeated=True,
 
 def las_beam_search(memory, mem_lens, p, beam_width, max_steps,
                     attention='vanilla', num_layers=2, length_penalty=1.0,
-                    temperature=1.0, dtype=np.float32, probability_fn='softmax'):
+                    temperature=1.0, dtype=np.float32, probability_fn='softmax',
+                    window=None):
     """Returns sequences[B,W,L] int32, lengths[B,W] int32, scores[B,W] f32,
     alignments[B,W,L,Tm] f32 exactly as BeamSearchDecoder.__call__ does."""
     memory = np.asarray(memory, dtype)
@@ -827,7 +853,7 @@ def las_beam_search(memory, mem_lens, p, beam_width, max_steps,
     mem_t = np.repeat(memory, W, axis=0)
     len_t = np.repeat(np.asarray(mem_lens), W, axis=0)
     values, keys, mask = attention_keys(mem_t, len_t, p, dtype)
-    state = speller_zero_state(B * W, Tm, E, H, num_layers, dtype)
+    state = speller_zero_state(B * W, Tm, E, H, num_layers, dtype, attention)
     ids = np.full((B, W), eos, np.int64)                 # start tokens
     logprobs = np.concatenate([np.zeros((B, 1), f32),
                                np.full((B, W - 1), -np.inf, f32)], 1)
@@ -855,7 +881,8 @@ def las_beam_search(memory, mem_lens, p, beam_width, max_steps,
         while not loop_finished.all():
             logits, new_state, _ = speller_step(ids.reshape(-1), state, values,
                                                 keys, mask, p, attention,
-                                                dtype, probability_fn=probability_fn)
+                                                dtype, probability_fn=probability_fn,
+                                                window=window)
             out = (logits.astype(f32) / f32(temperature)).reshape(B, W, V)
             new_lp = log_softmax(out).astype(f32)
             new_lp = np.where(finished[:, :, None], -fmax, new_lp)

@@ -48,6 +48,8 @@ def _grads(sv, NL, attention):
     ('location_aware+sigmoid', 6, 15, 16, 8, 16, 2, 6, 3, 5),
     ('vanilla+normalized_sigmoid', 4, 9, 24, 9, 16, 2, 5, 0, 1),
     ('vanilla+sigmoid', 4, 9, 24, 9, 16, 1, 5, 0, 1),
+    ('windowed', 6, 17, 16, 8, 16, 2, 7, 2, 3),             # row f4: attention.py:294-396, left = 2, right = 3
+    ('windowed+normalized_sigmoid', 5, 23, 16, 8, 16, 2, 6, 4, 5),
 ])
 def test_speller_fwd_bwd(attention, B, Tm, E, V, H, NL, U, numfilt, fs):
     from nabu_b200 import engine
@@ -56,6 +58,7 @@ def test_speller_fwd_bwd(attention, B, Tm, E, V, H, NL, U, numfilt, fs):
     full_attention = attention
     attention, _, prob_fn = attention.partition('+')
     prob_fn = prob_fn or 'softmax'
+    window = (numfilt, fs) if attention == 'windowed' else None
     p = O.init_speller_params(rng, V, E, H, NL, attention, max(numfilt, 1), fs)
     for k in p:
         if k.endswith('bias'):
@@ -69,7 +72,8 @@ def test_speller_fwd_bwd(attention, B, Tm, E, V, H, NL, U, numfilt, fs):
     dlog = rng.standard_normal((B, U, V)).astype(np.float32)
     for b in range(B):
         dlog[b, tl[b]:] = 0
-    ref_logits, ctx = O.speller_fwd(memory, mem_len, targets, tl, p, attention, NL, np.float64, probability_fn=prob_fn)
+    ref_logits, ctx = O.speller_fwd(memory, mem_len, targets, tl, p, attention, NL, np.float64, probability_fn=prob_fn,
+                                    window=window)
     ref_dmem, ref_g = O.speller_bwd(ctx, dlog.astype(np.float64))
 
     sv = _svars(p, attention, NL, dev)
@@ -90,6 +94,7 @@ def test_speller_fwd_bwd(attention, B, Tm, E, V, H, NL, U, numfilt, fs):
     ('location_aware', 4, 16, 25, 32, 30, 32, 2, 20, 1.0),   # beam 16 like the LAS recipe
     ('location_aware+normalized_sigmoid', 3, 4, 12, 16, 7, 8, 2, 9, 1.0),
     ('vanilla+sigmoid', 2, 3, 8, 8, 5, 8, 1, 6, 0.0),
+    ('windowed', 3, 4, 14, 16, 7, 8, 2, 9, 1.0),
 ])
 def test_las_beam_search_ids_bit_exact(attention, B, W, Tm, E, V, H, NL, max_steps, lp):
     from nabu_b200 import engine
@@ -97,7 +102,8 @@ def test_las_beam_search_ids_bit_exact(attention, B, W, Tm, E, V, H, NL, max_ste
     rng = np.random.default_rng(B * 10 + W)
     full_attention = attention
     attention, _, prob_fn = attention.partition('+')
-    numfilt, fs = (3, 5) if attention == 'location_aware' else (0, 1)
+    numfilt, fs = (3, 5) if attention == 'location_aware' else ((2, 3) if attention == 'windowed' else (0, 1))
+    window = (numfilt, fs) if attention == 'windowed' else None
     p = O.init_speller_params(rng, V, E, H, NL, attention, max(numfilt, 1), fs)
     p['out_bias'] = rng.standard_normal(V).astype(np.float32)
     p['out_bias'][V - 1] += 1.0       # make EOS likely enough that hypotheses finish
@@ -105,7 +111,7 @@ def test_las_beam_search_ids_bit_exact(attention, B, W, Tm, E, V, H, NL, max_ste
     mem_len = rng.integers(max(1, Tm // 2), Tm + 1, size=B).astype(np.int32)
     mem_len[0] = Tm
     ref = O.las_beam_search(memory, mem_len, p, W, max_steps, attention, NL, lp, 1.0, np.float32,
-                            probability_fn=prob_fn or 'softmax')
+                            probability_fn=prob_fn or 'softmax', window=window)
     sv = _svars(p, attention, NL, dev)
     got = engine.las_beam_search(torch.tensor(memory, device=dev), torch.tensor(mem_len, device=dev), sv, V, H, NL,
                                  full_attention, numfilt, fs, W, max_steps, lp, 1.0)

@@ -83,7 +83,7 @@ def test_pyramid_stack():
     assert np.array_equal(O.pyramid_stack_bwd(y, 5, 2), x)
 
 
-def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_fn='softmax'):
+def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_fn='softmax', window=None):
     """Independent torch-autograd twin of the Speller forward (used only to check the oracle)."""
     B, Tm, E = memory.shape
     V = p['out_bias'].shape[0]
@@ -97,6 +97,8 @@ def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_
     c = [torch.zeros(B, H, dtype=torch.float64) for _ in range(NL)]
     att = torch.zeros(B, E, dtype=torch.float64)
     al = torch.zeros(B, Tm, dtype=torch.float64)
+    if attention == 'windowed':
+        al[:, 0] = 1
     outs = []
     for u in range(U):
         act = (u < torch.tensor(tl))[:, None]
@@ -118,6 +120,15 @@ def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_
             cf = F.conv1d(padded, p['conv_kernel'].permute(2, 1, 0))            # [B,F,Tm]
             pre = pre + cf.transpose(1, 2) @ p['conv_dense_kernel']
         e = torch.tanh(pre) @ p['attention_v']
+        if attention == 'windowed':                  # written independently of the oracle: explicit index arithmetic
+            L, R = window
+            half = (torch.cumsum(al.detach(), 1) > 0.5)
+            win = torch.zeros_like(half)
+            for t in range(Tm):
+                left = half[:, t + L + 1] if t + L + 1 < Tm else torch.ones(B, dtype=torch.bool)
+                right = half[:, t - R] if t - R >= 0 else torch.zeros(B, dtype=torch.bool)
+                win[:, t] = left ^ right
+            e = e.masked_fill(~win, float('-inf'))
         e = e.masked_fill(~mask, float('-inf'))
         if probability_fn == 'softmax':
             a = torch.softmax(e, 1)
@@ -136,7 +147,7 @@ def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_
 
 
 @pytest.mark.parametrize('probability_fn', ['softmax', 'sigmoid', 'normalized_sigmoid'])
-@pytest.mark.parametrize('attention', ['vanilla', 'location_aware'])
+@pytest.mark.parametrize('attention', ['vanilla', 'location_aware', 'windowed'])
 def test_speller_oracle_matches_torch_autograd(attention, probability_fn):
     rng = np.random.default_rng(2)
     B, Tm, E, V, H, NL, U = 4, 9, 6, 5, 4, 2, 5
@@ -151,11 +162,13 @@ def test_speller_oracle_matches_torch_autograd(attention, probability_fn):
     dlog = rng.normal(size=(B, U, V))
     for b in range(B):
         dlog[b, tl[b]:] = 0
-    logits, ctx = O.speller_fwd(memory, mem_lens, targets, tl, p, attention, NL, probability_fn=probability_fn)
+    window = (2, 3) if attention == 'windowed' else None
+    logits, ctx = O.speller_fwd(memory, mem_lens, targets, tl, p, attention, NL, probability_fn=probability_fn,
+                                window=window)
     dmem, g = O.speller_bwd(ctx, dlog)
     tp = {k: torch.tensor(v, requires_grad=True) for k, v in p.items()}
     tm = torch.tensor(memory, requires_grad=True)
-    tlog = _torch_speller(tm, mem_lens, targets, tl, tp, attention, NL, probability_fn)
+    tlog = _torch_speller(tm, mem_lens, targets, tl, tp, attention, NL, probability_fn, window)
     assert np.abs(tlog.detach().numpy() - logits).max() < 1e-12
     (tlog * torch.tensor(dlog)).sum().backward()
     assert np.abs(tm.grad.numpy() - dmem).max() < 1e-10
