@@ -15,43 +15,50 @@ from . import tfreaders
 
 
 def get_filenames(dataconfs):
-    """dataconfs: list (one per data stream) of lists of database sections (dicts with 'dir').  Returns
-    (tab-joined filenames per example, names).  An example is kept only if every stream has it; names carry the
-    index of the section within the stream (`<name>-<i>`), as in the reference."""
-    files = []
-    for dataconfset in dataconfs:
-        setfiles = dict()
-        for i, dataconf in enumerate(dataconfset):
-            with open(os.path.join(dataconf['dir'], 'pointers.scp')) as fid:
-                for line in fid:
-                    (n, f) = line.strip().split('\t')
-                    setfiles['%s-%d' % (n, i)] = f
-        files.append(setfiles)
-    data_queue_elements, names = [], []
-    for name in files[0]:
-        if all(name in setfile for setfile in files):
-            data_queue_elements.append('\t'.join(setfile[name] for setfile in files))
-            names.append(name)
-        else:
-            print('%s was not found in all sets of data, ignoring this example' % name)
-    return data_queue_elements, names
+    """dataconfs: one list of database sections (dicts with 'dir') per data stream.  Returns (tab-joined file names
+    per example, example names).  Keys are `<utterance>-<index of the section within its stream>`; an example is kept
+    only when every stream has it, in the order of the first stream's pointers.scp (reference :10-55)."""
+    def stream_table(sections):
+        table = {}
+        for idx, section in enumerate(sections):
+            with open(os.path.join(section['dir'], 'pointers.scp')) as scp:
+                for line in scp:
+                    utt, path = line.strip().split('\t')
+                    table['%s-%d' % (utt, idx)] = path
+        return table
+
+    tables = [stream_table(sections) for sections in dataconfs]
+    elements, names = [], []
+    for key, first in tables[0].items():
+        missing = [t for t in tables[1:] if key not in t]
+        if missing:
+            print('%s was not found in all sets of data, ignoring this example' % key)
+            continue
+        elements.append('\t'.join([first] + [t[key] for t in tables[1:]]))
+        names.append(key)
+    return elements, names
 
 
 def bucket_boundaries(histogram, numbuckets):
-    """greedy boundaries that spread the elements of `histogram` evenly over the buckets (input_pipeline.py:176-202)"""
-    histogram = np.asarray(histogram)
-    boundaries = [0] * numbuckets
-    for i in range(numbuckets - 1):
-        numelements = int(histogram[boundaries[i]:].sum() / (numbuckets - i))
-        if numelements == 0:
-            print('%d buckets could not be reached, using %d buckets' % (numbuckets, i))
-        j = boundaries[i] + 1
-        while (j + 1 < len(histogram) and
-               abs(histogram[boundaries[i]:j].sum() - numelements) >=
-               abs(histogram[boundaries[i]:j + 1].sum() - numelements)):
-            j += 1
-        boundaries[i + 1] = j
-    return boundaries[1:]
+    """Greedy bucket boundaries that spread the utterances evenly (reference :176-202, reproduced decision for
+    decision -- tests/golden/bucket_boundaries.json comes from the reference's own function): bucket i starts at the
+    previous boundary and grows while one more length bin does not move its population further from the target
+    (remaining utterances // remaining buckets).  Prefix sums replace the reference's repeated slice sums; the counts
+    are integers, so the sums are exact either way."""
+    counts = np.asarray(histogram, dtype=np.float64)
+    nbins = counts.shape[0]
+    prefix = np.concatenate([[0.0], np.cumsum(counts)])         # prefix[j] = counts[:j].sum()
+    out, start = [], 0
+    for made in range(numbuckets - 1):
+        target = int((prefix[nbins] - prefix[start]) / (numbuckets - made))
+        if target == 0:
+            print('%d buckets could not be reached, using %d buckets' % (numbuckets, made))
+        edge = start + 1
+        while edge + 1 < nbins and abs(prefix[edge] - prefix[start] - target) >= abs(prefix[edge + 1] - prefix[start] - target):
+            edge += 1
+        out.append(edge)
+        start = edge
+    return out
 
 
 def batch_plan(histogram, batch_size, numbuckets, variable_batch_size=False):
