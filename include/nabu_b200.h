@@ -126,6 +126,10 @@ typedef struct {
   int U;                   /* decoder steps = max target length */
   int probability_fn;      /* alignments from the masked scores (components/attention.py:9-13, 41-55):
                             * 0 softmax, 1 normalized_sigmoid (sigmoid / its sum over the memory), 2 sigmoid */
+  /* the stochastic parts of training (speller.py:37-41, rnn_decoder.py:59-64); all zero = off (beam search ignores them) */
+  float dropout_keep;      /* DropoutWrapper(output_keep_prob) on every LSTM layer; 0 or >= 1: no dropout */
+  float sample_prob;       /* ScheduledEmbeddingTrainingHelper sampling probability */
+  unsigned seed;           /* counter-based generator (csrc/speller_kernels.cuh: dec_rng_u32); change it every step */
 } nabu_speller_desc_t;
 
 /* Parameter pack (device pointers).  Same field order for the gradient pack. */

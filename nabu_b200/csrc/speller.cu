@@ -36,6 +36,28 @@ __global__ void onehot0_kernel(float* align, int R, int Tm) {
   if (r < R) align[(size_t)r * Tm] = 1.f;
 }
 
+// one thread per decoder row: inverse-CDF draw from softmax(logits) with the counter generator (dec_uniform)
+__global__ void dec_sample_ids_kernel(const float* logits, long row_stride, int V, int* ids_next, int R, float prob,
+                                      unsigned seed, int u) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  if (!(dec_uniform(seed, 0x40000000u + (uint32_t)u, (uint32_t)r, 0u) < prob)) return;
+  const float ub = dec_uniform(seed, 0x40000000u + (uint32_t)u, (uint32_t)r, 1u);
+  const float* lg = logits + r * row_stride;
+  float mx = lg[0];
+  for (int k = 1; k < V; ++k) mx = fmaxf(mx, lg[k]);
+  float total = 0.f;
+  for (int k = 0; k < V; ++k) total += expf(lg[k] - mx);
+  const float thr = ub * total;
+  float c = 0.f;
+  int id = 0;
+  for (int k = 0; k < V; ++k) {
+    c += expf(lg[k] - mx);
+    if (c < thr) ++id;
+  }
+  ids_next[r] = min(id, V - 1);
+}
+
 __global__ void build_ids_kernel(const int* targets, int ldt, int R, int U, int V, int* ids_in) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= U * R) return;
@@ -70,7 +92,7 @@ __global__ void embedding_grad_kernel(const int* ids_in, const float* dz, int UR
 __global__ void dec_lstm_bwd_pointwise_kernel(float* gates /*[R][4H] in: i,g,f,o ; out: dz*/, const float* c_new,
                                               const float* c_prev, const float* dh_above, const float* dh_carry,
                                               float* dc_carry, float* dzT /*[4H][R]*/, int R, int H,
-                                              const int* tlen, int u) {
+                                              const int* tlen, int u, float keep, unsigned seed, int layer) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * H) return;
   const int r = i / H, j = i % H;
@@ -79,7 +101,11 @@ __global__ void dec_lstm_bwd_pointwise_kernel(float* gates /*[R][4H] in: i,g,f,o
   float dz[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) {
     const float ig = gp[0], gg = gp[H], fg = gp[2 * H], og = gp[3 * H];
-    const float dh = dh_above[i] + dh_carry[i];
+    // dh_above is the gradient wrt the cell OUTPUT (dropped), dh_carry wrt the state h
+    float dha = dh_above[i];
+    if (keep > 0.f && keep < 1.f)
+      dha = dec_uniform(seed, (uint32_t)(layer * 65536 + u), (uint32_t)r, (uint32_t)j) < keep ? dha / keep : 0.f;
+    const float dh = dha + dh_carry[i];
     const float tc = tanhf(c_new[i]);
     const float dc = dc_carry[i] + dh * og * (1.f - tc * tc);
     dz[0] = dc * gg * ig * (1.f - ig);
@@ -422,6 +448,7 @@ struct Saved {        // written by the forward, read by the backward
   float* ctx; float* ctxT; float* align;      // [(U+1)][B][E], [(U+1)][E][B], [(U+1)][B][Tm]
   float* q; float* cf; float* outin;          // [U][B][A], [U][B][Tm][F], [B][U][H+E]
   float* asum;                                // [U][B] sum of sigmoids (probability_fn = normalized_sigmoid)
+  float* out[4]; float* outT[4];              // dropout only: cell outputs [(U+1)][B][H] (slot u+1 = step u), [H][B] scratch
   size_t total;
 };
 
@@ -447,6 +474,11 @@ Saved carve_saved(void* base, const nabu_speller_desc_t& d) {
   s.cf = take(U * B * Tm * (F ? F : 1));
   s.outin = take(B * U * (H + E));
   s.asum = take(U * B);
+  const bool drop = d.dropout_keep > 0.f && d.dropout_keep < 1.f;
+  for (int l = 0; l < 4; ++l) {
+    s.out[l] = (drop && l < d.num_layers) ? take((U + 1) * B * H) : nullptr;
+    s.outT[l] = (drop && l < d.num_layers) ? take(H * B) : nullptr;
+  }
   s.total = off;
   return s;
 }
@@ -518,17 +550,20 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
                 float* const* hT_new, float* const* h_new, float* const* c_new, float* ctx_new, float* ctxT_new,
                 float* align_new, float* const* gates_out, float* logits, long logits_row_stride,
                 float temperature, float* q_save, float* cf_save, float* outin_save, long outin_row_stride,
-                const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save) {
+                const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save,
+                float* const* out_new, float* const* outT_new, float keep, unsigned seed) {
   const int H = d.H, E = d.E, V = d.V;
   for (int l = 0; l < d.num_layers; ++l) {
     LstmStepArgs a = {};
     if (l == 0) { a.inT0 = ctxT_prev; a.K0 = E; a.w0 = V; a.inT1 = hT_prev[0]; a.K1 = H; a.w1 = V + E; a.ids = ids; }
-    else { a.inT0 = hT_new[l - 1]; a.K0 = H; a.w0 = 0; a.inT1 = hT_prev[l]; a.K1 = H; a.w1 = H; a.ids = nullptr; }
+    else { a.inT0 = outT_new ? outT_new[l - 1] : hT_new[l - 1]; a.K0 = H; a.w0 = 0; a.inT1 = hT_prev[l]; a.K1 = H; a.w1 = H; a.ids = nullptr; }
     a.W = p.cell_kernel[l]; a.bias = p.cell_bias[l]; a.H = H; a.R = R;
     a.c_prev = c_prev[l]; a.h_prev = h_prev[l];
     a.c_new = c_new[l]; a.h_new = h_new[l]; a.hT_new = hT_new[l];
     a.gates_out = gates_out ? gates_out[l] : nullptr;
     a.tlen = tlen; a.u = u; a.done = done;
+    a.out_new = out_new ? out_new[l] : nullptr; a.outT_new = outT_new ? outT_new[l] : nullptr;
+    a.keep = keep; a.seed = seed; a.layer = l;
     const size_t smem = ((size_t)(a.K0 + a.K1) * 8 + SK_KSPLIT * ROWS * 8) * sizeof(float);
     NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: LSTM input too wide for the step kernel");
     if (smem > 48 * 1024)
@@ -541,7 +576,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
   a.R = R; a.Tm = d.Tm; a.E = E; a.H = H; a.A = d.A; a.V = V;
   a.F = d.attention == 1 ? d.numfilt : 0; a.ksz = d.attention == 1 ? d.filtersize : 1;
   a.rows_per_mem = rows_per_mem;
-  a.h_top = h_new[d.num_layers - 1];
+  a.h_top = out_new ? out_new[d.num_layers - 1] : h_new[d.num_layers - 1];
   a.Wq = p.query_kernel; a.Wc = p.conv_kernel; a.Wd = p.conv_dense_kernel; a.v = p.attention_v;
   a.Wo = p.out_kernel; a.bo = p.out_bias;
   a.keys = keys; a.values = values; a.mem_len = mem_len;
@@ -618,13 +653,15 @@ extern "C" int nabu_speller_fwd(const nabu_speller_desc_t* dp, const nabu_spelle
   if (d.attention == 2)
     if (int e = init_window_alignments(s.align, (int)B, (int)Tm, stream)) return e;
   const size_t F = d.attention == 1 ? d.numfilt : 0;
+  const bool drop = d.dropout_keep > 0.f && d.dropout_keep < 1.f;
   for (int u = 0; u < d.U; ++u) {
-    float *hTp[4], *hp[4], *cp[4], *hTn[4], *hn[4], *cn[4], *go[4];
+    float *hTp[4], *hp[4], *cp[4], *hTn[4], *hn[4], *cn[4], *go[4], *on[4], *oTn[4];
     for (int l = 0; l < d.num_layers; ++l) {
       hTp[l] = s.hT[l] + (size_t)u * H * B; hTn[l] = s.hT[l] + (size_t)(u + 1) * H * B;
       hp[l] = s.h[l] + (size_t)u * B * H; hn[l] = s.h[l] + (size_t)(u + 1) * B * H;
       cp[l] = s.c[l] + (size_t)u * B * H; cn[l] = s.c[l] + (size_t)(u + 1) * B * H;
       go[l] = s.gates[l] + (size_t)u * B * 4 * H;
+      on[l] = drop ? s.out[l] + (size_t)(u + 1) * B * H : nullptr; oTn[l] = s.outT[l];
     }
     if (int e = launch_step(d, *p, d.B, 1, s.ids_in + (size_t)u * B, s.keys, s.values, mem_len, hTp, hp, cp,
                             s.ctx + (size_t)u * B * E, s.ctxT + (size_t)u * E * B, s.align + (size_t)u * B * Tm,
@@ -632,8 +669,16 @@ extern "C" int nabu_speller_fwd(const nabu_speller_desc_t* dp, const nabu_spelle
                             s.align + (size_t)(u + 1) * B * Tm, go, logits + (size_t)u * d.V, (long)U * d.V, 1.f,
                             s.q + (size_t)u * B * d.A, F ? s.cf + (size_t)u * B * Tm * F : nullptr,
                             s.outin + (size_t)u * (H + E), (long)U * (H + E), target_len, u, nullptr, stream,
-                            s.asum + (size_t)u * B))
+                            s.asum + (size_t)u * B, drop ? on : nullptr, drop ? oTn : nullptr, d.dropout_keep, d.seed))
       return e;
+    // ScheduledEmbeddingTrainingHelper (rnn_decoder.py:59-64): with probability sample_prob the NEXT input token is a
+    // draw from Categorical(logits of this step) instead of the teacher's
+    if (d.sample_prob > 0.f && u + 1 < d.U) {
+      KernelScope ks("dec_sample_ids", stream);
+      dec_sample_ids_kernel<<<ceil_div(d.B, 128), 128, 0, stream>>>(logits + (size_t)u * d.V, (long)U * d.V, d.V,
+                                                                  s.ids_in + (size_t)(u + 1) * B, d.B, d.sample_prob, d.seed, u);
+      NABU_CHECK_LAUNCH();
+    }
   }
   return 0;
 }
@@ -689,7 +734,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
         KernelScope ks("dec_lstm_bwd_pointwise", stream);
         dec_lstm_bwd_pointwise_kernel<<<ceil_div(B * H, 256), 256, 0, stream>>>(
             s.gates[l] + (size_t)u * B * H4, s.c[l] + (size_t)(u + 1) * B * H, s.c[l] + (size_t)u * B * H, w.dh_above,
-            w.dh_carry[l], w.dc_carry[l], w.dzT, B, H, target_len, u);
+            w.dh_carry[l], w.dc_carry[l], w.dzT, B, H, target_len, u, d.dropout_keep, d.seed, l);
         NABU_CHECK_LAUNCH();
       }
       MatmulTArgs m = {};
@@ -703,6 +748,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
   }
   // ---- batched weight gradients over all (step, row) pairs --------------------------------------
   const int UB = U * B;
+  const bool drop = d.dropout_keep > 0.f && d.dropout_keep < 1.f;
   for (int l = 0; l < NL; ++l) {
     float* dz = s.gates[l];                                   // [U][B][4H], now dz
     float* dK = g->cell_kernel[l];
@@ -719,7 +765,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
                         w.gemm, w.gemm_bytes, stream)) return e;
     } else {
       // input rows: h of the layer below AFTER step u = slot u+1 ; recurrent rows: own h slot u
-      if (int e = gemm(GEMM_TN, H, H4, UB, 1.f, s.h[l - 1] + (size_t)B * H, H, dz, H4, 0.f, dK, H4, nullptr, nullptr,
+      if (int e = gemm(GEMM_TN, H, H4, UB, 1.f, (drop ? s.out[l - 1] : s.h[l - 1]) + (size_t)B * H, H, dz, H4, 0.f, dK, H4, nullptr, nullptr,
                         w.gemm, w.gemm_bytes, stream)) return e;
       if (int e = gemm(GEMM_TN, H, H4, UB, 1.f, s.h[l], H, dz, H4, 0.f, dK + (size_t)H * H4, H4, nullptr, nullptr,
                         w.gemm, w.gemm_bytes, stream)) return e;
@@ -731,7 +777,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
                     w.gemm, w.gemm_bytes, stream)) return e;
   if (int e = colsum(dlogits, B * U, V, V, g->out_bias, stream)) return e;
   // query layer: h_top after step u (slot u+1) against dq[u]
-  if (int e = gemm(GEMM_TN, H, A, UB, 1.f, s.h[NL - 1] + (size_t)B * H, H, w.dq, A, 0.f, g->query_kernel, A, nullptr,
+  if (int e = gemm(GEMM_TN, H, A, UB, 1.f, (drop ? s.out[NL - 1] : s.h[NL - 1]) + (size_t)B * H, H, w.dq, A, 0.f, g->query_kernel, A, nullptr,
                     nullptr, w.gemm, w.gemm_bytes, stream)) return e;
   // memory layer and the memory itself
   if (int e = gemm(GEMM_TN, E, A, B * Tm, 1.f, s.values, E, w.dkeys, A, 0.f, g->memory_kernel, A, nullptr, nullptr,

@@ -15,7 +15,8 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
                 float* const* hT_new, float* const* h_new, float* const* c_new, float* ctx_new, float* ctxT_new,
                 float* align_new, float* const* gates_out, float* logits, long logits_row_stride,
                 float temperature, float* q_save, float* cf_save, float* outin_save, long outin_row_stride,
-                const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save = nullptr);
+                const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save = nullptr,
+                float* const* out_new = nullptr, float* const* outT_new = nullptr, float keep = 1.f, unsigned seed = 0);
 
 // WindowedAttention's initial alignments: align [R][Tm] (already zeroed) gets 1 at frame 0 of every row
 int init_window_alignments(float* align, int R, int Tm, cudaStream_t stream);

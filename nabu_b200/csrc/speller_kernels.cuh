@@ -13,10 +13,29 @@
 // the weight slice of a CTA sits in shared memory).
 #pragma once
 #include "common.cuh"
+#include <stdint.h>
 #include <math_constants.h>
 
 namespace nabu {
 namespace dec {
+
+// Counter-based generator of the decoder's stochastic parts (DropoutWrapper masks, scheduled sampling): three rounds of
+// the lowbias32 integer finaliser over (seed, a, b, c).  Stateless, so the backward regenerates the forward's masks; the
+// oracle restates it (oracle/nabu_oracle.py: rng_u32).  Keys: dropout a = layer*65536 + step, b = row, c = unit;
+// sampling a = 0x40000000 + step, b = row, c = 0 (Bernoulli) / 1 (categorical).
+__host__ __device__ inline uint32_t dec_mix(uint32_t x) {
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ inline uint32_t dec_rng_u32(uint32_t seed, uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t x = dec_mix((seed ^ 0x9E3779B9u) + a);
+  x = dec_mix(x + b * 0x85EBCA6Bu);
+  x = dec_mix(x + c * 0xC2B2AE35u);
+  return x;
+}
+__host__ __device__ inline float dec_uniform(uint32_t seed, uint32_t a, uint32_t b, uint32_t c) {
+  return (float)(dec_rng_u32(seed, a, b, c) >> 8) * (1.f / 16777216.f);       // [0, 1), 24 bits
+}
 
 constexpr int ROWS = 64;       // decoder rows per CTA tile in the skinny matmuls
 constexpr int SK_THREADS = 512;
@@ -40,6 +59,10 @@ struct LstmStepArgs {
   float* gates_out;                       // [R][4H] activated i,g,f,o or nullptr
   const int* tlen; int u;                 // row r is active iff tlen == nullptr || u < tlen[r]
   const int* done;                        // optional device flag: non-zero -> the whole launch is a no-op
+  // DropoutWrapper(output_keep_prob = keep) (speller.py:37-41): the cell OUTPUT out = h * mask / keep feeds the next
+  // layer and the attention query, the state keeps h.  out_new == nullptr: no dropout (consumers read h).
+  float* out_new; float* outT_new;        // [R][H], [H][R]
+  float keep; unsigned seed; int layer;
 };
 
 __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmStepArgs a) {
@@ -109,6 +132,12 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
       a.c_new[(size_t)r2 * H + j] = cn;
       a.h_new[(size_t)r2 * H + j] = hn;
       a.hT_new[(size_t)j * R + r2] = hn;
+      if (a.out_new) {
+        float o = hn;
+        if (active) o = dec_uniform(a.seed, (uint32_t)(a.layer * 65536 + a.u), (uint32_t)r2, (uint32_t)j) < a.keep ? hn / a.keep : 0.f;
+        a.out_new[(size_t)r2 * H + j] = o;
+        a.outT_new[(size_t)j * R + r2] = o;
+      }
       if (a.gates_out) {
         float* gp = a.gates_out + (size_t)r2 * H4 + j;
         gp[0] = ig; gp[H] = gg; gp[2 * H] = fg; gp[3 * H] = og;

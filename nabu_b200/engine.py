@@ -377,13 +377,15 @@ class SpellerVars(object):
         return p
 
 
-def speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, U):
+def speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, U, dropout_keep=1.0, sample_prob=0.0,
+                 seed=0):
     d = L.SpellerDesc()
     d.B, d.Tm, d.E, d.V, d.H, d.num_layers, d.A = B, Tm, E, V, H, num_layers, H
     base, _, pf = attention.partition('+')
     d.attention = ATTENTION_IDS[base]
     d.probability_fn = PROBABILITY_FN_IDS[pf or 'softmax']
     d.numfilt, d.filtersize, d.U = numfilt, filtersize, U
+    d.dropout_keep, d.sample_prob, d.seed = float(dropout_keep), float(sample_prob), int(seed) & 0xFFFFFFFF
     return d
 
 
@@ -425,10 +427,13 @@ class _Speller(torch.autograd.Function):
         return (dmem, None, None, None, None, None) + (None,) * len(svars.all())
 
 
-def speller(memory, mem_len, targets, target_len, svars, V, H, num_layers, attention, numfilt, filtersize):
+def speller(memory, mem_len, targets, target_len, svars, V, H, num_layers, attention, numfilt, filtersize,
+            dropout_keep=1.0, sample_prob=0.0, seed=0):
+    """dropout_keep < 1: DropoutWrapper(output_keep_prob) on every LSTM layer; sample_prob > 0: scheduled sampling;
+    both drawn from the counter generator keyed by `seed` (use a new seed every training step)."""
     B, Tm, E = memory.shape
     U = targets.shape[1]
-    desc = speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, U)
+    desc = speller_desc(B, Tm, E, V, H, num_layers, attention, numfilt, filtersize, U, dropout_keep, sample_prob, seed)
     return _Speller.apply(memory, mem_len, targets, target_len, desc, svars, *[v.data for v in svars.all()])
 
 

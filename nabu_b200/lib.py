@@ -21,7 +21,8 @@ class NabuError(RuntimeError):
 
 class SpellerDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ('B', 'Tm', 'E', 'V', 'H', 'num_layers', 'A', 'attention', 'numfilt',
-                                    'filtersize', 'U', 'probability_fn')]
+                                    'filtersize', 'U', 'probability_fn')] + \
+               [('dropout_keep', c_float), ('sample_prob', c_float), ('seed', ctypes.c_uint)]
 
 
 class SpellerParams(ctypes.Structure):

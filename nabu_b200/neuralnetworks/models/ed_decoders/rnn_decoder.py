@@ -12,9 +12,9 @@ class RNNDecoder(ed_decoder.EDDecoder, metaclass=ABCMeta):
 
     def _decode(self, encoded, encoded_seq_length, targets, target_seq_length, is_training):
         output_name = list(self.output_dims.keys())[0]
-        if float(self.conf['sample_prob']) > 0 and is_training:
-            raise Exception('sample_prob > 0 (scheduled sampling) is not on the B200 hot path; set sample_prob = 0')
         cell = self.create_cell(encoded, encoded_seq_length, is_training)
+        if is_training:                       # ScheduledEmbeddingTrainingHelper(sampling_probability) :59-64
+            cell.sample_prob = float(self.conf['sample_prob'])
         tgt = list(targets.values())[0]
         tgt_len = list(target_seq_length.values())[0]
         logits = cell.teacher_forced(tgt, tgt_len)

@@ -37,10 +37,12 @@ class Speller(rnn_decoder.RNNDecoder):
         self._vars(list(encoded_dims.values())[0])
 
     def create_cell(self, encoded, encoded_seq_length, is_training):
-        if float(self.conf['dropout']) < 1 and is_training:
-            raise Exception('speller dropout < 1 is not on the B200 hot path yet; set dropout = 1')
         name = list(encoded.keys())[0]
         memory = encoded[name]
         svars, (V, H, NL, att, numfilt, filtersize) = self._vars(memory.shape[-1])
+        # DropoutWrapper(output_keep_prob = dropout) on every LSTMCell when training (speller.py:37-41); a fresh seed
+        # per call for the counter generator of the kernels
+        keep = float(self.conf['dropout']) if is_training else 1.0
+        self._calls = getattr(self, '_calls', 0) + 1
         return rnn_cell.AttentionProjectionCell(svars, memory, encoded_seq_length[name], V, H, NL, att, numfilt,
-                                                filtersize)
+                                                filtersize, dropout_keep=keep, seed=0x5EED0000 + self._calls)

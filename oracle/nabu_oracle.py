@@ -20,7 +20,8 @@ __all__ = [
     'dblstm_bwd', 'listener_fwd', 'listener_bwd', 'linear_fwd', 'linear_bwd',
     'log_softmax', 'ctc_loss_and_grad', 'ctc_brute_force', 'ctc_loss_mean',
     'average_cross_entropy', 'speller_fwd', 'speller_bwd', 'speller_step',
-    'speller_zero_state', 'attention_keys', 'attention_window', 'tf_adam_clip',
+    'speller_zero_state', 'attention_keys', 'attention_window', 'rng_u32',
+    'rng_uniform', 'speller_dropout_mask', 'speller_sample_ids', 'tf_adam_clip',
     'exponential_decay', 'ctc_beam_search', 'las_beam_search',
     'edit_distance', 'init_blstm_params', 'init_speller_params',
     'init_linear_params',
@@ -487,6 +488,50 @@ def speller_zero_state(B, Tm, E, H, num_layers, dtype=np.float64,
             'alignments': al}
 
 
+def rng_u32(seed, a, b, c):
+    """The counter-based generator of the CUDA decoder kernels (csrc/speller_kernels.cuh: dec_rng_u32), restated: three
+    rounds of the lowbias32 integer finaliser over (seed, a, b, c).  Arrays broadcast; all arithmetic mod 2^32."""
+    M = np.uint64(0xFFFFFFFF)
+
+    def mix(x):
+        x = x & M
+        x ^= x >> np.uint64(16)
+        x = (x * np.uint64(0x7FEB352D)) & M
+        x ^= x >> np.uint64(15)
+        x = (x * np.uint64(0x846CA68B)) & M
+        x ^= x >> np.uint64(16)
+        return x
+    seed, a, b, c = (np.asarray(v, np.uint64) for v in (seed, a, b, c))
+    x = mix((seed ^ np.uint64(0x9E3779B9)) + a)
+    x = mix(x + ((b * np.uint64(0x85EBCA6B)) & M))
+    x = mix(x + ((c * np.uint64(0xC2B2AE35)) & M))
+    return x.astype(np.uint32)
+
+
+def rng_uniform(seed, a, b, c):
+    """uniform in [0, 1) with 24 bits, as the kernels draw it"""
+    return (rng_u32(seed, a, b, c) >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
+
+
+def speller_dropout_mask(seed, layer, u, B, H, keep):
+    """DropoutWrapper(output_keep_prob=keep) mask of LSTM layer `layer` at decoder step u: [B, H] of 0/1"""
+    r, j = np.meshgrid(np.arange(B), np.arange(H), indexing='ij')
+    return (rng_uniform(seed, layer * 65536 + u, r, j) < keep).astype(np.float64)
+
+
+def speller_sample_ids(seed, u, logits, sample_prob):
+    """ScheduledEmbeddingTrainingHelper.sample (appendix B6) with the kernels' uniforms: -1 where the teacher's token
+    is kept, else a draw from Categorical(logits) by inverse CDF over the softmax."""
+    B, V = logits.shape
+    r = np.arange(B)
+    take = rng_uniform(seed, 0x40000000 + u, r, 0) < sample_prob
+    ub = rng_uniform(seed, 0x40000000 + u, r, 1)
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    cdf = np.cumsum(p, 1)
+    ids = (cdf < (ub * cdf[:, -1])[:, None]).sum(1)
+    return np.where(take, np.minimum(ids, V - 1), -1)
+
+
 def attention_window(prev_align, left, right):
     """WindowedAttention's score window (attention.py:372-383): True where the
     score is kept.  half_step = cumsum(prev) > 0.5; the window is the xor of
@@ -505,7 +550,8 @@ def attention_window(prev_align, left, right):
 
 
 def speller_step(ids, state, values, keys, mask, p, attention, dtype,
-                 want_cache=False, probability_fn='softmax', window=None):
+                 want_cache=False, probability_fn='softmax', window=None,
+                 drop=None):
     """One AttentionProjectionWrapper(AttentionWrapper(MultiRNNCell)) step
     (rnn_cell.py:145-155 + appendix B5) on one-hot inputs `ids` [B]."""
     num_layers = len(state['h'])
@@ -524,7 +570,8 @@ def speller_step(ids, state, values, keys, mask, p, attention, dtype,
         hs.append(h_new)
         cs.append(c_new)
         gs.append(g)
-        inp = h_new
+        # DropoutWrapper(output_keep_prob): the OUTPUT is dropped, the state is not
+        inp = h_new if drop is None else h_new * drop[1][l] / drop[0]
     query = inp
     q = query @ np.asarray(p['query_kernel'], dtype)
     pre = q[:, None, :] + keys
@@ -565,13 +612,13 @@ def speller_step(ids, state, values, keys, mask, p, attention, dtype,
         cache = dict(ids=ids, xins=xins, gates=gs, cs=cs, c_prev=state['c'],
                      h_prev=state['h'], query=query, sact=sact, cf=cf,
                      win=win, alpha=alpha, ctx=ctx, out_in=out_in,
-                     prev_align=state['alignments'], ssum=ssum)
+                     prev_align=state['alignments'], ssum=ssum, drop=drop)
     return logits, new_state, cache
 
 
 def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
                 num_layers=2, dtype=np.float64, probability_fn='softmax',
-                window=None):
+                window=None, dropout_keep=1.0, sample_prob=0.0, seed=0):
     """RNNDecoder._decode with sample_prob=0, dropout=1 (rnn_decoder.py:40-82):
     prepend SOS=V-1, teacher-forced dynamic_decode(impute_finished=True).
     Returns logits [B, max(target_lens), V] (zeros past each target length)."""
@@ -587,12 +634,20 @@ def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
     state = speller_zero_state(B, Tm, E, H, num_layers, dtype, attention)
     logits = np.zeros((B, U, V), dtype)
     caches = []
+    ids_in = ids_in.copy()
     for u in range(U):
         active = (u < target_lens)
+        drop = None
+        if dropout_keep < 1:
+            drop = (dropout_keep, [speller_dropout_mask(seed, l, u, B, H, dropout_keep).astype(dtype)
+                                   for l in range(num_layers)])
         lg, ns, cache = speller_step(ids_in[:, u], state, values, keys, mask,
                                      p, attention, dtype, want_cache=True,
                                      probability_fn=probability_fn,
-                                     window=window)
+                                     window=window, drop=drop)
+        if sample_prob > 0 and u + 1 < U:
+            smp = speller_sample_ids(seed, u, lg, sample_prob)
+            ids_in[:, u + 1] = np.where(smp >= 0, smp, ids_in[:, u + 1])
         am = active[:, None]
         logits[:, u] = np.where(am, lg, 0)
         state = {
@@ -605,7 +660,7 @@ def speller_fwd(memory, mem_lens, targets, target_lens, p, attention='vanilla',
         caches.append(cache)
     ctx = dict(caches=caches, values=values, keys=keys, mask=mask,
                memory=memory, p=p, attention=attention, num_layers=num_layers,
-               dtype=dtype, probability_fn=probability_fn)
+               dtype=dtype, probability_fn=probability_fn, ids_in=ids_in)
     return logits, ctx
 
 
@@ -634,7 +689,7 @@ def speller_bwd(ctx, dlogits):
         g['out_kernel'] += c['out_in'].T @ dl
         g['out_bias'] += dl.sum(0)
         dout_in = dl @ P['out_kernel'].T
-        dquery = dout_in[:, :H] + np.where(am, dh[NL - 1], 0)
+        dquery = dout_in[:, :H]                 # wrt the top layer's OUTPUT (the carried state gradient joins below)
         dctx = dout_in[:, H:] + np.where(am, dattn, 0)
         dalpha = np.einsum('be,bte->bt', dctx, values) + np.where(am, dalign, 0)
         dvalues += c['alpha'][:, :, None] * dctx[:, None, :]
@@ -673,7 +728,9 @@ def speller_bwd(ctx, dlogits):
         for l in range(NL - 1, -1, -1):
             K = P['cell_%d_kernel' % l]
             i, gg, f, o = c['gates'][l]
-            dh_tot = dinp if l == NL - 1 else dinp + np.where(am, dh[l], 0)
+            if c.get('drop') is not None:         # gradient wrt the layer's OUTPUT -> wrt h
+                dinp = dinp * c['drop'][1][l] / c['drop'][0]
+            dh_tot = dinp + np.where(am, dh[l], 0)
             tc = np.tanh(c['cs'][l])
             do = dh_tot * tc
             dcc = np.where(am, dc[l], 0) + dh_tot * o * (1 - tc * tc)

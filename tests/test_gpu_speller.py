@@ -185,3 +185,72 @@ def test_las_train_step_matches_oracle():
     for l in range(NL + 1):
         for k in glayers[l]:
             assert rel_err(glayers_got[l][k], glayers[l][k]) < 5 * TOL, (l, k)
+
+
+@pytest.mark.parametrize('attention,keep,sp,numfilt,fs', [
+    ('location_aware', 0.5, 0.0, 3, 5),      # output dropout only (the LAS/TIMIT recipe: dropout = 0.5)
+    ('vanilla', 1.0, 0.4, 0, 1),             # scheduled sampling only
+    ('location_aware', 0.7, 0.1, 3, 5),      # both (sample_prob = 0.1 is the recipe default)
+])
+def test_speller_dropout_and_scheduled_sampling(attention, keep, sp, numfilt, fs):
+    """Rows a6/a7 with the stochastic parts on (speller.py:37-41 DropoutWrapper(output_keep_prob), rnn_decoder.py:59-64
+    ScheduledEmbeddingTrainingHelper).  TF's random streams cannot be reproduced; the kernels draw from a counter-based
+    generator that the oracle restates, so for one seed the masks and the sampled tokens are THE SAME on both sides and
+    logits / gradients are compared as usual.  The oracle itself is pinned by the torch twin (tests/test_oracle.py)."""
+    from nabu_b200 import engine
+    dev = torch.device('cuda', 0)
+    B, Tm, E, V, H, NL, U, seed = 9, 14, 16, 8, 16, 2, 8, 4242
+    rng = np.random.default_rng(int(keep * 100 + sp * 10))
+    p = O.init_speller_params(rng, V, E, H, NL, attention, max(numfilt, 1), fs)
+    memory = rng.standard_normal((B, Tm, E)).astype(np.float32)
+    mem_len = rng.integers(Tm // 2, Tm + 1, size=B).astype(np.int32)
+    tl = rng.integers(1, U + 1, size=B).astype(np.int32)
+    tl[0] = U
+    targets = rng.integers(0, V, size=(B, U)).astype(np.int32)
+    dlog = rng.standard_normal((B, U, V)).astype(np.float32)
+    for b in range(B):
+        dlog[b, tl[b]:] = 0
+    ref_logits, ctx = O.speller_fwd(memory, mem_len, targets, tl, p, attention, NL, np.float64, dropout_keep=keep,
+                                    sample_prob=sp, seed=seed)
+    ref_dmem, ref_g = O.speller_bwd(ctx, dlog.astype(np.float64))
+    if sp > 0:
+        teacher = np.concatenate([np.full((B, 1), V - 1), targets], 1)[:, :U]
+        assert (ctx['ids_in'][:, :U] != teacher).any()
+    sv = _svars(p, attention, NL, dev)
+    mem_d = torch.tensor(memory, device=dev, requires_grad=True)
+    logits = engine.speller(mem_d, torch.tensor(mem_len, device=dev), torch.tensor(targets, device=dev),
+                            torch.tensor(tl, device=dev), sv, V, H, NL, attention, numfilt, fs, dropout_keep=keep,
+                            sample_prob=sp, seed=seed)
+    assert rel_err(logits.detach().cpu().numpy(), ref_logits) < TOL
+    logits.backward(torch.tensor(dlog, device=dev))
+    assert rel_err(mem_d.grad.cpu().numpy(), ref_dmem) < TOL
+    for k, v in _grads(sv, NL, attention).items():
+        assert rel_err(v, ref_g[k]) < TOL, k
+    # a different seed gives different masks / samples
+    other = engine.speller(mem_d.detach(), torch.tensor(mem_len, device=dev), torch.tensor(targets, device=dev),
+                           torch.tensor(tl, device=dev), sv, V, H, NL, attention, numfilt, fs, dropout_keep=keep,
+                           sample_prob=sp, seed=seed + 1)
+    assert rel_err(other.detach().cpu().numpy(), ref_logits) > 1e-3
+
+
+def test_las_recipe_settings_train():
+    """The shipped LAS/TIMIT recipe's stochastic settings (config/recipes/LAS/TIMIT/model.cfg: input_noise = 0.6,
+    dropout = 0.5 in listener and speller, sample_prob = 0.1) run through Trainer.update and learn."""
+    from nabu_b200.neuralnetworks.trainers import trainer_factory
+    dev = torch.device('cuda', 0)
+    V, D = 12, 40
+    mconf = make_conf('[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = listener\n'
+                      'num_units = 64\nnum_layers = 2\npyramid_steps = 2\ninput_noise = 0.6\ndropout = 0.5\n[decoder]\n'
+                      'decoder = speller\nnum_layers = 2\nnum_units = 32\ndropout = 0.5\nattention = vanilla\n'
+                      'sample_prob = 0.1\n' % (V - 1))
+    tconf = make_conf('[trainer]\ntrainer = standard\nloss = average_cross_entropy\ntrainlabels = 1\ntargets = text\n'
+                      'initial_learning_rate = 3e-3\n')
+    tr = trainer_factory.factory('standard')(tconf, None, mconf, None, None, None, 0, device=dev, seed=1)
+    tr.num_steps = 1000
+    tr.model.build({'features': D}, dev)
+    x, lens, targets, tl = synthetic_las_batch(8, 48, D, V, 9, ragged=True)
+    batch = ({'features': torch.from_numpy(x).to(dev)}, {'features': torch.from_numpy(lens).to(dev)},
+             {'text': torch.from_numpy(targets).to(dev)}, {'text': torch.from_numpy(tl).to(dev)})
+    losses = [float(tr.update(*batch)[0]) for _ in range(60)]
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-10:]) < 0.8 * np.mean(losses[:5]), (losses[:5], losses[-10:])

@@ -83,7 +83,8 @@ def test_pyramid_stack():
     assert np.array_equal(O.pyramid_stack_bwd(y, 5, 2), x)
 
 
-def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_fn='softmax', window=None):
+def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_fn='softmax', window=None, ids=None,
+                   drop=None):
     """Independent torch-autograd twin of the Speller forward (used only to check the oracle)."""
     B, Tm, E = memory.shape
     V = p['out_bias'].shape[0]
@@ -92,7 +93,8 @@ def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_
     mask = torch.arange(Tm)[None, :] < torch.tensor(mem_lens)[:, None]
     values = memory * mask[:, :, None]
     keys = values @ p['memory_kernel']
-    ids = torch.cat([torch.full((B, 1), V - 1, dtype=torch.long), torch.tensor(targets, dtype=torch.long)[:, :U]], 1)
+    if ids is None:
+        ids = torch.cat([torch.full((B, 1), V - 1, dtype=torch.long), torch.tensor(targets, dtype=torch.long)[:, :U]], 1)
     h = [torch.zeros(B, H, dtype=torch.float64) for _ in range(NL)]
     c = [torch.zeros(B, H, dtype=torch.float64) for _ in range(NL)]
     att = torch.zeros(B, E, dtype=torch.float64)
@@ -111,7 +113,7 @@ def _torch_speller(memory, mem_lens, targets, tl, p, attention, NL, probability_
             hn = torch.tanh(cn) * torch.sigmoid(o)
             nh.append(hn)
             nc.append(cn)
-            inp = hn
+            inp = hn if drop is None else hn * drop[1][u][l] / drop[0]      # output dropout; the state keeps hn
         pre = (inp @ p['query_kernel'])[:, None, :] + keys
         if attention == 'location_aware':
             ksz = p['conv_kernel'].shape[0]
@@ -260,3 +262,51 @@ def test_las_beam_search_wide_beam_beats_greedy():
 
 def test_edit_distance():
     assert O.edit_distance([1, 2, 3], [1, 3]) == 1 and O.edit_distance([], [1, 2]) == 2
+
+
+def test_speller_dropout_and_scheduled_sampling_oracle_matches_torch():
+    """Rows a6/a7 with the stochastic parts on: DropoutWrapper(output_keep_prob) on every LSTM layer and
+    ScheduledEmbeddingTrainingHelper.  The masks and draws come from the counter-based generator the kernels use, so
+    the oracle is deterministic; the torch twin is fed the same masks and the token ids the oracle ended up feeding."""
+    rng = np.random.default_rng(5)
+    B, Tm, E, V, H, NL, U = 5, 8, 6, 6, 4, 2, 6
+    keep, sp, seed = 0.6, 0.5, 1234
+    p = O.init_speller_params(rng, V, E, H, NL, 'location_aware', 3, 4, np.float64)
+    memory = rng.normal(size=(B, Tm, E))
+    mem_lens = np.array([8, 6, 5, 8, 7])
+    tl = np.array([6, 3, 1, 5, 6])
+    targets = rng.integers(0, V, size=(B, U))
+    dlog = rng.normal(size=(B, U, V))
+    for b in range(B):
+        dlog[b, tl[b]:] = 0
+    logits, ctx = O.speller_fwd(memory, mem_lens, targets, tl, p, 'location_aware', NL, dropout_keep=keep,
+                                sample_prob=sp, seed=seed)
+    teacher = np.concatenate([np.full((B, 1), V - 1), targets[:, :U]], 1)
+    assert (ctx['ids_in'][:, :U] != teacher[:, :U]).any()                    # some tokens were sampled
+    dmem, g = O.speller_bwd(ctx, dlog)
+    masks = [[torch.tensor(O.speller_dropout_mask(seed, l, u, B, H, keep)) for l in range(NL)] for u in range(U)]
+    frac = np.mean([m.numpy().mean() for ms in masks for m in ms])
+    assert abs(frac - keep) < 0.15
+    tp = {k: torch.tensor(v, requires_grad=True) for k, v in p.items()}
+    tm = torch.tensor(memory, requires_grad=True)
+    tlog = _torch_speller(tm, mem_lens, targets, tl, tp, 'location_aware', NL, ids=torch.tensor(ctx['ids_in']),
+                          drop=(keep, masks))
+    assert np.abs(tlog.detach().numpy() - logits).max() < 1e-12
+    (tlog * torch.tensor(dlog)).sum().backward()
+    assert np.abs(tm.grad.numpy() - dmem).max() < 1e-10
+    for k in g:
+        if tp[k].grad is not None:
+            assert np.abs(tp[k].grad.numpy() - g[k]).max() < 1e-10, k
+
+
+def test_counter_rng_is_uniform_and_sampling_follows_the_softmax():
+    u = O.rng_uniform(7, 3, np.arange(200000), 11)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3 and abs((u < 0.25).mean() - 0.25) < 5e-3
+    hist, _ = np.histogram(u, bins=16, range=(0, 1))
+    assert np.abs(hist / len(u) - 1 / 16).max() < 3e-3
+    logits = np.tile(np.log(np.array([[0.5, 0.25, 0.125, 0.125]])), (100000, 1))
+    ids = O.speller_sample_ids(99, 0, logits, 1.0)
+    freq = np.bincount(ids, minlength=4) / len(ids)
+    assert np.abs(freq - [0.5, 0.25, 0.125, 0.125]).max() < 5e-3
+    assert (O.speller_sample_ids(99, 0, logits, 0.0) == -1).all()
+    assert abs((O.speller_sample_ids(99, 1, logits, 0.3) >= 0).mean() - 0.3) < 5e-3
