@@ -182,6 +182,12 @@ int nabu_ctc_beam_search(const float* logits, const int* logit_len, int B, int T
                          int beam_width, int merge_repeated, int* out_ids, int* out_len,
                          float* out_neg_logprob, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- host helper (rows f1 / f3: TFRecord frames, TF checkpoint bundles) ---------------------------
+ * CRC-32C (Castagnoli, reflected 0x82F63B78) of `nbytes` HOST bytes, continuing from `crc` (0 to start).
+ * Replaces tensorflow/core/lib/hash/crc32c (external) behind tf.python_io.TFRecordWriter
+ * (processing/tfwriters/tfwriter.py:34-55) and tf.train.Saver (components/hooks.py:6-52).  Needs no device. */
+unsigned int nabu_crc32c(const void* data, size_t nbytes, unsigned int crc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,6 +122,50 @@ class ParamStore(object):
         return {'theta': self.theta.cpu(), 'm': self.m.cpu(), 'v': self.v.cpu(),
                 'names': [(v.name, v.shape, v.offset) for v in self.order]}
 
+    # ---- TF checkpoint interop: the store's variable names ARE the reference's TF names --
+    def save_tf_checkpoint(self, prefix, with_adam=False, global_step=None):
+        """Write `<prefix>.index` / `.data-*` as `tf.train.Saver(model.variables, sharded=True).save` would
+        (components/hooks.py:32-52 -> model/network.ckpt).  `with_adam` adds the optimizer slots under TF's names
+        (`<var>/Adam`, `<var>/Adam_1`), what the reference's validated.ckpt holds besides the variables."""
+        from .processing import tfcheckpoint
+        theta, m, v = self.theta.detach().cpu().numpy(), self.m.cpu().numpy(), self.v.cpu().numpy()
+        arrays = {}
+        for var in self.order:
+            sl = slice(var.offset, var.offset + var.numel)
+            arrays[var.name] = theta[sl].reshape(var.shape)
+            if with_adam:
+                arrays[var.name + '/Adam'] = m[sl].reshape(var.shape)
+                arrays[var.name + '/Adam_1'] = v[sl].reshape(var.shape)
+        if global_step is not None:
+            arrays['global_step'] = np.array(global_step, np.int32)
+        tfcheckpoint.write_checkpoint(prefix, arrays)
+
+    def load_tf_checkpoint(self, prefix, with_adam=False):
+        """Restore every variable from a TF checkpoint (a nabu-trained `model/network.ckpt`, LoadAtBegin
+        components/hooks.py:6-28).  Like Saver.restore it fails when a variable is missing or its shape differs;
+        keys of the checkpoint the model does not own are ignored.  Returns the checkpoint's global_step or None."""
+        from .processing import tfcheckpoint
+        have = {name: shape for name, shape, _ in tfcheckpoint.list_variables(prefix)}
+        want = [var.name for var in self.order]
+        if with_adam:
+            want += [n + s for n in want for s in ('/Adam', '/Adam_1')]
+        missing = [n for n in want if n not in have]
+        if missing:
+            raise KeyError('not found in checkpoint %s: %s' % (prefix, ', '.join(missing)))
+        for var in self.order:
+            if tuple(have[var.name]) != var.shape:
+                raise ValueError('%s: checkpoint shape %s, model shape %s' % (var.name, have[var.name], var.shape))
+        names = want + (['global_step'] if 'global_step' in have else [])
+        arrays = tfcheckpoint.read_checkpoint(prefix, names=set(names))
+        with torch.no_grad():
+            for var in self.order:
+                sl = slice(var.offset, var.offset + var.numel)
+                self.theta[sl].copy_(torch.from_numpy(arrays[var.name].astype(np.float32).reshape(-1)))
+                if with_adam:
+                    self.m[sl].copy_(torch.from_numpy(arrays[var.name + '/Adam'].astype(np.float32).reshape(-1)))
+                    self.v[sl].copy_(torch.from_numpy(arrays[var.name + '/Adam_1'].astype(np.float32).reshape(-1)))
+        return int(arrays['global_step']) if 'global_step' in arrays else None
+
     def load_state_dict(self, sd):
         self.theta.copy_(sd['theta'])
         self.m.copy_(sd['m'])

@@ -67,6 +67,7 @@ SIGNATURES = {
                                      c_float, c_float, P, P, P, P, ctypes.POINTER(c_int), P, c_size_t, P]),
     'nabu_ctc_beam_workspace_bytes': (c_size_t, [c_int] * 4),
     'nabu_ctc_beam_search': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    'nabu_crc32c': (ctypes.c_uint, [ctypes.c_char_p, c_size_t, ctypes.c_uint]),
 }
 
 _lib = None

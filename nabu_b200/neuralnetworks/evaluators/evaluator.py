@@ -32,7 +32,12 @@ class Evaluator(object, metaclass=ABCMeta):
     def evaluate(self):
         """Returns (validation loss, number of batches): init_validation + numbatches x update_loss."""
         if self.batch_source is None:
-            raise Exception('Evaluator.evaluate needs a batch_source (the TFRecord input pipeline is row f1)')
+            if self.dataconf is None:
+                raise Exception('Evaluator.evaluate needs a batch_source or a database configuration')
+            from ...processing import input_pipeline            # evaluator.py:78-104: one bucket, whole batches only
+            self.batch_source = input_pipeline.source_from_conf(
+                self.conf, self.dataconf, self.model.input_names, self.target_names,
+                device=getattr(self.model, 'device', 'cpu'))
         state = self.init_loss()
         numbatches = 0
         for batch in self.batch_source:

@@ -26,6 +26,7 @@ class Model(object):
 
     def build(self, input_dims, device='cuda'):
         """Declare every variable (the TF graph-construction step) and allocate the flat buffers."""
+        self.device = device
         if not self.store.materialised:
             encoded_dims = self.encoder.declare(dict(input_dims))
             self.decoder.declare(encoded_dims)

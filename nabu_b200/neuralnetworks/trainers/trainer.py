@@ -129,7 +129,16 @@ class Trainer(object, metaclass=ABCMeta):
         """Loop over the batch source (trainer.py:582-792).  `testing` builds the model and returns."""
         src = self.batch_source
         if src is None:
-            raise Exception('Trainer.train needs a batch_source (the TFRecord input pipeline is row f1, not built)')
+            # the reference's _data (trainer.py:286-415): sections named in the trainer cfg for every model input and
+            # every target, shuffled file queue, bucketing by the first input's length, variable batch size
+            if self.dataconf is None:
+                raise Exception('Trainer.train needs a batch_source or a database configuration')
+            from ...processing import input_pipeline
+            src = input_pipeline.source_from_conf(
+                self.conf, self.dataconf, self.model.input_names, [t for t in self.conf['targets'].split(' ') if t],
+                device=self.device, numbuckets=int(self.conf['numbuckets']),
+                variable_batch_size=self.conf['variable_batch_size'] == 'True', shuffle_seed=0)
+            self.batch_source = src
         steps_per_epoch = len(src)
         self.num_steps = steps_per_epoch * int(self.conf['num_epochs'])
         self.model.build(src.input_dims, self.device)
@@ -173,6 +182,9 @@ class Trainer(object, metaclass=ABCMeta):
         if self.expdir and self.task_index == 0:
             os.makedirs(os.path.join(self.expdir, 'model'), exist_ok=True)
             torch.save(self.model.store.state_dict(), os.path.join(self.expdir, 'model', 'network.pt'))
+            # SaveAtEnd (components/hooks.py:30-52, trainer.py:615-619): the model variables as a TF checkpoint under
+            # the reference's variable names -- readable by a nabu / TF-1.8 install and by Recognizer below
+            self.model.store.save_tf_checkpoint(os.path.join(self.expdir, 'model', 'network.ckpt'))
 
     # ---- ValidationSaveHook (hooks.py:54-86): every global variable, in memory -----------------------
     def _save_validated(self):

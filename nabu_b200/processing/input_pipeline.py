@@ -153,3 +153,20 @@ class BatchSource(object):
             for items in buckets:
                 if items:
                     yield self._emit(items)
+
+
+def dataconfs_for(conf, dataconf, names):
+    """The database sections a trainer / evaluator / recognizer cfg names for each stream: `conf[name]` is a space
+    separated list of sections of the database cfg (trainers/trainer.py:303-326, evaluators/evaluator.py:38-55,
+    recognizer.py:42-48)."""
+    out = []
+    for name in names:
+        out.append([dict(dataconf.items(section)) for section in conf[name].split(' ')])
+    return out
+
+
+def source_from_conf(conf, dataconf, input_names, target_names, device='cpu', **kw):
+    """BatchSource over the data sections `conf` names (trainer: shuffled, bucketed, variable batch size as its cfg
+    says; evaluator / recognizer: one bucket, their own batch_size)."""
+    confs = dataconfs_for(conf, dataconf, list(input_names) + list(target_names))
+    return BatchSource(confs, input_names, target_names, batch_size=int(conf['batch_size']), device=device, **kw)

@@ -1,5 +1,7 @@
 """GPU parity tests, model level: the Python mirror of nabu's plugin API (Model / Trainer / losses)
 driving the CUDA kernels, against the NumPy oracle on shared weights and seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -175,3 +177,71 @@ def test_loss_evaluator_and_validation_in_train_loop(capsys):
     # lr = 0: the validation loss repeats -> step 0 better (saved), step 2 worse (try 1), step 4 worse -> terminate
     assert out.count('validating model') == 3 and 'terminating training' in out
     assert tr2.global_step == 0                        # the terminate path restores the validated model (saved at step 0)
+
+
+def test_train_validate_recognize_from_nabu_data_directories(tmp_path, capsys):
+    """Rows f1 + f2 end to end: data prepared in nabu's on-disk format (TFRecord files, pointers.scp, metadata) ->
+    Trainer.train with the sections named in trainer.cfg / database.conf (bucketed, variable batch size), validation by
+    a loss evaluator reading its own sections, then Recognizer.recognize writing the decoded set."""
+    import configparser
+    from tests.test_processing import _write_stream
+    from nabu_b200.neuralnetworks.recognizer import Recognizer
+    from nabu_b200.neuralnetworks.trainers import trainer_factory
+    dev = torch.device('cuda', 0)
+    rng = np.random.default_rng(3)
+    alphabet = ['a', 'b', 'c', 'd', 'e']
+    D = 40
+
+    def make_set(tag, n):
+        lens = rng.integers(20, 60, size=n)
+        feats = [('%s%d' % (tag, i), rng.standard_normal((L, D)).astype(np.float32)) for i, L in enumerate(lens)]
+        texts = [('%s%d' % (tag, i), ' '.join(rng.choice(alphabet, size=max(1, L // 12)))) for i, L in enumerate(lens)]
+        fdir, tdir = str(tmp_path / (tag + 'fbank')), str(tmp_path / (tag + 'text'))
+        _write_stream(fdir, 'audio', feats, dim=D)
+        _write_stream(tdir, 'text', texts, alphabet=alphabet)
+        return fdir, tdir
+
+    trf, trt = make_set('train', 24)
+    dvf, dvt = make_set('dev', 8)
+    dataconf = configparser.ConfigParser()
+    dataconf.read_string('[trainfbank]\ndir = %s\ntype = audio_feature\n[traintext]\ndir = %s\ntype = string_eos\n'
+                         '[devfbank]\ndir = %s\ntype = audio_feature\n[devtext]\ndir = %s\ntype = string_eos\n'
+                         % (trf, trt, dvf, dvt))
+    V = len(alphabet) + 1                    # + EOS (string_eos appends it); CTC adds its blank through trainlabels
+    mconf = make_conf('[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = dblstm\n'
+                      'num_units = 64\nnum_layers = 2\ninput_noise = 0\ndropout = 1\n[decoder]\ndecoder = dnn_decoder\n'
+                      'num_layers = 0\n' % V)
+    tconf = make_conf('[trainer]\ntrainer = standard\nloss = CTC\ntrainlabels = 1\ntargets = text\nnum_epochs = 2\n'
+                      'batch_size = 4\nnumbuckets = 3\nvariable_batch_size = True\nvalid_frequency = 3\nnum_tries = None\n'
+                      'features = trainfbank\ntext = traintext\n')
+    econf = make_conf('[evaluator]\nevaluator = loss_evaluator\nloss = CTC\ntargets = text\nbatch_size = 4\n'
+                      'features = devfbank\ntext = devtext\n')
+    expdir = str(tmp_path / 'exp')
+    tr = trainer_factory.factory('standard')(tconf, dataconf, mconf, econf, expdir, None, 0, device=dev, seed=2)
+    from nabu_b200.processing import input_pipeline
+    tr.val_source = input_pipeline.source_from_conf(dict(econf.items('evaluator')), dataconf, ['features'], ['text'],
+                                                    device=dev)
+    tr.train()
+    out = capsys.readouterr().out
+    assert tr.global_step == tr.num_steps and tr.num_steps > 0
+    assert out.count('validating model') >= 2 and 'validation loss' in out
+    assert os.path.isfile(os.path.join(expdir, 'model', 'network.pt'))
+    rconf = make_conf('[recognizer]\nbatch_size = 3\nfeatures = devfbank\n[decoder]\ndecoder = ctc_decoder\n'
+                      'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']))
+    directory = Recognizer(tr.model, rconf, dataconf, expdir).recognize()
+    text = open(os.path.join(directory, 'text')).read()
+    lines = text.strip().split('\n')
+    assert len(lines) == 8 and sorted(l.split(' ')[0] for l in lines) == sorted('dev%d' % i for i in range(8))
+    # row f3: the TF checkpoint SaveAtEnd wrote carries the reference's variable names; a model that has no variables
+    # yet (another seed) restores from it inside Recognizer.recognize and decodes the same text
+    from nabu_b200.neuralnetworks.models.model import Model
+    from nabu_b200.processing import tfcheckpoint
+    saved = dict((n, s) for n, s, _ in tfcheckpoint.list_variables(os.path.join(expdir, 'model', 'network.ckpt')))
+    assert saved['DNNDecoder/text/outlayer/weights'] == (128, V + 1)
+    assert saved['DBLSTM/features/layer1/bidirectional_rnn/bw/layer_norm_basic_lstm_cell/kernel'] == (128 + 64, 256)
+    os.remove(os.path.join(expdir, 'model', 'network.pt'))
+    fresh = Model(mconf, 1, seed=99)
+    fresh.device = dev
+    directory = Recognizer(fresh, rconf, dataconf, expdir).recognize()
+    assert open(os.path.join(directory, 'text')).read() == text
+    assert torch.equal(fresh.store.theta, tr.model.store.theta)
