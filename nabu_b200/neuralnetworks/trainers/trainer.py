@@ -5,7 +5,9 @@ one gradient all-reduce when world_size > 1, elementwise clip(-1,1) + TF-Adam on
 `exponential_decay` learning rate.  The TF session / parameter-server / queue machinery of the
 reference (trainer.py:73-510) is replaced by a plain loop over a batch source: one process per
 GPU, synchronous data parallelism -- numerically the reference's `non_distributed` run at the
-global batch size.  Validation control flow is a "next" row (f2) and is not built here.
+global batch size.  The chief's validation / early-stopping branch (row f2) is `ValidationController`; data come
+from a batch source or from the database sections the cfg names (row f1); the final model is saved as a TF checkpoint
+under the reference's variable names (row f3).
 """
 import os
 import time
@@ -147,7 +149,7 @@ class Trainer(object, metaclass=ABCMeta):
         # validation (trainer.py:189-265, 646-733): evaluator named in the evaluator cfg, run by the chief every
         # valid_frequency steps on `val_source`
         evaluator, controller = None, None
-        if (self.evaluatorconf is not None and self.val_source is not None
+        if (self.evaluatorconf is not None and (self.val_source is not None or self.dataconf is not None)
                 and self.evaluatorconf.get('evaluator', 'evaluator') != 'None'):
             from ..evaluators import evaluator_factory
             evaluator = evaluator_factory.factory(self.evaluatorconf.get('evaluator', 'evaluator'))(

@@ -50,11 +50,14 @@ def bucket_boundaries(histogram, numbuckets):
     prefix = np.concatenate([[0.0], np.cumsum(counts)])         # prefix[j] = counts[:j].sum()
     out, start = [], 0
     for made in range(numbuckets - 1):
-        target = int((prefix[nbins] - prefix[start]) / (numbuckets - made))
+        # with more buckets than the data can fill, `start` runs past the histogram one bin per bucket (the
+        # reference's slices are empty there); its population is then zero
+        base = prefix[min(start, nbins)]
+        target = int((prefix[nbins] - base) / (numbuckets - made))
         if target == 0:
             print('%d buckets could not be reached, using %d buckets' % (numbuckets, made))
         edge = start + 1
-        while edge + 1 < nbins and abs(prefix[edge] - prefix[start] - target) >= abs(prefix[edge + 1] - prefix[start] - target):
+        while edge + 1 < nbins and abs(prefix[edge] - base - target) >= abs(prefix[edge + 1] - base - target):
             edge += 1
         out.append(edge)
         start = edge

@@ -30,6 +30,11 @@ h = np.zeros(120); h[40:60] = np.arange(20); h[100] = 500
 cases.append({'histogram': h.tolist(), 'numbuckets': 6, 'boundaries': [int(b) for b in ref(h, 6)]})
 h = np.zeros(64); h[[5, 17, 33, 63]] = [3, 1, 4, 1]
 cases.append({'histogram': h.tolist(), 'numbuckets': 5, 'boundaries': [int(b) for b in ref(h, 5)]})
+# more buckets than the data can fill: the boundaries run past the end of the histogram, one bin per bucket
+h = np.zeros(15); h[[9, 11, 12, 14]] = 1
+cases.append({'histogram': h.tolist(), 'numbuckets': 16, 'boundaries': [int(b) for b in ref(h, 16)]})
+h = np.zeros(6); h[3] = 7
+cases.append({'histogram': h.tolist(), 'numbuckets': 9, 'boundaries': [int(b) for b in ref(h, 9)]})
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'bucket_boundaries.json')
 json.dump(cases, open(out, 'w'))
 print('wrote %d cases to %s' % (len(cases), out))

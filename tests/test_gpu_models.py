@@ -218,10 +218,7 @@ def test_train_validate_recognize_from_nabu_data_directories(tmp_path, capsys):
                       'features = devfbank\ntext = devtext\n')
     expdir = str(tmp_path / 'exp')
     tr = trainer_factory.factory('standard')(tconf, dataconf, mconf, econf, expdir, None, 0, device=dev, seed=2)
-    from nabu_b200.processing import input_pipeline
-    tr.val_source = input_pipeline.source_from_conf(dict(econf.items('evaluator')), dataconf, ['features'], ['text'],
-                                                    device=dev)
-    tr.train()
+    tr.train()                               # the evaluator reads the sections validation_evaluator.cfg names
     out = capsys.readouterr().out
     assert tr.global_step == tr.num_steps and tr.num_steps > 0
     assert out.count('validating model') >= 2 and 'validation loss' in out

@@ -1,0 +1,91 @@
+"""The reference's only check, mirrored: `nabu/scripts/test_recipes.py:7-38` walks config/recipes and, per recipe, runs
+train / decode / test with `testing=True`, i.e. builds every graph and returns (trainers/trainer.py:610-611).  Here:
+every shipped recipe whose model is on the hot path (LAS/TIMIT, LAS/GP, DBLSTM/TIMIT) is read UNCHANGED from the
+reference tree -- model.cfg, trainer.cfg, validation_evaluator.cfg, recognizer.cfg -- and the trainer (model variables
+declared from the data's dimensions), the evaluator and the recognizer with its decoder are constructed from them over
+data directories in nabu's on-disk format.  The recipe files are not copied into this repo; the test is skipped where
+the reference tree is absent (the GPU box)."""
+import configparser
+import os
+
+import numpy as np
+import pytest
+
+from tests.test_processing import _write_stream
+
+RECIPES = '/root/reference/config/recipes'
+pytestmark = pytest.mark.skipif(not os.path.isdir(RECIPES), reason='reference tree not present')
+
+
+def _read(path):
+    conf = configparser.ConfigParser()
+    conf.read(path)
+    return conf
+
+
+def _database(tmp_path, sections, alphabet, dim=40):
+    """one tiny data directory per database section a cfg of the recipe names"""
+    rng = np.random.default_rng(0)
+    lines = []
+    for sec, kind in sorted(sections.items()):
+        d = str(tmp_path / sec)
+        lens = [9, 14, 11, 12]
+        if kind == 'audio_feature':
+            _write_stream(d, 'audio', [('u%d' % i, rng.standard_normal((L, dim)).astype(np.float32))
+                                       for i, L in enumerate(lens)], dim=dim)
+        else:
+            _write_stream(d, 'text', [('u%d' % i, ' '.join(rng.choice(alphabet, size=3))) for i in range(len(lens))],
+                          alphabet=alphabet)
+        lines.append('[%s]\ndir = %s\ntype = %s\n' % (sec, d, kind))
+    conf = configparser.ConfigParser()
+    conf.read_string(''.join(lines))
+    return conf
+
+
+def _sections(conf, section, names, kind, out):
+    for name in names:
+        for sec in conf.get(section, name).split(' '):
+            out[sec] = kind
+
+
+@pytest.mark.parametrize('recipe', ['LAS/TIMIT', 'LAS/GP', 'DBLSTM/TIMIT'])
+def test_recipe_builds(recipe, tmp_path):
+    from nabu_b200.neuralnetworks.evaluators import evaluator_factory
+    from nabu_b200.neuralnetworks.recognizer import Recognizer
+    from nabu_b200.neuralnetworks.trainers import trainer_factory
+    rdir = os.path.join(RECIPES, recipe)
+    mconf, tconf = _read(os.path.join(rdir, 'model.cfg')), _read(os.path.join(rdir, 'trainer.cfg'))
+    econf, rconf = _read(os.path.join(rdir, 'validation_evaluator.cfg')), _read(os.path.join(rdir, 'recognizer.cfg'))
+    inputs = mconf.get('io', 'inputs').split(' ')
+    outputs = mconf.get('io', 'outputs').split(' ')
+    dims = [int(d) for d in mconf.get('io', 'output_dims').split(' ')]
+    alphabet = ['s%d' % i for i in range(min(dims))]
+    sections = {}
+    _sections(tconf, 'trainer', inputs, 'audio_feature', sections)
+    _sections(tconf, 'trainer', tconf.get('trainer', 'targets').split(' '), 'string_eos', sections)
+    _sections(econf, 'evaluator', inputs, 'audio_feature', sections)
+    _sections(econf, 'evaluator', econf.get('evaluator', 'targets').split(' '), 'string_eos', sections)
+    _sections(rconf, 'recognizer', inputs, 'audio_feature', sections)
+    dataconf = _database(tmp_path, sections, alphabet)
+    tconf.set('trainer', 'batch_size', '2')          # four utterances per section here
+    trainer = trainer_factory.factory(tconf.get('trainer', 'trainer'))(
+        tconf, dataconf, mconf, econf, str(tmp_path / 'exp'), None, 0, device='cpu')
+    trainer.train(testing=True)
+    store = trainer.model.store
+    assert store.materialised and trainer.num_steps == len(trainer.batch_source) * int(trainer.conf['num_epochs'])
+    assert set(trainer.model.output_dims) == set(outputs)
+    scope = {'listener': 'Listener', 'dblstm': 'DBLSTM'}[mconf.get('encoder', 'encoder')]
+    assert any(v.name.startswith(scope + '/' + inputs[0] + '/layer0/') for v in store.order)
+    for out, d in zip(outputs, dims):
+        assert trainer.model.output_dims[out] == d + int(trainer.conf['trainlabels'])
+    evaluator = evaluator_factory.factory(econf.get('evaluator', 'evaluator'))(econf, dataconf, trainer.model)
+    assert evaluator.target_names == econf.get('evaluator', 'targets').split(' ')
+    recognizer = Recognizer(trainer.model, rconf, dataconf, str(tmp_path / 'exp'))
+    assert type(recognizer.decoder).__name__.lower().replace('_', '') == \
+        rconf.get('decoder', 'decoder').replace('_', '')
+
+
+def test_recipe_outside_the_hot_path_says_so():
+    from nabu_b200.neuralnetworks.models.model import Model
+    with pytest.raises(Exception, match='(?i)dnn|hot path|scope|unknown|undefined'):
+        Model(_read(os.path.join(RECIPES, 'DNN/WSJ/model.cfg')), 0).build({'features': 40}, 'cpu')
