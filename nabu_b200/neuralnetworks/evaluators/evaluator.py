@@ -29,18 +29,23 @@ class Evaluator(object, metaclass=ABCMeta):
         """the `loss` (and companion counter) variables of evaluator.py:68-76 at their initial value"""
         return {'loss': 0.0, 'count': 0.0}
 
-    def evaluate(self):
-        """Returns (validation loss, number of batches): init_validation + numbatches x update_loss."""
+    def source(self):
+        """the batch source: the one given, else the database sections the evaluator cfg names (evaluator.py:78-104:
+        one bucket, whole batches only)"""
         if self.batch_source is None:
             if self.dataconf is None:
                 raise Exception('Evaluator.evaluate needs a batch_source or a database configuration')
-            from ...processing import input_pipeline            # evaluator.py:78-104: one bucket, whole batches only
+            from ...processing import input_pipeline
             self.batch_source = input_pipeline.source_from_conf(
                 self.conf, self.dataconf, self.model.input_names, self.target_names,
-                device=getattr(self.model, 'device', 'cpu'))
+                device=getattr(self.model, 'device', 'cuda'))
+        return self.batch_source
+
+    def evaluate(self):
+        """Returns (validation loss, number of batches): init_validation + numbatches x update_loss."""
         state = self.init_loss()
         numbatches = 0
-        for batch in self.batch_source:
+        for batch in self.source():
             self.update_loss(state, *batch)
             numbatches += 1
         return state['loss'], numbatches

@@ -139,7 +139,8 @@ class Trainer(object, metaclass=ABCMeta):
             src = input_pipeline.source_from_conf(
                 self.conf, self.dataconf, self.model.input_names, [t for t in self.conf['targets'].split(' ') if t],
                 device=self.device, numbuckets=int(self.conf['numbuckets']),
-                variable_batch_size=self.conf['variable_batch_size'] == 'True', shuffle_seed=0)
+                variable_batch_size=self.conf['variable_batch_size'] == 'True', shuffle_seed=0,
+                rank=dist.get_rank() if self.world > 1 else 0, world=self.world)
             self.batch_source = src
         steps_per_epoch = len(src)
         self.num_steps = steps_per_epoch * int(self.conf['num_epochs'])

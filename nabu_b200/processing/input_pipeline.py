@@ -96,7 +96,7 @@ class BatchSource(object):
     `dataconfs` (inputs first), as trainers/trainer.py:404-415 does."""
 
     def __init__(self, dataconfs, input_names, target_names, batch_size, numbuckets=1, variable_batch_size=False,
-                 allow_smaller_final_batch=False, shuffle_seed=None, device='cpu'):
+                 allow_smaller_final_batch=False, shuffle_seed=None, device='cpu', rank=0, world=1):
         import torch
         self._torch = torch
         self.device = device
@@ -116,6 +116,12 @@ class BatchSource(object):
         self.input_dims = {n: self.readers[i].metadata['dim'] for i, n in enumerate(self.input_names)
                            if 'dim' in self.readers[i].metadata}
         self._epoch = 0
+        # synchronous data parallelism: every rank walks the SAME global batches (same seed, same order)
+        # and keeps utterances rank::world of each; equal shard sizes are what makes the mean of the ranks' batch means
+        # the global batch mean, so every batch size must divide
+        self.rank, self.world = int(rank), int(world)
+        if self.world > 1 and any(b % self.world for b in self.batch_sizes):
+            raise Exception('batch sizes %s are not divisible by the %d data-parallel ranks' % (self.batch_sizes, world))
 
     def __len__(self):
         return self.num_steps
@@ -126,6 +132,8 @@ class BatchSource(object):
 
     def _emit(self, items):
         torch = self._torch
+        if self.world > 1:
+            items = items[self.rank::self.world]
         streams = list(zip(*items))                     # per stream: list of (array, length)
         tensors, lengths = [], []
         for st in streams:

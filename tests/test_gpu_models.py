@@ -242,3 +242,56 @@ def test_train_validate_recognize_from_nabu_data_directories(tmp_path, capsys):
     directory = Recognizer(fresh, rconf, dataconf, expdir).recognize()
     assert open(os.path.join(directory, 'text')).read() == text
     assert torch.equal(fresh.store.theta, tr.model.store.theta)
+
+
+def test_scripts_train_test_decode_on_an_experiment_directory(tmp_path, capsys):
+    """The three per-experiment entry points (`run train|test|decode` end in nabu/scripts/{train,test,decode}.py):
+    everything is read from the cfg files of the experiment directory; the model travels from train to test / decode
+    as the TF checkpoint model/network.ckpt, as in the reference."""
+    from tests.test_processing import _write_stream
+    from nabu_b200.scripts import decode, test, train
+    rng = np.random.default_rng(5)
+    alphabet = ['a', 'b', 'c', 'd']
+    D = 40
+    sections = []
+    for tag, n in (('train', 16), ('dev', 4), ('test', 6)):
+        lens = rng.integers(20, 50, size=n)
+        fdir, tdir = str(tmp_path / (tag + 'fbank')), str(tmp_path / (tag + 'text'))
+        _write_stream(fdir, 'audio', [('%s%d' % (tag, i), rng.standard_normal((L, D)).astype(np.float32))
+                                      for i, L in enumerate(lens)], dim=D)
+        _write_stream(tdir, 'text', [('%s%d' % (tag, i), ' '.join(rng.choice(alphabet, size=max(1, L // 12))))
+                                     for i, L in enumerate(lens)], alphabet=alphabet)
+        sections.append('[%sfbank]\ndir = %s\ntype = audio_feature\n[%stext]\ndir = %s\ntype = string_eos\n'
+                        % (tag, fdir, tag, tdir))
+    expdir = str(tmp_path / 'exp')
+    os.makedirs(expdir)
+    V = len(alphabet) + 1
+    files = {
+        'database.conf': ''.join(sections),
+        'model.cfg': '[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = dblstm\n'
+                     'num_units = 64\nnum_layers = 2\ninput_noise = 0\ndropout = 1\n[decoder]\ndecoder = dnn_decoder\n'
+                     'num_layers = 0\n' % V,
+        'trainer.cfg': '[trainer]\ntrainer = standard\nloss = CTC\ntrainlabels = 1\ntargets = text\nnum_epochs = 2\n'
+                       'batch_size = 4\nnumbuckets = 2\nvalid_frequency = 3\nnum_tries = None\n'
+                       'features = trainfbank\ntext = traintext\n',
+        'validation_evaluator.cfg': '[evaluator]\nevaluator = loss_evaluator\nloss = CTC\ntargets = text\n'
+                                    'batch_size = 2\nfeatures = devfbank\ntext = devtext\n',
+        'test_evaluator.cfg': '[evaluator]\nevaluator = decoder_evaluator\ntargets = text\nbatch_size = 3\n'
+                              'features = testfbank\ntext = testtext\n[decoder]\ndecoder = ctc_decoder\n'
+                              'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']),
+        'recognizer.cfg': '[recognizer]\nbatch_size = 4\nfeatures = testfbank\n[decoder]\ndecoder = ctc_decoder\n'
+                          'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']),
+    }
+    for name, text in files.items():
+        with open(os.path.join(expdir, name), 'w') as fid:
+            fid.write(text)
+    tr = train.train(expdir, device=torch.device('cuda', 0))
+    out = capsys.readouterr().out
+    assert tr.global_step == tr.num_steps > 0 and 'validation loss' in out
+    assert os.path.isfile(os.path.join(expdir, 'model', 'network.ckpt.index'))
+    loss = test.test(expdir, device=torch.device('cuda', 0))
+    assert 0.0 <= loss and float(open(os.path.join(expdir, 'result')).read()) == loss      # label error rate
+    rec = decode.decode(expdir, device=torch.device('cuda', 0))
+    assert torch.equal(rec.model.store.theta, tr.model.store.theta)
+    lines = open(os.path.join(expdir, 'decoded', 'text')).read().strip().split('\n')
+    assert sorted(l.split(' ')[0] for l in lines) == sorted('test%d' % i for i in range(6))

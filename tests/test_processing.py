@@ -122,3 +122,26 @@ def test_readers_and_bucketed_batches(tmp_path):
     # fixed batch size, no buckets: num_steps = floor(#utterances / batch_size), the tail is dropped
     src = ip.BatchSource([[fconf], [tconf]], ['features'], ['text'], batch_size=4)
     assert len(src) == int(hist.sum() / 4) and sum(b[0]['features'].shape[0] for b in src) == 8
+
+
+def test_batch_source_shards_every_batch_over_the_ranks(tmp_path):
+    """Synchronous data parallelism from data directories: the ranks walk the same global batches and keep
+    utterances rank::world of each (SURVEY 8e); together they hold every global batch exactly once."""
+    rng = np.random.default_rng(1)
+    lens = [12, 30, 7, 25, 18, 9, 28, 14]
+    feats = [('utt%d' % i, rng.standard_normal((L, 3)).astype(np.float32)) for i, L in enumerate(lens)]
+    fdir = str(tmp_path / 'fbank')
+    _write_stream(fdir, 'audio', feats, dim=3)
+    fconf = {'dir': fdir, 'type': 'audio_feature'}
+    whole = list(ip.BatchSource([[fconf]], ['features'], [], batch_size=4, shuffle_seed=5))
+    parts = [list(ip.BatchSource([[fconf]], ['features'], [], batch_size=4, shuffle_seed=5, rank=r, world=2))
+             for r in range(2)]
+    assert len(whole) == len(parts[0]) == len(parts[1]) == 2
+    for g, p0, p1 in zip(whole, parts[0], parts[1]):
+        L = g[1]['features']
+        assert p0[1]['features'].tolist() == L[0::2].tolist() and p1[1]['features'].tolist() == L[1::2].tolist()
+        for r, p in enumerate((p0, p1)):
+            T = p[0]['features'].shape[1]
+            assert np.array_equal(p[0]['features'].numpy(), g[0]['features'][r::2, :T].numpy())
+    with pytest.raises(Exception, match='divisible'):
+        ip.BatchSource([[fconf]], ['features'], [], batch_size=3, rank=0, world=2)

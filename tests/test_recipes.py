@@ -89,3 +89,35 @@ def test_recipe_outside_the_hot_path_says_so():
     from nabu_b200.neuralnetworks.models.model import Model
     with pytest.raises(Exception, match='(?i)dnn|hot path|scope|unknown|undefined'):
         Model(_read(os.path.join(RECIPES, 'DNN/WSJ/model.cfg')), 0).build({'features': 40}, 'cpu')
+
+
+def test_scripts_build_from_an_experiment_directory(tmp_path):
+    """`run train|decode|test` copy the recipe into the experiment directory and call scripts/{train,decode,test}.py
+    on it; with testing=True these build everything and return (scripts/test_recipe.py:21-33)."""
+    import shutil
+    from nabu_b200.scripts import decode, test, train
+    rdir = os.path.join(RECIPES, 'DBLSTM/TIMIT')
+    expdir = str(tmp_path / 'exp')
+    os.makedirs(expdir)
+    for name in ('model.cfg', 'trainer.cfg', 'validation_evaluator.cfg', 'test_evaluator.cfg', 'recognizer.cfg'):
+        shutil.copy(os.path.join(rdir, name), expdir)
+    tconf, econf = _read(os.path.join(rdir, 'trainer.cfg')), _read(os.path.join(rdir, 'validation_evaluator.cfg'))
+    xconf, rconf = _read(os.path.join(rdir, 'test_evaluator.cfg')), _read(os.path.join(rdir, 'recognizer.cfg'))
+    sections = {}
+    for conf, sec in ((tconf, 'trainer'), (econf, 'evaluator'), (xconf, 'evaluator')):
+        _sections(conf, sec, ['features'], 'audio_feature', sections)
+        _sections(conf, sec, conf.get(sec, 'targets').split(' '), 'string_eos', sections)
+    _sections(rconf, 'recognizer', ['features'], 'audio_feature', sections)
+    dims = int(_read(os.path.join(rdir, 'model.cfg')).get('io', 'output_dims'))
+    dataconf = _database(tmp_path, sections, ['s%d' % i for i in range(dims)])
+    with open(os.path.join(expdir, 'database.conf'), 'w') as fid:
+        dataconf.write(fid)
+    tconf.set('trainer', 'batch_size', '2')          # four utterances per section here
+    with open(os.path.join(expdir, 'trainer.cfg'), 'w') as fid:
+        tconf.write(fid)
+    tr = train.train(expdir, testing=True, device='cpu')
+    assert tr.model.store.materialised and tr.num_steps > 0
+    rec = decode.decode(expdir, testing=True, device='cpu')
+    assert type(rec.decoder).__name__ == 'CTCDecoder'
+    ev = test.test(expdir, testing=True, device='cpu')
+    assert ev.target_names == ['text']
