@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from nabu_b200.processing import input_pipeline as ip
-from nabu_b200.processing import tfreaders, tfrecord
+from nabu_b200.processing import tfreaders, tfrecord, tfwriters
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -53,28 +53,40 @@ def test_bucket_boundaries_match_the_reference_function():
 
 
 def _write_stream(root, kind, items, dim=None, alphabet=None):
-    """a nabu data directory: pointers.scp, data/file<i>, max_length, sequence_length_histogram.npy, dim | alphabet"""
-    os.makedirs(os.path.join(root, 'data'))
-    lengths = []
-    with open(os.path.join(root, 'pointers.scp'), 'w') as scp:
-        for i, (name, value) in enumerate(items):
-            f = os.path.join(root, 'data', 'file%d' % i)
-            if kind == 'audio':
-                ex = tfrecord.make_example({'shape': np.array(value.shape, np.int32).tobytes(),
-                                            'data': value.reshape(-1).astype(np.float32).tobytes()})
-                lengths.append(value.shape[0])
-            else:
-                ex = tfrecord.make_example({'length': [len(value.split(' '))], 'data': value.encode()})
-                lengths.append(len(value.split(' ')))
-            tfrecord.write_records(f, [ex])
-            scp.write('%s\t%s\n' % (name, f))
-    open(os.path.join(root, 'max_length'), 'w').write(str(max(lengths)))
-    np.save(os.path.join(root, 'sequence_length_histogram.npy'), np.bincount(lengths, minlength=max(lengths) + 1))
+    """a nabu data directory (pointers.scp, data/file<i>, max_length, sequence_length_histogram.npy, dim | alphabet)
+    written by the package's own writers"""
+    writer = tfwriters.factory('audio_feature' if kind == 'audio' else 'string_eos')(root)
+    for name, value in items:
+        writer.write(value, name)
     if kind == 'audio':
-        open(os.path.join(root, 'dim'), 'w').write(str(dim))
+        writer.write_metadata(dim)
     else:
-        open(os.path.join(root, 'alphabet'), 'w').write(' '.join(alphabet))
-        open(os.path.join(root, 'nonesymbol'), 'w').write('<none>')
+        writer.write_metadata(alphabet)
+
+
+def test_writers_lay_out_a_nabu_data_directory(tmp_path):
+    """byte-level layout against the format description, independent of the readers"""
+    root = str(tmp_path / 'fbank')
+    w = tfwriters.factory('audio_feature')(root)
+    x = np.arange(6, dtype=np.float32).reshape(3, 2)
+    w.write(x, 'utt a')
+    w.write(np.zeros((5, 2), np.float32), 'uttb')
+    w.write_metadata(2)
+    assert open(os.path.join(root, 'pointers.scp')).read() == 'utt a\t%s/data/file0\nuttb\t%s/data/file1\n' % (root, root)
+    assert open(os.path.join(root, 'max_length')).read() == '5' and open(os.path.join(root, 'dim')).read() == '2'
+    assert np.load(os.path.join(root, 'sequence_length_histogram.npy')).tolist() == [0, 0, 0, 1, 0, 1]
+    (rec,) = list(tfrecord.read_records(os.path.join(root, 'data', 'file0')))
+    ex = tfrecord.parse_example(rec)
+    assert ex['shape'] == [np.array([3, 2], np.int32).tobytes()] and ex['data'] == [x.tobytes()]
+    root = str(tmp_path / 'text')
+    w = tfwriters.factory('string_eos')(root)
+    w.write('b a d', 'utt a')
+    w.write_metadata(['a', 'b', 'c', 'd'])
+    ex = tfrecord.parse_example(next(iter(tfrecord.read_records(os.path.join(root, 'data', 'file0')))))
+    assert ex['data'] == [b'b a d'] and list(ex['length']) == [5]             # string_writer.py: len of the STRING
+    assert open(os.path.join(root, 'alphabet')).read() == 'a b c d' and open(os.path.join(root, 'max_length')).read() == '3'
+    with pytest.raises(Exception, match='hybrid'):
+        tfwriters.factory('alignment')
 
 
 def test_readers_and_bucketed_batches(tmp_path):

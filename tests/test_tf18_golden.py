@@ -129,7 +129,7 @@ def _self_made_case(path):
     from nabu_b200.neuralnetworks.models.model import Model
     os.makedirs(path)
     cfgs = {'model.cfg': '[io]\ninputs = features\noutputs = text\noutput_dims = 7\n[encoder]\nencoder = dblstm\n'
-                         'num_units = 16\nnum_layers = 2\ninput_noise = 0\ndropout = 1\n[decoder]\n'
+                         'num_units = 64\nnum_layers = 2\ninput_noise = 0\ndropout = 1\n[decoder]\n'
                          'decoder = dnn_decoder\nnum_layers = 0\n',
             'trainer.cfg': '[trainer]\ntrainer = standard\nloss = CTC\ntrainlabels = 1\ntargets = text\n',
             'recognizer.cfg': '[recognizer]\nbatch_size = 4\n[decoder]\ndecoder = ctc_decoder\n'
