@@ -248,43 +248,9 @@ def test_scripts_train_test_decode_on_an_experiment_directory(tmp_path, capsys):
     """The three per-experiment entry points (`run train|test|decode` end in nabu/scripts/{train,test,decode}.py):
     everything is read from the cfg files of the experiment directory; the model travels from train to test / decode
     as the TF checkpoint model/network.ckpt, as in the reference."""
-    from tests.test_processing import _write_stream
     from nabu_b200.scripts import decode, test, train
-    rng = np.random.default_rng(5)
-    alphabet = ['a', 'b', 'c', 'd']
-    D = 40
-    sections = []
-    for tag, n in (('train', 16), ('dev', 4), ('test', 6)):
-        lens = rng.integers(20, 50, size=n)
-        fdir, tdir = str(tmp_path / (tag + 'fbank')), str(tmp_path / (tag + 'text'))
-        _write_stream(fdir, 'audio', [('%s%d' % (tag, i), rng.standard_normal((L, D)).astype(np.float32))
-                                      for i, L in enumerate(lens)], dim=D)
-        _write_stream(tdir, 'text', [('%s%d' % (tag, i), ' '.join(rng.choice(alphabet, size=max(1, L // 12))))
-                                     for i, L in enumerate(lens)], alphabet=alphabet)
-        sections.append('[%sfbank]\ndir = %s\ntype = audio_feature\n[%stext]\ndir = %s\ntype = string_eos\n'
-                        % (tag, fdir, tag, tdir))
-    expdir = str(tmp_path / 'exp')
-    os.makedirs(expdir)
-    V = len(alphabet) + 1
-    files = {
-        'database.conf': ''.join(sections),
-        'model.cfg': '[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = dblstm\n'
-                     'num_units = 64\nnum_layers = 2\ninput_noise = 0\ndropout = 1\n[decoder]\ndecoder = dnn_decoder\n'
-                     'num_layers = 0\n' % V,
-        'trainer.cfg': '[trainer]\ntrainer = standard\nloss = CTC\ntrainlabels = 1\ntargets = text\nnum_epochs = 2\n'
-                       'batch_size = 4\nnumbuckets = 2\nvalid_frequency = 3\nnum_tries = None\n'
-                       'features = trainfbank\ntext = traintext\n',
-        'validation_evaluator.cfg': '[evaluator]\nevaluator = loss_evaluator\nloss = CTC\ntargets = text\n'
-                                    'batch_size = 2\nfeatures = devfbank\ntext = devtext\n',
-        'test_evaluator.cfg': '[evaluator]\nevaluator = decoder_evaluator\ntargets = text\nbatch_size = 3\n'
-                              'features = testfbank\ntext = testtext\n[decoder]\ndecoder = ctc_decoder\n'
-                              'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']),
-        'recognizer.cfg': '[recognizer]\nbatch_size = 4\nfeatures = testfbank\n[decoder]\ndecoder = ctc_decoder\n'
-                          'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']),
-    }
-    for name, text in files.items():
-        with open(os.path.join(expdir, name), 'w') as fid:
-            fid.write(text)
+    from tests.util import write_experiment
+    expdir = write_experiment(str(tmp_path))
     tr = train.train(expdir, device=torch.device('cuda', 0))
     out = capsys.readouterr().out
     assert tr.global_step == tr.num_steps > 0 and 'validation loss' in out

@@ -105,7 +105,7 @@ def _check_cuda_case(case):
     assert np.array_equal(logit_len[o_name].cpu().numpy(), out['logits_len'])
     for b, n in enumerate(out['logits_len']):
         assert rel_err(got[b, :n], out['logits'][b, :n]) < TOL
-    assert abs(float(loss) - float(out['loss'])) / abs(float(out['loss'])) < TOL
+    assert abs(float(loss.detach()) - float(out["loss"])) / abs(float(out["loss"])) < TOL
     for name, g in model.store.grads_numpy().items():
         assert rel_err(g, out['grad/' + name]) < 5 * TOL, name
     decoder = decoder_factory.factory(conf['recognizer.cfg'].get('decoder', 'decoder'))(conf['recognizer.cfg'], model)

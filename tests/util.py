@@ -51,3 +51,50 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def write_experiment(root, num_epochs=2, variable_batch_size=True, n_train=16):
+    """An experiment directory as `run train` prepares it (database.conf, model.cfg, trainer.cfg,
+    validation_evaluator.cfg, test_evaluator.cfg, recognizer.cfg) over small data directories in nabu's on-disk
+    format under `root`: DBLSTM 2x64 + CTC on 40-dim features, 4 symbols.  Returns the experiment directory."""
+    import os
+    from nabu_b200.processing import tfwriters
+    rng = np.random.default_rng(5)
+    alphabet = ['a', 'b', 'c', 'd']
+    D = 40
+    sections = []
+    for tag, n in (('train', n_train), ('dev', 4), ('test', 6)):
+        lens = rng.integers(20, 50, size=n)
+        fdir, tdir = os.path.join(root, tag + 'fbank'), os.path.join(root, tag + 'text')
+        fw, tw = tfwriters.factory('audio_feature')(fdir), tfwriters.factory('string_eos')(tdir)
+        for i, L in enumerate(lens):
+            fw.write(rng.standard_normal((L, D)).astype(np.float32), '%s%d' % (tag, i))
+            tw.write(' '.join(rng.choice(alphabet, size=max(1, L // 12))), '%s%d' % (tag, i))
+        fw.write_metadata(D)
+        tw.write_metadata(alphabet)
+        sections.append('[%sfbank]\ndir = %s\ntype = audio_feature\n[%stext]\ndir = %s\ntype = string_eos\n'
+                        % (tag, fdir, tag, tdir))
+    expdir = os.path.join(root, 'exp')
+    os.makedirs(expdir)
+    V = len(alphabet) + 1                    # + EOS (string_eos appends it); CTC adds its blank through trainlabels
+    files = {
+        'database.conf': ''.join(sections),
+        'model.cfg': '[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = dblstm\n'
+                     'num_units = 64\nnum_layers = 2\ninput_noise = 0\ndropout = 1\n[decoder]\ndecoder = dnn_decoder\n'
+                     'num_layers = 0\n' % V,
+        'trainer.cfg': '[trainer]\ntrainer = standard\nloss = CTC\ntrainlabels = 1\ntargets = text\nnum_epochs = %d\n'
+                       'batch_size = 4\nnumbuckets = 2\nvariable_batch_size = %s\nvalid_frequency = 3\n'
+                       'num_tries = None\nfeatures = trainfbank\ntext = traintext\n'
+                       % (num_epochs, variable_batch_size),
+        'validation_evaluator.cfg': '[evaluator]\nevaluator = loss_evaluator\nloss = CTC\ntargets = text\n'
+                                    'batch_size = 2\nfeatures = devfbank\ntext = devtext\n',
+        'test_evaluator.cfg': '[evaluator]\nevaluator = decoder_evaluator\ntargets = text\nbatch_size = 3\n'
+                              'features = testfbank\ntext = testtext\n[decoder]\ndecoder = ctc_decoder\n'
+                              'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']),
+        'recognizer.cfg': '[recognizer]\nbatch_size = 4\nfeatures = testfbank\n[decoder]\ndecoder = ctc_decoder\n'
+                          'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']),
+    }
+    for name, text in files.items():
+        with open(os.path.join(expdir, name), 'w') as fid:
+            fid.write(text)
+    return expdir
