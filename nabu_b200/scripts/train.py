@@ -22,7 +22,8 @@ def train(expdir, testing=False, device=None):
         local_rank = int(os.environ.get('LOCAL_RANK', '0'))
         device = torch.device('cuda', local_rank)
         torch.cuda.set_device(device)
-    if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
+    own_group = int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized()
+    if own_group:
         dist.init_process_group('nccl' if torch.device(device).type == 'cuda' else 'gloo')
     if dist.is_available() and dist.is_initialized():
         task_index = dist.get_rank()
@@ -31,6 +32,9 @@ def train(expdir, testing=False, device=None):
         server=None, task_index=task_index, device=device)
     print('starting training')
     tr.train(testing)
+    if own_group:
+        dist.barrier()
+        dist.destroy_process_group()
     return tr
 
 
