@@ -187,24 +187,46 @@ def _i32(t, device):
     return t.to(device=device, dtype=torch.int32).contiguous()
 
 
+def _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT):
+    lib = L.load()
+    B, T, D = x.shape
+    y = torch.empty((B, yT, 2 * H), device=x.device, dtype=torch.float32)
+    gates = torch.empty((2, B, T, 4 * H), device=x.device, dtype=torch.float32)
+    cells = torch.empty((2, B, T, H), device=x.device, dtype=torch.float32)
+    nws = lib.nabu_blstm_workspace_bytes(B, T, D, H)
+    if nws == 0:
+        L.check(2, 'nabu_blstm_workspace_bytes')
+    ws = L.WORKSPACE.get(nws, x.device)
+    L.check(lib.nabu_blstm_fwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(bf), L.ptr(kb), L.ptr(bb),
+                               L.ptr(y), yT, L.ptr(gates), L.ptr(cells), L.ptr(ws), ws.numel(), L.stream()),
+            'nabu_blstm_fwd')
+    return y, gates, cells
+
+
+def _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, need_dx, H, yT, gvars):
+    lib = L.load()
+    B, T, D = x.shape
+    dkf, dbf, dkb, dbb = gvars
+    dy = dy.contiguous()
+    dx = torch.empty_like(x) if need_dx else None
+    ws = L.WORKSPACE.get(lib.nabu_blstm_workspace_bytes(B, T, D, H), x.device)
+    L.check(lib.nabu_blstm_bwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(kb), L.ptr(y), yT,
+                               L.ptr(gates), L.ptr(cells), L.ptr(dy), L.ptr(dx), L.ptr(dkf), L.ptr(dbf),
+                               L.ptr(dkb), L.ptr(dbb), L.ptr(ws), ws.numel(), L.stream()),
+            'nabu_blstm_bwd')
+    if _OVERLAP['on']:
+        # deferred weight gradients read these on the library's side stream until side_join()
+        _OVERLAP['keep'].append((x, y, gates, kf, kb, gvars))
+    return dx
+
+
 class _BLSTM(torch.autograd.Function):
     """components/layer.py:8-51 via nabu_blstm_fwd / nabu_blstm_bwd."""
 
     @staticmethod
     def forward(ctx, x, lens, kf, bf, kb, bb, H, yT, gvars):
-        lib = L.load()
         x = x.contiguous()
-        B, T, D = x.shape
-        y = torch.empty((B, yT, 2 * H), device=x.device, dtype=torch.float32)
-        gates = torch.empty((2, B, T, 4 * H), device=x.device, dtype=torch.float32)
-        cells = torch.empty((2, B, T, H), device=x.device, dtype=torch.float32)
-        nws = lib.nabu_blstm_workspace_bytes(B, T, D, H)
-        if nws == 0:
-            L.check(2, 'nabu_blstm_workspace_bytes')
-        ws = L.WORKSPACE.get(nws, x.device)
-        L.check(lib.nabu_blstm_fwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(bf), L.ptr(kb), L.ptr(bb),
-                                   L.ptr(y), yT, L.ptr(gates), L.ptr(cells), L.ptr(ws), ws.numel(), L.stream()),
-                'nabu_blstm_fwd')
+        y, gates, cells = _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT)
         ctx.save_for_backward(x, lens, kf, kb, y, gates, cells)
         ctx.H, ctx.yT, ctx.gvars = H, yT, gvars
         ctx.need_dx = x.requires_grad
@@ -212,21 +234,8 @@ class _BLSTM(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        lib = L.load()
         x, lens, kf, kb, y, gates, cells = ctx.saved_tensors
-        B, T, D = x.shape
-        H, yT = ctx.H, ctx.yT
-        dkf, dbf, dkb, dbb = ctx.gvars
-        dy = dy.contiguous()
-        dx = torch.empty_like(x) if ctx.need_dx else None
-        ws = L.WORKSPACE.get(lib.nabu_blstm_workspace_bytes(B, T, D, H), x.device)
-        L.check(lib.nabu_blstm_bwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(kb), L.ptr(y), yT,
-                                   L.ptr(gates), L.ptr(cells), L.ptr(dy), L.ptr(dx), L.ptr(dkf), L.ptr(dbf),
-                                   L.ptr(dkb), L.ptr(dbb), L.ptr(ws), ws.numel(), L.stream()),
-                'nabu_blstm_bwd')
-        if _OVERLAP['on']:
-            # deferred weight gradients read these on the library's side stream until side_join()
-            _OVERLAP['keep'].append((x, y, gates))
+        dx = _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, ctx.need_dx, ctx.H, ctx.yT, ctx.gvars)
         return dx, None, None, None, None, None, None, None, None
 
 
@@ -246,11 +255,65 @@ def side_join():
         _OVERLAP['keep'].clear()
 
 
+REC_UNIT = 64        # the recurrence kernels tile the hidden units by 64 (csrc/blstm.cu: KC)
+
+
+def _pad_gates(w, H, Hp, rows_h):
+    """[(D+H) | 1, 4H] -> [(D+Hp) | 1, 4Hp]: every gate block i,j,f,o widened to Hp columns, the h rows to Hp, zeros"""
+    lead = w.shape[0] - H if rows_h else None
+    g = w.reshape(w.shape[:-1] + (4, H))
+    g = torch.nn.functional.pad(g, (0, Hp - H)).reshape(w.shape[:-1] + (4 * Hp,))
+    if rows_h:
+        g = torch.cat([g, g.new_zeros((Hp - H, 4 * Hp))], 0)
+        assert g.shape[0] == lead + Hp
+    return g.contiguous()
+
+
+def _unpad_gates(g, H, Hp, rows_h):
+    if rows_h:
+        g = g[:g.shape[0] - (Hp - H)]
+    return g.reshape(g.shape[:-1] + (4, Hp))[..., :H].reshape(g.shape[:-1] + (4 * H,))
+
+
+class _BLSTMPadded(torch.autograd.Function):
+    """num_units that is not a multiple of 64 (the reference takes any): the same kernels on Hp = ceil64(H) units.  The
+    extra units have zero weights and biases: every gate pre-activation is 0, so c' = c*sigmoid(1) + sigmoid(0)*tanh(0)
+    stays 0 from the zero initial state and h = 0 -- they contribute nothing forward or backward, and the valid
+    units' arithmetic is unchanged.  Costs a padded copy of the weights and a slice of the outputs per call."""
+
+    @staticmethod
+    def forward(ctx, x, lens, kf, bf, kb, bb, H, yT, gvars):
+        Hp = (H + REC_UNIT - 1) // REC_UNIT * REC_UNIT
+        x = x.contiguous()
+        pkf, pbf = _pad_gates(kf.detach(), H, Hp, True), _pad_gates(bf.detach(), H, Hp, False)
+        pkb, pbb = _pad_gates(kb.detach(), H, Hp, True), _pad_gates(bb.detach(), H, Hp, False)
+        yp, gates, cells = _blstm_fwd_raw(x, lens, pkf, pbf, pkb, pbb, Hp, yT)
+        ctx.save_for_backward(x, lens, pkf, pkb, yp, gates, cells)
+        ctx.H, ctx.Hp, ctx.yT, ctx.gvars = H, Hp, yT, gvars
+        ctx.need_dx = x.requires_grad
+        return torch.cat([yp[..., :H], yp[..., Hp:Hp + H]], -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, lens, pkf, pkb, yp, gates, cells = ctx.saved_tensors
+        H, Hp = ctx.H, ctx.Hp
+        dyp = dy.new_zeros(dy.shape[:-1] + (2 * Hp,))
+        dyp[..., :H] = dy[..., :H]
+        dyp[..., Hp:Hp + H] = dy[..., H:]
+        pgrads = (torch.empty_like(pkf), pkf.new_empty(4 * Hp), torch.empty_like(pkb), pkb.new_empty(4 * Hp))
+        dx = _blstm_bwd_raw(x, lens, pkf, pkb, yp, gates, cells, dyp, ctx.need_dx, Hp, ctx.yT, pgrads)
+        side_join()                                      # deferred weight gradients must have landed before the slices
+        for real, pg, rows_h in zip(ctx.gvars, pgrads, (True, False, True, False)):
+            real.copy_(_unpad_gates(pg, H, Hp, rows_h))
+        return dx, None, None, None, None, None, None, None, None
+
+
 def blstm(x, lens, vf_k, vf_b, vb_k, vb_b, H, yT=None):
     """x [B,T,D] -> y [B,yT,2H]; v*_ are engine.Variable."""
     yT = x.shape[1] if yT is None else yT
-    return _BLSTM.apply(x, lens, vf_k.data, vf_b.data, vb_k.data, vb_b.data, H, yT,
-                        (vf_k.grad, vf_b.grad, vb_k.grad, vb_b.grad))
+    fn = _BLSTM if H % REC_UNIT == 0 else _BLSTMPadded
+    return fn.apply(x, lens, vf_k.data, vf_b.data, vb_k.data, vb_b.data, H, yT,
+                    (vf_k.grad, vf_b.grad, vb_k.grad, vb_b.grad))
 
 
 def pyramid_lengths(lens, numsteps):

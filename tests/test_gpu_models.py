@@ -34,7 +34,8 @@ def _ctc_trainer(H, NL, V, dev, seed=3):
     return tr
 
 
-@pytest.mark.parametrize('B,T,H,NL,ragged', [(6, 40, 64, 2, True), (32, 200, 256, 2, True)])
+@pytest.mark.parametrize('B,T,H,NL,ragged', [(6, 40, 64, 2, True), (32, 200, 256, 2, True),
+                                              (6, 40, 100, 2, True)])     # 100: not a multiple of the 64-unit tile
 def test_dblstm_ctc_train_step_matches_oracle(B, T, H, NL, ragged):
     """cfg-1 (DBLSTM 2x256 + CTC, 29 labels, 32x200x40): loss, every gradient and the Adam update."""
     dev = torch.device('cuda', 0)

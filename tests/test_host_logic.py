@@ -170,3 +170,34 @@ def test_evaluator_factory_and_running_mean():
 
     val, n = Fixed([(2.0, 4.0, None, None), (1.0, 12.0, None, None)]).evaluate()
     assert n == 2 and abs(val - (2.0 * 4 + 1.0 * 12) / 16) < 1e-12
+
+
+def test_padding_num_units_to_the_kernel_tile_changes_nothing():
+    """engine._BLSTMPadded runs num_units that are not a multiple of 64 on ceil64 units with zero weights for the extra
+    ones.  The claim that this is exact (extra units stay at c = h = 0, valid units and every gradient unchanged) is
+    checked here with the oracle on the same pad / unpad functions the CUDA path uses."""
+    import numpy as np
+    import torch
+    import oracle as O
+    from nabu_b200 import engine
+    rng = np.random.default_rng(0)
+    B, T, D, H, Hp = 3, 9, 5, 6, 64
+    x = rng.standard_normal((B, T, D))
+    lens = np.array([9, 6, 8])
+    p = O.init_blstm_params(rng, D, H, np.float64)
+    pad = lambda w, rows: engine._pad_gates(torch.from_numpy(w), H, Hp, rows).numpy()
+    pp = {k: pad(v, k.endswith('kernel')) for k, v in p.items()}
+    assert pp['fw_kernel'].shape == (D + Hp, 4 * Hp) and pp['bw_bias'].shape == (4 * Hp,)
+    y, cache = O.blstm_fwd(x, lens, p)
+    yp, cachep = O.blstm_fwd(x, lens, pp)
+    assert np.all(yp[..., H:Hp] == 0) and np.all(yp[..., Hp + H:] == 0)
+    assert np.array_equal(np.concatenate([yp[..., :H], yp[..., Hp:Hp + H]], -1), y)
+    dy = rng.standard_normal(y.shape)
+    dyp = np.zeros(yp.shape)
+    dyp[..., :H], dyp[..., Hp:Hp + H] = dy[..., :H], dy[..., H:]
+    dx, g = O.blstm_bwd(cache, dy)
+    dxp, gp = O.blstm_bwd(cachep, dyp)
+    assert np.allclose(dxp, dx, rtol=0, atol=1e-15)
+    for k in g:
+        got = engine._unpad_gates(torch.from_numpy(gp[k]), H, Hp, k.endswith('kernel')).numpy()
+        assert np.allclose(got, g[k], rtol=0, atol=1e-15), k
