@@ -262,3 +262,22 @@ def test_scripts_train_test_decode_on_an_experiment_directory(tmp_path, capsys):
     assert torch.equal(rec.model.store.theta, tr.model.store.theta)
     lines = open(os.path.join(expdir, 'decoded', 'text')).read().strip().split('\n')
     assert sorted(l.split(' ')[0] for l in lines) == sorted('test%d' % i for i in range(6))
+
+
+def test_scripts_on_a_las_experiment_directory(tmp_path, capsys):
+    """The LAS/TIMIT recipe's shape end to end (listener + speller with the recipe's input noise / dropout, trained
+    with average_cross_entropy on EOS-terminated targets, validated by beam-search label error rate, tested by loss,
+    decoded with the beam search into n-best files) through the three entry points."""
+    from nabu_b200.scripts import decode, test, train
+    from tests.util import write_experiment
+    expdir = write_experiment(str(tmp_path), model='las')
+    tr = train.train(expdir, device=torch.device('cuda', 0))
+    out = capsys.readouterr().out
+    assert tr.global_step == tr.num_steps > 0 and 'validation loss' in out
+    loss = test.test(expdir, device=torch.device('cuda', 0))
+    assert np.isfinite(loss) and loss > 0
+    rec = decode.decode(expdir, device=torch.device('cuda', 0))
+    assert torch.equal(rec.model.store.theta, tr.model.store.theta)
+    nbest = open(os.path.join(expdir, 'decoded', 'test0')).read().strip().split('\n')
+    assert len(nbest) == 4 and all(float(l.split(' ')[0]) <= 0 for l in nbest)          # score, then the symbols
+    assert np.load(os.path.join(expdir, 'decoded', 'test0_alignments.npy')).shape[0] == 4

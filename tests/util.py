@@ -53,10 +53,12 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def write_experiment(root, num_epochs=2, variable_batch_size=True, n_train=16):
+def write_experiment(root, num_epochs=2, variable_batch_size=True, n_train=16, model='dblstm'):
     """An experiment directory as `run train` prepares it (database.conf, model.cfg, trainer.cfg,
     validation_evaluator.cfg, test_evaluator.cfg, recognizer.cfg) over small data directories in nabu's on-disk
-    format under `root`: DBLSTM 2x64 + CTC on 40-dim features, 4 symbols.  Returns the experiment directory."""
+    format under `root`: DBLSTM 2x64 + CTC (model='dblstm', the DBLSTM/TIMIT recipe's shape) or Listener 2x64 +
+    Speller + beam search (model='las', the LAS/TIMIT recipe's shape) on 40-dim features, 4 symbols.  Returns the
+    experiment directory."""
     import os
     from nabu_b200.processing import tfwriters
     rng = np.random.default_rng(5)
@@ -94,6 +96,20 @@ def write_experiment(root, num_epochs=2, variable_batch_size=True, n_train=16):
         'recognizer.cfg': '[recognizer]\nbatch_size = 4\nfeatures = testfbank\n[decoder]\ndecoder = ctc_decoder\n'
                           'text_alphabet = %s\n' % ' '.join(alphabet + ['<eos>']),
     }
+    if model == 'las':
+        beam = '[decoder]\ndecoder = beam_search_decoder\nmax_steps = 12\nbeam_width = 4\nalphabet = %s\n' \
+            % ' '.join(alphabet + ['<eos>'])
+        files.update({
+            'model.cfg': '[io]\ninputs = features\noutputs = text\noutput_dims = %d\n[encoder]\nencoder = listener\n'
+                         'input_noise = 0.6\nnum_layers = 2\nnum_units = 64\npyramid_steps = 2\ndropout = 0.5\n'
+                         '[decoder]\ndecoder = speller\nnum_layers = 2\nnum_units = 64\ndropout = 0.5\n' % (V - 1),
+            'trainer.cfg': files['trainer.cfg'].replace('loss = CTC', 'loss = average_cross_entropy'),
+            'validation_evaluator.cfg': '[evaluator]\nevaluator = decoder_evaluator\ntargets = text\nbatch_size = 2\n'
+                                        'features = devfbank\ntext = devtext\n' + beam,
+            'test_evaluator.cfg': '[evaluator]\nevaluator = loss_evaluator\nloss = average_cross_entropy\n'
+                                  'targets = text\nbatch_size = 3\nfeatures = testfbank\ntext = testtext\n',
+            'recognizer.cfg': '[recognizer]\nbatch_size = 4\nfeatures = testfbank\n' + beam,
+        })
     for name, text in files.items():
         with open(os.path.join(expdir, name), 'w') as fid:
             fid.write(text)
