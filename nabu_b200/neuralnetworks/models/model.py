@@ -42,6 +42,32 @@ class Model(object):
                                                    is_training)
         return logits, logit_seq_length
 
+    # ---- model/model.pkl (trainers/trainer.py:790-792, scripts/decode.py:46-48) --------------------------------
+    def description(self):
+        """What the reference's pickle of the Model object amounts to: the parsed model.cfg and the number of
+        train labels -- enough to rebuild the same model; the variables travel separately as model/network.ckpt."""
+        conf = {sec: dict(self.conf.items(sec)) for sec in self.conf.sections()}
+        trainlabels = self.output_dims[self.output_names[0]] - int(self.conf.get('io', 'output_dims').split(' ')[0])
+        return {'format': 'nabu_b200.model/1', 'conf': conf, 'trainlabels': trainlabels}
+
+    def save(self, path):
+        import pickle
+        with open(path, 'wb') as fid:
+            pickle.dump(self.description(), fid, protocol=2)
+
+    @staticmethod
+    def load(path, seed=0):
+        import configparser
+        import pickle
+        with open(path, 'rb') as fid:
+            desc = pickle.load(fid)
+        if not isinstance(desc, dict) or desc.get('format') != 'nabu_b200.model/1':
+            raise Exception('%s was not written by nabu_b200 (a pickled TF-graph builder of the reference cannot be '
+                            'loaded; rebuild from model.cfg and restore model/network.ckpt)' % path)
+        conf = configparser.ConfigParser()
+        conf.read_dict(desc['conf'])
+        return Model(conf, desc['trainlabels'], None, seed=seed)
+
     @property
     def variables(self):
         return self.encoder.variables + self.decoder.variables

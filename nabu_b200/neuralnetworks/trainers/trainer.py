@@ -188,6 +188,7 @@ class Trainer(object, metaclass=ABCMeta):
             # SaveAtEnd (components/hooks.py:30-52, trainer.py:615-619): the model variables as a TF checkpoint under
             # the reference's variable names -- readable by a nabu / TF-1.8 install and by Recognizer below
             self.model.store.save_tf_checkpoint(os.path.join(self.expdir, 'model', 'network.ckpt'))
+            self.model.save(os.path.join(self.expdir, 'model', 'model.pkl'))        # trainer.py:790-792
 
     # ---- ValidationSaveHook (hooks.py:54-86): every global variable, in memory -----------------------
     def _save_validated(self):

@@ -121,3 +121,49 @@ def test_scripts_build_from_an_experiment_directory(tmp_path):
     assert type(rec.decoder).__name__ == 'CTCDecoder'
     ev = test.test(expdir, testing=True, device='cpu')
     assert ev.target_names == ['text']
+
+
+def test_run_commands_prepare_the_experiment_directory(tmp_path):
+    """prepare_train / prepare_test / prepare_decode lay the directories out as the reference does (cfg copies,
+    <expdir>/test and <expdir>/decode with a symlink to the training run's model) and the entry points build from
+    them; model/model.pkl carries the model description from train to test / decode."""
+    from nabu_b200.scripts import decode, load_model, prepare, test, train
+    rdir = os.path.join(RECIPES, 'LAS/TIMIT')
+    recipe = str(tmp_path / 'recipe')
+    os.makedirs(recipe)
+    import shutil
+    for name in os.listdir(rdir):
+        shutil.copy(os.path.join(rdir, name), recipe)
+    confs = {n: _read(os.path.join(rdir, n)) for n in ('trainer.cfg', 'validation_evaluator.cfg', 'test_evaluator.cfg',
+                                                        'recognizer.cfg')}
+    sections = {}
+    for name, sec in (('trainer.cfg', 'trainer'), ('validation_evaluator.cfg', 'evaluator'),
+                      ('test_evaluator.cfg', 'evaluator')):
+        _sections(confs[name], sec, ['features'], 'audio_feature', sections)
+        _sections(confs[name], sec, confs[name].get(sec, 'targets').split(' '), 'string_eos', sections)
+    _sections(confs['recognizer.cfg'], 'recognizer', ['features'], 'audio_feature', sections)
+    dataconf = _database(tmp_path, sections, ['s%d' % i for i in range(39)])
+    with open(os.path.join(recipe, 'database.conf'), 'w') as fid:
+        dataconf.write(fid)
+    confs['trainer.cfg'].set('trainer', 'batch_size', '2')
+    with open(os.path.join(recipe, 'trainer.cfg'), 'w') as fid:
+        confs['trainer.cfg'].write(fid)
+    expdir = str(tmp_path / 'exp')
+    assert prepare.prepare_train(expdir, recipe, run=False) == expdir
+    assert sorted(os.listdir(expdir)) == ['database.conf', 'model', 'model.cfg', 'trainer.cfg',
+                                          'validation_evaluator.cfg']
+    tr = train.train(expdir, testing=True, device='cpu')
+    tr.model.save(os.path.join(expdir, 'model', 'model.pkl'))               # what Trainer.train does at its end
+    tdir = prepare.prepare_test(expdir, recipe, run=False)
+    ddir = prepare.prepare_decode(expdir, recipe, run=False)
+    assert sorted(os.listdir(tdir)) == ['database.conf', 'model', 'test_evaluator.cfg']
+    assert sorted(os.listdir(ddir)) == ['database.conf', 'model', 'recognizer.cfg']
+    assert os.path.islink(os.path.join(ddir, 'model'))
+    model = load_model(ddir).build({'features': 40}, 'cpu')
+    assert [(v.name, v.shape) for v in model.store.order] == [(v.name, v.shape) for v in tr.model.store.order]
+    assert type(decode.decode(ddir, testing=True, device='cpu').decoder).__name__ == 'BeamSearchDecoder'
+    assert test.test(tdir, testing=True, device='cpu').target_names == ['text']
+    with pytest.raises(Exception, match='multi_machine'):
+        prepare.prepare_train(str(tmp_path / 'x'), recipe, mode='multi_machine', run=False)
+    with pytest.raises(Exception, match='trained model'):
+        prepare.prepare_test(str(tmp_path / 'nothing'), recipe, run=False)
