@@ -96,7 +96,7 @@ class BatchSource(object):
     `dataconfs` (inputs first), as trainers/trainer.py:404-415 does."""
 
     def __init__(self, dataconfs, input_names, target_names, batch_size, numbuckets=1, variable_batch_size=False,
-                 allow_smaller_final_batch=False, shuffle_seed=None, device='cpu', rank=0, world=1):
+                 allow_smaller_final_batch=False, shuffle_seed=None, device='cpu', rank=0, world=1, prefetch=None):
         import torch
         self._torch = torch
         self.device = device
@@ -119,6 +119,9 @@ class BatchSource(object):
         # synchronous data parallelism: every rank walks the SAME global batches (same seed, same order)
         # and keeps utterances rank::world of each; equal shard sizes are what makes the mean of the ranks' batch means
         # the global batch mean, so every batch size must divide
+        # batches read, parsed and padded ahead of the consumer by ONE background thread (the reference's queue runners,
+        # processing/input_pipeline.py:133-168; one thread keeps the order deterministic); 0 = read in the caller
+        self.prefetch = int(os.environ.get('NABU_PREFETCH', '0')) if prefetch is None else int(prefetch)
         self.rank, self.world = int(rank), int(world)
         if self.world > 1 and any(b % self.world for b in self.batch_sizes):
             raise Exception('batch sizes %s are not divisible by the %d data-parallel ranks' % (self.batch_sizes, world))
@@ -130,15 +133,28 @@ class BatchSource(object):
         # bucket_by_sequence_length: bucket i holds lengths in [boundaries[i-1], boundaries[i])
         return int(np.searchsorted(np.asarray(self.boundaries), length, side='right')) if self.boundaries else 0
 
-    def _emit(self, items):
+    def _host_batch(self, items, pin=False):
+        """padded host tensors of one batch; `pin`: page-locked when they are going to a GPU, so that the copy can be
+        asynchronous (the prefetch thread's batches)"""
         torch = self._torch
         if self.world > 1:
             items = items[self.rank::self.world]
         streams = list(zip(*items))                     # per stream: list of (array, length)
+        pin = pin and torch.device(self.device).type == 'cuda' and torch.cuda.is_available()
         tensors, lengths = [], []
         for st in streams:
-            tensors.append(torch.from_numpy(_pad([a for a, _ in st])).to(self.device))
-            lengths.append(torch.tensor([l for _, l in st], dtype=torch.int32).to(self.device))
+            t = torch.from_numpy(_pad([a for a, _ in st]))
+            n = torch.tensor([l for _, l in st], dtype=torch.int32)
+            tensors.append(t.pin_memory() if pin else t)
+            lengths.append(n.pin_memory() if pin else n)
+        return tensors, lengths
+
+    def _emit(self, items):
+        return self._to_device(*self._host_batch(items))
+
+    def _to_device(self, tensors, lengths):
+        tensors = [t.to(self.device, non_blocking=t.is_pinned()) for t in tensors]
+        lengths = [n.to(self.device, non_blocking=n.is_pinned()) for n in lengths]
         ni = len(self.input_names)
         inputs = {n: tensors[i] for i, n in enumerate(self.input_names)}
         ilen = {n: lengths[i] for i, n in enumerate(self.input_names)}
@@ -147,6 +163,46 @@ class BatchSource(object):
         return inputs, ilen, targets, tlen
 
     def __iter__(self):
+        if self.prefetch <= 0:
+            for items in self._batches():
+                yield self._emit(items)
+            return
+        import queue
+        import threading
+        q = queue.Queue(maxsize=self.prefetch)
+        stop = threading.Event()
+
+        def produce():
+            try:
+                for items in self._batches():
+                    batch = self._host_batch(items, pin=True)
+                    while not stop.is_set():
+                        try:
+                            q.put(batch, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+                q.put(None)
+            except BaseException as e:                   # surfaces in the consumer, not in a dead thread
+                q.put(e)
+
+        worker = threading.Thread(target=produce, daemon=True)
+        worker.start()
+        try:
+            while True:
+                batch = q.get()
+                if batch is None:
+                    return
+                if isinstance(batch, BaseException):
+                    raise batch
+                yield self._to_device(*batch)
+        finally:
+            stop.set()
+
+    def _batches(self):
+        """the examples of one pass over the data, grouped into batches (lists of per-stream (array, length))"""
         order = list(range(len(self.elements)))
         if self.shuffle_seed is not None:
             np.random.default_rng(self.shuffle_seed + self._epoch).shuffle(order)
@@ -158,12 +214,12 @@ class BatchSource(object):
             b = self._bucket(item[0][1])
             buckets[b].append(item)
             if len(buckets[b]) == self.batch_sizes[b]:
-                yield self._emit(buckets[b])
+                yield buckets[b]
                 buckets[b] = []
         if self.allow_smaller_final_batch:
             for items in buckets:
                 if items:
-                    yield self._emit(items)
+                    yield items
 
 
 def dataconfs_for(conf, dataconf, names):

@@ -157,3 +157,28 @@ def test_batch_source_shards_every_batch_over_the_ranks(tmp_path):
             assert np.array_equal(p[0]['features'].numpy(), g[0]['features'][r::2, :T].numpy())
     with pytest.raises(Exception, match='divisible'):
         ip.BatchSource([[fconf]], ['features'], [], batch_size=3, rank=0, world=2)
+
+
+def test_prefetch_thread_yields_the_same_batches_in_the_same_order(tmp_path):
+    rng = np.random.default_rng(2)
+    lens = rng.integers(5, 40, size=23)
+    fdir = str(tmp_path / 'fbank')
+    _write_stream(fdir, 'audio', [('u%d' % i, rng.standard_normal((L, 4)).astype(np.float32))
+                                  for i, L in enumerate(lens)], dim=4)
+    fconf = {'dir': fdir, 'type': 'audio_feature'}
+    kw = dict(batch_size=4, numbuckets=3, variable_batch_size=True, allow_smaller_final_batch=True, shuffle_seed=1)
+    plain = ip.BatchSource([[fconf]], ['features'], [], **kw)
+    ahead = ip.BatchSource([[fconf]], ['features'], [], prefetch=2, **kw)
+    for epoch in range(2):                                   # the shuffle advances per epoch on both
+        a, b = list(plain), list(ahead)
+        assert len(a) == len(b) > 3
+        for x, y in zip(a, b):
+            assert np.array_equal(x[0]['features'].numpy(), y[0]['features'].numpy())
+            assert x[1]['features'].tolist() == y[1]['features'].tolist()
+    # a consumer that stops early does not leave the producer blocked; a reader error surfaces in the consumer
+    it = iter(ahead)
+    next(it)
+    it.close()
+    os.remove(os.path.join(fdir, 'data', 'file3'))
+    with pytest.raises(Exception):
+        list(ip.BatchSource([[fconf]], ['features'], [], prefetch=2, **kw))
