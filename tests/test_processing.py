@@ -112,6 +112,13 @@ def test_readers_and_bucketed_batches(tmp_path):
     assert ids.dtype == np.int32 and ids.tolist() == want and n == len(want)
     assert sr.metadata['eos_label'] == 4 and sr.metadata['max_length'] == max(1 + L // 6 for L in lens[:-1]) + 1
 
+    # the plain string reader of the CTC recipes (type = string): same ids, no EOS, lengths and histogram as written
+    pr = tfreaders.factory('string')([tdir])
+    ids2, n2 = pr(elements[1].split('\t')[1])
+    assert ids2.tolist() == want[:-1] and n2 == len(want) - 1 and ids2.dtype == np.int32
+    assert pr.metadata['max_length'] == sr.metadata['max_length'] - 1 and 'eos_label' not in pr.metadata
+    assert pr.metadata['sequence_length_histogram'].sum() == 9
+
     # batch plan restated: boundaries from the histogram of the FIRST stream, variable batch sizes, num_steps
     hist = ar.metadata['sequence_length_histogram']
     bounds = ip.bucket_boundaries(hist, 3)

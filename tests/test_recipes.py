@@ -23,11 +23,15 @@ def _read(path):
     return conf
 
 
-def _database(tmp_path, sections, alphabet, dim=40):
-    """one tiny data directory per database section a cfg of the recipe names"""
+def _database(tmp_path, sections, alphabet, dim=40, recipe=None):
+    """one tiny data directory per database section a cfg of the recipe names; the data type of a section is the one
+    the recipe's own database.cfg gives it (e.g. `string` for the CTC targets of DBLSTM/TIMIT), when it ships one"""
     rng = np.random.default_rng(0)
     lines = []
+    shipped = _read(os.path.join(recipe, 'database.cfg')) if recipe else None
     for sec, kind in sorted(sections.items()):
+        if shipped is not None and shipped.has_section(sec):
+            kind = shipped.get(sec, 'type')
         d = str(tmp_path / sec)
         lens = [9, 14, 11, 12]
         if kind == 'audio_feature':
@@ -66,7 +70,7 @@ def test_recipe_builds(recipe, tmp_path):
     _sections(econf, 'evaluator', inputs, 'audio_feature', sections)
     _sections(econf, 'evaluator', econf.get('evaluator', 'targets').split(' '), 'string_eos', sections)
     _sections(rconf, 'recognizer', inputs, 'audio_feature', sections)
-    dataconf = _database(tmp_path, sections, alphabet)
+    dataconf = _database(tmp_path, sections, alphabet, recipe=rdir)
     tconf.set('trainer', 'batch_size', '2')          # four utterances per section here
     trainer = trainer_factory.factory(tconf.get('trainer', 'trainer'))(
         tconf, dataconf, mconf, econf, str(tmp_path / 'exp'), None, 0, device='cpu')
@@ -109,7 +113,8 @@ def test_scripts_build_from_an_experiment_directory(tmp_path):
         _sections(conf, sec, conf.get(sec, 'targets').split(' '), 'string_eos', sections)
     _sections(rconf, 'recognizer', ['features'], 'audio_feature', sections)
     dims = int(_read(os.path.join(rdir, 'model.cfg')).get('io', 'output_dims'))
-    dataconf = _database(tmp_path, sections, ['s%d' % i for i in range(dims)])
+    dataconf = _database(tmp_path, sections, ['s%d' % i for i in range(dims)], recipe=rdir)
+    assert dataconf.get('traintext', 'type') == 'string'
     with open(os.path.join(expdir, 'database.conf'), 'w') as fid:
         dataconf.write(fid)
     tconf.set('trainer', 'batch_size', '2')          # four utterances per section here
