@@ -212,6 +212,30 @@ def cpu_step_fn(w):
         return step, desc
 
 
+def ctc_loss_delta(trainer, w, dev):
+    """The metric's second half ("CTC loss delta vs the CPU reference"): the CUDA model's CTC loss on a bounded slice
+    of the workload against the oracle (fp64) fed the SAME weights and inputs.  Outside every timed region."""
+    import torch
+    import oracle as O
+    s = w['sample']
+    x, lens, labels, ll = synth_batch(w, 0, s['B'], s['T'])
+    params = trainer.model.store.to_numpy()
+    with torch.no_grad():
+        t = lambda a: torch.from_numpy(a).to(dev)
+        batch = ({'features': t(x)}, {'features': t(lens)}, {'text': t(labels)}, {'text': t(ll)})
+        logits, logit_len = trainer.model(batch[0], batch[1], batch[2], batch[3], True)
+        cuda_loss = float(trainer.loss_fn(batch[2], logits, logit_len, batch[3]))
+    layers = []
+    for l in range(w['layers']):
+        base = 'DBLSTM/features/layer%d/bidirectional_rnn/%%s/layer_norm_basic_lstm_cell/%%s' % l
+        layers.append({'%s_%s' % (d, k): params[base % (d, k)] for d in ('fw', 'bw') for k in ('kernel', 'bias')})
+    lin = {'weights': params['DNNDecoder/text/outlayer/weights'], 'biases': params['DNNDecoder/text/outlayer/biases']}
+    enc, _, _ = O.dblstm_fwd(x, lens, layers)
+    cpu_loss, _ = O.ctc_loss_mean(O.linear_fwd(enc, lin), lens, labels, ll)
+    return {'value': abs(cuda_loss - cpu_loss) / abs(cpu_loss), 'cuda': cuda_loss, 'cpu_fp64': float(cpu_loss),
+            'tolerance': 1e-4, 'sample': '%dx%dx%d slice, the weights after the timed steps' % (s['B'], s['T'], w['D'])}
+
+
 def run_cpu(w, steps, warmup, budget_s=None):
     step, desc = cpu_step_fn(w)
     for _ in range(warmup):
@@ -415,6 +439,11 @@ def main():
         torch.set_num_threads(cores)
         fps, sec, desc, n = run_cpu(w, 3, 1, budget_s=30)
         out['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+        if w['kind'] == 'ctc':
+            try:
+                out['ctc_loss_delta_vs_cpu'] = ctc_loss_delta(trainer, w, dev)
+            except Exception as e:          # a reported extra: it must never cost the bench line
+                out['ctc_loss_delta_vs_cpu'] = {'value': None, 'error': '%s: %s' % (type(e).__name__, e)}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
