@@ -232,7 +232,7 @@ def ctc_loss_delta(trainer, w, dev):
     lin = {'weights': params['DNNDecoder/text/outlayer/weights'], 'biases': params['DNNDecoder/text/outlayer/biases']}
     enc, _, _ = O.dblstm_fwd(x, lens, layers)
     cpu_loss, _ = O.ctc_loss_mean(O.linear_fwd(enc, lin), lens, labels, ll)
-    return {'value': abs(cuda_loss - cpu_loss) / abs(cpu_loss), 'cuda': cuda_loss, 'cpu_fp64': float(cpu_loss),
+    return {'value': float(abs(cuda_loss - cpu_loss) / abs(cpu_loss)), 'cuda': cuda_loss, 'cpu_fp64': float(cpu_loss),
             'tolerance': 1e-4, 'sample': '%dx%dx%d slice, the weights after the timed steps' % (s['B'], s['T'], w['D'])}
 
 
