@@ -123,7 +123,7 @@ class ParamStore(object):
                 'names': [(v.name, v.shape, v.offset) for v in self.order]}
 
     # ---- TF checkpoint interop: the store's variable names ARE the reference's TF names --
-    def save_tf_checkpoint(self, prefix, with_adam=False, global_step=None):
+    def save_tf_checkpoint(self, prefix, with_adam=False, global_step=None, extra=None):
         """Write `<prefix>.index` / `.data-*` as `tf.train.Saver(model.variables, sharded=True).save` would
         (components/hooks.py:32-52 -> model/network.ckpt).  `with_adam` adds the optimizer slots under TF's names
         (`<var>/Adam`, `<var>/Adam_1`), what the reference's validated.ckpt holds besides the variables."""
@@ -138,6 +138,7 @@ class ParamStore(object):
                 arrays[var.name + '/Adam_1'] = v[sl].reshape(var.shape)
         if global_step is not None:
             arrays['global_step'] = np.array(global_step, np.int32)
+        arrays.update(extra or {})                # the trainer's other global variables (learning_rate_fact, ...)
         tfcheckpoint.write_checkpoint(prefix, arrays)
 
     def load_tf_checkpoint(self, prefix, with_adam=False):

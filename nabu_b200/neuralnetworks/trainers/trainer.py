@@ -157,6 +157,16 @@ class Trainer(object, metaclass=ABCMeta):
                 self.evaluatorconf, self.dataconf, self.model, batch_source=self.val_source)
             controller = ValidationController(self.conf, self._save_validated, self._restore_validated, self._half_lr)
             self._controller = controller
+        # MonitoredTrainingSession(checkpoint_dir=<expdir>/logdir) (trainer.py:625-633): every global variable is saved
+        # there periodically and training picks up from it when the directory already holds a checkpoint
+        if self.restore_checkpoint():
+            print('WORKER %d: resuming from step %d (%s)' % (self.task_index, self.global_step, self._checkpoint_path()))
+        last_save = time.time()
+        if self.device.type == 'cuda':
+            used_mb = lambda: torch.cuda.max_memory_allocated() / 1e6
+            total_mb = torch.cuda.get_device_properties(self.device).total_memory / 1e6
+        else:
+            used_mb, total_mb = (lambda: 0), 0
         terminated = False
         while self.global_step < self.num_steps and not terminated:
             for batch in src:
@@ -180,8 +190,11 @@ class Trainer(object, metaclass=ABCMeta):
                 print('WORKER %d: step %d/%d loss: %f, learning rate: %f \n\t time elapsed: %f sec'
                       '\n\t %.0f frames/sec, peak memory usage: %d/%d MB'
                       % (self.task_index, self.global_step - 1, self.num_steps, loss_v, lr, elapsed,
-                         frames / max(elapsed, 1e-9), torch.cuda.max_memory_allocated() / 1e6,
-                         torch.cuda.get_device_properties(self.device).total_memory / 1e6))
+                         frames / max(elapsed, 1e-9), used_mb(), total_mb))
+                if time.time() - last_save >= self.checkpoint_secs:
+                    self.save_checkpoint()
+                    last_save = time.time()
+        self.save_checkpoint()
         if self.expdir and self.task_index == 0:
             os.makedirs(os.path.join(self.expdir, 'model'), exist_ok=True)
             torch.save(self.model.store.state_dict(), os.path.join(self.expdir, 'model', 'network.pt'))
@@ -189,6 +202,54 @@ class Trainer(object, metaclass=ABCMeta):
             # the reference's variable names -- readable by a nabu / TF-1.8 install and by Recognizer below
             self.model.store.save_tf_checkpoint(os.path.join(self.expdir, 'model', 'network.ckpt'))
             self.model.save(os.path.join(self.expdir, 'model', 'model.pkl'))        # trainer.py:790-792
+
+    # ---- checkpoint / resume: <expdir>/logdir/model.ckpt, a TF bundle with the Adam slots and the trainer's scalars ----
+    checkpoint_secs = float(os.environ.get('NABU_CHECKPOINT_SECS', '600'))     # TF's save_checkpoint_secs default
+
+    def _checkpoint_path(self):
+        return os.path.join(self.expdir, 'logdir', 'model.ckpt') if self.expdir else None
+
+    def save_checkpoint(self):
+        """chief only; written under a temporary prefix and renamed, index last, so that a run killed while saving
+        leaves the previous checkpoint intact"""
+        path = self._checkpoint_path()
+        if path is None or self.task_index != 0:
+            return
+        import numpy as np
+        extra = {'learning_rate_fact': np.array(self.learning_rate_fact, np.float64)}
+        controller = getattr(self, '_controller', None)
+        if controller is not None:
+            extra['validated_step'] = np.array(controller.validated_step, np.int64)
+            extra['best_validation'] = np.array(controller.best_validation, np.float64)
+            extra['num_tries'] = np.array(controller.num_tries, np.int64)
+        tmp = path + '.tmp'
+        self.model.store.save_tf_checkpoint(tmp, with_adam=True, global_step=self.global_step, extra=extra)
+        for suffix in ('.data-00000-of-00001', '.index'):
+            os.replace(tmp + suffix, path + suffix)
+        with open(os.path.join(os.path.dirname(path), 'checkpoint'), 'w') as fid:
+            fid.write('model_checkpoint_path: "model.ckpt"\nall_model_checkpoint_paths: "model.ckpt"\n')
+
+    def restore_checkpoint(self):
+        """every rank; returns whether a checkpoint was found.  Like the reference's session restore it brings back the
+        variables, the optimizer slots, global_step and the validation state; the position inside the epoch is not
+        part of it (the reference's input queues restart as well)."""
+        path = self._checkpoint_path()
+        if path is None or not os.path.isfile(path + '.index'):
+            return False
+        from ...processing import tfcheckpoint
+        step = self.model.store.load_tf_checkpoint(path, with_adam=True)
+        have = set(n for n, _, _ in tfcheckpoint.list_variables(path))
+        names = [n for n in ('learning_rate_fact', 'validated_step', 'best_validation', 'num_tries') if n in have]
+        scalars = tfcheckpoint.read_checkpoint(path, names=set(names)) if names else {}
+        self.global_step = int(step) if step is not None else 0
+        if 'learning_rate_fact' in scalars:
+            self.learning_rate_fact = float(scalars['learning_rate_fact'])
+        controller = getattr(self, '_controller', None)
+        if controller is not None and 'validated_step' in scalars:
+            controller.validated_step = int(scalars['validated_step'])
+            controller.best_validation = float(scalars['best_validation'])
+            controller.num_tries = int(scalars['num_tries'])
+        return True
 
     # ---- ValidationSaveHook (hooks.py:54-86): every global variable, in memory -----------------------
     def _save_validated(self):
