@@ -176,6 +176,7 @@ class Trainer(object, metaclass=ABCMeta):
                     print('WORKER %d: validating model' % self.task_index)
                     validation_loss, _ = evaluator.evaluate()
                     print('WORKER %d: validation loss: %f' % (self.task_index, validation_loss))
+                    self._log_scalars(step=self.global_step, validation_loss=float(validation_loss))
                     if validation_loss >= controller.best_validation:
                         print('WORKER %d: validation loss is worse' % self.task_index)
                     if controller.update(validation_loss, self.global_step) == 'terminate':
@@ -191,6 +192,8 @@ class Trainer(object, metaclass=ABCMeta):
                       '\n\t %.0f frames/sec, peak memory usage: %d/%d MB'
                       % (self.task_index, self.global_step - 1, self.num_steps, loss_v, lr, elapsed,
                          frames / max(elapsed, 1e-9), used_mb(), total_mb))
+                self._log_scalars(step=self.global_step - 1, training_loss=loss_v, learning_rate=lr,
+                                  frames_per_sec=frames / max(elapsed, 1e-9))
                 if time.time() - last_save >= self.checkpoint_secs:
                     self.save_checkpoint()
                     last_save = time.time()
@@ -202,6 +205,16 @@ class Trainer(object, metaclass=ABCMeta):
             # the reference's variable names -- readable by a nabu / TF-1.8 install and by Recognizer below
             self.model.store.save_tf_checkpoint(os.path.join(self.expdir, 'model', 'network.ckpt'))
             self.model.save(os.path.join(self.expdir, 'model', 'model.pkl'))        # trainer.py:790-792
+
+    def _log_scalars(self, **scalars):
+        """the reference's tf.summary scalars (training_loss trainer.py:541, learning rate :269, validation loss :258,
+        written by FileWriter(<expdir>/logdir) :636) as one JSON object per line in <expdir>/logdir/metrics.jsonl"""
+        if not self.expdir or self.task_index != 0:
+            return
+        import json
+        os.makedirs(os.path.join(self.expdir, 'logdir'), exist_ok=True)
+        with open(os.path.join(self.expdir, 'logdir', 'metrics.jsonl'), 'a') as fid:
+            fid.write(json.dumps(scalars) + '\n')
 
     # ---- checkpoint / resume: <expdir>/logdir/model.ckpt, a TF bundle with the Adam slots and the trainer's scalars ----
     checkpoint_secs = float(os.environ.get('NABU_CHECKPOINT_SECS', '600'))     # TF's save_checkpoint_secs default

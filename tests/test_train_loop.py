@@ -31,8 +31,9 @@ class StandardTrainer(standard_trainer.StandardTrainer):      # same name: the d
             self.model.store.m.add_(frames * 1e-6)
             self.model.store.v.add_(1.0)
         self.seen.append(self.global_step)
+        lr = self.learning_rate()                     # the real update reads the rate before it advances the step
         self.global_step += 1
-        return torch.tensor(frames), self.learning_rate()
+        return torch.tensor(frames), lr
 
 
 def _trainer(expdir, seen, crash_at=None):
@@ -56,8 +57,12 @@ def test_train_loop_checkpoints_and_resumes(tmp_path, monkeypatch, capsys):
     assert ref.global_step == ref.num_steps == 12 and seen_ref == list(range(12))
     for name in ('network.pt', 'network.ckpt.index', 'network.ckpt.data-00000-of-00001', 'model.pkl'):
         assert os.path.isfile(os.path.join(ref_dir, 'model', name)), name
-    assert sorted(os.listdir(os.path.join(ref_dir, 'logdir'))) == ['checkpoint', 'model.ckpt.data-00000-of-00001',
-                                                                  'model.ckpt.index']
+    assert sorted(os.listdir(os.path.join(ref_dir, 'logdir'))) == ['checkpoint', 'metrics.jsonl',
+                                                                  'model.ckpt.data-00000-of-00001', 'model.ckpt.index']
+    import json
+    rows = [json.loads(l) for l in open(os.path.join(ref_dir, 'logdir', 'metrics.jsonl'))]
+    assert [r['step'] for r in rows] == list(range(12)) and all(r['training_loss'] > 0 for r in rows)
+    assert rows[0]['learning_rate'] == 1e-3 and rows[-1]['learning_rate'] < rows[0]['learning_rate']
     saved = dict((n, s) for n, s, _ in tfcheckpoint.list_variables(os.path.join(ref_dir, 'logdir', 'model.ckpt')))
     assert saved['global_step'] == () and 'learning_rate_fact' in saved
     assert any(n.endswith('/kernel/Adam_1') for n in saved)
