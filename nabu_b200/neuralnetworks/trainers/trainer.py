@@ -95,6 +95,7 @@ class Trainer(object, metaclass=ABCMeta):
         self.val_source = val_source
         self.device = torch.device(device if device is not None else 'cuda')
         self.global_step = 0
+        self.should_terminate = False
         self.learning_rate_fact = 1.0
         self.num_steps = None      # steps per epoch * num_epochs, set by train()
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -167,7 +168,7 @@ class Trainer(object, metaclass=ABCMeta):
             total_mb = torch.cuda.get_device_properties(self.device).total_memory / 1e6
         else:
             used_mb, total_mb = (lambda: 0), 0
-        terminated = False
+        terminated = self.should_terminate          # an early-stopped experiment stays stopped when started again
         while self.global_step < self.num_steps and not terminated:
             for batch in src:
                 if self.global_step >= self.num_steps:
@@ -181,7 +182,7 @@ class Trainer(object, metaclass=ABCMeta):
                         print('WORKER %d: validation loss is worse' % self.task_index)
                     if controller.update(validation_loss, self.global_step) == 'terminate':
                         print('WORKER %d: terminating training' % self.task_index)
-                        terminated = True
+                        terminated = self.should_terminate = True
                         break
                 start = time.time()
                 loss, lr = self.update(*batch)
@@ -229,7 +230,8 @@ class Trainer(object, metaclass=ABCMeta):
         if path is None or self.task_index != 0:
             return
         import numpy as np
-        extra = {'learning_rate_fact': np.array(self.learning_rate_fact, np.float64)}
+        extra = {'learning_rate_fact': np.array(self.learning_rate_fact, np.float64),
+                 'should_terminate': np.array(bool(self.should_terminate))}          # trainer.py:97-104
         controller = getattr(self, '_controller', None)
         if controller is not None:
             extra['validated_step'] = np.array(controller.validated_step, np.int64)
@@ -252,11 +254,14 @@ class Trainer(object, metaclass=ABCMeta):
         from ...processing import tfcheckpoint
         step = self.model.store.load_tf_checkpoint(path, with_adam=True)
         have = set(n for n, _, _ in tfcheckpoint.list_variables(path))
-        names = [n for n in ('learning_rate_fact', 'validated_step', 'best_validation', 'num_tries') if n in have]
+        names = [n for n in ('learning_rate_fact', 'validated_step', 'best_validation', 'num_tries', 'should_terminate')
+                 if n in have]
         scalars = tfcheckpoint.read_checkpoint(path, names=set(names)) if names else {}
         self.global_step = int(step) if step is not None else 0
         if 'learning_rate_fact' in scalars:
             self.learning_rate_fact = float(scalars['learning_rate_fact'])
+        if 'should_terminate' in scalars:
+            self.should_terminate = bool(scalars['should_terminate'])
         controller = getattr(self, '_controller', None)
         if controller is not None and 'validated_step' in scalars:
             controller.validated_step = int(scalars['validated_step'])

@@ -97,12 +97,14 @@ def test_validation_state_travels_with_the_checkpoint(tmp_path):
     tr.train(testing=True)
     tr._controller = ValidationController(tr.conf, lambda: None, lambda: None, lambda: None)
     tr._controller.validated_step, tr._controller.best_validation, tr._controller.num_tries = 6, 1.25, 1
-    tr.global_step, tr.learning_rate_fact = 7, 0.25
+    tr.global_step, tr.learning_rate_fact, tr.should_terminate = 7, 0.25, True
     tr.save_checkpoint()
     other = _trainer(expdir, [])
     other.train(testing=True)
     other._controller = ValidationController(other.conf, lambda: None, lambda: None, lambda: None)
     assert other.restore_checkpoint()
-    assert (other.global_step, other.learning_rate_fact) == (7, 0.25)
+    assert (other.global_step, other.learning_rate_fact, other.should_terminate) == (7, 0.25, True)
+    other.train()                                   # stopped early before: no further step is taken
+    assert other.global_step == 7 and other.seen == []
     assert (other._controller.validated_step, other._controller.best_validation, other._controller.num_tries) == (6, 1.25, 1)
     assert torch.equal(other.model.store.theta, tr.model.store.theta)
