@@ -317,3 +317,17 @@ def write_checkpoint(prefix, arrays, shard_of=None, num_shards=1, producer=26):
     with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), 'checkpoint'), 'w') as f:
         base = os.path.basename(prefix)
         f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
+
+
+if __name__ == '__main__':                      # python -m nabu_b200.processing.tfcheckpoint <prefix> [name]
+    import sys
+    if len(sys.argv) < 2:
+        raise SystemExit('usage: python -m nabu_b200.processing.tfcheckpoint <checkpoint prefix> [variable name]')
+    if len(sys.argv) == 2:
+        total = 0
+        for var_name, var_shape, var_dtype in list_variables(sys.argv[1]):
+            total += int(np.prod(var_shape, dtype=np.int64))
+            print('%-100s %-18s %s' % (var_name, var_shape, var_dtype))
+        print('%d values' % total)
+    else:
+        print(read_checkpoint(sys.argv[1], names={sys.argv[2]})[sys.argv[2]])
