@@ -49,9 +49,11 @@ def _check_oracle_case(case):
     params = model.store.to_numpy()
     assert set('grad/' + n for n in params) == set(k for k in out if k.startswith('grad/'))
     mc, tc = conf['model.cfg'], conf['trainer.cfg']
-    if (mc.get('encoder', 'encoder'), mc.get('decoder', 'decoder'), tc.get('trainer', 'loss')) != \
-            ('dblstm', 'dnn_decoder', 'CTC'):
-        pytest.skip('oracle composition for this recipe is exercised by the GPU test')
+    kind = (mc.get('encoder', 'encoder'), mc.get('decoder', 'decoder'), tc.get('trainer', 'loss'))
+    if kind == ('listener', 'speller', 'average_cross_entropy'):
+        return _check_las_oracle(mc, params, inp, out)
+    if kind != ('dblstm', 'dnn_decoder', 'CTC'):
+        pytest.skip('no oracle composition for %s / %s / %s' % kind)
     i_name, o_name = mc.get('io', 'inputs').split(' ')[0], mc.get('io', 'outputs').split(' ')[0]
     layers = []
     for l in range(int(mc.get('encoder', 'num_layers'))):
@@ -78,6 +80,61 @@ def _check_oracle_case(case):
             ids, _ = O.ctc_beam_search(logits[b].astype(np.float32), inp['features_len'][b])
             sel = out['decoded_indices'][:, 0] == b
             assert list(ids) == out['decoded_values'][sel].tolist()
+
+
+def _las_params(mc, params):
+    """the oracle's parameter dicts from the reference's variable names (listener layers, speller)"""
+    i_name = mc.get('io', 'inputs').split(' ')[0]
+    NL = int(mc.get('encoder', 'num_layers'))
+    layers = []
+    for l in range(NL + 1):
+        mid = 'BLSTM/' if l < NL else ''
+        base = 'Listener/%s/layer%d/%sbidirectional_rnn/%%s/layer_norm_basic_lstm_cell/%%s' % (i_name, l, mid)
+        layers.append({'%s_%s' % (d, k): params[base % (d, k)] for d in ('fw', 'bw') for k in ('kernel', 'bias')})
+    attention = mc.get('decoder', 'attention') if mc.has_option('decoder', 'attention') else 'vanilla'
+    scope = 'Speller/decoder/attention_wrapper/' + {'vanilla': 'bahdanau_attention', 'windowed': 'windowed_attention',
+                                                     'location_aware': 'location_aware_attention'}[attention]
+    sp = {'memory_kernel': params['Speller/memory_layer/kernel'], 'query_kernel': params[scope + '/query_layer/kernel'],
+          'attention_v': params[scope + '/attention_v'], 'out_kernel': params['Speller/decoder/dense/kernel'],
+          'out_bias': params['Speller/decoder/dense/bias']}
+    if attention == 'location_aware':
+        sp['conv_kernel'] = params[scope + '/conv1d/kernel']
+        sp['conv_dense_kernel'] = params[scope + '/process_conv_features/kernel']
+    cells = int(mc.get('decoder', 'num_layers'))
+    for l in range(cells):
+        base = 'Speller/decoder/attention_wrapper/multi_rnn_cell/cell_%d/lstm_cell/' % l
+        sp['cell_%d_kernel' % l], sp['cell_%d_bias' % l] = params[base + 'kernel'], params[base + 'bias']
+    window = None
+    if attention == 'windowed':
+        window = (int(mc.get('decoder', 'left_window_width')), int(mc.get('decoder', 'right_window_width')))
+    fn = mc.get('decoder', 'probability_fn') if mc.has_option('decoder', 'probability_fn') else 'softmax'
+    steps = int(mc.get('encoder', 'pyramid_steps')) if mc.has_option('encoder', 'pyramid_steps') else 2
+    return layers, sp, dict(attention=attention, num_layers=cells, probability_fn=fn, window=window), steps
+
+
+def _las_oracle(mc, params, inp):
+    layers, sp, kw, steps = _las_params(mc, params)
+    enc, elens, caches = O.listener_fwd(inp['features'], inp['features_len'], layers, steps)
+    logits, ctx = O.speller_fwd(enc, elens, inp['targets'], inp['targets_len'], sp, kw['attention'], kw['num_layers'],
+                                np.float64, kw['probability_fn'], kw['window'])
+    loss, dlogits = O.average_cross_entropy(logits, inp['targets'], inp['targets_len'], inp['targets_len'])
+    dmem, gsp = O.speller_bwd(ctx, dlogits)
+    _, glayers = O.listener_bwd(caches, dmem, steps)
+    return logits, loss, gsp, glayers
+
+
+def _check_las_oracle(mc, params, inp, out):
+    logits, loss, gsp, glayers = _las_oracle(mc, params, inp)
+    for b, n in enumerate(inp['targets_len']):
+        assert rel_err(logits[b, :n], out['logits'][b, :n]) < TOL
+    assert abs(loss - float(out['loss'])) / abs(float(out['loss'])) < TOL
+    grads = {k[len('grad/'):]: v for k, v in out.items() if k.startswith('grad/')}
+    glayers_tf, gsp_tf, _, _ = _las_params(mc, grads)
+    for k in gsp:
+        assert rel_err(gsp[k], gsp_tf[k]) < 5 * TOL, k
+    for l, g in enumerate(glayers):
+        for k in g:
+            assert rel_err(g[k], glayers_tf[l][k]) < 5 * TOL, (l, k)
 
 
 @needs_goldens
@@ -113,7 +170,7 @@ def _check_cuda_case(case):
     if 'decoded_values' in out:                       # ctc_decoder: sparse ids, bit-exact
         assert np.array_equal(np.asarray(dec.indices), out['decoded_indices'])
         assert np.array_equal(np.asarray(dec.values), out['decoded_values'])
-    else:                                             # beam_search_decoder: ids and lengths bit-exact, scores 1e-4
+    elif 'decoded_sequences' in out:                  # beam_search_decoder: ids and lengths bit-exact, scores 1e-4
         seqs, lens, scores = [np.asarray(d.cpu() if torch.is_tensor(d) else d) for d in dec[:3]]
         assert np.array_equal(lens, out['decoded_lengths'])
         for b in range(seqs.shape[0]):
@@ -184,3 +241,57 @@ def test_harness_on_a_self_made_case(tmp_path):
 @pytest.mark.gpu
 def test_cuda_harness_on_a_self_made_case(tmp_path):
     _check_cuda_case(_self_made_case(str(tmp_path / 'case')))
+
+
+def _self_made_las_case(path, attention):
+    """the dump of a LAS recipe (listener + speller, average_cross_entropy), the oracle standing in for TensorFlow"""
+    from nabu_b200.neuralnetworks.models.model import Model
+    os.makedirs(path)
+    extra = {'vanilla': '', 'location_aware': 'numfilt = 3\nfiltersize = 5\n',
+             'windowed': 'left_window_width = 2\nright_window_width = 3\n'}[attention]
+    cfgs = {'model.cfg': '[io]\ninputs = features\noutputs = text\noutput_dims = 6\n[encoder]\nencoder = listener\n'
+                         'num_units = 64\nnum_layers = 2\npyramid_steps = 2\ninput_noise = 0\ndropout = 1\n[decoder]\n'
+                         'decoder = speller\nnum_layers = 2\nnum_units = 64\ndropout = 1\nsample_prob = 0\n'
+                         'attention = %s\n%s' % (attention, extra),
+            'trainer.cfg': '[trainer]\ntrainer = standard\nloss = average_cross_entropy\ntrainlabels = 1\n'
+                           'targets = text\n',
+            'recognizer.cfg': '[recognizer]\nbatch_size = 4\n[decoder]\ndecoder = beam_search_decoder\nmax_steps = 8\n'
+                              'beam_width = 3\nalphabet = a b c d e f <eos>\n'}
+    for name, text in cfgs.items():
+        with open(os.path.join(path, name), 'w') as fid:
+            fid.write(text)
+    conf = configparser.ConfigParser()
+    conf.read(os.path.join(path, 'model.cfg'))
+    rng = np.random.RandomState(5)
+    B, T, D = 4, 27, 12
+    x = rng.randn(B, T, D).astype(np.float32)
+    xl = rng.randint(17, T + 1, size=B).astype(np.int32)
+    yl = rng.randint(3, 7, size=B).astype(np.int32)
+    y = rng.randint(0, 6, size=(B, int(yl.max()))).astype(np.int32)
+    for b in range(B):
+        x[b, xl[b]:] = 0
+        y[b, yl[b] - 1] = 6                              # EOS = output_dims
+        y[b, yl[b]:] = 0
+    inp = dict(features=x, features_len=xl, targets=y, targets_len=yl)
+    np.savez(os.path.join(path, 'inputs.npz'), **inp)
+    model = Model(conf, 1, seed=6).build({'features': D}, 'cpu')
+    model.store.save_tf_checkpoint(os.path.join(path, 'network.ckpt'))
+    params = model.store.to_numpy()
+    logits, loss, gsp, glayers = _las_oracle(conf, params, inp)
+    out = {'logits': logits.astype(np.float32), 'logits_len': yl, 'loss': np.float32(loss)}
+    # gradients under the reference's variable names: invert the name map by feeding it the names themselves
+    names = {n: n for n in params}
+    lnames, snames, _, _ = _las_params(conf, names)
+    for k, g in gsp.items():
+        out['grad/' + snames[k]] = g
+    for l, g in enumerate(glayers):
+        for k, v in g.items():
+            out['grad/' + lnames[l][k]] = v
+    assert set(out) - {'logits', 'logits_len', 'loss'} == set('grad/' + n for n in params)
+    np.savez(os.path.join(path, 'outputs.npz'), **out)
+    return path
+
+
+@pytest.mark.parametrize('attention', ['vanilla', 'location_aware', 'windowed'])
+def test_harness_on_a_self_made_las_case(tmp_path, attention):
+    _check_oracle_case(_self_made_las_case(str(tmp_path / 'case'), attention))
