@@ -159,6 +159,35 @@ int nabu_speller_bwd(const nabu_speller_desc_t* d, const nabu_speller_params_t* 
                      float* dmemory, const nabu_speller_params_t* grads,
                      void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- a8 on its own: the attention mechanism step by step -------------------------------------------
+ * Replaces components/attention.py:142-184 (LocationAwareAttention.__call__), :186-240 (_bahdanau_location_score),
+ * :24-30 (vanilla Bahdanau), :294-396 (windowed) and the memory_layer / context computation of TF's BahdanauAttention
+ * / AttentionWrapper -- what models/ed_decoders/speller.py:57-61 builds as a separate object and
+ * components/beam_search_decoder.py:176 steps.  nabu_speller_fwd/bwd and nabu_las_beam_search run the same kernels
+ * fused with the LSTM cell and the projection; these entry points expose the mechanism alone.
+ *   nabu_attn_keys:      values [B,Tm,E] = memory * sequence_mask(mem_len); keys [B,Tm,A] = values . memory_kernel
+ *   nabu_attn_step_fwd:  query [R,H] (R = B * rows_per_mem decoder rows, rows_per_mem consecutive rows share a memory
+ *                        row = tile_batch) and align_prev [R,Tm]  ->  align_new [R,Tm], context [R,E] = align_new . values.
+ *                        q_save [R,A], cf_save [R,Tm,numfilt] (location_aware), asum_save [R] (normalized_sigmoid) are the
+ *                        activations nabu_attn_step_bwd needs; each may be NULL when no backward follows.
+ *   nabu_attn_step_bwd:  rows_per_mem = 1.  dalign_new [R,Tm] (NULL = 0) and dcontext [R,E] in; dquery [R,H] and
+ *                        dalign_prev [R,Tm] out; dkeys [B,Tm,A] and dvalues [B,Tm,E] are ACCUMULATED (+=: they collect
+ *                        over the decoder steps); grads->{query_kernel, attention_v, conv_kernel, conv_dense_kernel}
+ *                        receive THIS step's parameter gradients (overwritten). */
+size_t nabu_attn_workspace_bytes(const nabu_speller_desc_t* d, int R);
+int nabu_attn_keys(const nabu_speller_desc_t* d, const nabu_speller_params_t* p, const float* memory,
+                   const int* mem_len, float* values, float* keys, void* stream);
+int nabu_attn_step_fwd(const nabu_speller_desc_t* d, const nabu_speller_params_t* p, const float* query, int R,
+                       int rows_per_mem, const float* keys, const float* values, const int* mem_len,
+                       const float* align_prev, float* align_new, float* context, float* q_save, float* cf_save,
+                       float* asum_save, void* workspace, size_t ws_bytes, void* stream);
+int nabu_attn_step_bwd(const nabu_speller_desc_t* d, const nabu_speller_params_t* p, const float* query, int R,
+                       const float* keys, const float* values, const int* mem_len, const float* align_prev,
+                       const float* align_new, const float* q_save, const float* cf_save, const float* asum_save,
+                       const float* dalign_new, const float* dcontext, float* dquery, float* dalign_prev,
+                       float* dkeys, float* dvalues, const nabu_speller_params_t* grads, void* workspace,
+                       size_t ws_bytes, void* stream);
+
 /* ---- a13: LAS beam search -------------------------------------------------------------------------
  * Replaces decoders/beam_search_decoder.py:30-112 + components/beam_search_decoder.py:136-485
  * (initialize / step / finalize under dynamic_decode(maximum_iterations=max_steps)).
@@ -181,6 +210,24 @@ size_t nabu_ctc_beam_workspace_bytes(int B, int T, int V, int beam_width);
 int nabu_ctc_beam_search(const float* logits, const int* logit_len, int B, int T, int V,
                          int beam_width, int merge_repeated, int* out_ids, int* out_len,
                          float* out_neg_logprob, void* workspace, size_t ws_bytes, void* stream);
+
+/* The name SURVEY.md section 8b lists for the same entry point. */
+int nabu_ctc_prefix_beam(const float* logits, const int* logit_len, int B, int T, int V,
+                         int beam_width, int merge_repeated, int* out_ids, int* out_len,
+                         float* out_neg_logprob, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- e: the data-parallel step's one collective ------------------------------------------------------
+ * Replaces the gradient exchange of trainers/trainer.py:479-510, 556-569 (asynchronous parameter servers in the
+ * reference; here ONE synchronous ncclAllReduce(SUM, fp32) of the flat gradient buffer over NVLink, enqueued on the
+ * caller's stream like every other entry point).  One process per GPU: rank 0 calls nabu_comm_unique_id (HOST buffer
+ * of 128 bytes), hands the bytes to the other ranks by any means (torch.distributed, MPI, a file) and every rank calls
+ * nabu_comm_init with them.  Without a communicator nabu_allreduce_grads is the identity (a one-GPU job).
+ * NCCL is resolved with dlopen("libnccl.so.2") on the first of these calls. */
+int nabu_comm_unique_id(void* id128_host);
+int nabu_comm_init(const void* id128_host, int rank, int world);
+int nabu_comm_world(void);
+int nabu_comm_destroy(void);
+int nabu_allreduce_grads(float* grads, size_t n, void* stream);
 
 /* ---- host helper (rows f1 / f3: TFRecord frames, TF checkpoint bundles) ---------------------------
  * CRC-32C (Castagnoli, reflected 0x82F63B78) of `nbytes` HOST bytes, continuing from `crc` (0 to start).

@@ -1,6 +1,7 @@
 // Error string + device-property cache behind the C-ABI.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace nabu {
 
@@ -14,6 +15,27 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+void warn_once(const char* key, const char* fmt, ...) {
+  static char seen[64][96];
+  static int nseen = 0;
+  static int quiet = -1;
+  if (quiet < 0) quiet = (getenv("NABU_QUIET") && atoi(getenv("NABU_QUIET")) != 0) ? 1 : 0;
+  if (quiet) return;
+  for (int i = 0; i < nseen; ++i)
+    if (strncmp(seen[i], key, sizeof(seen[i]) - 1) == 0) return;
+  if (nseen < 64) {
+    strncpy(seen[nseen], key, sizeof(seen[nseen]) - 1);
+    seen[nseen][sizeof(seen[nseen]) - 1] = 0;
+    ++nseen;
+  }
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "[nabu_b200] ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
 
 int num_sms() {
   static int cached[64] = {0};

@@ -750,6 +750,12 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
       return e;
     if (launched) return 0;
   }
+  {
+    char key[96];
+    snprintf(key, sizeof(key), "fwd B=%d H=%d", B, H);
+    warn_once(key, "blstm forward recurrence B=%d num_units=%d is not on the tcgen05 cluster kernel (eligible: B <= 128 per launch, "
+              "num_units in {128, 256, 512}); falling back to the FFMA kernels", B, H);
+  }
   if (blstm_fwd_cluster_eligible(B, H)) {
     bool launched = false;
     if (int e = blstm_rec_fwd_cluster(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched)) return e;
@@ -830,6 +836,12 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
       NABU_CHECK_CUDA(cudaEventRecord(ov.ev_rec, ov.hp));
       NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, ov.ev_rec, 0));
     }
+  }
+  if (!launched) {
+    char key[96];
+    snprintf(key, sizeof(key), "bwd B=%d H=%d", B, H);
+    warn_once(key, "blstm backward recurrence B=%d num_units=%d is not on the TMEM-resident tcgen05 kernel (eligible: B <= 128 per "
+              "launch, num_units in {128, 256, 512}); falling back", B, H);
   }
   if (!launched && blstm_bwd_cluster_tc_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};

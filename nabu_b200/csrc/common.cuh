@@ -55,6 +55,10 @@ int overlap_init();                       // creates streams / events on first u
 int overlap_workspace(size_t bytes);      // grow-only device scratch owned by the library (side stream only)
 int overlap_join(cudaStream_t stream);    // stream waits for the deferred work, if any
 
+// One line on stderr the first time `key` is seen (a shape that leaves the tensor-core path must not do so silently);
+// NABU_QUIET=1 silences it.
+void warn_once(const char* key, const char* fmt, ...);
+
 int num_sms();                 // SM count of the current device (cached)
 int max_smem_optin();          // max dynamic shared memory per block (opt-in)
 

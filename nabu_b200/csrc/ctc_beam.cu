@@ -322,3 +322,11 @@ extern "C" int nabu_ctc_beam_search(const float* logits, const int* logit_len, i
   NABU_CHECK_LAUNCH();
   return 0;
 }
+
+// The name SURVEY.md section 8b lists for this entry point.
+extern "C" int nabu_ctc_prefix_beam(const float* logits, const int* logit_len, int B, int T, int V, int beam_width,
+                                    int merge_repeated, int* out_ids, int* out_len, float* out_neg_logprob,
+                                    void* workspace, size_t ws_bytes, void* stream) {
+  return nabu_ctc_beam_search(logits, logit_len, B, T, V, beam_width, merge_repeated, out_ids, out_len, out_neg_logprob,
+                              workspace, ws_bytes, stream);
+}

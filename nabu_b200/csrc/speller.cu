@@ -804,3 +804,147 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row a8 on its own (SURVEY.md section 8b export list): the attention mechanism as three entry points, for a caller that
+// steps the mechanism itself the way components/beam_search_decoder.py:176 steps the AttentionWrapper's cell.
+// The kernels are the fused ones above; the output projection they also contain runs on scratch / zero operands here.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace nabu {
+namespace dec {
+struct AttnWs {
+  float *dlogits, *dv_part, *dWd_part, *dWc_part;     // zeroed per call
+  float *logits, *ctxT, *outin, *dq;
+  int* tlen;
+  float* gemm; size_t gemm_bytes; size_t zero_bytes; size_t total;
+};
+AttnWs carve_attn(void* base, const nabu_speller_desc_t& d, int R) {
+  AttnWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) { float* q = (float*)(p + off); off += align_up(nfloats * sizeof(float), 256); return q; };
+  const size_t F = d.attention == 1 ? d.numfilt : 0, ksz = d.attention == 1 ? d.filtersize : 1;
+  w.dlogits = take((size_t)R * d.V);
+  w.dv_part = take((size_t)R * d.A);
+  w.dWd_part = take((size_t)R * (F ? F : 1) * d.A);
+  w.dWc_part = take((size_t)R * ksz * (F ? F : 1));
+  w.outin = take((size_t)R * (d.H + d.E));
+  w.zero_bytes = off;
+  w.logits = take((size_t)R * d.V);
+  w.ctxT = take((size_t)R * d.E);
+  w.dq = take((size_t)R * d.A);
+  w.tlen = (int*)take((size_t)R);
+  w.gemm = (float*)(p + off); w.gemm_bytes = sgemm_workspace_bytes(); off += w.gemm_bytes;
+  w.total = off;
+  return w;
+}
+}  // namespace dec
+}  // namespace nabu
+
+extern "C" size_t nabu_attn_workspace_bytes(const nabu_speller_desc_t* d, int R) {
+  if (check_desc(*d) || R <= 0) return 0;
+  return carve_attn(nullptr, *d, R).total;
+}
+
+extern "C" int nabu_attn_keys(const nabu_speller_desc_t* d, const nabu_speller_params_t* p, const float* memory,
+                              const int* mem_len, float* values, float* keys, void* stream) {
+  if (int e = check_desc(*d)) return e;
+  return prepare_memory(*d, *p, memory, mem_len, values, keys, (cudaStream_t)stream);
+}
+
+extern "C" int nabu_attn_step_fwd(const nabu_speller_desc_t* dp, const nabu_speller_params_t* p, const float* query, int R,
+                                  int rows_per_mem, const float* keys, const float* values, const int* mem_len,
+                                  const float* align_prev, float* align_new, float* context, float* q_save, float* cf_save,
+                                  float* asum_save, void* workspace, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const nabu_speller_desc_t& d = *dp;
+  if (int e = check_desc(d)) return e;
+  NABU_REQUIRE(R > 0 && rows_per_mem > 0 && R == d.B * rows_per_mem, "attn_step_fwd: R=%d must be B=%d x rows_per_mem=%d", R, d.B,
+               rows_per_mem);
+  AttnWs w = carve_attn(workspace, d, R);
+  NABU_REQUIRE(ws_bytes >= w.total, "attn_step_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  AttnStepArgs a = {};
+  a.R = R; a.Tm = d.Tm; a.E = d.E; a.H = d.H; a.A = d.A; a.V = d.V;
+  a.F = d.attention == 1 ? d.numfilt : 0; a.ksz = d.attention == 1 ? d.filtersize : 1;
+  a.rows_per_mem = rows_per_mem;
+  a.h_top = query;
+  a.Wq = p->query_kernel; a.Wc = p->conv_kernel; a.Wd = p->conv_dense_kernel; a.v = p->attention_v;
+  a.Wo = p->out_kernel; a.bo = p->out_bias;
+  a.keys = keys; a.values = values; a.mem_len = mem_len;
+  a.align_prev = align_prev; a.ctx_prev = context;
+  a.align_new = align_new; a.ctx_new = context; a.ctxT_new = w.ctxT;
+  a.logits = w.logits; a.logits_row_stride = d.V; a.temperature = 1.f;
+  a.q_save = q_save; a.cf_save = a.F ? cf_save : nullptr; a.outin_save = nullptr; a.outin_row_stride = 0;
+  a.tlen = nullptr; a.u = 0; a.done = nullptr;
+  a.prob = d.probability_fn; a.asum_save = asum_save;
+  a.win_left = d.attention == 2 ? d.numfilt : -1; a.win_right = d.filtersize;
+  const size_t smem = attn_step_smem(d.Tm, d.E, d.H, d.A, a.F, a.ksz);
+  NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "attn_step_fwd: memory too long for the attention step kernel (Tm=%d)", d.Tm);
+  if (smem > 48 * 1024)
+    NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KernelScope ks("dec_attn_step", stream);
+  dec_attn_step_kernel<<<R, 512, smem, stream>>>(a);
+  NABU_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int nabu_attn_step_bwd(const nabu_speller_desc_t* dp, const nabu_speller_params_t* p, const float* query, int R,
+                                  const float* keys, const float* values, const int* mem_len, const float* align_prev,
+                                  const float* align_new, const float* q_save, const float* cf_save, const float* asum_save,
+                                  const float* dalign_new, const float* dcontext, float* dquery, float* dalign_prev,
+                                  float* dkeys, float* dvalues, const nabu_speller_params_t* g, void* workspace,
+                                  size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const nabu_speller_desc_t& d = *dp;
+  if (int e = check_desc(d)) return e;
+  NABU_REQUIRE(R == d.B, "attn_step_bwd: one decoder row per memory row (R=%d, B=%d)", R, d.B);
+  AttnWs w = carve_attn(workspace, d, R);
+  NABU_REQUIRE(ws_bytes >= w.total, "attn_step_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  const int Tm = d.Tm, E = d.E, H = d.H, A = d.A, V = d.V;
+  const int F = d.attention == 1 ? d.numfilt : 0, ksz = d.attention == 1 ? d.filtersize : 1;
+  NABU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, stream));
+  NABU_CHECK_CUDA(cudaMemsetAsync(w.tlen, 1, (size_t)R * sizeof(int), stream));       // 0x01010101 > u = 0: every row active
+  // d(alignments) arriving from the consumer of align_new (the next step's location features); the kernel adds its own
+  // contribution through the context and leaves d(align_prev) in the same buffer
+  if (dalign_new) NABU_CHECK_CUDA(cudaMemcpyAsync(dalign_prev, dalign_new, (size_t)R * Tm * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  else NABU_CHECK_CUDA(cudaMemsetAsync(dalign_prev, 0, (size_t)R * Tm * sizeof(float), stream));
+  const size_t smem_attn = attn_bwd_smem(Tm, E, H, A, V, F, ksz);
+  NABU_REQUIRE(smem_attn <= (size_t)max_smem_optin(), "attn_step_bwd: memory too long for the attention kernel (Tm=%d)", Tm);
+  const void* attn_fn = A <= 256 ? (const void*)dec_attn_bwd_step_kernel<2> : (const void*)dec_attn_bwd_step_kernel<1>;
+  if (smem_attn > 48 * 1024)
+    NABU_CHECK_CUDA(cudaFuncSetAttribute(attn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn));
+  AttnBwdArgs a = {};
+  a.R = R; a.Tm = Tm; a.E = E; a.H = H; a.A = A; a.V = V; a.F = F; a.ksz = ksz; a.U = 1; a.u = 0;
+  a.dlogits = w.dlogits; a.dl_row_stride = V;                   // zeros: the projection's backward contributes nothing
+  a.outin = w.outin; a.outin_row_stride = H + E;
+  a.alpha = align_new; a.alpha_prev = align_prev;
+  a.q = q_save; a.cf = F ? cf_save : nullptr;
+  a.Wq = p->query_kernel; a.Wc = p->conv_kernel; a.Wd = p->conv_dense_kernel; a.v = p->attention_v; a.Wo = p->out_kernel;
+  a.keys = keys; a.values = values; a.mem_len = mem_len;
+  a.dctx_carry = dcontext; a.dalign_carry = dalign_prev; a.dh_above = dquery;
+  a.dq_save = w.dq; a.dkeys = dkeys; a.dvalues = dvalues;
+  a.dv_part = w.dv_part; a.dWd_part = w.dWd_part; a.dWc_part = w.dWc_part;
+  a.tlen = w.tlen; a.prob = d.probability_fn; a.asum = asum_save;
+  {
+    KernelScope ks("dec_attn_bwd_step", stream);
+    if (A <= 256) dec_attn_bwd_step_kernel<2><<<R, 512, smem_attn, stream>>>(a);
+    else dec_attn_bwd_step_kernel<1><<<R, 512, smem_attn, stream>>>(a);
+    NABU_CHECK_LAUNCH();
+  }
+  // this step's parameter gradients (overwritten, not accumulated): query layer, attention vector, location layers
+  if (int e = gemm(GEMM_TN, H, A, R, 1.f, query, H, w.dq, A, 0.f, g->query_kernel, A, nullptr, nullptr, w.gemm, w.gemm_bytes, stream))
+    return e;
+  {
+    KernelScope ks("reduce_rows", stream);
+    reduce_rows_kernel<<<ceil_div(A, 256), 256, 0, stream>>>(w.dv_part, R, A, g->attention_v);
+    NABU_CHECK_LAUNCH();
+  }
+  if (F > 0) {
+    KernelScope ks("reduce_rows", stream);
+    reduce_rows_kernel<<<ceil_div(F * A, 256), 256, 0, stream>>>(w.dWd_part, R, (long)F * A, g->conv_dense_kernel);
+    NABU_CHECK_LAUNCH();
+    reduce_rows_kernel<<<ceil_div(ksz * F, 256), 256, 0, stream>>>(w.dWc_part, R, (long)ksz * F, g->conv_kernel);
+    NABU_CHECK_LAUNCH();
+  }
+  return 0;
+}

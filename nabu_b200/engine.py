@@ -284,7 +284,7 @@ class _BLSTMPadded(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, lens, kf, bf, kb, bb, H, yT, gvars):
-        Hp = (H + REC_UNIT - 1) // REC_UNIT * REC_UNIT
+        Hp = rec_width(H, x.shape[0])
         x = x.contiguous()
         pkf, pbf = _pad_gates(kf.detach(), H, Hp, True), _pad_gates(bf.detach(), H, Hp, False)
         pkb, pbb = _pad_gates(kb.detach(), H, Hp, True), _pad_gates(bb.detach(), H, Hp, False)
@@ -309,10 +309,24 @@ class _BLSTMPadded(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None, None
 
 
+def rec_width(H, B=None):
+    """The number of hidden units the recurrence kernels run for a layer of `H` units.  The tcgen05 cluster kernels exist
+    for 256 and 512 units (csrc/blstm_cl_tc.cu, blstm_cl_bwd8.cu); with NABU_PAD_UNITS=1 a narrower layer -- every
+    shipped recipe uses num_units = 128 -- is zero-padded up to the next of those instead of taking the FFMA kernels
+    (exact, see _BLSTMPadded).  Otherwise: the next multiple of the 64-unit tile."""
+    import os
+    Hp = (H + REC_UNIT - 1) // REC_UNIT * REC_UNIT
+    if os.environ.get('NABU_PAD_UNITS', '0') == '1' and (B is None or B <= 128):
+        for w in (256, 512):
+            if H <= w:
+                return w
+    return Hp
+
+
 def blstm(x, lens, vf_k, vf_b, vb_k, vb_b, H, yT=None):
     """x [B,T,D] -> y [B,yT,2H]; v*_ are engine.Variable."""
     yT = x.shape[1] if yT is None else yT
-    fn = _BLSTM if H % REC_UNIT == 0 else _BLSTMPadded
+    fn = _BLSTM if rec_width(H, x.shape[0]) == H else _BLSTMPadded
     return fn.apply(x, lens, vf_k.data, vf_b.data, vb_k.data, vb_b.data, H, yT,
                     (vf_k.grad, vf_b.grad, vb_k.grad, vb_b.grad))
 

@@ -68,6 +68,18 @@ SIGNATURES = {
     'nabu_ctc_beam_workspace_bytes': (c_size_t, [c_int] * 4),
     'nabu_ctc_beam_search': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     'nabu_crc32c': (ctypes.c_uint, [ctypes.c_char_p, c_size_t, ctypes.c_uint]),
+    'nabu_attn_workspace_bytes': (c_size_t, [ctypes.POINTER(SpellerDesc), c_int]),
+    'nabu_attn_keys': (c_int, [ctypes.POINTER(SpellerDesc), ctypes.POINTER(SpellerParams), P, P, P, P, P]),
+    'nabu_attn_step_fwd': (c_int, [ctypes.POINTER(SpellerDesc), ctypes.POINTER(SpellerParams), P, c_int, c_int, P, P, P, P,
+                                   P, P, P, P, P, P, c_size_t, P]),
+    'nabu_attn_step_bwd': (c_int, [ctypes.POINTER(SpellerDesc), ctypes.POINTER(SpellerParams), P, c_int, P, P, P, P, P, P,
+                                   P, P, P, P, P, P, P, P, ctypes.POINTER(SpellerParams), P, c_size_t, P]),
+    'nabu_ctc_prefix_beam': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    'nabu_comm_unique_id': (c_int, [ctypes.c_char_p]),
+    'nabu_comm_init': (c_int, [ctypes.c_char_p, c_int, c_int]),
+    'nabu_comm_world': (c_int, []),
+    'nabu_comm_destroy': (c_int, []),
+    'nabu_allreduce_grads': (c_int, [P, c_size_t, P]),
 }
 
 _lib = None

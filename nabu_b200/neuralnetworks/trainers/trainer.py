@@ -230,7 +230,7 @@ class Trainer(object, metaclass=ABCMeta):
         if path is None or self.task_index != 0:
             return
         import numpy as np
-        extra = {'learning_rate_fact': np.array(self.learning_rate_fact, np.float64),
+        extra = {'learning_rate_fact': np.array(self.learning_rate_fact, np.float32),
                  'should_terminate': np.array(bool(self.should_terminate))}          # trainer.py:97-104
         controller = getattr(self, '_controller', None)
         if controller is not None:
@@ -267,18 +267,58 @@ class Trainer(object, metaclass=ABCMeta):
             controller.validated_step = int(scalars['validated_step'])
             controller.best_validation = float(scalars['best_validation'])
             controller.num_tries = int(scalars['num_tries'])
+        self._load_validated_from_disk()
         return True
 
-    # ---- ValidationSaveHook (hooks.py:54-86): every global variable, in memory -----------------------
+    # ---- ValidationSaveHook (hooks.py:54-86): every global variable, in memory AND as <expdir>/logdir/validated.ckpt ----
+    def _validated_path(self):
+        return os.path.join(self.expdir, 'logdir', 'validated.ckpt') if self.expdir else None
+
     def _save_validated(self):
         st = self.model.store
         self._validated = {'theta': st.theta.clone(), 'm': st.m.clone(), 'v': st.v.clone(),
                            'global_step': self.global_step, 'learning_rate_fact': self.learning_rate_fact,
                            'controller': self._controller.state()}
+        # on disk as well (the reference's validated.ckpt): go_back / early stopping must still find the best-validated
+        # parameters after a crash and resume
+        path = self._validated_path()
+        if path is not None and self.task_index == 0:
+            import numpy as np
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            cs = self._controller.state()
+            extra = {'learning_rate_fact': np.array(self.learning_rate_fact, np.float32),
+                     'validated_step': np.array(cs['validated_step'], np.int64),
+                     'best_validation': np.array(cs['best_validation'], np.float64)}
+            st.save_tf_checkpoint(path + '.tmp', with_adam=True, global_step=self.global_step, extra=extra)
+            for suffix in ('.data-00000-of-00001', '.index'):
+                os.replace(path + '.tmp' + suffix, path + suffix)
+
+    def _load_validated_from_disk(self):
+        """validated.ckpt -> the in-memory snapshot (after a resume); False when there is none"""
+        path = self._validated_path()
+        if path is None or not os.path.isfile(path + '.index'):
+            return False
+        from ...processing import tfcheckpoint
+        st = self.model.store
+        keep = (st.theta.clone(), st.m.clone(), st.v.clone())
+        step = st.load_tf_checkpoint(path, with_adam=True)
+        sc = tfcheckpoint.read_checkpoint(path, names={'learning_rate_fact', 'validated_step', 'best_validation'})
+        self._validated = {'theta': st.theta.clone(), 'm': st.m.clone(), 'v': st.v.clone(),
+                           'global_step': int(step) if step is not None else 0,
+                           'learning_rate_fact': float(sc['learning_rate_fact']),
+                           'controller': {'validated_step': int(sc['validated_step']),
+                                          'best_validation': float(sc['best_validation'])}}
+        st.theta.copy_(keep[0]); st.m.copy_(keep[1]); st.v.copy_(keep[2])
+        return True
 
     def _restore_validated(self):
         snap = getattr(self, '_validated', None)
-        if snap is None:          # the reference would fail to find validated.ckpt; nothing was ever better
+        if snap is None and self._load_validated_from_disk():
+            snap = self._validated
+        if snap is None:
+            # nothing was ever better than the initial best_validation (1.79e308), so nothing was saved: the reference
+            # fails here looking for validated.ckpt; say so instead of silently keeping the current parameters
+            print('WORKER %d: no validated checkpoint to go back to; keeping the current parameters' % self.task_index)
             return
         st = self.model.store
         st.theta.copy_(snap['theta']); st.m.copy_(snap['m']); st.v.copy_(snap['v'])

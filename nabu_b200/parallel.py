@@ -18,9 +18,43 @@ def shard_batch(arrays, rank, world):
     return tuple(a[rank::world] for a in arrays)
 
 
+_COMM = {'ready': False}
+
+
+def init_library_comm():
+    """One NCCL communicator owned by libnabu_b200.so (include/nabu_b200.h: nabu_comm_*): rank 0 draws the unique id,
+    torch.distributed carries its 128 bytes to the other ranks.  CUDA + NCCL jobs only; NABU_LIB_ALLREDUCE=0 keeps
+    torch's own all_reduce (the same ncclAllReduce on torch's communicator)."""
+    import ctypes
+    import os
+    import torch
+    from . import lib as L
+    if _COMM['ready'] or world_size() == 1 or os.environ.get('NABU_LIB_ALLREDUCE', '1') == '0':
+        return _COMM['ready']
+    if dist.get_backend() != 'nccl' or not torch.cuda.is_available():
+        return False
+    lib = L.load()
+    buf = ctypes.create_string_buffer(128)
+    if dist.get_rank() == 0:
+        L.check(lib.nabu_comm_unique_id(buf), 'nabu_comm_unique_id')
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device='cuda')
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    L.check(lib.nabu_comm_init(ctypes.create_string_buffer(raw, 128), dist.get_rank(), dist.get_world_size()),
+            'nabu_comm_init')
+    _COMM['ready'] = True
+    return True
+
+
 def allreduce_sum_(flat):
+    """the step's only collective: nabu_allreduce_grads (ncclAllReduce on the caller's stream) on CUDA jobs, torch's
+    all_reduce under gloo (the CPU tests)"""
     if world_size() > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if flat.is_cuda and init_library_comm():
+            from . import lib as L
+            L.check(L.load().nabu_allreduce_grads(L.ptr(flat), flat.numel(), L.stream()), 'nabu_allreduce_grads')
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     return flat
 
 

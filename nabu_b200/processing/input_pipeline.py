@@ -123,8 +123,16 @@ class BatchSource(object):
         # processing/input_pipeline.py:133-168; one thread keeps the order deterministic); 0 = read in the caller
         self.prefetch = int(os.environ.get('NABU_PREFETCH', '0')) if prefetch is None else int(prefetch)
         self.rank, self.world = int(rank), int(world)
-        if self.world > 1 and any(b % self.world for b in self.batch_sizes):
-            raise Exception('batch sizes %s are not divisible by the %d data-parallel ranks' % (self.batch_sizes, world))
+        if self.world > 1:
+            # The reference's per-bucket sizes (16, 14, 13, 11, ... with variable_batch_size) do not divide the number of
+            # ranks in general: round every bucket's size DOWN to a multiple of `world` (at least one utterance per
+            # rank) and recount the steps from the rounded sizes, so that stock recipes train under torchrun unchanged.
+            rounded = [max(b // self.world, 1) * self.world for b in self.batch_sizes]
+            if rounded != self.batch_sizes:
+                edges = [0] + list(self.boundaries) + [hist.size]
+                numutt = [hist[edges[i]:edges[i + 1]].sum() for i in range(len(rounded))]
+                self.batch_sizes = rounded
+                self.num_steps = int(sum(int(n) // b for n, b in zip(numutt, rounded)))
 
     def __len__(self):
         return self.num_steps
@@ -218,6 +226,11 @@ class BatchSource(object):
                 buckets[b] = []
         if self.allow_smaller_final_batch:
             for items in buckets:
+                # data parallel: a tail smaller than a multiple of the ranks is cut to that multiple (every rank needs
+                # the same number of utterances for the mean of the ranks' means to be the batch mean); fewer
+                # utterances than ranks are dropped
+                if self.world > 1:
+                    items = items[:len(items) // self.world * self.world]
                 if items:
                     yield items
 

@@ -549,6 +549,46 @@ def attention_window(prev_align, left, right):
     return np.logical_xor(sl, sr)
 
 
+def attention_step(query, prev_align, values, keys, mask, p, attention, dtype,
+                   probability_fn='softmax', window=None):
+    """One call of the attention mechanism + the AttentionWrapper's context
+    (components/attention.py:142-184 LocationAwareAttention.__call__,
+    :186-240 _bahdanau_location_score, :24-30 vanilla, :294-396 windowed;
+    appendix B4/B5): alignments [B,Tm], context [B,E] and the intermediates
+    the backward needs."""
+    q = query @ np.asarray(p['query_kernel'], dtype)
+    pre = q[:, None, :] + keys
+    cf = win = None
+    if attention == 'location_aware':
+        Wc = np.asarray(p['conv_kernel'], dtype)
+        Wd = np.asarray(p['conv_dense_kernel'], dtype)
+        cf, win = _conv_same(prev_align, Wc)
+        pre = pre + cf @ Wd
+    sact = np.tanh(pre)
+    e = sact @ np.asarray(p['attention_v'], dtype)
+    if attention == 'windowed':
+        e = np.where(attention_window(prev_align, *window), e, -np.inf)
+    e = np.where(mask, e, -np.inf)
+    ssum = None
+    if probability_fn == 'softmax':
+        m = e.max(1, keepdims=True)
+        ex = np.exp(e - m)
+        alpha = ex / ex.sum(1, keepdims=True)
+    else:
+        # components/attention.py:6-55: tf.sigmoid or normalized_sigmoid on the -inf masked scores
+        with np.errstate(over='ignore'):
+            sig = np.where(mask, 1.0 / (1.0 + np.exp(-np.where(mask, e, 0))), 0).astype(dtype)
+        if probability_fn == 'sigmoid':
+            alpha = sig
+        elif probability_fn == 'normalized_sigmoid':
+            ssum = sig.sum(1, keepdims=True)
+            alpha = sig / ssum
+        else:
+            raise ValueError('unknown probability_fn %r' % probability_fn)
+    ctx = np.einsum('bt,bte->be', alpha, values)
+    return alpha, ctx, (sact, cf, win, ssum)
+
+
 def speller_step(ids, state, values, keys, mask, p, attention, dtype,
                  want_cache=False, probability_fn='softmax', window=None,
                  drop=None):
@@ -573,36 +613,9 @@ def speller_step(ids, state, values, keys, mask, p, attention, dtype,
         # DropoutWrapper(output_keep_prob): the OUTPUT is dropped, the state is not
         inp = h_new if drop is None else h_new * drop[1][l] / drop[0]
     query = inp
-    q = query @ np.asarray(p['query_kernel'], dtype)
-    pre = q[:, None, :] + keys
-    cf = win = None
-    if attention == 'location_aware':
-        Wc = np.asarray(p['conv_kernel'], dtype)
-        Wd = np.asarray(p['conv_dense_kernel'], dtype)
-        cf, win = _conv_same(state['alignments'], Wc)
-        pre = pre + cf @ Wd
-    sact = np.tanh(pre)
-    e = sact @ np.asarray(p['attention_v'], dtype)
-    if attention == 'windowed':
-        e = np.where(attention_window(state['alignments'], *window), e, -np.inf)
-    e = np.where(mask, e, -np.inf)
-    ssum = None
-    if probability_fn == 'softmax':
-        m = e.max(1, keepdims=True)
-        ex = np.exp(e - m)
-        alpha = ex / ex.sum(1, keepdims=True)
-    else:
-        # components/attention.py:6-55: tf.sigmoid or normalized_sigmoid on the -inf masked scores
-        with np.errstate(over='ignore'):
-            sig = np.where(mask, 1.0 / (1.0 + np.exp(-np.where(mask, e, 0))), 0).astype(dtype)
-        if probability_fn == 'sigmoid':
-            alpha = sig
-        elif probability_fn == 'normalized_sigmoid':
-            ssum = sig.sum(1, keepdims=True)
-            alpha = sig / ssum
-        else:
-            raise ValueError('unknown probability_fn %r' % probability_fn)
-    ctx = np.einsum('bt,bte->be', alpha, values)
+    alpha, ctx, (sact, cf, win, ssum) = attention_step(
+        query, state['alignments'], values, keys, mask, p, attention, dtype,
+        probability_fn, window)
     out_in = np.concatenate([query, ctx], 1)
     logits = out_in @ np.asarray(p['out_kernel'], dtype) \
         + np.asarray(p['out_bias'], dtype)

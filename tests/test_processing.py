@@ -162,8 +162,19 @@ def test_batch_source_shards_every_batch_over_the_ranks(tmp_path):
         for r, p in enumerate((p0, p1)):
             T = p[0]['features'].shape[1]
             assert np.array_equal(p[0]['features'].numpy(), g[0]['features'][r::2, :T].numpy())
-    with pytest.raises(Exception, match='divisible'):
-        ip.BatchSource([[fconf]], ['features'], [], batch_size=3, rank=0, world=2)
+    # batch sizes that do not divide the ranks (the reference's variable batch sizes: 16, 14, 13, 11, ...) are rounded DOWN
+    # to a multiple of the world size and the step count follows: stock recipes run under torchrun unchanged
+    odd = [ip.BatchSource([[fconf]], ['features'], [], batch_size=3, shuffle_seed=5, rank=r, world=2) for r in range(2)]
+    assert odd[0].batch_sizes == [2] and len(odd[0]) == 4
+    got = [list(o) for o in odd]
+    assert len(got[0]) == len(got[1]) == 4 and all(b[0]['features'].shape[0] == 1 for b in got[0] + got[1])
+    # variable batch sizes over buckets, 3 ranks, smaller final batches: every rank sees the same number of batches with
+    # the same number of utterances in each
+    kw = dict(batch_size=5, numbuckets=2, variable_batch_size=True, allow_smaller_final_batch=True, shuffle_seed=1)
+    tri = [list(ip.BatchSource([[fconf]], ['features'], [], rank=r, world=3, **kw)) for r in range(3)]
+    assert len(tri[0]) == len(tri[1]) == len(tri[2]) >= 1
+    for b0, b1, b2 in zip(*tri):
+        assert b0[0]['features'].shape[0] == b1[0]['features'].shape[0] == b2[0]['features'].shape[0] >= 1
 
 
 def test_prefetch_thread_yields_the_same_batches_in_the_same_order(tmp_path):

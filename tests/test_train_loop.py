@@ -108,3 +108,33 @@ def test_validation_state_travels_with_the_checkpoint(tmp_path):
     assert other.global_step == 7 and other.seen == []
     assert (other._controller.validated_step, other._controller.best_validation, other._controller.num_tries) == (6, 1.25, 1)
     assert torch.equal(other.model.store.theta, tr.model.store.theta)
+
+
+def test_best_validated_snapshot_survives_a_restart(tmp_path):
+    """the go-back snapshot is also <expdir>/logdir/validated.ckpt (the reference's ValidationSaveHook,
+    components/hooks.py:54-86), so a resumed run that validates worse still goes back to the best parameters."""
+    from nabu_b200.neuralnetworks.trainers.trainer import ValidationController
+    expdir = write_experiment(str(tmp_path), num_epochs=1)
+    tr = _trainer(expdir, [])
+    tr.train(testing=True)
+    tr._controller = ValidationController(tr.conf, tr._save_validated, tr._restore_validated, tr._half_lr)
+    tr.global_step = 3
+    assert tr._controller.update(2.0, 3) == 'continue'          # better than 1.79e308: saved as the best
+    best = tr.model.store.theta.clone()
+    assert os.path.isfile(os.path.join(expdir, 'logdir', 'validated.ckpt.index'))
+    with torch.no_grad():
+        tr.model.store.theta.add_(1.0)                          # training goes on ...
+    tr.global_step = 6
+    tr.save_checkpoint()                                        # ... and the periodic checkpoint holds the later state
+    # a new process on the same directory
+    other = _trainer(expdir, [])
+    other.conf['go_back'] = 'True'
+    other.train(testing=True)
+    other._controller = ValidationController(other.conf, other._save_validated, other._restore_validated, other._half_lr)
+    assert other.restore_checkpoint() and other.global_step == 6
+    assert not torch.equal(other.model.store.theta, best)
+    assert other._controller.update(5.0, 6) == 'continue'       # worse: go back to validated.ckpt
+    for var in other.model.store.order:
+        sl = slice(var.offset, var.offset + var.numel)
+        assert torch.equal(other.model.store.theta[sl], best[sl]), var.name
+    assert other.global_step == 3 and other._controller.best_validation == 2.0

@@ -48,9 +48,50 @@ def synthetic_las_batch(B, T, D, V, U, ragged, seed=1234):
 
 
 def rel_err(a, b):
+    """max |a - b| / max |b| over the whole tensor (the error relative to the tensor's own scale)."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def row_rel_err(a, b, floor=1e-3):
+    """The worst ROW-normalised error: max over the rows r (all leading axes) of max |a_r - b_r| / max |b_r|.  Rows whose
+    own scale is below `floor` x the tensor's scale are normalised by that floor instead (a row of zeros has no relative
+    error; fp32 sums over 1e5 terms do not resolve 1e-3 of the tensor scale to 1e-4 either)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.ndim < 2:
+        return rel_err(a, b)
+    a2, b2 = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
+    scale = np.maximum(np.abs(b2).max(axis=1), floor * max(np.abs(b2).max(), 1e-30))
+    return float((np.abs(a2 - b2).max(axis=1) / scale).max())
+
+
+class ParityLog(object):
+    """Collects (tensor, global relative error, worst row-normalised error) of a parity test, asserts the bound on both
+    and leaves the table under gpurun_out/parity/ when that directory's parent exists (the GPU box), so that the errors
+    actually measured -- not just pass/fail -- end up in profiles/."""
+
+    def __init__(self, name):
+        self.name, self.rows = name, []
+
+    def check(self, tensor, got, ref, tol, row_tol=None):
+        g, r = rel_err(got, ref), row_rel_err(got, ref)
+        self.rows.append((tensor, g, r, tol, row_tol))
+        assert g < tol, '%s: %s relative error %.3e >= %.1e' % (self.name, tensor, g, tol)
+        if row_tol is not None:
+            assert r < row_tol, '%s: %s row-normalised error %.3e >= %.1e' % (self.name, tensor, r, row_tol)
+
+    def dump(self):
+        import json
+        import os
+        root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+        if not os.path.isdir(root):
+            return
+        os.makedirs(os.path.join(root, 'parity'), exist_ok=True)
+        with open(os.path.join(root, 'parity', self.name + '.json'), 'w') as fid:
+            json.dump([{'tensor': t, 'rel_err': g, 'row_rel_err': r, 'tol': tol, 'row_tol': rt}
+                       for t, g, r, tol, rt in self.rows], fid, indent=1)
 
 
 def write_experiment(root, num_epochs=2, variable_batch_size=True, n_train=16, model='dblstm'):
