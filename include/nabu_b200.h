@@ -76,6 +76,29 @@ int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int D, int H,
                    float* dx, float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
                    void* workspace, size_t ws_bytes, void* stream);
 
+/* The same layer with the tensor-core GEMMs' operand planes travelling with the activations.  The dense contractions of a
+ * layer (input projection, dKx, dKh, dX) run on tcgen05 with every fp32 operand carried as two fp16 planes ("hi", "lo");
+ * producing those planes by separate passes over y / dZ cost 18 % of the cfg-3 step in round 1.  With these entry points
+ * the forward recurrence writes the planes of y (y * 32 split in two fp16 numbers) next to y, the next layer reads them
+ * as x_planes, and the backward recurrence hands dZ to its three GEMMs as planes in library-owned scratch.
+ *   y_planes : nabu_blstm_planes_bytes(B, yT, H) bytes, caller-owned, written by _fwd_planes, to be passed again to
+ *              _bwd_planes of the same layer (dKh) and as x_planes to the layer that consumes y unchanged -- also after
+ *              pyramid_stack, which is a reshape of y and of its planes alike.  NULL: no planes are written / used.
+ *   x_planes : planes of x (the y_planes of the producer of x; needs D % 8 == 0) or NULL (the library splits x itself).
+ * Results are identical in accuracy class to nabu_blstm_fwd / _bwd (22-bit operands, fp32 accumulation); gates[] is NOT
+ * overwritten with dZ by _bwd_planes when the tcgen05 recurrence runs (it is still clobbered on the fallback kernels). */
+size_t nabu_blstm_planes_bytes(int B, int yT, int H);
+int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const int* len, int B, int T, int D, int H,
+                          const float* kernel_fw, const float* bias_fw,
+                          const float* kernel_bw, const float* bias_bw,
+                          float* y, void* y_planes, int yT, float* gates, float* cells,
+                          void* workspace, size_t ws_bytes, void* stream);
+int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const int* len, int B, int T, int D, int H,
+                          const float* kernel_fw, const float* kernel_bw,
+                          const float* y, const void* y_planes, int yT, float* gates, const float* cells, const float* dy,
+                          float* dx, float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
+                          void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- a2: pyramid_stack lengths -------------------------------------------------------------------
  * Replaces components/ops.py:55-58: out[b] = ceil(len[b] / numsteps).  (The data movement of
  * pyramid_stack is a free reshape of the yT-padded BLSTM output.) */

@@ -84,7 +84,7 @@ int overlap_workspace(size_t bytes) {
   Overlap& o = overlap();
   if (bytes <= o.ws_bytes) return 0;
   if (o.ws) {
-    NABU_CHECK_CUDA(cudaStreamSynchronize(o.side));
+    NABU_CHECK_CUDA(cudaDeviceSynchronize());          // the caller's stream may still read operand planes that live here
     NABU_CHECK_CUDA(cudaFree(o.ws));
     o.ws = nullptr; o.ws_bytes = 0;
   }

@@ -675,6 +675,114 @@ Ws carve_side(void* base, int H, int B, int T, int D) {
   return w;
 }
 
+// ---- operand planes that travel with the activations (include/nabu_b200.h: nabu_blstm_*_planes) ----------------------
+// planes of an [R, C] fp32 matrix: hi at the base, lo plane_half(R * C) bytes further
+size_t plane_half(size_t elems) { return align_up(elems * 2, 256); }
+
+__device__ float g_inv_y_scale = 1.f / Y_PLANE_SCALE;
+const float* inv_y_scale_ptr() {
+  static float* p = nullptr;
+  if (!p && cudaGetSymbolAddress((void**)&p, g_inv_y_scale) != cudaSuccess) p = nullptr;
+  return p;
+}
+
+// y planes for the recurrence kernels that do not write them themselves: split of y * 32 (8 values per thread)
+__global__ void __launch_bounds__(256) split_fixed_kernel(const float* __restrict__ src, size_t n8, __half* __restrict__ hi,
+                                                          __half* __restrict__ lo, float S) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    union { __half h[8]; uint4 u; } ph, pl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half h = __float2half_rn(v[j] * S);
+      ph.h[j] = h;
+      pl.h[j] = __float2half_rn((v[j] * S - __half2float(h)) * 2048.f);
+    }
+    reinterpret_cast<uint4*>(hi)[i] = ph.u;
+    reinterpret_cast<uint4*>(lo)[i] = pl.u;
+  }
+}
+
+// The backward recurrence writes the dZ planes with the gate columns of a direction in the order [unit quad][gate][4 units]
+// (blstm_cl_bwd8.cu: a thread's 16 values are then 32 contiguous bytes): column g*H + j sits at zperm(g, j).
+__host__ __device__ inline int zperm(int g, int j) { return (j >> 2) * 16 + g * 4 + (j & 3); }
+
+// dK[r][g*H + j] = tmp[r][zperm(g, j)]  (the weight-gradient GEMMs contract against the permuted planes)
+__global__ void __launch_bounds__(256) unpermute_cols_kernel(const float* __restrict__ tmp, int R, int H, float* __restrict__ out) {
+  const int H4 = 4 * H;
+  const size_t n = (size_t)R * H4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H4);
+    const size_t r = i / H4;
+    out[i] = tmp[r * H4 + zperm(c / H, c % H)];
+  }
+}
+// [Kx_fw | Kx_bw] with the same column order as the dZ planes: out[r][d*4H + zperm(g, j)] = kern[d][r][g*H + j], r < D
+__global__ void __launch_bounds__(256) permute_kx_kernel(const float* __restrict__ k0, const float* __restrict__ k1, int D, int H,
+                                                         float* __restrict__ out) {
+  const int H4 = 4 * H;
+  const size_t n = (size_t)D * 2 * H4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % (2 * H4));
+    const size_t r = i / (2 * H4);
+    const int d = cc / H4, c = cc % H4;
+    out[r * 2 * H4 + (size_t)d * H4 + zperm(c / H, c % H)] = (d ? k1 : k0)[r * H4 + c];
+  }
+}
+
+// Library-owned scratch of the planes path: two sets of dZ planes [B*T, 8H] (hi | lo) + their 1/scale -- the deferred weight
+// gradients of layer l read set k on the side stream while layer l-1's recurrence writes set k^1 --, the planes of a
+// layer input that arrived without planes (layer 0's features), the weights' planes for dX, split-K scratch.
+struct SideZ {
+  void *zh[2], *zl[2]; float* zglob[2];
+  void *xh, *xl; float* xglob;          // xglob: [0], [1] 1/scale of x, y; [8], [9] max bits (split_global's scratch)
+  void *yh, *yl;                        // planes of a y that arrived without planes (the plain entry points)
+  void *kh, *kl; float* kglob;          // [Kx_fw | Kx_bw] planes [D, 8H] for dX (columns in the planes' order)
+  float* kperm;                         // fp32 [D, 8H]: the permuted weights before their split (caller's stream)
+  float* dktmp[2];                      // fp32 [(D+H), 4H] per direction: weight gradients in the planes' column order
+  float* gemm; size_t gemm_bytes;
+  size_t total;
+};
+// The two dZ sets sit at FIXED places of the scratch (set k at k * set_cap), whatever the shape of the call: a layer's
+// deferred GEMMs still read set k while the next layer -- of another length or width in a pyramidal encoder -- writes
+// set k^1 and lays out its own misc region.  The capacities only grow, and growing reallocates behind a device sync.
+struct SideCap { size_t set_cap, misc_cap; };
+SideCap& side_cap() {
+  static SideCap c = {0, 0};
+  return c;
+}
+size_t sidez_set_bytes(int H, int B, int T) { return 2 * align_up((size_t)B * T * 8 * H * 2, 256) + 256; }
+SideZ carve_sidez(void* base, size_t set_cap, int H, int B, int T, int D) {
+  SideZ w = {};
+  char* b = (char*)base;
+  const size_t H4 = (size_t)4 * H, D8 = align_up(D, 8);
+  const size_t plane = align_up((size_t)B * T * 2 * H4 * 2, 256);
+  for (int k = 0; k < 2; ++k) {
+    char* s = b + (size_t)k * set_cap;
+    w.zh[k] = s; w.zl[k] = s + plane; w.zglob[k] = (float*)(s + 2 * plane);
+  }
+  size_t off = 2 * set_cap;
+  auto take = [&](size_t bytes) { void* p = b + off; off += align_up(bytes, 256); return p; };
+  w.xh = take((size_t)B * T * D8 * 2); w.xl = take((size_t)B * T * D8 * 2);
+  w.xglob = (float*)take(256);
+  w.yh = take((size_t)B * (T + YT_SLACK) * 2 * H * 2); w.yl = take((size_t)B * (T + YT_SLACK) * 2 * H * 2);
+  w.kh = take((size_t)D * 2 * H4 * 2); w.kl = take((size_t)D * 2 * H4 * 2);
+  w.kglob = (float*)take(256);
+  w.kperm = (float*)take((size_t)D * 2 * H4 * 4);
+  for (int d = 0; d < 2; ++d) w.dktmp[d] = (float*)take((size_t)(D + H) * H4 * 4);
+  w.gemm_bytes = sgemm_workspace_bytes();
+  w.gemm = (float*)take(w.gemm_bytes);
+  w.total = off;
+  return w;
+}
+struct ZState { unsigned calls; cudaEvent_t done[2]; bool recorded[2]; cudaEvent_t dx_done[2]; bool dx_recorded[2]; };
+ZState& zstate() {
+  static ZState z = {};
+  return z;
+}
+
 // fp16-split tensor-core GEMMs (gemm_h2.cu) for the layer-sized contractions; NABU_GEMM=tf32|simt keeps gemm().
 bool use_h2(int B, int T, int D, int H, int yT) {
   static int enabled = -1;
@@ -697,11 +805,28 @@ extern "C" size_t nabu_blstm_workspace_bytes(int B, int T, int D, int H) {
   return carve(nullptr, H, B, T, D).total;
 }
 
+extern "C" size_t nabu_blstm_planes_bytes(int B, int yT, int H) {
+  if (B <= 0 || yT <= 0 || H <= 0 || H % 4) return 0;
+  return 2 * plane_half((size_t)B * yT * 2 * H);
+}
+
 extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int D, int H,
                               const float* kernel_fw, const float* bias_fw, const float* kernel_bw,
                               const float* bias_bw, float* y, int yT, float* gates, float* cells,
                               void* workspace, size_t ws_bytes, void* stream_) {
+  return nabu_blstm_fwd_planes(x, nullptr, len, B, T, D, H, kernel_fw, bias_fw, kernel_bw, bias_bw, y, nullptr, yT, gates, cells,
+                               workspace, ws_bytes, stream_);
+}
+
+extern "C" int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const int* len, int B, int T, int D, int H,
+                                     const float* kernel_fw, const float* bias_fw, const float* kernel_bw,
+                                     const float* bias_bw, float* y, void* y_planes, int yT, float* gates, float* cells,
+                                     void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  NABU_REQUIRE(!x_planes || D % 8 == 0, "blstm_fwd: input planes need D %% 8 == 0 (D=%d)", D);
+  NABU_REQUIRE(!y_planes || H % 4 == 0, "blstm_fwd: output planes need num_units %% 4 == 0 (H=%d)", H);
+  void* yh = y_planes;
+  void* yl = y_planes ? (char*)y_planes + plane_half((size_t)B * yT * 2 * H) : nullptr;
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_fwd: bad shape B=%d T=%d D=%d H=%d yT=%d", B, T, D, H, yT);
   Ws w = carve(workspace, H, B, T, D);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
@@ -714,8 +839,14 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   // input projection for all T at once: Gx = X . Kx + b
   if (use_h2(B, T, D, H, yT)) {
     const int D8 = (int)align_up(D, 8);
-    if (int e = split_rows(x, D, B * T, D, w.p1h, w.p1l, D8, w.row1, stream)) return e;
     H2Operand xa = {w.p1h, w.p1l, D8, w.row1, nullptr};
+    if (x_planes) {        // the producer of x already wrote its operand planes (scale 32): no pass over x at all
+      xa.hi = x_planes; xa.lo = (const char*)x_planes + plane_half((size_t)B * T * D); xa.ld = D;
+      xa.row_inv = nullptr; xa.glob_inv = inv_y_scale_ptr();
+      NABU_REQUIRE(xa.glob_inv != nullptr, "blstm_fwd: device constant unavailable");
+    } else if (int e = split_rows(x, D, B * T, D, w.p1h, w.p1l, D8, w.row1, stream)) {
+      return e;
+    }
     for (int d = 0; d < 2; ++d) {
       if (int e = split_global(kern[d], H4, D, H4, w.wh[d], w.wl[d], H4, (unsigned*)(w.glob + 8 + d), w.glob + d, stream))
         return e;
@@ -728,9 +859,24 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
         return e;
   }
   NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
-  if (yT > T)
+  if (yT > T) {
     NABU_CHECK_CUDA(cudaMemset2DAsync(y + (size_t)T * 2 * H, (size_t)yT * 2 * H * sizeof(float), 0,
                                       (size_t)(yT - T) * 2 * H * sizeof(float), B, stream));
+    if (y_planes)
+      for (void* pl : {yh, yl})
+        NABU_CHECK_CUDA(cudaMemset2DAsync((char*)pl + (size_t)T * 2 * H * 2, (size_t)yT * 2 * H * 2, 0,
+                                          (size_t)(yT - T) * 2 * H * 2, B, stream));
+  }
+  // y planes for the kernels that do not write them themselves (everything but the tcgen05 cluster kernel)
+  auto planes_after = [&]() -> int {
+    if (!y_planes) return 0;
+    const size_t n8 = (size_t)B * yT * 2 * H / 8;
+    KernelScope ks("split_fixed", stream);
+    split_fixed_kernel<<<(unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)num_sms() * 8), 256, 0, stream>>>(
+        y, n8, (__half*)yh, (__half*)yl, Y_PLANE_SCALE);
+    NABU_CHECK_LAUNCH();
+    return 0;
+  };
   // The tcgen05 recurrence (blstm_tc.cu) is opt-in (NABU_REC=tc): measured 20.8 us/step at cfg-3, the FFMA kernel
   // with the batch-group split is faster; see DESIGN.md section 6.
   static int use_tc = -1;
@@ -741,12 +887,13 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   BlstmTcPlan tpl;
   if (use_tc && blstm_tc_plan(B, H, &tpl)) {
     NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)4 * 128 * H * sizeof(float), stream));
-    return blstm_rec_fwd_tc(tpl, kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream);
+    if (int e = blstm_rec_fwd_tc(tpl, kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream)) return e;
+    return planes_after();
   }
   NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * (ceil_div(B, 128) * 128) * sizeof(float), stream));
   if (blstm_fwd_cluster_tc_eligible(B, H)) {
     bool launched = false;
-    if (int e = blstm_rec_fwd_cluster_tc(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched))
+    if (int e = blstm_rec_fwd_cluster_tc(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched, yh, yl))
       return e;
     if (launched) return 0;
   }
@@ -759,7 +906,7 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   if (blstm_fwd_cluster_eligible(B, H)) {
     bool launched = false;
     if (int e = blstm_rec_fwd_cluster(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched)) return e;
-    if (launched) return 0;
+    if (launched) return planes_after();
   }
   RecParams rp = {};
   rp.kernel[0] = kern[0]; rp.kernel[1] = kern[1];
@@ -767,7 +914,8 @@ extern "C" int nabu_blstm_fwd(const float* x, const int* len, int B, int T, int 
   rp.cells[0] = c[0]; rp.cells[1] = c[1];
   rp.y = y; rp.xchg = w.xchg; rp.counters = w.counters; rp.len = len;
   rp.B = B; rp.T = T; rp.yT = yT; rp.D = D; rp.H = H;
-  return run_recurrence(false, rp, B, H, stream);
+  if (int e = run_recurrence(false, rp, B, H, stream)) return e;
+  return planes_after();
 }
 
 extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int D, int H,
@@ -775,7 +923,17 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
                               float* gates, const float* cells, const float* dy, float* dx,
                               float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
                               void* workspace, size_t ws_bytes, void* stream_) {
+  return nabu_blstm_bwd_planes(x, nullptr, len, B, T, D, H, kernel_fw, kernel_bw, y, nullptr, yT, gates, cells, dy, dx,
+                               dkernel_fw, dbias_fw, dkernel_bw, dbias_bw, workspace, ws_bytes, stream_);
+}
+
+extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const int* len, int B, int T, int D, int H,
+                                     const float* kernel_fw, const float* kernel_bw, const float* y, const void* y_planes,
+                                     int yT, float* gates, const float* cells, const float* dy, float* dx,
+                                     float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
+                                     void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  NABU_REQUIRE(!x_planes || D % 8 == 0, "blstm_bwd: input planes need D %% 8 == 0 (D=%d)", D);
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_bwd: bad shape");
   Ws w = carve(workspace, H, B, T, D);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
@@ -799,6 +957,39 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
   // which is issued on a high-priority stream so that its clusters take SMs as the GEMM's CTAs retire.
   Overlap& ov = overlap();
   const bool defer = ov.on && blstm_bwd_cluster8_eligible(B, H) && use_h2(B, T, D, H, yT);
+  // dZ as operand planes straight from the recurrence (NABU_ZPLANES=0 keeps the fp32 dZ + split passes): the planes live
+  // in library-owned scratch, two sets used alternately (see SideZ)
+  static int zplanes_on = -1;
+  if (zplanes_on < 0) zplanes_on = (getenv("NABU_ZPLANES") && atoi(getenv("NABU_ZPLANES")) == 0) ? 0 : 1;
+  const bool zplanes = zplanes_on && blstm_bwd_cluster8_eligible(B, H) && use_h2(B, T, D, H, yT) &&
+                       gemm_h2_eligible(GEMM_NT, B * T, D, 2 * H4) && inv_y_scale_ptr() != nullptr;
+  SideZ sz = {};
+  int zk = 0;
+  if (zplanes) {
+    if (int e = overlap_init()) return e;
+    SideCap& cap = side_cap();
+    const size_t set_need = sidez_set_bytes(H, B, T);
+    const size_t misc_need = carve_sidez(nullptr, 0, H, B, T, D).total;
+    if (set_need > cap.set_cap || misc_need > cap.misc_cap) {
+      NABU_CHECK_CUDA(cudaDeviceSynchronize());         // the sets move: nothing may be in flight
+      cap.set_cap = std::max(cap.set_cap, set_need);
+      cap.misc_cap = std::max(cap.misc_cap, misc_need);
+      zstate().recorded[0] = zstate().recorded[1] = zstate().dx_recorded[0] = zstate().dx_recorded[1] = false;
+    }
+    if (int e = overlap_workspace(2 * cap.set_cap + cap.misc_cap)) return e;
+    sz = carve_sidez(ov.ws, cap.set_cap, H, B, T, D);
+    ZState& zs = zstate();
+    zk = (int)(zs.calls++ & 1u);
+    if (!zs.done[0]) {
+      for (int k = 0; k < 2; ++k) {
+        NABU_CHECK_CUDA(cudaEventCreateWithFlags(&zs.done[k], cudaEventDisableTiming));
+        NABU_CHECK_CUDA(cudaEventCreateWithFlags(&zs.dx_done[k], cudaEventDisableTiming));
+      }
+    }
+    // set zk was last read by the GEMMs of two calls ago (side stream and the caller's stream of that call)
+    if (zs.recorded[zk]) NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, zs.done[zk], 0));
+    if (zs.dx_recorded[zk]) NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, zs.dx_done[zk], 0));
+  }
   if (blstm_bwd_cluster8_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};
     NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, stream));
@@ -829,7 +1020,9 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
       }
     }
     ov.in_defer = defer;
-    const int re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched);
+    const int re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched,
+                                          zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr,
+                                          zplanes ? sz.zglob[zk] : nullptr);
     ov.in_defer = false;
     if (re) return re;
     if (defer) {
@@ -863,6 +1056,79 @@ extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int 
     KernelScope ks("sum_groups", stream);
     sum_groups_kernel<<<ceil_div(2 * H4, 256), 256, 0, stream>>>(w.dbpart, ngrp, H4, dbias_fw, dbias_bw);
     NABU_CHECK_LAUNCH();
+  }
+  if (zplanes && launched) {
+    // ---- every contraction reads the planes the recurrences wrote: no split / absmax pass over x, y or dZ ------------
+    const float* inv_y = inv_y_scale_ptr();
+    const int D8 = (int)align_up(D, 8);
+    ZState& zs = zstate();
+    H2Operand zb[2];
+    for (int d = 0; d < 2; ++d)
+      zb[d] = {(const __half*)sz.zh[zk] + (size_t)d * H4, (const __half*)sz.zl[zk] + (size_t)d * H4, 2 * H4, nullptr, sz.zglob[zk]};
+    auto weight_grads = [&](cudaStream_t ws) -> int {
+      H2Operand xa;
+      if (x_planes) {
+        xa = {x_planes, (const char*)x_planes + plane_half((size_t)B * T * D), D, nullptr, inv_y};
+      } else {
+        if (int e = split_global(x, D, B * T, D, sz.xh, sz.xl, D8, (unsigned*)(sz.xglob + 8), sz.xglob, ws)) return e;
+        xa = {sz.xh, sz.xl, D8, nullptr, sz.xglob};
+      }
+      for (int d = 0; d < 2; ++d)
+        if (int e = gemm_h2(GEMM_TN, D, H4, B * T, 1.f, xa, zb[d], 0.f, sz.dktmp[d], H4, nullptr, nullptr, sz.gemm, sz.gemm_bytes, ws))
+          return e;
+      const void* yh = y_planes;
+      const void* yl = y_planes ? (const char*)y_planes + plane_half((size_t)B * yT * 2 * H) : nullptr;
+      const float* yinv = inv_y;
+      if (T > 1 && !y_planes) {          // y without planes (a caller of the plain entry point): split it here
+        if (int e = split_global(y, 2 * H, B * yT, 2 * H, sz.yh, sz.yl, 2 * H, (unsigned*)(sz.xglob + 9), sz.xglob + 1, ws)) return e;
+        yh = sz.yh; yl = sz.yl; yinv = sz.xglob + 1;
+      }
+      for (int d = 0; d < 2; ++d) {
+        float* dKh = sz.dktmp[d] + (size_t)D * H4;
+        if (T > 1) {
+          GemmSeg seg;
+          seg.seg = T - 1; seg.segA = yT; seg.segB = T;
+          seg.offA = d == 0 ? 0 : 1; seg.offB = d == 0 ? 1 : 0;
+          H2Operand ya = {(const __half*)yh + d * H, (const __half*)yl + d * H, 2 * H, nullptr, yinv};
+          if (int e = gemm_h2(GEMM_TN, H, H4, B * (T - 1), 1.f, ya, zb[d], 0.f, dKh, H4, nullptr, &seg, sz.gemm, sz.gemm_bytes, ws))
+            return e;
+        } else {
+          NABU_CHECK_CUDA(cudaMemsetAsync(dKh, 0, (size_t)H * H4 * sizeof(float), ws));
+        }
+        KernelScope ks("unpermute_cols", ws);
+        unpermute_cols_kernel<<<num_sms() * 4, 256, 0, ws>>>(sz.dktmp[d], D + H, H, dkern[d]);
+        NABU_CHECK_LAUNCH();
+      }
+      return 0;
+    };
+    if (dx) {
+      // dX = [dZ_fw | dZ_bw] . [Kx_fw | Kx_bw]^T as ONE contraction over K = 8H.  It is on the critical path (the layer
+      // below waits for it), so it runs BEFORE the deferred weight gradients are released: sharing the tensor cores
+      // with them cost it 6 ms per step.
+      {
+        KernelScope ks("permute_kx", stream);
+        permute_kx_kernel<<<num_sms() * 4, 256, 0, stream>>>(kern[0], kern[1], D, H, sz.kperm);
+        NABU_CHECK_LAUNCH();
+      }
+      if (int e = split_global(sz.kperm, 2 * H4, D, 2 * H4, sz.kh, sz.kl, 2 * H4, (unsigned*)(sz.kglob + 8), sz.kglob, stream)) return e;
+      H2Operand za = {sz.zh[zk], sz.zl[zk], 2 * H4, nullptr, sz.zglob[zk]};
+      H2Operand kb = {sz.kh, sz.kl, 2 * H4, nullptr, sz.kglob};
+      if (int e = gemm_h2(GEMM_NT, B * T, D, 2 * H4, 1.f, za, kb, 0.f, dx, D, nullptr, nullptr, nullptr, 0, stream)) return e;
+    }
+    NABU_CHECK_CUDA(cudaEventRecord(zs.dx_done[zk], stream));
+    zs.dx_recorded[zk] = true;
+    if (defer) {
+      NABU_CHECK_CUDA(cudaStreamWaitEvent(ov.side, zs.dx_done[zk], 0));
+      if (int e = weight_grads(ov.side)) return e;
+      NABU_CHECK_CUDA(cudaEventRecord(ov.ev_done, ov.side));
+      NABU_CHECK_CUDA(cudaEventRecord(zs.done[zk], ov.side));
+      zs.recorded[zk] = true;
+      ov.pending = true;
+    } else {
+      if (int e = weight_grads(stream)) return e;
+      zs.recorded[zk] = false;
+    }
+    return 0;
   }
   // gates[] now hold dZ (zero for t >= len)
   if (use_h2(B, T, D, H, yT)) {

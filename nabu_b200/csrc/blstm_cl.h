@@ -4,6 +4,10 @@
 
 namespace nabu {
 
+// fixed power-of-two scale of the fp16 hi/lo operand planes of a BLSTM output: |h| < 1, so h * 32 < 32 sits where the
+// per-row / per-matrix scales of gemm_h2.cu put an operand's maximum ([32, 64))
+constexpr float Y_PLANE_SCALE = 32.f;
+
 // B <= 128 and num_units in {128, 256, 512} (64 CTAs per direction = 8 clusters of 8); NABU_REC_BWD=flat disables.
 bool blstm_bwd_cluster_eligible(int B, int H);
 
@@ -20,9 +24,10 @@ int blstm_rec_fwd_cluster(const float* const kernel[2], float* const gates[2], f
 
 // tcgen05 forward (blstm_cl_tc.cu): B <= 128, num_units in {256, 512}; NABU_REC_FWD=ffma|flat disables.
 bool blstm_fwd_cluster_tc_eligible(int B, int H);
+// yh / yl (optional): fp16 hi / lo planes [B, yT, 2H] of y * 32 written by the kernel (cl_common.cuh).
 int blstm_rec_fwd_cluster_tc(const float* const kernel[2], float* const gates[2], float* const cells[2], float* y,
                              float* xchg, unsigned* counters, const int* len, int B, int T, int yT, int D, int H,
-                             cudaStream_t stream, bool* launched);
+                             cudaStream_t stream, bool* launched, void* yh = nullptr, void* yl = nullptr);
 
 // tcgen05 backward: same eligibility; rowmax = 128 zeroed words of scratch (per-row max |dy|, filled by a pre-pass);
 // the exchange buffer must be zeroed by the caller (rows b >= B are read); NABU_REC_BWD=ffma|flat disables.
@@ -36,8 +41,11 @@ int blstm_rec_bwd_cluster_tc(const float* const kernel[2], float* const gates[2]
 // num_units in {256, 512}; preferred over the cluster-of-4 kernel; NABU_REC_BWD=cl4|ffma|flat disables.  rowmax and the
 // (zeroed) exchange buffer as for blstm_rec_bwd_cluster_tc.
 bool blstm_bwd_cluster8_eligible(int B, int H);
+// zh / zl / zinv (optional): the kernel writes the fp16 hi / lo planes [B*T, 8H] of dZ (fw | bw) scaled by one power of two
+// and 1/scale to *zinv INSTEAD of the fp32 dZ in gates[] (which then keeps the forward's activations).
 int blstm_rec_bwd_cluster8(const float* const kernel[2], float* const gates[2], const float* const cells[2],
                            const float* dy, float* dbpart, float* xchg, unsigned* rowmax, const int* len, int B, int T, int yT,
-                           int D, int H, cudaStream_t stream, bool* launched);
+                           int D, int H, cudaStream_t stream, bool* launched, void* zh = nullptr, void* zl = nullptr,
+                           float* zinv = nullptr);
 
 }  // namespace nabu

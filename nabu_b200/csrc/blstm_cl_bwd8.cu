@@ -65,7 +65,7 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
   __shared__ __align__(8) uint64_t rx_bar;
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float scale[BT];
+  __shared__ unsigned gmax_bits;                      // max over the batch of the rows' max |dy| (the planes' scale)
 
   const int H = p.H, H4 = 4 * p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -80,16 +80,11 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
   const float* cells = p.cells[dir];
   uint8_t* dzx = reinterpret_cast<uint8_t*>(p.xchg) + (size_t)dir * 2 * H4 * BT * 4;   // [2 parity][8 slices][SLICE]
 
+  if (tid == 0) gmax_bits = 0u;
+  __syncthreads();
   if (tid < BT) {
     const float G = tid < p.B ? __uint_as_float(rowmax[tid]) : 0.f;
-    float S = 1.f;
-    if (G > 0.f && G < 3.0e38f) {
-      int e;
-      frexpf(G, &e);                                   // G in [2^(e-1), 2^e)
-      e = e < -100 ? -100 : (e > 100 ? 100 : e);
-      S = ldexpf(1.f, 6 - e);                          // G * S in [32, 64)
-    }
-    scale[tid] = S;
+    if (G > 0.f && G < 3.0e38f) atomicMax(&gmax_bits, __float_as_uint(G));      // positive floats order like their bits
   }
   if (tid == 0) {
     mbar_init(smem_u32(&rx_bar), 1);
@@ -103,23 +98,30 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
   tc_fence_after();
   const uint32_t tm = tmem_slot;
 
-  // resident weights -> TMEM: A[m][kl] = Kh[NC*q + m][g*H + (q'*8 + r)*16 + u],  kl = q'*64 + g*16 + u.
-  // One (q', g) group = 16 consecutive floats of a Kh row = 8 packed columns; warps w and w+4 share a lane quadrant.
+  // resident weights -> TMEM: A[m][kl] = Kh[NC*q + m][g*H + (q'*8 + r)*16 + u],  kl = q'*64 + (u/4)*16 + g*4 + u%4:
+  // inside a producer CTA's 64 columns the order is [unit quad][gate][4 units], so that the 16 values a pointwise thread
+  // owns (4 gates x 4 units of one row) are 32 contiguous bytes of the exchanged operand -- two 16-byte stores instead
+  // of four 8-byte ones (the LSU transaction count bounds the pointwise stage).  One (q', quad) group = 16 consecutive
+  // k = 8 packed columns; warps w and w+4 share a lane quadrant.
   {
     const int m = (warp & 3) * 32 + lane;
     const float* wrow = Kh + (size_t)(NC * q + m) * H4;
     const uint32_t tbase = tm + ((uint32_t)((warp & 3) * 32) << 16);
     for (int grp = warp >> 2; grp < KBN * 4; grp += 2) {
-      const int qq = grp >> 2, g = grp & 3;
-      const float* src = wrow + g * H + (qq * CLS + r) * HS;
+      const int qq = grp >> 2, uq = grp & 3;
       uint32_t vh[8], vl[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        __half h0, l0, h1, l1;
-        split_h(src[2 * c], &h0, &l0);
-        split_h(src[2 * c + 1], &h1, &l1);
-        vh[c] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        vl[c] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      for (int g = 0; g < 4; ++g) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + g * H + (qq * CLS + r) * HS + uq * 4);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          __half h0, l0, h1, l1;
+          split_h(wv[2 * c], &h0, &l0);
+          split_h(wv[2 * c + 1], &h1, &l1);
+          vh[g * 2 + c] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          vl[g * 2 + c] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
       }
       tmem_st8(tbase + TM_AH + (uint32_t)grp * 8, vh);
       tmem_st8(tbase + TM_AL + (uint32_t)grp * 8, vl);
@@ -138,14 +140,27 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
   // contiguous bytes of a (row, gate) in every global array, so a warp access is 8 rows x 2 full sectors (the LSU
   // transaction count, not bytes, bounded the first version of this kernel: one 16-byte access per lane and line).
   const int ug = (tid & 3) * 4, rw = tid >> 2;
+  // ONE power-of-two scale for the exchanged gate gradients and their operand planes: the largest |dy| of the batch lands
+  // in [32, 64) (every CTA computes the same value).  Gate derivatives are <= 1, so dz starts below that bound and would
+  // have to grow 1000x through the recurrence to reach fp16's maximum (conversions saturate instead of producing inf);
+  // values down to 1e-6 of the batch maximum keep the full 22 bits, smaller ones an absolute error of 2^-41 of it.
+  float zS = 1.f;
+  {
+    const float G = __uint_as_float(gmax_bits);
+    if (G > 0.f) {
+      int e;
+      frexpf(G, &e);                                   // G in [2^(e-1), 2^e)
+      e = e < -100 ? -100 : (e > 100 ? 100 : e);
+      zS = ldexpf(1.f, 6 - e);                         // G * zS in [32, 64)
+    }
+    if (p.zinv && blockIdx.x == 0 && tid == 0) *p.zinv = 1.f / zS;
+  }
+  const float zSi = 1.f / zS;
   int plen[2];
-  float pS[2], pSi[2];
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int b = rw + 64 * rr;
     plen[rr] = b < p.B ? p.len[b] : 0;
-    pS[rr] = scale[b];
-    pSi[rr] = 1.f / pS[rr];
   }
   float dbacc[4][4], dcc[2][4];
 #pragma unroll
@@ -293,7 +308,7 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) dh[rr][u] = fmaf(dh[rr][u], pSi[rr], dyv[rr][u]);
+      for (int u = 0; u < 4; ++u) dh[rr][u] = fmaf(dh[rr][u], zSi, dyv[rr][u]);
     // my receive buffer is free for the next step once these loads have returned (nothing to publish: relaxed)
     if (s > 0) cluster_arrive_relaxed();
     float dzv[2][4][4];
@@ -317,34 +332,59 @@ blstm_rec_bwd_cluster8_kernel(const ClParams p, const unsigned* __restrict__ row
         dcc[rr][u] = dcn;
       }
     {
-      // dz_t, scaled, split and flagged, into K block q of slice r (all 128 rows: the consumers wait for every half)
+      // dz_t, scaled, split and flagged: the thread's 16 values of a row (k = quad*16 + g*4 + u) are two 16-byte chunks of
+      // the hi tile and two of the lo tile of K block q of slice r (all 128 rows: the consumers wait for every half).
+      // The SAME words are the row's piece of the dZ operand planes of the weight-gradient / dX GEMMs (column order
+      // [unit quad][gate][4 units] inside a direction, undone by the host: blstm.cu), so no pass ever re-reads dZ; the
+      // exchange flag stays in the lowest bit of both halves there (hi + lo / 2048 still carries dz to 2^-20).
       const unsigned short fb = (unsigned short)ll_flag(iter);
       uint8_t* blk = dznext + (size_t)r * SLICE + (size_t)q * 2 * A_TILE;
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr)
+      for (int rr = 0; rr < 2; ++rr) {
+        uint32_t wh[8], wl[8];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           unsigned short hh[4], hl[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            split_h_sat_flag(dzv[rr][g][u] * pS[rr], fb, &hh[u], &hl[u]);
+            split_h_sat_flag(dzv[rr][g][u] * zS, fb, &hh[u], &hl[u]);
             dbacc[g][u] += dzv[rr][g][u];
           }
-          uint8_t* t = blk + sw128_h(rw + 64 * rr, g * 16 + ug);
-          __stcg(reinterpret_cast<uint2*>(t), make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16)));
-          __stcg(reinterpret_cast<uint2*>(t + A_TILE), make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16)));
+          wh[2 * g] = (uint32_t)hh[0] | ((uint32_t)hh[1] << 16); wh[2 * g + 1] = (uint32_t)hh[2] | ((uint32_t)hh[3] << 16);
+          wl[2 * g] = (uint32_t)hl[0] | ((uint32_t)hl[1] << 16); wl[2 * g + 1] = (uint32_t)hl[2] | ((uint32_t)hl[3] << 16);
         }
+        const int row = rw + 64 * rr;
+        uint8_t* t0 = blk + sw128_h(row, ug * 4);             // k = (ug / 4) * 16: gates 0, 1
+        uint8_t* t1 = blk + sw128_h(row, ug * 4 + 8);         // gates 2, 3
+        __stcg(reinterpret_cast<uint4*>(t0), make_uint4(wh[0], wh[1], wh[2], wh[3]));
+        __stcg(reinterpret_cast<uint4*>(t1), make_uint4(wh[4], wh[5], wh[6], wh[7]));
+        __stcg(reinterpret_cast<uint4*>(t0 + A_TILE), make_uint4(wl[0], wl[1], wl[2], wl[3]));
+        __stcg(reinterpret_cast<uint4*>(t1 + A_TILE), make_uint4(wl[4], wl[5], wl[6], wl[7]));
+        if (p.zh && row < p.B) {
+          const size_t zo = ((size_t)row * p.T + tt[rr]) * (2 * H4) + (size_t)dir * H4 + (size_t)(j0 + ug) * 4;
+          uint4* zh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.zh) + zo);
+          uint4* zl = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.zl) + zo);
+          // frames past the utterance's length: exact zeros (a flagged zero is -2^-34, and dX must be 0 there exactly)
+          const uint32_t km = valid[rr] ? 0xFFFFFFFFu : 0u;
+          __stcg(zh, make_uint4(wh[0] & km, wh[1] & km, wh[2] & km, wh[3] & km));
+          __stcg(zh + 1, make_uint4(wh[4] & km, wh[5] & km, wh[6] & km, wh[7] & km));
+          __stcg(zl, make_uint4(wl[0] & km, wl[1] & km, wl[2] & km, wl[3] & km));
+          __stcg(zl + 1, make_uint4(wl[4] & km, wl[5] & km, wl[6] & km, wl[7] & km));
+        }
+      }
     }
     CL_STAMP(iter, 6); CL_STAMP(iter, 7); CL_STAMP(iter, 8); CL_STAMP(iter, 9);
-    // ---- off the critical path: the fp32 dz the weight-gradient GEMMs read ------------------------------------------
+    // ---- without operand planes: the fp32 dz into gates[] for the split passes / fp32 GEMMs of the host -----------------
+    if (!p.zh) {
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int b = rw + 64 * rr;
-      if (b < p.B) {
-        float* gp = gates + ((size_t)b * p.T + tt[rr]) * H4 + j0 + ug;
+      for (int rr = 0; rr < 2; ++rr) {
+        const int b = rw + 64 * rr;
+        if (b < p.B) {
+          float* gp = gates + ((size_t)b * p.T + tt[rr]) * H4 + j0 + ug;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          __stcg(reinterpret_cast<float4*>(gp + g * H), make_float4(dzv[rr][g][0], dzv[rr][g][1], dzv[rr][g][2], dzv[rr][g][3]));
+          for (int g = 0; g < 4; ++g)
+            __stcg(reinterpret_cast<float4*>(gp + g * H), make_float4(dzv[rr][g][0], dzv[rr][g][1], dzv[rr][g][2], dzv[rr][g][3]));
+        }
       }
     }
   }
@@ -429,8 +469,9 @@ bool blstm_bwd_cluster8_eligible(int B, int H) {
 
 int blstm_rec_bwd_cluster8(const float* const kernel[2], float* const gates[2], const float* const cells[2],
                            const float* dy, float* dbpart, float* xchg, unsigned* rowmax, const int* len, int B, int T, int yT,
-                           int D, int H, cudaStream_t stream, bool* launched) {
+                           int D, int H, cudaStream_t stream, bool* launched, void* zh, void* zl, float* zinv) {
   ClParams p = {};
+  p.zh = zh; p.zl = zl; p.zinv = zinv;
   p.kernel[0] = kernel[0]; p.kernel[1] = kernel[1];
   p.gates[0] = gates[0]; p.gates[1] = gates[1];
   p.cells[0] = cells[0]; p.cells[1] = cells[1];

@@ -304,9 +304,30 @@ blstm_rec_fwd_cluster_tc_kernel(const ClParams p) {
           __stcg(reinterpret_cast<float2*>(cp), make_float2(av[4][0], av[4][1]));
         }
       }
-      float* yp = p.y + ((size_t)pb * p.yT + tt) * 2 * H + dir * H + j0 + pu;
+      const size_t yo = ((size_t)pb * p.yT + tt) * 2 * H + dir * H + j0 + pu;
+      float* yp = p.y + yo;
       if constexpr (UPT == 4) __stcg(reinterpret_cast<float4*>(yp), make_float4(hn[0], hn[1], hn[2], hn[3]));
       else __stcg(reinterpret_cast<float2*>(yp), make_float2(hn[0], hn[1]));
+      if (p.yh) {
+        // the operand planes of the GEMMs that read y (next layer's input projection, dKh, next layer's dKx): clean split
+        // (no exchange flag) of y * 32, so no separate split / absmax pass ever re-reads y
+        unsigned short ph[UPT], pl[UPT];
+#pragma unroll
+        for (int u = 0; u < UPT; ++u) {
+          __half hi, lo;
+          split_h(hn[u] * Y_PLANE_SCALE, &hi, &lo);
+          ph[u] = __half_as_ushort(hi); pl[u] = __half_as_ushort(lo);
+        }
+        __half* yh = reinterpret_cast<__half*>(p.yh) + yo;
+        __half* yl = reinterpret_cast<__half*>(p.yl) + yo;
+        if constexpr (UPT == 4) {
+          __stcg(reinterpret_cast<uint2*>(yh), make_uint2((uint32_t)ph[0] | ((uint32_t)ph[1] << 16), (uint32_t)ph[2] | ((uint32_t)ph[3] << 16)));
+          __stcg(reinterpret_cast<uint2*>(yl), make_uint2((uint32_t)pl[0] | ((uint32_t)pl[1] << 16), (uint32_t)pl[2] | ((uint32_t)pl[3] << 16)));
+        } else {
+          __stcg(reinterpret_cast<unsigned*>(yh), (uint32_t)ph[0] | ((uint32_t)ph[1] << 16));
+          __stcg(reinterpret_cast<unsigned*>(yl), (uint32_t)pl[0] | ((uint32_t)pl[1] << 16));
+        }
+      }
     }
   }
   tc_fence_before();
@@ -765,8 +786,9 @@ bool blstm_fwd_cluster_tc_eligible(int B, int H) {
 
 int blstm_rec_fwd_cluster_tc(const float* const kernel[2], float* const gates[2], float* const cells[2], float* y,
                              float* xchg, unsigned* counters, const int* len, int B, int T, int yT, int D, int H,
-                             cudaStream_t stream, bool* launched) {
+                             cudaStream_t stream, bool* launched, void* yh, void* yl) {
   ClParams p = {};
+  p.yh = yh; p.yl = yl;
   p.kernel[0] = kernel[0]; p.kernel[1] = kernel[1];
   p.gates[0] = gates[0]; p.gates[1] = gates[1];
   p.cells[0] = cells[0]; p.cells[1] = cells[1];

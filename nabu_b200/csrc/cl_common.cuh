@@ -2,6 +2,7 @@
 // cluster-barrier PTX wrappers and the NABU_REC_TRACE phase stamps.
 #pragma once
 #include "common.cuh"
+#include "blstm_cl.h"
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,6 +27,11 @@ struct ClParams {
   long long* trace;         // NABU_REC_TRACE: per-phase globaltimer stamps of every CTA for steps [TRACE_S0, TRACE_S0 + TRACE_N)
   int B, T, yT, D, H;
   int fences;               // NABU_REC_FENCES: per-thread __threadfence + proxy fence before publishing (debug)
+  // fp16 hi/lo planes for the tensor-core GEMMs, written by the recurrences themselves (gemm_h2.cu's operand format):
+  // fwd: yh / yl [B, yT, 2H] = split of y * 32;  bwd: zh / zl [B*T, 8H] (fw | bw gate gradients side by side) = split of
+  // dZ * S, S the power of two that puts the largest |dy| of the batch in [32, 64), 1/S written to *zinv.  NULL = off.
+  void *yh, *yl, *zh, *zl;
+  float* zinv;
 };
 
 constexpr int TRACE_S0 = 200, TRACE_N = 8, TRACE_PH = 10, TRACE_CTAS = 256;

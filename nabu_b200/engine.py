@@ -188,7 +188,13 @@ def _i32(t, device):
     return t.to(device=device, dtype=torch.int32).contiguous()
 
 
-def _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT):
+def planes_enabled():
+    """operand planes travel with the activations (include/nabu_b200.h: nabu_blstm_*_planes); NABU_PLANES=0 turns it off"""
+    import os
+    return os.environ.get('NABU_PLANES', '1') != '0'
+
+
+def _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT, x_planes=None, want_planes=False):
     lib = L.load()
     B, T, D = x.shape
     y = torch.empty((B, yT, 2 * H), device=x.device, dtype=torch.float32)
@@ -198,46 +204,59 @@ def _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT):
     if nws == 0:
         L.check(2, 'nabu_blstm_workspace_bytes')
     ws = L.WORKSPACE.get(nws, x.device)
-    L.check(lib.nabu_blstm_fwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(bf), L.ptr(kb), L.ptr(bb),
-                               L.ptr(y), yT, L.ptr(gates), L.ptr(cells), L.ptr(ws), ws.numel(), L.stream()),
-            'nabu_blstm_fwd')
-    return y, gates, cells
+    y_planes = None
+    if want_planes and H % 4 == 0:
+        y_planes = torch.empty(lib.nabu_blstm_planes_bytes(B, yT, H), device=x.device, dtype=torch.uint8)
+    if x_planes is not None and D % 8:
+        x_planes = None
+    L.check(lib.nabu_blstm_fwd_planes(L.ptr(x), L.ptr(x_planes), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(bf), L.ptr(kb),
+                                      L.ptr(bb), L.ptr(y), L.ptr(y_planes), yT, L.ptr(gates), L.ptr(cells), L.ptr(ws),
+                                      ws.numel(), L.stream()), 'nabu_blstm_fwd_planes')
+    return y, gates, cells, y_planes
 
 
-def _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, need_dx, H, yT, gvars):
+def _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, need_dx, H, yT, gvars, x_planes=None, y_planes=None):
     lib = L.load()
     B, T, D = x.shape
     dkf, dbf, dkb, dbb = gvars
     dy = dy.contiguous()
     dx = torch.empty_like(x) if need_dx else None
     ws = L.WORKSPACE.get(lib.nabu_blstm_workspace_bytes(B, T, D, H), x.device)
-    L.check(lib.nabu_blstm_bwd(L.ptr(x), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(kb), L.ptr(y), yT,
-                               L.ptr(gates), L.ptr(cells), L.ptr(dy), L.ptr(dx), L.ptr(dkf), L.ptr(dbf),
-                               L.ptr(dkb), L.ptr(dbb), L.ptr(ws), ws.numel(), L.stream()),
-            'nabu_blstm_bwd')
+    if x_planes is not None and D % 8:
+        x_planes = None
+    L.check(lib.nabu_blstm_bwd_planes(L.ptr(x), L.ptr(x_planes), L.ptr(lens), B, T, D, H, L.ptr(kf), L.ptr(kb), L.ptr(y),
+                                      L.ptr(y_planes), yT, L.ptr(gates), L.ptr(cells), L.ptr(dy), L.ptr(dx), L.ptr(dkf),
+                                      L.ptr(dbf), L.ptr(dkb), L.ptr(dbb), L.ptr(ws), ws.numel(), L.stream()),
+            'nabu_blstm_bwd_planes')
     if _OVERLAP['on']:
         # deferred weight gradients read these on the library's side stream until side_join()
-        _OVERLAP['keep'].append((x, y, gates, kf, kb, gvars))
+        _OVERLAP['keep'].append((x, y, gates, kf, kb, gvars, x_planes, y_planes))
     return dx
 
 
 class _BLSTM(torch.autograd.Function):
-    """components/layer.py:8-51 via nabu_blstm_fwd / nabu_blstm_bwd."""
+    """components/layer.py:8-51 via nabu_blstm_fwd_planes / nabu_blstm_bwd_planes.  Returns (y, y_planes): the second output
+    is the fp16 operand-plane image of y (uint8, not differentiable; an empty tensor when planes are off) that the
+    consumer of y hands back as `x_planes`."""
 
     @staticmethod
-    def forward(ctx, x, lens, kf, bf, kb, bb, H, yT, gvars):
+    def forward(ctx, x, lens, kf, bf, kb, bb, H, yT, gvars, x_planes):
         x = x.contiguous()
-        y, gates, cells = _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT)
+        y, gates, cells, y_planes = _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT, x_planes, planes_enabled())
         ctx.save_for_backward(x, lens, kf, kb, y, gates, cells)
         ctx.H, ctx.yT, ctx.gvars = H, yT, gvars
+        ctx.x_planes, ctx.y_planes = x_planes, y_planes
         ctx.need_dx = x.requires_grad
-        return y
+        out_planes = y_planes if y_planes is not None else torch.empty(0, dtype=torch.uint8, device=x.device)
+        ctx.mark_non_differentiable(out_planes)
+        return y, out_planes
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dplanes):
         x, lens, kf, kb, y, gates, cells = ctx.saved_tensors
-        dx = _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, ctx.need_dx, ctx.H, ctx.yT, ctx.gvars)
-        return dx, None, None, None, None, None, None, None, None
+        dx = _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, ctx.need_dx, ctx.H, ctx.yT, ctx.gvars, ctx.x_planes,
+                            ctx.y_planes)
+        return dx, None, None, None, None, None, None, None, None, None
 
 
 _OVERLAP = {'on': False, 'keep': []}
@@ -288,7 +307,7 @@ class _BLSTMPadded(torch.autograd.Function):
         x = x.contiguous()
         pkf, pbf = _pad_gates(kf.detach(), H, Hp, True), _pad_gates(bf.detach(), H, Hp, False)
         pkb, pbb = _pad_gates(kb.detach(), H, Hp, True), _pad_gates(bb.detach(), H, Hp, False)
-        yp, gates, cells = _blstm_fwd_raw(x, lens, pkf, pbf, pkb, pbb, Hp, yT)
+        yp, gates, cells, _ = _blstm_fwd_raw(x, lens, pkf, pbf, pkb, pbb, Hp, yT)
         ctx.save_for_backward(x, lens, pkf, pkb, yp, gates, cells)
         ctx.H, ctx.Hp, ctx.yT, ctx.gvars = H, Hp, yT, gvars
         ctx.need_dx = x.requires_grad
@@ -311,24 +330,32 @@ class _BLSTMPadded(torch.autograd.Function):
 
 def rec_width(H, B=None):
     """The number of hidden units the recurrence kernels run for a layer of `H` units.  The tcgen05 cluster kernels exist
-    for 256 and 512 units (csrc/blstm_cl_tc.cu, blstm_cl_bwd8.cu); with NABU_PAD_UNITS=1 a narrower layer -- every
-    shipped recipe uses num_units = 128 -- is zero-padded up to the next of those instead of taking the FFMA kernels
-    (exact, see _BLSTMPadded).  Otherwise: the next multiple of the 64-unit tile."""
+    for 256 and 512 units (csrc/blstm_cl_tc.cu, blstm_cl_bwd8.cu); a narrower layer -- every recipe the reference ships
+    uses num_units = 128 -- is zero-padded up to the next of those (exact, see _BLSTMPadded) when the batch is large
+    enough for that to win: measured on a B200 at num_units = 128, T = 800 (tools/h128_probe.py, profiles/r2_h128_probe.txt)
+    the padded tcgen05 path takes 6.6 / 10.7 us per time step forward / backward against 8.9 / 12.1 on the FFMA cluster
+    kernels at B = 128, but 5.7 / 7.4 against 5.6 / 5.8 at B = 16.  NABU_PAD_UNITS=0 / 1 forces it off / on.
+    Otherwise: the next multiple of the 64-unit tile."""
     import os
     Hp = (H + REC_UNIT - 1) // REC_UNIT * REC_UNIT
-    if os.environ.get('NABU_PAD_UNITS', '0') == '1' and (B is None or B <= 128):
-        for w in (256, 512):
-            if H <= w:
-                return w
+    mode = os.environ.get('NABU_PAD_UNITS', 'auto')
+    if mode != '0' and (B is None or B <= 128) and H < 512 and H not in (256,):
+        if mode == '1' or (B is not None and B > 32):
+            return 256 if H <= 256 else 512
     return Hp
 
 
-def blstm(x, lens, vf_k, vf_b, vb_k, vb_b, H, yT=None):
-    """x [B,T,D] -> y [B,yT,2H]; v*_ are engine.Variable."""
+def blstm(x, lens, vf_k, vf_b, vb_k, vb_b, H, yT=None, x_planes=None, want_planes=False):
+    """x [B,T,D] -> y [B,yT,2H]; v*_ are engine.Variable.  `x_planes`: the operand planes of x when x IS the unchanged
+    output of another blstm (or its pyramid_stack reshape); `want_planes`: also return y's planes (or None)."""
     yT = x.shape[1] if yT is None else yT
-    fn = _BLSTM if rec_width(H, x.shape[0]) == H else _BLSTMPadded
-    return fn.apply(x, lens, vf_k.data, vf_b.data, vb_k.data, vb_b.data, H, yT,
-                    (vf_k.grad, vf_b.grad, vb_k.grad, vb_b.grad))
+    gv = (vf_k.grad, vf_b.grad, vb_k.grad, vb_b.grad)
+    if rec_width(H, x.shape[0]) == H:
+        y, planes = _BLSTM.apply(x, lens, vf_k.data, vf_b.data, vb_k.data, vb_b.data, H, yT, gv, x_planes)
+        planes = planes if planes.numel() else None
+    else:
+        y, planes = _BLSTMPadded.apply(x, lens, vf_k.data, vf_b.data, vb_k.data, vb_b.data, H, yT, gv), None
+    return (y, planes) if want_planes else y
 
 
 def pyramid_lengths(lens, numsteps):

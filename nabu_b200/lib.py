@@ -48,6 +48,10 @@ SIGNATURES = {
     'nabu_blstm_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, c_size_t, P]),
     'nabu_blstm_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_size_t,
                                P]),
+    'nabu_blstm_planes_bytes': (c_size_t, [c_int] * 3),
+    'nabu_blstm_fwd_planes': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, P, P, c_size_t, P]),
+    'nabu_blstm_bwd_planes': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P,
+                                      c_size_t, P]),
     'nabu_pyramid_lengths': (c_int, [P, c_int, c_int, P, P]),
     'nabu_linear_fwd': (c_int, [P, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     'nabu_linear_bwd': (c_int, [P, c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),

@@ -24,11 +24,13 @@ class DBLSTM(ed_encoder.EDEncoder):
             h = inputs[inp]
             if is_training and noise > 0:
                 h = h + torch.randn_like(h) * noise
+            planes = None       # tensor-core operand planes of h, valid while h is a BLSTM output nobody touched
             for l in range(int(self.conf['num_layers'])):
-                h = layer.blstm(self.store, h, input_seq_length[inp], int(self.conf['num_units']),
-                                '%s/%s/layer%d' % (self.scope, inp, l))
+                h, planes = layer.blstm(self.store, h, input_seq_length[inp], int(self.conf['num_units']),
+                                        '%s/%s/layer%d' % (self.scope, inp, l), planes=planes, want_planes=True)
                 if is_training and keep < 1:
                     h = torch.nn.functional.dropout(h, 1 - keep, True)
+                    planes = None
             encoded[inp] = h
             encoded_seq_length[inp] = input_seq_length[inp]
         return encoded, encoded_seq_length

@@ -28,11 +28,14 @@ class Listener(ed_encoder.EDEncoder):
             lens = input_seq_length[inp]
             if is_training and noise > 0:
                 h = h + torch.randn_like(h) * noise
+            planes = None       # tensor-core operand planes of h, valid while h is a (stacked) BLSTM output nobody touched
             for l in range(n):
-                h, lens = layer.pblstm(self.store, h, lens, H, steps, '%s/%s/layer%d' % (self.scope, inp, l))
+                h, lens, planes = layer.pblstm(self.store, h, lens, H, steps, '%s/%s/layer%d' % (self.scope, inp, l),
+                                               planes=planes, want_planes=True)
                 if is_training and keep < 1:
                     h = torch.nn.functional.dropout(h, 1 - keep, True)
-            h = layer.blstm(self.store, h, lens, H, '%s/%s/layer%d' % (self.scope, inp, n))
+                    planes = None
+            h = layer.blstm(self.store, h, lens, H, '%s/%s/layer%d' % (self.scope, inp, n), planes=planes)
             if is_training and keep < 1:
                 h = torch.nn.functional.dropout(h, 1 - keep, True)
             encoded[inp] = h

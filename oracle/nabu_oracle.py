@@ -20,7 +20,7 @@ __all__ = [
     'dblstm_bwd', 'listener_fwd', 'listener_bwd', 'linear_fwd', 'linear_bwd',
     'log_softmax', 'ctc_loss_and_grad', 'ctc_brute_force', 'ctc_loss_mean',
     'average_cross_entropy', 'speller_fwd', 'speller_bwd', 'speller_step',
-    'speller_zero_state', 'attention_keys', 'attention_window', 'rng_u32',
+    'speller_zero_state', 'attention_keys', 'attention_step', 'attention_window', 'rng_u32',
     'rng_uniform', 'speller_dropout_mask', 'speller_sample_ids', 'tf_adam_clip',
     'exponential_decay', 'ctc_beam_search', 'las_beam_search',
     'edit_distance', 'init_blstm_params', 'init_speller_params',

@@ -107,9 +107,10 @@ def test_attention_entry_points(attention, B, Tm, E, H, numfilt, fs):
     dprev = torch.empty((B, Tm), device=dev)
     dkeys = torch.zeros((B, Tm, H), device=dev)
     dvalues = torch.zeros((B, Tm, E), device=dev)
+    d_dalpha, d_dctx = t(dalpha), t(dctx)          # held: a temporary's memory would be recycled by the next allocation
     L.check(lib.nabu_attn_step_bwd(ctypes.byref(desc), ctypes.byref(pk), L.ptr(d_q), B, L.ptr(d_keys), L.ptr(d_values),
                                    L.ptr(d_len), L.ptr(d_prev), L.ptr(d_alpha), L.ptr(q_save), L.ptr(cf_save), None,
-                                   L.ptr(t(dalpha)), L.ptr(t(dctx)), L.ptr(dq), L.ptr(dprev), L.ptr(dkeys), L.ptr(dvalues),
+                                   L.ptr(d_dalpha), L.ptr(d_dctx), L.ptr(dq), L.ptr(dprev), L.ptr(dkeys), L.ptr(dvalues),
                                    ctypes.byref(gk), L.ptr(ws), nws, L.stream()), 'nabu_attn_step_bwd')
     torch.cuda.synchronize()
     assert rel_err(dq.cpu().numpy(), tq.grad.numpy()) < TOL

@@ -272,3 +272,92 @@ def test_gemm_split_fp16_splitk_tn():
     B = rng.standard_normal((R, N)).astype(np.float32) * 1e3
     c = engine.gemm(2, dev(A), dev(B), M, N, R, M, N, N, precision=2)
     assert rel_err(c.cpu().numpy(), A.astype(np.float64).T @ B.astype(np.float64)) < 2e-5
+
+
+@pytest.mark.parametrize('B,T,H,pyramid', [
+    (128, 40, 512, False),    # cfg-3 width: tcgen05 recurrences write the planes themselves
+    (64, 37, 256, True),      # cfg-2 width, odd T: yT = T + 1, the stacked output and its planes feed the next layer
+    (6, 9, 64, False),        # FFMA kernels: planes from the fixed-scale split pass
+])
+def test_blstm_operand_planes_travel_between_layers(B, T, H, pyramid):
+    """nabu_blstm_fwd_planes / nabu_blstm_bwd_planes (include/nabu_b200.h): layer 1 writes the fp16 hi/lo operand planes
+    of its output, layer 2 consumes them as x_planes (forward: input projection; backward: dKx), both layers hand dZ to
+    their GEMMs as planes.  Results against the fp64 oracle of the two-layer stack."""
+    from nabu_b200 import lib as L
+    lib = L.load()
+    rng = np.random.default_rng(B + T)
+    D = 40
+    x = rng.standard_normal((B, T, D)).astype(np.float32)
+    lens = rng.integers(max(1, T // 2), T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    steps = 2 if pyramid else 1
+    p1 = O.init_blstm_params(rng, D, H)
+    p2 = O.init_blstm_params(rng, 2 * H * steps, H)
+    # oracle
+    y1_ref, c1 = O.blstm_fwd(x, lens, p1)
+    if pyramid:
+        x2_ref, lens2 = O.pyramid_stack_fwd(y1_ref, lens, 2)
+    else:
+        x2_ref, lens2 = y1_ref, lens
+    y2_ref, c2 = O.blstm_fwd(x2_ref, lens2, p2)
+    dy2 = rng.standard_normal(y2_ref.shape).astype(np.float32)
+    for b in range(B):
+        dy2[b, lens2[b]:] = 0
+    dx2_ref, g2_ref = O.blstm_bwd(c2, dy2.astype(np.float64))
+    dy1_ref = O.pyramid_stack_bwd(dx2_ref, T, 2) if pyramid else dx2_ref
+    dx1_ref, g1_ref = O.blstm_bwd(c1, dy1_ref)
+
+    def layer_fwd(xd, ld, p, Tl, Dl, yT, x_planes):
+        pd = {k: dev(v) for k, v in p.items()}
+        y = torch.full((B, yT, 2 * H), 7.0, device='cuda')
+        gates = torch.empty((2, B, Tl, 4 * H), device='cuda')
+        cells = torch.empty((2, B, Tl, H), device='cuda')
+        planes = torch.full((lib.nabu_blstm_planes_bytes(B, yT, H),), 0x55, dtype=torch.uint8, device='cuda')
+        nws = lib.nabu_blstm_workspace_bytes(B, Tl, Dl, H)
+        ws = torch.empty(nws, dtype=torch.uint8, device='cuda')
+        L.check(lib.nabu_blstm_fwd_planes(L.ptr(xd), L.ptr(x_planes), L.ptr(ld), B, Tl, Dl, H, L.ptr(pd['fw_kernel']),
+                                          L.ptr(pd['fw_bias']), L.ptr(pd['bw_kernel']), L.ptr(pd['bw_bias']), L.ptr(y),
+                                          L.ptr(planes), yT, L.ptr(gates), L.ptr(cells), L.ptr(ws), nws, L.stream()), 'fwd')
+        return dict(pd=pd, y=y, gates=gates, cells=cells, planes=planes, ws=ws, nws=nws, x=xd, len=ld, x_planes=x_planes,
+                    T=Tl, D=Dl, yT=yT)
+
+    def layer_bwd(st, dyd, need_dx):
+        pd = st['pd']
+        dx = torch.empty_like(st['x']) if need_dx else None
+        gk = {k: torch.full_like(v, 3.0) for k, v in pd.items()}
+        L.check(lib.nabu_blstm_bwd_planes(L.ptr(st['x']), L.ptr(st['x_planes']), L.ptr(st['len']), B, st['T'], st['D'], H,
+                                          L.ptr(pd['fw_kernel']), L.ptr(pd['bw_kernel']), L.ptr(st['y']), L.ptr(st['planes']),
+                                          st['yT'], L.ptr(st['gates']), L.ptr(st['cells']), L.ptr(dyd), L.ptr(dx),
+                                          L.ptr(gk['fw_kernel']), L.ptr(gk['fw_bias']), L.ptr(gk['bw_kernel']),
+                                          L.ptr(gk['bw_bias']), L.ptr(st['ws']), st['nws'], L.stream()), 'bwd')
+        return dx, gk
+
+    yT1 = (T + steps - 1) // steps * steps
+    s1 = layer_fwd(dev(x), dev(lens), p1, T, D, yT1, None)
+    # the planes hold y * 32 as hi + lo / 2048 (fp16), zero rows past the lengths and in the padding
+    half = s1['planes'].numel() // 2
+    hi = s1['planes'][:half].view(torch.float16)[:B * yT1 * 2 * H].float().view(B, yT1, 2 * H)
+    lo = s1['planes'][half:].view(torch.float16)[:B * yT1 * 2 * H].float().view(B, yT1, 2 * H)
+    rebuilt = ((hi.double() + lo.double() / 2048) / 32).cpu().numpy()
+    assert np.abs(rebuilt - s1['y'].double().cpu().numpy()).max() < 2e-7
+    assert np.all(rebuilt[:, T:] == 0) and np.all(rebuilt[1, lens[1]:] == 0)
+    if pyramid:
+        x2 = s1['y'].view(B, yT1 // 2, 4 * H)
+        l2 = dev(lens2.astype(np.int32))
+    else:
+        x2, l2 = s1['y'], dev(lens)
+    T2, D2 = x2.shape[1], x2.shape[2]
+    s2 = layer_fwd(x2, l2, p2, T2, D2, T2, s1['planes'])
+    assert rel_err(s2['y'].cpu().numpy(), y2_ref) < TOL
+    dx2, g2 = layer_bwd(s2, dev(dy2), True)
+    assert rel_err(dx2.cpu().numpy(), dx2_ref) < TOL
+    for k in g2_ref:
+        assert rel_err(g2[k].cpu().numpy(), g2_ref[k]) < TOL, ('layer 2', k)
+    dy1 = dx2.view(B, yT1, 2 * H)
+    dx1, g1 = layer_bwd(s1, dy1, True)
+    torch.cuda.synchronize()
+    assert rel_err(dx1.cpu().numpy(), dx1_ref) < TOL
+    for k in g1_ref:
+        assert rel_err(g1[k].cpu().numpy(), g1_ref[k]) < TOL, ('layer 1', k)
