@@ -494,13 +494,38 @@ blstm_rec_bwd_kernel(const RecParams p) {
   }
 }
 
-__global__ void sum_groups_kernel(const float* part, int ngrp, int n, float* out0, float* out1) {
+__global__ void sum_groups_kernel(const float* part, int ngrp, int n, float* out0, float* out1, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * n) return;
   const int dir = i / n, k = i % n;
-  float s = 0.f;
+  float* out = dir ? out1 : out0;
+  float s = accumulate ? out[k] : 0.f;
   for (int g = 0; g < ngrp; ++g) s += part[((size_t)dir * 8 + g) * n + k];
-  (dir ? out1 : out0)[k] = s;
+  out[k] = s;
+}
+// word 0 = max over the batch of the rows' max |dy|, words 1..127 = 0 (see blstm_rec_bwd_chain: rowmax_ready)
+__global__ void batch_max_kernel(const unsigned* rowmax, int B, unsigned* out) {
+  __shared__ unsigned m;
+  if (threadIdx.x == 0) m = 0u;
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float G = __uint_as_float(rowmax[i]);
+    if (G > 0.f && G < 3.0e38f) atomicMax(&m, rowmax[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) out[threadIdx.x] = threadIdx.x == 0 ? m : 0u;
+}
+__global__ void rows_absmax_kernel(const float* __restrict__ dy, const int* __restrict__ len, int yT, int W, unsigned* rowmax) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)len[b] * W;
+  const float* src = dy + (size_t)b * yT * W;
+  float m = 0.f;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i + 3 < n; i += (size_t)gridDim.x * blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(rowmax + b, __float_as_uint(m));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -622,6 +647,7 @@ int run_recurrence(bool backward, RecParams rp, int B, int H, cudaStream_t strea
 // [gemm scratch][fp16 split planes P1 (layer input / output side), P2, P3 (gate side), weights, scales]
 constexpr int YT_SLACK = 16;    // yT - T the split planes are sized for (pyramid padding)
 struct Ws {
+  unsigned* rowmax_all; unsigned* rowmax_tile;     // B > 128: every row's max |dy|, and the 128-word image handed to the tiles
   unsigned* counters; unsigned* rowmax; float* xchg; float* dcbuf; float* dbpart; float* gemm; size_t gemm_bytes;
   void *p1h, *p1l, *p2h, *p2l, *p3h, *p3l, *wh[2], *wl[2];
   float *row1, *row2, *glob;      // row scales of P1 / P2|P3 rows; 16 global scalars (inverse scales + max bits)
@@ -634,6 +660,7 @@ Ws carve(void* base, int H, int B, int T, int D) {
   char* b = (char*)base;
   auto take = [&](size_t bytes) { void* p = b + off; off += align_up(bytes, 256); return p; };
   w.counters = (unsigned*)take(1024); w.rowmax = w.counters + 64;
+  w.rowmax_all = (unsigned*)take((size_t)Bp * 4); w.rowmax_tile = (unsigned*)take(512);
   {
     size_t xf = (size_t)2 * 2 * 4 * H * Bp;
     if (xf < (size_t)4 * 128 * H) xf = (size_t)4 * 128 * H;      // the tcgen05 path exchanges [2][2][128][H]
@@ -896,12 +923,35 @@ extern "C" int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const
     if (int e = blstm_rec_fwd_cluster_tc(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched, yh, yl))
       return e;
     if (launched) return 0;
+  } else if (B > 128 && blstm_fwd_cluster_tc_eligible(128, H)) {
+    // more than 128 rows: the tcgen05 recurrence tile by tile (128 rows each, one after the other)
+    bool any = false;
+    for (int b0 = 0; b0 < B; b0 += 128) {
+      const int Bt = std::min(128, B - b0);
+      if (b0 > 0) {
+        NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
+        NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * 128 * sizeof(float), stream));
+      }
+      float* gt[2] = {g[0] + (size_t)b0 * T * H4, g[1] + (size_t)b0 * T * H4};
+      float* ct[2] = {c[0] + (size_t)b0 * T * H, c[1] + (size_t)b0 * T * H};
+      bool launched = false;
+      if (int e = blstm_rec_fwd_cluster_tc(kern, gt, ct, y + (size_t)b0 * yT * 2 * H, w.xchg, w.counters, len + b0, Bt, T, yT, D, H,
+                                           stream, &launched, yh ? (char*)yh + (size_t)b0 * yT * 2 * H * 2 : nullptr,
+                                           yl ? (char*)yl + (size_t)b0 * yT * 2 * H * 2 : nullptr))
+        return e;
+      if (!launched) {
+        NABU_REQUIRE(b0 == 0, "blstm_fwd: the tcgen05 recurrence stopped being launchable between batch tiles");
+        break;
+      }
+      any = true;
+    }
+    if (any) return 0;
   }
   {
     char key[96];
     snprintf(key, sizeof(key), "fwd B=%d H=%d", B, H);
-    warn_once(key, "blstm forward recurrence B=%d num_units=%d is not on the tcgen05 cluster kernel (eligible: B <= 128 per launch, "
-              "num_units in {128, 256, 512}); falling back to the FFMA kernels", B, H);
+    warn_once(key, "blstm forward recurrence B=%d num_units=%d is not on the tcgen05 cluster kernels (they exist for num_units 256 "
+              "and 512; the Python engine pads narrower layers up to them): falling back to the FFMA kernels", B, H);
   }
   if (blstm_fwd_cluster_eligible(B, H)) {
     bool launched = false;
@@ -956,12 +1006,16 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
   // weight-gradient GEMMs of THIS layer run on a side stream while the caller goes on to the next layer's recurrence,
   // which is issued on a high-priority stream so that its clusters take SMs as the GEMM's CTAs retire.
   Overlap& ov = overlap();
-  const bool defer = ov.on && blstm_bwd_cluster8_eligible(B, H) && use_h2(B, T, D, H, yT);
+  // a batch of more than 128 rows runs the tcgen05 recurrence tile by tile (128 rows each, one after the other: two
+  // tiles' clusters are not co-resident)
+  const int ntile = ceil_div(B, 128);
+  const bool tc_ok = blstm_bwd_cluster8_eligible(std::min(B, 128), H) && (ntile == 1 || blstm_bwd_chain_eligible(128, H));
+  const bool defer = ov.on && tc_ok && use_h2(B, T, D, H, yT);
   // dZ as operand planes straight from the recurrence (NABU_ZPLANES=0 keeps the fp32 dZ + split passes): the planes live
   // in library-owned scratch, two sets used alternately (see SideZ)
   static int zplanes_on = -1;
   if (zplanes_on < 0) zplanes_on = (getenv("NABU_ZPLANES") && atoi(getenv("NABU_ZPLANES")) == 0) ? 0 : 1;
-  const bool zplanes = zplanes_on && blstm_bwd_cluster8_eligible(B, H) && use_h2(B, T, D, H, yT) &&
+  const bool zplanes = zplanes_on && tc_ok && use_h2(B, T, D, H, yT) &&
                        gemm_h2_eligible(GEMM_NT, B * T, D, 2 * H4) && inv_y_scale_ptr() != nullptr;
   SideZ sz = {};
   int zk = 0;
@@ -990,7 +1044,7 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
     if (zs.recorded[zk]) NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, zs.done[zk], 0));
     if (zs.dx_recorded[zk]) NABU_CHECK_CUDA(cudaStreamWaitEvent(stream, zs.dx_done[zk], 0));
   }
-  if (blstm_bwd_cluster8_eligible(B, H)) {
+  if (tc_ok) {
     const float* cc[2] = {c[0], c[1]};
     NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, stream));
     NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H4 * 128 * sizeof(float), stream));
@@ -1020,9 +1074,54 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
       }
     }
     ov.in_defer = defer;
-    const int re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched,
-                                          zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr,
-                                          zplanes ? sz.zglob[zk] : nullptr);
+    int re = 0;
+    if (ntile == 1) {
+      if (blstm_bwd_chain_eligible(B, H))
+        re = blstm_rec_bwd_chain(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched, &ngrp,
+                                 zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr, zplanes ? sz.zglob[zk] : nullptr);
+      if (!re && !launched) {
+        ngrp = 1;
+        re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched,
+                                    zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr,
+                                    zplanes ? sz.zglob[zk] : nullptr);
+      }
+    } else {
+      // one scale for the whole batch: every row's max |dy| first, then its maximum in word 0 of the tiles' 128-word image
+      NABU_CHECK_CUDA(cudaMemsetAsync(w.rowmax_all, 0, (size_t)B * 4, rs));
+      {
+        KernelScope ks("row_absmax", rs);
+        rows_absmax_kernel<<<dim3(32, B), 256, 0, rs>>>(dy, len, yT, 2 * H, w.rowmax_all);
+        NABU_CHECK_LAUNCH();
+        batch_max_kernel<<<1, 256, 0, rs>>>(w.rowmax_all, B, w.rowmax_tile);
+        NABU_CHECK_LAUNCH();
+      }
+      for (int tb = 0; tb < ntile && !re; ++tb) {
+        const int b0 = tb * 128, Bt = std::min(128, B - b0);
+        if (tb > 0) {
+          NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, rs));
+          NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H4 * 128 * sizeof(float), rs));
+        }
+        float* gt[2] = {g[0] + (size_t)b0 * T * H4, g[1] + (size_t)b0 * T * H4};
+        const float* ct[2] = {c[0] + (size_t)b0 * T * H, c[1] + (size_t)b0 * T * H};
+        bool l1 = false;
+        int slots = 1;
+        re = blstm_rec_bwd_chain(kern, gt, ct, dy + (size_t)b0 * yT * 2 * H, w.dbpart, w.xchg, w.rowmax_tile, len + b0, Bt, T, yT,
+                                 D, H, rs, &l1, &slots,
+                                 zplanes ? (char*)sz.zh[zk] + (size_t)b0 * T * 2 * H4 * 2 : nullptr,
+                                 zplanes ? (char*)sz.zl[zk] + (size_t)b0 * T * 2 * H4 * 2 : nullptr,
+                                 zplanes ? sz.zglob[zk] : nullptr, true);
+        if (re) break;
+        if (!l1) {
+          NABU_REQUIRE(tb == 0, "blstm_bwd: the tcgen05 recurrence stopped being launchable between batch tiles");
+          break;
+        }
+        launched = true;
+        KernelScope ks("sum_groups", rs);
+        sum_groups_kernel<<<ceil_div(2 * H4, 256), 256, 0, rs>>>(w.dbpart, slots, H4, dbias_fw, dbias_bw, tb > 0);
+        NABU_CHECK_LAUNCH();
+      }
+      ngrp = launched ? 0 : 1;                         // tiles done: the bias gradients are complete
+    }
     ov.in_defer = false;
     if (re) return re;
     if (defer) {
@@ -1033,8 +1132,8 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
   if (!launched) {
     char key[96];
     snprintf(key, sizeof(key), "bwd B=%d H=%d", B, H);
-    warn_once(key, "blstm backward recurrence B=%d num_units=%d is not on the TMEM-resident tcgen05 kernel (eligible: B <= 128 per "
-              "launch, num_units in {128, 256, 512}); falling back", B, H);
+    warn_once(key, "blstm backward recurrence B=%d num_units=%d is not on the TMEM-resident tcgen05 kernels (they exist for "
+              "num_units 256 and 512; the Python engine pads narrower layers up to them): falling back", B, H);
   }
   if (!launched && blstm_bwd_cluster_tc_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};
@@ -1052,9 +1151,9 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
   }
   if (!launched)
     if (int e = run_recurrence(true, rp, B, H, stream, &ngrp)) return e;
-  {
+  if (ngrp > 0 || !launched) {
     KernelScope ks("sum_groups", stream);
-    sum_groups_kernel<<<ceil_div(2 * H4, 256), 256, 0, stream>>>(w.dbpart, ngrp, H4, dbias_fw, dbias_bw);
+    sum_groups_kernel<<<ceil_div(2 * H4, 256), 256, 0, stream>>>(w.dbpart, std::max(ngrp, 1), H4, dbias_fw, dbias_bw, 0);
     NABU_CHECK_LAUNCH();
   }
   if (zplanes && launched) {

@@ -48,4 +48,16 @@ int blstm_rec_bwd_cluster8(const float* const kernel[2], float* const gates[2], 
                            int D, int H, cudaStream_t stream, bool* launched, void* zh = nullptr, void* zl = nullptr,
                            float* zinv = nullptr);
 
+// "Chains" version of the cluster-of-8 backward (blstm_cl_bwd8c.cu): the batch tile is cut into independent chains of 16 /
+// 32 / 64 rows, each run by its own warpgroup (two chains of 64 for B > 64, one chain sized to the batch below that).
+// Same arguments as blstm_rec_bwd_cluster8; *nslots = the number of bias-gradient partial slots written (dbpart[dir][slot]).
+// NABU_REC_BWD=cl8 keeps the single-chain kernel.
+bool blstm_bwd_chain_eligible(int B, int H);
+int blstm_rec_bwd_chain(const float* const kernel[2], float* const gates[2], const float* const cells[2], const float* dy,
+                        float* dbpart, float* xchg, unsigned* rowmax, const int* len, int B, int T, int yT, int D, int H,
+                        cudaStream_t stream, bool* launched, int* nslots, void* zh = nullptr, void* zl = nullptr,
+                        float* zinv = nullptr, bool rowmax_ready = false);
+// rowmax_ready: `rowmax` already holds the rows' max |dy| (a batch cut into tiles of 128 rows passes ONE word, the maximum
+// of the whole batch, so that every tile scales its gradients alike).
+
 }  // namespace nabu

@@ -99,6 +99,10 @@ def _blstm_case(B, T, D, H, ragged, seed, yT=None, need_dx=True):
     (4, 1, 8, 64, False),        # T=1
     (128, 48, 40, 512, True),    # cfg-3 width and batch: every row of the tcgen05 cluster kernels, flag parity wraps 12 times
     (77, 33, 24, 256, True),     # H=256 variants (clusters of 4 forward, 2 clusters of 8 per direction backward), odd batch
+    (200, 21, 40, 512, True),    # more than 128 rows at cfg-3 width: two batch tiles of the tcgen05 recurrences (128 + 72)
+    (260, 9, 24, 256, True),     # three tiles (128 + 128 + 4)
+    (48, 30, 40, 512, True),     # chains of the backward recurrence: 2 x 32 rows
+    (9, 17, 40, 256, True),      # one chain of 16 rows
 ])
 def test_blstm_fwd_bwd(B, T, D, H, ragged):
     _blstm_case(B, T, D, H, ragged, seed=B * 1000 + T)
