@@ -918,6 +918,11 @@ extern "C" int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const
     return planes_after();
   }
   NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * (ceil_div(B, 128) * 128) * sizeof(float), stream));
+  if (blstm_fwd_chain_eligible(B, H)) {
+    bool launched = false;
+    if (int e = blstm_rec_fwd_chain(kern, g, c, y, w.xchg, len, B, T, yT, D, H, stream, &launched, yh, yl)) return e;
+    if (launched) return 0;
+  }
   if (blstm_fwd_cluster_tc_eligible(B, H)) {
     bool launched = false;
     if (int e = blstm_rec_fwd_cluster_tc(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched, yh, yl))
