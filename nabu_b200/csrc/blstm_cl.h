@@ -61,8 +61,8 @@ int blstm_rec_bwd_chain(const float* const kernel[2], float* const gates[2], con
 // of the whole batch, so that every tile scales its gradients alike).
 
 // Small-batch forward (blstm_cl_fwdc.cu): transposed product with the weights in TMEM and the batch as the MMA's N, one or
-// two chains of 16 / 32 rows: B <= 64 (NABU_FWD_CHAIN_MAXB), num_units in {256, 512}; NABU_REC_FWD=cl4 keeps the 128-row
-// kernel for every batch.
+// one, two or four chains of 16 / 32 rows: B <= 128 (NABU_FWD_CHAIN_MAXB lowers that), num_units in {256, 512};
+// NABU_REC_FWD=cl4 keeps the 128-row kernel (blstm_cl_tc.cu).
 bool blstm_fwd_chain_eligible(int B, int H);
 int blstm_rec_fwd_chain(const float* const kernel[2], float* const gates[2], float* const cells[2], float* y, float* xchg,
                         const int* len, int B, int T, int yT, int D, int H, cudaStream_t stream, bool* launched,

@@ -360,7 +360,7 @@ int launch_fwd_chain(const ClParams& p, cudaStream_t stream, bool* launched) {
     cudaGetLastError();
     return 0;
   }
-  KernelScope ks(NCH == 2 ? "blstm_rec_fwd_chain2" : "blstm_rec_fwd_chain1", stream);
+  KernelScope ks(NCH == 4 ? "blstm_rec_fwd_chain4" : NCH == 2 ? "blstm_rec_fwd_chain2" : "blstm_rec_fwd_chain1", stream);
   ClParams pt = p;
   pt.trace = trace_buffer();
   NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, pt));
@@ -379,9 +379,11 @@ int dispatch_fwd_chain(const ClParams& p, cudaStream_t stream, bool* launched) {
   }
   // measured (tools/smallb_probe.py, one cfg-3 layer, T = 600): B = 16: 2.9 ms as 16x1 (4.7 ms on the 128-row kernel),
   // B = 32: 3.5 ms as 32x1 (3.7 as 16x2, 4.9), B = 64: 4.5 ms as 32x2 (5.6); at B = 128 two chains of 64 lose (7.2 vs 6.9)
+  // and four chains of 32 beat the 128-row kernel at B = 128 as well (7.9 against 8.5 us per time step in the cfg-3 step)
   int nb = p.B <= 16 ? 16 : 32;
-  int nch = p.B <= 32 ? 1 : 2;
+  int nch = p.B <= 32 ? 1 : p.B <= 64 ? 2 : 4;
   if (force && fnb * fnch >= p.B) { nb = fnb; nch = fnch; }
+  if (nb == 32 && nch == 4) return launch_fwd_chain<KB, 32, 4>(p, stream, launched);
   if (nb == 16 && nch == 1) return launch_fwd_chain<KB, 16, 1>(p, stream, launched);
   if (nb == 16 && nch == 2) return launch_fwd_chain<KB, 16, 2>(p, stream, launched);
   if (nb == 32 && nch == 1) return launch_fwd_chain<KB, 32, 1>(p, stream, launched);
@@ -393,7 +395,7 @@ int dispatch_fwd_chain(const ClParams& p, cudaStream_t stream, bool* launched) {
 }  // namespace
 
 bool blstm_fwd_chain_eligible(int B, int H) {
-  static int enabled = -1, maxb = 64;
+  static int enabled = -1, maxb = 128;
   if (enabled < 0) {
     const char* e = getenv("NABU_REC_FWD");
     enabled = (e && (strcmp(e, "flat") == 0 || strcmp(e, "ffma") == 0 || strcmp(e, "cl4") == 0)) ? 0 : 1;
