@@ -31,7 +31,7 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, log=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
     headers.append(os.path.join(ROOT, 'include', 'nabu_b200.h'))
@@ -55,8 +55,19 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
+    link = None
     if jobs or force or _stale(LIB, objs):
-        run([NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcudart_static', '-lpthread', '-ldl', '-lrt'])
+        link = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcudart_static', '-lpthread', '-ldl', '-lrt']
+        run(link)
+    if log:
+        import hashlib
+        import time
+        with open(os.path.join(OBJ, 'build.log'), 'w') as fid:
+            fid.write('# %s: %d translation units compiled, library %s\n' % (time.strftime('%Y-%m-%d %H:%M:%S'), len(jobs),
+                                                                              'linked' if link else 'up to date'))
+            for cmd in jobs + ([link] if link else []):
+                fid.write(' '.join(cmd) + '\n')
+            fid.write('sha256 %s  %s\n' % (hashlib.sha256(open(LIB, 'rb').read()).hexdigest(), os.path.relpath(LIB, ROOT)))
     return LIB
 
 

@@ -280,10 +280,10 @@ def read_checkpoint(prefix, names=None, check_crc=True):
     return out
 
 
-def write_checkpoint(prefix, arrays, shard_of=None, num_shards=1, producer=26):
+def write_checkpoint(prefix, arrays, shard_of=None, num_shards=1, producer=1):
     """Write {name: ndarray} as a V2 bundle.  `shard_of(name) -> shard id` spreads the variables over `num_shards`
     data files the way a sharded Saver spreads them over parameter-server devices (default: one shard).  `producer`
-    26 = TF_GRAPH_DEF_VERSION of TF 1.8."""
+    1 = kTensorBundleVersion, what TF's BundleWriter puts in the header's VersionDef (tensor_bundle.cc; min_consumer 0)."""
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
     files = [open(_shard_name(prefix, s, num_shards), 'wb') for s in range(num_shards)]
     offsets = [0] * num_shards

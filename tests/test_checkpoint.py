@@ -39,8 +39,8 @@ def test_reader_on_a_hand_assembled_bundle(tmp_path):
     w = np.arange(6, dtype='<f4').reshape(2, 3)
     step = np.array(5, dtype='<i8')
     data = step.tobytes() + w.tobytes()                      # BundleWriter lays the tensors out in key order
-    # BundleHeaderProto{num_shards=1, version{producer=26}}; BundleEntryProto per tensor
-    header = bytes([0x08, 1, 0x1a, 2, 0x08, 26])
+    # BundleHeaderProto{num_shards=1, version{producer=1 = kTensorBundleVersion}}; BundleEntryProto per tensor
+    header = bytes([0x08, 1, 0x1a, 2, 0x08, 1])
     e_w = bytes([0x08, 1, 0x12, 8, 0x12, 2, 0x08, 2, 0x12, 2, 0x08, 3, 0x20, 8, 0x28, 24, 0x35]) + \
         struct.pack('<I', C._mask(R.crc32c_py(w.tobytes())))
     e_s = bytes([0x08, 9, 0x12, 0, 0x28, 8, 0x35]) + struct.pack('<I', C._mask(R.crc32c_py(step.tobytes())))
