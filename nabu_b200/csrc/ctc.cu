@@ -81,6 +81,10 @@ __global__ void ctc_alpha_beta_kernel(const float* logits, const float* lse, con
   __syncthreads();
   int rep = 0;
   for (int i = 1 + threadIdx.x; i < L; i += blockDim.x) rep += (lab[i] == lab[i - 1]);
+  // a label outside [0, blank) (a reader's "none" symbol = -1, or output_dims of the model cfg too small) would index the
+  // logits out of bounds: such an utterance is flagged like an infeasible one (loss = +inf, zero gradient; TF raises)
+  for (int i = threadIdx.x; i < L; i += blockDim.x)
+    if (lab[i] < 0 || lab[i] >= blank) rep += (1 << 20);
   if (rep) atomicAdd(&s_rep, rep);
   __syncthreads();
   const bool feasible = (Tb >= L + s_rep) && Tb > 0;

@@ -73,6 +73,11 @@ __global__ void masked_ce_kernel(const float* logits, const int* targets, int ld
     s = warp_sum(s);
     const float lse = mx + logf(s);
     const int tgt = targets[(size_t)b * ldt + u];
+    if (tgt < 0 || tgt >= V) {       // not a class of this output: +inf loss, zero gradient (TF returns NaN / raises)
+      acc = CUDART_INF_F;
+      if (g) for (int k = lane; k < V; k += 32) g[k] = 0.f;
+      continue;
+    }
     acc += lse - x[tgt];
     if (g) {
       const float sc = grad_scale * inv_len;

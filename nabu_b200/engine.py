@@ -123,7 +123,7 @@ class ParamStore(object):
                 'names': [(v.name, v.shape, v.offset) for v in self.order]}
 
     # ---- TF checkpoint interop: the store's variable names ARE the reference's TF names --
-    def save_tf_checkpoint(self, prefix, with_adam=False, global_step=None, extra=None):
+    def save_tf_checkpoint(self, prefix, with_adam=False, global_step=None, extra=None, state_file=True):
         """Write `<prefix>.index` / `.data-*` as `tf.train.Saver(model.variables, sharded=True).save` would
         (components/hooks.py:32-52 -> model/network.ckpt).  `with_adam` adds the optimizer slots under TF's names
         (`<var>/Adam`, `<var>/Adam_1`), what the reference's validated.ckpt holds besides the variables."""
@@ -139,7 +139,7 @@ class ParamStore(object):
         if global_step is not None:
             arrays['global_step'] = np.array(global_step, np.int32)
         arrays.update(extra or {})                # the trainer's other global variables (learning_rate_fact, ...)
-        tfcheckpoint.write_checkpoint(prefix, arrays)
+        tfcheckpoint.write_checkpoint(prefix, arrays, state_file=state_file)
 
     def load_tf_checkpoint(self, prefix, with_adam=False):
         """Restore every variable from a TF checkpoint (a nabu-trained `model/network.ckpt`, LoadAtBegin

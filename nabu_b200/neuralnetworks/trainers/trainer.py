@@ -161,7 +161,7 @@ class Trainer(object, metaclass=ABCMeta):
         # MonitoredTrainingSession(checkpoint_dir=<expdir>/logdir) (trainer.py:625-633): every global variable is saved
         # there periodically and training picks up from it when the directory already holds a checkpoint
         if self.restore_checkpoint():
-            print('WORKER %d: resuming from step %d (%s)' % (self.task_index, self.global_step, self._checkpoint_path()))
+            print('WORKER %d: resuming from step %d (%s)' % (self.task_index, self.global_step, getattr(self, '_restored_from', self._checkpoint_path())))
         last_save = time.time()
         if self.device.type == 'cuda':
             used_mb = lambda: torch.cuda.max_memory_allocated() / 1e6
@@ -224,12 +224,15 @@ class Trainer(object, metaclass=ABCMeta):
         return os.path.join(self.expdir, 'logdir', 'model.ckpt') if self.expdir else None
 
     def save_checkpoint(self):
-        """chief only; written under a temporary prefix and renamed, index last, so that a run killed while saving
-        leaves the previous checkpoint intact"""
+        """chief only.  Crash-safe the way tf.train.Saver is: the bundle goes to a NEW step-suffixed prefix
+        (`model.ckpt-<step>`), the `checkpoint` state file is switched to it last and atomically, the previous prefix is
+        deleted afterwards -- a run killed at any point leaves a state file that names a complete checkpoint."""
         path = self._checkpoint_path()
         if path is None or self.task_index != 0:
             return
+        import glob
         import numpy as np
+        from ...processing import tfcheckpoint
         extra = {'learning_rate_fact': np.array(self.learning_rate_fact, np.float32),
                  'should_terminate': np.array(bool(self.should_terminate))}          # trainer.py:97-104
         controller = getattr(self, '_controller', None)
@@ -237,21 +240,26 @@ class Trainer(object, metaclass=ABCMeta):
             extra['validated_step'] = np.array(controller.validated_step, np.int64)
             extra['best_validation'] = np.array(controller.best_validation, np.float64)
             extra['num_tries'] = np.array(controller.num_tries, np.int64)
-        tmp = path + '.tmp'
-        self.model.store.save_tf_checkpoint(tmp, with_adam=True, global_step=self.global_step, extra=extra)
-        for suffix in ('.data-00000-of-00001', '.index'):
-            os.replace(tmp + suffix, path + suffix)
-        with open(os.path.join(os.path.dirname(path), 'checkpoint'), 'w') as fid:
-            fid.write('model_checkpoint_path: "model.ckpt"\nall_model_checkpoint_paths: "model.ckpt"\n')
+        prefix = '%s-%d' % (path, self.global_step)
+        self.model.store.save_tf_checkpoint(prefix, with_adam=True, global_step=self.global_step, extra=extra,
+                                            state_file=False)
+        tfcheckpoint.write_state_file(prefix)
+        for old in glob.glob(path + '-*') + glob.glob(path + '.*'):
+            if not old.startswith(prefix + '.'):
+                os.remove(old)
 
     def restore_checkpoint(self):
         """every rank; returns whether a checkpoint was found.  Like the reference's session restore it brings back the
         variables, the optimizer slots, global_step and the validation state; the position inside the epoch is not
         part of it (the reference's input queues restart as well)."""
         path = self._checkpoint_path()
-        if path is None or not os.path.isfile(path + '.index'):
+        if path is None:
             return False
         from ...processing import tfcheckpoint
+        path = tfcheckpoint.latest_checkpoint(os.path.dirname(path))
+        if path is None:
+            return False
+        self._restored_from = path
         step = self.model.store.load_tf_checkpoint(path, with_adam=True)
         have = set(n for n, _, _ in tfcheckpoint.list_variables(path))
         names = [n for n in ('learning_rate_fact', 'validated_step', 'best_validation', 'num_tries', 'should_terminate')

@@ -280,7 +280,7 @@ def read_checkpoint(prefix, names=None, check_crc=True):
     return out
 
 
-def write_checkpoint(prefix, arrays, shard_of=None, num_shards=1, producer=1):
+def write_checkpoint(prefix, arrays, shard_of=None, num_shards=1, producer=1, state_file=True):
     """Write {name: ndarray} as a V2 bundle.  `shard_of(name) -> shard id` spreads the variables over `num_shards`
     data files the way a sharded Saver spreads them over parameter-server devices (default: one shard).  `producer`
     1 = kTensorBundleVersion, what TF's BundleWriter puts in the header's VersionDef (tensor_bundle.cc; min_consumer 0)."""
@@ -313,10 +313,30 @@ def write_checkpoint(prefix, arrays, shard_of=None, num_shards=1, producer=1):
         for f in files:
             f.close()
     write_table(prefix + '.index', items)
-    # the `checkpoint` state file tf.train.latest_checkpoint reads
-    with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), 'checkpoint'), 'w') as f:
-        base = os.path.basename(prefix)
+    if state_file:
+        write_state_file(prefix)
+
+
+def write_state_file(prefix):
+    """the `checkpoint` state file tf.train.latest_checkpoint reads, replaced atomically"""
+    path = os.path.join(os.path.dirname(os.path.abspath(prefix)), 'checkpoint')
+    base = os.path.basename(prefix)
+    with open(path + '.tmp', 'w') as f:
         f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (base, base))
+    os.replace(path + '.tmp', path)
+
+
+def latest_checkpoint(directory):
+    """tf.train.latest_checkpoint: the prefix the directory's `checkpoint` state file names, or None"""
+    path = os.path.join(directory, 'checkpoint')
+    if not os.path.isfile(path):
+        return None
+    for line in open(path):
+        if line.startswith('model_checkpoint_path:'):
+            name = line.split(':', 1)[1].strip().strip('"')
+            prefix = name if os.path.isabs(name) else os.path.join(directory, name)
+            return prefix if os.path.isfile(prefix + '.index') else None
+    return None
 
 
 if __name__ == '__main__':                      # python -m nabu_b200.processing.tfcheckpoint <prefix> [name]

@@ -365,3 +365,28 @@ def test_blstm_operand_planes_travel_between_layers(B, T, H, pyramid):
     assert rel_err(dx1.cpu().numpy(), dx1_ref) < TOL
     for k in g1_ref:
         assert rel_err(g1[k].cpu().numpy(), g1_ref[k]) < TOL, ('layer 1', k)
+
+
+def test_out_of_range_labels_are_flagged_not_dereferenced():
+    """a label that is not a class of the output (a reader's none-symbol -1, or output_dims too small) gives
+    loss = +inf and a zero gradient for that utterance (TF raises / returns NaN) instead of indexing the logits out of
+    bounds; the other utterances of the batch are unaffected."""
+    from nabu_b200 import engine
+    rng = np.random.default_rng(0)
+    B, T, V, L = 3, 12, 5, 3
+    logits = rng.standard_normal((B, T, V)).astype(np.float32)
+    labels = np.array([[0, 1, 2], [1, -1, 0], [2, V - 1, 1]], np.int32)      # -1, and the blank index as a label
+    lens, ll = np.full(B, T, np.int32), np.full(B, L, np.int32)
+    loss, grad = engine.ctc_loss_per_utt(dev(logits), dev(lens), dev(labels), dev(ll), want_grad=True)
+    loss, grad = loss.cpu().numpy(), grad.cpu().numpy()
+    ref, _ = O.ctc_loss_and_grad(logits[:1], lens[:1], labels[:1], ll[:1])
+    assert abs(loss[0] - ref[0]) < 1e-4 * abs(ref[0])
+    assert np.isinf(loss[1]) and np.isinf(loss[2]) and np.all(grad[1:] == 0) and np.isfinite(grad[0]).all()
+    # masked cross entropy
+    U = 4
+    lg = rng.standard_normal((B, U, V)).astype(np.float32)
+    tg = np.array([[0, 1, 2, 3], [1, V, 0, 0], [2, -3, 1, 1]], np.int32)
+    tl = np.full(B, U, np.int32)
+    x = torch.tensor(lg, device='cuda', requires_grad=True)
+    out = engine.masked_ce_mean(x, dev(tg), dev(tl), dev(tl))
+    assert np.isinf(float(out))

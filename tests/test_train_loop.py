@@ -57,13 +57,15 @@ def test_train_loop_checkpoints_and_resumes(tmp_path, monkeypatch, capsys):
     assert ref.global_step == ref.num_steps == 12 and seen_ref == list(range(12))
     for name in ('network.pt', 'network.ckpt.index', 'network.ckpt.data-00000-of-00001', 'model.pkl'):
         assert os.path.isfile(os.path.join(ref_dir, 'model', name)), name
+    # step-suffixed prefix like tf.train.Saver's, the state file names it, older prefixes are gone
     assert sorted(os.listdir(os.path.join(ref_dir, 'logdir'))) == ['checkpoint', 'metrics.jsonl',
-                                                                  'model.ckpt.data-00000-of-00001', 'model.ckpt.index']
+                                                                  'model.ckpt-12.data-00000-of-00001', 'model.ckpt-12.index']
+    assert tfcheckpoint.latest_checkpoint(os.path.join(ref_dir, 'logdir')) == os.path.join(ref_dir, 'logdir', 'model.ckpt-12')
     import json
     rows = [json.loads(l) for l in open(os.path.join(ref_dir, 'logdir', 'metrics.jsonl'))]
     assert [r['step'] for r in rows] == list(range(12)) and all(r['training_loss'] > 0 for r in rows)
     assert rows[0]['learning_rate'] == 1e-3 and rows[-1]['learning_rate'] < rows[0]['learning_rate']
-    saved = dict((n, s) for n, s, _ in tfcheckpoint.list_variables(os.path.join(ref_dir, 'logdir', 'model.ckpt')))
+    saved = dict((n, s) for n, s, _ in tfcheckpoint.list_variables(os.path.join(ref_dir, 'logdir', 'model.ckpt-12')))
     assert saved['global_step'] == () and 'learning_rate_fact' in saved
     assert any(n.endswith('/kernel/Adam_1') for n in saved)
 
@@ -72,8 +74,12 @@ def test_train_loop_checkpoints_and_resumes(tmp_path, monkeypatch, capsys):
     with pytest.raises(_Crash):
         _trainer(expdir, seen, crash_at=5).train()
     assert seen == list(range(5))
-    assert int(tfcheckpoint.read_checkpoint(os.path.join(expdir, 'logdir', 'model.ckpt'),
+    assert int(tfcheckpoint.read_checkpoint(tfcheckpoint.latest_checkpoint(os.path.join(expdir, 'logdir')),
                                             names={'global_step'})['global_step']) == 5
+    # a save that dies after the bundle is written but before the state file is switched leaves the previous
+    # checkpoint in charge (the old scheme replaced .data before .index)
+    open(os.path.join(expdir, 'logdir', 'model.ckpt-99.index'), 'wb').write(b'torn')
+    assert tfcheckpoint.latest_checkpoint(os.path.join(expdir, 'logdir')).endswith('model.ckpt-5')
     again = _trainer(expdir, seen)
     again.train()
     assert 'resuming from step 5' in capsys.readouterr().out
