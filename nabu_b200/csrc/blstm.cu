@@ -918,18 +918,24 @@ extern "C" int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const
     return planes_after();
   }
   NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * (ceil_div(B, 128) * 128) * sizeof(float), stream));
-  if (blstm_fwd_chain_eligible(B, H)) {
-    bool launched = false;
-    if (int e = blstm_rec_fwd_chain(kern, g, c, y, w.xchg, len, B, T, yT, D, H, stream, &launched, yh, yl)) return e;
-    if (launched) return 0;
-  }
-  if (blstm_fwd_cluster_tc_eligible(B, H)) {
-    bool launched = false;
-    if (int e = blstm_rec_fwd_cluster_tc(kern, g, c, y, w.xchg, w.counters, len, B, T, yT, D, H, stream, &launched, yh, yl))
-      return e;
-    if (launched) return 0;
-  } else if (B > 128 && blstm_fwd_cluster_tc_eligible(128, H)) {
-    // more than 128 rows: the tcgen05 recurrence tile by tile (128 rows each, one after the other)
+  // the tcgen05 recurrences: the chain kernel (blstm_cl_fwdc.cu) for up to 128 rows, the 128-row kernel (blstm_cl_tc.cu)
+  // when it is forced or the chain kernel cannot be placed; more than 128 rows tile by tile, one tile after the other
+  auto rec_tile = [&](int b0, int Bt, bool* launched) -> int {
+    float* gt[2] = {g[0] + (size_t)b0 * T * H4, g[1] + (size_t)b0 * T * H4};
+    float* ct[2] = {c[0] + (size_t)b0 * T * H, c[1] + (size_t)b0 * T * H};
+    void* th = yh ? (char*)yh + (size_t)b0 * yT * 2 * H * 2 : nullptr;
+    void* tl = yl ? (char*)yl + (size_t)b0 * yT * 2 * H * 2 : nullptr;
+    *launched = false;
+    if (blstm_fwd_chain_eligible(Bt, H))
+      if (int e = blstm_rec_fwd_chain(kern, gt, ct, y + (size_t)b0 * yT * 2 * H, w.xchg, len + b0, Bt, T, yT, D, H, stream, launched, th, tl))
+        return e;
+    if (!*launched && blstm_fwd_cluster_tc_eligible(Bt, H))
+      if (int e = blstm_rec_fwd_cluster_tc(kern, gt, ct, y + (size_t)b0 * yT * 2 * H, w.xchg, w.counters, len + b0, Bt, T, yT, D, H,
+                                           stream, launched, th, tl))
+        return e;
+    return 0;
+  };
+  if (blstm_fwd_chain_eligible(std::min(B, 128), H) || blstm_fwd_cluster_tc_eligible(std::min(B, 128), H)) {
     bool any = false;
     for (int b0 = 0; b0 < B; b0 += 128) {
       const int Bt = std::min(128, B - b0);
@@ -937,13 +943,8 @@ extern "C" int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const
         NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
         NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H * 128 * sizeof(float), stream));
       }
-      float* gt[2] = {g[0] + (size_t)b0 * T * H4, g[1] + (size_t)b0 * T * H4};
-      float* ct[2] = {c[0] + (size_t)b0 * T * H, c[1] + (size_t)b0 * T * H};
       bool launched = false;
-      if (int e = blstm_rec_fwd_cluster_tc(kern, gt, ct, y + (size_t)b0 * yT * 2 * H, w.xchg, w.counters, len + b0, Bt, T, yT, D, H,
-                                           stream, &launched, yh ? (char*)yh + (size_t)b0 * yT * 2 * H * 2 : nullptr,
-                                           yl ? (char*)yl + (size_t)b0 * yT * 2 * H * 2 : nullptr))
-        return e;
+      if (int e = rec_tile(b0, Bt, &launched)) return e;
       if (!launched) {
         NABU_REQUIRE(b0 == 0, "blstm_fwd: the tcgen05 recurrence stopped being launchable between batch tiles");
         break;
@@ -1013,8 +1014,11 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
   Overlap& ov = overlap();
   // a batch of more than 128 rows runs the tcgen05 recurrence tile by tile (128 rows each, one after the other: two
   // tiles' clusters are not co-resident)
-  const int ntile = ceil_div(B, 128);
-  const bool tc_ok = blstm_bwd_cluster8_eligible(std::min(B, 128), H) && (ntile == 1 || blstm_bwd_chain_eligible(128, H));
+  // (num_units = 1024: tiles of 32 rows, the chain kernel's limit there -- blstm_cl_bwd8c.cu)
+  const int TILE_B = H == 1024 ? 32 : 128;
+  const int ntile = ceil_div(B, TILE_B);
+  const bool tc_ok = H == 1024 ? blstm_bwd_chain_eligible(std::min(B, TILE_B), H)
+                               : blstm_bwd_cluster8_eligible(std::min(B, 128), H) && (ntile == 1 || blstm_bwd_chain_eligible(128, H));
   const bool defer = ov.on && tc_ok && use_h2(B, T, D, H, yT);
   // dZ as operand planes straight from the recurrence (NABU_ZPLANES=0 keeps the fp32 dZ + split passes): the planes live
   // in library-owned scratch, two sets used alternately (see SideZ)
@@ -1084,7 +1088,7 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
       if (blstm_bwd_chain_eligible(B, H))
         re = blstm_rec_bwd_chain(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched, &ngrp,
                                  zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr, zplanes ? sz.zglob[zk] : nullptr);
-      if (!re && !launched) {
+      if (!re && !launched && blstm_bwd_cluster8_eligible(B, H)) {
         ngrp = 1;
         re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched,
                                     zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr,
@@ -1101,7 +1105,7 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
         NABU_CHECK_LAUNCH();
       }
       for (int tb = 0; tb < ntile && !re; ++tb) {
-        const int b0 = tb * 128, Bt = std::min(128, B - b0);
+        const int b0 = tb * TILE_B, Bt = std::min(TILE_B, B - b0);
         if (tb > 0) {
           NABU_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 1024, rs));
           NABU_CHECK_CUDA(cudaMemsetAsync(w.xchg, 0, (size_t)2 * 2 * H4 * 128 * sizeof(float), rs));

@@ -32,6 +32,14 @@ __device__ __forceinline__ void umma_f16_ts_c(uint32_t tmem_d, uint32_t tmem_a, 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+__device__ __forceinline__ void umma_f16_ss_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void tmem_st8_c(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
@@ -77,6 +85,10 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
   constexpr int BST = BLK + 64;                       // block stride (+16 banks)
   constexpr int CSTRIDE = (CSLICE + CLS * BST + 1023) / 1024 * 1024;   // shared memory of one chain
   constexpr int ACOLS = KBN * 32;                     // TMEM columns of one half of the weights
+  // num_units = 1024 (NQ = 8): the hi halves of the CTA's [128 units x 512] weight block fill the 256 TMEM columns the
+  // accumulators leave, the lo halves sit in shared memory as K-major SWIZZLE_128B tiles (the A operand of an SS-form MMA)
+  constexpr bool LOS = NQ > 4;
+  constexpr int WLO = LOS ? KBN * A_TILE : 0;         // bytes of the lo halves in shared memory
   constexpr uint32_t TM_AH = 256, TM_AL = 256 + ACOLS;
   constexpr int RPT = NB >= 32 ? NB / 32 : 1;         // batch rows per pointwise thread
   constexpr int CPB = NB / 8;                         // 16-byte chunks per thread and K block (hi tile, then lo tile)
@@ -95,7 +107,7 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
   const int ch = __shfl_sync(0xffffffffu, tid >> 7, 0);          // chain of this warpgroup (warp-uniform)
   const int t = tid & 127, wq = __shfl_sync(0xffffffffu, t >> 5, 0);
   const int per_dir = NQ * CLS;
-  const int dir = blockIdx.x / per_dir;
+  const int dir = p.dir0 + blockIdx.x / per_dir;
   const int q = (blockIdx.x % per_dir) / CLS;
   const int r = blockIdx.x % CLS;
   const int j0 = (q * CLS + r) * HS;
@@ -103,7 +115,8 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
   float* gates = p.gates[dir];
   const float* cells = p.cells[dir];
   uint8_t* dzx = reinterpret_cast<uint8_t*>(p.xchg) + (size_t)dir * 2 * CLS * XSLICE;   // [2 parity][8 slices][XSLICE]
-  uint8_t* Bs = sm + (size_t)ch * CSTRIDE;            // my chain's dz slice; after the MMAs: staging of 7 blocks
+  uint8_t* Wlo = sm;                                  // (LOS) [KBN][128 units x 64 k] fp16
+  uint8_t* Bs = sm + WLO + (size_t)ch * CSTRIDE;      // my chain's dz slice; after the MMAs: staging of 7 blocks
   float* rbuf = reinterpret_cast<float*>(Bs + CSLICE);   // [CLS src][NB batch][16 units], blocks BST bytes apart
 
   if (tid == 0) gmax_bits = 0u;
@@ -150,10 +163,17 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
         }
       }
       tmem_st8_c(tbase + TM_AH + (uint32_t)grp * 8, vh);
-      tmem_st8_c(tbase + TM_AL + (uint32_t)grp * 8, vl);
+      if constexpr (LOS) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint32_t*>(Wlo + (size_t)qq * A_TILE + sw128_h(m, uq * 16 + 2 * c)) = vl[c];
+      } else {
+        tmem_st8_c(tbase + TM_AL + (uint32_t)grp * 8, vl);
+      }
     }
     tmem_st_wait_c();
   }
+  if constexpr (LOS) fence_proxy_async_smem();         // generic writes of Wlo -> tensor-core (async proxy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -272,7 +292,8 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
             if (elect_one()) {
               umma_f16_ts_c(tm_d1, ah, bh, idesc, acc);
               umma_f16_ts_c(tm_d2, ah, bl, idesc, acc);
-              umma_f16_ts_c(tm_d2, al, bh, idesc, 1u);
+              if constexpr (LOS) umma_f16_ss_c(tm_d2, make_desc(smem_u32(Wlo) + kb * A_TILE + ks * 32, 16, 1024, 2), bh, idesc, 1u);
+              else umma_f16_ts_c(tm_d2, al, bh, idesc, 1u);
             }
           }
           if (kb == KBN - 1 && elect_one()) umma_commit(mma_u);
@@ -443,7 +464,8 @@ int launch_chain(const ClParams& p, unsigned* rowmax, cudaStream_t stream, bool*
   // Every CTA allocates all 512 TMEM columns, so two CTAs of this kernel on one SM deadlock (the second one waits in
   // tcgen05.alloc for the first, which spins on data the second one would produce): the small-batch variants ask for
   // more than half of an SM's shared memory to keep the scheduler from co-locating them.
-  const size_t smem = std::max<size_t>(1024 + (size_t)NCH * CSTRIDE, (size_t)max_smem_optin() / 2 + 2048);
+  constexpr int WLO = NQ > 4 ? NQ * A_TILE : 0;
+  const size_t smem = std::max<size_t>(1024 + WLO + (size_t)NCH * CSTRIDE, (size_t)max_smem_optin() / 2 + 2048);
   auto* fn = blstm_rec_bwd_chain_kernel<NQ, NB, NCH>;
   *launched = false;
   if (smem > (size_t)max_smem_optin()) return 0;
@@ -465,7 +487,13 @@ int launch_chain(const ClParams& p, unsigned* rowmax, cudaStream_t stream, bool*
   if (getenv("NABU_DEBUG"))
     fprintf(stderr, "[nabu] bwd chain kernel NQ=%d NB=%d NCH=%d: smem %zu B, max active clusters %d (%s), need %d\n", NQ, NB, NCH,
             smem, nclusters, cudaGetErrorString(oe), 2 * NQ);
-  if (oe != cudaSuccess || nclusters < 2 * NQ) {
+  // both directions in one launch when their clusters are co-resident (2 NQ clusters of 8), else one after the other
+  // (num_units = 1024: 16 clusters of 8 do not fit the 148 SMs)
+  int ndir = 2;
+  if (oe == cudaSuccess && nclusters < 2 * NQ && nclusters >= NQ) {
+    ndir = 1;
+    cfg.gridDim = dim3(NQ * CLS);
+  } else if (oe != cudaSuccess || nclusters < 2 * NQ) {
     cudaGetLastError();
     return 0;
   }
@@ -474,11 +502,14 @@ int launch_chain(const ClParams& p, unsigned* rowmax, cudaStream_t stream, bool*
     row_absmax_kernel<<<dim3(32, p.B), 256, 0, stream>>>(p.dy, p.len, p.yT, 2 * p.H, rowmax);
     NABU_CHECK_LAUNCH();
   }
-  KernelScope ks(NCH == 4 ? "blstm_rec_bwd_chain4" : NCH == 2 ? "blstm_rec_bwd_chain2" : "blstm_rec_bwd_chain1", stream);
   ClParams pt = p;
   pt.trace = trace_buffer();
   const unsigned* rm = rowmax;
-  NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, pt, rm));
+  for (int d0 = 0; d0 < 2; d0 += ndir) {
+    KernelScope ks(NCH == 4 ? "blstm_rec_bwd_chain4" : NCH == 2 ? "blstm_rec_bwd_chain2" : "blstm_rec_bwd_chain1", stream);
+    pt.dir0 = d0;
+    NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, pt, rm));
+  }
   trace_dump("bwd8c", pt.trace, stream);
   *launched = true;
   return 0;
@@ -498,6 +529,14 @@ int dispatch_chain(const ClParams& p, unsigned* rowmax, cudaStream_t stream, boo
   // and four chains of 32 beat two of 64 at B = 128 (cfg-3 step 195 ms against 203 ms; 10.5 us per time step alone)
   int nb = p.B <= 32 ? 16 : 32;
   int nch = p.B <= 16 ? 1 : p.B <= 64 ? 2 : 4;
+  if constexpr (NQ > 4) {                             // num_units = 1024: at most 32 rows per launch (shared memory)
+    NABU_REQUIRE(p.B <= 32, "blstm bwd chain kernel: num_units = 1024 takes at most 32 rows per launch (got %d)", p.B);
+    nb = 16; nch = p.B <= 16 ? 1 : 2;
+    if (force && fnb * fnch >= p.B && fnb * fnch <= 32) { nb = fnb; nch = fnch; }
+    if (nb == 32) return launch_chain<NQ, 32, 1>(p, rowmax, stream, launched, rmr);
+    if (nch == 1) return launch_chain<NQ, 16, 1>(p, rowmax, stream, launched, rmr);
+    return launch_chain<NQ, 16, 2>(p, rowmax, stream, launched, rmr);
+  } else {
   if (force && fnb * fnch >= p.B) { nb = fnb; nch = fnch; }
   if (nb == 32 && nch == 4) return launch_chain<NQ, 32, 4>(p, rowmax, stream, launched, rmr);
   if (nb == 16 && nch == 1) return launch_chain<NQ, 16, 1>(p, rowmax, stream, launched, rmr);
@@ -506,6 +545,7 @@ int dispatch_chain(const ClParams& p, unsigned* rowmax, cudaStream_t stream, boo
   if (nb == 16 && nch == 2) return launch_chain<NQ, 16, 2>(p, rowmax, stream, launched, rmr);
   if (nb == 32 && nch == 2) return launch_chain<NQ, 32, 2>(p, rowmax, stream, launched, rmr);
   return launch_chain<NQ, 64, 2>(p, rowmax, stream, launched, rmr);
+  }
 }
 
 }  // namespace
@@ -517,7 +557,7 @@ bool blstm_bwd_chain_eligible(int B, int H) {
     enabled = (e && (strcmp(e, "flat") == 0 || strcmp(e, "ffma") == 0 || strcmp(e, "cl4") == 0 || strcmp(e, "cl8") == 0)) ? 0 : 1;
   }
   if (!enabled) return false;
-  return B <= 128 && B > 0 && (H == 256 || H == 512);
+  return B > 0 && ((B <= 128 && (H == 256 || H == 512)) || (B <= 32 && H == 1024));
 }
 
 int blstm_rec_bwd_chain(const float* const kernel[2], float* const gates[2], const float* const cells[2], const float* dy,
@@ -531,11 +571,13 @@ int blstm_rec_bwd_chain(const float* const kernel[2], float* const gates[2], con
   p.B = B; p.T = T; p.yT = yT; p.D = D; p.H = H;
   p.zh = zh; p.zl = zl; p.zinv = zinv;
   *nslots = B <= 16 ? 1 : B <= 64 ? 2 : 4;
+  if (H == 1024) *nslots = B <= 16 ? 1 : 2;
   if (const char* e = getenv("NABU_BWD_CHAINS")) {
     int a = 0, b = 0;
     if (sscanf(e, "%dx%d", &a, &b) == 2 && a * b >= B) *nslots = b;
   }
-  return H == 512 ? dispatch_chain<4>(p, rowmax, stream, launched, rowmax_ready) : dispatch_chain<2>(p, rowmax, stream, launched, rowmax_ready);
+  return H == 1024 ? dispatch_chain<8>(p, rowmax, stream, launched, rowmax_ready)
+                   : H == 512 ? dispatch_chain<4>(p, rowmax, stream, launched, rowmax_ready) : dispatch_chain<2>(p, rowmax, stream, launched, rowmax_ready);
 }
 
 }  // namespace nabu

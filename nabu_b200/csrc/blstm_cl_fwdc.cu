@@ -76,7 +76,7 @@ blstm_rec_fwd_chain_kernel(const ClParams p) {
   const int ch = __shfl_sync(0xffffffffu, tid >> 7, 0);
   const int t = tid & 127, wq = __shfl_sync(0xffffffffu, t >> 5, 0);
   const int per_dir = H / HS;                          // CTAs per direction
-  const int dir = blockIdx.x / per_dir;
+  const int dir = p.dir0 + blockIdx.x / per_dir;
   const int q = (blockIdx.x % per_dir) / CLS;
   const int r = blockIdx.x % CLS;
   const int j0 = (q * CLS + r) * HS;
@@ -339,8 +339,10 @@ int launch_fwd_chain(const ClParams& p, cudaStream_t stream, bool* launched) {
   *launched = false;
   if (smem > (size_t)max_smem_optin()) return 0;
   NABU_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // num_units = 1024: the 2 x 128 CTAs of both directions do not fit the GPU, the directions run one after the other
+  const int ndir = 2 * (p.H / 8) <= num_sms() ? 2 : 1;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (p.H / 8));
+  cfg.gridDim = dim3(ndir * (p.H / 8));
   cfg.blockDim = dim3(128 * NCH);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -360,10 +362,13 @@ int launch_fwd_chain(const ClParams& p, cudaStream_t stream, bool* launched) {
     cudaGetLastError();
     return 0;
   }
-  KernelScope ks(NCH == 4 ? "blstm_rec_fwd_chain4" : NCH == 2 ? "blstm_rec_fwd_chain2" : "blstm_rec_fwd_chain1", stream);
   ClParams pt = p;
   pt.trace = trace_buffer();
-  NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, pt));
+  for (int d0 = 0; d0 < 2; d0 += ndir) {
+    KernelScope ks(NCH == 4 ? "blstm_rec_fwd_chain4" : NCH == 2 ? "blstm_rec_fwd_chain2" : "blstm_rec_fwd_chain1", stream);
+    pt.dir0 = d0;
+    NABU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, pt));
+  }
   trace_dump("fwdc", pt.trace, stream);
   *launched = true;
   return 0;
@@ -402,7 +407,7 @@ bool blstm_fwd_chain_eligible(int B, int H) {
     if (const char* m = getenv("NABU_FWD_CHAIN_MAXB")) maxb = atoi(m);
   }
   if (!enabled) return false;
-  return B <= maxb && B <= 128 && B > 0 && (H == 256 || H == 512);
+  return B <= maxb && B <= 128 && B > 0 && (H == 256 || H == 512 || H == 1024);
 }
 
 int blstm_rec_fwd_chain(const float* const kernel[2], float* const gates[2], float* const cells[2], float* y, float* xchg,
@@ -415,7 +420,8 @@ int blstm_rec_fwd_chain(const float* const kernel[2], float* const gates[2], flo
   p.y = y; p.xchg = xchg; p.len = len;
   p.B = B; p.T = T; p.yT = yT; p.D = D; p.H = H;
   p.yh = yh; p.yl = yl;
-  return H == 512 ? dispatch_fwd_chain<2>(p, stream, launched) : dispatch_fwd_chain<1>(p, stream, launched);
+  return H == 1024 ? dispatch_fwd_chain<4>(p, stream, launched)
+                   : H == 512 ? dispatch_fwd_chain<2>(p, stream, launched) : dispatch_fwd_chain<1>(p, stream, launched);
 }
 
 }  // namespace nabu

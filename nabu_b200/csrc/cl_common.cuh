@@ -32,6 +32,7 @@ struct ClParams {
   // dZ * S, S the power of two that puts the largest |dy| of the batch in [32, 64), 1/S written to *zinv.  NULL = off.
   void *yh, *yl, *zh, *zl;
   float* zinv;
+  int dir0;                 // first direction of this launch (kernels that run the directions one after the other: H = 1024)
 };
 
 constexpr int TRACE_S0 = 200, TRACE_N = 8, TRACE_PH = 10, TRACE_CTAS = 256;

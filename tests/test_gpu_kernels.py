@@ -116,6 +116,13 @@ def test_blstm_h1024_sequential_directions():
     _blstm_case(8, 4, 32, 1024, True, seed=11)
 
 
+@pytest.mark.parametrize('B,T,D', [(32, 24, 40), (40, 11, 64), (20, 9, 2048)])
+def test_blstm_h1024_tensor_core_chains(B, T, D):
+    """configs[4] width (DBLSTM 6 x 1024): the chain kernels with the directions one after the other, forward weights in
+    TMEM, backward weights hi in TMEM / lo in shared memory, backward batch tiles of 32 rows."""
+    _blstm_case(B, T, D, 1024, True, seed=B + T)
+
+
 @pytest.mark.parametrize('B,T,V,L,ragged', [(4, 30, 6, 7, True), (32, 200, 29, 20, True), (2, 5, 3, 2, False),
                                             (3, 40, 29, 0, False), (8, 1500, 29, 150, True)])
 def test_ctc(B, T, V, L, ragged):
