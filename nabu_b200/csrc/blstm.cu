@@ -956,8 +956,8 @@ extern "C" int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const
   {
     char key[96];
     snprintf(key, sizeof(key), "fwd B=%d H=%d", B, H);
-    warn_once(key, "blstm forward recurrence B=%d num_units=%d is not on the tcgen05 cluster kernels (they exist for num_units 256 "
-              "and 512; the Python engine pads narrower layers up to them): falling back to the FFMA kernels", B, H);
+    warn_once(key, "blstm forward recurrence B=%d num_units=%d is not on the tcgen05 cluster kernels (they exist for num_units 256, "
+              "512 and 1024; the Python engine pads other widths up to them): falling back to the FFMA kernels", B, H);
   }
   if (blstm_fwd_cluster_eligible(B, H)) {
     bool launched = false;
@@ -1142,7 +1142,7 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
     char key[96];
     snprintf(key, sizeof(key), "bwd B=%d H=%d", B, H);
     warn_once(key, "blstm backward recurrence B=%d num_units=%d is not on the TMEM-resident tcgen05 kernels (they exist for "
-              "num_units 256 and 512; the Python engine pads narrower layers up to them): falling back", B, H);
+              "num_units 256, 512 and 1024; the Python engine pads other widths up to them): falling back", B, H);
   }
   if (!launched && blstm_bwd_cluster_tc_eligible(B, H)) {
     const float* cc[2] = {c[0], c[1]};

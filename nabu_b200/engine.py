@@ -330,7 +330,7 @@ class _BLSTMPadded(torch.autograd.Function):
 
 def rec_width(H, B=None):
     """The number of hidden units the recurrence kernels run for a layer of `H` units.  The tcgen05 cluster kernels exist
-    for 256 and 512 units (csrc/blstm_cl_tc.cu, blstm_cl_bwd8.cu); a narrower layer -- every recipe the reference ships
+    for 256, 512 and 1024 units (csrc/blstm_cl_fwdc.cu, blstm_cl_bwd8c.cu); a narrower layer -- every recipe the reference ships
     uses num_units = 128 -- is zero-padded up to the next of those (exact, see _BLSTMPadded) when the batch is large
     enough for that to win: measured on a B200 at num_units = 128, T = 800 (tools/h128_probe.py, profiles/r2_h128_probe.txt)
     the padded tcgen05 path takes 6.6 / 10.7 us per time step forward / backward against 8.9 / 12.1 on the FFMA cluster
@@ -339,7 +339,9 @@ def rec_width(H, B=None):
     import os
     Hp = (H + REC_UNIT - 1) // REC_UNIT * REC_UNIT
     mode = os.environ.get('NABU_PAD_UNITS', 'auto')
-    if mode != '0' and (B is None or B <= 128) and H < 512 and H not in (256,):
+    if mode != '0' and H < 1024 and H not in (256, 512):
+        if H > 512:                    # 513 .. 1023 units: the FFMA kernels take 17 / 35 us per time step there
+            return 1024
         if mode == '1' or (B is not None and B > 32):
             return 256 if H <= 256 else 512
     return Hp
