@@ -57,9 +57,16 @@ __device__ __forceinline__ void ld4c(const float* p, float (&v)[4]) {
 }
 // 128 threads of one chain (named barrier 1 + chain; barrier 0 is __syncthreads)
 __device__ __forceinline__ void bar_chain(int ch) { asm volatile("bar.sync %0, 128;" ::"r"(ch + 1) : "memory"); }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+// Relaxed on purpose: the arrival only says "my loads of the receive buffer have returned" -- `dep` is a value computed
+// from every one of them, so the instruction cannot issue before they have -- and publishes no writes.  The .release form
+// compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive: 0.5 us of every time step (ncu, profiles/r2_ncu_full.md).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster, float dep) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster), "f"(dep) : "memory");
 }
+// Keeps the arithmetic on a prefetched value BELOW this point of the instruction stream: without it the compiler starts
+// tanh(c) right behind the prefetch loads and the chain stalls on their L2 / HBM latency in front of the MMAs.
+__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -236,8 +243,7 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
 #pragma unroll
       for (int i = 1; i < CPB; ++i) v[0][i] = ld_relaxed_v4(chunk(0, i));
     }
-    // ---- prefetch pointwise operands -------------------------------------------------------------------------
-    float gt[RPT][4][4], ct[RPT][4], cprev[RPT][4], dyv[RPT][4];
+    // ---- pointwise operands: L2 prefetch now (no registers held), the loads themselves behind the MMA issue -----------
     bool valid[RPT];
     int tt[RPT];
 #pragma unroll
@@ -245,19 +251,12 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
       const int b = ch * NB + rw + 32 * rr;
       valid[rr] = s < plen[rr];
       tt[rr] = valid[rr] ? (dir ? plen[rr] - 1 - s : s) : s;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ct[rr][u] = cprev[rr][u] = dyv[rr][u] = 0.f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) gt[rr][g][u] = 0.f;
-      }
       if (valid[rr]) {
         const float* gp = gates + ((size_t)b * p.T + tt[rr]) * H4 + j0 + ug;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ld4c(gp + g * H, gt[rr][g]);
-        ld4c(cells + ((size_t)b * p.T + tt[rr]) * H + j0 + ug, ct[rr]);
-        if (s > 0) ld4c(cells + ((size_t)b * p.T + (dir ? tt[rr] + 1 : tt[rr] - 1)) * H + j0 + ug, cprev[rr]);
-        ld4c(p.dy + ((size_t)b * p.yT + tt[rr]) * 2 * H + dir * H + j0 + ug, dyv[rr]);
+        for (int g = 0; g < 4; ++g) prefetch_l2(gp + g * H);
+        prefetch_l2(cells + ((size_t)b * p.T + tt[rr]) * H + j0 + ug);
+        prefetch_l2(p.dy + ((size_t)b * p.yT + tt[rr]) * 2 * H + dir * H + j0 + ug);
       }
     }
 
@@ -300,6 +299,31 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
         }
         __syncwarp();
       }
+    }
+    // (the staging registers v[][] are dead here: the operands of the pointwise stage take their place while the tensor
+    // pipe, the TMEM drain and the reduce-scatter run)
+    // ---- prefetch pointwise operands -------------------------------------------------------------------------
+    float gt[RPT][4][4], ct[RPT][4], cprev[RPT][4], dyv[RPT][4];
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr) {
+      const int b = ch * NB + rw + 32 * rr;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ct[rr][u] = cprev[rr][u] = dyv[rr][u] = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gt[rr][g][u] = 0.f;
+      }
+      if (valid[rr]) {
+        const float* gp = gates + ((size_t)b * p.T + tt[rr]) * H4 + j0 + ug;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ld4c(gp + g * H, gt[rr][g]);
+        ld4c(cells + ((size_t)b * p.T + tt[rr]) * H + j0 + ug, ct[rr]);
+        if (s > 0) ld4c(cells + ((size_t)b * p.T + (dir ? tt[rr] + 1 : tt[rr] - 1)) * H + j0 + ug, cprev[rr]);
+        ld4c(p.dy + ((size_t)b * p.yT + tt[rr]) * 2 * H + dir * H + j0 + ug, dyv[rr]);
+      }
+    }
+
+    if (iter > 0) {
       mbar_wait(mma_u, par);
       tc_fence_after();
       if (ch == 0) CL_STAMP(iter, 3);
@@ -309,7 +333,21 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
         float* dstcol = (d == r) ? rbuf + (size_t)r * (BST / 4) + u
                                  : reinterpret_cast<float*>(Bs) + (size_t)(d < r ? d : d - 1) * (BST / 4) + u;
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-        if constexpr (NB >= 32) {
+        if constexpr (NB >= 32 && NCH == 4) {
+          // 512 threads leave 128 registers each: 16 columns at a time (64 live registers of a 32-column drain next to
+          // the prefetched pointwise operands spilled to local memory, and a reload behind the polling loads in the LSU
+          // queue costs an L2 round trip)
+#pragma unroll
+          for (int k = 0; k < NB / 16; ++k) {
+            uint32_t v1[16], v2[16];
+            tmem_ld16(tm_d1 + lane_base + (uint32_t)(k * 16), v1);
+            tmem_ld16(tm_d2 + lane_base + (uint32_t)(k * 16), v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              dstcol[(k * 16 + i) * 16] = fmaf(__uint_as_float(v2[i]), 1.f / 2048.f, __uint_as_float(v1[i]));
+          }
+        } else if constexpr (NB >= 32) {
 #pragma unroll
           for (int k = 0; k < NB / 32; ++k) {
             uint32_t v1[32], v2[32];
@@ -339,6 +377,14 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
       mbar_wait(rx_u, par);                            // the 7 remote blocks have landed in my buffer
       if (ch == 0) CL_STAMP(iter, 5);
     }
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pin(ct[rr][u]); pin(cprev[rr][u]); pin(dyv[rr][u]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pin(gt[rr][g][u]);
+      }
 
     // ---- pointwise gate gradients for my 16 units --------------------------------------------------------------
     float dh[RPT][4];
@@ -364,7 +410,10 @@ blstm_rec_bwd_chain_kernel(const ClParams p, const unsigned* __restrict__ rowmax
     // "free" barrier of every CTA of the cluster (lane d -> CTA d)
     if (s > 0) {
       __syncwarp();
-      if (lane < CLS) mbar_arrive_remote(map_to_rank(free_u, (uint32_t)lane));
+      float dep = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < RPT; ++rr) dep += (dh[rr][0] + dh[rr][1]) + (dh[rr][2] + dh[rr][3]);
+      if (lane < CLS) mbar_arrive_remote(map_to_rank(free_u, (uint32_t)lane), dep);
     }
     float dzv[RPT][4][4];
 #pragma unroll

@@ -32,9 +32,11 @@ __device__ __forceinline__ void tmem_st8_f(uint32_t taddr, const uint32_t (&r)[8
 }
 __device__ __forceinline__ void tmem_st_wait_f() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bar_chain_f(int ch) { asm volatile("bar.sync %0, 128;" ::"r"(ch + 1) : "memory"); }
-__device__ __forceinline__ void mbar_arrive_remote_f(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+// relaxed, ordered behind the loads of the receive buffer by the data dependency on `dep` (see blstm_cl_bwd8c.cu)
+__device__ __forceinline__ void mbar_arrive_remote_f(uint32_t bar_cluster, float dep) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster), "f"(dep) : "memory");
 }
+__device__ __forceinline__ void pin_f(float& x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ void mbar_wait_cluster_f(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -252,6 +254,10 @@ blstm_rec_fwd_chain_kernel(const ClParams p) {
       mbar_wait(rx_u, par);
       if (ch == 0) CL_STAMP(s, 5);
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pin_f(gx[g][u]);
 
     // ---- pointwise cell update for my 8 units -------------------------------------------------------------------
     float av[5][4], hn[4] = {0.f, 0.f, 0.f, 0.f};
@@ -266,7 +272,8 @@ blstm_rec_fwd_chain_kernel(const ClParams p) {
     }
     if (s + 1 < p.T) {                                 // my receive buffer is free once these loads have returned
       __syncwarp();
-      if (lane < CLS) mbar_arrive_remote_f(map_to_rank(free_u, (uint32_t)lane));
+      const float dep = ((gx[0][0] + gx[1][1]) + (gx[2][2] + gx[3][3])) + ((gx[0][3] + gx[1][2]) + (gx[2][1] + gx[3][0]));
+      if (lane < CLS) mbar_arrive_remote_f(map_to_rank(free_u, (uint32_t)lane), dep);
     }
     if (prow) {
 #pragma unroll

@@ -52,8 +52,15 @@ __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier
 // Gate non-linearities from MUFU.EX2 / MUFU.RCP (4-5 instructions instead of ~40 for expf and ~60 for tanhf; the
 // pointwise stage of a time step is issue-bound on them).  Absolute error <= 2e-7 on values in (-1, 1): the same order
 // as the fp32 rounding of the cell state they feed, three orders below the 1e-4 parity bar (tests/test_gpu_kernels.py).
-__device__ __forceinline__ float sigmoid_tc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_tc(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+// ex2.approx.ftz: the non-ftz form brackets every MUFU.EX2 with a denormal-range test and two scalings (FSETP + 2 FMUL);
+// a result below 2^-126 flushed to zero changes neither 1 / (1 + e) nor 1 - 2 / (1 + e).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_tc(float x) { return __fdividef(1.f, 1.f + ex2_ftz(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float tanh_tc(float x) { return 1.f - __fdividef(2.f, 1.f + ex2_ftz(x * 2.8853900817779268f)); }
 
 // ---- flag-in-data exchange ("LL"): the value written at step s carries ll_flag(s) in the lowest bit of BOTH of its
 // fp16 halves; a buffer is rewritten every second step, so consecutive tenants of a location differ in that bit and the
