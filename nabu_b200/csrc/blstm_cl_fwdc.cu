@@ -37,6 +37,27 @@ __device__ __forceinline__ void mbar_arrive_remote_f(uint32_t bar_cluster, float
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster), "f"(dep) : "memory");
 }
 __device__ __forceinline__ void pin_f(float& x) { asm volatile("" : "+f"(x)); }
+// N = 1, 2 or 4 consecutive floats / packed fp16 values (the pointwise stage gives every thread NB / 16 units of a row)
+template <int N> __device__ __forceinline__ void ldcg_n(const float* p, float (&v)[N]) {
+  if constexpr (N == 4) { const float4 a = __ldcg(reinterpret_cast<const float4*>(p)); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+  else if constexpr (N == 2) { const float2 a = __ldcg(reinterpret_cast<const float2*>(p)); v[0] = a.x; v[1] = a.y; }
+  else v[0] = __ldcg(p);
+}
+template <int N> __device__ __forceinline__ void lds_add_n(const float* p, float (&v)[N]) {
+  if constexpr (N == 4) { const float4 a = *reinterpret_cast<const float4*>(p); v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; }
+  else if constexpr (N == 2) { const float2 a = *reinterpret_cast<const float2*>(p); v[0] += a.x; v[1] += a.y; }
+  else v[0] += *p;
+}
+template <int N> __device__ __forceinline__ void stcg_n(float* p, const float (&v)[N]) {
+  if constexpr (N == 4) __stcg(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  else if constexpr (N == 2) __stcg(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  else __stcg(p, v[0]);
+}
+template <int N> __device__ __forceinline__ void stcg_h(void* p, const unsigned short (&h)[N]) {
+  if constexpr (N == 4) __stcg(reinterpret_cast<uint2*>(p), make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16)));
+  else if constexpr (N == 2) __stcg(reinterpret_cast<unsigned*>(p), (uint32_t)h[0] | ((uint32_t)h[1] << 16));
+  else __stcg(reinterpret_cast<unsigned short*>(p), h[0]);
+}
 __device__ __forceinline__ void mbar_wait_cluster_f(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -136,33 +157,34 @@ blstm_rec_fwd_chain_kernel(const ClParams p) {
   const uint32_t Bs_u = smem_u32(Bs), rbuf_u = smem_u32(rbuf);
   const uint32_t rx_u = smem_u32(&rx_bar[ch]), mma_u = smem_u32(&mma_bar[ch]), free_u = smem_u32(&free_bar[ch]);
   const uint32_t tm_d1 = tm + (uint32_t)(ch * 2 * NB), tm_d2 = tm_d1 + NB;
-  // pointwise: thread (row, 4 of the CTA's 8 units)
-  const int prl = t >> 1, pu = (t & 1) * 4;
+  // pointwise: all 128 threads of the chain, thread = (row, UPT of the CTA's 8 units).  (With 4 units per thread whatever
+  // NB, half of the threads idled at NB = 32 and the stage is latency-bound on the per-thread instruction chain.)
+  constexpr int UPT = NB >= 64 ? 4 : NB / 16, TPR = HS / UPT;
+  const int prl = t / TPR, pu = (t % TPR) * UPT;
   const bool pact = prl < NB;
   const int pb = ch * NB + prl;                        // batch row
   const bool prow = pact && pb < p.B;
   const int plen = prow ? p.len[pb] : 0;
-  float ccarry[4] = {0.f, 0.f, 0.f, 0.f};
+  float ccarry[UPT];
+#pragma unroll
+  for (int u = 0; u < UPT; ++u) ccarry[u] = 0.f;
 
   for (int s = 0; s < p.T; ++s) {
     const uint8_t* hprev = hx + (size_t)((s + 1) & 1) * CLS * XSLICE;
     uint8_t* hnext = hx + (size_t)(s & 1) * CLS * XSLICE;
     if (ch == 0) CL_STAMP(s, 0);
-    float gx[4][4];
+    float gx[4][UPT];
     const bool valid = s < plen;
     const int tt = valid ? (dir ? plen - 1 - s : s) : s;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) gx[g][u] = 0.f;
+      for (int u = 0; u < UPT; ++u) gx[g][u] = 0.f;
     auto prefetch_gx = [&]() {
       if (valid) {
         const float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(gp + g * H));
-          gx[g][0] = v.x; gx[g][1] = v.y; gx[g][2] = v.z; gx[g][3] = v.w;
-        }
+        for (int g = 0; g < 4; ++g) ldcg_n<UPT>(gp + g * H, gx[g]);
       }
     };
     if (s == 0) prefetch_gx();
@@ -257,27 +279,26 @@ blstm_rec_fwd_chain_kernel(const ClParams p) {
 #pragma unroll
     for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) pin_f(gx[g][u]);
+      for (int u = 0; u < UPT; ++u) pin_f(gx[g][u]);
 
     // ---- pointwise cell update for my 8 units -------------------------------------------------------------------
-    float av[5][4], hn[4] = {0.f, 0.f, 0.f, 0.f};
+    float av[5][UPT], hn[UPT];
+#pragma unroll
+    for (int u = 0; u < UPT; ++u) hn[u] = 0.f;
     if (s > 0 && pact) {
 #pragma unroll
       for (int src = 0; src < CLS; ++src)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 x = *reinterpret_cast<const float4*>(rbuf + (size_t)src * (BST / 4) + prl * 32 + g * 8 + pu);
-          gx[g][0] += x.x; gx[g][1] += x.y; gx[g][2] += x.z; gx[g][3] += x.w;
-        }
+        for (int g = 0; g < 4; ++g) lds_add_n<UPT>(rbuf + (size_t)src * (BST / 4) + prl * 32 + g * 8 + pu, gx[g]);
     }
     if (s + 1 < p.T) {                                 // my receive buffer is free once these loads have returned
       __syncwarp();
-      const float dep = ((gx[0][0] + gx[1][1]) + (gx[2][2] + gx[3][3])) + ((gx[0][3] + gx[1][2]) + (gx[2][1] + gx[3][0]));
+      const float dep = (gx[0][0] + gx[1][0]) + (gx[2][0] + gx[3][0]);
       if (lane < CLS) mbar_arrive_remote_f(map_to_rank(free_u, (uint32_t)lane), dep);
     }
     if (prow) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UPT; ++u) {
         const float ig = sigmoid_tc(gx[0][u]);
         const float gg = tanh_tc(gx[1][u]);
         const float fg = sigmoid_tc(gx[2][u] + 1.0f);
@@ -293,13 +314,13 @@ blstm_rec_fwd_chain_kernel(const ClParams p) {
     if (pact) {
       // h_t, split, flagged, in the consumers' UMMA layout (every row of the tile: rows b >= B as zeros)
       const unsigned short fb = (unsigned short)ll_flag(s);
-      unsigned short hh[4], hl[4];
+      unsigned short hh[UPT], hl[UPT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) split_h_flag(hn[u], fb, &hh[u], &hl[u]);
+      for (int u = 0; u < UPT; ++u) split_h_flag(hn[u], fb, &hh[u], &hl[u]);
       const int j = j0 + pu;
       uint8_t* tp = hnext + (size_t)(j / KS) * XSLICE + (size_t)((j % KS) / 64) * 2 * XTILE + sw128_h(pb, j % 64);
-      __stcg(reinterpret_cast<uint2*>(tp), make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16)));
-      __stcg(reinterpret_cast<uint2*>(tp + XTILE), make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16)));
+      stcg_h<UPT>(tp, hh);
+      stcg_h<UPT>(tp + XTILE, hl);
     }
     if (ch == 0) { CL_STAMP(s, 6); CL_STAMP(s, 7); CL_STAMP(s, 8); CL_STAMP(s, 9); }
     // ---- off the critical path: what the backward pass and the next layer need --------------------------------------
@@ -308,23 +329,21 @@ blstm_rec_fwd_chain_kernel(const ClParams p) {
         float* gp = gates + ((size_t)pb * p.T + tt) * H4 + j0 + pu;
         float* cp = cells + ((size_t)pb * p.T + tt) * H + j0 + pu;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) __stcg(reinterpret_cast<float4*>(gp + g * H), make_float4(av[g][0], av[g][1], av[g][2], av[g][3]));
-        __stcg(reinterpret_cast<float4*>(cp), make_float4(av[4][0], av[4][1], av[4][2], av[4][3]));
+        for (int g = 0; g < 4; ++g) stcg_n<UPT>(gp + g * H, av[g]);
+        stcg_n<UPT>(cp, av[4]);
       }
       const size_t yo = ((size_t)pb * p.yT + tt) * 2 * H + dir * H + j0 + pu;
-      __stcg(reinterpret_cast<float4*>(p.y + yo), make_float4(hn[0], hn[1], hn[2], hn[3]));
+      stcg_n<UPT>(p.y + yo, hn);
       if (p.yh) {
-        unsigned short ph[4], pl[4];
+        unsigned short ph[UPT], pl[UPT];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UPT; ++u) {
           __half hi, lo;
           split_h(hn[u] * Y_PLANE_SCALE, &hi, &lo);
           ph[u] = __half_as_ushort(hi); pl[u] = __half_as_ushort(lo);
         }
-        __stcg(reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.yh) + yo),
-               make_uint2((uint32_t)ph[0] | ((uint32_t)ph[1] << 16), (uint32_t)ph[2] | ((uint32_t)ph[3] << 16)));
-        __stcg(reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.yl) + yo),
-               make_uint2((uint32_t)pl[0] | ((uint32_t)pl[1] << 16), (uint32_t)pl[2] | ((uint32_t)pl[3] << 16)));
+        stcg_h<UPT>(reinterpret_cast<__half*>(p.yh) + yo, ph);
+        stcg_h<UPT>(reinterpret_cast<__half*>(p.yl) + yo, pl);
       }
     }
   }
