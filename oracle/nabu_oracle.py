@@ -1,7 +1,9 @@
 """NumPy restatement of nabu's per-utterance training / decoding hot path.
 
-TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED (no
-reference golden vectors exist; TF-1.8 is external).  Every function cites the
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Pinned against the
+reference's own Python executed over a restated TF-1.8 API
+(tests/golden/tf18shim_cases); TensorFlow's kernels themselves are restated,
+never run (no reference golden vectors exist; TF-1.8 is external).  Every function cites the
 reference call site it follows (paths relative to /root/reference/nabu) and,
 where the arithmetic is TensorFlow's, the TF-1.8 op it restates (SURVEY.md
 appendix B).

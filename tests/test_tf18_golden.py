@@ -14,8 +14,11 @@ import torch
 import oracle as O
 from tests.util import rel_err
 
-CASES = sorted(os.path.dirname(p) for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
-                                                                  'tf18', '*', 'outputs.npz')))
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+# tf18/: dumps of a real TF-1.8 run (tools/tf18_dump.py; none committed).  tf18shim_cases/: the reference's own Python
+# executed from /root/reference over tests/golden/tf18shim (tests/golden/make_tf18shim_golden.py; committed).
+CASES = sorted(os.path.dirname(p) for d in ('tf18', 'tf18shim_cases')
+               for p in glob.glob(os.path.join(_GOLDEN, d, '*', 'outputs.npz')))
 TOL = 1e-4
 needs_goldens = pytest.mark.skipif(not CASES, reason='no tests/golden/tf18/* (run tools/tf18_dump.py in a TF-1.8 env)')
 
@@ -43,6 +46,25 @@ def test_checkpoint_written_by_tensorflow_restores_and_oracle_matches(case):
     _check_oracle_case(case)
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/nabu'), reason='the reference tree exists in the build container only')
+def test_committed_shim_cases_are_what_the_reference_code_produces(tmp_path):
+    """provenance of tests/golden/tf18shim_cases: re-run the generator (the reference's own Python from /root/reference
+    over tests/golden/tf18shim) for two cases and compare every array with the committed files"""
+    import subprocess
+    import sys
+    names = ['las_windowed_pyramid3', 'dblstm_ctc']
+    env = dict(os.environ, NABU_SHIM_OUT=str(tmp_path))
+    subprocess.run([sys.executable, os.path.join(_GOLDEN, 'make_tf18shim_golden.py')] + names, check=True, env=env,
+                   stdout=subprocess.DEVNULL)
+    for name in names:
+        for fname in ('inputs.npz', 'outputs.npz'):
+            new = np.load(os.path.join(str(tmp_path), name, fname))
+            old = np.load(os.path.join(_GOLDEN, 'tf18shim_cases', name, fname))
+            assert sorted(new.files) == sorted(old.files)
+            for k in new.files:
+                assert np.array_equal(new[k], old[k]), (name, fname, k)
+
+
 def _check_oracle_case(case):
     conf, inp, out = _load(case)
     model = _model(conf, 'cpu', case, inp['features'].shape[2])
@@ -51,7 +73,7 @@ def _check_oracle_case(case):
     mc, tc = conf['model.cfg'], conf['trainer.cfg']
     kind = (mc.get('encoder', 'encoder'), mc.get('decoder', 'decoder'), tc.get('trainer', 'loss'))
     if kind == ('listener', 'speller', 'average_cross_entropy'):
-        return _check_las_oracle(mc, params, inp, out)
+        return _check_las_oracle(mc, params, inp, out, conf['recognizer.cfg'])
     if kind != ('dblstm', 'dnn_decoder', 'CTC'):
         pytest.skip('no oracle composition for %s / %s / %s' % kind)
     i_name, o_name = mc.get('io', 'inputs').split(' ')[0], mc.get('io', 'outputs').split(' ')[0]
@@ -123,8 +145,20 @@ def _las_oracle(mc, params, inp):
     return logits, loss, gsp, glayers
 
 
-def _check_las_oracle(mc, params, inp, out):
+def _check_las_oracle(mc, params, inp, out, rc=None):
     logits, loss, gsp, glayers = _las_oracle(mc, params, inp)
+    if rc is not None and 'decoded_sequences' in out:          # the reference's BeamSearchDecoder, ids bit-exact
+        layers, sp, kw, steps = _las_params(mc, params)
+        enc, elens, _ = O.listener_fwd(inp['features'], inp['features_len'], layers, steps)
+        get = lambda k, d: float(rc.get('decoder', k)) if rc.has_option('decoder', k) else d    # noqa: E731
+        seqs, lens, scores, aligns = O.las_beam_search(
+            enc.astype(np.float32), elens, sp, int(rc.get('decoder', 'beam_width')), int(rc.get('decoder', 'max_steps')),
+            kw['attention'], kw['num_layers'], get('length_penalty', 1.0), get('temperature', 1.0), np.float32,
+            kw['probability_fn'], kw['window'])
+        assert np.array_equal(lens, out['decoded_lengths'])
+        assert seqs.shape == out['decoded_sequences'].shape and np.array_equal(seqs, out['decoded_sequences'])
+        assert rel_err(scores, out['decoded_scores']) < TOL
+        assert aligns.shape == out['decoded_alignments'].shape and rel_err(aligns, out['decoded_alignments']) < TOL
     for b, n in enumerate(inp['targets_len']):
         assert rel_err(logits[b, :n], out['logits'][b, :n]) < TOL
     assert abs(loss - float(out['loss'])) / abs(float(out['loss'])) < TOL
