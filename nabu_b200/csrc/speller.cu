@@ -10,6 +10,7 @@
 //           (step, row) pairs (the per-step kernels only produce dz / dq / per-row partials).
 // Rows whose target is shorter than U are frozen after their last step (state copied through, zero
 // logits), exactly like impute_finished=True; their gradients are zero.
+#include <cooperative_groups.h>
 #include "speller_kernels.cuh"
 #include "speller_api.h"
 #include "gemm.h"
@@ -147,14 +148,22 @@ struct AttnBwdArgs {
 constexpr int TT = 16;     // memory positions per dpre tile
 constexpr int MAXF = 16;   // max numfilt held in registers
 
-// 512 threads per row.  TSPLIT = 2 (A <= 256): thread (unit c = tid % 256, half th = tid / 256) takes the tile's positions
+// 512 threads per CTA.  TSPLIT = 2 (A <= 256): thread (unit c = tid % 256, half th = tid / 256) takes the tile's positions
 // of parity th in the score backward; TSPLIT = 1 (A <= 512): one unit per thread.
-template <int TSPLIT>
-__global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArgs a) {
+// CS = CTAs per decoder row (a thread-block cluster, round 2): with one CTA per row a batch of 64 rows runs on 64 of the
+// 148 SMs at 16 warps each and the kernel is bound by instruction issue and load latency.  The memory positions of a row
+// are cut into CS contiguous ranges (multiples of TT); a CTA runs phases B-D on its range; the softmax dot product, the
+// per-unit sums dq / dv / dWd and the rows of dcf are exchanged through distributed shared memory (two cluster barriers);
+// the taus of the location backward, the taps of dWc and the output units of phase F are cut CS ways as well.
+template <int TSPLIT, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArgs a) {
   constexpr int NT = 512, NW = NT / 32, NA = 1;
   extern __shared__ __align__(16) float sm[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = blockIdx.x;
+  const int cr = CS > 1 ? (int)cluster.block_rank() : 0;
+  const int r = blockIdx.x / CS;
   const int Tm = a.Tm, E = a.E, H = a.H, A = a.A, V = a.V, F = a.F, ksz = a.ksz;
   const int padl = (ksz - 1) / 2;
   auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };   // every piece starts on a 16-byte boundary (attn_bwd_smem)
@@ -173,13 +182,23 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
   float* wd = dcf + r4((size_t)Tm * F);    // [F][A]
   float* wc = wd + r4((size_t)F * A);      // [ksz][F]
   float* dpre = wc + r4((size_t)ksz * F);  // [TT][A]
+  float* xdot = dpre + (size_t)TT * A;     // [CS] partial softmax dots, slot = source CTA           (CS > 1)
+  float* xch = xdot + 4;                   // [CS][2 + F][A] partial dq, dv, dWd, slot = source CTA   (CS > 1)
 
-  if (!(a.u < a.tlen[r])) {
-    for (int i = tid; i < H; i += NT) a.dh_above[(size_t)r * H + i] = 0.f;
-    for (int i = tid; i < A; i += NT) a.dq_save[(size_t)r * A + i] = 0.f;
+  if (!(a.u < a.tlen[r])) {                // the whole cluster leaves: no barrier has been touched yet
+    if (cr == 0) {
+      for (int i = tid; i < H; i += NT) a.dh_above[(size_t)r * H + i] = 0.f;
+      for (int i = tid; i < A; i += NT) a.dq_save[(size_t)r * A + i] = 0.f;
+    }
     return;
   }
+  // every CTA of the cluster is running before the first store into a peer's shared memory: arrive here, wait in phase C
+  if (CS > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   const int len = min(a.mem_len[r], Tm);
+  // this CTA's memory positions [tb, te), output taus [ub, ue)
+  const int per = CS > 1 ? ((len + CS * TT - 1) / (CS * TT)) * TT : len;
+  const int tb = min(len, cr * per), te = min(len, tb + per);
+  const int uper = (Tm + CS - 1) / CS, ub = min(Tm, cr * uper), ue = min(Tm, ub + uper);
   for (int i = tid; i < V; i += NT) dl[i] = a.dlogits[r * a.dl_row_stride + i];
   for (int i = tid; i < H + E; i += NT) oin[i] = a.outin[r * a.outin_row_stride + i];
   for (int i = tid; i < Tm; i += NT) al[i] = a.alpha[(size_t)r * Tm + i];
@@ -188,12 +207,12 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
     ap[i] = (F > 0 && t >= 0 && t < Tm) ? a.alpha_prev[(size_t)r * Tm + t] : 0.f;
   }
   for (int i = tid; i < A; i += NT) qs[i] = a.q[(size_t)r * A + i];
-  for (int i = tid; i < Tm * F; i += NT) cf[i] = a.cf[(size_t)r * Tm * F + i];
+  for (int i = tb * F + tid; i < te * F; i += NT) cf[i] = a.cf[(size_t)r * Tm * F + i];
   for (int i = tid; i < F * A; i += NT) wd[i] = a.Wd[i];
   for (int i = tid; i < ksz * F; i += NT) wc[i] = a.Wc[i];
   __syncthreads();
 
-  // phase A: d[h_top, ctx] = dlogits . Wo^T ; dctx += carry
+  // phase A: d[h_top, ctx] = dlogits . Wo^T ; dctx += carry   (every CTA of the row computes all of it: it is small)
   for (int k = tid; k < H + E; k += NT) {
     float s = 0.f;
     for (int vv = 0; vv < V; ++vv) s = fmaf(dl[vv], a.Wo[(size_t)k * V + vv], s);
@@ -205,58 +224,65 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
   const float* values = a.values + (size_t)r * Tm * E;
   float* dvalues = a.dvalues + (size_t)r * Tm * E;
   const bool vecE = (E & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.values) | reinterpret_cast<uintptr_t>(a.dvalues)) & 15) == 0;
-  for (int t = warp; t < Tm; t += NW) {
+  for (int t = tb + warp; t < te; t += NW) {
     float s = 0.f;
-    if (t < len) {
-      const float at = al[t];
-      if (vecE && E <= 512) {
-        // all of this position's loads (values and the dvalues accumulator) are issued before the first use: the old
-        // scalar read-modify-write loop was a chain of E/32 dependent L2 round trips per position
-        const float4* vp = reinterpret_cast<const float4*>(values + (size_t)t * E);
-        float4* dp = reinterpret_cast<float4*>(dvalues + (size_t)t * E);
-        float4 xv[4], xd[4];
+    const float at = al[t];
+    if (vecE && E <= 512) {
+      // all of this position's loads (values and the dvalues accumulator) are issued before the first use: the old
+      // scalar read-modify-write loop was a chain of E/32 dependent L2 round trips per position
+      const float4* vp = reinterpret_cast<const float4*>(values + (size_t)t * E);
+      float4* dp = reinterpret_cast<float4*>(dvalues + (size_t)t * E);
+      float4 xv[4], xd[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i4 = lane + 32 * j;
-          if (i4 * 4 < E) { xv[j] = __ldg(vp + i4); xd[j] = dp[i4]; }
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int i4 = lane + 32 * j;
+        if (i4 * 4 < E) { xv[j] = __ldg(vp + i4); xd[j] = dp[i4]; }
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i4 = lane + 32 * j;
-          if (i4 * 4 < E) {
-            const float4 dc = *reinterpret_cast<const float4*>(dctx + i4 * 4);
-            s += (dc.x * xv[j].x + dc.y * xv[j].y) + (dc.z * xv[j].z + dc.w * xv[j].w);
-            xd[j].x = fmaf(at, dc.x, xd[j].x); xd[j].y = fmaf(at, dc.y, xd[j].y);
-            xd[j].z = fmaf(at, dc.z, xd[j].z); xd[j].w = fmaf(at, dc.w, xd[j].w);
-            dp[i4] = xd[j];
-          }
-        }
-      } else {
-        for (int i = lane; i < E; i += 32) {
-          s = fmaf(dctx[i], values[(size_t)t * E + i], s);
-          dvalues[(size_t)t * E + i] += at * dctx[i];
+      for (int j = 0; j < 4; ++j) {
+        const int i4 = lane + 32 * j;
+        if (i4 * 4 < E) {
+          const float4 dc = *reinterpret_cast<const float4*>(dctx + i4 * 4);
+          s += (dc.x * xv[j].x + dc.y * xv[j].y) + (dc.z * xv[j].z + dc.w * xv[j].w);
+          xd[j].x = fmaf(at, dc.x, xd[j].x); xd[j].y = fmaf(at, dc.y, xd[j].y);
+          xd[j].z = fmaf(at, dc.z, xd[j].z); xd[j].w = fmaf(at, dc.w, xd[j].w);
+          dp[i4] = xd[j];
         }
       }
-      s = warp_sum(s);
+    } else {
+      for (int i = lane; i < E; i += 32) {
+        s = fmaf(dctx[i], values[(size_t)t * E + i], s);
+        dvalues[(size_t)t * E + i] += at * dctx[i];
+      }
     }
-    if (lane == 0) dal[t] = (t < len) ? s + a.dalign_carry[(size_t)r * Tm + t] : 0.f;
+    s = warp_sum(s);
+    if (lane == 0) dal[t] = s + a.dalign_carry[(size_t)r * Tm + t];
   }
   __syncthreads();
-  // phase C: probability function backward (components/attention.py:9-13, 41-55)
+  // phase C: probability function backward (components/attention.py:9-13, 41-55), positions [tb, te)
   //   softmax:             de = alpha * (dalpha - sum alpha*dalpha)
   //   normalized_sigmoid:  alpha = s / S  ->  de = (dalpha - sum alpha*dalpha) / S * s * (1 - s),  s = alpha * S
   //   sigmoid:             de = dalpha * alpha * (1 - alpha)
   if (a.prob == 2) {
-    for (int t = tid; t < Tm; t += NT) dal[t] = dal[t] * al[t] * (1.f - al[t]);
+    for (int t = tb + tid; t < te; t += NT) dal[t] = dal[t] * al[t] * (1.f - al[t]);
+    if (CS > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
   } else {
     float part = 0.f;
-    for (int t = tid; t < Tm; t += NT) part += al[t] * dal[t];
-    const float dot = block_reduce(part, red, false);
+    for (int t = tb + tid; t < te; t += NT) part += al[t] * dal[t];
+    float dot = block_reduce(part, red, false);
+    if (CS > 1) {
+      asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+      if (tid < CS) *cluster.map_shared_rank(xdot + cr, tid) = dot;      // my partial into slot cr of every CTA
+      cluster.sync();
+      dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) dot += xdot[c];
+    }
     if (a.prob == 0) {
-      for (int t = tid; t < Tm; t += NT) dal[t] = al[t] * (dal[t] - dot);
+      for (int t = tb + tid; t < te; t += NT) dal[t] = al[t] * (dal[t] - dot);
     } else {
       const float S = a.asum[r], iS = 1.f / S;
-      for (int t = tid; t < Tm; t += NT) {
+      for (int t = tb + tid; t < te; t += NT) {
         const float sg = al[t] * S;
         dal[t] = (dal[t] - dot) * iS * sg * (1.f - sg);
       }
@@ -278,8 +304,8 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
       wdreg[i][f] = (f < F && c < A) ? wd[f * A + c] : 0.f;   // this thread's column of Wd: constant over the positions
     }
   }
-  for (int t0 = 0; t0 < len; t0 += TT) {
-    const int nt = min(TT, len - t0);
+  for (int t0 = tb; t0 < te; t0 += TT) {
+    const int nt = min(TT, te - t0);
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
       const int c = TSPLIT == 2 ? (tid & 255) : tid;
@@ -319,7 +345,8 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
     }
     __syncthreads();
     // dcf[t][f] = sum_c dpre[t][c] * Wd[f][c]: one warp per memory position, lanes stride the attention units (both
-    // operands are then read at consecutive addresses; the (t, f)-per-thread mapping hit one bank with 10 lanes)
+    // operands are then read at consecutive addresses; the (t, f)-per-thread mapping hit one bank with 10 lanes).
+    // The row goes to every CTA of the cluster (phase E needs the neighbours' rows within the filter's reach).
     if (!(a.ablate & 1))
     for (int tt = warp; tt < nt; tt += NW) {
       float acc0[MAXF];
@@ -335,7 +362,11 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
       for (int f = 0; f < MAXF; ++f)
         if (f < F) {
           const float s0 = warp_sum(acc0[f]);
-          if (lane == 0) dcf[(t0 + tt) * F + f] = s0;
+          if (CS == 1) {
+            if (lane == 0) dcf[(t0 + tt) * F + f] = s0;
+          } else if (lane < CS) {
+            *cluster.map_shared_rank(dcf + (t0 + tt) * F + f, lane) = s0;
+          }
         }
     }
     __syncthreads();
@@ -353,28 +384,67 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
         if (f < F) dpre[(2 + f) * A + c] = dWd[0][f];
     }
     __syncthreads();
+    float q0 = dq[0], v0 = dv[0];
     if (th == 0 && c < A) {
-      float q0 = dq[0], v0 = dv[0];
-      if (TSPLIT == 2) { q0 += dpre[c]; v0 += dpre[A + c]; }
+      if (TSPLIT == 2) {
+        q0 += dpre[c]; v0 += dpre[A + c];
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f)
+          if (f < F) dWd[0][f] += dpre[(2 + f) * A + c];
+      }
+      if (CS > 1) {                          // this CTA's sums into slot cr of every other CTA
+        const size_t slot = (size_t)cr * (2 + F) * A;
+        for (int pc = 0; pc < CS; ++pc) {
+          if (pc == cr) continue;
+          float* px = cluster.map_shared_rank(xch, pc) + slot;
+          px[c] = q0;
+          px[A + c] = v0;
+#pragma unroll
+          for (int f = 0; f < MAXF; ++f)
+            if (f < F) px[(2 + f) * A + c] = dWd[0][f];
+        }
+      }
+    }
+    if (CS > 1) cluster.sync();              // the sums and every CTA's rows of dcf have arrived; no remote access after this
+    if (th == 0 && c < A) {
+      if (CS > 1) {
+        // summed in CTA order whatever the CTA, so that every CTA of the row holds the same bits of dq
+        float qs_ = 0.f, vs_ = 0.f, ws_[MAXF];
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) ws_[f] = 0.f;
+        for (int pc = 0; pc < CS; ++pc) {
+          const float* px = xch + (size_t)pc * (2 + F) * A;
+          qs_ += pc == cr ? q0 : px[c];
+          vs_ += pc == cr ? v0 : px[A + c];
+#pragma unroll
+          for (int f = 0; f < MAXF; ++f)
+            if (f < F) ws_[f] += pc == cr ? dWd[0][f] : px[(2 + f) * A + c];
+        }
+        q0 = qs_; v0 = vs_;
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) dWd[0][f] = ws_[f];
+      }
       dqs[c] = q0;
-      a.dq_save[(size_t)r * A + c] = q0;
-      a.dv_part[(size_t)r * A + c] += v0;
+      if (cr == 0) {
+        a.dq_save[(size_t)r * A + c] = q0;
+        a.dv_part[(size_t)r * A + c] += v0;
+      }
 #pragma unroll
       for (int f = 0; f < MAXF; ++f)
-        if (f < F) a.dWd_part[((size_t)r * F + f) * A + c] += dWd[0][f] + (TSPLIT == 2 ? dpre[(2 + f) * A + c] : 0.f);
+        if (f < F && f % CS == cr) a.dWd_part[((size_t)r * F + f) * A + c] += dWd[0][f];
     }
   }
   __syncthreads();
-  // phase E: location-feature backward
+  // phase E: location-feature backward, taus [ub, ue) and every CS-th tap product of dWc
   if (F > 0 && !(a.ablate & 2)) {
     // dalign_prev[tau] = sum_{k,f} dcf[tau - k + padl][f] * Wc[k][f]
-    // (the taps are split over the two halves of the block; partial sums meet in the dpre scratch)
+    // (the taps are split over the groups of 128 threads; partial sums meet in the dpre scratch)
     {
       constexpr int NG = NT / 128;                      // tap groups
       const bool split2 = NG * Tm <= TT * A;            // room for every group's partial sums in the scratch
       const int half = split2 ? tid >> 7 : 0, kh = split2 ? (ksz + NG - 1) / NG : ksz;
       const int k0 = half * kh, k1 = min(ksz, k0 + kh);
-      for (int tau = split2 ? (tid & 127) : tid; tau < Tm; tau += split2 ? 128 : NT) {
+      for (int tau = ub + (split2 ? (tid & 127) : tid); tau < ue; tau += split2 ? 128 : NT) {
         float s = 0.f;
         for (int k = k0; k < k1; ++k) {
           const int t = tau - k + padl;
@@ -397,7 +467,7 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
       }
       __syncthreads();
       if (split2)
-        for (int tau = tid; tau < Tm; tau += NT) {
+        for (int tau = ub + tid; tau < ue; tau += NT) {
           float s = 0.f;
 #pragma unroll
           for (int gq = 0; gq < NG; ++gq) s += dpre[gq * Tm + tau];
@@ -405,17 +475,17 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
         }
     }
     // dWc[k][f] += sum_t alpha_prev[t + k - padl] * dcf[t][f]
-    for (int i = tid; i < ksz * F; i += NT) {
+    for (int i = cr + CS * tid; i < ksz * F; i += CS * NT) {
       const int k = i / F, f = i % F;
       float s = 0.f;
       for (int t = 0; t < Tm; ++t) s = fmaf(ap[t + k], dcf[t * F + f], s);
       a.dWc_part[(size_t)r * ksz * F + i] += s;
     }
   } else {
-    for (int tau = tid; tau < Tm; tau += NT) a.dalign_carry[(size_t)r * Tm + tau] = 0.f;
+    for (int tau = ub + tid; tau < ue; tau += NT) a.dalign_carry[(size_t)r * Tm + tau] = 0.f;
   }
-  // phase F: dh_top = dquery_part + dq . Wq^T   (warp per output unit, lanes over A)
-  for (int k = warp; k < H; k += 4 * NW) {               // 4 output units per warp iteration: independent load chains
+  // phase F: dh_top = dquery_part + dq . Wq^T   (warp per output unit, lanes over A; the CTAs take turns over the groups)
+  for (int k = warp + cr * 4 * NW; k < H; k += CS * 4 * NW) {      // 4 output units per warp iteration: independent load chains
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = lane; c < A; c += 32) {
       const float dqc = dqs[c];
@@ -431,10 +501,32 @@ __global__ void __launch_bounds__(512) dec_attn_bwd_step_kernel(const AttnBwdArg
   }
 }
 
-inline size_t attn_bwd_smem(int Tm, int E, int H, int A, int V, int F, int ksz) {
+inline size_t attn_bwd_smem(int Tm, int E, int H, int A, int V, int F, int ksz, int cs = 4) {
   auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
   return (r4(V) + r4(H + E) + r4(E) + r4(H) + r4(Tm) + r4(Tm + ksz) + r4(Tm) + r4(A) + r4(A) + 32 + 2 * r4((size_t)Tm * F) +
-          r4((size_t)F * A) + r4((size_t)ksz * F) + (size_t)TT * A) * sizeof(float);
+          r4((size_t)F * A) + r4((size_t)ksz * F) + (size_t)TT * A + 4 + (cs > 1 ? (size_t)cs * (2 + F) * A : 0)) * sizeof(float);
+}
+
+// CTAs per decoder row: as many as keep the grid within one wave of the 148 SMs (NABU_ATTN_BWD_CLUSTER=1|2|4 forces)
+inline int attn_bwd_cluster(int rows) {
+  static int forced = -1;
+  if (forced < 0) forced = getenv("NABU_ATTN_BWD_CLUSTER") ? atoi(getenv("NABU_ATTN_BWD_CLUSTER")) : 0;
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  return rows * 4 <= 160 ? 4 : rows * 2 <= 160 ? 2 : 1;
+}
+
+// the kernel for (A, CTAs per row); its dynamic shared memory limit raised once per variant
+inline int attn_bwd_launch(const AttnBwdArgs& a, int rows, cudaStream_t stream) {
+  const int cs = attn_bwd_cluster(rows);
+  const size_t smem = attn_bwd_smem(a.Tm, a.E, a.H, a.A, a.V, a.F, a.ksz, cs);
+  NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "attention backward: memory too long for the kernel (Tm=%d)", a.Tm);
+  void (*fn)(const AttnBwdArgs) =
+      a.A <= 256 ? (cs == 4 ? dec_attn_bwd_step_kernel<2, 4> : cs == 2 ? dec_attn_bwd_step_kernel<2, 2> : dec_attn_bwd_step_kernel<2, 1>)
+                 : (cs == 4 ? dec_attn_bwd_step_kernel<1, 4> : cs == 2 ? dec_attn_bwd_step_kernel<1, 2> : dec_attn_bwd_step_kernel<1, 1>);
+  if (smem > 48 * 1024) NABU_CHECK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<rows * cs, 512, smem, stream>>>(a);
+  NABU_CHECK_LAUNCH();
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -699,11 +791,6 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
   const int H4 = 4 * H;
   NABU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, stream));
 
-  const size_t smem_attn = attn_bwd_smem(Tm, E, H, A, V, F, ksz);
-  NABU_REQUIRE(smem_attn <= (size_t)max_smem_optin(), "speller_bwd: memory too long for the attention kernel (Tm=%d)", Tm);
-  const void* attn_fn = A <= 256 ? (const void*)dec_attn_bwd_step_kernel<2> : (const void*)dec_attn_bwd_step_kernel<1>;
-  if (smem_attn > 48 * 1024)
-    NABU_CHECK_CUDA(cudaFuncSetAttribute(attn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn));
   const size_t smem_mm = ((size_t)H4 * 8 + MT_KSPLIT * ROWS * 8) * sizeof(float);
   NABU_REQUIRE(smem_mm <= (size_t)max_smem_optin(), "speller_bwd: num_units too large");
   if (smem_mm > 48 * 1024)
@@ -725,9 +812,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
       a.ablate = getenv("NABU_ATTN_ABLATE") ? atoi(getenv("NABU_ATTN_ABLATE")) : 0;
       a.prob = d.probability_fn; a.asum = s.asum + (size_t)u * B;
       KernelScope ks("dec_attn_bwd_step", stream);
-      if (A <= 256) dec_attn_bwd_step_kernel<2><<<B, 512, smem_attn, stream>>>(a);
-      else dec_attn_bwd_step_kernel<1><<<B, 512, smem_attn, stream>>>(a);
-      NABU_CHECK_LAUNCH();
+      if (int e = attn_bwd_launch(a, B, stream)) return e;
     }
     for (int l = NL - 1; l >= 0; --l) {
       {
@@ -908,11 +993,6 @@ extern "C" int nabu_attn_step_bwd(const nabu_speller_desc_t* dp, const nabu_spel
   // contribution through the context and leaves d(align_prev) in the same buffer
   if (dalign_new) NABU_CHECK_CUDA(cudaMemcpyAsync(dalign_prev, dalign_new, (size_t)R * Tm * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   else NABU_CHECK_CUDA(cudaMemsetAsync(dalign_prev, 0, (size_t)R * Tm * sizeof(float), stream));
-  const size_t smem_attn = attn_bwd_smem(Tm, E, H, A, V, F, ksz);
-  NABU_REQUIRE(smem_attn <= (size_t)max_smem_optin(), "attn_step_bwd: memory too long for the attention kernel (Tm=%d)", Tm);
-  const void* attn_fn = A <= 256 ? (const void*)dec_attn_bwd_step_kernel<2> : (const void*)dec_attn_bwd_step_kernel<1>;
-  if (smem_attn > 48 * 1024)
-    NABU_CHECK_CUDA(cudaFuncSetAttribute(attn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attn));
   AttnBwdArgs a = {};
   a.R = R; a.Tm = Tm; a.E = E; a.H = H; a.A = A; a.V = V; a.F = F; a.ksz = ksz; a.U = 1; a.u = 0;
   a.dlogits = w.dlogits; a.dl_row_stride = V;                   // zeros: the projection's backward contributes nothing
@@ -927,9 +1007,7 @@ extern "C" int nabu_attn_step_bwd(const nabu_speller_desc_t* dp, const nabu_spel
   a.tlen = w.tlen; a.prob = d.probability_fn; a.asum = asum_save;
   {
     KernelScope ks("dec_attn_bwd_step", stream);
-    if (A <= 256) dec_attn_bwd_step_kernel<2><<<R, 512, smem_attn, stream>>>(a);
-    else dec_attn_bwd_step_kernel<1><<<R, 512, smem_attn, stream>>>(a);
-    NABU_CHECK_LAUNCH();
+    if (int e = attn_bwd_launch(a, R, stream)) return e;
   }
   // this step's parameter gradients (overwritten, not accumulated): query layer, attention vector, location layers
   if (int e = gemm(GEMM_TN, H, A, R, 1.f, query, H, w.dq, A, 0.f, g->query_kernel, A, nullptr, nullptr, w.gemm, w.gemm_bytes, stream))
