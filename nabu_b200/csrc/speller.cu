@@ -94,6 +94,7 @@ __global__ void dec_lstm_bwd_pointwise_kernel(float* gates /*[R][4H] in: i,g,f,o
                                               const float* c_prev, const float* dh_above, const float* dh_carry,
                                               float* dc_carry, float* dzT /*[4H][R]*/, int R, int H,
                                               const int* tlen, int u, float keep, unsigned seed, int layer) {
+  chain_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * H) return;
   const int r = i / H, j = i % H;
@@ -186,6 +187,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
   float* xch = xdot + 4;                   // [CS][2 + F][A] partial dq, dv, dWd, slot = source CTA   (CS > 1)
 
   if (!(a.u < a.tlen[r])) {                // the whole cluster leaves: no barrier has been touched yet
+    chain_wait();
     if (cr == 0) {
       for (int i = tid; i < H; i += NT) a.dh_above[(size_t)r * H + i] = 0.f;
       for (int i = tid; i < A; i += NT) a.dq_save[(size_t)r * A + i] = 0.f;
@@ -217,8 +219,12 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
     float s = 0.f;
     for (int vv = 0; vv < V; ++vv) s = fmaf(dl[vv], a.Wo[(size_t)k * V + vv], s);
     if (k < H) dquery[k] = s;
-    else dctx[k - H] = s + a.dctx_carry[(size_t)r * E + (k - H)];
+    else dctx[k - H] = s;
   }
+  // everything above read the forward's saved tensors and weights only and ran next to the previous kernel of the chain
+  chain_wait();
+  __syncthreads();
+  for (int i = tid; i < E; i += NT) dctx[i] += a.dctx_carry[(size_t)r * E + i];
   __syncthreads();
   // phase B: dalpha[t] = dctx . values[t] + carry ; dvalues[t] += alpha[t] * dctx
   const float* values = a.values + (size_t)r * Tm * E;
@@ -524,8 +530,7 @@ inline int attn_bwd_launch(const AttnBwdArgs& a, int rows, cudaStream_t stream) 
       a.A <= 256 ? (cs == 4 ? dec_attn_bwd_step_kernel<2, 4> : cs == 2 ? dec_attn_bwd_step_kernel<2, 2> : dec_attn_bwd_step_kernel<2, 1>)
                  : (cs == 4 ? dec_attn_bwd_step_kernel<1, 4> : cs == 2 ? dec_attn_bwd_step_kernel<1, 2> : dec_attn_bwd_step_kernel<1, 1>);
   if (smem > 48 * 1024) NABU_CHECK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fn<<<rows * cs, 512, smem, stream>>>(a);
-  NABU_CHECK_LAUNCH();
+  NABU_CHECK_CUDA(chain_launch(fn, dim3(rows * cs), dim3(512), smem, stream, a));
   return 0;
 }
 
@@ -661,8 +666,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
     if (smem > 48 * 1024)
       NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelScope ks("dec_lstm_step", stream);
-    dec_lstm_step_kernel<<<dim3(H / 2, ceil_div(R, ROWS)), SK_THREADS, smem, stream>>>(a);
-    NABU_CHECK_LAUNCH();
+    NABU_CHECK_CUDA(chain_launch(dec_lstm_step_kernel, dim3(H / 2, ceil_div(R, ROWS)), dim3(SK_THREADS), smem, stream, a));
   }
   AttnStepArgs a = {};
   a.R = R; a.Tm = d.Tm; a.E = E; a.H = H; a.A = d.A; a.V = V;
@@ -684,8 +688,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
   if (smem > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelScope ks("dec_attn_step", stream);
-  dec_attn_step_kernel<<<R, 512, smem, stream>>>(a);
-  NABU_CHECK_LAUNCH();
+  NABU_CHECK_CUDA(chain_launch(dec_attn_step_kernel, dim3(R), dim3(512), smem, stream, a));
   return 0;
 }
 
@@ -817,18 +820,16 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
     for (int l = NL - 1; l >= 0; --l) {
       {
         KernelScope ks("dec_lstm_bwd_pointwise", stream);
-        dec_lstm_bwd_pointwise_kernel<<<ceil_div(B * H, 256), 256, 0, stream>>>(
+        NABU_CHECK_CUDA(chain_launch(dec_lstm_bwd_pointwise_kernel, dim3(ceil_div(B * H, 256)), dim3(256), 0, stream,
             s.gates[l] + (size_t)u * B * H4, s.c[l] + (size_t)(u + 1) * B * H, s.c[l] + (size_t)u * B * H, w.dh_above,
-            w.dh_carry[l], w.dc_carry[l], w.dzT, B, H, target_len, u, d.dropout_keep, d.seed, l);
-        NABU_CHECK_LAUNCH();
+            w.dh_carry[l], w.dc_carry[l], w.dzT, B, H, target_len, u, d.dropout_keep, d.seed, l));
       }
       MatmulTArgs m = {};
       m.xT = w.dzT; m.K = H4; m.R = B; m.W = p->cell_kernel[l]; m.ldw = H4;
       if (l > 0) { m.row0 = 0; m.N = 2 * H; m.N0 = H; m.out0 = w.dh_above; m.ld0 = H; m.out1 = w.dh_carry[l]; m.ld1 = H; }
       else { m.row0 = V; m.N = E + H; m.N0 = E; m.out0 = w.dctx_carry; m.ld0 = E; m.out1 = w.dh_carry[0]; m.ld1 = H; }
       KernelScope ks("dec_matmul_t", stream);
-      dec_matmul_t_kernel<<<dim3(ceil_div(m.N, 8), ceil_div(B, ROWS)), MT_THREADS, smem_mm, stream>>>(m);
-      NABU_CHECK_LAUNCH();
+      NABU_CHECK_CUDA(chain_launch(dec_matmul_t_kernel, dim3(ceil_div(m.N, 8), ceil_div(B, ROWS)), dim3(MT_THREADS), smem_mm, stream, m));
     }
   }
   // ---- batched weight gradients over all (step, row) pairs --------------------------------------
@@ -968,8 +969,7 @@ extern "C" int nabu_attn_step_fwd(const nabu_speller_desc_t* dp, const nabu_spel
   if (smem > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelScope ks("dec_attn_step", stream);
-  dec_attn_step_kernel<<<R, 512, smem, stream>>>(a);
-  NABU_CHECK_LAUNCH();
+  NABU_CHECK_CUDA(chain_launch(dec_attn_step_kernel, dim3(R), dim3(512), smem, stream, a));
   return 0;
 }
 

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include <stdint.h>
 #include <math_constants.h>
+#include <stdlib.h>
+#include <utility>
 
 namespace nabu {
 namespace dec {
@@ -44,6 +46,36 @@ constexpr int MT_THREADS = 256;                // dec_matmul_t: measured slower 
 constexpr int MT_KSPLIT = MT_THREADS / ROWS;
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch of the decoder's chain of small kernels (round 2).  A decoder step is a chain of
+// kernels of 10-80 us, each of which begins by staging weights (or, for the attention step, by the location features,
+// which depend on the PREVIOUS step's alignments only).  Launched with the programmatic-stream-serialization attribute,
+// kernel N+1 starts as soon as every CTA of kernel N has passed chain_wait(), runs its prologue next to N's body and
+// blocks in its own chain_wait() until N has completed and flushed.  Rule for every kernel of the chain: before
+// chain_wait() it reads only what was complete two kernels ago (weights, saved forward tensors, the previous step's
+// alignments - kernel N has itself waited for N-1) and writes nothing but its own shared memory.  NABU_PDL=0 launches
+// the same kernels without the attribute (chain_wait() is then a no-op).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void chain_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline bool chain_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("NABU_PDL") ? atoi(getenv("NABU_PDL")) : 1;
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t chain_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = chain_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // LSTM cell step.  grid = (H/2, ceil(R/ROWS)); CTA (slice, tile) owns hidden units 2*slice,
 // 2*slice+1 (8 gate columns) for ROWS rows; SK_KSPLIT-way k-split over the SK_THREADS threads.
 // ------------------------------------------------------------------------------------------------
@@ -67,7 +99,6 @@ struct LstmStepArgs {
 
 __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmStepArgs a) {
   extern __shared__ __align__(16) float sm[];
-  if (a.done && *a.done) return;
   const int Ktot = a.K0 + a.K1;
   float* Ws = sm;                          // [Ktot][8]
   float* red = sm + (size_t)Ktot * 8;      // [SK_KSPLIT][ROWS][8]
@@ -80,6 +111,8 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
     const int wrow = k < a.K0 ? a.w0 + k : a.w1 + (k - a.K0);
     Ws[i] = a.W[(size_t)wrow * H4 + (c >> 1) * H + j0 + (c & 1)];
   }
+  chain_wait();                            // the weight slice was staged next to the previous kernel
+  if (a.done && *a.done) return;
   __syncthreads();
   const int rl = tid % ROWS, ks = tid / ROWS;
   const int r = r0 + rl;
@@ -183,7 +216,6 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a) {
   constexpr int NT = 512, NW = NT / 32;                // 512 threads per decoder row
   extern __shared__ __align__(16) float sm[];
-  if (a.done && *a.done) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.x;
   const int mrow = r / a.rows_per_mem;
@@ -204,6 +236,27 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   float* cpart = vs + r4(A);               // [NT * 4] context partials of the t-splits
 
   const bool active = (a.tlen == nullptr) || (a.u < a.tlen[r]);
+  if (active) {
+    // prologue, next to the LSTM step that produces this step's query (see chain_wait): weights, the previous
+    // alignments (complete since the previous step) and phase 1, the location features
+    //   cf[t][f] = sum_k alpha_prev[t + k - padl] * Wc[k][f]
+    for (int i = tid; i < Tm + ksz; i += NT) {
+      const int t = i - padl;
+      ap[i] = ((F > 0 || a.win_left >= 0) && t >= 0 && t < Tm) ? __ldcg(a.align_prev + (size_t)r * Tm + t) : 0.f;
+    }
+    for (int i = tid; i < F * A; i += NT) wd[i] = a.Wd[i];
+    for (int i = tid; i < ksz * F; i += NT) wc[i] = a.Wc[i];
+    for (int i = tid; i < A; i += NT) vs[i] = a.v[i];
+    __syncthreads();
+    for (int i = tid; i < Tm * F; i += NT) {
+      const int t = i / F, f = i % F;
+      float s = 0.f;
+      for (int k = 0; k < ksz; ++k) s = fmaf(ap[t + k], wc[k * F + f], s);
+      cf[i] = s;
+    }
+  }
+  chain_wait();
+  if (a.done && *a.done) return;
   if (!active) {                           // finished row: copy the state through, emit zeros
     for (int t = tid; t < Tm; t += NT) a.align_new[(size_t)r * Tm + t] = a.align_prev[(size_t)r * Tm + t];
     for (int i = tid; i < E; i += NT) {
@@ -220,13 +273,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   const int len = min(a.mem_len[mrow], Tm);
 
   for (int i = tid; i < H; i += NT) query[i] = a.h_top[(size_t)r * H + i];
-  for (int i = tid; i < Tm + ksz; i += NT) {
-    const int t = i - padl;
-    ap[i] = ((F > 0 || a.win_left >= 0) && t >= 0 && t < Tm) ? a.align_prev[(size_t)r * Tm + t] : 0.f;
-  }
-  for (int i = tid; i < F * A; i += NT) wd[i] = a.Wd[i];
-  for (int i = tid; i < ksz * F; i += NT) wc[i] = a.Wc[i];
-  for (int i = tid; i < A; i += NT) vs[i] = a.v[i];
+  if (a.cf_save) for (int i = tid; i < Tm * F; i += NT) a.cf_save[(size_t)r * Tm * F + i] = cf[i];
   __syncthreads();
 
   // phase 0: q = query . Wq
@@ -245,14 +292,6 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     const float s = (s0 + s1) + (s2 + s3);
     q[c] = s;
     if (a.q_save) a.q_save[(size_t)r * A + c] = s;
-  }
-  // phase 1: location features cf[t][f] = sum_k alpha_prev[t + k - padl] * Wc[k][f]
-  for (int i = tid; i < Tm * F; i += NT) {
-    const int t = i / F, f = i % F;
-    float s = 0.f;
-    for (int k = 0; k < ksz; ++k) s = fmaf(ap[t + k], wc[k * F + f], s);
-    cf[i] = s;
-    if (a.cf_save) a.cf_save[(size_t)r * Tm * F + i] = s;
   }
   __syncthreads();
   // phase 2: scores e[t] = v . tanh(q + keys[t] + cf[t] . Wd), one warp per memory position, 128-bit loads of the keys
@@ -474,6 +513,7 @@ __global__ void __launch_bounds__(MT_THREADS) dec_matmul_t_kernel(const MatmulTA
     const int n = n0 + c;
     Ws[k * 8 + c] = (n < a.N) ? a.W[(size_t)(a.row0 + n) * a.ldw + k] : 0.f;
   }
+  chain_wait();                            // the weight slice was staged next to the previous kernel
   __syncthreads();
   const int rl = tid % ROWS, ks = tid / ROWS, r = r0 + rl;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
