@@ -90,37 +90,11 @@ __global__ void embedding_grad_kernel(const int* ids_in, const float* dz, int UR
 // ------------------------------------------------------------------------------------------------
 // backward of the LSTM pointwise part for one layer / step.  One thread per (r, j).
 // ------------------------------------------------------------------------------------------------
-__global__ void dec_lstm_bwd_pointwise_kernel(float* gates /*[R][4H] in: i,g,f,o ; out: dz*/, const float* c_new,
-                                              const float* c_prev, const float* dh_above, const float* dh_carry,
-                                              float* dc_carry, float* dzT /*[4H][R]*/, int R, int H,
-                                              const int* tlen, int u, float keep, unsigned seed, int layer) {
+__global__ void dec_lstm_bwd_pointwise_kernel(const LstmBwdPw p, const float* dh_above, int R, int H) {
   chain_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * H) return;
-  const int r = i / H, j = i % H;
-  float* gp = gates + (size_t)r * 4 * H + j;
-  const bool active = u < tlen[r];
-  float dz[4] = {0.f, 0.f, 0.f, 0.f};
-  if (active) {
-    const float ig = gp[0], gg = gp[H], fg = gp[2 * H], og = gp[3 * H];
-    // dh_above is the gradient wrt the cell OUTPUT (dropped), dh_carry wrt the state h
-    float dha = dh_above[i];
-    if (keep > 0.f && keep < 1.f)
-      dha = dec_uniform(seed, (uint32_t)(layer * 65536 + u), (uint32_t)r, (uint32_t)j) < keep ? dha / keep : 0.f;
-    const float dh = dha + dh_carry[i];
-    const float tc = tanhf(c_new[i]);
-    const float dc = dc_carry[i] + dh * og * (1.f - tc * tc);
-    dz[0] = dc * gg * ig * (1.f - ig);
-    dz[1] = dc * ig * (1.f - gg * gg);
-    dz[2] = dc * c_prev[i] * fg * (1.f - fg);
-    dz[3] = dh * tc * og * (1.f - og);
-    dc_carry[i] = dc * fg;
-  }
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    gp[g * H] = dz[g];
-    dzT[(size_t)(g * H + j) * R + r] = dz[g];
-  }
+  lstm_bwd_unit(p, R, H, i / H, i % H, dh_above[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -143,6 +117,7 @@ struct AttnBwdArgs {
   const int* tlen;
   int prob;                                          // probability_fn: 0 softmax, 1 normalized_sigmoid, 2 sigmoid
   const float* asum;                                 // [R] sum of sigmoids of this step (prob == 1)
+  LstmBwdPw pw;                                      // pw.gates != nullptr: dh_above goes straight through the top LSTM layer's cell backward
   int ablate;                                        // NABU_ATTN_ABLATE (profiling only, results are then wrong): 1 skip dcf, 2 skip the conv backward, 4 skip the score backward
 };
 
@@ -189,7 +164,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
   if (!(a.u < a.tlen[r])) {                // the whole cluster leaves: no barrier has been touched yet
     chain_wait();
     if (cr == 0) {
-      for (int i = tid; i < H; i += NT) a.dh_above[(size_t)r * H + i] = 0.f;
+      if (a.pw.gates) for (int i = tid; i < H; i += NT) lstm_bwd_unit(a.pw, a.R, H, r, i, 0.f);      // dz = 0 for this row
+      else for (int i = tid; i < H; i += NT) a.dh_above[(size_t)r * H + i] = 0.f;
       for (int i = tid; i < A; i += NT) a.dq_save[(size_t)r * A + i] = 0.f;
     }
     return;
@@ -502,8 +478,17 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float t = warp_sum(s[j]);
-      if (lane == 0 && k + NW * j < H) a.dh_above[(size_t)r * H + k + NW * j] = dquery[k + NW * j] + t;
+      if (lane == 0 && k + NW * j < H) {
+        if (a.pw.gates) dquery[k + NW * j] += t;             // finished below, one thread per unit
+        else a.dh_above[(size_t)r * H + k + NW * j] = dquery[k + NW * j] + t;
+      }
     }
+  }
+  if (a.pw.gates) {
+    // the top LSTM layer's cell backward on this CTA's units (group k / (4 NW) belongs to CTA group % CS)
+    __syncthreads();
+    for (int k = tid; k < H; k += NT)
+      if ((k / (4 * NW)) % CS == cr) lstm_bwd_unit(a.pw, a.R, H, r, k, dquery[k]);
   }
 }
 
@@ -582,7 +567,7 @@ Saved carve_saved(void* base, const nabu_speller_desc_t& d) {
 
 struct Work {         // backward scratch
   float* dh_carry[4]; float* dc_carry[4];     // [B][H]
-  float* dh_above; float* dzT;                // [B][H], [4H][B]
+  float* dh_above; float* dzT[4];             // [B][H], per layer [4H][B] (the fused cell backward of layer l-1 writes its dz while layer l's is still being read)
   float* dctx_carry; float* dalign_carry;     // [B][E], [B][Tm]
   float* dq; float* dkeys; float* dvalues;    // [U][B][A], [B][Tm][A], [B][Tm][E]
   float* dv_part; float* dWd_part; float* dWc_part;
@@ -608,7 +593,7 @@ Work carve_work(void* base, const nabu_speller_desc_t& d) {
   w.dWc_part = take(B * ksz * (F ? F : 1));
   w.zero_bytes = off;
   w.dh_above = take(B * H);
-  w.dzT = take(4 * H * B);
+  for (int l = 0; l < d.num_layers; ++l) w.dzT[l] = take(4 * H * B);
   w.dq = take(U * B * A);
   w.gemm = (float*)(p + off); w.gemm_bytes = sgemm_workspace_bytes(); off += w.gemm_bytes;
   w.total = off;
@@ -661,7 +646,7 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
     a.tlen = tlen; a.u = u; a.done = done;
     a.out_new = out_new ? out_new[l] : nullptr; a.outT_new = outT_new ? outT_new[l] : nullptr;
     a.keep = keep; a.seed = seed; a.layer = l;
-    const size_t smem = ((size_t)(a.K0 + a.K1) * 8 + SK_KSPLIT * ROWS * 8) * sizeof(float);
+    const size_t smem = ((size_t)(a.K0 + a.K1) * 8 + SK_KSPLIT * ROWS * 8) * sizeof(float) + dk_stage_bytes();
     NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: LSTM input too wide for the step kernel");
     if (smem > 48 * 1024)
       NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -794,13 +779,23 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
   const int H4 = 4 * H;
   NABU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, stream));
 
-  const size_t smem_mm = ((size_t)H4 * 8 + MT_KSPLIT * ROWS * 8) * sizeof(float);
+  const size_t smem_mm = ((size_t)H4 * 8 + MT_KSPLIT * ROWS * 8) * sizeof(float) + dk_stage_bytes();
   NABU_REQUIRE(smem_mm <= (size_t)max_smem_optin(), "speller_bwd: num_units too large");
   if (smem_mm > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_matmul_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mm));
 
+  // NABU_DEC_FUSE=0: the cell backward as a kernel of its own (round 1) instead of inside the kernels that produce its input
+  static const bool fuse = !(getenv("NABU_DEC_FUSE") && atoi(getenv("NABU_DEC_FUSE")) == 0);
   for (int u = U - 1; u >= 0; --u) {
+    auto pw_of = [&](int l) {
+      LstmBwdPw q = {};
+      q.gates = s.gates[l] + (size_t)u * B * H4; q.c_new = s.c[l] + (size_t)(u + 1) * B * H; q.c_prev = s.c[l] + (size_t)u * B * H;
+      q.dh_carry = w.dh_carry[l]; q.dc_carry = w.dc_carry[l]; q.dzT = w.dzT[l]; q.tlen = target_len; q.u = u;
+      q.keep = d.dropout_keep; q.seed = d.seed; q.layer = l;
+      return q;
+    };
     AttnBwdArgs a = {};
+    if (fuse) a.pw = pw_of(NL - 1);
     a.R = B; a.Tm = Tm; a.E = E; a.H = H; a.A = A; a.V = V; a.F = F; a.ksz = ksz; a.U = U; a.u = u;
     a.dlogits = dlogits + (size_t)u * V; a.dl_row_stride = (long)U * V;
     a.outin = s.outin + (size_t)u * (H + E); a.outin_row_stride = (long)U * (H + E);
@@ -818,16 +813,16 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
       if (int e = attn_bwd_launch(a, B, stream)) return e;
     }
     for (int l = NL - 1; l >= 0; --l) {
-      {
+      if (!fuse) {
         KernelScope ks("dec_lstm_bwd_pointwise", stream);
         NABU_CHECK_CUDA(chain_launch(dec_lstm_bwd_pointwise_kernel, dim3(ceil_div(B * H, 256)), dim3(256), 0, stream,
-            s.gates[l] + (size_t)u * B * H4, s.c[l] + (size_t)(u + 1) * B * H, s.c[l] + (size_t)u * B * H, w.dh_above,
-            w.dh_carry[l], w.dc_carry[l], w.dzT, B, H, target_len, u, d.dropout_keep, d.seed, l));
+                                     pw_of(l), (const float*)w.dh_above, B, H));
       }
       MatmulTArgs m = {};
-      m.xT = w.dzT; m.K = H4; m.R = B; m.W = p->cell_kernel[l]; m.ldw = H4;
+      m.xT = w.dzT[l]; m.K = H4; m.R = B; m.W = p->cell_kernel[l]; m.ldw = H4;
       if (l > 0) { m.row0 = 0; m.N = 2 * H; m.N0 = H; m.out0 = w.dh_above; m.ld0 = H; m.out1 = w.dh_carry[l]; m.ld1 = H; }
       else { m.row0 = V; m.N = E + H; m.N0 = E; m.out0 = w.dctx_carry; m.ld0 = E; m.out1 = w.dh_carry[0]; m.ld1 = H; }
+      if (fuse && l > 0) m.pw = pw_of(l - 1);               // d(output of layer l-1) goes through its cell backward at once
       KernelScope ks("dec_matmul_t", stream);
       NABU_CHECK_CUDA(chain_launch(dec_matmul_t_kernel, dim3(ceil_div(m.N, 8), ceil_div(B, ROWS)), dim3(MT_THREADS), smem_mm, stream, m));
     }

@@ -76,6 +76,81 @@ inline cudaError_t chain_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bulk-copy staging of the transposed activations of the skinny matmuls (round 2).  With one row tile (R <= ROWS) a chunk
+// of XC consecutive k-rows of a [K][R] operand is one contiguous piece of memory: thread 0 streams the chunks into a
+// double buffer with cp.async.bulk (completion on an mbarrier) while the block multiplies the previous chunk, instead of
+// every thread chasing its own chain of L2 round trips (K / KSPLIT dependent-latency loads per thread).
+// ------------------------------------------------------------------------------------------------
+constexpr int XC = 128;          // k-rows per chunk
+__device__ __forceinline__ uint32_t dk_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dk_bar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dk_s32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void dk_bar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "DK_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DK_DONE;\n"
+      "bra DK_WAIT;\n"
+      "DK_DONE:\n"
+      "}" ::"r"(dk_s32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void dk_bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer's last generic reads are ordered before the copy
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dk_s32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dk_s32(dst)), "l"(src), "r"(bytes), "r"(dk_s32(bar)) : "memory");
+}
+// acc[0..7] += sum_k x[k][rl] * Ws[(wrow0 + k)][0..7] over the k of this thread's split, operand [K][R] streamed in chunks.
+// Called by all threads of the block; `phase` carries the barriers' parities from one operand to the next.
+template <int NTHREADS>
+__device__ __forceinline__ void dk_stream_fma(const float* __restrict__ xT, int K, int R, const float* Ws, int wrow0, float* xs,
+                                              uint64_t* bar, unsigned& issued, unsigned& consumed, int rl, int ks, bool row_ok,
+                                              float (&acc)[8]) {
+  constexpr int KSPLIT = NTHREADS / ROWS;
+  const int tid = threadIdx.x;
+  const int nch = (K + XC - 1) / XC;
+  if (nch == 0) return;
+  auto issue = [&](int ch) {
+    const int kk = min(XC, K - ch * XC);
+    const unsigned b = issued & 1;
+    dk_bulk_load(xs + (size_t)b * XC * R, xT + (size_t)ch * XC * R, (unsigned)(kk * R * sizeof(float)), &bar[b]);
+    ++issued;
+  };
+  // (the caller guarantees that both buffers are free on entry)
+  if (tid == 0) { issue(0); if (nch > 1) issue(1); }
+  for (int ch = 0; ch < nch; ++ch) {
+    const unsigned b = consumed & 1;
+    dk_bar_wait(&bar[b], (consumed >> 1) & 1);
+    ++consumed;
+    const float* xc = xs + (size_t)b * XC * R;
+    const int kk = min(XC, K - ch * XC);
+    if (row_ok) {
+#pragma unroll 8
+      for (int k = ks; k < kk; k += KSPLIT) {
+        const float x = xc[k * R + rl];
+        const float* wp = Ws + (size_t)(wrow0 + ch * XC + k) * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+        acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+        acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+        acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+        acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+      }
+    }
+    __syncthreads();                                     // the buffer is free again
+    if (tid == 0 && ch + 2 < nch) issue(ch + 2);
+  }
+}
+__device__ __forceinline__ bool dk_bulk_ok(const void* p0, const void* p1, int R) {
+  return gridDim.y == 1 && (R & 3) == 0 && ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
+}
+inline size_t dk_stage_bytes() { return (size_t)2 * XC * ROWS * sizeof(float); }
+
+// ------------------------------------------------------------------------------------------------
 // LSTM cell step.  grid = (H/2, ceil(R/ROWS)); CTA (slice, tile) owns hidden units 2*slice,
 // 2*slice+1 (8 gate columns) for ROWS rows; SK_KSPLIT-way k-split over the SK_THREADS threads.
 // ------------------------------------------------------------------------------------------------
@@ -111,13 +186,20 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
     const int wrow = k < a.K0 ? a.w0 + k : a.w1 + (k - a.K0);
     Ws[i] = a.W[(size_t)wrow * H4 + (c >> 1) * H + j0 + (c & 1)];
   }
+  __shared__ uint64_t bars[2];
+  if (tid == 0) { dk_bar_init(&bars[0]); dk_bar_init(&bars[1]); }
   chain_wait();                            // the weight slice was staged next to the previous kernel
   if (a.done && *a.done) return;
   __syncthreads();
   const int rl = tid % ROWS, ks = tid / ROWS;
   const int r = r0 + rl;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (r < R) {
+  if (dk_bulk_ok(a.inT0, a.inT1, R)) {
+    float* xs = red + SK_KSPLIT * ROWS * 8;            // [2][XC][R]
+    unsigned issued = 0, consumed = 0;
+    dk_stream_fma<SK_THREADS>(a.inT0, a.K0, R, Ws, 0, xs, bars, issued, consumed, rl, ks, r < R, acc);
+    dk_stream_fma<SK_THREADS>(a.inT1, a.K1, R, Ws, a.K0, xs, bars, issued, consumed, rl, ks, r < R, acc);
+  } else if (r < R) {
 #pragma unroll 16
     for (int k = ks; k < a.K0; k += SK_KSPLIT) {
       const float x = __ldcg(a.inT0 + (size_t)k * R + r);
@@ -492,6 +574,41 @@ inline size_t attn_step_smem(int Tm, int E, int H, int A, int F, int ksz) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward of one LSTM cell unit (row r, unit j) given the gradient `dha` wrt the cell OUTPUT; fused into the kernel
+// that produces dha (round 2: the attention backward for the top layer, the transposed matmul of the layer above for the
+// others) instead of a kernel of its own.  gates [R][4H] holds the activated i,g,f,o and receives dz; dzT [4H][R].
+// ------------------------------------------------------------------------------------------------
+struct LstmBwdPw {
+  float* gates; const float* c_new; const float* c_prev; const float* dh_carry; float* dc_carry; float* dzT;
+  const int* tlen; int u; float keep; unsigned seed; int layer;
+};
+__device__ __forceinline__ void lstm_bwd_unit(const LstmBwdPw& p, int R, int H, int r, int j, float dha) {
+  const size_t i = (size_t)r * H + j;
+  float* gp = p.gates + (size_t)r * 4 * H + j;
+  const bool active = p.u < p.tlen[r];
+  float dz[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float ig = gp[0], gg = gp[H], fg = gp[2 * H], og = gp[3 * H];
+    // dha is the gradient wrt the cell OUTPUT (dropped), dh_carry wrt the state h
+    if (p.keep > 0.f && p.keep < 1.f)
+      dha = dec_uniform(p.seed, (uint32_t)(p.layer * 65536 + p.u), (uint32_t)r, (uint32_t)j) < p.keep ? dha / p.keep : 0.f;
+    const float dh = dha + p.dh_carry[i];
+    const float tc = tanhf(p.c_new[i]);
+    const float dc = p.dc_carry[i] + dh * og * (1.f - tc * tc);
+    dz[0] = dc * gg * ig * (1.f - ig);
+    dz[1] = dc * ig * (1.f - gg * gg);
+    dz[2] = dc * p.c_prev[i] * fg * (1.f - fg);
+    dz[3] = dh * tc * og * (1.f - og);
+    p.dc_carry[i] = dc * fg;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    gp[g * H] = dz[g];
+    p.dzT[(size_t)(g * H + j) * R + r] = dz[g];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Skinny transposed-weight matmul: out[r][n] = sum_k xT[k][r] * W[row0 + n][k]  (d(input) = dz.K^T).
 // grid = (N/8, ceil(R/ROWS)).  Output columns [0,N0) go to out0, [N0,N) to out1.
 // ------------------------------------------------------------------------------------------------
@@ -500,6 +617,9 @@ struct MatmulTArgs {
   const float* W; int ldw; int row0;      // W[(row0+n)][k]
   int N, N0;
   float* out0; int ld0; float* out1; int ld1;
+  // pw.gates != nullptr: columns [0, N0) are d(output) of the LSTM layer below (N0 = its num_units); instead of being
+  // stored they go straight through that layer's cell backward (lstm_bwd_unit)
+  LstmBwdPw pw;
 };
 
 __global__ void __launch_bounds__(MT_THREADS) dec_matmul_t_kernel(const MatmulTArgs a) {
@@ -513,11 +633,17 @@ __global__ void __launch_bounds__(MT_THREADS) dec_matmul_t_kernel(const MatmulTA
     const int n = n0 + c;
     Ws[k * 8 + c] = (n < a.N) ? a.W[(size_t)(a.row0 + n) * a.ldw + k] : 0.f;
   }
+  __shared__ uint64_t bars[2];
+  if (tid == 0) { dk_bar_init(&bars[0]); dk_bar_init(&bars[1]); }
   chain_wait();                            // the weight slice was staged next to the previous kernel
   __syncthreads();
   const int rl = tid % ROWS, ks = tid / ROWS, r = r0 + rl;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (r < a.R) {
+  if (dk_bulk_ok(a.xT, a.xT, a.R)) {
+    float* xs = red + MT_KSPLIT * ROWS * 8;            // [2][XC][R]
+    unsigned issued = 0, consumed = 0;
+    dk_stream_fma<MT_THREADS>(a.xT, a.K, a.R, Ws, 0, xs, bars, issued, consumed, rl, ks, r < a.R, acc);
+  } else if (r < a.R) {
 #pragma unroll 16
     for (int k = ks; k < a.K; k += MT_KSPLIT) {
       const float x = __ldcg(a.xT + (size_t)k * a.R + r);
@@ -538,8 +664,9 @@ __global__ void __launch_bounds__(MT_THREADS) dec_matmul_t_kernel(const MatmulTA
       float s = 0.f;
 #pragma unroll
       for (int k2 = 0; k2 < MT_KSPLIT; ++k2) s += red[(k2 * ROWS + rl2) * 8 + c];
-      if (n < a.N0) a.out0[(size_t)r2 * a.ld0 + n] = s;
-      else a.out1[(size_t)r2 * a.ld1 + (n - a.N0)] = s;
+      if (n >= a.N0) a.out1[(size_t)r2 * a.ld1 + (n - a.N0)] = s;
+      else if (a.pw.gates) lstm_bwd_unit(a.pw, a.R, a.N0, r2, n, s);
+      else a.out0[(size_t)r2 * a.ld0 + n] = s;
     }
   }
 }
