@@ -34,6 +34,7 @@ struct BeamBuf {
   int* pred_hist; int* parent_hist;                 // [max_steps][R]
   float* align_hist;                                // [max_steps][R][Tm]
   int* done; int* n_steps;                          // device scalars
+  float* wf[4];                                     // the cells' weight slices as the step kernel stages them
   size_t total;
 };
 
@@ -57,6 +58,7 @@ BeamBuf carve_beam(void* base, const nabu_speller_desc_t& d, int W, int max_step
   b.pred_hist = (int*)take((size_t)max_steps * R); b.parent_hist = (int*)take((size_t)max_steps * R);
   b.align_hist = (float*)take((size_t)max_steps * R * Tm);
   b.done = (int*)take(2); b.n_steps = b.done + 1;
+  for (int l = 0; l < d.num_layers; ++l) b.wf[l] = (float*)take(dec::relayout_fwd_floats(d, l));
   b.total = off;
   return b;
 }
@@ -300,13 +302,14 @@ extern "C" int nabu_las_beam_search(const nabu_speller_desc_t* dp, const nabu_sp
   NABU_REQUIRE(prune_smem <= 200 * 1024, "las_beam_search: W*V too large");
   if (prune_smem > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(las_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prune_smem));
+  if (int e = dec::relayout_fwd(d, *p, bb.wf, stream)) return e;
   int P = 0;   // index of the "previous" state set
   for (int t = 0; t < max_steps; ++t) {
     const int N = (P + 1) % 3, G = (P + 2) % 3;
     if (int e = dec::launch_step(d, *p, R, W, bb.ids, bb.keys, bb.values, mem_len, bb.hT[P], bb.h[P], bb.c[P], bb.ctx[P],
                                  bb.ctxT[P], bb.align[P], bb.hT[N], bb.h[N], bb.c[N], bb.ctx[N], bb.ctxT[N], bb.align[N],
                                  nullptr, bb.logits, V, temperature, nullptr, nullptr, nullptr, 0, nullptr, t,
-                                 bb.done, stream))
+                                 bb.done, stream, nullptr, nullptr, nullptr, 1.f, 0, bb.wf))
       return e;
     {
       KernelScope ks("las_prune", stream);

@@ -531,6 +531,7 @@ struct Saved {        // written by the forward, read by the backward
   float* q; float* cf; float* outin;          // [U][B][A], [U][B][Tm][F], [B][U][H+E]
   float* asum;                                // [U][B] sum of sigmoids (probability_fn = normalized_sigmoid)
   float* out[4]; float* outT[4];              // dropout only: cell outputs [(U+1)][B][H] (slot u+1 = step u), [H][B] scratch
+  float* wf[4]; float* wb[4];                 // the cells' weight slices as the step / transposed-matmul kernels stage them
   size_t total;
 };
 
@@ -556,6 +557,10 @@ Saved carve_saved(void* base, const nabu_speller_desc_t& d) {
   s.cf = take(U * B * Tm * (F ? F : 1));
   s.outin = take(B * U * (H + E));
   s.asum = take(U * B);
+  for (int l = 0; l < d.num_layers; ++l) {
+    s.wf[l] = take(relayout_fwd_floats(d, l));
+    s.wb[l] = take((l == 0 ? E + H : 2 * H) * 4 * H);
+  }
   const bool drop = d.dropout_keep > 0.f && d.dropout_keep < 1.f;
   for (int l = 0; l < 4; ++l) {
     s.out[l] = (drop && l < d.num_layers) ? take((U + 1) * B * H) : nullptr;
@@ -624,6 +629,20 @@ int check_desc(const nabu_speller_desc_t& d) {
   return 0;
 }
 
+size_t relayout_fwd_floats(const nabu_speller_desc_t& d, int l) {
+  return (size_t)(l == 0 ? d.E + d.H : 2 * d.H) * 4 * d.H;
+}
+int relayout_fwd(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, float* const* out, cudaStream_t stream) {
+  for (int l = 0; l < d.num_layers; ++l) {
+    const long n = (long)relayout_fwd_floats(d, l);
+    KernelScope ks("dec_relayout", stream);
+    if (l == 0) dec_relayout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p.cell_kernel[0], out[0], d.H, d.E, d.V, d.H, d.V + d.E);
+    else dec_relayout_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p.cell_kernel[l], out[l], d.H, d.H, 0, d.H, d.H);
+    NABU_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
 // Launch one full decoder step (all LSTM layers + attention/projection).  Shared with las_beam.cu.
 int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, int R, int rows_per_mem,
                 const int* ids, const float* keys, const float* values, const int* mem_len,
@@ -633,13 +652,14 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
                 float* align_new, float* const* gates_out, float* logits, long logits_row_stride,
                 float temperature, float* q_save, float* cf_save, float* outin_save, long outin_row_stride,
                 const int* tlen, int u, const int* done, cudaStream_t stream, float* asum_save,
-                float* const* out_new, float* const* outT_new, float keep, unsigned seed) {
+                float* const* out_new, float* const* outT_new, float keep, unsigned seed, const float* const* cell_relayout) {
   const int H = d.H, E = d.E, V = d.V;
   for (int l = 0; l < d.num_layers; ++l) {
     LstmStepArgs a = {};
     if (l == 0) { a.inT0 = ctxT_prev; a.K0 = E; a.w0 = V; a.inT1 = hT_prev[0]; a.K1 = H; a.w1 = V + E; a.ids = ids; }
     else { a.inT0 = outT_new ? outT_new[l - 1] : hT_new[l - 1]; a.K0 = H; a.w0 = 0; a.inT1 = hT_prev[l]; a.K1 = H; a.w1 = H; a.ids = nullptr; }
     a.W = p.cell_kernel[l]; a.bias = p.cell_bias[l]; a.H = H; a.R = R;
+    a.Wr = cell_relayout ? cell_relayout[l] : nullptr;
     a.c_prev = c_prev[l]; a.h_prev = h_prev[l];
     a.c_new = c_new[l]; a.h_new = h_new[l]; a.hT_new = hT_new[l];
     a.gates_out = gates_out ? gates_out[l] : nullptr;
@@ -716,6 +736,7 @@ extern "C" int nabu_speller_fwd(const nabu_speller_desc_t* dp, const nabu_spelle
   Saved s = carve_saved(saved, d);
   const size_t B = d.B, Tm = d.Tm, E = d.E, H = d.H, U = d.U;
   if (int e = prepare_memory(d, *p, memory, mem_len, s.values, s.keys, stream)) return e;
+  if (int e = relayout_fwd(d, *p, s.wf, stream)) return e;
   {
     KernelScope ks("build_ids", stream);
     build_ids_kernel<<<ceil_div(d.U * d.B, 256), 256, 0, stream>>>(targets, ldt, d.B, d.U, d.V, s.ids_in);
@@ -749,7 +770,7 @@ extern "C" int nabu_speller_fwd(const nabu_speller_desc_t* dp, const nabu_spelle
                             s.align + (size_t)(u + 1) * B * Tm, go, logits + (size_t)u * d.V, (long)U * d.V, 1.f,
                             s.q + (size_t)u * B * d.A, F ? s.cf + (size_t)u * B * Tm * F : nullptr,
                             s.outin + (size_t)u * (H + E), (long)U * (H + E), target_len, u, nullptr, stream,
-                            s.asum + (size_t)u * B, drop ? on : nullptr, drop ? oTn : nullptr, d.dropout_keep, d.seed))
+                            s.asum + (size_t)u * B, drop ? on : nullptr, drop ? oTn : nullptr, d.dropout_keep, d.seed, s.wf))
       return e;
     // ScheduledEmbeddingTrainingHelper (rnn_decoder.py:59-64): with probability sample_prob the NEXT input token is a
     // draw from Categorical(logits of this step) instead of the teacher's
@@ -784,6 +805,12 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
   if (smem_mm > 48 * 1024)
     NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_matmul_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mm));
 
+  for (int l = 0; l < NL; ++l) {
+    const int N = l == 0 ? E + H : 2 * H, row0 = l == 0 ? V : 0;
+    KernelScope ks("dec_relayout", stream);
+    dec_relayout_bwd_kernel<<<(unsigned)(((long)N * H4 + 255) / 256), 256, 0, stream>>>(p->cell_kernel[l], s.wb[l], H4, H4, row0, N);
+    NABU_CHECK_LAUNCH();
+  }
   // NABU_DEC_FUSE=0: the cell backward as a kernel of its own (round 1) instead of inside the kernels that produce its input
   static const bool fuse = !(getenv("NABU_DEC_FUSE") && atoi(getenv("NABU_DEC_FUSE")) == 0);
   for (int u = U - 1; u >= 0; --u) {
@@ -819,7 +846,7 @@ extern "C" int nabu_speller_bwd(const nabu_speller_desc_t* dp, const nabu_spelle
                                      pw_of(l), (const float*)w.dh_above, B, H));
       }
       MatmulTArgs m = {};
-      m.xT = w.dzT[l]; m.K = H4; m.R = B; m.W = p->cell_kernel[l]; m.ldw = H4;
+      m.xT = w.dzT[l]; m.K = H4; m.R = B; m.W = p->cell_kernel[l]; m.ldw = H4; m.Wr = s.wb[l];
       if (l > 0) { m.row0 = 0; m.N = 2 * H; m.N0 = H; m.out0 = w.dh_above; m.ld0 = H; m.out1 = w.dh_carry[l]; m.ld1 = H; }
       else { m.row0 = V; m.N = E + H; m.N0 = E; m.out0 = w.dctx_carry; m.ld0 = E; m.out1 = w.dh_carry[0]; m.ld1 = H; }
       if (fuse && l > 0) m.pw = pw_of(l - 1);               // d(output of layer l-1) goes through its cell backward at once

@@ -151,6 +151,29 @@ __device__ __forceinline__ bool dk_bulk_ok(const void* p0, const void* p1, int R
 inline size_t dk_stage_bytes() { return (size_t)2 * XC * ROWS * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------------
+// Weight slices of the skinny matmuls laid out the way their CTAs stage them (once per forward / backward / beam search
+// instead of a strided gather in every one of the U steps):
+//   forward:  Wr[slice][k][c] = W[wrow(k)][(c >> 1) * H + 2 * slice + (c & 1)]   slice < H/2, k over both input segments
+//   backward: Wb[slice][k][c] = W[row0 + 8 * slice + c][k]                       slice < N/8, k < K
+// ------------------------------------------------------------------------------------------------
+__global__ void dec_relayout_fwd_kernel(const float* W, float* Wr, int H, int K0, int w0, int K1, int w1) {
+  const long i = blockIdx.x * 256L + threadIdx.x;
+  const int Ktot = K0 + K1;
+  if (i >= (long)(H / 2) * Ktot * 8) return;
+  const int c = (int)(i & 7);
+  const long t = i >> 3;
+  const int k = (int)(t % Ktot), slice = (int)(t / Ktot);
+  const int wrow = k < K0 ? w0 + k : w1 + (k - K0);
+  Wr[i] = W[(size_t)wrow * 4 * H + (c >> 1) * H + 2 * slice + (c & 1)];
+}
+__global__ void dec_relayout_bwd_kernel(const float* W, float* Wb, int K, int ldw, int row0, int N) {
+  const long i = blockIdx.x * 256L + threadIdx.x;
+  if (i >= (long)N * K) return;
+  const int k = (int)(i % K), n = (int)(i / K);          // k fastest: coalesced reads of W's rows
+  Wb[((size_t)(n >> 3) * K + k) * 8 + (n & 7)] = W[(size_t)(row0 + n) * ldw + k];
+}
+
+// ------------------------------------------------------------------------------------------------
 // LSTM cell step.  grid = (H/2, ceil(R/ROWS)); CTA (slice, tile) owns hidden units 2*slice,
 // 2*slice+1 (8 gate columns) for ROWS rows; SK_KSPLIT-way k-split over the SK_THREADS threads.
 // ------------------------------------------------------------------------------------------------
@@ -159,6 +182,7 @@ struct LstmStepArgs {
   const float* inT1; int K1; int w1;      // transposed input segment 1 (this layer's h_prev) [K1][R]
   const int* ids;                         // optional one-hot ids [R] (weight rows 0..V-1), or nullptr
   const float* W; const float* bias;      // [(rows), 4H], [4H]
+  const float* Wr;                        // optional [H/2][K0 + K1][8]: the CTAs' weight slices laid out contiguously (relayout_fwd)
   int H, R;
   const float* c_prev;                    // [R][H]
   const float* h_prev;                    // [R][H] row-major (copy-through for finished rows)
@@ -181,14 +205,20 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
   const int H = a.H, H4 = 4 * a.H, R = a.R;
   const int j0 = blockIdx.x * 2;
   const int r0 = blockIdx.y * ROWS;
-  for (int i = tid; i < Ktot * 8; i += SK_THREADS) {
-    const int c = i & 7, k = i >> 3;
-    const int wrow = k < a.K0 ? a.w0 + k : a.w1 + (k - a.K0);
-    Ws[i] = a.W[(size_t)wrow * H4 + (c >> 1) * H + j0 + (c & 1)];
+  __shared__ uint64_t bars[3];
+  if (tid == 0) { dk_bar_init(&bars[0]); dk_bar_init(&bars[1]); dk_bar_init(&bars[2]); }
+  if (a.Wr) {                              // the slice is one contiguous piece: one bulk copy
+    if (tid == 0) dk_bulk_load(Ws, a.Wr + (size_t)blockIdx.x * Ktot * 8, (unsigned)(Ktot * 8 * sizeof(float)), &bars[2]);
+  } else {
+    for (int i = tid; i < Ktot * 8; i += SK_THREADS) {
+      const int c = i & 7, k = i >> 3;
+      const int wrow = k < a.K0 ? a.w0 + k : a.w1 + (k - a.K0);
+      Ws[i] = a.W[(size_t)wrow * H4 + (c >> 1) * H + j0 + (c & 1)];
+    }
   }
-  __shared__ uint64_t bars[2];
-  if (tid == 0) { dk_bar_init(&bars[0]); dk_bar_init(&bars[1]); }
+  __syncthreads();                         // (the barriers are initialised for every thread)
   chain_wait();                            // the weight slice was staged next to the previous kernel
+  if (a.Wr) dk_bar_wait(&bars[2], 0);
   if (a.done && *a.done) return;
   __syncthreads();
   const int rl = tid % ROWS, ks = tid / ROWS;
@@ -615,6 +645,7 @@ __device__ __forceinline__ void lstm_bwd_unit(const LstmBwdPw& p, int R, int H, 
 struct MatmulTArgs {
   const float* xT; int K; int R;          // [K][R]
   const float* W; int ldw; int row0;      // W[(row0+n)][k]
+  const float* Wr;                        // optional [N/8][K][8]: the CTAs' weight slices laid out contiguously (relayout_bwd)
   int N, N0;
   float* out0; int ld0; float* out1; int ld1;
   // pw.gates != nullptr: columns [0, N0) are d(output) of the LSTM layer below (N0 = its num_units); instead of being
@@ -628,14 +659,20 @@ __global__ void __launch_bounds__(MT_THREADS) dec_matmul_t_kernel(const MatmulTA
   float* red = sm + (size_t)a.K * 8;       // [MT_KSPLIT][ROWS][8]
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * 8, r0 = blockIdx.y * ROWS;
-  for (int i = tid; i < a.K * 8; i += MT_THREADS) {
-    const int c = i / a.K, k = i % a.K;    // k fastest: coalesced rows of W
-    const int n = n0 + c;
-    Ws[k * 8 + c] = (n < a.N) ? a.W[(size_t)(a.row0 + n) * a.ldw + k] : 0.f;
+  __shared__ uint64_t bars[3];
+  if (tid == 0) { dk_bar_init(&bars[0]); dk_bar_init(&bars[1]); dk_bar_init(&bars[2]); }
+  if (a.Wr) {
+    if (tid == 0) dk_bulk_load(Ws, a.Wr + (size_t)blockIdx.x * a.K * 8, (unsigned)(a.K * 8 * sizeof(float)), &bars[2]);
+  } else {
+    for (int i = tid; i < a.K * 8; i += MT_THREADS) {
+      const int c = i / a.K, k = i % a.K;    // k fastest: coalesced rows of W
+      const int n = n0 + c;
+      Ws[k * 8 + c] = (n < a.N) ? a.W[(size_t)(a.row0 + n) * a.ldw + k] : 0.f;
+    }
   }
-  __shared__ uint64_t bars[2];
-  if (tid == 0) { dk_bar_init(&bars[0]); dk_bar_init(&bars[1]); }
+  __syncthreads();                         // (the barriers are initialised for every thread)
   chain_wait();                            // the weight slice was staged next to the previous kernel
+  if (a.Wr) dk_bar_wait(&bars[2], 0);
   __syncthreads();
   const int rl = tid % ROWS, ks = tid / ROWS, r = r0 + rl;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
