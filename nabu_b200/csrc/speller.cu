@@ -148,8 +148,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
   float* dctx = oin + r4(H + E);           // [E]
   float* dquery = dctx + r4(E);            // [H]
   float* al = dquery + r4(H);              // [Tm]
-  float* ap = al + r4(Tm);                 // [Tm + ksz] zero-padded alpha_prev
-  float* dal = ap + r4(Tm + ksz);          // [Tm] dalpha, then de
+  float* ap = al + r4(Tm);                 // [Tm + ksz + 4] zero-padded alpha_prev
+  float* dal = ap + r4(Tm + ksz + 4);      // [Tm] dalpha, then de
   float* qs = dal + r4(Tm);                // [A]
   float* dqs = qs + r4(A);                 // [A]
   float* red = dqs + r4(A);                // [32]
@@ -180,7 +180,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
   for (int i = tid; i < V; i += NT) dl[i] = a.dlogits[r * a.dl_row_stride + i];
   for (int i = tid; i < H + E; i += NT) oin[i] = a.outin[r * a.outin_row_stride + i];
   for (int i = tid; i < Tm; i += NT) al[i] = a.alpha[(size_t)r * Tm + i];
-  for (int i = tid; i < Tm + ksz; i += NT) {
+  for (int i = tid; i < Tm + ksz + 4; i += NT) {
     const int t = i - padl;
     ap[i] = (F > 0 && t >= 0 && t < Tm) ? a.alpha_prev[(size_t)r * Tm + t] : 0.f;
   }
@@ -422,11 +422,14 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
     // dalign_prev[tau] = sum_{k,f} dcf[tau - k + padl][f] * Wc[k][f]
     // (the taps are split over the groups of 128 threads; partial sums meet in the dpre scratch)
     {
-      constexpr int NG = NT / 128;                      // tap groups
+      // tap groups of GS threads, GS the power of two that covers this CTA's taus (64 threads x 8 groups for 63 taus)
+      int GS = 32;
+      while (GS < ue - ub && GS < NT) GS <<= 1;
+      const int NG = NT / GS;
       const bool split2 = NG * Tm <= TT * A;            // room for every group's partial sums in the scratch
-      const int half = split2 ? tid >> 7 : 0, kh = split2 ? (ksz + NG - 1) / NG : ksz;
+      const int half = split2 ? tid / GS : 0, kh = split2 ? (ksz + NG - 1) / NG : ksz;
       const int k0 = half * kh, k1 = min(ksz, k0 + kh);
-      for (int tau = ub + (split2 ? (tid & 127) : tid); tau < ue; tau += split2 ? 128 : NT) {
+      for (int tau = ub + (split2 ? (tid & (GS - 1)) : tid); tau < ue; tau += split2 ? GS : NT) {
         float s = 0.f;
         for (int k = k0; k < k1; ++k) {
           const int t = tau - k + padl;
@@ -451,17 +454,28 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
       if (split2)
         for (int tau = ub + tid; tau < ue; tau += NT) {
           float s = 0.f;
-#pragma unroll
           for (int gq = 0; gq < NG; ++gq) s += dpre[gq * Tm + tau];
           a.dalign_carry[(size_t)r * Tm + tau] = s;
         }
     }
     // dWc[k][f] += sum_t alpha_prev[t + k - padl] * dcf[t][f]
-    for (int i = cr + CS * tid; i < ksz * F; i += CS * NT) {
-      const int k = i / F, f = i % F;
-      float s = 0.f;
-      for (int t = 0; t < Tm; ++t) s = fmaf(ap[t + k], dcf[t * F + f], s);
-      a.dWc_part[(size_t)r * ksz * F + i] += s;
+    // a thread takes 4 consecutive taps of one filter (a sliding window over alpha_prev in registers: two reads per
+    // 4 FMAs); the quads are dealt out to the CTAs of the row in turn
+    for (int i = cr + CS * tid; i < ((ksz + 3) / 4) * F; i += CS * NT) {
+      const int f = i % F, kq = (i / F) * 4;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float a0 = ap[kq], a1 = ap[kq + 1], a2 = ap[kq + 2];
+#pragma unroll 4
+      for (int t = 0; t < Tm; ++t) {
+        const float a3 = ap[t + kq + 3], dd = dcf[t * F + f];
+        s0 = fmaf(a0, dd, s0); s1 = fmaf(a1, dd, s1); s2 = fmaf(a2, dd, s2); s3 = fmaf(a3, dd, s3);
+        a0 = a1; a1 = a2; a2 = a3;
+      }
+      float* out = a.dWc_part + (size_t)r * ksz * F;
+      out[kq * F + f] += s0;
+      if (kq + 1 < ksz) out[(kq + 1) * F + f] += s1;
+      if (kq + 2 < ksz) out[(kq + 2) * F + f] += s2;
+      if (kq + 3 < ksz) out[(kq + 3) * F + f] += s3;
     }
   } else {
     for (int tau = ub + tid; tau < ue; tau += NT) a.dalign_carry[(size_t)r * Tm + tau] = 0.f;
@@ -494,7 +508,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_bwd_s
 
 inline size_t attn_bwd_smem(int Tm, int E, int H, int A, int V, int F, int ksz, int cs = 4) {
   auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
-  return (r4(V) + r4(H + E) + r4(E) + r4(H) + r4(Tm) + r4(Tm + ksz) + r4(Tm) + r4(A) + r4(A) + 32 + 2 * r4((size_t)Tm * F) +
+  return (r4(V) + r4(H + E) + r4(E) + r4(H) + r4(Tm) + r4(Tm + ksz + 4) + r4(Tm) + r4(A) + r4(A) + 32 + 2 * r4((size_t)Tm * F) +
           r4((size_t)F * A) + r4((size_t)ksz * F) + (size_t)TT * A + 4 + (cs > 1 ? (size_t)cs * (2 + F) * A : 0)) * sizeof(float);
 }
 

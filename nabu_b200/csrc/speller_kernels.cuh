@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };   // every piece starts on a 16-byte boundary (attn_step_smem)
   float* query = sm;                       // [H]
   float* q = query + r4(H);                // [A]
-  float* ap = q + r4(A);                   // [Tm + ksz] zero padded alpha_prev
-  float* e = ap + r4(Tm + ksz);            // [Tm]
+  float* ap = q + r4(A);                   // [Tm + ksz + 4] zero padded alpha_prev
+  float* e = ap + r4(Tm + ksz + 4);        // [Tm]
   float* ctx = e + r4(Tm);                 // [E]
   float* red = ctx + r4(E);                // [32]
   float* part = red + 32;                  // [NW][32] projection partials
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     // prologue, next to the LSTM step that produces this step's query (see chain_wait): weights, the previous
     // alignments (complete since the previous step) and phase 1, the location features
     //   cf[t][f] = sum_k alpha_prev[t + k - padl] * Wc[k][f]
-    for (int i = tid; i < Tm + ksz; i += NT) {
+    for (int i = tid; i < Tm + ksz + 4; i += NT) {
       const int t = i - padl;
       ap[i] = ((F > 0 || a.win_left >= 0) && t >= 0 && t < Tm) ? __ldcg(a.align_prev + (size_t)r * Tm + t) : 0.f;
     }
@@ -360,11 +360,22 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     for (int i = tid; i < ksz * F; i += NT) wc[i] = a.Wc[i];
     for (int i = tid; i < A; i += NT) vs[i] = a.v[i];
     __syncthreads();
-    for (int i = tid; i < Tm * F; i += NT) {
-      const int t = i / F, f = i % F;
-      float s = 0.f;
-      for (int k = 0; k < ksz; ++k) s = fmaf(ap[t + k], wc[k * F + f], s);
-      cf[i] = s;
+    // a thread takes 4 consecutive positions of one filter: per tap one weight and one new alignment are read for 4 FMAs
+    // (a sliding window in registers) instead of two reads per FMA
+    for (int i = tid; i < ((Tm + 3) / 4) * F; i += NT) {
+      const int f = i % F, t0 = (i / F) * 4;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float a0 = ap[t0], a1 = ap[t0 + 1], a2 = ap[t0 + 2];
+#pragma unroll 4
+      for (int k = 0; k < ksz; ++k) {
+        const float a3 = ap[t0 + k + 3], w = wc[k * F + f];
+        s0 = fmaf(a0, w, s0); s1 = fmaf(a1, w, s1); s2 = fmaf(a2, w, s2); s3 = fmaf(a3, w, s3);
+        a0 = a1; a1 = a2; a2 = a3;
+      }
+      cf[t0 * F + f] = s0;
+      if (t0 + 1 < Tm) cf[(t0 + 1) * F + f] = s1;
+      if (t0 + 2 < Tm) cf[(t0 + 2) * F + f] = s2;
+      if (t0 + 3 < Tm) cf[(t0 + 3) * F + f] = s3;
     }
   }
   chain_wait();
@@ -599,7 +610,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
 inline size_t attn_step_smem(int Tm, int E, int H, int A, int F, int ksz) {
   // the arrays read with 128-bit accesses (q, wd, vs, cpart) must start on 16-byte boundaries: round every piece up to 4
   auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
-  return (r4(H) + r4(A) + r4(Tm + ksz) + r4(Tm) + r4(E) + 32 + 512 + r4((size_t)Tm * F) + r4((size_t)F * A) +
+  return (r4(H) + r4(A) + r4(Tm + ksz + 4) + r4(Tm) + r4(E) + 32 + 512 + r4((size_t)Tm * F) + r4((size_t)F * A) +
           r4((size_t)ksz * F) + r4(A) + 2048) * sizeof(float);
 }
 
