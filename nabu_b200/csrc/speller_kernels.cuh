@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   }
   const int len = min(a.mem_len[mrow], Tm);
 
+  __syncthreads();                         // the location features were written by other threads (4 positions each)
   for (int i = tid; i < H; i += NT) query[i] = a.h_top[(size_t)r * H + i];
   if (a.cf_save) for (int i = tid; i < Tm * F; i += NT) a.cf_save[(size_t)r * Tm * F + i] = cf[i];
   __syncthreads();
