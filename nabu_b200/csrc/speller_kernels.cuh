@@ -76,10 +76,11 @@ inline cudaError_t chain_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Bulk-copy staging of the transposed activations of the skinny matmuls (round 2).  With one row tile (R <= ROWS) a chunk
-// of XC consecutive k-rows of a [K][R] operand is one contiguous piece of memory: thread 0 streams the chunks into a
-// double buffer with cp.async.bulk (completion on an mbarrier) while the block multiplies the previous chunk, instead of
-// every thread chasing its own chain of L2 round trips (K / KSPLIT dependent-latency loads per thread).
+// Bulk-copy staging of the transposed activations of the skinny matmuls (round 2).  Warp 0 streams chunks of XC
+// consecutive k-rows of a [K][R] operand into a double buffer with cp.async.bulk (completion on an mbarrier) while the
+// block multiplies the previous chunk, instead of every thread chasing its own chain of L2 round trips (K / KSPLIT
+// dependent-latency loads per thread).  One row tile (R <= ROWS, training): a chunk is one contiguous copy; several row
+// tiles (beam search, R = B * W): one 256-byte copy per k-row segment.
 // ------------------------------------------------------------------------------------------------
 constexpr int XC = 128;          // k-rows per chunk
 __device__ __forceinline__ uint32_t dk_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,34 +105,54 @@ __device__ __forceinline__ void dk_bulk_load(void* dst, const void* src, unsigne
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dk_s32(dst)), "l"(src), "r"(bytes), "r"(dk_s32(bar)) : "memory");
 }
-// acc[0..7] += sum_k x[k][rl] * Ws[(wrow0 + k)][0..7] over the k of this thread's split, operand [K][R] streamed in chunks.
-// Called by all threads of the block; `phase` carries the barriers' parities from one operand to the next.
+__device__ __forceinline__ void dk_bulk_copy(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dk_s32(dst)), "l"(src), "r"(bytes), "r"(dk_s32(bar)) : "memory");
+}
+// acc[0..7] += sum_k x[k][r0 + rl] * Ws[(wrow0 + k)][0..7] over the k of this thread's split, operand [K][R] streamed in
+// chunks of XC k-rows: one copy per chunk when the block's rows are all R rows (the chunk is contiguous), otherwise one
+// copy per k-row segment of nr floats, dealt out to the lanes of warp 0.  Called by all threads of the block; `issued` /
+// `consumed` carry the double buffer's position from one operand to the next.
 template <int NTHREADS>
-__device__ __forceinline__ void dk_stream_fma(const float* __restrict__ xT, int K, int R, const float* Ws, int wrow0, float* xs,
-                                              uint64_t* bar, unsigned& issued, unsigned& consumed, int rl, int ks, bool row_ok,
-                                              float (&acc)[8]) {
+__device__ __forceinline__ void dk_stream_fma(const float* __restrict__ xT, int K, int R, int r0, const float* Ws, int wrow0,
+                                              float* xs, uint64_t* bar, unsigned& issued, unsigned& consumed, int rl, int ks,
+                                              bool row_ok, float (&acc)[8]) {
   constexpr int KSPLIT = NTHREADS / ROWS;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nch = (K + XC - 1) / XC;
   if (nch == 0) return;
-  auto issue = [&](int ch) {
+  const int nr = min(ROWS, R - r0);
+  const bool contig = nr == R;
+  const int rs = contig ? R : ROWS;                      // row stride of a staged chunk
+  auto issue = [&](int ch) {                             // warp 0, all lanes
     const int kk = min(XC, K - ch * XC);
     const unsigned b = issued & 1;
-    dk_bulk_load(xs + (size_t)b * XC * R, xT + (size_t)ch * XC * R, (unsigned)(kk * R * sizeof(float)), &bar[b]);
+    float* dst = xs + (size_t)b * XC * ROWS;
+    if (contig) {
+      if (lane == 0) dk_bulk_load(dst, xT + (size_t)ch * XC * R, (unsigned)(kk * R * sizeof(float)), &bar[b]);
+    } else {
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dk_s32(&bar[b])), "r"((unsigned)(kk * nr * sizeof(float))) : "memory");
+      }
+      __syncwarp();
+      const float* src = xT + (size_t)ch * XC * R + r0;
+      for (int k = lane; k < kk; k += 32) dk_bulk_copy(dst + k * ROWS, src + (size_t)k * R, (unsigned)(nr * sizeof(float)), &bar[b]);
+    }
     ++issued;
   };
   // (the caller guarantees that both buffers are free on entry)
-  if (tid == 0) { issue(0); if (nch > 1) issue(1); }
+  if (tid < 32) { issue(0); if (nch > 1) issue(1); }
   for (int ch = 0; ch < nch; ++ch) {
     const unsigned b = consumed & 1;
     dk_bar_wait(&bar[b], (consumed >> 1) & 1);
     ++consumed;
-    const float* xc = xs + (size_t)b * XC * R;
+    const float* xc = xs + (size_t)b * XC * ROWS;
     const int kk = min(XC, K - ch * XC);
     if (row_ok) {
 #pragma unroll 8
       for (int k = ks; k < kk; k += KSPLIT) {
-        const float x = xc[k * R + rl];
+        const float x = xc[k * rs + rl];
         const float* wp = Ws + (size_t)(wrow0 + ch * XC + k) * 8;
         const float4 w0 = *reinterpret_cast<const float4*>(wp);
         const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
@@ -142,11 +163,11 @@ __device__ __forceinline__ void dk_stream_fma(const float* __restrict__ xT, int 
       }
     }
     __syncthreads();                                     // the buffer is free again
-    if (tid == 0 && ch + 2 < nch) issue(ch + 2);
+    if (tid < 32 && ch + 2 < nch) issue(ch + 2);
   }
 }
 __device__ __forceinline__ bool dk_bulk_ok(const void* p0, const void* p1, int R) {
-  return gridDim.y == 1 && (R & 3) == 0 && ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
+  return (R & 3) == 0 && ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
 }
 inline size_t dk_stage_bytes() { return (size_t)2 * XC * ROWS * sizeof(float); }
 
@@ -227,8 +248,8 @@ __global__ void __launch_bounds__(SK_THREADS) dec_lstm_step_kernel(const LstmSte
   if (dk_bulk_ok(a.inT0, a.inT1, R)) {
     float* xs = red + SK_KSPLIT * ROWS * 8;            // [2][XC][R]
     unsigned issued = 0, consumed = 0;
-    dk_stream_fma<SK_THREADS>(a.inT0, a.K0, R, Ws, 0, xs, bars, issued, consumed, rl, ks, r < R, acc);
-    dk_stream_fma<SK_THREADS>(a.inT1, a.K1, R, Ws, a.K0, xs, bars, issued, consumed, rl, ks, r < R, acc);
+    dk_stream_fma<SK_THREADS>(a.inT0, a.K0, R, r0, Ws, 0, xs, bars, issued, consumed, rl, ks, r < R, acc);
+    dk_stream_fma<SK_THREADS>(a.inT1, a.K1, R, r0, Ws, a.K0, xs, bars, issued, consumed, rl, ks, r < R, acc);
   } else if (r < R) {
 #pragma unroll 16
     for (int k = ks; k < a.K0; k += SK_KSPLIT) {
@@ -691,7 +712,7 @@ __global__ void __launch_bounds__(MT_THREADS) dec_matmul_t_kernel(const MatmulTA
   if (dk_bulk_ok(a.xT, a.xT, a.R)) {
     float* xs = red + MT_KSPLIT * ROWS * 8;            // [2][XC][R]
     unsigned issued = 0, consumed = 0;
-    dk_stream_fma<MT_THREADS>(a.xT, a.K, a.R, Ws, 0, xs, bars, issued, consumed, rl, ks, r < a.R, acc);
+    dk_stream_fma<MT_THREADS>(a.xT, a.K, a.R, r0, Ws, 0, xs, bars, issued, consumed, rl, ks, r < a.R, acc);
   } else if (r < a.R) {
 #pragma unroll 16
     for (int k = ks; k < a.K; k += MT_KSPLIT) {
