@@ -804,6 +804,14 @@ def tensordot(a, b, axes, name=None):
     return Tensor(torch.tensordot(a, b, axes))
 
 
+def norm(tensor, ord='euclidean', axis=None, keepdims=None, name=None, keep_dims=None):        # noqa: A002
+    """linalg_ops.norm, euclidean"""
+    assert ord in ('euclidean', 2)
+    t = _t(tensor)
+    keep = builtins.bool(keepdims or keep_dims)
+    return Tensor(torch.sqrt(torch.sum(t * t, dim=_ints(axis), keepdim=keep)) if axis is not None else torch.sqrt(torch.sum(t * t)))
+
+
 def clip_by_value(t, lo, hi, name=None):
     return Tensor(torch.clamp(_t(t), float(lo), float(hi)))
 

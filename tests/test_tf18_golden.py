@@ -214,6 +214,24 @@ def _check_cuda_case(case):
         assert rel_err(scores, out['decoded_scores']) < TOL
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/nabu'), reason='the reference tree exists in the build container only')
+def test_reference_maxnorm_constraint_zeroes_the_weights():
+    """SURVEY 8 row f4 / DESIGN 7b: the reference's MaxNorm (components/constraints.py:21-30) divides by
+    `norms + tensor.dtype.min`, i.e. by about -3.4e38, so the "constrained" variable is (minus) zero whatever its norm.
+    Shown by running the reference's own class over the TF-API stand-in; nabu_b200's trainer raises when a cfg asks for
+    norm_constraint instead of reproducing it."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, tensorflow as tf, py2ref; py2ref.install()\n"
+            "from nabu.neuralnetworks.components.constraints import MaxNorm\n"
+            "w = np.random.RandomState(0).randn(5, 3) * 4\n"
+            "out = MaxNorm(1)(tf.constant(w)).numpy()\n"
+            "assert np.all(np.abs(out) < 1e-30) and np.all(np.abs(w) > 1e-3), out\n"
+            % (os.path.join(_GOLDEN, 'tf18shim'), _GOLDEN))
+    subprocess.run([sys.executable, '-c', code], check=True)
+
+
 # ---- the harness itself, on a case in the dump's format made by this repository's own oracle ---------------------
 def _self_made_case(path):
     """what tools/tf18_dump.py writes for a DBLSTM + CTC recipe, with the oracle standing in for TensorFlow"""
