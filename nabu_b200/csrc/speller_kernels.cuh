@@ -79,8 +79,8 @@ inline cudaError_t chain_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block,
 // Bulk-copy staging of the transposed activations of the skinny matmuls (round 2).  Warp 0 streams chunks of XC
 // consecutive k-rows of a [K][R] operand into a double buffer with cp.async.bulk (completion on an mbarrier) while the
 // block multiplies the previous chunk, instead of every thread chasing its own chain of L2 round trips (K / KSPLIT
-// dependent-latency loads per thread).  One row tile (R <= ROWS, training): a chunk is one contiguous copy; several row
-// tiles (beam search, R = B * W): one 256-byte copy per k-row segment.
+// dependent-latency loads per thread).  Used when the launch has one row tile (R <= ROWS, training): a chunk is then one
+// contiguous copy.
 // ------------------------------------------------------------------------------------------------
 constexpr int XC = 128;          // k-rows per chunk
 __device__ __forceinline__ uint32_t dk_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,14 +105,9 @@ __device__ __forceinline__ void dk_bulk_load(void* dst, const void* src, unsigne
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dk_s32(dst)), "l"(src), "r"(bytes), "r"(dk_s32(bar)) : "memory");
 }
-__device__ __forceinline__ void dk_bulk_copy(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dk_s32(dst)), "l"(src), "r"(bytes), "r"(dk_s32(bar)) : "memory");
-}
 // acc[0..7] += sum_k x[k][r0 + rl] * Ws[(wrow0 + k)][0..7] over the k of this thread's split, operand [K][R] streamed in
-// chunks of XC k-rows: one copy per chunk when the block's rows are all R rows (the chunk is contiguous), otherwise one
-// copy per k-row segment of nr floats, dealt out to the lanes of warp 0.  Called by all threads of the block; `issued` /
-// `consumed` carry the double buffer's position from one operand to the next.
+// chunks of XC k-rows, one copy per chunk (the block's rows are all R rows, so a chunk is contiguous).  Called by all
+// threads of the block; `issued` / `consumed` carry the double buffer's position from one operand to the next.
 template <int NTHREADS>
 __device__ __forceinline__ void dk_stream_fma(const float* __restrict__ xT, int K, int R, int r0, const float* Ws, int wrow0,
                                               float* xs, uint64_t* bar, unsigned& issued, unsigned& consumed, int rl, int ks,
@@ -121,24 +116,13 @@ __device__ __forceinline__ void dk_stream_fma(const float* __restrict__ xT, int 
   const int tid = threadIdx.x, lane = tid & 31;
   const int nch = (K + XC - 1) / XC;
   if (nch == 0) return;
-  const int nr = min(ROWS, R - r0);
-  const bool contig = nr == R;
-  const int rs = contig ? R : ROWS;                      // row stride of a staged chunk
+  const int rs = R;                                      // row stride of a staged chunk (one row tile: the chunk is contiguous)
+  (void)r0;
   auto issue = [&](int ch) {                             // warp 0, all lanes
     const int kk = min(XC, K - ch * XC);
     const unsigned b = issued & 1;
     float* dst = xs + (size_t)b * XC * ROWS;
-    if (contig) {
-      if (lane == 0) dk_bulk_load(dst, xT + (size_t)ch * XC * R, (unsigned)(kk * R * sizeof(float)), &bar[b]);
-    } else {
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dk_s32(&bar[b])), "r"((unsigned)(kk * nr * sizeof(float))) : "memory");
-      }
-      __syncwarp();
-      const float* src = xT + (size_t)ch * XC * R + r0;
-      for (int k = lane; k < kk; k += 32) dk_bulk_copy(dst + k * ROWS, src + (size_t)k * R, (unsigned)(nr * sizeof(float)), &bar[b]);
-    }
+    if (lane == 0) dk_bulk_load(dst, xT + (size_t)ch * XC * R, (unsigned)(kk * R * sizeof(float)), &bar[b]);
     ++issued;
   };
   // (the caller guarantees that both buffers are free on entry)
@@ -166,8 +150,11 @@ __device__ __forceinline__ void dk_stream_fma(const float* __restrict__ xT, int 
     if (tid < 32 && ch + 2 < nch) issue(ch + 2);
   }
 }
+// Several row tiles (beam search, R = B * W rows): a chunk is XC separate 256-byte segments; staging them with one bulk
+// copy each was measured and is SLOWER than the per-thread loads (LAS beam-16 decode 24.9 -> 38.2 ms), so those launches
+// keep the register path.
 __device__ __forceinline__ bool dk_bulk_ok(const void* p0, const void* p1, int R) {
-  return (R & 3) == 0 && ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
+  return gridDim.y == 1 && (R & 3) == 0 && ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
 }
 inline size_t dk_stage_bytes() { return (size_t)2 * XC * ROWS * sizeof(float); }
 
