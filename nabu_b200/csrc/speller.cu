@@ -702,12 +702,9 @@ int launch_step(const nabu_speller_desc_t& d, const nabu_speller_params_t& p, in
   a.tlen = tlen; a.u = u; a.done = done;
   a.prob = d.probability_fn; a.asum_save = asum_save;
   a.win_left = d.attention == 2 ? d.numfilt : -1; a.win_right = d.filtersize;
-  const size_t smem = attn_step_smem(d.Tm, E, H, d.A, a.F, a.ksz);
-  NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "speller: memory too long for the attention step kernel (Tm=%d)", d.Tm);
-  if (smem > 48 * 1024)
-    NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NABU_REQUIRE(attn_step_smem(d.Tm, E, H, d.A, a.F, a.ksz, attn_step_cluster(R, a.rows_per_mem)) <= (size_t)max_smem_optin(), "speller: memory too long for the attention step kernel (Tm=%d)", d.Tm);
   KernelScope ks("dec_attn_step", stream);
-  NABU_CHECK_CUDA(chain_launch(dec_attn_step_kernel, dim3(R), dim3(512), smem, stream, a));
+  NABU_CHECK_CUDA(attn_step_launch(a, R, nullptr, stream));
   return 0;
 }
 
@@ -1000,12 +997,9 @@ extern "C" int nabu_attn_step_fwd(const nabu_speller_desc_t* dp, const nabu_spel
   a.tlen = nullptr; a.u = 0; a.done = nullptr;
   a.prob = d.probability_fn; a.asum_save = asum_save;
   a.win_left = d.attention == 2 ? d.numfilt : -1; a.win_right = d.filtersize;
-  const size_t smem = attn_step_smem(d.Tm, d.E, d.H, d.A, a.F, a.ksz);
-  NABU_REQUIRE(smem <= (size_t)max_smem_optin(), "attn_step_fwd: memory too long for the attention step kernel (Tm=%d)", d.Tm);
-  if (smem > 48 * 1024)
-    NABU_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NABU_REQUIRE(attn_step_smem(d.Tm, d.E, d.H, d.A, a.F, a.ksz, attn_step_cluster(R, a.rows_per_mem)) <= (size_t)max_smem_optin(), "attn_step_fwd: memory too long for the attention step kernel (Tm=%d)", d.Tm);
   KernelScope ks("dec_attn_step", stream);
-  NABU_CHECK_CUDA(chain_launch(dec_attn_step_kernel, dim3(R), dim3(512), smem, stream, a));
+  NABU_CHECK_CUDA(attn_step_launch(a, R, nullptr, stream));
   return 0;
 }
 

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <stdint.h>
 #include <math_constants.h>
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <utility>
 
@@ -333,11 +334,21 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
-__global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a) {
-  constexpr int NT = 512, NW = NT / 32;                // 512 threads per decoder row
+// CS = CTAs per decoder row (a thread-block cluster; round 2, training batches whose rows alone cannot fill the 148 SMs):
+// the memory positions are cut into CS ranges; a CTA computes the location features, scores, probabilities and the
+// partial context of its range; the softmax statistics (maximum and sum of its range, combined as in an online
+// softmax) and the partial contexts are exchanged through distributed shared memory (two cluster barriers); the query
+// projection is computed by every CTA, the output projection by CTA 0.  CS = 1 is the round-1 kernel, bit for bit (the
+// beam search, whose ids are held bit-exact, always runs it).
+template <int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a) {
+  constexpr int NT = 512, NW = NT / 32;                // 512 threads per CTA
   extern __shared__ __align__(16) float sm[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = blockIdx.x;
+  const int cr = CS > 1 ? (int)cluster.block_rank() : 0;
+  const int r = blockIdx.x / CS;
   const int mrow = r / a.rows_per_mem;
   const int Tm = a.Tm, E = a.E, H = a.H, A = a.A, V = a.V, F = a.F, ksz = a.ksz;
   const int padl = (ksz - 1) / 2;
@@ -354,6 +365,10 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   float* wc = wd + r4((size_t)F * A);      // [ksz][F]
   float* vs = wc + r4((size_t)ksz * F);    // [A] attention vector
   float* cpart = vs + r4(A);               // [NT * 4] context partials of the t-splits
+  float* xstat = cpart + NT * 4;           // [CS][4] (maximum, sum) of every CTA's range          (CS > 1)
+  float* xctx = xstat + 4 * 4;             // [CS][E] partial contexts, slot = source CTA           (CS > 1)
+  // this CTA's memory positions [tb, te)
+  const int per = (Tm + CS - 1) / CS, tb = min(Tm, cr * per), te = min(Tm, tb + per);
 
   const bool active = (a.tlen == nullptr) || (a.u < a.tlen[r]);
   if (active) {
@@ -370,8 +385,8 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     __syncthreads();
     // a thread takes 4 consecutive positions of one filter: per tap one weight and one new alignment are read for 4 FMAs
     // (a sliding window in registers) instead of two reads per FMA
-    for (int i = tid; i < ((Tm + 3) / 4) * F; i += NT) {
-      const int f = i % F, t0 = (i / F) * 4;
+    for (int i = tid; i < ((te - tb + 3) / 4) * F; i += NT) {
+      const int f = i % F, t0 = tb + (i / F) * 4;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       float a0 = ap[t0], a1 = ap[t0 + 1], a2 = ap[t0 + 2];
 #pragma unroll 4
@@ -381,13 +396,16 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
         a0 = a1; a1 = a2; a2 = a3;
       }
       cf[t0 * F + f] = s0;
-      if (t0 + 1 < Tm) cf[(t0 + 1) * F + f] = s1;
-      if (t0 + 2 < Tm) cf[(t0 + 2) * F + f] = s2;
-      if (t0 + 3 < Tm) cf[(t0 + 3) * F + f] = s3;
+      if (t0 + 1 < te) cf[(t0 + 1) * F + f] = s1;
+      if (t0 + 2 < te) cf[(t0 + 2) * F + f] = s2;
+      if (t0 + 3 < te) cf[(t0 + 3) * F + f] = s3;
     }
+    // every CTA of the cluster is running before the first store into a peer's shared memory: arrive here, wait in phase 3
+    if (CS > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   }
   chain_wait();
   if (a.done && *a.done) return;
+  if (!active && cr != 0) return;
   if (!active) {                           // finished row: copy the state through, emit zeros
     for (int t = tid; t < Tm; t += NT) a.align_new[(size_t)r * Tm + t] = a.align_prev[(size_t)r * Tm + t];
     for (int i = tid; i < E; i += NT) {
@@ -405,7 +423,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
 
   __syncthreads();                         // the location features were written by other threads (4 positions each)
   for (int i = tid; i < H; i += NT) query[i] = a.h_top[(size_t)r * H + i];
-  if (a.cf_save) for (int i = tid; i < Tm * F; i += NT) a.cf_save[(size_t)r * Tm * F + i] = cf[i];
+  if (a.cf_save) for (int i = tb * F + tid; i < te * F; i += NT) a.cf_save[(size_t)r * Tm * F + i] = cf[i];
   __syncthreads();
 
   // phase 0: q = query . Wq
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     for (; k < H; ++k) s0 = fmaf(query[k], __ldg(a.Wq + (size_t)k * A + c), s0);
     const float s = (s0 + s1) + (s2 + s3);
     q[c] = s;
-    if (a.q_save) a.q_save[(size_t)r * A + c] = s;
+    if (a.q_save && cr == 0) a.q_save[(size_t)r * A + c] = s;
   }
   __syncthreads();
   // phase 2: scores e[t] = v . tanh(q + keys[t] + cf[t] . Wd), one warp per memory position, 128-bit loads of the keys
@@ -431,20 +449,20 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   const float* keys = a.keys + (size_t)mrow * Tm * A;
   const bool vec4 = ((A | E) & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.keys) | reinterpret_cast<uintptr_t>(a.values)) & 15) == 0;
   if (vec4) {
-    for (int t = warp; t < Tm; t += 2 * NW) {
+    for (int t = tb + warp; t < te; t += 2 * NW) {
       const int t1 = t + NW;
       float sa = 0.f, sb = 0.f;
       for (int c = lane * 4; c < A; c += 128) {
         float4 ka = make_float4(0.f, 0.f, 0.f, 0.f), kb = ka;
         if (t < len) ka = __ldg(reinterpret_cast<const float4*>(keys + (size_t)t * A + c));
-        if (t1 < len) kb = __ldg(reinterpret_cast<const float4*>(keys + (size_t)t1 * A + c));
+        if (t1 < len && t1 < te) kb = __ldg(reinterpret_cast<const float4*>(keys + (size_t)t1 * A + c));
         const float4 qq = *reinterpret_cast<const float4*>(q + c);
         const float4 vv = *reinterpret_cast<const float4*>(vs + c);
         float pa[4] = {qq.x + ka.x, qq.y + ka.y, qq.z + ka.z, qq.w + ka.w};
         float pb[4] = {qq.x + kb.x, qq.y + kb.y, qq.z + kb.z, qq.w + kb.w};
         for (int f = 0; f < F; ++f) {
           const float4 w4 = *reinterpret_cast<const float4*>(wd + f * A + c);
-          const float ca = cf[t * F + f], cb = t1 < Tm ? cf[t1 * F + f] : 0.f;
+          const float ca = cf[t * F + f], cb = t1 < te ? cf[t1 * F + f] : 0.f;
           pa[0] = fmaf(ca, w4.x, pa[0]); pa[1] = fmaf(ca, w4.y, pa[1]); pa[2] = fmaf(ca, w4.z, pa[2]); pa[3] = fmaf(ca, w4.w, pa[3]);
           pb[0] = fmaf(cb, w4.x, pb[0]); pb[1] = fmaf(cb, w4.y, pb[1]); pb[2] = fmaf(cb, w4.z, pb[2]); pb[3] = fmaf(cb, w4.w, pb[3]);
         }
@@ -455,11 +473,11 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
       sb = warp_sum(sb);
       if (lane == 0) {
         e[t] = (t < len) ? sa : -CUDART_INF_F;
-        if (t1 < Tm) e[t1] = (t1 < len) ? sb : -CUDART_INF_F;
+        if (t1 < te) e[t1] = (t1 < len) ? sb : -CUDART_INF_F;
       }
     }
   } else {
-    for (int t = warp; t < Tm; t += NW) {
+    for (int t = tb + warp; t < te; t += NW) {
       float s = 0.f;
       if (t < len) {
         for (int c = lane; c < A; c += 32) {
@@ -483,7 +501,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
       cpart[t] = c > 0.5f ? 1.f : 0.f;
     }
     __syncthreads();
-    for (int t = tid; t < Tm; t += NT) {
+    for (int t = tb + tid; t < te; t += NT) {
       const bool sl = t + a.win_left + 1 < Tm ? cpart[t + a.win_left + 1] != 0.f : true;
       const bool sr = t - a.win_right >= 0 ? cpart[t - a.win_right] != 0.f : false;
       if (!(sl != sr)) e[t] = -CUDART_INF_F;
@@ -492,6 +510,52 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   }
   // phase 3: alignments from the masked scores: softmax, or sigmoid / normalised sigmoid (components/attention.py:41-55;
   // tf.sigmoid(-inf) = 0 on the masked positions)
+  if (CS > 1) {
+    // the cluster form: statistics of this CTA's range, one exchange, then the global normalisation
+    float mx = -CUDART_INF_F, sum = 0.f;
+    if (a.prob == 0) {
+      for (int t = tb + tid; t < te; t += NT) mx = fmaxf(mx, e[t]);
+      mx = block_reduce(mx, red, true);
+      for (int t = tb + tid; t < te; t += NT) {
+        const float p = (t < len && e[t] > -CUDART_INF_F) ? expf(e[t] - mx) : 0.f;
+        e[t] = p;
+        sum += p;
+      }
+    } else {
+      for (int t = tb + tid; t < te; t += NT) {
+        const float p = (t < len) ? 1.f / (1.f + expf(-e[t])) : 0.f;
+        e[t] = p;
+        sum += p;
+      }
+    }
+    sum = block_reduce(sum, red, false);
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    if (tid < CS) {
+      float* px = cluster.map_shared_rank(xstat, tid) + cr * 4;
+      px[0] = mx; px[1] = sum;
+    }
+    cluster.sync();
+    float scale = 1.f;
+    if (a.prob == 0) {
+      float M = -CUDART_INF_F, total = 0.f;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) M = fmaxf(M, xstat[c * 4]);
+#pragma unroll
+      for (int c = 0; c < CS; ++c) total += xstat[c * 4 + 1] > 0.f ? xstat[c * 4 + 1] * expf(xstat[c * 4] - M) : 0.f;
+      scale = sum > 0.f ? expf(mx - M) / total : 0.f;
+    } else if (a.prob == 1) {
+      float total = 0.f;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) total += xstat[c * 4 + 1];
+      scale = 1.f / total;
+      if (a.asum_save && tid == 0 && cr == 0) a.asum_save[r] = total;
+    }
+    for (int t = tb + tid; t < te; t += NT) {
+      const float p = e[t] * scale;
+      e[t] = p;
+      a.align_new[(size_t)r * Tm + t] = p;
+    }
+  } else
   if (a.prob == 0) {
     float mx = -CUDART_INF_F;
     for (int t = tid; t < Tm; t += NT) mx = fmaxf(mx, e[t]);
@@ -539,10 +603,11 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
     const int TS = NT / NC4 > 0 ? NT / NC4 : 1;            // E <= 1024 -> NC4 <= 256
     const int cg = tid % NC4, ts = tid / NC4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int lim = min(te, len);                          // this CTA's valid positions end here
     if (ts < TS) {
-      int t = ts;
+      int t = tb + ts;
 #pragma unroll 1
-      for (; t + 3 * TS < len; t += 4 * TS) {
+      for (; t + 3 * TS < lim; t += 4 * TS) {
         const float4 x0 = __ldg(reinterpret_cast<const float4*>(values + (size_t)(t) * E) + cg);
         const float4 x1 = __ldg(reinterpret_cast<const float4*>(values + (size_t)(t + TS) * E) + cg);
         const float4 x2 = __ldg(reinterpret_cast<const float4*>(values + (size_t)(t + 2 * TS) * E) + cg);
@@ -553,7 +618,7 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
         acc.z += (e0 * x0.z + e1 * x1.z) + (e2 * x2.z + e3 * x3.z);
         acc.w += (e0 * x0.w + e1 * x1.w) + (e2 * x2.w + e3 * x3.w);
       }
-      for (; t < len; t += TS) {
+      for (; t < lim; t += TS) {
         const float4 x0 = __ldg(reinterpret_cast<const float4*>(values + (size_t)t * E) + cg);
         const float e0 = e[t];
         acc.x = fmaf(e0, x0.x, acc.x); acc.y = fmaf(e0, x0.y, acc.y); acc.z = fmaf(e0, x0.z, acc.z); acc.w = fmaf(e0, x0.w, acc.w);
@@ -565,17 +630,33 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
       float s = 0.f;
       for (int k = 0; k < TS; ++k) s += cpart[(size_t)(k * NC4 + (i >> 2)) * 4 + (i & 3)];
       ctx[i] = s;
-      a.ctx_new[(size_t)r * E + i] = s;
-      a.ctxT_new[(size_t)i * a.R + r] = s;
     }
   } else {
     for (int i = tid; i < E; i += NT) {
       float s = 0.f;
-      for (int t = 0; t < len; ++t) s = fmaf(e[t], values[(size_t)t * E + i], s);
+      for (int t = tb; t < min(te, len); ++t) s = fmaf(e[t], values[(size_t)t * E + i], s);
       ctx[i] = s;
-      a.ctx_new[(size_t)r * E + i] = s;
-      a.ctxT_new[(size_t)i * a.R + r] = s;
     }
+  }
+  if (CS > 1) {
+    // partial contexts into slot cr of every other CTA; summed in CTA order so that every CTA holds the same bits
+    for (int i = tid; i < E; i += NT) {
+      const float s = ctx[i];
+      for (int pc = 0; pc < CS; ++pc)
+        if (pc != cr) cluster.map_shared_rank(xctx, pc)[(size_t)cr * E + i] = s;
+    }
+    cluster.sync();                          // no remote access after this
+    if (cr != 0) return;                     // the output projection and the row's outputs are CTA 0's
+    for (int i = tid; i < E; i += NT) {
+      float s = 0.f;
+      for (int pc = 0; pc < CS; ++pc) s += pc == cr ? ctx[i] : xctx[(size_t)pc * E + i];
+      ctx[i] = s;
+    }
+  }
+  for (int i = tid; i < E; i += NT) {        // (each thread reads back what it wrote)
+    const float s = ctx[i];
+    a.ctx_new[(size_t)r * E + i] = s;
+    a.ctxT_new[(size_t)i * a.R + r] = s;
   }
   __syncthreads();
   if (a.outin_save) {
@@ -616,11 +697,31 @@ __global__ void __launch_bounds__(512) dec_attn_step_kernel(const AttnStepArgs a
   }
 }
 
-inline size_t attn_step_smem(int Tm, int E, int H, int A, int F, int ksz) {
+inline size_t attn_step_smem(int Tm, int E, int H, int A, int F, int ksz, int cs = 1) {
   // the arrays read with 128-bit accesses (q, wd, vs, cpart) must start on 16-byte boundaries: round every piece up to 4
   auto r4 = [](size_t n) { return (n + 3) & ~(size_t)3; };
   return (r4(H) + r4(A) + r4(Tm + ksz + 4) + r4(Tm) + r4(E) + 32 + 512 + r4((size_t)Tm * F) + r4((size_t)F * A) +
-          r4((size_t)ksz * F) + r4(A) + 2048) * sizeof(float);
+          r4((size_t)ksz * F) + r4(A) + 2048 + 16 + (cs > 1 ? (size_t)cs * E : 0)) * sizeof(float);
+}
+// CTAs per decoder row of the attention step: clusters only for training-size batches (one memory per row) that cannot
+// fill the SMs on their own (NABU_ATTN_FWD_CLUSTER=1|2|4 forces)
+inline int attn_step_cluster(int rows, int rows_per_mem) {
+  static int forced = -1;
+  if (forced < 0) forced = getenv("NABU_ATTN_FWD_CLUSTER") ? atoi(getenv("NABU_ATTN_FWD_CLUSTER")) : 0;
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  if (rows_per_mem != 1) return 1;
+  return rows * 4 <= 160 ? 4 : rows * 2 <= 160 ? 2 : 1;
+}
+inline cudaError_t attn_step_launch(const AttnStepArgs& a, int rows, size_t* smem_out, cudaStream_t stream) {
+  const int cs = attn_step_cluster(rows, a.rows_per_mem);
+  const size_t smem = attn_step_smem(a.Tm, a.E, a.H, a.A, a.F, a.ksz, cs);
+  if (smem_out) *smem_out = smem;
+  void (*fn)(const AttnStepArgs) = cs == 4 ? dec_attn_step_kernel<4> : cs == 2 ? dec_attn_step_kernel<2> : dec_attn_step_kernel<1>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  return chain_launch(fn, dim3(rows * cs), dim3(512), smem, stream, a);
 }
 
 // ------------------------------------------------------------------------------------------------
