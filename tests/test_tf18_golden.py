@@ -12,7 +12,7 @@ import pytest
 import torch
 
 import oracle as O
-from tests.util import rel_err
+from tests.util import ParityLog, rel_err
 
 _GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 # tf18/: dumps of a real TF-1.8 run (tools/tf18_dump.py; none committed).  tf18shim_cases/: the reference's own Python
@@ -65,8 +65,23 @@ def test_committed_shim_cases_are_what_the_reference_code_produces(tmp_path):
                 assert np.array_equal(new[k], old[k]), (name, fname, k)
 
 
+def _oracle_tol(case):
+    """shim cases are fp64 results stored as float32: the fp64 oracle must reproduce them to storage rounding; a real
+    TF-1.8 dump is fp32 arithmetic: the north star's 1e-4"""
+    return 1e-6 if 'tf18shim_cases' in case else TOL
+
+
 def _check_oracle_case(case):
     conf, inp, out = _load(case)
+    global TOL
+    keep, TOL = TOL, _oracle_tol(case)
+    try:
+        return _check_oracle_case_at(case, conf, inp, out)
+    finally:
+        TOL = keep
+
+
+def _check_oracle_case_at(case, conf, inp, out):
     model = _model(conf, 'cpu', case, inp['features'].shape[2])
     params = model.store.to_numpy()
     assert set('grad/' + n for n in params) == set(k for k in out if k.startswith('grad/'))
@@ -182,6 +197,7 @@ def _check_cuda_case(case):
     from nabu_b200.neuralnetworks.decoders import decoder_factory
     from nabu_b200.neuralnetworks.trainers import loss_functions
     conf, inp, out = _load(case)
+    log = ParityLog('tf18_' + os.path.basename(case))
     dev = torch.device('cuda', 0)
     model = _model(conf, dev, case, inp['features'].shape[2])
     mc = conf['model.cfg']
@@ -195,10 +211,11 @@ def _check_cuda_case(case):
     got = logits[o_name].detach().cpu().numpy()
     assert np.array_equal(logit_len[o_name].cpu().numpy(), out['logits_len'])
     for b, n in enumerate(out['logits_len']):
-        assert rel_err(got[b, :n], out['logits'][b, :n]) < TOL
-    assert abs(float(loss.detach()) - float(out["loss"])) / abs(float(out["loss"])) < TOL
+        log.check('logits[%d]' % b, got[b, :n], out['logits'][b, :n], TOL)
+    log.check('loss', np.array([float(loss.detach())]), np.array([float(out['loss'])]), TOL)
     for name, g in model.store.grads_numpy().items():
-        assert rel_err(g, out['grad/' + name]) < 5 * TOL, name
+        log.check('grad/' + name, g, out['grad/' + name], TOL)          # the north star's 1e-4, of the tensor's scale
+    log.dump()
     decoder = decoder_factory.factory(conf['recognizer.cfg'].get('decoder', 'decoder'))(conf['recognizer.cfg'], model)
     dec = decoder(batch[0], batch[1])[o_name]
     if 'decoded_values' in out:                       # ctc_decoder: sparse ids, bit-exact
