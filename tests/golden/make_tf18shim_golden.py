@@ -113,33 +113,76 @@ def _livelier_values(variables, seed):
             v.t.copy_(v.t.float().double())                   # the values ARE float32 numbers
 
 
-def _decode(recognizer_cfg, model, inp, bits):
+def _decode(recognizer_cfg, model, inp, bits, i_name='features', o_name='text'):
     """a new graph (names start over, variables stay = restored) in the given precision, through the reference's
     decoder_factory and the decoder's own __call__"""
     from nabu.neuralnetworks.decoders import decoder_factory
     tf.reset_default_graph()
     tf.cast_variables_(bits)
     decoder = decoder_factory.factory(recognizer_cfg.get('decoder', 'decoder'))(recognizer_cfg, model)
-    out = decoder({'features': tf.constant(inp['features'])}, {'features': tf.constant(inp['features_len'])})['text']
+    out = decoder({i_name: tf.constant(inp['features'])}, {i_name: tf.constant(inp['features_len'])})[o_name]
     tf.cast_variables_(64)
     return out
 
 
 def make_case(name, case, seed):
+    ctc = case['kind'] == 'ctc'
+    model_cfg = _conf((DBLSTM if ctc else LAS) % case)
+    trainer_cfg = _conf(CTC_TRAINER if ctc else CE_TRAINER)
+    recognizer_cfg = _conf(CTC_RECOGNIZER if ctc else BEAM_RECOGNIZER % case)
+    return run_case(os.path.join(OUT, name), model_cfg, trainer_cfg, recognizer_cfg, _inputs(case, seed + 1), seed)
+
+
+def make_recipe_case(recipe_dir, path, seed=100, B=3, T=60, max_steps=12, beam_width=None):
+    """the reference's own SHIPPED recipe (config/recipes/<...>/{model,trainer,recognizer}.cfg, unchanged except that the
+    stochastic parts are off - input_noise 0, dropout 1, sample_prob 0 - and the beam search is cut to `max_steps`)"""
+    def read(fname):
+        conf = configparser.ConfigParser()
+        conf.read(os.path.join(recipe_dir, fname))
+        return conf
+    model_cfg, trainer_cfg, recognizer_cfg = read('model.cfg'), read('trainer.cfg'), read('recognizer.cfg')
+    model_cfg.set('encoder', 'input_noise', '0')
+    model_cfg.set('encoder', 'dropout', '1')
+    las = model_cfg.get('decoder', 'decoder') == 'speller'
+    if las:
+        model_cfg.set('decoder', 'dropout', '1')
+        model_cfg.set('decoder', 'sample_prob', '0')
+        recognizer_cfg.set('decoder', 'max_steps', str(max_steps))
+        if beam_width:
+            recognizer_cfg.set('decoder', 'beam_width', str(beam_width))
+    V = int(model_cfg.get('io', 'output_dims').split(' ')[0])
+    rng = np.random.RandomState(seed + 1)
+    x = rng.randn(B, T, 40).astype(np.float32)
+    xl = rng.randint(int(0.6 * T), T + 1, size=B).astype(np.int32)
+    xl[0] = T
+    if las:
+        yl = rng.randint(3, 8, size=B).astype(np.int32)
+        y = rng.randint(0, V, size=(B, int(yl.max()))).astype(np.int32)
+        for b in range(B):
+            y[b, yl[b] - 1] = V
+    else:
+        yl = np.maximum(xl // 10, 1).astype(np.int32)
+        y = rng.randint(0, V, size=(B, int(yl.max()))).astype(np.int32)
+    for b in range(B):
+        x[b, xl[b]:] = 0
+        y[b, yl[b]:] = 0
+    return run_case(path, model_cfg, trainer_cfg, recognizer_cfg,
+                    dict(features=x, features_len=xl, targets=y, targets_len=yl), seed)
+
+
+def run_case(path, model_cfg, trainer_cfg, recognizer_cfg, inp, seed):
     from nabu.neuralnetworks.models.model import Model
     from nabu.neuralnetworks.trainers import loss_functions
 
     tf.reset_all(seed)
     tf.set_float_bits(64)
-    ctc = case['kind'] == 'ctc'
-    model_cfg = _conf((DBLSTM if ctc else LAS) % case)
-    trainer_cfg = _conf(CTC_TRAINER if ctc else CE_TRAINER)
-    recognizer_cfg = _conf(CTC_RECOGNIZER if ctc else BEAM_RECOGNIZER % case)
-    inp = _inputs(case, seed + 1)
+    i_name = model_cfg.get('io', 'inputs').split(' ')[0]
+    o_name = model_cfg.get('io', 'outputs').split(' ')[0]
+    ctc = trainer_cfg.get('trainer', 'loss') == 'CTC'
 
     # ---- the training graph: Model, loss function, gradients (reference trainer.py:297-371 builds exactly these)
     model = Model(conf=model_cfg, trainlabels=int(trainer_cfg.get('trainer', 'trainlabels')), constraint=None)
-    feed = lambda key: {('features' if key.startswith('features') else 'text'): tf.constant(inp[key])}   # noqa: E731
+    feed = lambda key: {(i_name if key.startswith('features') else o_name): tf.constant(inp[key])}   # noqa: E731
     model(feed('features'), feed('features_len'), feed('targets'), feed('targets_len'), True)   # creates the variables
     _livelier_values(model.variables, seed)
     tf.reset_default_graph()
@@ -149,7 +192,7 @@ def make_case(name, case, seed):
     variables = model.variables
     assert len(set(v.op.name for v in variables)) == len(variables) == len(tf.global_variables())
     loss.t.backward()
-    out = {'logits': logits['text'].numpy().astype(np.float32), 'logits_len': logit_len['text'].numpy().astype(np.int32),
+    out = {'logits': logits[o_name].numpy().astype(np.float32), 'logits_len': logit_len[o_name].numpy().astype(np.int32),
            'loss': np.float32(loss.numpy())}
     for v in variables:
         assert v.t.grad is not None, v.op.name
@@ -157,14 +200,14 @@ def make_case(name, case, seed):
     params = {v.op.name: v.numpy().astype(np.float32) for v in variables}
 
     # ---- the decoding graph (reference recognizer.py:60-83)
-    dec64 = _decode(recognizer_cfg, model, inp, 64)
+    dec64 = _decode(recognizer_cfg, model, inp, 64, i_name, o_name)
     assert len(tf.global_variables()) == len(variables), 'the decoding graph created variables of its own'
     if ctc:
         out['decoded_indices'] = dec64.indices.numpy().astype(np.int64)
         out['decoded_values'] = dec64.values.numpy().astype(np.int32)
         out['decoded_shape'] = dec64.dense_shape.numpy().astype(np.int64)
     else:
-        dec32 = _decode(recognizer_cfg, model, inp, 32)
+        dec32 = _decode(recognizer_cfg, model, inp, 32, i_name, o_name)
         seq64, len64 = dec64[0].numpy(), dec64[1].numpy()
         seq32, len32 = dec32[0].numpy(), dec32[1].numpy()
         if not (np.array_equal(len64, len32) and np.array_equal(seq64, seq32)):
@@ -175,7 +218,6 @@ def make_case(name, case, seed):
 
     # ---- write
     from nabu_b200.processing.tfcheckpoint import write_checkpoint
-    path = os.path.join(OUT, name)
     if os.path.isdir(path):
         shutil.rmtree(path)
     os.makedirs(path)
@@ -195,6 +237,12 @@ def make_case(name, case, seed):
 
 def main():
     py2ref.install(os.environ.get('NABU_REFERENCE', '/root/reference'))
+    if len(sys.argv) > 3 and sys.argv[1] == '--recipe':          # --recipe <recipe dir> <output dir> [seed]
+        for seed in range(int(sys.argv[4]) if len(sys.argv) > 4 else 100, 140):
+            if make_recipe_case(sys.argv[2], sys.argv[3], seed) is not None:
+                print('%s: seed %d' % (sys.argv[2], seed))
+                return
+        raise RuntimeError('no robust seed')
     only = sys.argv[1:]
     for name, case in CASES.items():
         if only and name not in only:
