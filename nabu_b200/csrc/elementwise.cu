@@ -182,6 +182,7 @@ extern "C" int nabu_pyramid_lengths(const int* len, int B, int numsteps, int* ou
 extern "C" int nabu_linear_fwd(const float* x, int N, int D, int V, const float* W, const float* b, float* y,
                                void* workspace, size_t ws_bytes, void* stream) {
   (void)workspace; (void)ws_bytes;
+  if (linear_skinny_eligible(x, N, D, V)) return linear_skinny_fwd(x, N, D, V, W, b, y, (cudaStream_t)stream);
   return gemm(GEMM_NN, N, V, D, 1.f, x, D, W, V, 0.f, y, V, b, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
@@ -190,10 +191,13 @@ extern "C" int nabu_linear_bwd(const float* x, int N, int D, int V, const float*
   cudaStream_t stream = (cudaStream_t)stream_;
   if (dx)
     if (int e = gemm(GEMM_NT, N, D, V, 1.f, dy, V, W, V, 0.f, dx, D, nullptr, nullptr, nullptr, 0, stream)) return e;
-  if (dW)
+  if (dW && linear_skinny_eligible(x, N, D, V) && workspace && ws_bytes >= (size_t)D * 32 * sizeof(float)) {
+    if (int e = linear_skinny_dw(x, N, D, V, dy, dW, (float*)workspace, ws_bytes, stream)) return e;
+  } else if (dW) {
     if (int e = gemm(GEMM_TN, D, V, N, 1.f, x, D, dy, V, 0.f, dW, V, nullptr, nullptr, (float*)workspace, ws_bytes,
                       stream))
       return e;
+  }
   if (db)
     if (int e = colsum(dy, N, V, V, db, stream)) return e;
   return 0;

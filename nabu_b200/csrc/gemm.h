@@ -59,6 +59,12 @@ bool gemm_h2_eligible(GemmMode mode, int M, int N, int K);
 int gemm_h2_auto(GemmMode mode, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
                  float beta, float* C, int ldc, const float* bias, void* workspace, size_t ws_bytes, cudaStream_t stream);
 
+// Output layers with V <= 32 units (linear_skinny.cu): HBM-bound FFMA kernels, y = x.W + b and dW = x^T.dy
+bool linear_skinny_eligible(const float* x, int N, int D, int V);
+int linear_skinny_fwd(const float* x, int N, int D, int V, const float* W, const float* b, float* y, cudaStream_t stream);
+int linear_skinny_dw(const float* x, int N, int D, int V, const float* dy, float* dW, float* workspace, size_t ws_bytes,
+                     cudaStream_t stream);
+
 // out[n] = sum_m X[m,n]
 int colsum(const float* X, int M, int N, int ldx, float* out, cudaStream_t stream);
 

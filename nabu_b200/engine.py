@@ -249,11 +249,16 @@ class _BLSTM(torch.autograd.Function):
         ctx.need_dx = x.requires_grad
         out_planes = y_planes if y_planes is not None else torch.empty(0, dtype=torch.uint8, device=x.device)
         ctx.mark_non_differentiable(out_planes)
+        # without this autograd hands backward() a zero-filled "gradient" of the planes: a 786 MB byte fill per layer at cfg-3
+        # (5 x 0.2 ms per step in profiles/r2f_launches_step.csv)
+        ctx.set_materialize_grads(False)
         return y, out_planes
 
     @staticmethod
     def backward(ctx, dy, _dplanes):
         x, lens, kf, kb, y, gates, cells = ctx.saved_tensors
+        if dy is None:
+            dy = torch.zeros_like(y)
         dx = _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, ctx.need_dx, ctx.H, ctx.yT, ctx.gvars, ctx.x_planes,
                             ctx.y_planes)
         return dx, None, None, None, None, None, None, None, None, None

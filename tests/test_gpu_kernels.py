@@ -189,6 +189,36 @@ def test_linear_and_ce():
     assert rel_err(grad.cpu().numpy(), d_ref) < TOL
 
 
+@pytest.mark.parametrize('N,D,V', [(333, 256, 29), (64 * 5 + 1, 1024, 29), (7, 512, 32), (1000, 1024, 5), (4099, 512, 30)])
+def test_linear_output_layer_with_few_units(N, D, V):
+    """dnn_decoder.py:53-57 at the shapes linear_skinny.cu takes (V <= 32, D % 256 == 0): ragged N, every row tile / row
+    chunk boundary, against the fp64 oracle; twice, bit-identical (fixed summation order)."""
+    from nabu_b200 import lib as L
+    lib = L.load()
+    rng = np.random.default_rng(N + D + V)
+    x = rng.standard_normal((N, D)).astype(np.float32)
+    p = O.init_linear_params(rng, D, V)
+    p['biases'] = rng.standard_normal(V).astype(np.float32)
+    dy = rng.standard_normal((N, V)).astype(np.float32)
+    y_ref = O.linear_fwd(x, p)
+    dx_ref, g_ref = O.linear_bwd(x, p, dy.astype(np.float64))
+    xd, Wd, bd, dyd = dev(x), dev(p['weights']), dev(p['biases']), dev(dy)
+    ws = torch.empty(lib.nabu_gemm_workspace_bytes(), dtype=torch.uint8, device='cuda')
+    outs = []
+    for _ in range(2):
+        y = torch.full((N, V), 7.0, device='cuda'); dx = torch.empty_like(xd)
+        dW = torch.full_like(Wd, 7.0); db = torch.empty_like(bd)
+        L.check(lib.nabu_linear_fwd(L.ptr(xd), N, D, V, L.ptr(Wd), L.ptr(bd), L.ptr(y), None, 0, L.stream()), 'lf')
+        L.check(lib.nabu_linear_bwd(L.ptr(xd), N, D, V, L.ptr(Wd), L.ptr(dyd), L.ptr(dx), L.ptr(dW), L.ptr(db),
+                                    L.ptr(ws), ws.numel(), L.stream()), 'lb')
+        outs.append((y.cpu().numpy(), dW.cpu().numpy()))
+    assert rel_err(outs[0][0], y_ref) < TOL
+    assert rel_err(outs[0][1], g_ref['weights']) < TOL
+    assert rel_err(dx.cpu().numpy(), dx_ref) < TOL
+    assert rel_err(db.cpu().numpy(), g_ref['biases']) < TOL
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_clip_adam_matches_tf_formula():
     from nabu_b200 import lib as L
     lib = L.load()
