@@ -13,9 +13,16 @@
 //     and the weight operand of NN) get one global S; the quantisation floor 2^-36 * max is far below the
 //     2^-24 * sqrt(K) rounding noise of the fp32 accumulation itself.
 // The kernel then needs no converter: TMA -> tcgen05.mma.kind::f16 x 3 per k-step (D1 += Ah.Bh, D2 += Ah.Bl + Al.Bh),
-// epilogue out = (D1 + D2 * 2^-11) / (S_A S_B).  One CTA = one 128 x 256 tile, BK = 64, 2 stages of 96 KB, TMEM
-// 512 columns (two fp32 accumulators).  K-major and MN-major SWIZZLE_128B operand layouts, so NN / NT / TN and the
-// per-utterance row segmentation of dKh need no transposes.
+// epilogue out = (D1 + D2 * 2^-11) / (S_A S_B).  One CTA = one 128 x 256 tile, TMEM 512 columns (two fp32 accumulators).
+// K-major (SWIZZLE_64B) and MN-major (SWIZZLE_128B) operand layouts, so NN / NT / TN and the per-utterance row
+// segmentation of dKh need no transposes.
+// Round 2, last revision (tools/gemm_bench.py, 192 000 x 2048 outputs: time per tile = 1.19 us per 64 of K + 7.5 us):
+//   * BK = 32 in FOUR stages of 48 KB instead of BK = 64 in two of 96 KB: with two stages only one stage's bytes are in
+//     flight while the other is multiplied, and a fill (L2 latency + 96 KB at one SM's L2 bandwidth, 1.6 us) took twice
+//     the 0.8 us of its 12 MMAs; three stages of 48 KB in flight cover the latency;
+//   * EIGHT epilogue warps instead of four (two per TMEM lane quadrant, four 32-column chunks each; the transposition
+//     buffers live in the pipeline stages, which are idle by then): the drain of a tile was bound by the instruction
+//     latencies of one warp per scheduler.
 #include "common.cuh"
 #include "gemm.h"
 #include "tc_common.cuh"
@@ -26,13 +33,16 @@ namespace {
 
 using namespace tc;
 
-constexpr int H2_BM = 128, H2_BN = 256, H2_BK = 64, H2_STAGES = 2;
-constexpr int H2_THREADS = 192;
-constexpr int H2_A_TILE = H2_BM * H2_BK * 2;             // 16 KB
-constexpr int H2_B_TILE = H2_BN * H2_BK * 2;             // 32 KB
-constexpr int H2_STAGE = 2 * H2_A_TILE + 2 * H2_B_TILE;  // 96 KB
+constexpr int H2_BM = 128, H2_BN = 256, H2_BK = 32, H2_STAGES = 4;
+constexpr int H2_EPI_WARPS = 8;
+constexpr int H2_THREADS = 64 + 32 * H2_EPI_WARPS;
+constexpr int H2_A_TILE = H2_BM * H2_BK * 2;             // 8 KB
+constexpr int H2_B_TILE = H2_BN * H2_BK * 2;             // 16 KB
+constexpr int H2_STAGE = 2 * H2_A_TILE + 2 * H2_B_TILE;  // 48 KB
+constexpr int H2_MN_BLK = 64 * H2_BK * 2;                // one 64-wide M/N block of an MN-major tile: BK rows of 128 B
 constexpr int H2_TPAD = 36;                              // padded row of the epilogue transpose buffer (floats)
-constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256 + 4 * 32 * H2_TPAD * 4 + 2 * H2_BN * 4;   // + column scale / bias of the tile
+constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256 + 2 * H2_BN * 4;   // + barriers, column scale / bias of the tile
+static_assert(H2_EPI_WARPS * 32 * H2_TPAD * 4 <= H2_STAGES * H2_STAGE, "epilogue transposition buffers live in the stages");
 
 struct H2Args {
   int M, N;
@@ -104,8 +114,8 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int seg = kb / g.kps, kk = (kb % g.kps) * H2_BK;
         if (g.a_mn_major) {
           for (int j = 0; j < H2_BM / 64; ++j) {
-            tma_load_3d(sa + j * 8192, &mapAh, bar_full(s), m0 + 64 * j, kk, seg);
-            tma_load_3d(sa + H2_A_TILE + j * 8192, &mapAl, bar_full(s), m0 + 64 * j, kk, seg);
+            tma_load_3d(sa + j * H2_MN_BLK, &mapAh, bar_full(s), m0 + 64 * j, kk, seg);
+            tma_load_3d(sa + H2_A_TILE + j * H2_MN_BLK, &mapAl, bar_full(s), m0 + 64 * j, kk, seg);
           }
         } else {
           tma_load_3d(sa, &mapAh, bar_full(s), kb * H2_BK, m0, 0);
@@ -113,8 +123,8 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         }
         if (g.b_mn_major) {
           for (int j = 0; j < H2_BN / 64; ++j) {
-            tma_load_3d(sb + j * 8192, &mapBh, bar_full(s), n0 + 64 * j, kk, seg);
-            tma_load_3d(sb + H2_B_TILE + j * 8192, &mapBl, bar_full(s), n0 + 64 * j, kk, seg);
+            tma_load_3d(sb + j * H2_MN_BLK, &mapBh, bar_full(s), n0 + 64 * j, kk, seg);
+            tma_load_3d(sb + H2_B_TILE + j * H2_MN_BLK, &mapBl, bar_full(s), n0 + 64 * j, kk, seg);
           }
         } else {
           tma_load_3d(sb, &mapBh, bar_full(s), kb * H2_BK, n0, 0);
@@ -126,11 +136,13 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(H2_BM, H2_BN, g.a_mn_major, g.b_mn_major);
-      // K-major SWIZZLE_128B: rows of 128 B (64 fp16 of K), 8-row groups 1024 B apart (SBO), k-step (16) = +32 B.
+      // K-major SWIZZLE_64B: rows of 64 B (32 fp16 of K), 8-row groups 512 B apart (SBO), k-step (16) = +32 B.
       // MN-major SWIZZLE_128B: rows of 128 B (64 fp16 of M/N) per k, 8-k groups 1024 B apart (SBO), 64-wide M/N
-      // blocks 8192 B apart (LBO), k-step (16 rows) = +2048 B.
-      const uint32_t a_lbo = g.a_mn_major ? 8192u : 16u, b_lbo = g.b_mn_major ? 8192u : 16u;
+      // blocks H2_MN_BLK = 4096 B apart (LBO), k-step (16 rows) = +2048 B.
+      const uint32_t a_lbo = g.a_mn_major ? (uint32_t)H2_MN_BLK : 16u, b_lbo = g.b_mn_major ? (uint32_t)H2_MN_BLK : 16u;
       const uint32_t a_kstep = g.a_mn_major ? 2048u : 32u, b_kstep = g.b_mn_major ? 2048u : 32u;
+      const uint32_t a_sbo = g.a_mn_major ? 1024u : 512u, b_sbo = g.b_mn_major ? 1024u : 512u;
+      const uint32_t a_lay = g.a_mn_major ? 2u : 4u, b_lay = g.b_mn_major ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
       for (int i = 0; i < nkb; ++i) {
         const int s = i % H2_STAGES;
         const uint32_t ph = (i / H2_STAGES) & 1;
@@ -140,10 +152,10 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const uint32_t sb = sa + 2 * H2_A_TILE;
 #pragma unroll
         for (int k = 0; k < H2_BK / 16; ++k) {
-          const uint64_t a_hi = make_desc(sa + k * a_kstep, a_lbo, 1024u, 2u);
-          const uint64_t a_lo = make_desc(sa + H2_A_TILE + k * a_kstep, a_lbo, 1024u, 2u);
-          const uint64_t b_hi = make_desc(sb + k * b_kstep, b_lbo, 1024u, 2u);
-          const uint64_t b_lo = make_desc(sb + H2_B_TILE + k * b_kstep, b_lbo, 1024u, 2u);
+          const uint64_t a_hi = make_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t a_lo = make_desc(sa + H2_A_TILE + k * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t b_hi = make_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lay);
+          const uint64_t b_lo = make_desc(sb + H2_B_TILE + k * b_kstep, b_lbo, b_sbo, b_lay);
           const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
           umma_f16(tmem_d, a_hi, b_hi, idesc, acc);
           umma_f16(tmem_d + H2_BN, a_hi, b_lo, idesc, acc);
@@ -167,12 +179,15 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     float sa_inv = g.a_glob_inv ? __ldg(g.a_glob_inv) : 1.f;
     if (g.a_row_inv && m < g.M) sa_inv *= __ldg(g.a_row_inv + m);
     sa_inv *= g.b_glob_inv ? __ldg(g.b_glob_inv) : 1.f;
-    float* tbuf = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256) + (warp - 2) * (32 * H2_TPAD);
+    // transposition buffers: in the pipeline stages (every load has landed and every MMA has read its operands once
+    // bar_tmem has fired; nothing is written there before)
+    float* tbuf = reinterpret_cast<float*>(base_ptr) + (warp - 2) * (32 * H2_TPAD);
+    const int chalf = (warp - 2) >> 2;                   // which four 32-column chunks of the tile this warp drains
     // Column scale and bias of this tile are staged in shared memory while the main loop runs (the epilogue warps are
     // idle then); per-chunk global loads of them used to stall every chunk of the epilogue.
-    float* cs_s = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256) + 4 * 32 * H2_TPAD;
+    float* cs_s = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256);
     float* bs_s = cs_s + H2_BN;
-    for (int c = threadIdx.x - 64; c < H2_BN; c += 128) {
+    for (int c = threadIdx.x - 64; c < H2_BN; c += 32 * H2_EPI_WARPS) {
       const int n = n0 + c;
       float cs = 1.f, bs = 0.f;
       if (n < g.N) {
@@ -185,13 +200,14 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       cs_s[c] = cs;
       bs_s[c] = bs;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPI_WARPS) : "memory");
     const int rl = lane >> 3, c4 = (lane & 7) * 4;       // read phase: row within a group of 4, first of 4 columns
     if (nkb > 0) {
       mbar_wait(bar_tmem, 0);
       tc_fence_after();
     }
-    const int nchunks = max(0, min(H2_BN / 32, (g.N - n0 + 31) / 32));
+    const int ch0 = chalf * (H2_BN / 64);
+    const int nchunks = max(ch0, min(ch0 + H2_BN / 64, (g.N - n0 + 31) / 32));     // this warp: chunks [ch0, nchunks)
     uint32_t ra[2][32], rb[2][32];                     // double-buffered TMEM reads: chunk c+1 is in flight during chunk c
     auto issue = [&](int ch, int buf) {
       if (nkb > 0) {
@@ -202,11 +218,12 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         for (int j = 0; j < 32; ++j) ra[buf][j] = rb[buf][j] = 0u;
       }
     };
-    if (nchunks > 0) issue(0, 0);
+    if (nchunks > ch0) issue(ch0, 0);
 #pragma unroll
-    for (int ch = 0; ch < H2_BN / 32; ++ch) {
+    for (int cc = 0; cc < H2_BN / 64; ++cc) {
+      const int ch = ch0 + cc;
       if (ch >= nchunks) break;
-      const int c0 = ch * 32, buf = ch & 1;
+      const int c0 = ch * 32, buf = cc & 1;
       if (nkb > 0) tmem_ld_wait();
       if (ch + 1 < nchunks) issue(ch + 1, buf ^ 1);
 #pragma unroll
@@ -425,6 +442,8 @@ split_global_sub_kernel(const float* __restrict__ src, int ld, int R, int C, con
 
 int make_map_h(CUtensorMap* map, const __half* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                uint64_t stride2, uint32_t box0, uint32_t box1) {
+  // the box's inner extent IS the swizzle span: 64 fp16 = SWIZZLE_128B (MN-major operands), 32 fp16 = SWIZZLE_64B (K-major)
+  const CUtensorMapSwizzle swz = box0 * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   EncodeTiledFn enc = get_encode();
   NABU_REQUIRE(enc != nullptr, "gemm_h2: cuTensorMapEncodeTiled entry point missing");
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -432,7 +451,7 @@ int make_map_h(CUtensorMap* map, const __half* ptr, uint64_t d0, uint64_t d1, ui
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   const int r = (int)enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NABU_REQUIRE(r == 0, "gemm_h2: cuTensorMapEncodeTiled failed (%d)", r);
   return 0;
@@ -520,25 +539,25 @@ int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A,
     NABU_REQUIRE(!A.row_inv && !B.row_inv, "gemm_h2: TN operands take a global scale");
     const uint64_t sA = segp ? (uint64_t)segp->segA : (uint64_t)K, sB = segp ? (uint64_t)segp->segB : (uint64_t)K;
     const size_t oa = segp ? (size_t)segp->offA * A.ld : 0, ob = segp ? (size_t)segp->offB * B.ld : 0;
-    if (int e = make_map_h(&mAh, Ah + oa, M, seg, nseg, A.ld, sA * A.ld, 64, 64)) return e;
-    if (int e = make_map_h(&mAl, Al + oa, M, seg, nseg, A.ld, sA * A.ld, 64, 64)) return e;
-    if (int e = make_map_h(&mBh, Bh + ob, N, seg, nseg, B.ld, sB * B.ld, 64, 64)) return e;
-    if (int e = make_map_h(&mBl, Bl + ob, N, seg, nseg, B.ld, sB * B.ld, 64, 64)) return e;
+    if (int e = make_map_h(&mAh, Ah + oa, M, seg, nseg, A.ld, sA * A.ld, 64, H2_BK)) return e;
+    if (int e = make_map_h(&mAl, Al + oa, M, seg, nseg, A.ld, sA * A.ld, 64, H2_BK)) return e;
+    if (int e = make_map_h(&mBh, Bh + ob, N, seg, nseg, B.ld, sB * B.ld, 64, H2_BK)) return e;
+    if (int e = make_map_h(&mBl, Bl + ob, N, seg, nseg, B.ld, sB * B.ld, 64, H2_BK)) return e;
     g.a_mn_major = 1; g.b_mn_major = 1;
     g.kps = ceil_div(seg, H2_BK);
     g.kblocks = g.kps * nseg;
   } else {
-    if (int e = make_map_h(&mAh, Ah, K, M, 1, A.ld, (uint64_t)M * A.ld, 64, H2_BM)) return e;
-    if (int e = make_map_h(&mAl, Al, K, M, 1, A.ld, (uint64_t)M * A.ld, 64, H2_BM)) return e;
+    if (int e = make_map_h(&mAh, Ah, K, M, 1, A.ld, (uint64_t)M * A.ld, H2_BK, H2_BM)) return e;
+    if (int e = make_map_h(&mAl, Al, K, M, 1, A.ld, (uint64_t)M * A.ld, H2_BK, H2_BM)) return e;
     g.a_mn_major = 0;
     if (mode == GEMM_NN) {
       NABU_REQUIRE(!B.row_inv, "gemm_h2: the NN weight operand takes a global scale");
-      if (int e = make_map_h(&mBh, Bh, N, K, 1, B.ld, (uint64_t)K * B.ld, 64, 64)) return e;
-      if (int e = make_map_h(&mBl, Bl, N, K, 1, B.ld, (uint64_t)K * B.ld, 64, 64)) return e;
+      if (int e = make_map_h(&mBh, Bh, N, K, 1, B.ld, (uint64_t)K * B.ld, 64, H2_BK)) return e;
+      if (int e = make_map_h(&mBl, Bl, N, K, 1, B.ld, (uint64_t)K * B.ld, 64, H2_BK)) return e;
       g.b_mn_major = 1;
     } else {
-      if (int e = make_map_h(&mBh, Bh, K, N, 1, B.ld, (uint64_t)N * B.ld, 64, H2_BN)) return e;
-      if (int e = make_map_h(&mBl, Bl, K, N, 1, B.ld, (uint64_t)N * B.ld, 64, H2_BN)) return e;
+      if (int e = make_map_h(&mBh, Bh, K, N, 1, B.ld, (uint64_t)N * B.ld, H2_BK, H2_BN)) return e;
+      if (int e = make_map_h(&mBl, Bl, K, N, 1, B.ld, (uint64_t)N * B.ld, H2_BK, H2_BN)) return e;
       g.b_mn_major = 0;
     }
     g.kblocks = ceil_div(K, H2_BK);
@@ -546,8 +565,8 @@ int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A,
   }
   const int tiles = ceil_div(M, H2_BM) * ceil_div(N, H2_BN);
   int splits = 1;
-  if (workspace != nullptr && tiles < num_sms() && g.kblocks >= 32) {
-    splits = min(num_sms() / tiles, g.kblocks / 8);
+  if (workspace != nullptr && tiles < num_sms() && g.kblocks >= 64) {          // k blocks of 32: at least 512 of K per split
+    splits = min(num_sms() / tiles, g.kblocks / 16);
     const size_t per = (size_t)M * N * sizeof(float);
     if ((size_t)splits * per > ws_bytes) splits = (int)(ws_bytes / per);
     if (splits < 1) splits = 1;
