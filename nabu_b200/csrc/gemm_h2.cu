@@ -17,23 +17,25 @@
 // K-major (SWIZZLE_64B) and MN-major (SWIZZLE_128B) operand layouts, so NN / NT / TN and the per-utterance row
 // segmentation of dKh need no transposes.
 // Round 2, last revision (tools/gemm_bench.py, 192 000 x 2048 outputs: time per tile = 1.19 us per 64 of K + 7.5 us):
-//   * BK = 32 in FOUR stages of 48 KB instead of BK = 64 in two of 96 KB: with two stages only one stage's bytes are in
-//     flight while the other is multiplied, and a fill (L2 latency + 96 KB at one SM's L2 bandwidth, 1.6 us) took twice
-//     the 0.8 us of its 12 MMAs; three stages of 48 KB in flight cover the latency;
-//   * EIGHT epilogue warps instead of four (two per TMEM lane quadrant, four 32-column chunks each; the transposition
-//     buffers live in the pipeline stages, which are idle by then): the drain of a tile was bound by the instruction
-//     latencies of one warp per scheduler.
+//   * the 1.19 us per 64 of K are 12 MMAs of 128 x 256 x 16 = 1536 tensor-pipe cycles at the ~1.3 GHz the SMs hold
+//     under tensor load (MEASURED_PEAKS.json: 1327 MHz): the main loop is MMA-bound -- BK = 32 in four stages instead of
+//     BK = 64 in two left it unchanged -- and the 7.5 us per tile were launch, pipeline fill and a serial epilogue;
+//   * so the kernel is PERSISTENT (one CTA per SM, items = (split, row tile, column tile), column tile fastest): the TMA
+//     warp runs ahead into the next tile (BK = 32, three stages of 48 KB), EIGHT epilogue warps (two per TMEM lane
+//     quadrant) first pull their 32 x 128 share of D1 + D2 * 2^-11 into registers, hand tensor memory back to the MMA
+//     warp ("drained" barrier) and only then transpose and store, under the next tile's main loop.
 #include "common.cuh"
 #include "gemm.h"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#include <algorithm>
 
 namespace nabu {
 namespace {
 
 using namespace tc;
 
-constexpr int H2_BM = 128, H2_BN = 256, H2_BK = 32, H2_STAGES = 4;
+constexpr int H2_BM = 128, H2_BN = 256, H2_BK = 32, H2_STAGES = 3;
 constexpr int H2_EPI_WARPS = 8;
 constexpr int H2_THREADS = 64 + 32 * H2_EPI_WARPS;
 constexpr int H2_A_TILE = H2_BM * H2_BK * 2;             // 8 KB
@@ -41,8 +43,9 @@ constexpr int H2_B_TILE = H2_BN * H2_BK * 2;             // 16 KB
 constexpr int H2_STAGE = 2 * H2_A_TILE + 2 * H2_B_TILE;  // 48 KB
 constexpr int H2_MN_BLK = 64 * H2_BK * 2;                // one 64-wide M/N block of an MN-major tile: BK rows of 128 B
 constexpr int H2_TPAD = 36;                              // padded row of the epilogue transpose buffer (floats)
-constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256 + 2 * H2_BN * 4;   // + barriers, column scale / bias of the tile
-static_assert(H2_EPI_WARPS * 32 * H2_TPAD * 4 <= H2_STAGES * H2_STAGE, "epilogue transposition buffers live in the stages");
+// stages | barriers (256 B) | column scale and bias of the tile | one transposition buffer per epilogue warp
+constexpr int H2_SMEM = H2_STAGES * H2_STAGE + 1024 + 256 + 2 * H2_BN * 4 + H2_EPI_WARPS * 32 * H2_TPAD * 4;
+static_assert(H2_SMEM <= 227 * 1024, "gemm_h2: shared memory");
 
 struct H2Args {
   int M, N;
@@ -54,6 +57,7 @@ struct H2Args {
   const float* b_row_inv; const float* b_glob_inv;       // 1 / S of B: per output column, or one value, or neither
   float* C; int ldc;
   float* part;
+  int tiles_m, tiles_n, splits;                          // work items of the persistent grid
 };
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -77,14 +81,21 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   const uint32_t bars = base + H2_STAGES * H2_STAGE;
   auto bar_full = [&](int s) { return bars + 8u * s; };
   auto bar_empty = [&](int s) { return bars + 8u * (H2_STAGES + s); };
-  const uint32_t bar_tmem = bars + 8u * (2 * H2_STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + H2_STAGES * H2_STAGE + 8 * (2 * H2_STAGES + 1));
+  const uint32_t bar_tmem = bars + 8u * (2 * H2_STAGES);            // accumulators of a tile complete   (MMA -> epilogue)
+  const uint32_t bar_drained = bars + 8u * (2 * H2_STAGES + 1);     // accumulators read into registers  (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + H2_STAGES * H2_STAGE + 8 * (2 * H2_STAGES + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * H2_BM, n0 = blockIdx.x * H2_BN;
-  const int kb_begin = blockIdx.z * g.kb_per_split;
-  const int kb_end = min(g.kblocks, kb_begin + g.kb_per_split);
-  const int nkb = max(0, kb_end - kb_begin);
+  // Persistent: CTA c works on items c, c + gridDim.x, ...; item = (split z, row tile, column tile), column tile fastest
+  // (the CTAs that run at the same time share their A rows through L2).
+  const int total = g.tiles_n * g.tiles_m * g.splits;
+  auto decode = [&](int item, int* m0, int* n0, int* kb_begin, int* nkb, int* z) {
+    const int tn = item % g.tiles_n, tm = (item / g.tiles_n) % g.tiles_m;
+    *z = item / (g.tiles_n * g.tiles_m);
+    *m0 = tm * H2_BM; *n0 = tn * H2_BN;
+    *kb_begin = *z * g.kb_per_split;
+    *nkb = max(0, min(g.kblocks, *kb_begin + g.kb_per_split) - *kb_begin);
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < H2_STAGES; ++s) {
@@ -92,6 +103,7 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       mbar_init(bar_empty(s), 1);
     }
     mbar_init(bar_tmem, 1);
+    mbar_init(bar_drained, H2_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512u);
@@ -101,34 +113,39 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   const uint32_t tmem_d = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: runs ahead into the next tile while the epilogue of this one drains =====
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int kb = kb_begin + i;
-        const int s = i % H2_STAGES;
-        const uint32_t ph = (i / H2_STAGES) & 1;
-        mbar_wait(bar_empty(s), ph ^ 1);
-        mbar_expect_tx(bar_full(s), H2_STAGE);
-        const uint32_t sa = base + s * H2_STAGE;
-        const uint32_t sb = sa + 2 * H2_A_TILE;
-        const int seg = kb / g.kps, kk = (kb % g.kps) * H2_BK;
-        if (g.a_mn_major) {
-          for (int j = 0; j < H2_BM / 64; ++j) {
-            tma_load_3d(sa + j * H2_MN_BLK, &mapAh, bar_full(s), m0 + 64 * j, kk, seg);
-            tma_load_3d(sa + H2_A_TILE + j * H2_MN_BLK, &mapAl, bar_full(s), m0 + 64 * j, kk, seg);
+      int it = 0;                                        // k blocks issued by this CTA so far (stage / phase counter)
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(item, &m0, &n0, &kb_begin, &nkb, &z);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int kb = kb_begin + i;
+          const int s = it % H2_STAGES;
+          const uint32_t ph = (it / H2_STAGES) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          mbar_expect_tx(bar_full(s), H2_STAGE);
+          const uint32_t sa = base + s * H2_STAGE;
+          const uint32_t sb = sa + 2 * H2_A_TILE;
+          const int seg = kb / g.kps, kk = (kb % g.kps) * H2_BK;
+          if (g.a_mn_major) {
+            for (int j = 0; j < H2_BM / 64; ++j) {
+              tma_load_3d(sa + j * H2_MN_BLK, &mapAh, bar_full(s), m0 + 64 * j, kk, seg);
+              tma_load_3d(sa + H2_A_TILE + j * H2_MN_BLK, &mapAl, bar_full(s), m0 + 64 * j, kk, seg);
+            }
+          } else {
+            tma_load_3d(sa, &mapAh, bar_full(s), kb * H2_BK, m0, 0);
+            tma_load_3d(sa + H2_A_TILE, &mapAl, bar_full(s), kb * H2_BK, m0, 0);
           }
-        } else {
-          tma_load_3d(sa, &mapAh, bar_full(s), kb * H2_BK, m0, 0);
-          tma_load_3d(sa + H2_A_TILE, &mapAl, bar_full(s), kb * H2_BK, m0, 0);
-        }
-        if (g.b_mn_major) {
-          for (int j = 0; j < H2_BN / 64; ++j) {
-            tma_load_3d(sb + j * H2_MN_BLK, &mapBh, bar_full(s), n0 + 64 * j, kk, seg);
-            tma_load_3d(sb + H2_B_TILE + j * H2_MN_BLK, &mapBl, bar_full(s), n0 + 64 * j, kk, seg);
+          if (g.b_mn_major) {
+            for (int j = 0; j < H2_BN / 64; ++j) {
+              tma_load_3d(sb + j * H2_MN_BLK, &mapBh, bar_full(s), n0 + 64 * j, kk, seg);
+              tma_load_3d(sb + H2_B_TILE + j * H2_MN_BLK, &mapBl, bar_full(s), n0 + 64 * j, kk, seg);
+            }
+          } else {
+            tma_load_3d(sb, &mapBh, bar_full(s), kb * H2_BK, n0, 0);
+            tma_load_3d(sb + H2_B_TILE, &mapBl, bar_full(s), kb * H2_BK, n0, 0);
           }
-        } else {
-          tma_load_3d(sb, &mapBh, bar_full(s), kb * H2_BK, n0, 0);
-          tma_load_3d(sb + H2_B_TILE, &mapBl, bar_full(s), kb * H2_BK, n0, 0);
         }
       }
     }
@@ -143,123 +160,139 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const uint32_t a_kstep = g.a_mn_major ? 2048u : 32u, b_kstep = g.b_mn_major ? 2048u : 32u;
       const uint32_t a_sbo = g.a_mn_major ? 1024u : 512u, b_sbo = g.b_mn_major ? 1024u : 512u;
       const uint32_t a_lay = g.a_mn_major ? 2u : 4u, b_lay = g.b_mn_major ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % H2_STAGES;
-        const uint32_t ph = (i / H2_STAGES) & 1;
-        mbar_wait(bar_full(s), ph);
+      int it = 0, j = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(item, &m0, &n0, &kb_begin, &nkb, &z);
+        // the epilogue warps hold the previous tile's accumulators in registers: tensor memory may be overwritten
+        mbar_wait(bar_drained, (uint32_t)(j & 1) ^ 1u);
         tc_fence_after();
-        const uint32_t sa = base + s * H2_STAGE;
-        const uint32_t sb = sa + 2 * H2_A_TILE;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % H2_STAGES;
+          const uint32_t ph = (it / H2_STAGES) & 1;
+          mbar_wait(bar_full(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * H2_STAGE;
+          const uint32_t sb = sa + 2 * H2_A_TILE;
 #pragma unroll
-        for (int k = 0; k < H2_BK / 16; ++k) {
-          const uint64_t a_hi = make_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lay);
-          const uint64_t a_lo = make_desc(sa + H2_A_TILE + k * a_kstep, a_lbo, a_sbo, a_lay);
-          const uint64_t b_hi = make_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lay);
-          const uint64_t b_lo = make_desc(sb + H2_B_TILE + k * b_kstep, b_lbo, b_sbo, b_lay);
-          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          umma_f16(tmem_d, a_hi, b_hi, idesc, acc);
-          umma_f16(tmem_d + H2_BN, a_hi, b_lo, idesc, acc);
-          umma_f16(tmem_d + H2_BN, a_lo, b_hi, idesc, 1u);
+          for (int k = 0; k < H2_BK / 16; ++k) {
+            const uint64_t a_hi = make_desc(sa + k * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t a_lo = make_desc(sa + H2_A_TILE + k * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t b_hi = make_desc(sb + k * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint64_t b_lo = make_desc(sb + H2_B_TILE + k * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+            umma_f16(tmem_d, a_hi, b_hi, idesc, acc);
+            umma_f16(tmem_d + H2_BN, a_hi, b_lo, idesc, acc);
+            umma_f16(tmem_d + H2_BN, a_lo, b_hi, idesc, 1u);
+          }
+          umma_commit(bar_empty(s));
         }
-        umma_commit(bar_empty(s));
+        umma_commit(bar_tmem);
       }
-      umma_commit(bar_tmem);
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> (warp-private smem transpose) -> coalesced global stores =====
+    // ===== epilogue: TMEM -> registers (then the MMA warp may start the next tile) -> warp-private smem transpose ->
+    // coalesced global stores, overlapped with the next tile's main loop =====
     // tcgen05.ld hands every thread one ROW of the tile; storing that directly makes each warp instruction touch 32
-    // rows (measured: 29 us per tile, 0.7 TB/s).  Each warp therefore transposes its 32 x 32 chunk through a padded
+    // rows (measured: 29 us per tile, 0.7 TB/s).  Each warp therefore transposes its 32 x 32 chunks through a padded
     // shared buffer and writes full 128-byte row segments (8 lanes x float4 per row, 4 rows per instruction).
     const int q = warp & 3;
-    const int m = m0 + 32 * q + lane;
     const bool split = g.part != nullptr;
-    float* Cout = split ? g.part + (size_t)blockIdx.z * g.M * g.N : g.C;
     const int ldc = split ? g.N : g.ldc;
-    const bool vec = ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (ldc % 4 == 0);
-    float sa_inv = g.a_glob_inv ? __ldg(g.a_glob_inv) : 1.f;
-    if (g.a_row_inv && m < g.M) sa_inv *= __ldg(g.a_row_inv + m);
-    sa_inv *= g.b_glob_inv ? __ldg(g.b_glob_inv) : 1.f;
-    // transposition buffers: in the pipeline stages (every load has landed and every MMA has read its operands once
-    // bar_tmem has fired; nothing is written there before)
-    float* tbuf = reinterpret_cast<float*>(base_ptr) + (warp - 2) * (32 * H2_TPAD);
+    float* tbuf = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256 + 2 * H2_BN * 4) + (warp - 2) * (32 * H2_TPAD);
     const int chalf = (warp - 2) >> 2;                   // which four 32-column chunks of the tile this warp drains
-    // Column scale and bias of this tile are staged in shared memory while the main loop runs (the epilogue warps are
-    // idle then); per-chunk global loads of them used to stall every chunk of the epilogue.
+    constexpr int NCH = H2_BN / 64;                      // chunks per warp
     float* cs_s = reinterpret_cast<float*>(base_ptr + H2_STAGES * H2_STAGE + 256);
     float* bs_s = cs_s + H2_BN;
-    for (int c = threadIdx.x - 64; c < H2_BN; c += 32 * H2_EPI_WARPS) {
-      const int n = n0 + c;
-      float cs = 1.f, bs = 0.f;
-      if (n < g.N) {
-        if (g.b_row_inv) cs = __ldg(g.b_row_inv + n);
-        if (!split) {
-          cs *= g.alpha;
-          if (g.bias) bs = __ldg(g.bias + n);
-        }
-      }
-      cs_s[c] = cs;
-      bs_s[c] = bs;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPI_WARPS) : "memory");
     const int rl = lane >> 3, c4 = (lane & 7) * 4;       // read phase: row within a group of 4, first of 4 columns
-    if (nkb > 0) {
-      mbar_wait(bar_tmem, 0);
-      tc_fence_after();
-    }
-    const int ch0 = chalf * (H2_BN / 64);
-    const int nchunks = max(ch0, min(ch0 + H2_BN / 64, (g.N - n0 + 31) / 32));     // this warp: chunks [ch0, nchunks)
-    uint32_t ra[2][32], rb[2][32];                     // double-buffered TMEM reads: chunk c+1 is in flight during chunk c
-    auto issue = [&](int ch, int buf) {
-      if (nkb > 0) {
-        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(ch * 32), ra[buf]);
-        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(H2_BN + ch * 32), rb[buf]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ra[buf][j] = rb[buf][j] = 0u;
-      }
-    };
-    if (nchunks > ch0) issue(ch0, 0);
-#pragma unroll
-    for (int cc = 0; cc < H2_BN / 64; ++cc) {
-      const int ch = ch0 + cc;
-      if (ch >= nchunks) break;
-      const int c0 = ch * 32, buf = cc & 1;
-      if (nkb > 0) tmem_ld_wait();
-      if (ch + 1 < nchunks) issue(ch + 1, buf ^ 1);
-#pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        float4 v;
-        v.x = fmaf(__uint_as_float(rb[buf][j4 + 0]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 0])) * sa_inv;
-        v.y = fmaf(__uint_as_float(rb[buf][j4 + 1]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 1])) * sa_inv;
-        v.z = fmaf(__uint_as_float(rb[buf][j4 + 2]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 2])) * sa_inv;
-        v.w = fmaf(__uint_as_float(rb[buf][j4 + 3]), 1.f / 2048.f, __uint_as_float(ra[buf][j4 + 3])) * sa_inv;
-        *reinterpret_cast<float4*>(tbuf + lane * H2_TPAD + j4) = v;
-      }
-      __syncwarp();
-      const int n = n0 + c0 + c4;
-      const float4 cs4 = *reinterpret_cast<const float4*>(cs_s + c0 + c4);
-      const float4 bs4 = *reinterpret_cast<const float4*>(bs_s + c0 + c4);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + rl;
-        const int mm = m0 + 32 * q + rr;
-        const float4 t4 = *reinterpret_cast<const float4*>(tbuf + rr * H2_TPAD + c4);
-        float v[4] = {fmaf(t4.x, cs4.x, bs4.x), fmaf(t4.y, cs4.y, bs4.y), fmaf(t4.z, cs4.z, bs4.z), fmaf(t4.w, cs4.w, bs4.w)};
-        if (mm < g.M && n < g.N) {
-          float* cp = Cout + (size_t)mm * ldc + n;
-          const int nv = min(4, g.N - n);
-          if (nv == 4 && vec) {
-            if (!split && g.beta != 0.f) {
-              const float4 o = *reinterpret_cast<const float4*>(cp);
-              v[0] += g.beta * o.x; v[1] += g.beta * o.y; v[2] += g.beta * o.z; v[3] += g.beta * o.w;
-            }
-            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-            for (int j = 0; j < nv; ++j) cp[j] = (!split && g.beta != 0.f) ? v[j] + g.beta * cp[j] : v[j];
+    const float ag = (g.a_glob_inv ? __ldg(g.a_glob_inv) : 1.f) * (g.b_glob_inv ? __ldg(g.b_glob_inv) : 1.f);
+    int j = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+      int m0, n0, kb_begin, nkb, z;
+      decode(item, &m0, &n0, &kb_begin, &nkb, &z);
+      const int m = m0 + 32 * q + lane;
+      float* Cout = split ? g.part + (size_t)z * g.M * g.N : g.C;
+      const bool vec = ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (ldc % 4 == 0);
+      float sa_inv = ag;
+      if (g.a_row_inv && m < g.M) sa_inv *= __ldg(g.a_row_inv + m);
+      // column scale and bias of this tile -> shared memory (every epilogue warp is done with the previous tile's)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPI_WARPS) : "memory");
+      for (int c = threadIdx.x - 64; c < H2_BN; c += 32 * H2_EPI_WARPS) {
+        const int n = n0 + c;
+        float cs = 1.f, bs = 0.f;
+        if (n < g.N) {
+          if (g.b_row_inv) cs = __ldg(g.b_row_inv + n);
+          if (!split) {
+            cs *= g.alpha;
+            if (g.bias) bs = __ldg(g.bias + n);
           }
         }
+        cs_s[c] = cs;
+        bs_s[c] = bs;
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPI_WARPS) : "memory");
+      const int ch0 = chalf * NCH;
+      const int nchunks = max(ch0, min(ch0 + NCH, (g.N - n0 + 31) / 32));     // this warp: chunks [ch0, nchunks)
+      mbar_wait(bar_tmem, (uint32_t)(j & 1));
+      tc_fence_after();
+      // phase 1: my 32 rows x 128 columns of D1 + D2 * 2^-11, scaled by the row's 1 / S, into registers
+      float acc[NCH][32];
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t ra[16], rb[16];
+          if (nkb > 0 && ch0 + cc < nchunks) {
+            tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)((ch0 + cc) * 32 + h * 16), ra);
+            tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(H2_BN + (ch0 + cc) * 32 + h * 16), rb);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ra[i] = rb[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            acc[cc][h * 16 + i] = fmaf(__uint_as_float(rb[i]), 1.f / 2048.f, __uint_as_float(ra[i])) * sa_inv;
+        }
+      }
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(bar_drained);
+      // phase 2: transpose and store
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) {
+        const int ch = ch0 + cc;
+        if (ch >= nchunks) break;
+        const int c0 = ch * 32;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4)
+          *reinterpret_cast<float4*>(tbuf + lane * H2_TPAD + j4) = make_float4(acc[cc][j4], acc[cc][j4 + 1], acc[cc][j4 + 2], acc[cc][j4 + 3]);
+        __syncwarp();
+        const int n = n0 + c0 + c4;
+        const float4 cs4 = *reinterpret_cast<const float4*>(cs_s + c0 + c4);
+        const float4 bs4 = *reinterpret_cast<const float4*>(bs_s + c0 + c4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rl;
+          const int mm = m0 + 32 * q + rr;
+          const float4 t4 = *reinterpret_cast<const float4*>(tbuf + rr * H2_TPAD + c4);
+          float v[4] = {fmaf(t4.x, cs4.x, bs4.x), fmaf(t4.y, cs4.y, bs4.y), fmaf(t4.z, cs4.z, bs4.z), fmaf(t4.w, cs4.w, bs4.w)};
+          if (mm < g.M && n < g.N) {
+            float* cp = Cout + (size_t)mm * ldc + n;
+            const int nv = min(4, g.N - n);
+            if (nv == 4 && vec) {
+              if (!split && g.beta != 0.f) {
+                const float4 o = *reinterpret_cast<const float4*>(cp);
+                v[0] += g.beta * o.x; v[1] += g.beta * o.y; v[2] += g.beta * o.z; v[3] += g.beta * o.w;
+              }
+              *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+              for (int jj = 0; jj < nv; ++jj) cp[jj] = (!split && g.beta != 0.f) ? v[jj] + g.beta * cp[jj] : v[jj];
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();
@@ -581,7 +614,11 @@ int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A,
   }
   {
     KernelScope ks(mode == GEMM_NN ? "gemm_h2_nn" : mode == GEMM_NT ? "gemm_h2_nt" : "gemm_h2_tn", stream);
-    gemm_h2_kernel<<<dim3(ceil_div(N, H2_BN), ceil_div(M, H2_BM), splits), H2_THREADS, H2_SMEM, stream>>>(mAh, mAl, mBh, mBl, g);
+    g.tiles_n = ceil_div(N, H2_BN); g.tiles_m = ceil_div(M, H2_BM); g.splits = splits;
+    const long total = (long)g.tiles_n * g.tiles_m * splits;
+    NABU_REQUIRE(total < (1L << 31), "gemm_h2: too many tiles");
+    const int grid = (int)std::min<long>(total, num_sms());
+    gemm_h2_kernel<<<grid, H2_THREADS, H2_SMEM, stream>>>(mAh, mAl, mBh, mBl, g);
     NABU_CHECK_LAUNCH();
   }
   if (splits > 1) return splitk_reduce(workspace, splits, C, M, N, ldc, alpha, beta, bias, stream);
