@@ -98,6 +98,16 @@ int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const int* len, 
                           const float* y, const void* y_planes, int yT, float* gates, const float* cells, const float* dy,
                           float* dx, float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
                           void* workspace, size_t ws_bytes, void* stream);
+/* Optional, one-shot (consumed by the NEXT nabu_blstm_bwd / nabu_blstm_bwd_planes call of the calling thread, whatever
+ * its outcome): hand-over of max |dx| between the backward calls of stacked layers (components/layer.py:8-51 stacked by
+ * models/ed_encoders/{dblstm,listener}.py).  The backward recurrence exchanges its gate gradients under one power-of-two
+ * scale taken from max |dy| over the batch; without a hint every call reads dy once to find it.
+ *   dx_absmax_out  device buffer of 128 words: the call also leaves max |dx| there (word 0 = the bits of the float, the
+ *                  other words 0), written by the dX contraction's epilogue on `stream`;
+ *   dy_absmax_in   such a buffer, filled by the call whose dx IS this call's dy (same memory, unmodified -- the caller's
+ *                  responsibility): the pass over dy is skipped.
+ * Either may be NULL.  Results are bit-identical with and without hints. */
+int nabu_blstm_bwd_hints(unsigned* dx_absmax_out, const unsigned* dy_absmax_in);
 
 /* ---- a2: pyramid_stack lengths -------------------------------------------------------------------
  * Replaces components/ops.py:55-58: out[b] = ceil(len[b] / numsteps).  (The data movement of

@@ -974,6 +974,25 @@ extern "C" int nabu_blstm_fwd_planes(const float* x, const void* x_planes, const
   return planes_after();
 }
 
+// One-shot hand-over of max |dx| between the backward calls of consecutive layers (nabu_blstm_bwd_hints).
+namespace {
+struct BwdHints { unsigned* dx_out; const unsigned* dy_in; };
+thread_local BwdHints t_bwd_hints = {nullptr, nullptr};
+// fills the promised max |dx| on every path that did not get it from the dX contraction's epilogue
+struct DxMaxGuard {
+  unsigned* out; const float* dx; size_t rows, cols; cudaStream_t stream; bool filled;
+  ~DxMaxGuard() {
+    if (out && dx && !filled) absmax_accumulate(dx, (int)cols, rows, cols, out, stream);
+  }
+};
+}  // namespace
+
+extern "C" int nabu_blstm_bwd_hints(unsigned* dx_absmax_out, const unsigned* dy_absmax_in) {
+  t_bwd_hints.dx_out = dx_absmax_out;
+  t_bwd_hints.dy_in = dy_absmax_in;
+  return 0;
+}
+
 extern "C" int nabu_blstm_bwd(const float* x, const int* len, int B, int T, int D, int H,
                               const float* kernel_fw, const float* kernel_bw, const float* y, int yT,
                               float* gates, const float* cells, const float* dy, float* dx,
@@ -989,8 +1008,12 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
                                      float* dkernel_fw, float* dbias_fw, float* dkernel_bw, float* dbias_bw,
                                      void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const BwdHints hints = t_bwd_hints;                   // consumed by this call, whatever its outcome
+  t_bwd_hints = BwdHints{nullptr, nullptr};
   NABU_REQUIRE(!x_planes || D % 8 == 0, "blstm_bwd: input planes need D %% 8 == 0 (D=%d)", D);
   NABU_REQUIRE(B > 0 && T > 0 && D > 0 && H > 0 && yT >= T, "blstm_bwd: bad shape");
+  if (hints.dx_out && dx) NABU_CHECK_CUDA(cudaMemsetAsync(hints.dx_out, 0, 512, stream));
+  DxMaxGuard dxmax = {hints.dx_out, dx, (size_t)B * T, (size_t)D, stream, false};
   Ws w = carve(workspace, H, B, T, D);
   NABU_REQUIRE(ws_bytes >= w.total, "blstm_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
   const int H4 = 4 * H;
@@ -1085,9 +1108,16 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
     ov.in_defer = defer;
     int re = 0;
     if (ntile == 1) {
-      if (blstm_bwd_chain_eligible(B, H))
+      if (blstm_bwd_chain_eligible(B, H)) {
+        // max |dy| handed over by the caller (the layer above's dX epilogue wrote it): no pass over dy.  The image is
+        // 128 words, word 0 = the maximum, the others 0 -- what the kernel expects of its per-row array.
+        const bool have_max = hints.dy_in != nullptr && B <= 128;
+        if (have_max) NABU_CHECK_CUDA(cudaMemcpyAsync(w.rowmax, hints.dy_in, 512, cudaMemcpyDeviceToDevice, rs));
         re = blstm_rec_bwd_chain(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched, &ngrp,
-                                 zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr, zplanes ? sz.zglob[zk] : nullptr);
+                                 zplanes ? sz.zh[zk] : nullptr, zplanes ? sz.zl[zk] : nullptr, zplanes ? sz.zglob[zk] : nullptr,
+                                 have_max);
+        if (!launched && have_max) NABU_CHECK_CUDA(cudaMemsetAsync(w.rowmax, 0, 512, rs));   // the fallback computes its own
+      }
       if (!re && !launched && blstm_bwd_cluster8_eligible(B, H)) {
         ngrp = 1;
         re = blstm_rec_bwd_cluster8(kern, g, cc, dy, w.dbpart, w.xchg, w.rowmax, len, B, T, yT, D, H, rs, &launched,
@@ -1221,7 +1251,8 @@ extern "C" int nabu_blstm_bwd_planes(const float* x, const void* x_planes, const
       if (int e = split_global(sz.kperm, 2 * H4, D, 2 * H4, sz.kh, sz.kl, 2 * H4, (unsigned*)(sz.kglob + 8), sz.kglob, stream)) return e;
       H2Operand za = {sz.zh[zk], sz.zl[zk], 2 * H4, nullptr, sz.zglob[zk]};
       H2Operand kb = {sz.kh, sz.kl, 2 * H4, nullptr, sz.kglob};
-      if (int e = gemm_h2(GEMM_NT, B * T, D, 2 * H4, 1.f, za, kb, 0.f, dx, D, nullptr, nullptr, nullptr, 0, stream)) return e;
+      if (int e = gemm_h2(GEMM_NT, B * T, D, 2 * H4, 1.f, za, kb, 0.f, dx, D, nullptr, nullptr, nullptr, 0, stream, hints.dx_out)) return e;
+      dxmax.filled = true;
     }
     NABU_CHECK_CUDA(cudaEventRecord(zs.dx_done[zk], stream));
     zs.dx_recorded[zk] = true;

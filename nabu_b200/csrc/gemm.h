@@ -50,8 +50,12 @@ int split_rows_pair(const float* s0, const float* s1, int ld, int R, int C, void
 int split_global_pair(const float* s0, const float* s1, int ld, int R, int C, void* hi, void* lo, unsigned* maxbits,
                       float* glob_inv, cudaStream_t stream);
 // Same contract as gemm_tc() on pre-split operands.  NN: A rows / B global; NT: A rows, B rows or global; TN: global.
+// absmax_out (optional, device): atomicMax of the bits of max |C| over the outputs written (the caller zeroes it).
 int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A, const H2Operand& B, float beta, float* C,
-            int ldc, const float* bias, const GemmSeg* seg, float* workspace, size_t ws_bytes, cudaStream_t stream);
+            int ldc, const float* bias, const GemmSeg* seg, float* workspace, size_t ws_bytes, cudaStream_t stream,
+            unsigned* absmax_out = nullptr);
+// atomicMax of the bits of max |src| over an [R, C] matrix with row pitch ld into *out (not zeroed here)
+int absmax_accumulate(const float* src, int ld, size_t R, size_t C, unsigned* out, cudaStream_t stream);
 
 // fp32 operands: split both into `workspace` (gemm_h2_auto_workspace_bytes), then gemm_h2.
 size_t gemm_h2_auto_workspace_bytes(GemmMode mode, int M, int N, int K);

@@ -58,6 +58,7 @@ struct H2Args {
   float* C; int ldc;
   float* part;
   int tiles_m, tiles_n, splits;                          // work items of the persistent grid
+  unsigned* absmax_out;                                  // optional: max |C| over the outputs this launch writes (bits of a float, atomicMax)
 };
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -206,6 +207,7 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     float* bs_s = cs_s + H2_BN;
     const int rl = lane >> 3, c4 = (lane & 7) * 4;       // read phase: row within a group of 4, first of 4 columns
     const float ag = (g.a_glob_inv ? __ldg(g.a_glob_inv) : 1.f) * (g.b_glob_inv ? __ldg(g.b_glob_inv) : 1.f);
+    float vmax = 0.f;                                     // max |value stored| by this thread (absmax_out)
     int j = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
       int m0, n0, kb_begin, nkb, z;
@@ -286,13 +288,22 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                 v[0] += g.beta * o.x; v[1] += g.beta * o.y; v[2] += g.beta * o.z; v[3] += g.beta * o.w;
               }
               *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+              vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
             } else {
-              for (int jj = 0; jj < nv; ++jj) cp[jj] = (!split && g.beta != 0.f) ? v[jj] + g.beta * cp[jj] : v[jj];
+              for (int jj = 0; jj < nv; ++jj) {
+                const float o = (!split && g.beta != 0.f) ? v[jj] + g.beta * cp[jj] : v[jj];
+                cp[jj] = o;
+                vmax = fmaxf(vmax, fabsf(o));
+              }
             }
           }
         }
         __syncwarp();
       }
+    }
+    if (g.absmax_out) {
+      vmax = warp_max(vmax);
+      if (lane == 0 && vmax > 0.f) atomicMax(g.absmax_out, __float_as_uint(vmax));     // positive floats order like their bits
     }
   }
   tc_fence_before();
@@ -555,8 +566,17 @@ int split_global(const float* src, int ld, int R, int C, void* hi, void* lo, int
   return 0;
 }
 
+int absmax_accumulate(const float* src, int ld, size_t R, size_t C, unsigned* out, cudaStream_t stream) {
+  const int blocks = (int)min((size_t)num_sms() * 16, R);
+  KernelScope ks("absmax", stream);
+  absmax_kernel<<<blocks, 256, 0, stream>>>(src, ld, R, C, out);
+  NABU_CHECK_LAUNCH();
+  return 0;
+}
+
 int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A, const H2Operand& B, float beta, float* C,
-            int ldc, const float* bias, const GemmSeg* segp, float* workspace, size_t ws_bytes, cudaStream_t stream) {
+            int ldc, const float* bias, const GemmSeg* segp, float* workspace, size_t ws_bytes, cudaStream_t stream,
+            unsigned* absmax_out) {
   NABU_REQUIRE(!(segp && mode != GEMM_TN), "gemm_h2: row segmentation only in TN mode");
   NABU_REQUIRE(A.ld % 8 == 0 && B.ld % 8 == 0, "gemm_h2: operand leading dimensions must be multiples of 8");
   CUtensorMap mAh, mAl, mBh, mBl;
@@ -607,6 +627,7 @@ int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A,
   g.kb_per_split = ceil_div(g.kblocks, splits);
   splits = ceil_div(g.kblocks, g.kb_per_split);
   g.part = splits > 1 ? workspace : nullptr;
+  g.absmax_out = splits > 1 ? nullptr : absmax_out;       // split-K: the outputs only exist after the reduction (below)
   static bool attr_set = false;
   if (!attr_set) {
     NABU_CHECK_CUDA(cudaFuncSetAttribute(gemm_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H2_SMEM));
@@ -621,7 +642,10 @@ int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A,
     gemm_h2_kernel<<<grid, H2_THREADS, H2_SMEM, stream>>>(mAh, mAl, mBh, mBl, g);
     NABU_CHECK_LAUNCH();
   }
-  if (splits > 1) return splitk_reduce(workspace, splits, C, M, N, ldc, alpha, beta, bias, stream);
+  if (splits > 1) {
+    if (int e = splitk_reduce(workspace, splits, C, M, N, ldc, alpha, beta, bias, stream)) return e;
+    if (absmax_out) return absmax_accumulate(C, ldc, (size_t)M, (size_t)N, absmax_out, stream);
+  }
   return 0;
 }
 

@@ -215,12 +215,30 @@ def _blstm_fwd_raw(x, lens, kf, bf, kb, bb, H, yT, x_planes=None, want_planes=Fa
     return y, gates, cells, y_planes
 
 
+# max |dx| of the last BLSTM backward call, for the call whose dy IS that dx (nabu_blstm_bwd_hints): the tensor itself is
+# held (its memory cannot be handed to another tensor meanwhile) together with its version counter (any in-place
+# modification, autograd's gradient accumulation included, bumps it; views share it).
+_DXMAX = {'dx': None, 'version': None, 'buf': None}
+
+
+def _dy_absmax_hint(dy):
+    dx, ver, buf = _DXMAX['dx'], _DXMAX['version'], _DXMAX['buf']
+    _DXMAX['dx'] = _DXMAX['version'] = _DXMAX['buf'] = None
+    if dx is None or not dy.is_contiguous():
+        return None
+    same = dy.data_ptr() == dx.data_ptr() and dy.numel() == dx.numel() and dy.dtype == dx.dtype and dy._version == ver
+    return buf if same else None
+
+
 def _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, need_dx, H, yT, gvars, x_planes=None, y_planes=None):
     lib = L.load()
     B, T, D = x.shape
     dkf, dbf, dkb, dbb = gvars
+    hint_in = _dy_absmax_hint(dy)
     dy = dy.contiguous()
     dx = torch.empty_like(x) if need_dx else None
+    hint_out = torch.empty(128, dtype=torch.int32, device=x.device) if need_dx else None
+    L.check(lib.nabu_blstm_bwd_hints(L.ptr(hint_out), L.ptr(hint_in)), 'nabu_blstm_bwd_hints')
     ws = L.WORKSPACE.get(lib.nabu_blstm_workspace_bytes(B, T, D, H), x.device)
     if x_planes is not None and D % 8:
         x_planes = None
@@ -230,7 +248,9 @@ def _blstm_bwd_raw(x, lens, kf, kb, y, gates, cells, dy, need_dx, H, yT, gvars, 
             'nabu_blstm_bwd_planes')
     if _OVERLAP['on']:
         # deferred weight gradients read these on the library's side stream until side_join()
-        _OVERLAP['keep'].append((x, y, gates, kf, kb, gvars, x_planes, y_planes))
+        _OVERLAP['keep'].append((x, y, gates, kf, kb, gvars, x_planes, y_planes, hint_in))
+    if need_dx:
+        _DXMAX['dx'], _DXMAX['version'], _DXMAX['buf'] = dx, dx._version, hint_out
     return dx
 
 
@@ -275,6 +295,7 @@ def set_overlap(on):
 
 
 def side_join():
+    _DXMAX['dx'] = _DXMAX['version'] = _DXMAX['buf'] = None
     if _OVERLAP['on']:
         L.check(L.load().nabu_side_join(L.stream()), 'nabu_side_join')
         _OVERLAP['keep'].clear()

@@ -52,6 +52,7 @@ SIGNATURES = {
     'nabu_blstm_fwd_planes': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, P, P, c_size_t, P]),
     'nabu_blstm_bwd_planes': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P,
                                       c_size_t, P]),
+    'nabu_blstm_bwd_hints': (c_int, [P, P]),
     'nabu_pyramid_lengths': (c_int, [P, c_int, c_int, P, P]),
     'nabu_linear_fwd': (c_int, [P, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
     'nabu_linear_bwd': (c_int, [P, c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),

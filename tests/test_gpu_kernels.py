@@ -402,6 +402,25 @@ def test_blstm_operand_planes_travel_between_layers(B, T, H, pyramid):
     assert rel_err(dx1.cpu().numpy(), dx1_ref) < TOL
     for k in g1_ref:
         assert rel_err(g1[k].cpu().numpy(), g1_ref[k]) < TOL, ('layer 1', k)
+    if H < 256:
+        return                                           # the fallback kernels overwrite the saved gates: no second pass
+    # nabu_blstm_bwd_hints: layer 2 leaves max |dx| behind (from the dX contraction's epilogue), layer 1 takes it instead
+    # of reading dy -- bit-identical results
+    hint = torch.full((128,), -1, dtype=torch.int32, device='cuda')
+    L.check(lib.nabu_blstm_bwd_hints(L.ptr(hint), None), 'hints')
+    dx2b, g2b = layer_bwd(s2, dev(dy2), True)
+    assert torch.equal(dx2b, dx2)
+    h = hint.cpu().numpy()
+    assert np.all(h[1:] == 0) and h[:1].view(np.float32)[0] == np.abs(dx2b.cpu().numpy()).max()
+    L.check(lib.nabu_blstm_bwd_hints(None, L.ptr(hint)), 'hints')
+    dx1b, g1b = layer_bwd(s1, dx2b.view(B, yT1, 2 * H), True)
+    torch.cuda.synchronize()
+    assert torch.equal(dx1b, dx1)
+    for k in g1:
+        assert torch.equal(g1b[k], g1[k]), ('layer 1 with the max |dy| hint', k)
+    # a hint is consumed by ONE call: the next call computes max |dy| itself again
+    dx1c, _ = layer_bwd(s1, dx2b.view(B, yT1, 2 * H), True)
+    assert torch.equal(dx1c, dx1)
 
 
 def test_out_of_range_labels_are_flagged_not_dereferenced():

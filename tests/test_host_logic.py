@@ -201,3 +201,27 @@ def test_padding_num_units_to_the_kernel_tile_changes_nothing():
     for k in g:
         got = engine._unpad_gates(torch.from_numpy(gp[k]), H, Hp, k.endswith('kernel')).numpy()
         assert np.allclose(got, g[k], rtol=0, atol=1e-15), k
+
+
+def test_dy_absmax_hint_only_for_the_unmodified_dx_tensor():
+    """engine._dy_absmax_hint (nabu_blstm_bwd_hints): the max |dx| a layer's backward left behind is handed to the next
+    backward call only if its dy IS that dx -- same memory, same version counter (views share it, in-place writes bump
+    it) -- and only once."""
+    import torch
+    from nabu_b200 import engine
+    dx = torch.zeros(4, 6, 8)
+    buf = torch.zeros(128, dtype=torch.int32)
+
+    def store():
+        engine._DXMAX['dx'], engine._DXMAX['version'], engine._DXMAX['buf'] = dx, dx._version, buf
+    store()
+    assert engine._dy_absmax_hint(dx.view(4, 3, 16)) is buf          # pyramid_stack's reshape: same memory
+    assert engine._dy_absmax_hint(dx) is None                        # consumed
+    store()
+    assert engine._dy_absmax_hint(dx.clone()) is None                # another tensor
+    store()
+    dx.add_(1.0)                                                     # e.g. autograd accumulating a second gradient in place
+    assert engine._dy_absmax_hint(dx) is None
+    store()
+    assert engine._dy_absmax_hint(dx[:, :3]) is None                 # part of it
+    assert engine._DXMAX['dx'] is None
