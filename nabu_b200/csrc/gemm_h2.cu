@@ -638,7 +638,10 @@ int gemm_h2(GemmMode mode, int M, int N, int K, float alpha, const H2Operand& A,
     g.tiles_n = ceil_div(N, H2_BN); g.tiles_m = ceil_div(M, H2_BM); g.splits = splits;
     const long total = (long)g.tiles_n * g.tiles_m * splits;
     NABU_REQUIRE(total < (1L << 31), "gemm_h2: too many tiles");
-    const int grid = (int)std::min<long>(total, num_sms());
+    // TN = the weight gradients, which run on a side stream beside a recurrence that holds 64 SMs: one item per CTA, so
+    // that the hardware scheduler balances them over whatever SMs are free (their few tiles with K ~ 1e5 have nothing to
+    // gain from persistence); NN / NT run alone and persist
+    const int grid = mode == GEMM_TN ? (int)total : (int)std::min<long>(total, num_sms());
     gemm_h2_kernel<<<grid, H2_THREADS, H2_SMEM, stream>>>(mAh, mAl, mBh, mBl, g);
     NABU_CHECK_LAUNCH();
   }
