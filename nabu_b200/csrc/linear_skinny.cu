@@ -6,7 +6,7 @@
 // (profiles/r2g_bench_default.json, kernel_time_shares): sgemm_nn 1.17 ms (forward, 0.67 TB/s), sgemm_tn 1.10 ms (dW).
 //
 //   linear_skinny_fwd_kernel   persistent, one CTA per SM.  W (zero-padded to 32 columns) stays in shared memory for the
-//                              CTA's lifetime; x goes through a double-buffered cp.async tile [64 rows x 128 k]; lane =
+//                              CTA's lifetime; x goes through a double-buffered cp.async tile [128 rows x 64 k]; lane =
 //                              output unit, every warp keeps 8 rows in registers, so one W load (conflict-free, 128 B per
 //                              warp) and 8 broadcast 16-byte x loads feed 32 FMAs per lane.  fp32 accumulation in k order.
 //   linear_skinny_dw_kernel    dW = x^T.dy: thread = one input unit k (a warp reads 128 contiguous bytes of an x row), 32
@@ -23,7 +23,7 @@
 namespace nabu {
 namespace {
 
-constexpr int LS_ROWS = 64, LS_KC = 128, LS_THREADS = 256, LS_RW = 8;   // forward tile: rows, k per chunk; rows per warp
+constexpr int LS_ROWS = 128, LS_KC = 64, LS_THREADS = 512, LS_RW = 8;   // forward tile: rows, k per chunk; rows per warp (16 warps: four per scheduler)
 
 __device__ __forceinline__ void ls_cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
@@ -46,7 +46,7 @@ linear_skinny_fwd_kernel(const float* __restrict__ x, int N, int D, int V, const
   const int ntiles = (N + LS_ROWS - 1) / LS_ROWS, nkc = D / LS_KC;
   const int mytiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   const int niter = mytiles * nkc;
-  // chunk `it` of this CTA: tile blockIdx.x + (it / nkc) * gridDim.x, k chunk it % nkc; 8 16-byte copies per thread
+  // chunk `it` of this CTA: tile blockIdx.x + (it / nkc) * gridDim.x, k chunk it % nkc; 4 16-byte copies per thread
   auto stage = [&](int it, int buf) {
     const int tile = blockIdx.x + (it / nkc) * gridDim.x, kc = it % nkc;
     float* dst = xs + (size_t)buf * LS_ROWS * LS_KC;
@@ -121,10 +121,18 @@ linear_skinny_dw_kernel(const float* __restrict__ x, int N, int D, int V, const 
     if (r0 + DW_TILE < row1) stage(r0 + DW_TILE, buf ^ 1);
     const int nr = min(DW_TILE, row1 - r0);
     const float* xp = x + (size_t)r0 * D + k;
+    // the x values of the next 8 rows are in flight while the current 8 are multiplied
+    float xn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xn[j] = (j < nr) ? __ldg(xp + (size_t)j * D) : 0.f;
     for (int rb = 0; rb < nr; rb += 8) {
       float xv[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] = (rb + j < nr) ? __ldg(xp + (size_t)(rb + j) * D) : 0.f;
+      for (int j = 0; j < 8; ++j) xv[j] = xn[j];
+      if (rb + 8 < nr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xn[j] = (rb + 8 + j < nr) ? __ldg(xp + (size_t)(rb + 8 + j) * D) : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
 #pragma unroll

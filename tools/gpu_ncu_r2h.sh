@@ -4,10 +4,17 @@
 # ncu cannot launch cooperative cluster kernels: NABU_REC_NOCOOP=1.
 mkdir -p gpurun_out
 export NABU_REC_NOCOOP=1
+if [ -z "$SKIP_LAUNCHES" ]; then
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 372 -c 130 --csv \
   --log-file gpurun_out/launches_r2h_ctc.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_launch.log 2>&1
 echo "launch list (cfg-3) exit $? lines $(wc -l < gpurun_out/launches_r2h_ctc.csv)"
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_h2_kernel|linear_skinny" -s 108 -c 22 -o gpurun_out/r2h_full_gemm -f \
+fi
+# per step 37 launches match (10 x-projections, output layer forward, dW + its reduction, 24 backward contractions): skip the
+# three warm-up steps and layer 0's two small x-projections.  The report stays on the box (> 64 MiB with sources): the
+# summary is made there.
+timeout -s KILL 900 ncu --set full --clock-control none -k regex:"gemm_h2_kernel|linear_skinny" -s 113 -c 16 -o /tmp/r2h_full_gemm -f \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full_gemm.log 2>&1
 echo "gemm full exit $?"
-ls -la gpurun_out/*.ncu-rep
+python tools/ncu_summary.py full /tmp/r2h_full_gemm.ncu-rep > gpurun_out/r2h_ncu_gemm_linear.md 2> gpurun_out/ncu_summary.err
+ncu -i /tmp/r2h_full_gemm.ncu-rep --page raw --csv > gpurun_out/r2h_ncu_gemm_linear_raw.csv 2>/dev/null
+ls -la /tmp/*.ncu-rep gpurun_out/r2h_ncu_gemm_linear*; head -30 gpurun_out/r2h_ncu_gemm_linear.md | cut -c1-400
