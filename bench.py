@@ -456,6 +456,13 @@ def rooflines(w, wkey, prof, steps, step_ms):
                              'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'mma_rate_tflops': 3 * ach,
                              'mma_frac': 3 * ach / tf_peak, 'traffic': None,
                              'peak_source': src + ' bf16 sustained (fp16 MMA runs at the same rate)'}
+            try:        # the committed ncu capture of the x-projection launches of this command (None when there is none)
+                e = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json'))).get(wkey, {}).get('gemm_h2_nn')
+                if e:
+                    roofline_gemm['traffic'] = e['dram_bytes_per_launch']
+                    roofline_gemm['ncu'] = {k: e[k] for k in ('launch', 'tensor_pipe_active_pct', 'sm_mhz_under_load', 'source')}
+            except Exception:
+                pass
     else:
         # LAS: the attention step (keys + values streamed once per decoder step)
         att = [k for k in prof if k.startswith('dec_attn_step') or k == 'dec_attn_fwd_persist']
