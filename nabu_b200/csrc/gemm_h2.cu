@@ -90,12 +90,15 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   // Persistent: CTA c works on items c, c + gridDim.x, ...; item = (split z, row tile, column tile), column tile fastest
   // (the CTAs that run at the same time share their A rows through L2).
   const int total = g.tiles_n * g.tiles_m * g.splits;
-  auto decode = [&](int item, int* m0, int* n0, int* kb_begin, int* nkb, int* z) {
+  struct Item { int m0, n0, kb_begin, nkb, z; };
+  auto decode = [&](int item) {
+    Item t;
     const int tn = item % g.tiles_n, tm = (item / g.tiles_n) % g.tiles_m;
-    *z = item / (g.tiles_n * g.tiles_m);
-    *m0 = tm * H2_BM; *n0 = tn * H2_BN;
-    *kb_begin = *z * g.kb_per_split;
-    *nkb = max(0, min(g.kblocks, *kb_begin + g.kb_per_split) - *kb_begin);
+    t.z = item / (g.tiles_n * g.tiles_m);
+    t.m0 = tm * H2_BM; t.n0 = tn * H2_BN;
+    t.kb_begin = t.z * g.kb_per_split;
+    t.nkb = max(0, min(g.kblocks, t.kb_begin + g.kb_per_split) - t.kb_begin);
+    return t;
   };
 
   if (threadIdx.x == 0) {
@@ -118,8 +121,8 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     if (lane == 0) {
       int it = 0;                                        // k blocks issued by this CTA so far (stage / phase counter)
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        int m0, n0, kb_begin, nkb, z;
-        decode(item, &m0, &n0, &kb_begin, &nkb, &z);
+        const Item ti = decode(item);
+        const int m0 = ti.m0, n0 = ti.n0, kb_begin = ti.kb_begin, nkb = ti.nkb;
         for (int i = 0; i < nkb; ++i, ++it) {
           const int kb = kb_begin + i;
           const int s = it % H2_STAGES;
@@ -163,8 +166,7 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const uint32_t a_lay = g.a_mn_major ? 2u : 4u, b_lay = g.b_mn_major ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
       int it = 0, j = 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
-        int m0, n0, kb_begin, nkb, z;
-        decode(item, &m0, &n0, &kb_begin, &nkb, &z);
+        const int nkb = decode(item).nkb;
         // the epilogue warps hold the previous tile's accumulators in registers: tensor memory may be overwritten
         mbar_wait(bar_drained, (uint32_t)(j & 1) ^ 1u);
         tc_fence_after();
@@ -210,8 +212,8 @@ gemm_h2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     float vmax = 0.f;                                     // max |value stored| by this thread (absmax_out)
     int j = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
-      int m0, n0, kb_begin, nkb, z;
-      decode(item, &m0, &n0, &kb_begin, &nkb, &z);
+      const Item ti = decode(item);
+      const int m0 = ti.m0, n0 = ti.n0, nkb = ti.nkb, z = ti.z;
       const int m = m0 + 32 * q + lane;
       float* Cout = split ? g.part + (size_t)z * g.M * g.N : g.C;
       const bool vec = ((reinterpret_cast<uintptr_t>(Cout) & 15) == 0) && (ldc % 4 == 0);
