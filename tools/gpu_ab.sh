@@ -1,5 +1,7 @@
 #!/bin/bash
-# same-box A/B: HEAD library (nabu_b200/csrc/build/lib_head.so) against the working tree's, then env variants of the latter
+# same-box A/B: a reference build of the library (nabu_b200/csrc/build/lib_head.so -- build the commit to compare against in a
+# git worktree and copy its libnabu_b200.so there; it must export every symbol lib.py binds) against the working tree's, then
+# env variants of the latter
 mkdir -p gpurun_out
 cp nabu_b200/libnabu_b200.so /tmp/cur.so
 run() {  # label, env...

@@ -1,4 +1,9 @@
-"""Per-chain view of a NABU_REC_TRACE dump of the chain recurrences (slot = chain * grid + CTA, cl_common.cuh CH_STAMP).
+"""Per-chain view of a NABU_REC_TRACE dump of the chain recurrences (slot = chain * grid + CTA).
+
+Needs a DIAGNOSTIC build in which thread 0 of EVERY chain stamps (a CH_STAMP macro next to CL_STAMP in cl_common.cuh with
+slot = chain * gridDim.x + blockIdx.x, TRACE_CTAS = 512); the committed kernels stamp chain 0 only, because the extra
+stamps cost 0.6 us per backward time step (profiles/r2h_recurrence_experiments.md).  Kept as the reader of such dumps.
+
 
 usage: python tools/trace_chains.py gpurun_out/trace.bwd8c.bin <grid CTAs> <chains>
 Shows, per chain, when each phase happens inside a step period (mean over CTAs and steps, relative to the earliest
